@@ -1,0 +1,126 @@
+"""Parity of the fused CUDA kNN (through the C ABI) against the CPU oracle: bit-exact indices.
+
+Reference call sites: tf_util.pairwise_distance/knn (Networks/dgcnn/utils/tf_util.py:638-671),
+SmoothConstraint Dmat/top_k (Util/SmoothConstraint.py:141-154).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import knn as ok
+
+pytestmark = pytest.mark.gpu
+
+
+def _cloud(rng, B, N, D, dup_frac=0.05, kind="uniform"):
+    if kind == "uniform":
+        x = rng.uniform(-1, 1, (B, N, D)).astype(np.float32)
+    elif kind == "relu":  # feature-like: non-negative, clustered
+        x = np.maximum(rng.standard_normal((B, N, D)), 0).astype(np.float32)
+    else:  # coarse grid -> massive exact ties
+        x = rng.integers(0, 4, (B, N, D)).astype(np.float32) * 0.25
+    ndup = int(N * dup_frac)
+    if ndup:
+        for b in range(B):
+            src = rng.integers(0, N, ndup)
+            dst = rng.integers(0, N, ndup)
+            x[b, dst] = x[b, src]
+    return x
+
+
+CASES = [
+    # B, N, D, k, flavour, kind
+    (2, 128, 3, 20, 0, "uniform"),
+    (3, 333, 3, 20, 0, "uniform"),      # ragged N (not a tile multiple)
+    (2, 1024, 3, 20, 0, "uniform"),
+    (2, 1024, 6, 10, 1, "uniform"),     # smooth flavour (clamped), k=10
+    (2, 1024, 64, 20, 0, "relu"),
+    (1, 777, 64, 20, 0, "relu"),
+    (1, 512, 128, 20, 0, "relu"),
+    (1, 600, 9, 40, 0, "uniform"),      # k > 32 -> two list slots
+    (2, 512, 3, 20, 0, "grid"),         # many exact ties -> lower index first
+    (2, 512, 6, 10, 1, "grid"),
+    (1, 64, 3, 64, 0, "uniform"),       # k == N
+    (1, 20, 3, 20, 0, "uniform"),       # N < tile, k == N
+    (4, 2048, 3, 20, 0, "uniform"),
+    (1, 4096, 64, 20, 0, "relu"),       # one full-size S3DIS cloud
+]
+
+
+@pytest.mark.parametrize("B,N,D,k,flavour,kind", CASES)
+def test_knn_fused_bit_exact(cuda, B, N, D, k, flavour, kind):
+    from weaksuppointcloudseg_b200 import ops
+
+    rng = np.random.default_rng(1234 + N + D)
+    x = _cloud(rng, B, N, D, kind=kind)
+    ref_idx, ref_d = ok.knn(x, k, flavour, return_dist=True)
+    xd = torch.from_numpy(x).to(cuda)
+    idx, dist = ops.knn_fused(xd, k, flavour, return_dist=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(idx.cpu().numpy(), ref_idx)
+    assert np.array_equal(dist.cpu().numpy(), ref_d)  # distances are bit-exact too
+
+
+def test_knn_channel_window(cuda):
+    """kNN on channels 6:9 of a 9-channel S3DIS cloud (DGCNN_S3DIS.py:32) without a copy."""
+    from weaksuppointcloudseg_b200 import ops
+
+    rng = np.random.default_rng(7)
+    x = rng.uniform(0, 1, (2, 700, 9)).astype(np.float32)
+    ref = ok.knn(x, 20, 0, coff=6, D=3)
+    got = ops.knn_fused(torch.from_numpy(x).to(cuda), 20, 0, coff=6, D=3)
+    assert np.array_equal(got.cpu().numpy(), ref)
+
+
+def test_self_is_rank0_and_zero(cuda):
+    """SURVEY §4 invariant 2: without duplicates each point is its own nearest neighbour at d == 0."""
+    from weaksuppointcloudseg_b200 import ops
+
+    rng = np.random.default_rng(3)
+    x = torch.from_numpy(rng.uniform(-1, 1, (2, 1000, 64)).astype(np.float32)).to(cuda)
+    idx, dist = ops.knn_fused(x, 20, return_dist=True)
+    assert torch.equal(idx[:, :, 0].cpu(), torch.arange(1000, dtype=torch.int32).expand(2, -1))
+    assert float(dist[:, :, 0].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("flavour", [0, 1])
+def test_unfused_pair_matches_oracle(cuda, flavour):
+    from weaksuppointcloudseg_b200 import ops
+
+    rng = np.random.default_rng(11)
+    x = _cloud(rng, 2, 300, 6)
+    adj_ref = ok.pairwise_distance(x, flavour)
+    adj = ops.pairwise_distance(torch.from_numpy(x).to(cuda), flavour)
+    assert np.array_equal(adj.cpu().numpy(), adj_ref)
+    idx, vals = ops.topk_rows(adj, 20, return_vals=True)
+    ridx, rvals = ok.topk_rows(adj_ref, 20, return_vals=True)
+    assert np.array_equal(idx.cpu().numpy(), ridx)
+    assert np.array_equal(vals.cpu().numpy(), rvals)
+    # fused == unfused
+    assert torch.equal(ops.knn_fused(torch.from_numpy(x).to(cuda), 20, flavour), idx)
+
+
+def test_full_size_properties(cuda):
+    """cfg-3-sized batch slice: sortedness + self-inclusion properties (size-independent checks)."""
+    from weaksuppointcloudseg_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.rand((8, 4096, 64), device=cuda, generator=g)
+    idx, dist = ops.knn_fused(x, 20, return_dist=True)
+    assert bool((dist[..., 1:] >= dist[..., :-1]).all())
+    assert bool((idx >= 0).all()) and bool((idx < 4096).all())
+    assert bool((idx[..., 0] == torch.arange(4096, device=cuda, dtype=torch.int32)).all())
+    # no duplicate neighbour within a row
+    s = torch.sort(idx, dim=-1).values
+    assert bool((s[..., 1:] != s[..., :-1]).all())
+
+
+def test_errors_are_loud(cuda):
+    from weaksuppointcloudseg_b200 import ops
+    from weaksuppointcloudseg_b200._lib import WspcError
+
+    x = torch.zeros((1, 16, 3), device=cuda)
+    with pytest.raises(WspcError):
+        ops.knn_fused(x, 20)  # k > N
+    with pytest.raises(WspcError):
+        ops.knn_fused(x.cpu(), 4)  # CPU tensor: no fallback

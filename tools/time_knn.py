@@ -1,0 +1,31 @@
+"""Dev tool: CUDA-event timing of the fused kNN kernel at benchmark shapes."""
+import sys, os, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from weaksuppointcloudseg_b200 import ops
+
+def bench(B, N, D, k, flavour, iters=5):
+    x = torch.rand((B, N, D), device="cuda")
+    for _ in range(2):
+        ops.knn_fused(x, k, flavour)
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
+    ev[0].record()
+    for i in range(iters):
+        ops.knn_fused(x, k, flavour)
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    ts = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(iters))
+    ms = ts[len(ts) // 2]
+    eq_bytes = B * (2 * N * N * 4 + N * D * 4 + N * k * 4)
+    flops = B * (2.0 * N * N * D)
+    print(json.dumps(dict(B=B, N=N, D=D, k=k, flavour=flavour, ms=round(ms, 3), equiv_GBs=round(eq_bytes / ms / 1e6, 1),
+                          fma_TFLOPs=round(flops / ms / 1e9, 2))))
+
+if __name__ == "__main__":
+    B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+    bench(B, 4096, 3, 20, 0)
+    bench(B, 4096, 6, 10, 1)
+    bench(B, 4096, 64, 20, 0)
+    bench(max(B // 8, 1), 8192, 64, 40, 0)
+    bench(B, 2048, 64, 20, 0)

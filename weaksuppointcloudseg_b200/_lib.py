@@ -1,0 +1,103 @@
+"""ctypes binding of libwspc.so (the C ABI declared in include/wspc.h).
+
+The shared library is built in-tree by ``__graft_entry__.build()`` /
+``make -C weaksuppointcloudseg_b200/csrc``.  There is no CPU or PyTorch
+fallback: if the library is missing, or the device is not sm_100, every
+operator raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int32, c_longlong, c_size_t, c_uint64, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libwspc.so")
+
+DIST_TFUTIL = 0
+DIST_SMOOTH = 1
+
+
+class WspcError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def _declare(lib):
+    P = c_void_p
+    lib.wspc_version.restype = c_int
+    lib.wspc_last_error.restype = c_char_p
+    lib.wspc_launch_count.restype = c_uint64
+    lib.wspc_knn_workspace_bytes.restype = c_size_t
+    lib.wspc_knn_workspace_bytes.argtypes = [c_int, c_int, c_int]
+    lib.wspc_knn_fused.restype = c_int
+    lib.wspc_knn_fused.argtypes = [P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, c_size_t, P]
+    lib.wspc_pairwise_distance.restype = c_int
+    lib.wspc_pairwise_distance.argtypes = [P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, c_size_t, P]
+    lib.wspc_topk_rows.restype = c_int
+    lib.wspc_topk_rows.argtypes = [P, c_longlong, c_int, c_int, P, P, P]
+    for name, spec in _EXTRA_DECLS.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = spec
+
+
+# filled by the other binding sections below (name -> (restype, argtypes))
+_EXTRA_DECLS: dict = {}
+
+
+def lib():
+    """Load (once) and return the ctypes handle; raise loudly if absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise WspcError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU/PyTorch fallback for the wspc hot path)")
+        h = ctypes.CDLL(LIB_PATH)
+        _declare(h)
+        _lib = h
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise WspcError(f"libwspc error {rc}: {lib().wspc_last_error().decode()}")
+
+
+def launch_count() -> int:
+    return int(lib().wspc_launch_count())
+
+
+def ptr(t) -> c_void_p:
+    return c_void_p(0 if t is None else t.data_ptr())
+
+
+def stream() -> c_void_p:
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*tensors) -> None:
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise WspcError("wspc operators take CUDA tensors only (no CPU fallback)")
+        if not t.is_contiguous():
+            raise WspcError("wspc operators take contiguous tensors")
+
+
+_ws = {}
+
+
+def workspace(nbytes: int, device, slot: str = "default") -> torch.Tensor:
+    """Grow-only per-(device, slot) scratch buffer; stream-ordered reuse."""
+    key = (torch.device(device).index, slot)
+    buf = _ws.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _ws[key] = buf
+    return buf

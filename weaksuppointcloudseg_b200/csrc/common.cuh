@@ -1,0 +1,100 @@
+// Shared device/host helpers for the wspc sm_100a kernels.
+// Everything here is internal; the public surface is include/wspc.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <stdarg.h>
+#include "../../include/wspc.h"
+
+namespace wspc {
+
+// ---- error plumbing (thread-local last-error string, never throws) ---------
+void set_error(const char* fmt, ...);
+int  cuda_fail(cudaError_t e, const char* what);
+int  check_arch();   // WSPC_OK iff the current device is sm_100
+
+#define WSPC_CUDA(call)                                                     \
+  do {                                                                      \
+    cudaError_t _e = (call);                                                \
+    if (_e != cudaSuccess) return ::wspc::cuda_fail(_e, #call);             \
+  } while (0)
+
+#define WSPC_LAUNCH_CHECK(name)                                             \
+  do {                                                                      \
+    cudaError_t _e = cudaGetLastError();                                    \
+    if (_e != cudaSuccess) return ::wspc::cuda_fail(_e, name);              \
+  } while (0)
+
+#define WSPC_REQUIRE(cond, ...)                                             \
+  do {                                                                      \
+    if (!(cond)) { ::wspc::set_error(__VA_ARGS__); return WSPC_ERR_INVALID; } \
+  } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
+
+constexpr int kNumSM = 148;   // B200: 2 dies x 74 SMs
+
+// ---- PTX wrappers: mbarrier + bulk async copy (TMA engine, 1-D) ------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) { }
+}
+// 1-D bulk copy global -> shared (UBLKCP), completion counted in bytes on `bar`.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+// generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05 operand reads)
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+}  // namespace wspc
