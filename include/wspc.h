@@ -75,6 +75,141 @@ int wspc_pairwise_distance(const float* x, int B, int N, int ldx, int coff, int 
 int wspc_topk_rows(const float* adj, long long rows, int ncols, int k, int32_t* idx, float* vals,
                    wspc_stream_t stream);
 
+/* ------------------------------------------------ 1x1-conv (shared MLP) --- */
+/* The reference's EdgeConv / per-point layers are tf_util.conv2d with a [1,1]
+ * kernel followed by batch_norm_for_conv2d(is_dist=True) and ReLU
+ * (Networks/dgcnn/utils/tf_util.py:115-173,502-535,577-592) applied to
+ * get_edge_feature's output (tf_util.py:674-706) or to the previous layer.
+ * Here a layer is one GEMM whose A operand is *synthesised on load* from what is
+ * already in HBM (so edge features and normalised activations never round-trip
+ * through memory) and whose epilogue folds the bias, the BN batch statistics,
+ * the ReLU mask of the backward pass or the gather's scatter-add gradient.     */
+
+/* A-operand loader modes */
+#define WSPC_OP_PLAIN 0     /* a[row, c]                                                            */
+#define WSPC_OP_BNRELU 1    /* relu(p[row,c]*sc[c] + sh[c]) (* dmask[row,c] * dscale)   tf_util.py:167-172,631-635 */
+#define WSPC_OP_EDGE 2      /* row=(point i, slot r): [x_i | x_idx[i,r] - x_i], C = 2*Cx            tf_util.py:696-705 */
+#define WSPC_OP_DY 3        /* c1[c]*p[row,c] + c2[c] + c3[c]*y[row,c]  (BN backward as an affine map; c1==NULL: p) */
+#define WSPC_OP_DY_SPARSE 4 /* as DY with G[row,c] = (amax[cloud,c]==row%npts) ? dg[cloud,c] : 0   (max_pool2d grad) */
+
+typedef struct wspc_operand {
+  const float* p;   /* PLAIN: matrix; BNRELU: pre-BN activation; EDGE: point features; DY: upstream gradient G */
+  long long ld;     /* leading dimension of p (floats) */
+  int C;            /* logical channels */
+  const float* sc;  /* BNRELU: gamma*rsqrt(var+eps) */
+  const float* sh;  /* BNRELU: beta - mean*sc */
+  const float* dmask; /* BNRELU: optional dropout mask (rows, C) of 0/1 floats, or NULL */
+  float dscale;     /* BNRELU: 1/keep_prob */
+  const int32_t* idx; /* EDGE: (points, k) neighbour ids, local to the cloud */
+  int k;            /* EDGE: neighbours per point */
+  int npts;         /* EDGE / DY_SPARSE: points per cloud */
+  const float* y;   /* DY*: pre-BN output of the layer being differentiated */
+  long long ldy;
+  const float* c1;  /* DY*: per-channel affine of the BN backward (wspc_bn_bwd_coeffs) */
+  const float* c2;
+  const float* c3;
+  const float* dg;  /* DY_SPARSE: (clouds, C) gradient w.r.t. the max-pooled feature, already ReLU-gated */
+  const int32_t* amax; /* DY_SPARSE: (clouds, C) first arg-max point */
+} wspc_operand_t;
+
+/* epilogue modes */
+#define WSPC_EPI_STORE 0          /* out = acc + bias (+ rowbias[cloud])                                     */
+#define WSPC_EPI_STORE_STATS 1    /* as STORE, and stats += per-column (sum, sum of squares)  -> tf.nn.moments */
+#define WSPC_EPI_RELUMASK_STATS 2 /* out = acc*[relu(yprev*scp+shp)>0](*dmask*dscale); stats += (sum, sum*yprev) */
+#define WSPC_EPI_ACCUM 3          /* out += acc                                                               */
+#define WSPC_EPI_EDGE_SCATTER 4   /* acc=[dE_c|dE_d]: dx[i]+=dE_c-dE_d, dx[idx]+=dE_d (Gather/Concat/Sub grads) */
+
+typedef struct wspc_epilogue {
+  float* out;
+  long long ldo;
+  const float* bias;     /* (N) or NULL */
+  const float* rowbias;  /* (clouds, ldrb) per-cloud additive row or NULL (folded tiled global feature) */
+  int rb_rows;           /* rows per cloud for rowbias */
+  long long ldrb;
+  double* stats;         /* (2, N) fp64 accumulators, caller zeroes them */
+  const float* yprev;    /* RELUMASK: pre-BN activation of the producing layer (rows, ldyp) */
+  long long ldyp;
+  const float* scp;
+  const float* shp;
+  const float* dmask;    /* RELUMASK: optional dropout mask of the producing layer's output */
+  float dscale;
+  float* dx;             /* EDGE_SCATTER: (points, lddx) gradient accumulator (atomics) */
+  long long lddx;
+  const int32_t* idx;
+  int k;
+  int npts;
+} wspc_epilogue_t;
+
+/* out(M,N) = A(M,K) * Bm(K,N) with A read through `a_mode` and the result written through
+ * `epi_mode`.  Bm is row-major (K,N) with leading dimension ldb, or, if b_transposed, stored
+ * as (N,K) row-major (i.e. the layer's own weight matrix used for the data gradient).
+ * Forward:  A = PLAIN/BNRELU/EDGE, Bm = W(Cin,Cout)           tf_util.py:160-165
+ * Backward: A = DY/DY_SPARSE,      Bm = W^T (b_transposed=1)   Conv2DBackpropInput [TF] */
+int wspc_conv1x1_rows(const wspc_operand_t* A, int a_mode, const float* Bm, long long ldb, int b_transposed,
+                      long long M, int N, int K, const wspc_epilogue_t* epi, int epi_mode,
+                      wspc_stream_t stream);
+
+/* dW(K1,K2) = sum_rows A(row,:)^T dY(row,:), db(K2) = sum_rows dY(row,:)   (Conv2DBackpropFilter,
+ * BiasAddGrad [TF]).  A through a_mode (PLAIN/BNRELU/EDGE), dY through g_mode (DY/DY_SPARSE).
+ * Deterministic: row slabs are reduced in a fixed order in fp64.  db may be NULL. */
+size_t wspc_conv1x1_wgrad_workspace_bytes(int K1, int K2);
+int wspc_conv1x1_wgrad(const wspc_operand_t* A, int a_mode, const wspc_operand_t* G, int g_mode, long long M,
+                       float* dW, float* db, void* workspace, size_t workspace_bytes, wspc_stream_t stream);
+
+/* ------------------------------------------------- batch norm + pooling --- */
+/* batch_norm_dist_template (tf_util.py:502-535).  stats = (2,C) fp64 (sum, sum of squares) produced by
+ * WSPC_EPI_STORE_STATS over `rows` rows.  training: mean/biased var from stats, pop <- pop*decay +
+ * batch*(1-decay) (:524-525); else the population statistics are used (:530).  Outputs the folded
+ * affine sc = gamma*rsqrt(var+eps), sh = beta - mean*sc consumed by WSPC_OP_BNRELU, and (optionally)
+ * mean / invstd for the backward pass. */
+int wspc_bn_finalize(const double* stats, int C, double rows, const float* gamma, const float* beta, float eps,
+                     float decay, int training, float* pop_mean, float* pop_var, float* sc, float* sh,
+                     float* save_mean, float* save_invstd, wspc_stream_t stream);
+/* BN backward folded into dy = c1*G + c2 + c3*y; stats = (2,C) fp64 (sum G, sum G*y).
+ * Also emits dgamma, dbeta. */
+int wspc_bn_bwd_coeffs(const double* stats, int C, double rows, const float* gamma, const float* mean,
+                       const float* invstd, float* c1, float* c2, float* c3, float* dgamma, float* dbeta,
+                       wspc_stream_t stream);
+/* out[p, c] = max_r relu(y[p,r,c]*sc[c]+sh[c])  == tf.reduce_max(relu(bn(.)), axis=-2)
+ * (DGCNN_S3DIS.py:46,62,78; transform_nets.py:27).  y (P,k,C) dense, out strided by ldo. */
+int wspc_maxk_bnrelu_fwd(const float* y, const float* sc, const float* sh, long long P, int k, int C, float* out,
+                         long long ldo, wspc_stream_t stream);
+/* gradient of the above w.r.t. the BN output, already ReLU-masked: G (P,k,C); equal split among ties
+ * [TF _MinOrMaxGrad]; stats (2,C) += (sum G, sum G*y). */
+int wspc_maxk_bnrelu_bwd(const float* y, const float* sc, const float* sh, const float* out, long long ldo,
+                         const float* dout, long long lddo, long long P, int k, int C, float* G, double* stats,
+                         wspc_stream_t stream);
+/* g[b,c] = max_n relu(bn(y[b,n,c])), amax = first arg-max  == tf_util.max_pool2d([N,1]) (tf_util.py:357-380) */
+int wspc_maxn_bnrelu_fwd(const float* y, const float* sc, const float* sh, int B, int N, int C, float* g,
+                         int32_t* amax, wspc_stream_t stream);
+/* dg = dgin*[g>0]; stats (2,C) = (sum, sum*y at the arg-max rows): the sparse gradient of max_pool2d */
+int wspc_maxn_bwd_gate(const float* g, const float* dgin, const int32_t* amax, const float* y, int B, int N, int C,
+                       float* dg, double* stats, wspc_stream_t stream);
+/* S[b,c] = sum_n dY[b,n,c], dY through a WSPC_OP_DY operand: gradient of the tiled global feature (tf.tile grad) */
+int wspc_cloud_colsum(const wspc_operand_t* G, int B, int N, float* S, wspc_stream_t stream);
+
+/* ----------------------------------------------------- head + weak losses --- */
+/* softmax + masked CE + Siamese + inexact (MIL) + manifold smoothness, values and dZ in one call.
+ * S3DIS_DGCNN_trainer.py:85-102,120-137 / ShapeNet_DGCNN_trainer.py:85-100,115-133;
+ * Util/SmoothConstraint.py:155-165 (the kNN graph comes from wspc_knn_fused with WSPC_DIST_SMOOTH).
+ *   Z (B,N,C) logits, Y (B,N,C) one-hot float, Mask (B,N); sm_idx/sm_dist (B,N,knn) or NULL
+ *   full=1: loss = seg + siamese + inexact + smooth (ramp-up gate open); full=0: seg only ("Plain")
+ *   P (B,N,C) softmax out; dZ (B,N,C) d loss / d Z (required if want_grad or full)
+ *   losses[5] = {seg, siamese, inexact, smooth, total}            C <= 64 */
+size_t wspc_head_losses_workspace_bytes(int B, int N, int C);
+int wspc_head_losses(const float* Z, const float* Y, const float* Mask, const int32_t* sm_idx, const float* sm_dist,
+                     int B, int N, int C, int knn, float gamma, float siam_w, int full, int want_grad, float* P,
+                     float* dZ, float* losses, void* workspace, size_t workspace_bytes, wspc_stream_t stream);
+
+/* ------------------------------------------------------------ optimiser --- */
+/* tf.train.AdamOptimizer update on flat fp32 buffers (eps not bias-corrected);
+ * lr_t = lr*sqrt(1-b2^t)/(1-b1^t) is computed by the caller; gscale multiplies g (1/world_size). */
+int wspc_adam_tf(float* p, const float* g, float* m, float* v, long long n, float lr_t, float b1, float b2,
+                 float eps, float gscale, wspc_stream_t stream);
+/* tf.nn.dropout keep-mask (0/1 floats) from a Philox-4x32-10 stream: keep iff floor(keep + U) == 1 */
+int wspc_dropout_mask(float* mask, long long n, float keep, uint64_t seed, uint64_t offset, wspc_stream_t stream);
+int wspc_zero(void* ptr, size_t bytes, wspc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

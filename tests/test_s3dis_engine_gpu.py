@@ -1,0 +1,144 @@
+"""S3DIS DGCNN: CUDA engine (through the C ABI) vs the CPU oracle on the same seeded inputs.
+
+Tolerance (the reference defines none): per tensor max|a-b| / max|b| <= 1e-3, fp32.
+kNN-2/3 consume computed features, so logits are compared with teacher forcing (the engine is fed the
+oracle's neighbour lists); kNN itself is checked bit-exactly stage-wise (engine features -> oracle kNN).
+Biases of BN'd convs have an analytically zero gradient (pure rounding noise) and are excluded
+(SURVEY §7.3-8).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import dgcnn as od
+from oracle import knn as oknn
+from weaksuppointcloudseg_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+@pytest.fixture(scope="module")
+def setup(cuda):
+    from weaksuppointcloudseg_b200.engine_s3dis import S3DISEngine
+
+    n_samples, N = 3, 384
+    X, Y, M, _ = syn.s3dis_batch(n_samples, N=N, n_labelled=12, seed=77)
+    B = 2 * n_samples
+    params = od.init_params(od.S3DIS_LAYERS, seed=5)
+    rng = np.random.default_rng(9)
+    for k in params:  # non-trivial BN affine so gamma/beta gradients are exercised
+        if k.endswith("gamma"):
+            params[k] = rng.uniform(0.5, 1.5, params[k].shape).astype(np.float32)
+        if k.endswith("beta"):
+            params[k] = rng.uniform(-0.2, 0.2, params[k].shape).astype(np.float32)
+    mask = np.floor(0.7 + rng.random((B, N, 256))).astype(np.float32)
+    # oracle
+    p = od.to_torch(params)
+    opt = od.AdamTF(p, od.trainable_names(p))
+    rec = {}
+    out = od.train_step_s3dis(p, opt, torch.from_numpy(X), torch.from_numpy(Y), torch.from_numpy(M), step=0,
+                              dropout_mask=torch.from_numpy(mask), rec=rec)
+    # engine, teacher-forced kNN 2/3
+    eng = S3DISEngine(params, B, N, device=cuda)
+    ov = {f"knn{i}": rec[f"knn{i}/idx"].to(torch.int32).to(cuda) for i in (2, 3)}
+    Xd, Yd, Md = (torch.from_numpy(a).to(cuda) for a in (X, Y, M))
+    losses = eng.train_step(Xd, Yd, Md, lr=1e-3, bn_decay=od.bn_decay(0, n_samples, 300000),
+                            dropout_mask=torch.from_numpy(mask).to(cuda), knn_override=ov)
+    torch.cuda.synchronize()
+    return dict(eng=eng, out=out, rec=rec, p=p, losses=losses.cpu().numpy(), X=X, params0=params)
+
+
+def test_knn1_and_smooth_graph_bit_exact(setup):
+    eng, rec, X = setup["eng"], setup["rec"], setup["X"]
+    assert np.array_equal(eng.idx[0].cpu().numpy(), rec["knn1/idx"].numpy().astype(np.int32))
+    idx, d = oknn.knn(X, 10, oknn.SMOOTH, coff=0, D=6, return_dist=True)
+    assert np.array_equal(eng.idxS.cpu().numpy(), idx)
+    assert np.array_equal(eng.dS.cpu().numpy(), d)
+
+
+def test_features_and_stagewise_knn(setup):
+    eng, rec = setup["eng"], setup["rec"]
+    B, N = eng.B, eng.N
+    cat = eng.cat.cpu().numpy().reshape(B, N, 192)
+    for i, name in enumerate(["net_1", "net_2", "net_3"]):
+        assert rel(cat[:, :, 64 * i:64 * (i + 1)], rec[name].detach().numpy()) <= TOL
+    # stage-wise kNN: the oracle's kNN on the ENGINE's features == the engine's own fused kNN on them
+    from weaksuppointcloudseg_b200 import ops
+    for i in range(2):
+        feats = np.ascontiguousarray(cat[:, :, 64 * i:64 * (i + 1)])
+        got = ops.knn_fused(torch.from_numpy(feats).to(eng.dev), 20).cpu().numpy()
+        assert np.array_equal(got, oknn.knn(feats, 20))
+
+
+def test_logits_probs_losses(setup):
+    eng, out = setup["eng"], setup["out"]
+    assert rel(eng.Z.cpu().numpy(), out["Z"].detach().numpy()) <= TOL
+    assert rel(eng.Zp.cpu().numpy(), out["Z_prob"].detach().numpy()) <= TOL
+    names = ["loss_seg", "loss_siamese", "loss_inexact", "loss_smooth", "loss"]
+    for v, n in zip(setup["losses"], names):
+        ref = float(out[n])
+        assert abs(v - ref) <= TOL * abs(ref), (n, v, ref)
+
+
+def test_gradients(setup):
+    eng, out = setup["eng"], setup["out"]
+    got = eng.vs.grads()
+    worst = {}
+    for name, g in out["grads"].items():
+        if name.endswith("/biases") and name != "seg/conv3/biases":
+            # analytically zero: both sides must be tiny relative to the weight gradient scale
+            assert np.abs(got[name]).max() <= 1e-4 * max(np.abs(got[name.replace("biases", "weights")]).max(), 1e-12)
+            continue
+        worst[name] = rel(got[name], g.numpy())
+    bad = {k: v for k, v in worst.items() if v > TOL}
+    assert not bad, bad
+
+
+def test_adam_and_pop_stats(setup):
+    eng, p = setup["eng"], setup["p"]
+    got = eng.vs.export()
+    for name in got:
+        ref = p[name].detach().numpy()
+        if name.endswith("/biases") and name != "seg/conv3/biases":
+            continue  # Adam normalises rounding-noise gradients to +-lr
+        if name.endswith("pop_mean") or name.endswith("pop_var"):
+            assert rel(got[name], ref) <= TOL, name
+        else:
+            # one Adam step moves every weight by <= lr = 1e-3; compare the *update*
+            d_ref = ref - setup["params0"][name]
+            d_got = got[name] - setup["params0"][name]
+            assert np.abs(d_got - d_ref).max() <= 0.05 * 1e-3 + TOL * np.abs(d_ref).max(), name
+
+
+def test_inference_mode_uses_population_stats(setup, cuda):
+    """is_training=False: BN uses pop stats (tf_util.py:529-530), dropout is the identity (:632-634)."""
+    eng, p = setup["eng"], setup["p"]
+    X = torch.from_numpy(setup["X"])
+    rec = {}
+    Zref = od.get_model_s3dis(p, X, False, rec=rec)
+    # engine weights differ slightly after its own Adam step -> load the oracle's
+    eng.vs.load({k: v.detach().numpy() for k, v in p.items()})
+    ov = {f"knn{i}": rec[f"knn{i}/idx"].to(torch.int32).to(cuda) for i in (2, 3)}
+    Z = eng.forward(X.to(cuda), False, knn_override=ov)
+    assert rel(Z.cpu().numpy(), Zref.detach().numpy()) <= TOL
+
+
+def test_siamese_zero_for_identical_pairs(setup, cuda):
+    """SURVEY §4 invariant 3: identical pair members, no dropout -> loss_siamese == 0."""
+    eng = setup["eng"]
+    X = torch.from_numpy(setup["X"]).to(cuda).clone()
+    X[1::2] = X[0::2]
+    eng.forward(X, False)
+    B, N = eng.B, eng.N
+    Y = torch.zeros((B, N, 13), device=cuda)
+    Y[..., 0] = 1
+    M = torch.ones((B, N), device=cuda)
+    l = eng.losses_and_grad(Y, M, full=True, want_grad=True).cpu().numpy()
+    assert l[1] == 0.0
+    assert l[3] >= 0.0

@@ -101,3 +101,55 @@ def workspace(nbytes: int, device, slot: str = "default") -> torch.Tensor:
         buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
         _ws[key] = buf
     return buf
+
+
+# ---------------------------------------------------------------------------------------------
+# struct mirrors of include/wspc.h
+# ---------------------------------------------------------------------------------------------
+c_double = ctypes.c_double
+_P = c_void_p
+
+
+class Operand(ctypes.Structure):
+    """wspc_operand_t"""
+    _fields_ = [("p", _P), ("ld", c_longlong), ("C", c_int), ("sc", _P), ("sh", _P), ("dmask", _P),
+                ("dscale", c_float), ("idx", _P), ("k", c_int), ("npts", c_int), ("y", _P), ("ldy", c_longlong),
+                ("c1", _P), ("c2", _P), ("c3", _P), ("dg", _P), ("amax", _P)]
+
+
+class Epilogue(ctypes.Structure):
+    """wspc_epilogue_t"""
+    _fields_ = [("out", _P), ("ldo", c_longlong), ("bias", _P), ("rowbias", _P), ("rb_rows", c_int),
+                ("ldrb", c_longlong), ("stats", _P), ("yprev", _P), ("ldyp", c_longlong), ("scp", _P), ("shp", _P),
+                ("dmask", _P), ("dscale", c_float), ("dx", _P), ("lddx", c_longlong), ("idx", _P), ("k", c_int),
+                ("npts", c_int)]
+
+
+OP_PLAIN, OP_BNRELU, OP_EDGE, OP_DY, OP_DY_SPARSE = range(5)
+EPI_STORE, EPI_STORE_STATS, EPI_RELUMASK_STATS, EPI_ACCUM, EPI_EDGE_SCATTER = range(5)
+
+_OPP = ctypes.POINTER(Operand)
+_EPP = ctypes.POINTER(Epilogue)
+_EXTRA_DECLS.update({
+    "wspc_conv1x1_rows": (c_int, [_OPP, c_int, _P, c_longlong, c_int, c_longlong, c_int, c_int, _EPP, c_int, _P]),
+    "wspc_conv1x1_wgrad_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "wspc_conv1x1_wgrad": (c_int, [_OPP, c_int, _OPP, c_int, c_longlong, _P, _P, _P, c_size_t, _P]),
+    "wspc_bn_finalize": (c_int, [_P, c_int, c_double, _P, _P, c_float, c_float, c_int, _P, _P, _P, _P, _P, _P, _P]),
+    "wspc_bn_bwd_coeffs": (c_int, [_P, c_int, c_double, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "wspc_maxk_bnrelu_fwd": (c_int, [_P, _P, _P, c_longlong, c_int, c_int, _P, c_longlong, _P]),
+    "wspc_maxk_bnrelu_bwd": (c_int, [_P, _P, _P, _P, c_longlong, _P, c_longlong, c_longlong, c_int, c_int, _P, _P, _P]),
+    "wspc_maxn_bnrelu_fwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P, _P]),
+    "wspc_maxn_bwd_gate": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P]),
+    "wspc_cloud_colsum": (c_int, [_OPP, c_int, c_int, _P, _P]),
+    "wspc_head_losses_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "wspc_head_losses": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_int, _P, _P,
+                                 _P, _P, c_size_t, _P]),
+    "wspc_adam_tf": (c_int, [_P, _P, _P, _P, c_longlong, c_float, c_float, c_float, c_float, c_float, _P]),
+    "wspc_dropout_mask": (c_int, [_P, c_longlong, c_float, c_uint64, c_uint64, _P]),
+    "wspc_zero": (c_int, [_P, c_size_t, _P]),
+})
+
+
+def dptr(t) -> int:
+    """raw device address (0 for None) for struct fields"""
+    return 0 if t is None else t.data_ptr()

@@ -1,0 +1,285 @@
+// Batch-norm bookkeeping, max-over-k / max-over-N pooling (forward + backward) and small reductions.
+//
+// Reference semantics:
+//   batch_norm_dist_template           Networks/dgcnn/utils/tf_util.py:502-535 (biased var, eps 1e-3, pop update)
+//   tf.reduce_max(axis=-2)             S3DIS/DGCNN_S3DIS.py:46,62,78   (gradient split equally among ties [TF])
+//   tf_util.max_pool2d([N,1])          tf_util.py:357-380, DGCNN_S3DIS.py:85 (gradient to the first arg-max [TF])
+#include "operand.cuh"
+#include <math_constants.h>
+
+namespace wspc {
+void count_launch(int n = 1);
+namespace {
+
+// ------------------------------------------------------------ BN finalize ---
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, int C, double rows, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float decay, int training,
+                                   float* __restrict__ pop_mean, float* __restrict__ pop_var, float* __restrict__ sc,
+                                   float* __restrict__ sh, float* __restrict__ save_mean,
+                                   float* __restrict__ save_invstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float mean, var;
+  if (training) {
+    const double m = stats[c] / rows;
+    double v = stats[C + c] / rows - m * m;   // biased variance (tf.nn.moments)
+    if (v < 0.0) v = 0.0;
+    mean = (float)m;
+    var = (float)v;
+    pop_mean[c] = pop_mean[c] * decay + mean * (1.f - decay);   // tf_util.py:524
+    pop_var[c] = pop_var[c] * decay + var * (1.f - decay);      // tf_util.py:525
+  } else {
+    mean = pop_mean[c];
+    var = pop_var[c];
+  }
+  const float invstd = rsqrtf(var + eps);
+  const float s = invstd * gamma[c];
+  sc[c] = s;
+  sh[c] = beta[c] - mean * s;
+  if (save_mean) save_mean[c] = mean;
+  if (save_invstd) save_invstd[c] = invstd;
+}
+
+// stats = (sum G, sum G*y) over the rows the layer normalised over.
+__global__ void bn_bwd_coeffs_kernel(const double* __restrict__ stats, int C, double rows,
+                                     const float* __restrict__ gamma, const float* __restrict__ mean,
+                                     const float* __restrict__ invstd, float* __restrict__ c1, float* __restrict__ c2,
+                                     float* __restrict__ c3, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double s = invstd[c], mu = mean[c], g = gamma[c];
+  const double dB = stats[c];
+  const double dG = s * (stats[C + c] - mu * dB);
+  const double k1 = g * s;
+  const double k3 = -g * s * s * dG / rows;
+  const double k2 = -g * s * dB / rows - k3 * mu;
+  c1[c] = (float)k1;
+  c2[c] = (float)k2;
+  c3[c] = (float)k3;
+  dgamma[c] = (float)dG;
+  dbeta[c] = (float)dB;
+}
+
+// ------------------------------------------------------------- max over k ---
+// one thread per (point, channel): channels fastest => coalesced rows of C floats
+__global__ void maxk_fwd_kernel(const float* __restrict__ y, const float* __restrict__ sc, const float* __restrict__ sh,
+                                long long P, int k, int C, float* __restrict__ out, long long ldo) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= P * C) return;
+  const long long p = t / C;
+  const int c = (int)(t - p * C);
+  const float s = sc[c], h = sh[c];
+  const float* yp = y + p * k * C + c;
+  float m = 0.f;  // relu output is >= 0
+  for (int r = 0; r < k; ++r) m = fmaxf(m, fmaf(yp[(size_t)r * C], s, h));
+  out[p * ldo + c] = m;
+}
+
+__global__ void maxk_bwd_kernel(const float* __restrict__ y, const float* __restrict__ sc, const float* __restrict__ sh,
+                                const float* __restrict__ out, long long ldo, const float* __restrict__ dout,
+                                long long lddo, long long P, int k, int C, float* __restrict__ G,
+                                double* __restrict__ stats) {
+  __shared__ float red[2][128];
+  const int tid = threadIdx.x;
+  // block covers (blockDim.x / C) points x C channels (C divides 256, C <= 128)
+  const long long t = (long long)blockIdx.x * blockDim.x + tid;
+  const bool valid = t < P * C;
+  const long long p = valid ? t / C : 0;
+  const int c = valid ? (int)(t - p * C) : 0;
+  (&red[0][0])[tid] = 0.f;  // blockDim.x == 256 == 2*128
+  __syncthreads();
+  float s0 = 0.f, s1 = 0.f;
+  if (valid) {
+    const float s = sc[c], h = sh[c];
+    const float m = out[p * ldo + c];
+    const float go = dout[p * lddo + c];
+    const float* yp = y + p * k * C + c;
+    float* gp = G + p * k * C + c;
+    int cnt = 0;
+    if (m > 0.f) {
+      for (int r = 0; r < k; ++r) cnt += (fmaxf(fmaf(yp[(size_t)r * C], s, h), 0.f) == m) ? 1 : 0;
+    }
+    const float share = (cnt > 0) ? go / (float)cnt : 0.f;
+    for (int r = 0; r < k; ++r) {
+      const float yv = yp[(size_t)r * C];
+      const bool hit = (m > 0.f) && (fmaxf(fmaf(yv, s, h), 0.f) == m);
+      const float g = hit ? share : 0.f;
+      gp[(size_t)r * C] = g;
+      s0 += g;
+      s1 += g * yv;
+    }
+  }
+  // channels repeat with period C inside the block (blockDim % C == 0 guaranteed by the wrapper)
+  atomicAdd(&red[0][c], s0);
+  atomicAdd(&red[1][c], s1);
+  __syncthreads();
+  if (tid < C) {
+    atomicAdd(stats + tid, (double)red[0][tid]);
+    atomicAdd(stats + C + tid, (double)red[1][tid]);
+  }
+}
+
+// ------------------------------------------------------------- max over N ---
+// grid (C/32, B); block 32 x 8: lane = channel, 8 point groups
+__global__ void maxn_fwd_kernel(const float* __restrict__ y, const float* __restrict__ sc, const float* __restrict__ sh,
+                                int N, int C, float* __restrict__ g, int32_t* __restrict__ amax) {
+  __shared__ float sv[8][32];
+  __shared__ int si[8][32];
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int grp = threadIdx.y;
+  float best = -1.f;
+  int bi = 0x7fffffff;
+  if (c < C) {
+    const float s = sc[c], h = sh[c];
+    const float* yb = y + (size_t)b * N * C + c;
+    for (int n = grp; n < N; n += 8) {
+      const float a = fmaxf(fmaf(yb[(size_t)n * C], s, h), 0.f);
+      if (a > best) { best = a; bi = n; }   // strict > keeps the first index within this group
+    }
+  }
+  sv[grp][threadIdx.x] = best;
+  si[grp][threadIdx.x] = bi;
+  __syncthreads();
+  if (grp == 0 && c < C) {
+    for (int q = 1; q < 8; ++q) {
+      const float v = sv[q][threadIdx.x];
+      const int i = si[q][threadIdx.x];
+      if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+    }
+    g[(size_t)b * C + c] = best;
+    amax[(size_t)b * C + c] = bi;
+  }
+}
+
+// gate the incoming gradient by the ReLU (g > 0) and accumulate the BN-backward statistics of the sparse G
+__global__ void maxn_bwd_gate_kernel(const float* __restrict__ g, const float* __restrict__ dgin,
+                                     const int32_t* __restrict__ amax, const float* __restrict__ y, int B, int N, int C,
+                                     float* __restrict__ dg, double* __restrict__ stats) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s0 = 0.0, s1 = 0.0;
+  for (int b = 0; b < B; ++b) {
+    const size_t o = (size_t)b * C + c;
+    const float v = (g[o] > 0.f) ? dgin[o] : 0.f;
+    dg[o] = v;
+    s0 += v;
+    s1 += (double)v * (double)y[((size_t)b * N + amax[o]) * C + c];
+  }
+  stats[c] = s0;
+  stats[C + c] = s1;
+}
+
+// ------------------------------------------------------ per-cloud col sums --
+// S[b, c] = sum_n dY[b, n, c] with dY read through an OP_DY operand.  grid (C/32, B), block 32 x 8
+template <int GMODE>
+__global__ void cloud_colsum_kernel(const Operand G, int N, float* __restrict__ S) {
+  __shared__ float red[8][32];
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float s = 0.f;
+  if (c < G.C) {
+    for (int n = threadIdx.y; n < N; n += 8) {
+      const long long row = (long long)b * N + n;
+      const float g = G.p[row * G.ld + c];
+      s += G.c1 ? fmaf(G.c1[c], g, fmaf(G.c3[c], G.y[row * G.ldy + c], G.c2[c])) : g;
+    }
+  }
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < G.C) {
+    float t = 0.f;
+    for (int q = 0; q < 8; ++q) t += red[q][threadIdx.x];
+    S[(size_t)b * G.C + c] = t;
+  }
+}
+
+}  // namespace
+}  // namespace wspc
+
+using namespace wspc;
+
+extern "C" int wspc_bn_finalize(const double* stats, int C, double rows, const float* gamma, const float* beta,
+                                float eps, float decay, int training, float* pop_mean, float* pop_var, float* sc,
+                                float* sh, float* save_mean, float* save_invstd, wspc_stream_t stream) {
+  if (int rc = check_arch()) return rc;
+  WSPC_REQUIRE(gamma && beta && pop_mean && pop_var && sc && sh, "bn_finalize: null pointer");
+  WSPC_REQUIRE(!training || stats, "bn_finalize: training needs batch statistics");
+  WSPC_REQUIRE(C >= 1 && rows >= 1, "bn_finalize: bad shape");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      stats, C, rows, gamma, beta, eps, decay, training, pop_mean, pop_var, sc, sh, save_mean, save_invstd);
+  count_launch();
+  WSPC_LAUNCH_CHECK("bn_finalize_kernel");
+  return WSPC_OK;
+}
+
+extern "C" int wspc_bn_bwd_coeffs(const double* stats, int C, double rows, const float* gamma, const float* mean,
+                                  const float* invstd, float* c1, float* c2, float* c3, float* dgamma, float* dbeta,
+                                  wspc_stream_t stream) {
+  if (int rc = check_arch()) return rc;
+  WSPC_REQUIRE(stats && gamma && mean && invstd && c1 && c2 && c3 && dgamma && dbeta, "bn_bwd_coeffs: null pointer");
+  bn_bwd_coeffs_kernel<<<(C + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      stats, C, rows, gamma, mean, invstd, c1, c2, c3, dgamma, dbeta);
+  count_launch();
+  WSPC_LAUNCH_CHECK("bn_bwd_coeffs_kernel");
+  return WSPC_OK;
+}
+
+extern "C" int wspc_maxk_bnrelu_fwd(const float* y, const float* sc, const float* sh, long long P, int k, int C,
+                                    float* out, long long ldo, wspc_stream_t stream) {
+  if (int rc = check_arch()) return rc;
+  WSPC_REQUIRE(y && sc && sh && out, "maxk_fwd: null pointer");
+  WSPC_REQUIRE(P >= 1 && k >= 1 && C >= 1 && ldo >= C, "maxk_fwd: bad shape");
+  const long long total = P * C;
+  maxk_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(y, sc, sh, P, k,
+                                                                                                     C, out, ldo);
+  count_launch();
+  WSPC_LAUNCH_CHECK("maxk_fwd_kernel");
+  return WSPC_OK;
+}
+
+extern "C" int wspc_maxk_bnrelu_bwd(const float* y, const float* sc, const float* sh, const float* out, long long ldo,
+                                    const float* dout, long long lddo, long long P, int k, int C, float* G,
+                                    double* stats, wspc_stream_t stream) {
+  if (int rc = check_arch()) return rc;
+  WSPC_REQUIRE(y && sc && sh && out && dout && G && stats, "maxk_bwd: null pointer");
+  WSPC_REQUIRE(C >= 1 && C <= 128 && (256 % C) == 0, "maxk_bwd: C=%d must divide 256 and be <= 128", C);
+  const long long total = P * C;
+  maxk_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      y, sc, sh, out, ldo, dout, lddo, P, k, C, G, stats);
+  count_launch();
+  WSPC_LAUNCH_CHECK("maxk_bwd_kernel");
+  return WSPC_OK;
+}
+
+extern "C" int wspc_maxn_bnrelu_fwd(const float* y, const float* sc, const float* sh, int B, int N, int C, float* g,
+                                    int32_t* amax, wspc_stream_t stream) {
+  if (int rc = check_arch()) return rc;
+  WSPC_REQUIRE(y && sc && sh && g && amax, "maxn_fwd: null pointer");
+  dim3 grid((C + 31) / 32, B), block(32, 8);
+  maxn_fwd_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(y, sc, sh, N, C, g, amax);
+  count_launch();
+  WSPC_LAUNCH_CHECK("maxn_fwd_kernel");
+  return WSPC_OK;
+}
+
+extern "C" int wspc_maxn_bwd_gate(const float* g, const float* dgin, const int32_t* amax, const float* y, int B, int N,
+                                  int C, float* dg, double* stats, wspc_stream_t stream) {
+  if (int rc = check_arch()) return rc;
+  WSPC_REQUIRE(g && dgin && amax && y && dg && stats, "maxn_bwd_gate: null pointer");
+  maxn_bwd_gate_kernel<<<(C + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(g, dgin, amax, y, B, N, C,
+                                                                                           dg, stats);
+  count_launch();
+  WSPC_LAUNCH_CHECK("maxn_bwd_gate_kernel");
+  return WSPC_OK;
+}
+
+extern "C" int wspc_cloud_colsum(const wspc_operand_t* G, int B, int N, float* S, wspc_stream_t stream) {
+  if (int rc = check_arch()) return rc;
+  WSPC_REQUIRE(G && G->p && S, "cloud_colsum: null pointer");
+  dim3 grid((G->C + 31) / 32, B), block(32, 8);
+  cloud_colsum_kernel<OP_DY><<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*G, N, S);
+  count_launch();
+  WSPC_LAUNCH_CHECK("cloud_colsum_kernel");
+  return WSPC_OK;
+}

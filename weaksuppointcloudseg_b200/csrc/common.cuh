@@ -33,7 +33,7 @@ int  check_arch();   // WSPC_OK iff the current device is sm_100
   } while (0)
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
-static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
+__host__ __device__ static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
 
 constexpr int kNumSM = 148;   // B200: 2 dies x 74 SMs
 

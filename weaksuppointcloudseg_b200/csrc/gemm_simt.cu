@@ -1,0 +1,435 @@
+// fp32 CUDA-core GEMMs for the shared-MLP (1x1 conv) layers: generic in operand / epilogue mode.
+//
+// These kernels serve every layer shape of the two DGCNN variants (Cin 6..1280, Cout 13..1024),
+// the small per-cloud products and the weight gradients.  (The large 64-wide EdgeConv layers are
+// additionally served by the tcgen05 path in gemm_tc.cu.)
+//
+//   rowgemm : out(M,N) = A(M,K) * Bm(K,N)          forward and data-gradient
+//   colgemm : dW(K1,K2) = sum_rows A^T dY           weight-gradient, deterministic slab reduction
+#include "operand.cuh"
+
+namespace wspc {
+void count_launch(int n = 1);
+namespace {
+
+constexpr int BM = 128, BN = 64, BK = 16, ALD = BM + 4;
+constexpr int RG_THREADS = 256;
+
+template <int AMODE, int EMODE>
+__global__ void __launch_bounds__(RG_THREADS)
+rowgemm_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, int bT, long long M, int N, int K,
+               const Epilogue E) {
+  __shared__ __align__(16) float As[2][BK][ALD];
+  __shared__ __align__(16) float Bs[2][BK][BN];
+  __shared__ float red[2][BN];
+
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const long long row0 = (long long)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int nk = (K + BK - 1) / BK;
+
+  // loader mapping
+  const int a_lr = tid & 127, a_h = tid >> 7;        // A: row a_lr, channels kc + a_h*8 .. +8
+  const long long a_row = row0 + a_lr;
+  const bool a_valid = a_row < M;
+  const int b_kk = tid >> 4, b_nn = (tid & 15) * 4;  // B: row b_kk, cols b_nn..+3
+
+  float areg[8], breg[4];
+  auto gload = [&](int kc) {
+    if (a_valid) load8<AMODE>(A, a_row, kc * BK + a_h * 8, areg);
+    else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) areg[i] = 0.f;
+    }
+    const int kg = kc * BK + b_kk;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + b_nn + j;
+      float v = 0.f;
+      if (kg < K && n < N) v = bT ? Bm[(long long)n * ldb + kg] : Bm[(long long)kg * ldb + n];
+      breg[j] = v;
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) As[buf][a_h * 8 + i][a_lr] = areg[i];
+    *reinterpret_cast<float4*>(&Bs[buf][b_kk][b_nn]) = make_float4(breg[0], breg[1], breg[2], breg[3]);
+  };
+
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  for (int kc = 0; kc < nk; ++kc) {
+    const int cur = kc & 1;
+    if (kc + 1 < nk) gload(kc + 1);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[cur][kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[cur][kk][64 + ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[cur][kk][tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kc + 1 < nk) {
+      sstore(cur ^ 1);
+      __syncthreads();
+    }
+  }
+
+  // ------------------------------------------------------------ epilogue ---
+  const int col0 = n0 + tx * 4;
+  constexpr bool kStats = (EMODE == EPI_STORE_STATS || EMODE == EPI_RELUMASK_STATS);
+  float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+  if (kStats) {
+    if (tid < 2 * BN) (&red[0][0])[tid] = 0.f;
+    __syncthreads();
+  }
+
+  if (EMODE == EPI_EDGE_SCATTER) {
+    const int Cx = N >> 1;
+    long long cur_pt = -1;
+    float csum[4] = {0.f, 0.f, 0.f, 0.f};
+    auto flush = [&]() {
+      if (cur_pt >= 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int col = col0 + j;
+          if (col < N) atomicAdd(E.dx + cur_pt * E.lddx + (col < Cx ? col : col - Cx), csum[j]);
+        }
+      }
+    };
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const long long row = row0 + ((i < 4) ? (ty * 4 + i) : (64 + ty * 4 + i - 4));
+      if (row < M) {
+        const long long pt = row / E.k;
+        if (pt != cur_pt) {
+          flush();
+          cur_pt = pt;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) csum[j] = 0.f;
+        }
+        const long long nb = (pt / E.npts) * E.npts + E.idx[row];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int col = col0 + j;
+          if (col < Cx) csum[j] += acc[i][j];
+          else if (col < N) {
+            csum[j] -= acc[i][j];
+            atomicAdd(E.dx + nb * E.lddx + (col - Cx), acc[i][j]);
+          }
+        }
+      }
+    }
+    flush();
+  } else {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const long long row = row0 + ((i < 4) ? (ty * 4 + i) : (64 + ty * 4 + i - 4));
+    if (row >= M) continue;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = acc[i][j];
+    if (EMODE == EPI_STORE || EMODE == EPI_STORE_STATS) {
+      const float* rb = E.rowbias ? E.rowbias + (row / E.rb_rows) * E.ldrb : nullptr;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = col0 + j;
+        if (col < N) {
+          if (E.bias) v[j] += E.bias[col];
+          if (rb) v[j] += rb[col];
+        }
+      }
+    } else if (EMODE == EPI_RELUMASK_STATS) {
+      const float* yp = E.yprev + row * E.ldyp;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = col0 + j;
+        if (col < N) {
+          const float y = yp[col];
+          const bool on = fmaf(y, E.scp[col], E.shp[col]) > 0.f;
+          float g = on ? v[j] : 0.f;
+          if (E.dmask) g *= E.dmask[row * N + col] * E.dscale;
+          v[j] = g;
+          s0[j] += g;
+          s1[j] += g * y;
+        }
+      }
+    } else if (EMODE == EPI_ACCUM) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = col0 + j;
+        if (col < N) v[j] += E.out[row * E.ldo + col];
+      }
+    }
+    if (EMODE == EPI_STORE_STATS) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { s0[j] += v[j]; s1[j] += v[j] * v[j]; }
+    }
+    float* o = E.out + row * E.ldo + col0;
+    if (col0 + 3 < N && ((E.ldo & 3) == 0) && aligned16(E.out)) {
+      *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (col0 + j < N) o[j] = v[j];
+    }
+  }
+  }
+
+  if (kStats) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      atomicAdd(&red[0][tx * 4 + j], s0[j]);
+      atomicAdd(&red[1][tx * 4 + j], s1[j]);
+    }
+    __syncthreads();
+    if (tid < 2 * BN) {
+      const int which = tid / BN, c = tid % BN;
+      if (n0 + c < N) atomicAdd(E.stats + (size_t)which * N + n0 + c, (double)red[which][c]);
+    }
+  }
+}
+
+// ------------------------------------------------------------- colgemm -----
+constexpr int CT = 64;    // output tile (K1 x K2)
+constexpr int CR = 16;    // rows per smem chunk
+
+template <int AMODE, int GMODE>
+__global__ void __launch_bounds__(256)
+colgemm_kernel(const Operand A, const Operand G, long long M, long long rows_per_slab, int K1p, int K2p,
+               float* __restrict__ partial, float* __restrict__ partial_b) {
+  __shared__ __align__(16) float As[2][CR][CT];
+  __shared__ __align__(16) float Gs[2][CR][CT];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int k1_0 = blockIdx.x * CT, k2_0 = blockIdx.y * CT;
+  const long long r_begin = (long long)blockIdx.z * rows_per_slab;
+  const long long r_end = (r_begin + rows_per_slab < M) ? r_begin + rows_per_slab : M;
+
+  const bool isA = tid < 128;
+  const int lt = tid & 127;
+  const int l_r = lt >> 3, l_c = (lt & 7) * 8;
+  float reg[8];
+  auto gload = [&](long long rbase) {
+    const long long row = rbase + l_r;
+    if (row < r_end) {
+      if (isA) load8<AMODE>(A, row, k1_0 + l_c, reg);
+      else     load8<GMODE>(G, row, k2_0 + l_c, reg);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) reg[i] = 0.f;
+    }
+  };
+  auto sstore = [&](int buf) {
+    float* dst = isA ? &As[buf][l_r][l_c] : &Gs[buf][l_r][l_c];
+    *reinterpret_cast<float4*>(dst) = make_float4(reg[0], reg[1], reg[2], reg[3]);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(reg[4], reg[5], reg[6], reg[7]);
+  };
+
+  float acc[4][4];
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  if (r_begin < r_end) {
+    gload(r_begin);
+    sstore(0);
+    __syncthreads();
+    int cur = 0;
+    for (long long rb = r_begin; rb < r_end; rb += CR) {
+      const bool more = rb + CR < r_end;
+      if (more) gload(rb + CR);
+#pragma unroll
+      for (int r = 0; r < CR; ++r) {
+        const float4 a = *reinterpret_cast<const float4*>(&As[cur][r][ty * 4]);
+        const float4 g = *reinterpret_cast<const float4*>(&Gs[cur][r][tx * 4]);
+        const float av[4] = {a.x, a.y, a.z, a.w};
+        const float gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], gv[j], acc[i][j]);
+        if (ty == 0) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) bsum[j] += gv[j];
+        }
+      }
+      if (more) {
+        sstore(cur ^ 1);
+        __syncthreads();
+        cur ^= 1;
+      }
+    }
+  }
+  float* out = partial + (size_t)blockIdx.z * K1p * K2p;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int k1 = k1_0 + ty * 4 + i;
+    *reinterpret_cast<float4*>(out + (size_t)k1 * K2p + k2_0 + tx * 4) =
+        make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+  }
+  if (blockIdx.x == 0 && ty == 0) {
+    *reinterpret_cast<float4*>(partial_b + (size_t)blockIdx.z * K2p + k2_0 + tx * 4) =
+        make_float4(bsum[0], bsum[1], bsum[2], bsum[3]);
+  }
+}
+
+__global__ void slab_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ partial_b, int S,
+                                   int K1, int K2, int K1p, int K2p, float* __restrict__ dW,
+                                   float* __restrict__ db) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = K1 * K2;
+  if (i < total) {
+    const int k1 = i / K2, k2 = i % K2;
+    double s = 0.0;
+    for (int z = 0; z < S; ++z) s += (double)partial[((size_t)z * K1p + k1) * K2p + k2];
+    dW[i] = (float)s;
+  } else if (db && i < total + K2) {
+    const int k2 = i - total;
+    double s = 0.0;
+    for (int z = 0; z < S; ++z) s += (double)partial_b[(size_t)z * K2p + k2];
+    db[k2] = (float)s;
+  }
+}
+
+struct WgradPlan {
+  int K1p, K2p, t1, t2, S;
+  size_t partial_bytes, bias_bytes;
+};
+WgradPlan wgrad_plan(int K1, int K2) {
+  WgradPlan p;
+  p.t1 = (K1 + CT - 1) / CT;
+  p.t2 = (K2 + CT - 1) / CT;
+  p.K1p = p.t1 * CT;
+  p.K2p = p.t2 * CT;
+  const int tiles = p.t1 * p.t2;
+  p.S = (4 * kNumSM + tiles - 1) / tiles;  // ~4 CTAs per SM in flight
+  if (p.S < 1) p.S = 1;
+  p.partial_bytes = align_up((size_t)p.S * p.K1p * p.K2p * sizeof(float), 256);
+  p.bias_bytes = align_up((size_t)p.S * p.K2p * sizeof(float), 256);
+  return p;
+}
+
+template <int AMODE>
+int launch_rows_e(const Operand& A, const float* Bm, long long ldb, int bT, long long M, int N, int K,
+                  const Epilogue& E, int emode, cudaStream_t st) {
+  dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN));
+#define WSPC_RG(EM)                                                                          \
+  case EM:                                                                                   \
+    rowgemm_kernel<AMODE, EM><<<grid, RG_THREADS, 0, st>>>(A, Bm, ldb, bT, M, N, K, E);      \
+    break;
+  switch (emode) {
+    WSPC_RG(EPI_STORE)
+    WSPC_RG(EPI_STORE_STATS)
+    WSPC_RG(EPI_RELUMASK_STATS)
+    WSPC_RG(EPI_ACCUM)
+    WSPC_RG(EPI_EDGE_SCATTER)
+    default:
+      set_error("conv1x1_rows: bad epilogue mode %d", emode);
+      return WSPC_ERR_INVALID;
+  }
+#undef WSPC_RG
+  count_launch();
+  WSPC_LAUNCH_CHECK("rowgemm_kernel");
+  return WSPC_OK;
+}
+
+template <int AMODE>
+int launch_wgrad_g(const Operand& A, const Operand& G, int gmode, long long M, const WgradPlan& p, float* partial,
+                   float* partial_b, cudaStream_t st) {
+  long long rps = (M + p.S - 1) / p.S;
+  rps = (rps + CR - 1) / CR * CR;
+  dim3 grid(p.t1, p.t2, p.S);
+  if (gmode == OP_DY)
+    colgemm_kernel<AMODE, OP_DY><<<grid, 256, 0, st>>>(A, G, M, rps, p.K1p, p.K2p, partial, partial_b);
+  else if (gmode == OP_DY_SPARSE)
+    colgemm_kernel<AMODE, OP_DY_SPARSE><<<grid, 256, 0, st>>>(A, G, M, rps, p.K1p, p.K2p, partial, partial_b);
+  else {
+    set_error("conv1x1_wgrad: bad gradient operand mode %d", gmode);
+    return WSPC_ERR_INVALID;
+  }
+  count_launch();
+  WSPC_LAUNCH_CHECK("colgemm_kernel");
+  return WSPC_OK;
+}
+
+}  // namespace
+}  // namespace wspc
+
+using namespace wspc;
+
+extern "C" int wspc_conv1x1_rows(const wspc_operand_t* A, int a_mode, const float* Bm, long long ldb,
+                                 int b_transposed, long long M, int N, int K, const wspc_epilogue_t* epi,
+                                 int epi_mode, wspc_stream_t stream) {
+  if (int rc = check_arch()) return rc;
+  WSPC_REQUIRE(A && Bm && epi, "conv1x1_rows: null argument");
+  WSPC_REQUIRE(M >= 1 && N >= 1 && K >= 1, "conv1x1_rows: bad shape M=%lld N=%d K=%d", M, N, K);
+  WSPC_REQUIRE(A->p || a_mode == OP_DY_SPARSE, "conv1x1_rows: operand pointer is null");
+  WSPC_REQUIRE(A->C == K, "conv1x1_rows: operand channels %d != K %d", A->C, K);
+  if (epi_mode == EPI_EDGE_SCATTER) WSPC_REQUIRE(epi->dx && epi->idx && epi->k > 0 && epi->npts > 0 && (N % 2) == 0,
+                                                 "conv1x1_rows: incomplete scatter epilogue");
+  else WSPC_REQUIRE(epi->out, "conv1x1_rows: output pointer is null");
+  if (epi_mode == EPI_STORE_STATS || epi_mode == EPI_RELUMASK_STATS)
+    WSPC_REQUIRE(epi->stats, "conv1x1_rows: stats pointer is null");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (a_mode) {
+    case OP_PLAIN: return launch_rows_e<OP_PLAIN>(*A, Bm, ldb, b_transposed, M, N, K, *epi, epi_mode, st);
+    case OP_BNRELU: return launch_rows_e<OP_BNRELU>(*A, Bm, ldb, b_transposed, M, N, K, *epi, epi_mode, st);
+    case OP_EDGE: return launch_rows_e<OP_EDGE>(*A, Bm, ldb, b_transposed, M, N, K, *epi, epi_mode, st);
+    case OP_DY: return launch_rows_e<OP_DY>(*A, Bm, ldb, b_transposed, M, N, K, *epi, epi_mode, st);
+    case OP_DY_SPARSE: return launch_rows_e<OP_DY_SPARSE>(*A, Bm, ldb, b_transposed, M, N, K, *epi, epi_mode, st);
+  }
+  set_error("conv1x1_rows: bad operand mode %d", a_mode);
+  return WSPC_ERR_INVALID;
+}
+
+extern "C" size_t wspc_conv1x1_wgrad_workspace_bytes(int K1, int K2) {
+  if (K1 < 1 || K2 < 1) return 0;
+  const WgradPlan p = wgrad_plan(K1, K2);
+  return p.partial_bytes + p.bias_bytes;
+}
+
+extern "C" int wspc_conv1x1_wgrad(const wspc_operand_t* A, int a_mode, const wspc_operand_t* G, int g_mode,
+                                  long long M, float* dW, float* db, void* workspace, size_t workspace_bytes,
+                                  wspc_stream_t stream) {
+  if (int rc = check_arch()) return rc;
+  WSPC_REQUIRE(A && G && dW && workspace, "conv1x1_wgrad: null argument");
+  WSPC_REQUIRE(M >= 1 && A->C >= 1 && G->C >= 1, "conv1x1_wgrad: bad shape");
+  const WgradPlan p = wgrad_plan(A->C, G->C);
+  if (workspace_bytes < p.partial_bytes + p.bias_bytes) {
+    set_error("conv1x1_wgrad: workspace %zu < required %zu", workspace_bytes, p.partial_bytes + p.bias_bytes);
+    return WSPC_ERR_WORKSPACE;
+  }
+  float* partial = static_cast<float*>(workspace);
+  float* partial_b = reinterpret_cast<float*>(static_cast<char*>(workspace) + p.partial_bytes);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc;
+  switch (a_mode) {
+    case OP_PLAIN: rc = launch_wgrad_g<OP_PLAIN>(*A, *G, g_mode, M, p, partial, partial_b, st); break;
+    case OP_BNRELU: rc = launch_wgrad_g<OP_BNRELU>(*A, *G, g_mode, M, p, partial, partial_b, st); break;
+    case OP_EDGE: rc = launch_wgrad_g<OP_EDGE>(*A, *G, g_mode, M, p, partial, partial_b, st); break;
+    default:
+      set_error("conv1x1_wgrad: bad operand mode %d", a_mode);
+      return WSPC_ERR_INVALID;
+  }
+  if (rc) return rc;
+  const int total = A->C * G->C + (db ? G->C : 0);
+  slab_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(partial, partial_b, p.S, A->C, G->C, p.K1p, p.K2p, dW, db);
+  count_launch();
+  WSPC_LAUNCH_CHECK("slab_reduce_kernel");
+  return WSPC_OK;
+}

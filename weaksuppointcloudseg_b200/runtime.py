@@ -1,0 +1,216 @@
+"""Host-side runtime shared by the two DGCNN engines: the scope-keyed variable store (TF variable names,
+SURVEY §5 checkpoint row), per-layer scratch, and the layer-level launch helpers that translate
+"conv2d 1x1 -> BN -> ReLU" (reference tf_util.conv2d, Networks/dgcnn/utils/tf_util.py:115-173) into
+calls of the C ABI (include/wspc.h).  No arithmetic happens in Python/PyTorch here: torch only owns
+device memory and the stream.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+BN_EPS = 1e-3  # tf_util.py:527
+
+
+class VariableStore:
+    """All trainable variables live in ONE flat fp32 buffer (theta) with a same-shaped gradient buffer and
+    Adam slots, so the optimiser and the data-parallel all-reduce are one call each.  Population BN
+    statistics (non-trainable) live in a second flat buffer.  Views are keyed by TF variable names."""
+
+    def __init__(self, params: "OrderedDict[str, np.ndarray]", device):
+        self.device = device
+        tn = [k for k in params if not (k.endswith("pop_mean") or k.endswith("pop_var"))]
+        sn = [k for k in params if k not in tn]
+        self.trainable_names, self.state_names = tn, sn
+
+        def pack(names):
+            offs, n = {}, 0
+            for k in names:
+                offs[k] = (n, params[k].shape)
+                n += (int(np.prod(params[k].shape)) + 3) // 4 * 4   # keep every view 16-byte aligned
+            return offs, n
+
+        self._toffs, nt = pack(tn)
+        self._soffs, ns = pack(sn)
+        self.theta = torch.zeros(nt, dtype=torch.float32, device=device)
+        self.grad = torch.zeros(nt, dtype=torch.float32, device=device)
+        self.adam_m = torch.zeros(nt, dtype=torch.float32, device=device)
+        self.adam_v = torch.zeros(nt, dtype=torch.float32, device=device)
+        self.state = torch.zeros(max(ns, 4), dtype=torch.float32, device=device)
+        self.step = 0  # tf global_step (S3DIS_DGCNN_trainer.py:78)
+        self.load(params)
+
+    def _view(self, buf, offs, name):
+        o, shape = offs[name]
+        return buf[o:o + int(np.prod(shape))].view(*shape)
+
+    def p(self, name):
+        return self._view(self.theta, self._toffs, name)
+
+    def g(self, name):
+        return self._view(self.grad, self._toffs, name)
+
+    def s(self, name):
+        return self._view(self.state, self._soffs, name)
+
+    def get(self, name):
+        return self.p(name) if name in self._toffs else self.s(name)
+
+    def load(self, params):
+        for k in self.trainable_names:
+            self.p(k).copy_(torch.as_tensor(np.asarray(params[k]), dtype=torch.float32))
+        for k in self.state_names:
+            self.s(k).copy_(torch.as_tensor(np.asarray(params[k]), dtype=torch.float32))
+
+    def export(self) -> "OrderedDict[str, np.ndarray]":
+        out = OrderedDict()
+        for k in self.trainable_names:
+            out[k] = self.p(k).detach().cpu().numpy().copy()
+        for k in self.state_names:
+            out[k] = self.s(k).detach().cpu().numpy().copy()
+        return out
+
+    def grads(self) -> "OrderedDict[str, np.ndarray]":
+        return OrderedDict((k, self.g(k).detach().cpu().numpy().copy()) for k in self.trainable_names)
+
+    def num_trainable(self) -> int:
+        return sum(int(np.prod(s)) for _, s in self._toffs.values())
+
+    def adam_step(self, lr, b1=0.9, b2=0.999, eps=1e-8, gscale=1.0):
+        """tf.train.AdamOptimizer.apply_gradients [TF] on the flat buffers (one launch)."""
+        self.step += 1
+        t = self.step
+        lr_t = lr * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t)
+        L.check(L.lib().wspc_adam_tf(L.ptr(self.theta), L.ptr(self.grad), L.ptr(self.adam_m), L.ptr(self.adam_v),
+                                     self.theta.numel(), lr_t, b1, b2, eps, gscale, L.stream()))
+
+
+class Layer:
+    """One conv2d-1x1 (+BN) layer: views of its variables/gradients plus per-channel scratch."""
+
+    def __init__(self, vs: VariableStore, scope: str, cin: int, cout: int, has_bn: bool):
+        self.scope, self.cin, self.cout, self.has_bn = scope, cin, cout, has_bn
+        dev = vs.device
+        self.W, self.b = vs.p(f"{scope}/weights"), vs.p(f"{scope}/biases")
+        self.dW, self.db = vs.g(f"{scope}/weights"), vs.g(f"{scope}/biases")
+        if has_bn:
+            self.gamma, self.beta = vs.p(f"{scope}/bn/gamma"), vs.p(f"{scope}/bn/beta")
+            self.dgamma, self.dbeta = vs.g(f"{scope}/bn/gamma"), vs.g(f"{scope}/bn/beta")
+            self.pop_mean, self.pop_var = vs.s(f"{scope}/bn/pop_mean"), vs.s(f"{scope}/bn/pop_var")
+            f = lambda: torch.empty(cout, dtype=torch.float32, device=dev)  # noqa: E731
+            self.sc, self.sh, self.mean, self.invstd = f(), f(), f(), f()
+            self.c1, self.c2, self.c3 = f(), f(), f()
+            self.stats = torch.zeros((2, cout), dtype=torch.float64, device=dev)    # fwd: sum, sum^2
+            self.bstats = torch.zeros((2, cout), dtype=torch.float64, device=dev)   # bwd: sum G, sum G*y
+
+
+# ---- operand / epilogue builders ------------------------------------------------------------------
+def op_plain(t, ld, C):
+    return L.Operand(p=L.dptr(t), ld=ld, C=C), L.OP_PLAIN
+
+
+def op_bnrelu(y, layer: Layer, dmask=None, keep=1.0):
+    return (L.Operand(p=L.dptr(y), ld=layer.cout, C=layer.cout, sc=L.dptr(layer.sc), sh=L.dptr(layer.sh),
+                      dmask=L.dptr(dmask), dscale=1.0 / keep), L.OP_BNRELU)
+
+
+def op_edge(x, ld, cx, idx, k, npts):
+    return L.Operand(p=L.dptr(x), ld=ld, C=2 * cx, idx=L.dptr(idx), k=k, npts=npts), L.OP_EDGE
+
+
+def op_dy(G, ldg, y, ldy, layer: Layer | None, C):
+    """upstream gradient through the layer's BN backward (layer=None or no BN: identity)."""
+    if layer is not None and layer.has_bn:
+        return (L.Operand(p=L.dptr(G), ld=ldg, C=C, y=L.dptr(y), ldy=ldy, c1=L.dptr(layer.c1), c2=L.dptr(layer.c2),
+                          c3=L.dptr(layer.c3)), L.OP_DY)
+    return L.Operand(p=L.dptr(G), ld=ldg, C=C), L.OP_DY
+
+
+def op_dy_sparse(y, layer: Layer, dg, amax, npts):
+    return (L.Operand(p=0, ld=0, C=layer.cout, y=L.dptr(y), ldy=layer.cout, c1=L.dptr(layer.c1), c2=L.dptr(layer.c2),
+                      c3=L.dptr(layer.c3), dg=L.dptr(dg), amax=L.dptr(amax), npts=npts), L.OP_DY_SPARSE)
+
+
+def _addr(t, col_off=0):
+    return 0 if t is None else t.data_ptr() + 4 * col_off
+
+
+def rows_gemm(A, Bm, ldb, bT, M, N, K, epi: L.Epilogue, epi_mode):
+    a, amode = A
+    L.check(L.lib().wspc_conv1x1_rows(ctypes.byref(a), amode, L.ptr(Bm) if torch.is_tensor(Bm) else Bm, ldb, bT, M, N, K,
+                                      ctypes.byref(epi), epi_mode, L.stream()))
+
+
+def wgrad(A, G, M, dW, db, device):
+    a, amode = A
+    g, gmode = G
+    nbytes = L.lib().wspc_conv1x1_wgrad_workspace_bytes(a.C, g.C)
+    ws = L.workspace(nbytes, device, "wgrad")
+    L.check(L.lib().wspc_conv1x1_wgrad(ctypes.byref(a), amode, ctypes.byref(g), gmode, M,
+                                       dW if isinstance(dW, ctypes.c_void_p) else L.ptr(dW), L.ptr(db), L.ptr(ws),
+                                       ws.numel(), L.stream()))
+
+
+def zero_(t):
+    L.check(L.lib().wspc_zero(L.ptr(t), t.numel() * t.element_size(), L.stream()))
+
+
+def conv_forward(layer: Layer, A, M, y_out, ldo, training, decay, rowbias=None, rb_rows=1, Wview=None):
+    """y_out = A @ W + b (+ per-cloud row bias); accumulates BN batch statistics and folds them into
+    (sc, sh) for the consumer (tf_util.py:160-169, 521-530)."""
+    W = layer.W if Wview is None else Wview
+    K = A[0].C
+    epi = L.Epilogue(out=L.dptr(y_out), ldo=ldo, bias=L.dptr(layer.b), rowbias=L.dptr(rowbias), rb_rows=rb_rows,
+                     ldrb=layer.cout)
+    if layer.has_bn and training:
+        zero_(layer.stats)
+        epi.stats = L.dptr(layer.stats)
+        rows_gemm(A, W, layer.cout, 0, M, layer.cout, K, epi, L.EPI_STORE_STATS)
+    else:
+        rows_gemm(A, W, layer.cout, 0, M, layer.cout, K, epi, L.EPI_STORE)
+    if layer.has_bn:
+        bn_finalize(layer, M, training, decay)
+
+
+def bn_finalize(layer: Layer, rows, training, decay):
+    d = 0.9 if decay is None else decay   # tf_util.py:523
+    L.check(L.lib().wspc_bn_finalize(L.ptr(layer.stats), layer.cout, float(rows), L.ptr(layer.gamma), L.ptr(layer.beta),
+                                     BN_EPS, d, 1 if training else 0, L.ptr(layer.pop_mean), L.ptr(layer.pop_var),
+                                     L.ptr(layer.sc), L.ptr(layer.sh), L.ptr(layer.mean), L.ptr(layer.invstd),
+                                     L.stream()))
+
+
+def bn_bwd_coeffs(layer: Layer, rows):
+    L.check(L.lib().wspc_bn_bwd_coeffs(L.ptr(layer.bstats), layer.cout, float(rows), L.ptr(layer.gamma),
+                                       L.ptr(layer.mean), L.ptr(layer.invstd), L.ptr(layer.c1), L.ptr(layer.c2),
+                                       L.ptr(layer.c3), L.ptr(layer.dgamma), L.ptr(layer.dbeta), L.stream()))
+
+
+def epi_relumask(out, prev: Layer, yprev, dmask=None, keep=1.0):
+    """dA -> gradient w.r.t. the producing layer's BN output (ReLU mask, dropout) + its BN-backward sums."""
+    zero_(prev.bstats)
+    return (L.Epilogue(out=L.dptr(out), ldo=prev.cout, stats=L.dptr(prev.bstats), yprev=L.dptr(yprev), ldyp=prev.cout,
+                       scp=L.dptr(prev.sc), shp=L.dptr(prev.sh), dmask=L.dptr(dmask), dscale=1.0 / keep),
+            L.EPI_RELUMASK_STATS)
+
+
+def epi_scatter(dx_addr, lddx, idx, k, npts):
+    return L.Epilogue(dx=dx_addr, lddx=lddx, idx=L.dptr(idx), k=k, npts=npts), L.EPI_EDGE_SCATTER
+
+
+def maxk_fwd(layer: Layer, y, P, k, out_addr, ldo):
+    L.check(L.lib().wspc_maxk_bnrelu_fwd(L.ptr(y), L.ptr(layer.sc), L.ptr(layer.sh), P, k, layer.cout,
+                                         ctypes.c_void_p(out_addr), ldo, L.stream()))
+
+
+def maxk_bwd(layer: Layer, y, P, k, out_addr, ldo, dout_addr, lddo, G):
+    zero_(layer.bstats)
+    L.check(L.lib().wspc_maxk_bnrelu_bwd(L.ptr(y), L.ptr(layer.sc), L.ptr(layer.sh), ctypes.c_void_p(out_addr), ldo,
+                                         ctypes.c_void_p(dout_addr), lddo, P, k, layer.cout, L.ptr(G),
+                                         L.ptr(layer.bstats), L.stream()))
