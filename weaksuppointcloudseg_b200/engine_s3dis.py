@@ -61,6 +61,20 @@ class S3DISEngine:
         self.losses = torch.zeros(5, **f32)
         self.zero_bias = torch.zeros(512, **f32)
         self.seed = 1234
+        self.prof = None   # optional list of (tag, start_event, end_event) filled around the kNN launches
+
+    def _tick(self):
+        if self.prof is None:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def _tock(self, tag, t0):
+        if t0 is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.prof.append((tag, t0, e))
 
     # -------------------------------------------------------------------------------- forward ----
     def forward(self, X, is_training, bn_decay=None, dropout_mask=None, knn_override=None):
@@ -77,8 +91,10 @@ class S3DISEngine:
                 self.idx[i].copy_(ov[f"knn{i + 1}"])
                 return
             ws = L.workspace(L.lib().wspc_knn_workspace_bytes(B, N, D), self.dev, "knn")
+            t0 = self._tick()
             L.check(L.lib().wspc_knn_fused(ctypes.c_void_p(src), B, N, ld, coff, D, k, L.DIST_TFUTIL,
                                            L.ptr(self.idx[i]), None, L.ptr(ws), ws.numel(), L.stream()))
+            self._tock(f"knn_D{D}_k{k}", t0)
 
         # block 1: kNN on normalised xyz (ch 6:9), edge feature of all 9 channels      (:32-46)
         knn_into(0, X.data_ptr(), 9, self.knn_coff, 3)
@@ -131,8 +147,10 @@ class S3DISEngine:
                 self.dS.copy_(smooth_graph[1])
             else:   # SmoothConstraint.py:141-154 on X[:, :, 0:6]  (S3DIS_DGCNN_trainer.py:137)
                 ws = L.workspace(L.lib().wspc_knn_workspace_bytes(B, N, 6), self.dev, "knn")
+                t0 = self._tick()
                 L.check(L.lib().wspc_knn_fused(L.ptr(self.X), B, N, 9, 0, 6, SMOOTH_KNN, L.DIST_SMOOTH, L.ptr(self.idxS),
                                                L.ptr(self.dS), L.ptr(ws), ws.numel(), L.stream()))
+                self._tock(f"knn_D6_k{SMOOTH_KNN}", t0)
         nbytes = L.lib().wspc_head_losses_workspace_bytes(B, N, C)
         ws = L.workspace(nbytes, self.dev, "head")
         L.check(L.lib().wspc_head_losses(L.ptr(self.Z), L.ptr(Y), L.ptr(Mask), L.ptr(self.idxS) if full else None,
