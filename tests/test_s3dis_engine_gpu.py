@@ -97,12 +97,14 @@ def test_gradients(setup):
     eng, out = setup["eng"], setup["out"]
     got = eng.vs.grads()
     worst = {}
+    gmax = max(float(g.abs().max()) for g in out["grads"].values())
     for name, g in out["grads"].items():
-        if name.endswith("/biases") and name != "seg/conv3/biases":
-            # analytically zero: both sides must be tiny relative to the weight gradient scale
-            assert np.abs(got[name]).max() <= 1e-4 * max(np.abs(got[name.replace("biases", "weights")]).max(), 1e-12)
-            continue
         a, b = got[name].astype(np.float64), g.numpy().astype(np.float64)
+        if np.abs(b).max() < 1e-6 * gmax:
+            # analytically zero (biases of BN'd convs; adj_conv7's beta, whose per-channel shift of the tiled
+            # global feature is removed again by seg/conv1's BN): both sides are rounding noise
+            assert np.abs(a).max() < 1e-5 * gmax, name
+            continue
         worst[name] = (rel(a, b), np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
     bad = {k: v for k, v in worst.items() if v[0] > 2e-2 or v[1] > 5e-3}
     assert not bad, bad

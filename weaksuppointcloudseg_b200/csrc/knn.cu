@@ -23,7 +23,7 @@ constexpr int TM = 128;      // query rows per CTA
 constexpr int TN = 128;      // candidate columns per tile
 constexpr int DLD = TN + 4;  // distance-tile leading dimension (floats)
 constexpr int NSTAGE = 3;    // bulk-copy pipeline depth
-constexpr int KNN_THREADS = 256;
+constexpr int KNN_THREADS = 512;
 
 // ------------------------------------------------------------------ prep ---
 // x (B,N,ldx)[coff:coff+D] -> xT (B,Dp,Npad) zero padded, sq (B,Npad):
@@ -79,6 +79,47 @@ __device__ __forceinline__ void list_insert(float (&ld)[KSLOT], int (&li)[KSLOT]
   }
 }
 
+// Insert when the candidate's index is known to exceed every stored index (columns are visited in
+// strictly ascending order per row): (d', j') <lex (d, j)  <=>  d' <= d, so no index compare is needed.
+template <int KSLOT>
+__device__ __forceinline__ void list_insert_ordered(float (&ld)[KSLOT], int (&li)[KSLOT], float cd, int cj,
+                                                    int lane) {
+  if (KSLOT == 1) {
+    const int pos = __popc(__ballot_sync(0xffffffffu, ld[0] <= cd));
+    const float up_d = __shfl_up_sync(0xffffffffu, ld[0], 1);
+    const int up_i = __shfl_up_sync(0xffffffffu, li[0], 1);
+    const bool gt = lane > pos;
+    ld[0] = gt ? up_d : ld[0];
+    li[0] = gt ? up_i : li[0];
+    if (lane == pos) { ld[0] = cd; li[0] = cj; }
+  } else {
+    int pos = 0;
+#pragma unroll
+    for (int s = 0; s < KSLOT; ++s) pos += __popc(__ballot_sync(0xffffffffu, ld[s] <= cd));
+    float carry_d = 0.f;
+    int carry_i = 0;
+#pragma unroll
+    for (int s = 0; s < KSLOT; ++s) {
+      float up_d = __shfl_up_sync(0xffffffffu, ld[s], 1);
+      int up_i = __shfl_up_sync(0xffffffffu, li[s], 1);
+      const float last_d = __shfl_sync(0xffffffffu, ld[s], 31);
+      const int last_i = __shfl_sync(0xffffffffu, li[s], 31);
+      if (lane == 0) { up_d = carry_d; up_i = carry_i; }
+      const int e = s * 32 + lane;
+      if (e > pos) { ld[s] = up_d; li[s] = up_i; }
+      else if (e == pos) { ld[s] = cd; li[s] = cj; }
+      carry_d = last_d;
+      carry_i = last_i;
+    }
+  }
+}
+
+template <int KSLOT>
+__device__ __forceinline__ float list_tau_d(const float (&ld)[KSLOT], int k) {
+  const int e = k - 1;
+  return __shfl_sync(0xffffffffu, (KSLOT == 1 || e < 32) ? ld[0] : ld[KSLOT - 1], e & 31);
+}
+
 template <int KSLOT>
 __device__ __forceinline__ void list_tau(const float (&ld)[KSLOT], const int (&li)[KSLOT], int k,
                                          float& td, int& ti) {
@@ -104,6 +145,13 @@ __device__ __forceinline__ float dist_value(int flavour, float sqi, float sqj, f
 
 // ---------------------------------------------------------------- main ------
 // MODE 0: fused top-k (idx/dist out).  MODE 1: write the full adjacency.
+//
+// 512 threads = 16 warps.  GEMM phase: thread (tx = tid%32, ty = tid/32) owns rows {ty*4+i, 64+ty*4+i}
+// x cols {tx*4+j} (8x4 accumulators, one sequential fmaf chain each).  Selection phase: warp w owns
+// rows w*8..w*8+7; lane l looks at columns {l, l+32, l+64, l+96} of the distance tile.  For each
+// 32-column group the warp ballots "beats the current k-th" per row and inserts the survivors with
+// warp-shuffle insertion; four rows are inserted in lock-step (independent dependency chains, padded
+// with sentinel no-op inserts) so the shuffle/ballot latency of one row hides behind the others.
 template <int KC, int KSLOT, int MODE>
 __global__ void __launch_bounds__(KNN_THREADS, 1)
 knn_tile_kernel(const float* __restrict__ xT, const float* __restrict__ sq, int N, int Npad, int Dp,
@@ -118,8 +166,8 @@ knn_tile_kernel(const float* __restrict__ xT, const float* __restrict__ sq, int 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
-  const int tx = tid & 15;
-  const int ty = tid >> 4;
+  const int tx = lane;
+  const int ty = warp;
   const int b = blockIdx.y;
   const int i0 = blockIdx.x * TM;
   const float* xTb = xT + (size_t)b * Dp * Npad;
@@ -156,19 +204,22 @@ knn_tile_kernel(const float* __restrict__ xT, const float* __restrict__ sq, int 
     sqa[4] = s1.x; sqa[5] = s1.y; sqa[6] = s1.z; sqa[7] = s1.w;
   }
 
-  // sorted lists: this warp owns rows warp*16 .. warp*16+15
-  float ld[16][KSLOT];
-  int li[16][KSLOT];
+  // sorted lists: this warp owns rows warp*8 .. warp*8+7; taud/taui = current k-th entry (all lanes)
+  float ld[8][KSLOT];
+  int li[8][KSLOT];
+  float taud[8];
   if (MODE == 0) {
 #pragma unroll
-    for (int r = 0; r < 16; ++r)
+    for (int r = 0; r < 8; ++r) {
 #pragma unroll
       for (int s = 0; s < KSLOT; ++s) { ld[r][s] = CUDART_INF_F; li[r][s] = INT_MAX; }
+      taud[r] = CUDART_INF_F;
+    }
   }
 
   mbar_wait(&bars[NSTAGE], 0);
 
-  float acc[8][8];
+  float acc[8][4];
   for (int t = 0; t < total; ++t) {
     const int s = t % NSTAGE;
     const int jt = t / nchunk, c = t - jt * nchunk;
@@ -176,7 +227,7 @@ knn_tile_kernel(const float* __restrict__ xT, const float* __restrict__ sq, int 
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     }
     mbar_wait(&bars[s], (t / NSTAGE) & 1);
 
@@ -187,37 +238,37 @@ knn_tile_kernel(const float* __restrict__ xT, const float* __restrict__ sq, int 
       const float4 a0 = *reinterpret_cast<const float4*>(Ap + kk * TM + ty * 4);
       const float4 a1 = *reinterpret_cast<const float4*>(Ap + kk * TM + 64 + ty * 4);
       const float4 b0 = *reinterpret_cast<const float4*>(Bp + kk * TN + tx * 4);
-      const float4 b1 = *reinterpret_cast<const float4*>(Bp + kk * TN + 64 + tx * 4);
       const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      const float bv[4] = {b0.x, b0.y, b0.z, b0.w};
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = __fmaf_rn(av[i], bv[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) acc[i][j] = __fmaf_rn(av[i], bv[j], acc[i][j]);
     }
 
     const bool last = (c == nchunk - 1);
     const int col0 = jt * TN;
     if (last) {
       const float4 q0 = *reinterpret_cast<const float4*>(sqb + col0 + tx * 4);
-      const float4 q1 = *reinterpret_cast<const float4*>(sqb + col0 + 64 + tx * 4);
-      const float sqj[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+      const float sqj[4] = {q0.x, q0.y, q0.z, q0.w};
       if (MODE == 0) {
         __syncthreads();  // every warp has finished scanning the previous distance tile
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int row = (i < 4) ? (ty * 4 + i) : (64 + ty * 4 + i - 4);
-          float4 d0, d1;
+          float4 d0;
           d0.x = dist_value(flavour, sqa[i], sqj[0], acc[i][0]);
           d0.y = dist_value(flavour, sqa[i], sqj[1], acc[i][1]);
           d0.z = dist_value(flavour, sqa[i], sqj[2], acc[i][2]);
           d0.w = dist_value(flavour, sqa[i], sqj[3], acc[i][3]);
-          d1.x = dist_value(flavour, sqa[i], sqj[4], acc[i][4]);
-          d1.y = dist_value(flavour, sqa[i], sqj[5], acc[i][5]);
-          d1.z = dist_value(flavour, sqa[i], sqj[6], acc[i][6]);
-          d1.w = dist_value(flavour, sqa[i], sqj[7], acc[i][7]);
+          if (col0 + tx * 4 + 3 >= N) {   // ragged last tile: padded columns never pass the filter
+            const float qnan = __int_as_float(0x7fc00000);
+            if (col0 + tx * 4 + 0 >= N) d0.x = qnan;
+            if (col0 + tx * 4 + 1 >= N) d0.y = qnan;
+            if (col0 + tx * 4 + 2 >= N) d0.z = qnan;
+            d0.w = qnan;
+          }
           *reinterpret_cast<float4*>(Ds + row * DLD + tx * 4) = d0;
-          *reinterpret_cast<float4*>(Ds + row * DLD + 64 + tx * 4) = d1;
         }
       } else {
 #pragma unroll
@@ -226,8 +277,8 @@ knn_tile_kernel(const float* __restrict__ xT, const float* __restrict__ sq, int 
           if (row < N) {
             float* orow = adj_out + ((size_t)b * N + row) * N;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int col = col0 + ((j < 4) ? (tx * 4 + j) : (64 + tx * 4 + j - 4));
+            for (int j = 0; j < 4; ++j) {
+              const int col = col0 + tx * 4 + j;
               if (col < N) orow[col] = dist_value(flavour, sqa[i], sqj[j], acc[i][j]);
             }
           }
@@ -238,26 +289,33 @@ knn_tile_kernel(const float* __restrict__ xT, const float* __restrict__ sq, int 
     if (tid == 0 && t + NSTAGE < total) issue(t + NSTAGE);
 
     if (MODE == 0 && last) {
+      // this warp's 8 rows x 4 column groups (lane + 32*q): conflict-free LDS.32
+      float v[8][4];
 #pragma unroll
-      for (int r = 0; r < 16; ++r) {
-        const int row = warp * 16 + r;
-        const float4 v = *reinterpret_cast<const float4*>(Ds + row * DLD + lane * 4);
-        const float vv[4] = {v.x, v.y, v.z, v.w};
-        float td; int ti;
-        list_tau<KSLOT>(ld[r], li[r], k, td, ti);
+      for (int r = 0; r < 8; ++r) {
+        const float* drow = Ds + (warp * 8 + r) * DLD + lane;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int j = col0 + lane * 4 + q;
-          const bool pass = (j < N) && ((vv[q] < td) || (vv[q] == td && j < ti));
-          unsigned m = __ballot_sync(0xffffffffu, pass);
-          while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-            const float cd = __shfl_sync(0xffffffffu, vv[q], src);
-            const int cj = col0 + src * 4 + q;
-            list_insert<KSLOT>(ld[r], li[r], cd, cj, lane);
-          }
-          if (q < 3) list_tau<KSLOT>(ld[r], li[r], k, td, ti);
+        for (int q = 0; q < 4; ++q) v[r][q] = drow[32 * q];
+      }
+      // Columns are visited in strictly ascending order for every row (tiles, then 32-column groups,
+      // then lanes), so "beats the current k-th" is the strict test d < tau_d and ties keep the lower
+      // index by construction (tf.nn.top_k's rule).
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        unsigned m[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) m[r] = __ballot_sync(0xffffffffu, v[r][q] < taud[r]);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          if (m[r] == 0u) continue;      // warp-uniform
+          unsigned mm = m[r];
+          do {
+            const int src = __ffs(mm) - 1;
+            mm &= mm - 1u;
+            const float cd = __shfl_sync(0xffffffffu, v[r][q], src);
+            list_insert_ordered<KSLOT>(ld[r], li[r], cd, col0 + 32 * q + src, lane);
+          } while (mm);
+          taud[r] = list_tau_d<KSLOT>(ld[r], k);
         }
       }
     }
@@ -265,8 +323,8 @@ knn_tile_kernel(const float* __restrict__ xT, const float* __restrict__ sq, int 
 
   if (MODE == 0) {
 #pragma unroll
-    for (int r = 0; r < 16; ++r) {
-      const int row = i0 + warp * 16 + r;
+    for (int r = 0; r < 8; ++r) {
+      const int row = i0 + warp * 8 + r;
       if (row < N) {
 #pragma unroll
         for (int s = 0; s < KSLOT; ++s) {
