@@ -149,6 +149,11 @@ int wspc_conv1x1_rows(const wspc_operand_t* A, int a_mode, const float* Bm, long
                       long long M, int N, int K, const wspc_epilogue_t* epi, int epi_mode,
                       wspc_stream_t stream);
 
+/* Kernel selection for wspc_conv1x1_rows: 0 = auto (tcgen05 tensor-core kernel for eligible shapes, CUDA-core
+ * kernel otherwise), 1 = CUDA-core kernel only (used by the tests to A/B the two device paths).  Returns the
+ * previous setting.  Both paths are sm_100a CUDA; neither is a CPU fallback. */
+int wspc_set_gemm_path(int path);
+
 /* dW(K1,K2) = sum_rows A(row,:)^T dY(row,:), db(K2) = sum_rows dY(row,:)   (Conv2DBackpropFilter,
  * BiasAddGrad [TF]).  A through a_mode (PLAIN/BNRELU/EDGE), dY through g_mode (DY/DY_SPARSE).
  * Deterministic: row slabs are reduced in a fixed order in fp64.  db may be NULL. */

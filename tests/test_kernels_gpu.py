@@ -1,0 +1,215 @@
+"""Kernel-level parity: every MLP / pooling / loss kernel against fp64 torch formulas on identical inputs
+(no ReLU/arg-max discontinuity in play, so the bound is tight).  The GEMMs are checked on both device
+paths: tcgen05 (auto) and CUDA-core (wspc_set_gemm_path(1)).
+
+Reference semantics: tf_util.conv2d / batch_norm_dist_template / get_edge_feature
+(Networks/dgcnn/utils/tf_util.py:115-173,502-535,674-706) and SURVEY App. E for the gradients.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+@pytest.fixture(params=[0, 1], ids=["tcgen05", "cuda-core"])
+def gemm_path(request, cuda):
+    from weaksuppointcloudseg_b200 import _lib as L
+    old = L.lib().wspc_set_gemm_path(request.param)
+    yield request.param
+    L.lib().wspc_set_gemm_path(old)
+
+
+def _tol(path):
+    # bf16x3 split on tensor cores carries ~2^-16 relative error per product; fp32 FMA chains ~1e-6
+    return 2e-4 if path == 0 else 2e-5
+
+
+def test_fwd_bnrelu_store_stats(cuda, gemm_path):
+    from weaksuppointcloudseg_b200 import _lib as L, runtime as rt
+    g = torch.Generator(device="cuda").manual_seed(0)
+    M, K, N = 128 * 37 + 53, 64, 64
+    y = torch.randn((M, K), device=cuda, generator=g)
+    sc = torch.rand(K, device=cuda, generator=g) + 0.5
+    sh = torch.randn(K, device=cuda, generator=g) * 0.2
+    W = torch.randn((K, N), device=cuda, generator=g) * 0.2
+    b = torch.randn(N, device=cuda, generator=g)
+    out = torch.empty((M, N), device=cuda)
+    stats = torch.zeros((2, N), dtype=torch.float64, device=cuda)
+    A = (L.Operand(p=y.data_ptr(), ld=K, C=K, sc=sc.data_ptr(), sh=sh.data_ptr(), dscale=1.0), L.OP_BNRELU)
+    epi = L.Epilogue(out=out.data_ptr(), ldo=N, bias=b.data_ptr(), stats=stats.data_ptr())
+    rt.rows_gemm(A, W, N, 0, M, N, K, epi, L.EPI_STORE_STATS)
+    ref = torch.relu(y.double() * sc.double() + sh.double()) @ W.double() + b.double()
+    assert rel(out, ref) <= _tol(gemm_path)
+    assert rel(stats[0], out.double().sum(0)) <= 1e-6
+    assert rel(stats[1], (out.double() ** 2).sum(0)) <= 1e-6
+
+
+@pytest.mark.parametrize("Cx", [64, 16])
+def test_fwd_edge(cuda, gemm_path, Cx):
+    from weaksuppointcloudseg_b200 import _lib as L, runtime as rt
+    g = torch.Generator(device="cuda").manual_seed(1)
+    B, Np, k, N = 3, 200, 20, 64
+    x = torch.randn((B * Np, 192), device=cuda, generator=g)
+    idx = torch.randint(0, Np, (B, Np, k), device=cuda, generator=g, dtype=torch.int32)
+    W = torch.randn((2 * Cx, N), device=cuda, generator=g) * 0.1
+    b = torch.zeros(N, device=cuda)
+    R = B * Np * k
+    out = torch.empty((R, N), device=cuda)
+    stats = torch.zeros((2, N), dtype=torch.float64, device=cuda)
+    A = (L.Operand(p=x.data_ptr() + 4 * 64, ld=192, C=2 * Cx, idx=idx.data_ptr(), k=k, npts=Np), L.OP_EDGE)
+    epi = L.Epilogue(out=out.data_ptr(), ldo=N, bias=b.data_ptr(), stats=stats.data_ptr())
+    rt.rows_gemm(A, W, N, 0, R, N, 2 * Cx, epi, L.EPI_STORE_STATS)
+    xs = x[:, 64:64 + Cx].double().view(B, Np, Cx)
+    gidx = (idx.long() + torch.arange(B, device=cuda).view(B, 1, 1) * Np).reshape(-1)
+    nb = xs.reshape(B * Np, Cx)[gidx].view(B, Np, k, Cx)
+    ctr = xs.unsqueeze(2).expand(B, Np, k, Cx)
+    ref = (torch.cat([ctr, nb - ctr], -1) @ W.double()).reshape(R, N)
+    assert rel(out, ref) <= _tol(gemm_path)
+
+
+def test_bwd_dy_relumask_and_scatter(cuda, gemm_path):
+    from weaksuppointcloudseg_b200 import _lib as L, runtime as rt
+    g = torch.Generator(device="cuda").manual_seed(2)
+    B, Np, k = 2, 150, 20
+    R, C = B * Np * k, 64
+    G = torch.randn((R, C), device=cuda, generator=g)
+    y = torch.randn((R, C), device=cuda, generator=g)
+    c1, c2, c3 = (torch.randn(C, device=cuda, generator=g) * 0.5 for _ in range(3))
+    dy = c1.double() * G.double() + c2.double() + c3.double() * y.double()
+    A = (L.Operand(p=G.data_ptr(), ld=C, C=C, y=y.data_ptr(), ldy=C, c1=c1.data_ptr(), c2=c2.data_ptr(),
+                   c3=c3.data_ptr()), L.OP_DY)
+    # (a) previous layer is conv+BN+ReLU: masked gradient + BN-backward sums
+    W = torch.randn((64, C), device=cuda, generator=g) * 0.2          # layer weight (Cin=64, Cout=C)
+    yprev = torch.randn((R, 64), device=cuda, generator=g)
+    scp = torch.rand(64, device=cuda, generator=g) + 0.5
+    shp = torch.randn(64, device=cuda, generator=g) * 0.3
+    out = torch.empty((R, 64), device=cuda)
+    stats = torch.zeros((2, 64), dtype=torch.float64, device=cuda)
+    epi = L.Epilogue(out=out.data_ptr(), ldo=64, stats=stats.data_ptr(), yprev=yprev.data_ptr(), ldyp=64,
+                     scp=scp.data_ptr(), shp=shp.data_ptr(), dscale=1.0)
+    rt.rows_gemm(A, W, C, 1, R, 64, C, epi, L.EPI_RELUMASK_STATS)
+    on = torch.addcmul(shp, yprev, scp) > 0           # same fp32 expression class as the kernel's fmaf
+    ref = (dy @ W.double().T) * on
+    bad = (out.double() - ref).abs() > _tol(gemm_path) * ref.abs().max()
+    # elements whose activation is within rounding of 0 may legitimately flip the mask
+    near0 = (yprev.double() * scp.double() + shp.double()).abs() < 1e-6
+    assert int((bad & ~near0).sum()) == 0
+    assert rel(stats[0], out.double().sum(0)) <= 1e-6
+    assert rel(stats[1], (out.double() * yprev.double()).sum(0)) <= 1e-6
+    # (b) previous "layer" is the edge-feature gather: scatter-add gradient (tf_util.py:696-705 backward)
+    We = torch.randn((128, C), device=cuda, generator=g) * 0.2
+    idx = torch.randint(0, Np, (B, Np, k), device=cuda, generator=g, dtype=torch.int32)
+    dx = torch.zeros((B * Np, 192), device=cuda)
+    epi = L.Epilogue(dx=dx.data_ptr() + 4 * 64, lddx=192, idx=idx.data_ptr(), k=k, npts=Np)
+    rt.rows_gemm(A, We, C, 1, R, 128, C, epi, L.EPI_EDGE_SCATTER)
+    dE = (dy @ We.double().T).view(B, Np, k, 128)
+    ref_dx = torch.zeros((B * Np, 64), dtype=torch.float64, device=cuda)
+    ref_dx += (dE[..., :64] - dE[..., 64:]).sum(2).reshape(B * Np, 64)
+    gidx = (idx.long() + torch.arange(B, device=cuda).view(B, 1, 1) * Np).reshape(-1)
+    ref_dx.index_add_(0, gidx, dE[..., 64:].reshape(-1, 64))
+    assert rel(dx[:, 64:128], ref_dx) <= 5 * _tol(gemm_path)
+    assert float(dx[:, :64].abs().max()) == 0 and float(dx[:, 128:].abs().max()) == 0
+
+
+def test_wgrad_matches_fp64(cuda):
+    from weaksuppointcloudseg_b200 import _lib as L, runtime as rt
+    g = torch.Generator(device="cuda").manual_seed(3)
+    M, K1, K2 = 5000, 64, 64
+    a = torch.randn((M, K1), device=cuda, generator=g)
+    sc = torch.rand(K1, device=cuda, generator=g) + 0.5
+    sh = torch.randn(K1, device=cuda, generator=g) * 0.2
+    G = torch.randn((M, K2), device=cuda, generator=g)
+    y = torch.randn((M, K2), device=cuda, generator=g)
+    c1, c2, c3 = (torch.randn(K2, device=cuda, generator=g) * 0.5 for _ in range(3))
+    dW = torch.empty((K1, K2), device=cuda)
+    db = torch.empty(K2, device=cuda)
+    A = (L.Operand(p=a.data_ptr(), ld=K1, C=K1, sc=sc.data_ptr(), sh=sh.data_ptr(), dscale=1.0), L.OP_BNRELU)
+    Gop = (L.Operand(p=G.data_ptr(), ld=K2, C=K2, y=y.data_ptr(), ldy=K2, c1=c1.data_ptr(), c2=c2.data_ptr(),
+                     c3=c3.data_ptr()), L.OP_DY)
+    rt.wgrad(A, Gop, M, dW, db, cuda)
+    act = torch.relu(a.double() * sc.double() + sh.double())
+    dy = c1.double() * G.double() + c2.double() + c3.double() * y.double()
+    assert rel(dW, act.T @ dy) <= 2e-5
+    assert rel(db, dy.sum(0)) <= 2e-5
+
+
+def test_maxk_fwd_bwd(cuda):
+    from weaksuppointcloudseg_b200 import _lib as L
+    g = torch.Generator(device="cuda").manual_seed(4)
+    P, k, C = 700, 20, 64
+    y = torch.randn((P, k, C), device=cuda, generator=g)
+    y[:, 3] = y[:, 7]                                   # exact ties -> equal split of the gradient
+    sc = torch.rand(C, device=cuda, generator=g) + 0.5
+    sh = torch.randn(C, device=cuda, generator=g) * 0.5
+    out = torch.zeros((P, 192), device=cuda)
+    L.check(L.lib().wspc_maxk_bnrelu_fwd(L.ptr(y), L.ptr(sc), L.ptr(sh), P, k, C, ctypes.c_void_p(out.data_ptr() + 256),
+                                         192, L.stream()))
+    act = torch.relu(torch.addcmul(sh, y, sc))
+    ref = act.amax(1)
+    assert torch.equal(out[:, 64:128], ref)
+    dout = torch.randn((P, 192), device=cuda, generator=g)
+    G = torch.empty((P, k, C), device=cuda)
+    stats = torch.zeros((2, C), dtype=torch.float64, device=cuda)
+    L.check(L.lib().wspc_maxk_bnrelu_bwd(L.ptr(y), L.ptr(sc), L.ptr(sh), ctypes.c_void_p(out.data_ptr() + 256), 192,
+                                         ctypes.c_void_p(dout.data_ptr() + 256), 192, P, k, C, L.ptr(G), L.ptr(stats),
+                                         L.stream()))
+    hit = (act == ref.unsqueeze(1)) & (ref.unsqueeze(1) > 0)
+    cnt = hit.sum(1, keepdim=True).clamp_min(1)
+    Gref = hit * dout[:, 64:128].unsqueeze(1) / cnt
+    assert rel(G, Gref) <= 1e-6
+    assert rel(stats[0], G.double().sum((0, 1))) <= 1e-6
+    assert rel(stats[1], (G.double() * y.double()).sum((0, 1))) <= 1e-6
+
+
+def test_maxn_and_bn_kernels(cuda):
+    from weaksuppointcloudseg_b200 import _lib as L
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B, N, C = 3, 333, 96
+    y = torch.randn((B, N, C), device=cuda, generator=g)
+    y[:, 100] = y[:, 50]                                # ties -> first index wins (tf max_pool grad)
+    stats = torch.stack([y.double().sum((0, 1)), (y.double() ** 2).sum((0, 1))])
+    gamma = torch.rand(C, device=cuda, generator=g) + 0.5
+    beta = torch.randn(C, device=cuda, generator=g) * 0.1
+    pm, pv = torch.zeros(C, device=cuda), torch.ones(C, device=cuda)
+    sc, sh, mean, inv = (torch.empty(C, device=cuda) for _ in range(4))
+    L.check(L.lib().wspc_bn_finalize(L.ptr(stats), C, float(B * N), L.ptr(gamma), L.ptr(beta), 1e-3, 0.5, 1, L.ptr(pm),
+                                     L.ptr(pv), L.ptr(sc), L.ptr(sh), L.ptr(mean), L.ptr(inv), L.stream()))
+    m = y.double().mean((0, 1))
+    v = y.double().var((0, 1), unbiased=False)
+    assert rel(mean, m) <= 1e-6 and rel(sc, gamma.double() * torch.rsqrt(v + 1e-3)) <= 1e-6
+    assert rel(pm, 0.5 * m) <= 1e-6 and rel(pv, 0.5 + 0.5 * v) <= 1e-6
+    gmax = torch.empty((B, C), device=cuda)
+    amax = torch.empty((B, C), dtype=torch.int32, device=cuda)
+    L.check(L.lib().wspc_maxn_bnrelu_fwd(L.ptr(y), L.ptr(sc), L.ptr(sh), B, N, C, L.ptr(gmax), L.ptr(amax), L.stream()))
+    act = torch.relu(torch.addcmul(sh, y, sc))
+    assert torch.equal(gmax, act.amax(1))
+    first = (act == act.amax(1, keepdim=True)).to(torch.uint8).argmax(1)
+    assert torch.equal(amax.long(), first)
+
+
+def test_adam_tf_and_dropout_mask(cuda):
+    from weaksuppointcloudseg_b200 import _lib as L
+    g = torch.Generator(device="cuda").manual_seed(6)
+    n = 100003
+    p = torch.randn(n + 1, device=cuda, generator=g)[:n]
+    p = p.clone()
+    gr = torch.randn(n, device=cuda, generator=g)
+    m, v = torch.zeros(n, device=cuda), torch.zeros(n, device=cuda)
+    p0 = p.double().clone()
+    lr_t = 1e-3 * (1 - 0.999) ** 0.5 / (1 - 0.9)
+    L.check(L.lib().wspc_adam_tf(L.ptr(p), L.ptr(gr), L.ptr(m), L.ptr(v), n, lr_t, 0.9, 0.999, 1e-8, 0.5, L.stream()))
+    gg = gr.double() * 0.5
+    mr, vr = 0.1 * gg, 0.001 * gg * gg
+    assert rel(p, p0 - lr_t * mr / (vr.sqrt() + 1e-8)) <= 1e-6
+    mask = torch.empty(1 << 20, device=cuda)
+    L.check(L.lib().wspc_dropout_mask(L.ptr(mask), mask.numel(), 0.7, 1234, 0, L.stream()))
+    assert set(mask.unique().tolist()) <= {0.0, 1.0}
+    assert abs(float(mask.mean()) - 0.7) < 5e-3

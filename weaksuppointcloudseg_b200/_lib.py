@@ -147,6 +147,7 @@ _EXTRA_DECLS.update({
     "wspc_adam_tf": (c_int, [_P, _P, _P, _P, c_longlong, c_float, c_float, c_float, c_float, c_float, _P]),
     "wspc_dropout_mask": (c_int, [_P, c_longlong, c_float, c_uint64, c_uint64, _P]),
     "wspc_zero": (c_int, [_P, c_size_t, _P]),
+    "wspc_set_gemm_path": (c_int, [c_int]),
 })
 
 

@@ -8,8 +8,13 @@
 //   colgemm : dW(K1,K2) = sum_rows A^T dY           weight-gradient, deterministic slab reduction
 #include "operand.cuh"
 
+#include <stdlib.h>
+
 namespace wspc {
 void count_launch(int n = 1);
+int rowgemm_tc_dispatch(const Operand& A, int amode, const float* Bm, long long ldb, int bT, long long M, int N, int K,
+                        const Epilogue& E, int emode, cudaStream_t st);
+static int g_gemm_path = 0;   // 0 = auto (tcgen05 where eligible), 1 = CUDA-core kernels only
 namespace {
 
 constexpr int BM = 128, BN = 64, BK = 16, ALD = BM + 4;
@@ -372,6 +377,12 @@ int launch_wgrad_g(const Operand& A, const Operand& G, int gmode, long long M, c
 
 using namespace wspc;
 
+extern "C" int wspc_set_gemm_path(int path) {
+  const int old = wspc::g_gemm_path;
+  wspc::g_gemm_path = path;
+  return old;
+}
+
 extern "C" int wspc_conv1x1_rows(const wspc_operand_t* A, int a_mode, const float* Bm, long long ldb,
                                  int b_transposed, long long M, int N, int K, const wspc_epilogue_t* epi,
                                  int epi_mode, wspc_stream_t stream) {
@@ -386,6 +397,12 @@ extern "C" int wspc_conv1x1_rows(const wspc_operand_t* A, int a_mode, const floa
   if (epi_mode == EPI_STORE_STATS || epi_mode == EPI_RELUMASK_STATS)
     WSPC_REQUIRE(epi->stats, "conv1x1_rows: stats pointer is null");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // tensor-core (tcgen05) path for eligible shapes; WSPC_GEMM=simt forces the CUDA-core kernels (A/B testing)
+  static const bool env_simt = []() { const char* e = getenv("WSPC_GEMM"); return e && strcmp(e, "simt") == 0; }();
+  if (!env_simt && g_gemm_path == 0) {
+    const int rc = rowgemm_tc_dispatch(*A, a_mode, Bm, ldb, b_transposed, M, N, K, *epi, epi_mode, st);
+    if (rc != 0) return rc < 0 ? rc : WSPC_OK;
+  }
   switch (a_mode) {
     case OP_PLAIN: return launch_rows_e<OP_PLAIN>(*A, Bm, ldb, b_transposed, M, N, K, *epi, epi_mode, st);
     case OP_BNRELU: return launch_rows_e<OP_BNRELU>(*A, Bm, ldb, b_transposed, M, N, K, *epi, epi_mode, st);

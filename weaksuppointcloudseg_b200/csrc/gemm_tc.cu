@@ -1,0 +1,490 @@
+// tcgen05 (5th-gen tensor core) path for the wide shared-MLP GEMMs:  out(M,N) = A(M,K) * Bm(K,N)
+//
+// Used for every 1x1-conv forward / data-gradient GEMM whose K is a multiple of 8 with 16-byte aligned rows
+// (all EdgeConv layers except the 18-wide first one, and the per-point layers).  One CTA owns 128-row tiles
+// (persistent loop).  Per tile:
+//   1. all 8 warps synthesise the A operand on load (BN+ReLU of the previous layer, gathered edge feature,
+//      or the BN-backward affine of the upstream gradient), split every fp32 value into bf16 hi + bf16 lo
+//      and store both into shared memory in the UMMA no-swizzle K-major core-matrix layout
+//      ([K/8][rows][8 elems], 16 B per row and 8-column group, +16 B pad per group against bank conflicts);
+//   2. one thread issues tcgen05.mma (kind::f16, bf16 x bf16 -> fp32 in TMEM) three times over K:
+//      A_hi*B_hi + A_lo*B_hi + A_hi*B_lo  (error ~2^-16 relative, i.e. fp32-class accuracy for the 1e-3
+//      parity bar; a single bf16 pass would not hold it), then tcgen05.commit -> mbarrier;
+//   3. all warps read the accumulator back with tcgen05.ld (one thread = one output row), stage it through
+//      shared memory and write it out coalesced while folding the epilogue (bias / BN batch statistics /
+//      ReLU-mask + BN-backward sums / edge-gradient scatter).
+// The weight matrix is split and laid out once per CTA.  Two CTAs per SM overlap load, MMA and epilogue
+// phases of different tiles when shared memory allows (K<=64).
+#include "operand.cuh"
+#include <cuda_bf16.h>
+
+namespace wspc {
+void count_launch(int n = 1);
+namespace {
+
+constexpr int TC_THREADS = 256;
+constexpr int TILE_M = 128;
+constexpr int A_GROUP_BYTES = TILE_M * 16 + 16;   // one 8-column group of the A tile (LBO), padded
+constexpr int STAGE_LD = 64 + 4;                  // staging row pitch (floats) for a 64-column pass
+
+// ---------------------------------------------------------------- tcgen05 PTX ---
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_alloc(uint32_t* slot_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory descriptor, no swizzle, K-major: core matrix = 8 rows x 16 B stored contiguously (128 B);
+// SBO = distance between 8-row groups, LBO = distance between the two 8-column halves of a K=16 slice.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128
+__device__ __forceinline__ uint32_t umma_idesc(int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+
+__device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * i] - __bfloat162float(h0));
+    const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(h1));
+    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+struct TcSmem {
+  int Kp, Npad, b_group_bytes;
+  size_t off_bhi, off_blo, off_ahi, off_alo, off_stage, off_misc, total;
+};
+__host__ __device__ inline TcSmem tc_smem_plan(int K, int N, bool need_stage) {
+  TcSmem s;
+  s.Kp = (K + 15) / 16 * 16;
+  s.Npad = (N + 15) / 16 * 16;
+  s.b_group_bytes = s.Npad * 16 + 16;
+  const size_t bbytes = (size_t)(s.Kp / 8) * s.b_group_bytes;
+  const size_t abytes = (size_t)(s.Kp / 8) * A_GROUP_BYTES;
+  size_t o = 0;
+  s.off_bhi = o; o += (bbytes + 127) / 128 * 128;
+  s.off_blo = o; o += (bbytes + 127) / 128 * 128;
+  s.off_ahi = o; o += (abytes + 127) / 128 * 128;
+  s.off_alo = o; o += (abytes + 127) / 128 * 128;
+  s.off_stage = o; o += need_stage ? (size_t)TILE_M * STAGE_LD * 4 : 0;
+  s.off_misc = o; o += 64;
+  s.total = o;
+  return s;
+}
+
+// ------------------------------------------------------------------ kernel ---
+template <int AMODE, int EMODE, int MINB, int MAXPASS>
+__global__ void __launch_bounds__(TC_THREADS, MINB)
+rowgemm_tc_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, int bT, long long M, int N, int K,
+                  const Epilogue E, int num_tiles, int tmem_cols) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr bool kStage = (EMODE != EPI_EDGE_SCATTER) || true;
+  const TcSmem sp = tc_smem_plan(K, N, kStage);
+  unsigned char* sBhi = smem + sp.off_bhi;
+  unsigned char* sBlo = smem + sp.off_blo;
+  unsigned char* sAhi = smem + sp.off_ahi;
+  unsigned char* sAlo = smem + sp.off_alo;
+  float* stage = reinterpret_cast<float*>(smem + sp.off_stage);
+  uint64_t* mma_bar = reinterpret_cast<uint64_t*>(smem + sp.off_misc);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + sp.off_misc + 16);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int Kp = sp.Kp, k8n = Kp / 8;
+
+  // ---- one-time: TMEM, barrier, weights ------------------------------------------------------------
+  if (warp == 0) tc_alloc(tmem_slot, (uint32_t)tmem_cols);
+  if (tid == 32) {
+    mbar_init(mma_bar, 1);
+    mbar_fence_init();
+  }
+  // weights: element (n, k) of Bm^T -> group k/8, row n, slot k%8 ; zero padded
+  for (int e = tid; e < sp.Npad * k8n; e += TC_THREADS) {
+    const int n = e % sp.Npad, g = e / sp.Npad;
+    float w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = g * 8 + i;
+      w[i] = (n < N && k < K) ? (bT ? Bm[(long long)n * ldb + k] : Bm[(long long)k * ldb + n]) : 0.f;
+    }
+    uint4 hi, lo;
+    split8(w, hi, lo);
+    *reinterpret_cast<uint4*>(sBhi + (size_t)g * sp.b_group_bytes + n * 16) = hi;
+    *reinterpret_cast<uint4*>(sBlo + (size_t)g * sp.b_group_bytes + n * 16) = lo;
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t idesc = umma_idesc(sp.Npad);
+
+  // ---- per-thread loader constants: this thread always handles column group kg = tid % k8n -------------
+  // (TC_THREADS % k8n == 0 is guaranteed by the host: Kp/8 in {2,4,8,16,32,...} dividing 256)
+  const int kg = tid % k8n;
+  const int rstep = TC_THREADS / k8n;        // rows covered per sweep
+  const int r0 = tid / k8n;
+  float pc0[8], pc1[8], pc2[8];              // per-channel constants (sc/sh or c1/c2/c3)
+  const bool kvalid = kg * 8 < K;
+  if (AMODE == OP_BNRELU) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = kg * 8 + i;
+      pc0[i] = (c < K) ? A.sc[c] : 0.f;
+      pc1[i] = (c < K) ? A.sh[c] : 0.f;
+    }
+  } else if (AMODE == OP_DY) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = kg * 8 + i;
+      pc0[i] = (A.c1 && c < K) ? A.c1[c] : 1.f;
+      pc1[i] = (A.c1 && c < K) ? A.c2[c] : 0.f;
+      pc2[i] = (A.c1 && c < K) ? A.c3[c] : 0.f;
+    }
+  }
+
+  // epilogue-side per-thread accumulators: this thread always stores columns c4*4..+3 of a 64-col pass
+  const int e_c4 = tid & 15, e_r0 = tid >> 4;     // 16 rows per sweep, 8 sweeps per tile
+  constexpr bool kStats = (EMODE == EPI_STORE_STATS || EMODE == EPI_RELUMASK_STATS);
+  double st0[kStats ? MAXPASS : 1][4], st1[kStats ? MAXPASS : 1][4];
+  if (kStats) {
+#pragma unroll
+    for (int p = 0; p < MAXPASS; ++p)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { st0[p][j] = 0.0; st1[p][j] = 0.0; }
+  }
+  const int npass = (N + 63) / 64;
+
+  uint32_t phase = 0;
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const long long row0 = (long long)tile * TILE_M;
+
+    // ---------------------------------------------------------------- 1. A operand -> smem ------
+#pragma unroll 2
+    for (int r = r0; r < TILE_M; r += rstep) {
+      const long long row = row0 + r;
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = 0.f;
+      if (row < M && kvalid) {
+        if (AMODE == OP_PLAIN) {
+          ld8(A.p + row * A.ld + kg * 8, v);
+        } else if (AMODE == OP_BNRELU) {
+          float y[8];
+          ld8(A.p + row * A.ld + kg * 8, y);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = fmaxf(fmaf(y[i], pc0[i], pc1[i]), 0.f);
+          if (A.dmask) {
+            float m[8];
+            ld8(A.dmask + row * A.C + kg * 8, m);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] *= m[i] * A.dscale;
+          }
+        } else if (AMODE == OP_EDGE) {
+          const int Cx = A.C >> 1;
+          const long long pt = row / A.k;
+          if (kg * 8 < Cx) {
+            ld8(A.p + pt * A.ld + kg * 8, v);
+          } else {
+            const long long nb = (pt / A.npts) * A.npts + A.idx[row];
+            float xi[8], xj[8];
+            ld8(A.p + pt * A.ld + kg * 8 - Cx, xi);
+            ld8(A.p + nb * A.ld + kg * 8 - Cx, xj);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = xj[i] - xi[i];
+          }
+        } else if (AMODE == OP_DY) {
+          float g[8];
+          ld8(A.p + row * A.ld + kg * 8, g);
+          if (A.c1) {
+            float y[8];
+            ld8(A.y + row * A.ldy + kg * 8, y);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = fmaf(pc0[i], g[i], fmaf(pc2[i], y[i], pc1[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = g[i];
+          }
+        } else {  // OP_DY_SPARSE
+          load8<OP_DY_SPARSE>(A, row, kg * 8, v);
+        }
+      }
+      uint4 hi, lo;
+      split8(v, hi, lo);
+      *reinterpret_cast<uint4*>(sAhi + (size_t)kg * A_GROUP_BYTES + r * 16) = hi;
+      *reinterpret_cast<uint4*>(sAlo + (size_t)kg * A_GROUP_BYTES + r * 16) = lo;
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+
+    // ---------------------------------------------------------------- 2. MMA issue --------------
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t a_hi = smem_u32(sAhi), a_lo = smem_u32(sAlo), b_hi = smem_u32(sBhi), b_lo = smem_u32(sBlo);
+      uint32_t accum = 0;
+#pragma unroll 1
+      for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t ab = (pass == 1) ? a_lo : a_hi;
+        const uint32_t bb = (pass == 2) ? b_lo : b_hi;
+        for (int kk = 0; kk < Kp / 16; ++kk) {
+          const uint64_t ad = umma_desc(ab + (uint32_t)(2 * kk) * A_GROUP_BYTES, A_GROUP_BYTES, 128);
+          const uint64_t bd = umma_desc(bb + (uint32_t)(2 * kk) * sp.b_group_bytes, sp.b_group_bytes, 128);
+          tc_mma_bf16(tmem_base, ad, bd, idesc, accum);
+          accum = 1;
+        }
+      }
+      tc_commit(mma_bar);
+    }
+    mbar_wait(mma_bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+
+    // ---------------------------------------------------------------- 3. epilogue ---------------
+    const int lq = warp & 3, ch = warp >> 2;        // TMEM lane quadrant / 32-column half of a 64-col pass
+    const int trow = lq * 32 + lane;                // tile-local row owned in TMEM
+    for (int p = 0; p < npass; ++p) {
+      float v[32];
+      tc_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(p * 64 + ch * 32), v);
+      if (EMODE == EPI_EDGE_SCATTER && p * 64 >= (N >> 1)) {
+        // neighbour half [dE_d]: scatter to dx[idx], subtract from the staged centre sum
+        const int Cx = N >> 1;
+        const long long row = row0 + trow;
+        float* srow = stage + trow * STAGE_LD + ch * 32;
+        if (row < M) {
+          const long long pt = row / E.k;
+          const long long nb = (pt / E.npts) * E.npts + E.idx[row];
+          float* dst = E.dx + nb * E.lddx + (p * 64 - Cx) + ch * 32;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) red_add_v4(dst + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          float4 c = *reinterpret_cast<float4*>(srow + i);
+          c.x -= v[i]; c.y -= v[i + 1]; c.z -= v[i + 2]; c.w -= v[i + 3];
+          *reinterpret_cast<float4*>(srow + i) = c;
+        }
+      } else {
+        float* srow = stage + trow * STAGE_LD + ch * 32;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(srow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
+      if (EMODE == EPI_EDGE_SCATTER) {
+        if (p + 1 < npass) { __syncwarp(); continue; }   // (Cx == 64: pass 0 = centre part, pass 1 = neighbour part)
+      }
+      __syncthreads();
+      if (EMODE == EPI_EDGE_SCATTER) {
+        // centre reduction: rows of one point are consecutive; thread = (column, quarter of the rows)
+        const int col = tid & 63, q = tid >> 6;
+        long long cur = -1;
+        float acc = 0.f;
+        for (int r = q * 32; r < q * 32 + 32; ++r) {
+          const long long row = row0 + r;
+          if (row >= M) break;
+          const long long pt = row / E.k;
+          if (pt != cur) {
+            if (cur >= 0) atomicAdd(E.dx + cur * E.lddx + col, acc);
+            cur = pt;
+            acc = 0.f;
+          }
+          acc += stage[r * STAGE_LD + col];
+        }
+        if (cur >= 0) atomicAdd(E.dx + cur * E.lddx + col, acc);
+      } else {
+        const int cbase = p * 64 + e_c4 * 4;
+        if (cbase < N) {
+          float bias[4] = {0.f, 0.f, 0.f, 0.f}, scp[4], shp[4];
+          if ((EMODE == EPI_STORE || EMODE == EPI_STORE_STATS) && E.bias) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bias[j] = (cbase + j < N) ? E.bias[cbase + j] : 0.f;
+          }
+          if (EMODE == EPI_RELUMASK_STATS) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              scp[j] = (cbase + j < N) ? E.scp[cbase + j] : 0.f;
+              shp[j] = (cbase + j < N) ? E.shp[cbase + j] : -1.f;
+            }
+          }
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int r = e_r0 + 16 * it;
+            const long long row = row0 + r;
+            if (row >= M) break;
+            const float4 s4 = *reinterpret_cast<const float4*>(stage + r * STAGE_LD + e_c4 * 4);
+            float o[4] = {s4.x, s4.y, s4.z, s4.w};
+            if (EMODE == EPI_STORE || EMODE == EPI_STORE_STATS) {
+              const float* rb = E.rowbias ? E.rowbias + (row / E.rb_rows) * E.ldrb + cbase : nullptr;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                o[j] += bias[j];
+                if (rb && cbase + j < N) o[j] += rb[j];
+              }
+              if (EMODE == EPI_STORE_STATS) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { st0[p][j] += (double)o[j]; st1[p][j] += (double)o[j] * (double)o[j]; }
+              }
+            } else if (EMODE == EPI_RELUMASK_STATS) {
+              const float4 y4 = *reinterpret_cast<const float4*>(E.yprev + row * E.ldyp + cbase);
+              const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
+              float dm[4] = {1.f, 1.f, 1.f, 1.f};
+              if (E.dmask) {
+                const float4 m4 = *reinterpret_cast<const float4*>(E.dmask + row * N + cbase);
+                dm[0] = m4.x * E.dscale; dm[1] = m4.y * E.dscale; dm[2] = m4.z * E.dscale; dm[3] = m4.w * E.dscale;
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const bool on = fmaf(yv[j], scp[j], shp[j]) > 0.f;
+                o[j] = on ? o[j] * dm[j] : 0.f;
+                st0[p][j] += (double)o[j];
+                st1[p][j] += (double)o[j] * (double)yv[j];
+              }
+            } else if (EMODE == EPI_ACCUM) {
+              const float4 c4 = *reinterpret_cast<const float4*>(E.out + row * E.ldo + cbase);
+              o[0] += c4.x; o[1] += c4.y; o[2] += c4.z; o[3] += c4.w;
+            }
+            *reinterpret_cast<float4*>(E.out + row * E.ldo + cbase) = make_float4(o[0], o[1], o[2], o[3]);
+          }
+        }
+      }
+      __syncthreads();   // staging free for the next pass / tile
+    }
+    tc_fence_before();
+    __syncthreads();     // TMEM accumulator and A tile free for the next tile
+    tc_fence_after();
+  }
+
+  // ---- flush BN statistics ---------------------------------------------------------------------
+  if (kStats) {
+    for (int p = 0; p < npass; ++p) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        double a = st0[p][j], b = st1[p][j];
+        a += __shfl_xor_sync(0xffffffffu, a, 16);   // lanes l and l+16 own the same columns
+        b += __shfl_xor_sync(0xffffffffu, b, 16);
+        const int col = p * 64 + e_c4 * 4 + j;
+        if (lane < 16 && col < N) {
+          atomicAdd(E.stats + col, a);
+          atomicAdd(E.stats + N + col, b);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 0) tc_dealloc(tmem_base, (uint32_t)tmem_cols);
+}
+
+bool tc_supported(const Operand& A, int amode, const float* Bm, long long M, int N, int K, const Epilogue& E, int emode) {
+  if (K % 8 != 0 || K < 16 || K > 256) return false;
+  const int k8n = ((K + 15) / 16 * 16) / 8;
+  if (TC_THREADS % k8n != 0) return false;
+  if (N % 4 != 0 || N < 16 || N > 256) return false;
+  if (amode == OP_EDGE && ((A.C / 2) % 8 != 0 || (A.ld % 4) != 0)) return false;
+  if (amode != OP_DY_SPARSE && (!aligned16(A.p) || (A.ld % 4) != 0)) return false;
+  if (amode == OP_DY && A.c1 && (!aligned16(A.y) || (A.ldy % 4) != 0)) return false;
+  if (amode == OP_BNRELU && A.dmask && (!aligned16(A.dmask) || (A.C % 4) != 0)) return false;
+  if (emode == EPI_EDGE_SCATTER) {
+    if (N != 128 || (E.lddx % 4) != 0 || !aligned16(E.dx)) return false;
+  } else {
+    if (!aligned16(E.out) || (E.ldo % 4) != 0) return false;
+    if (emode == EPI_RELUMASK_STATS && (!aligned16(E.yprev) || (E.ldyp % 4) != 0)) return false;
+    if (emode == EPI_RELUMASK_STATS && E.dmask && !aligned16(E.dmask)) return false;
+  }
+  const TcSmem sp = tc_smem_plan(K, N, true);
+  return sp.total <= 200 * 1024;
+}
+
+template <int AMODE, int EMODE>
+int launch_tc(const Operand& A, const float* Bm, long long ldb, int bT, long long M, int N, int K, const Epilogue& E,
+              cudaStream_t st) {
+  const TcSmem sp = tc_smem_plan(K, N, true);
+  const int num_tiles = (int)((M + TILE_M - 1) / TILE_M);
+  const int npass = (N + 63) / 64;
+  int tmem_cols = 64;
+  while (tmem_cols < npass * 64) tmem_cols <<= 1;
+  const bool two = sp.total <= 110 * 1024;
+  const int ctas = two ? 2 * kNumSM : kNumSM;
+  const int grid = num_tiles < ctas ? num_tiles : ctas;
+#define WSPC_TC_LAUNCH(MINB_, NP_)                                                                          \
+  {                                                                                                         \
+    auto kern = rowgemm_tc_kernel<AMODE, EMODE, MINB_, NP_>;                                                \
+    WSPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total));      \
+    kern<<<grid, TC_THREADS, sp.total, st>>>(A, Bm, ldb, bT, M, N, K, E, num_tiles, tmem_cols);             \
+  }
+  if (npass <= 1) { if (two) WSPC_TC_LAUNCH(2, 1) else WSPC_TC_LAUNCH(1, 1) }
+  else if (npass <= 2) { if (two) WSPC_TC_LAUNCH(2, 2) else WSPC_TC_LAUNCH(1, 2) }
+  else WSPC_TC_LAUNCH(1, 4)
+#undef WSPC_TC_LAUNCH
+  count_launch();
+  WSPC_LAUNCH_CHECK("rowgemm_tc_kernel");
+  return WSPC_OK;
+}
+
+}  // namespace
+
+// returns 1 if the tensor-core path handled the call, 0 if the shape is not eligible, <0 on error
+int rowgemm_tc_dispatch(const Operand& A, int amode, const float* Bm, long long ldb, int bT, long long M, int N, int K,
+                        const Epilogue& E, int emode, cudaStream_t st) {
+  if (!tc_supported(A, amode, Bm, M, N, K, E, emode)) return 0;
+  int rc = -100;
+#define WSPC_TC(AM, EM) \
+  if (amode == AM && emode == EM) rc = launch_tc<AM, EM>(A, Bm, ldb, bT, M, N, K, E, st);
+  WSPC_TC(OP_PLAIN, EPI_STORE) WSPC_TC(OP_PLAIN, EPI_STORE_STATS)
+  WSPC_TC(OP_BNRELU, EPI_STORE) WSPC_TC(OP_BNRELU, EPI_STORE_STATS)
+  WSPC_TC(OP_EDGE, EPI_STORE) WSPC_TC(OP_EDGE, EPI_STORE_STATS)
+  WSPC_TC(OP_DY, EPI_STORE) WSPC_TC(OP_DY, EPI_RELUMASK_STATS) WSPC_TC(OP_DY, EPI_EDGE_SCATTER) WSPC_TC(OP_DY, EPI_ACCUM)
+  WSPC_TC(OP_DY_SPARSE, EPI_STORE) WSPC_TC(OP_DY_SPARSE, EPI_ACCUM)
+#undef WSPC_TC
+  if (rc == -100) return 0;
+  return rc == WSPC_OK ? 1 : rc;
+}
+
+}  // namespace wspc
