@@ -119,25 +119,42 @@ def test_bwd_dy_relumask_and_scatter(cuda, gemm_path):
     assert float(dx[:, :64].abs().max()) == 0 and float(dx[:, 128:].abs().max()) == 0
 
 
-def test_wgrad_matches_fp64(cuda):
+@pytest.mark.parametrize("K1,K2,mode", [(64, 64, "bnrelu"), (128, 64, "edge"), (192, 1024, "plain"), (512, 256, "bnrelu"),
+                                        (18, 64, "edge"), (256, 13, "bnrelu")])
+def test_wgrad_matches_fp64(cuda, gemm_path, K1, K2, mode):
     from weaksuppointcloudseg_b200 import _lib as L, runtime as rt
     g = torch.Generator(device="cuda").manual_seed(3)
-    M, K1, K2 = 5000, 64, 64
-    a = torch.randn((M, K1), device=cuda, generator=g)
-    sc = torch.rand(K1, device=cuda, generator=g) + 0.5
-    sh = torch.randn(K1, device=cuda, generator=g) * 0.2
+    B, Np, k = 2, 100, 20
+    M = B * Np * k + (0 if mode == "edge" else 37)
     G = torch.randn((M, K2), device=cuda, generator=g)
     y = torch.randn((M, K2), device=cuda, generator=g)
     c1, c2, c3 = (torch.randn(K2, device=cuda, generator=g) * 0.5 for _ in range(3))
-    dW = torch.empty((K1, K2), device=cuda)
-    db = torch.empty(K2, device=cuda)
-    A = (L.Operand(p=a.data_ptr(), ld=K1, C=K1, sc=sc.data_ptr(), sh=sh.data_ptr(), dscale=1.0), L.OP_BNRELU)
+    dy = c1.double() * G.double() + c2.double() + c3.double() * y.double()
     Gop = (L.Operand(p=G.data_ptr(), ld=K2, C=K2, y=y.data_ptr(), ldy=K2, c1=c1.data_ptr(), c2=c2.data_ptr(),
                      c3=c3.data_ptr()), L.OP_DY)
+    if mode == "edge":
+        Cx = K1 // 2
+        x = torch.randn((B * Np, Cx), device=cuda, generator=g)
+        idx = torch.randint(0, Np, (B, Np, k), device=cuda, generator=g, dtype=torch.int32)
+        A = (L.Operand(p=x.data_ptr(), ld=Cx, C=K1, idx=idx.data_ptr(), k=k, npts=Np), L.OP_EDGE)
+        gidx = (idx.long() + torch.arange(B, device=cuda).view(B, 1, 1) * Np).reshape(-1)
+        ctr = x.double().view(B, Np, 1, Cx).expand(B, Np, k, Cx)
+        nb = x.double()[gidx].view(B, Np, k, Cx)
+        act = torch.cat([ctr, nb - ctr], -1).reshape(M, K1)
+    else:
+        a = torch.randn((M, K1), device=cuda, generator=g)
+        if mode == "bnrelu":
+            sc = torch.rand(K1, device=cuda, generator=g) + 0.5
+            sh = torch.randn(K1, device=cuda, generator=g) * 0.2
+            A = (L.Operand(p=a.data_ptr(), ld=K1, C=K1, sc=sc.data_ptr(), sh=sh.data_ptr(), dscale=1.0), L.OP_BNRELU)
+            act = torch.relu(a.double() * sc.double() + sh.double())
+        else:
+            A = (L.Operand(p=a.data_ptr(), ld=K1, C=K1), L.OP_PLAIN)
+            act = a.double()
+    dW = torch.empty((K1, K2), device=cuda)
+    db = torch.empty(K2, device=cuda)
     rt.wgrad(A, Gop, M, dW, db, cuda)
-    act = torch.relu(a.double() * sc.double() + sh.double())
-    dy = c1.double() * G.double() + c2.double() + c3.double() * y.double()
-    assert rel(dW, act.T @ dy) <= 2e-5
+    assert rel(dW, act.T @ dy) <= _tol(gemm_path)
     assert rel(db, dy.sum(0)) <= 2e-5
 
 

@@ -12,6 +12,9 @@
 
 namespace wspc {
 void count_launch(int n = 1);
+int wgrad_tc_slabs(int K1, int K2);
+int wgrad_tc_dispatch(const Operand& A, int amode, const Operand& G, int gmode, long long M, int S, int K1p, int K2p,
+                      float* partial, float* partial_b, cudaStream_t st);
 int rowgemm_tc_dispatch(const Operand& A, int amode, const float* Bm, long long ldb, int bT, long long M, int N, int K,
                         const Epilogue& E, int emode, cudaStream_t st);
 static int g_gemm_path = 0;   // 0 = auto (tcgen05 where eligible), 1 = CUDA-core kernels only
@@ -312,7 +315,7 @@ __global__ void slab_reduce_kernel(const float* __restrict__ partial, const floa
 }
 
 struct WgradPlan {
-  int K1p, K2p, t1, t2, S;
+  int K1p, K2p, t1, t2, S, S_tc;
   size_t partial_bytes, bias_bytes;
 };
 WgradPlan wgrad_plan(int K1, int K2) {
@@ -324,8 +327,10 @@ WgradPlan wgrad_plan(int K1, int K2) {
   const int tiles = p.t1 * p.t2;
   p.S = (4 * kNumSM + tiles - 1) / tiles;  // ~4 CTAs per SM in flight
   if (p.S < 1) p.S = 1;
-  p.partial_bytes = align_up((size_t)p.S * p.K1p * p.K2p * sizeof(float), 256);
-  p.bias_bytes = align_up((size_t)p.S * p.K2p * sizeof(float), 256);
+  p.S_tc = wgrad_tc_slabs(K1, K2);
+  const int smax = p.S > p.S_tc ? p.S : p.S_tc;
+  p.partial_bytes = align_up((size_t)smax * p.K1p * p.K2p * sizeof(float), 256);
+  p.bias_bytes = align_up((size_t)smax * p.K2p * sizeof(float), 256);
   return p;
 }
 
@@ -435,6 +440,13 @@ extern "C" int wspc_conv1x1_wgrad(const wspc_operand_t* A, int a_mode, const wsp
   float* partial_b = reinterpret_cast<float*>(static_cast<char*>(workspace) + p.partial_bytes);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int rc;
+  int S_used = p.S;
+  static const bool env_simt = []() { const char* e = getenv("WSPC_GEMM"); return e && strcmp(e, "simt") == 0; }();
+  if (!env_simt && g_gemm_path == 0) {
+    rc = wgrad_tc_dispatch(*A, a_mode, *G, g_mode, M, p.S_tc, p.K1p, p.K2p, partial, db ? partial_b : nullptr, st);
+    if (rc < 0) return rc;
+    if (rc == 1) { S_used = p.S_tc; goto reduce; }
+  }
   switch (a_mode) {
     case OP_PLAIN: rc = launch_wgrad_g<OP_PLAIN>(*A, *G, g_mode, M, p, partial, partial_b, st); break;
     case OP_BNRELU: rc = launch_wgrad_g<OP_BNRELU>(*A, *G, g_mode, M, p, partial, partial_b, st); break;
@@ -444,8 +456,9 @@ extern "C" int wspc_conv1x1_wgrad(const wspc_operand_t* A, int a_mode, const wsp
       return WSPC_ERR_INVALID;
   }
   if (rc) return rc;
+reduce:
   const int total = A->C * G->C + (db ? G->C : 0);
-  slab_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(partial, partial_b, p.S, A->C, G->C, p.K1p, p.K2p, dW, db);
+  slab_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(partial, partial_b, S_used, A->C, G->C, p.K1p, p.K2p, dW, db);
   count_launch();
   WSPC_LAUNCH_CHECK("slab_reduce_kernel");
   return WSPC_OK;

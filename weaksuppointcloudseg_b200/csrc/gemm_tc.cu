@@ -100,6 +100,69 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// Loads the 8 channels [kg*8, kg*8+8) of logical row `row` of an operand (zeros if !valid).
+// pc0..2 hold the thread's per-channel constants (BNRELU: sc, sh; DY: c1, c2, c3).
+template <int AMODE>
+__device__ __forceinline__ void load_chunk(const Operand& A, long long row, int kg, bool valid, const float (&pc0)[8],
+                                           const float (&pc1)[8], const float (&pc2)[8], float (&v)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = 0.f;
+  if (!valid) return;
+  if (AMODE == OP_PLAIN) {
+    ld8(A.p + row * A.ld + kg * 8, v);
+  } else if (AMODE == OP_BNRELU) {
+    float y[8];
+    ld8(A.p + row * A.ld + kg * 8, y);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaxf(fmaf(y[i], pc0[i], pc1[i]), 0.f);
+    if (A.dmask) {
+      float m[8];
+      ld8(A.dmask + row * A.C + kg * 8, m);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] *= m[i] * A.dscale;
+    }
+  } else if (AMODE == OP_EDGE) {
+    const int Cx = A.C >> 1;
+    const long long pt = row / A.k;
+    if (kg * 8 < Cx) {
+      ld8(A.p + pt * A.ld + kg * 8, v);
+    } else {
+      const long long nb = (pt / A.npts) * A.npts + A.idx[row];
+      float xi[8], xj[8];
+      ld8(A.p + pt * A.ld + kg * 8 - Cx, xi);
+      ld8(A.p + nb * A.ld + kg * 8 - Cx, xj);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = xj[i] - xi[i];
+    }
+  } else if (AMODE == OP_DY) {
+    float g[8];
+    ld8(A.p + row * A.ld + kg * 8, g);
+    if (A.c1) {
+      float y[8];
+      ld8(A.y + row * A.ldy + kg * 8, y);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = fmaf(pc0[i], g[i], fmaf(pc2[i], y[i], pc1[i]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = g[i];
+    }
+  } else {  // OP_DY_SPARSE
+    load8<OP_DY_SPARSE>(A, row, kg * 8, v);
+  }
+}
+
+template <int AMODE>
+__device__ __forceinline__ void load_consts(const Operand& A, int kg, int K, float (&pc0)[8], float (&pc1)[8],
+                                            float (&pc2)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = kg * 8 + i;
+    pc0[i] = 0.f; pc1[i] = 0.f; pc2[i] = 0.f;
+    if (AMODE == OP_BNRELU && c < K) { pc0[i] = A.sc[c]; pc1[i] = A.sh[c]; }
+    if (AMODE == OP_DY && A.c1 && c < K) { pc0[i] = A.c1[c]; pc1[i] = A.c2[c]; pc2[i] = A.c3[c]; }
+  }
+}
+
 struct TcSmem {
   int Kp, Npad, b_group_bytes;
   size_t off_bhi, off_blo, off_ahi, off_alo, off_stage, off_misc, total;
@@ -175,22 +238,7 @@ rowgemm_tc_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, 
   const int r0 = tid / k8n;
   float pc0[8], pc1[8], pc2[8];              // per-channel constants (sc/sh or c1/c2/c3)
   const bool kvalid = kg * 8 < K;
-  if (AMODE == OP_BNRELU) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = kg * 8 + i;
-      pc0[i] = (c < K) ? A.sc[c] : 0.f;
-      pc1[i] = (c < K) ? A.sh[c] : 0.f;
-    }
-  } else if (AMODE == OP_DY) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = kg * 8 + i;
-      pc0[i] = (A.c1 && c < K) ? A.c1[c] : 1.f;
-      pc1[i] = (A.c1 && c < K) ? A.c2[c] : 0.f;
-      pc2[i] = (A.c1 && c < K) ? A.c3[c] : 0.f;
-    }
-  }
+  load_consts<AMODE>(A, kg, K, pc0, pc1, pc2);
 
   // epilogue-side per-thread accumulators: this thread always stores columns c4*4..+3 of a 64-col pass
   const int e_c4 = tid & 15, e_r0 = tid >> 4;     // 16 rows per sweep, 8 sweeps per tile
@@ -213,51 +261,7 @@ rowgemm_tc_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, 
     for (int r = r0; r < TILE_M; r += rstep) {
       const long long row = row0 + r;
       float v[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = 0.f;
-      if (row < M && kvalid) {
-        if (AMODE == OP_PLAIN) {
-          ld8(A.p + row * A.ld + kg * 8, v);
-        } else if (AMODE == OP_BNRELU) {
-          float y[8];
-          ld8(A.p + row * A.ld + kg * 8, y);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = fmaxf(fmaf(y[i], pc0[i], pc1[i]), 0.f);
-          if (A.dmask) {
-            float m[8];
-            ld8(A.dmask + row * A.C + kg * 8, m);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] *= m[i] * A.dscale;
-          }
-        } else if (AMODE == OP_EDGE) {
-          const int Cx = A.C >> 1;
-          const long long pt = row / A.k;
-          if (kg * 8 < Cx) {
-            ld8(A.p + pt * A.ld + kg * 8, v);
-          } else {
-            const long long nb = (pt / A.npts) * A.npts + A.idx[row];
-            float xi[8], xj[8];
-            ld8(A.p + pt * A.ld + kg * 8 - Cx, xi);
-            ld8(A.p + nb * A.ld + kg * 8 - Cx, xj);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = xj[i] - xi[i];
-          }
-        } else if (AMODE == OP_DY) {
-          float g[8];
-          ld8(A.p + row * A.ld + kg * 8, g);
-          if (A.c1) {
-            float y[8];
-            ld8(A.y + row * A.ldy + kg * 8, y);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = fmaf(pc0[i], g[i], fmaf(pc2[i], y[i], pc1[i]));
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = g[i];
-          }
-        } else {  // OP_DY_SPARSE
-          load8<OP_DY_SPARSE>(A, row, kg * 8, v);
-        }
-      }
+      load_chunk<AMODE>(A, row, kg, row < M && kvalid, pc0, pc1, pc2, v);
       uint4 hi, lo;
       split8(v, hi, lo);
       *reinterpret_cast<uint4*>(sAhi + (size_t)kg * A_GROUP_BYTES + r * 16) = hi;
@@ -468,6 +472,203 @@ int launch_tc(const Operand& A, const float* Bm, long long ldb, int bT, long lon
   return WSPC_OK;
 }
 
+
+// ------------------------------------------------------------------ weight gradient on tensor cores ---
+// dW(K1,K2) = sum_rows A(row,:)^T dY(row,:).  The reduction runs over rows, so both operands are "MN-major"
+// for the MMA (channels contiguous, rows = K).  The shared-memory image is the same [channel group][row][8]
+// layout as above — read by the tensor core with the roles of LBO/SBO swapped — so the loaders are shared.
+// Each CTA owns a slab of rows and one (128 x <=256) tile of dW, accumulates it in TMEM over the whole slab
+// and writes a partial; slab_reduce_kernel adds the partials in fp64 in a fixed order (deterministic).
+__device__ __forceinline__ uint32_t umma_idesc_mn(int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(TILE_M >> 4) << 24);
+}
+
+template <int AMODE, int GMODE, int MINB>
+__global__ void __launch_bounds__(TC_THREADS, MINB)
+colgemm_tc_kernel(const Operand A, const Operand G, long long M, long long rows_per_slab, int K1p, int K2p, int K2t,
+                  float* __restrict__ partial, float* __restrict__ partial_b, int tmem_cols) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int gGroups = K2t / 8;                         // power of two, <= 32
+  unsigned char* sAhi = smem;
+  unsigned char* sAlo = sAhi + 16 * A_GROUP_BYTES;
+  unsigned char* sGhi = sAlo + 16 * A_GROUP_BYTES;
+  unsigned char* sGlo = sGhi + (size_t)gGroups * A_GROUP_BYTES;
+  unsigned char* misc = sGlo + (size_t)gGroups * A_GROUP_BYTES;
+  uint64_t* mma_bar = reinterpret_cast<uint64_t*>(misc);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 16);
+  float* bred = reinterpret_cast<float*>(misc + 32);   // [K2t] bias-gradient reduction
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int k1_0 = blockIdx.y * TILE_M, k2_0 = blockIdx.z * 256;
+  const long long r_begin = (long long)blockIdx.x * rows_per_slab;
+  const long long r_end = (r_begin + rows_per_slab < M) ? r_begin + rows_per_slab : M;
+
+  if (warp == 0) tc_alloc(tmem_slot, (uint32_t)tmem_cols);
+  if (tid == 32) { mbar_init(mma_bar, 1); mbar_fence_init(); }
+  for (int i = tid; i < K2t; i += TC_THREADS) bred[i] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t idesc = umma_idesc_mn(K2t);
+
+  // fixed per-thread channel groups
+  const int gA = tid & 15, rA0 = tid >> 4;                 // A: 16 groups, 16 rows per sweep
+  const int gG = tid % gGroups, rG0 = tid / gGroups;       // dY: gGroups groups
+  const int rGstep = TC_THREADS / gGroups;
+  const int cA = k1_0 / 8 + gA, cG = k2_0 / 8 + gG;        // absolute channel groups
+  const bool vA = cA * 8 < A.C, vG = cG * 8 < G.C;
+  float a0[8], a1[8], a2[8], g0[8], g1[8], g2[8];
+  load_consts<AMODE>(A, cA, A.C, a0, a1, a2);
+  load_consts<GMODE>(G, cG, G.C, g0, g1, g2);
+  double bsum[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) bsum[i] = 0.0;
+
+  uint32_t phase = 0, accum = 0;
+  bool pending = false;
+  for (long long rb = r_begin; rb < r_end; rb += TILE_M) {
+    if (pending) { mbar_wait(mma_bar, phase); phase ^= 1; pending = false; }   // MMAs done reading smem
+#pragma unroll 2
+    for (int r = rA0; r < TILE_M; r += 16) {
+      const long long row = rb + r;
+      float v[8];
+      load_chunk<AMODE>(A, row, cA, vA && row < r_end, a0, a1, a2, v);
+      uint4 hi, lo;
+      split8(v, hi, lo);
+      *reinterpret_cast<uint4*>(sAhi + (size_t)gA * A_GROUP_BYTES + r * 16) = hi;
+      *reinterpret_cast<uint4*>(sAlo + (size_t)gA * A_GROUP_BYTES + r * 16) = lo;
+    }
+#pragma unroll 2
+    for (int r = rG0; r < TILE_M; r += rGstep) {
+      const long long row = rb + r;
+      float v[8];
+      load_chunk<GMODE>(G, row, cG, vG && row < r_end, g0, g1, g2, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) bsum[i] += (double)v[i];
+      uint4 hi, lo;
+      split8(v, hi, lo);
+      *reinterpret_cast<uint4*>(sGhi + (size_t)gG * A_GROUP_BYTES + r * 16) = hi;
+      *reinterpret_cast<uint4*>(sGlo + (size_t)gG * A_GROUP_BYTES + r * 16) = lo;
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t ah = smem_u32(sAhi), al = smem_u32(sAlo), gh = smem_u32(sGhi), gl = smem_u32(sGlo);
+#pragma unroll 1
+      for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t ab = (pass == 1) ? al : ah;
+        const uint32_t gb = (pass == 2) ? gl : gh;
+        for (int j = 0; j < TILE_M / 16; ++j) {
+          // rows 16j..16j+15 = one K=16 slice: k-groups of 8 rows are 128 B apart, channel groups A_GROUP_BYTES apart
+          const uint64_t ad = umma_desc(ab + (uint32_t)j * 256, 128, A_GROUP_BYTES);
+          const uint64_t gd = umma_desc(gb + (uint32_t)j * 256, 128, A_GROUP_BYTES);
+          tc_mma_bf16(tmem_base, ad, gd, idesc, accum);
+          accum = 1;
+        }
+      }
+      tc_commit(mma_bar);
+    }
+    pending = true;
+  }
+  if (pending) { mbar_wait(mma_bar, phase); phase ^= 1; }
+  tc_fence_after();
+
+  // epilogue: TMEM (lane = k1 within tile, column = k2) -> partial
+  {
+    const int lq = warp & 3, ch = warp >> 2;
+    const int k1 = k1_0 + lq * 32 + lane;
+    float* prow = partial + ((size_t)blockIdx.x * K1p + k1) * K2p + k2_0;
+    for (int c0 = ch * 32; c0 < K2t; c0 += 64) {
+      float v[32];
+      if (r_begin < r_end) tc_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)c0, v);
+      else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0.f;
+      }
+      if (k1 < K1p) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          if (k2_0 + c0 + i < K2p) *reinterpret_cast<float4*>(prow + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
+    }
+  }
+  if (blockIdx.y == 0 && partial_b) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(&bred[gG * 8 + i], (float)bsum[i]);
+    __syncthreads();
+    for (int i = tid; i < K2t; i += TC_THREADS)
+      if (k2_0 + i < K2p) partial_b[(size_t)blockIdx.x * K2p + k2_0 + i] = bred[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc_dealloc(tmem_base, (uint32_t)tmem_cols);
+}
+
+bool wgrad_tc_supported(const Operand& A, int amode, const Operand& G, int gmode) {
+  if (amode != OP_PLAIN && amode != OP_BNRELU && amode != OP_EDGE) return false;
+  if (gmode != OP_DY && gmode != OP_DY_SPARSE) return false;
+  if (A.C % 8 != 0 || G.C % 8 != 0 || A.C < 16 || G.C < 16) return false;
+  if (!aligned16(A.p) || (A.ld % 4) != 0) return false;
+  if (amode == OP_EDGE && ((A.C / 2) % 8) != 0) return false;
+  if (amode == OP_BNRELU && A.dmask && (!aligned16(A.dmask) || (A.C % 4) != 0)) return false;
+  if (gmode == OP_DY && (!aligned16(G.p) || (G.ld % 4) != 0)) return false;
+  if (gmode == OP_DY && G.c1 && (!aligned16(G.y) || (G.ldy % 4) != 0)) return false;
+  return true;
+}
+
+template <int AMODE, int GMODE>
+int launch_wgrad_tc(const Operand& A, const Operand& G, long long M, int S, int K1p, int K2p, float* partial,
+                    float* partial_b, cudaStream_t st) {
+  const int t1 = (A.C + TILE_M - 1) / TILE_M, t2 = (G.C + 255) / 256;
+  int K2t = 16;
+  const int k2max = G.C < 256 ? G.C : 256;
+  while (K2t < k2max) K2t <<= 1;
+  int tmem_cols = 64;
+  while (tmem_cols < K2t) tmem_cols <<= 1;
+  const size_t smem = (size_t)(32 + 2 * (K2t / 8)) * A_GROUP_BYTES + 32 + (size_t)K2t * 4 + 64;
+  long long rps = (M + S - 1) / S;
+  rps = (rps + TILE_M - 1) / TILE_M * TILE_M;
+  dim3 grid(S, t1, t2);
+  if (smem <= 110 * 1024) {
+    auto kern = colgemm_tc_kernel<AMODE, GMODE, 2>;
+    WSPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, TC_THREADS, smem, st>>>(A, G, M, rps, K1p, K2p, K2t, partial, partial_b, tmem_cols);
+  } else {
+    auto kern = colgemm_tc_kernel<AMODE, GMODE, 1>;
+    WSPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, TC_THREADS, smem, st>>>(A, G, M, rps, K1p, K2p, K2t, partial, partial_b, tmem_cols);
+  }
+  count_launch();
+  WSPC_LAUNCH_CHECK("colgemm_tc_kernel");
+  return WSPC_OK;
+}
+
+}  // namespace
+
+int wgrad_tc_slabs(int K1, int K2) {
+  const int tiles = ((K1 + TILE_M - 1) / TILE_M) * ((K2 + 255) / 256);
+  int S = (2 * kNumSM) / tiles;
+  return S < 1 ? 1 : S;
+}
+
+// returns 1 if handled (partials written for S slabs), 0 if not eligible, <0 on error
+int wgrad_tc_dispatch(const Operand& A, int amode, const Operand& G, int gmode, long long M, int S, int K1p, int K2p,
+                      float* partial, float* partial_b, cudaStream_t st) {
+  if (!wgrad_tc_supported(A, amode, G, gmode)) return 0;
+  int rc = -100;
+#define WSPC_WG(AM, GM) \
+  if (amode == AM && gmode == GM) rc = launch_wgrad_tc<AM, GM>(A, G, M, S, K1p, K2p, partial, partial_b, st);
+  WSPC_WG(OP_PLAIN, OP_DY) WSPC_WG(OP_BNRELU, OP_DY) WSPC_WG(OP_EDGE, OP_DY) WSPC_WG(OP_PLAIN, OP_DY_SPARSE)
+#undef WSPC_WG
+  if (rc == -100) return 0;
+  return rc == WSPC_OK ? 1 : rc;
+}
+
+namespace {
 }  // namespace
 
 // returns 1 if the tensor-core path handled the call, 0 if the shape is not eligible, <0 on error
