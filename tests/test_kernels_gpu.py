@@ -230,3 +230,65 @@ def test_adam_tf_and_dropout_mask(cuda):
     L.check(L.lib().wspc_dropout_mask(L.ptr(mask), mask.numel(), 0.7, 1234, 0, L.stream()))
     assert set(mask.unique().tolist()) <= {0.0, 1.0}
     assert abs(float(mask.mean()) - 0.7) < 5e-3
+
+
+@pytest.mark.parametrize("K,N,kind", [(192, 1024, "plain_rowbias"), (512, 256, "bnrelu_drop"), (512, 192, "dy_store"),
+                                      (1024, 192, "sparse_accum"), (256, 16, "bnrelu_drop"), (1024, 512, "plain_small")])
+def test_rows_gemm_chunked_shapes(cuda, gemm_path, K, N, kind):
+    """per-point layer shapes: K > 128 is accumulated in TMEM over 64-channel chunks, N > 128 is tiled"""
+    from weaksuppointcloudseg_b200 import _lib as L, runtime as rt
+    g = torch.Generator(device="cuda").manual_seed(7)
+    Bc, Np = 3, 173
+    M = Bc * Np if kind != "plain_small" else 5
+    W = torch.randn((K, N), device=cuda, generator=g) * 0.1
+    out = torch.randn((M, N), device=cuda, generator=g)
+    out0 = out.double().clone()
+    if kind in ("plain_rowbias", "plain_small"):
+        a = torch.randn((M, K), device=cuda, generator=g)
+        b = torch.randn(N, device=cuda, generator=g)
+        rb = torch.randn((Bc, N), device=cuda, generator=g)
+        stats = torch.zeros((2, N), dtype=torch.float64, device=cuda)
+        A = (L.Operand(p=a.data_ptr(), ld=K, C=K), L.OP_PLAIN)
+        use_rb = kind == "plain_rowbias"
+        epi = L.Epilogue(out=out.data_ptr(), ldo=N, bias=b.data_ptr(), rowbias=rb.data_ptr() if use_rb else 0, rb_rows=Np,
+                         ldrb=N, stats=stats.data_ptr())
+        rt.rows_gemm(A, W, N, 0, M, N, K, epi, L.EPI_STORE_STATS)
+        ref = a.double() @ W.double() + b.double()
+        if use_rb:
+            ref = ref + rb.double().repeat_interleave(Np, 0)
+        assert rel(out, ref) <= _tol(gemm_path)
+        assert rel(stats[0], out.double().sum(0)) <= 1e-6 and rel(stats[1], (out.double() ** 2).sum(0)) <= 1e-6
+    elif kind == "bnrelu_drop":
+        y = torch.randn((M, K), device=cuda, generator=g)
+        sc = torch.rand(K, device=cuda, generator=g) + 0.5
+        sh = torch.randn(K, device=cuda, generator=g) * 0.2
+        dm = torch.floor(0.7 + torch.rand((M, K), device=cuda, generator=g))
+        b = torch.randn(N, device=cuda, generator=g)
+        A = (L.Operand(p=y.data_ptr(), ld=K, C=K, sc=sc.data_ptr(), sh=sh.data_ptr(), dmask=dm.data_ptr(), dscale=1 / 0.7),
+             L.OP_BNRELU)
+        rt.rows_gemm(A, W, N, 0, M, N, K, L.Epilogue(out=out.data_ptr(), ldo=N, bias=b.data_ptr()), L.EPI_STORE)
+        ref = (torch.relu(y.double() * sc.double() + sh.double()) * dm.double() / 0.7) @ W.double() + b.double()
+        assert rel(out, ref) <= _tol(gemm_path)
+    elif kind == "dy_store":
+        G = torch.randn((M, K), device=cuda, generator=g)
+        y = torch.randn((M, K), device=cuda, generator=g)
+        c1, c2, c3 = (torch.randn(K, device=cuda, generator=g) * 0.5 for _ in range(3))
+        Wl = torch.randn((N, K), device=cuda, generator=g) * 0.1          # layer weight (Cin=N, Cout=K)
+        A = (L.Operand(p=G.data_ptr(), ld=K, C=K, y=y.data_ptr(), ldy=K, c1=c1.data_ptr(), c2=c2.data_ptr(),
+                       c3=c3.data_ptr()), L.OP_DY)
+        rt.rows_gemm(A, Wl, K, 1, M, N, K, L.Epilogue(out=out.data_ptr(), ldo=N), L.EPI_STORE)
+        dy = c1.double() * G.double() + c2.double() + c3.double() * y.double()
+        assert rel(out, dy @ Wl.double().T) <= _tol(gemm_path)
+    else:  # sparse_accum: gradient of max_pool2d + BN folded, accumulated onto dcat
+        y = torch.randn((M, K), device=cuda, generator=g)
+        c1, c2, c3 = (torch.randn(K, device=cuda, generator=g) * 0.5 for _ in range(3))
+        dg = torch.randn((Bc, K), device=cuda, generator=g)
+        amax = torch.randint(0, Np, (Bc, K), device=cuda, generator=g, dtype=torch.int32)
+        Wl = torch.randn((N, K), device=cuda, generator=g) * 0.1
+        A = (L.Operand(p=0, ld=0, C=K, y=y.data_ptr(), ldy=K, c1=c1.data_ptr(), c2=c2.data_ptr(), c3=c3.data_ptr(),
+                       dg=dg.data_ptr(), amax=amax.data_ptr(), npts=Np), L.OP_DY_SPARSE)
+        rt.rows_gemm(A, Wl, K, 1, M, N, K, L.Epilogue(out=out.data_ptr(), ldo=N), L.EPI_ACCUM)
+        Gd = torch.zeros((Bc, Np, K), dtype=torch.float64, device=cuda)
+        Gd.scatter_(1, amax.long().unsqueeze(1), dg.double().unsqueeze(1))
+        dy = c1.double() * Gd.reshape(M, K) + c2.double() + c3.double() * y.double()
+        assert rel(out, out0 + dy @ Wl.double().T) <= _tol(gemm_path)

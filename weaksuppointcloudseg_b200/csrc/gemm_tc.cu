@@ -186,13 +186,16 @@ __host__ __device__ inline TcSmem tc_smem_plan(int K, int N, bool need_stage) {
 }
 
 // ------------------------------------------------------------------ kernel ---
+// K is processed in chunks of KC channels (KC = Kp when K <= 128, else 64) accumulated in TMEM; N is tiled
+// by blockIdx.y (whole N when it fits one tile, else 128 columns per tile).  When there is a single chunk
+// and a single N tile (all EdgeConv layers) the split weights stay resident in shared memory for the whole
+// persistent loop; otherwise the CTA re-splits the (KC x Nt) weight block it needs per chunk (L2-resident).
 template <int AMODE, int EMODE, int MINB, int MAXPASS>
 __global__ void __launch_bounds__(TC_THREADS, MINB)
 rowgemm_tc_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, int bT, long long M, int N, int K,
-                  const Epilogue E, int num_tiles, int tmem_cols) {
+                  const Epilogue E, int num_tiles, int tmem_cols, int KC, int NtMax) {
   extern __shared__ __align__(128) unsigned char smem[];
-  constexpr bool kStage = (EMODE != EPI_EDGE_SCATTER) || true;
-  const TcSmem sp = tc_smem_plan(K, N, kStage);
+  const TcSmem sp = tc_smem_plan(KC, NtMax, true);
   unsigned char* sBhi = smem + sp.off_bhi;
   unsigned char* sBlo = smem + sp.off_blo;
   unsigned char* sAhi = smem + sp.off_ahi;
@@ -202,46 +205,50 @@ rowgemm_tc_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + sp.off_misc + 16);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int Kp = sp.Kp, k8n = Kp / 8;
+  const int k8c = sp.Kp / 8;                      // channel groups per chunk
+  const int nkc = (K + KC - 1) / KC;
+  const int n0 = (gridDim.y > 1) ? blockIdx.y * NtMax : 0;
+  const int Nt = (N - n0 < NtMax) ? (N - n0) : NtMax;
+  const int Ntp = (Nt + 15) / 16 * 16;
+  const bool resident_w = (nkc == 1);
 
-  // ---- one-time: TMEM, barrier, weights ------------------------------------------------------------
   if (warp == 0) tc_alloc(tmem_slot, (uint32_t)tmem_cols);
   if (tid == 32) {
     mbar_init(mma_bar, 1);
     mbar_fence_init();
   }
-  // weights: element (n, k) of Bm^T -> group k/8, row n, slot k%8 ; zero padded
-  for (int e = tid; e < sp.Npad * k8n; e += TC_THREADS) {
-    const int n = e % sp.Npad, g = e / sp.Npad;
-    float w[8];
+  // weights of chunk kc: element (n, k) of Bm^T -> group (k - kc*KC)/8, row n, slot k%8 ; zero padded
+  auto load_w = [&](int kc) {
+    for (int e = tid; e < sp.Npad * k8c; e += TC_THREADS) {
+      const int n = e % sp.Npad, g = e / sp.Npad;
+      float w[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int k = g * 8 + i;
-      w[i] = (n < N && k < K) ? (bT ? Bm[(long long)n * ldb + k] : Bm[(long long)k * ldb + n]) : 0.f;
+      for (int i = 0; i < 8; ++i) {
+        const int k = kc * KC + g * 8 + i;
+        w[i] = (n < Nt && k < K) ? (bT ? Bm[(long long)(n0 + n) * ldb + k] : Bm[(long long)k * ldb + n0 + n]) : 0.f;
+      }
+      uint4 hi, lo;
+      split8(w, hi, lo);
+      *reinterpret_cast<uint4*>(sBhi + (size_t)g * sp.b_group_bytes + n * 16) = hi;
+      *reinterpret_cast<uint4*>(sBlo + (size_t)g * sp.b_group_bytes + n * 16) = lo;
     }
-    uint4 hi, lo;
-    split8(w, hi, lo);
-    *reinterpret_cast<uint4*>(sBhi + (size_t)g * sp.b_group_bytes + n * 16) = hi;
-    *reinterpret_cast<uint4*>(sBlo + (size_t)g * sp.b_group_bytes + n * 16) = lo;
-  }
+  };
+  if (resident_w) load_w(0);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t idesc = umma_idesc(sp.Npad);
+  const uint32_t idesc = umma_idesc(Ntp);
 
-  // ---- per-thread loader constants: this thread always handles column group kg = tid % k8n -------------
-  // (TC_THREADS % k8n == 0 is guaranteed by the host: Kp/8 in {2,4,8,16,32,...} dividing 256)
-  const int kg = tid % k8n;
-  const int rstep = TC_THREADS / k8n;        // rows covered per sweep
-  const int r0 = tid / k8n;
-  float pc0[8], pc1[8], pc2[8];              // per-channel constants (sc/sh or c1/c2/c3)
-  const bool kvalid = kg * 8 < K;
-  load_consts<AMODE>(A, kg, K, pc0, pc1, pc2);
+  // this thread always handles channel group kg (within the chunk) of rows r0, r0+rstep, ...
+  const int kg = tid % k8c;
+  const int rstep = TC_THREADS / k8c;
+  const int r0 = tid / k8c;
+  float pc0[8], pc1[8], pc2[8];
+  if (resident_w) load_consts<AMODE>(A, kg, K, pc0, pc1, pc2);
 
-  // epilogue-side per-thread accumulators: this thread always stores columns c4*4..+3 of a 64-col pass
-  const int e_c4 = tid & 15, e_r0 = tid >> 4;     // 16 rows per sweep, 8 sweeps per tile
+  const int e_c4 = tid & 15, e_r0 = tid >> 4;     // epilogue: 4 fixed columns, 16 rows per sweep
   constexpr bool kStats = (EMODE == EPI_STORE_STATS || EMODE == EPI_RELUMASK_STATS);
   double st0[kStats ? MAXPASS : 1][4], st1[kStats ? MAXPASS : 1][4];
   if (kStats) {
@@ -250,60 +257,68 @@ rowgemm_tc_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, 
 #pragma unroll
       for (int j = 0; j < 4; ++j) { st0[p][j] = 0.0; st1[p][j] = 0.0; }
   }
-  const int npass = (N + 63) / 64;
 
   uint32_t phase = 0;
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     const long long row0 = (long long)tile * TILE_M;
-
-    // ---------------------------------------------------------------- 1. A operand -> smem ------
-#pragma unroll 2
-    for (int r = r0; r < TILE_M; r += rstep) {
-      const long long row = row0 + r;
-      float v[8];
-      load_chunk<AMODE>(A, row, kg, row < M && kvalid, pc0, pc1, pc2, v);
-      uint4 hi, lo;
-      split8(v, hi, lo);
-      *reinterpret_cast<uint4*>(sAhi + (size_t)kg * A_GROUP_BYTES + r * 16) = hi;
-      *reinterpret_cast<uint4*>(sAlo + (size_t)kg * A_GROUP_BYTES + r * 16) = lo;
-    }
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-
-    // ---------------------------------------------------------------- 2. MMA issue --------------
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t a_hi = smem_u32(sAhi), a_lo = smem_u32(sAlo), b_hi = smem_u32(sBhi), b_lo = smem_u32(sBlo);
-      uint32_t accum = 0;
-#pragma unroll 1
-      for (int pass = 0; pass < 3; ++pass) {
-        const uint32_t ab = (pass == 1) ? a_lo : a_hi;
-        const uint32_t bb = (pass == 2) ? b_lo : b_hi;
-        for (int kk = 0; kk < Kp / 16; ++kk) {
-          const uint64_t ad = umma_desc(ab + (uint32_t)(2 * kk) * A_GROUP_BYTES, A_GROUP_BYTES, 128);
-          const uint64_t bd = umma_desc(bb + (uint32_t)(2 * kk) * sp.b_group_bytes, sp.b_group_bytes, 128);
-          tc_mma_bf16(tmem_base, ad, bd, idesc, accum);
-          accum = 1;
-        }
+    uint32_t accum = 0;
+    for (int kc = 0; kc < nkc; ++kc) {
+      // ------------------------------------------------------------ 1. operands -> smem ------
+      const int cg = kc * (KC / 8) + kg;            // absolute channel group
+      const bool kvalid = cg * 8 < K;
+      if (!resident_w) {
+        load_w(kc);
+        load_consts<AMODE>(A, cg, K, pc0, pc1, pc2);
       }
-      tc_commit(mma_bar);
+#pragma unroll 2
+      for (int r = r0; r < TILE_M; r += rstep) {
+        const long long row = row0 + r;
+        float v[8];
+        load_chunk<AMODE>(A, row, cg, row < M && kvalid, pc0, pc1, pc2, v);
+        uint4 hi, lo;
+        split8(v, hi, lo);
+        *reinterpret_cast<uint4*>(sAhi + (size_t)kg * A_GROUP_BYTES + r * 16) = hi;
+        *reinterpret_cast<uint4*>(sAlo + (size_t)kg * A_GROUP_BYTES + r * 16) = lo;
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncthreads();
+      // ------------------------------------------------------------ 2. MMA issue --------------
+      if (tid == 0) {
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(sAhi), a_lo = smem_u32(sAlo), b_hi = smem_u32(sBhi), b_lo = smem_u32(sBlo);
+#pragma unroll 1
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t ab = (pass == 1) ? a_lo : a_hi;
+          const uint32_t bb = (pass == 2) ? b_lo : b_hi;
+          for (int kk = 0; kk < sp.Kp / 16; ++kk) {
+            const uint64_t ad = umma_desc(ab + (uint32_t)(2 * kk) * A_GROUP_BYTES, A_GROUP_BYTES, 128);
+            const uint64_t bd = umma_desc(bb + (uint32_t)(2 * kk) * sp.b_group_bytes, sp.b_group_bytes, 128);
+            tc_mma_bf16(tmem_base, ad, bd, idesc, accum);
+            accum = 1;
+          }
+        }
+        tc_commit(mma_bar);
+      }
+      mbar_wait(mma_bar, phase);                    // MMAs of this chunk finished (smem reusable)
+      phase ^= 1;
     }
-    mbar_wait(mma_bar, phase);
-    phase ^= 1;
     tc_fence_after();
 
     // ---------------------------------------------------------------- 3. epilogue ---------------
     const int lq = warp & 3, ch = warp >> 2;        // TMEM lane quadrant / 32-column half of a 64-col pass
     const int trow = lq * 32 + lane;                // tile-local row owned in TMEM
-    for (int p = 0; p < npass; ++p) {
+    const int npass = (Nt + 63) / 64;
+#pragma unroll
+    for (int p = 0; p < MAXPASS; ++p) {
+      if (p >= npass) break;
       float v[32];
       tc_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(p * 64 + ch * 32), v);
+      float* srow = stage + trow * STAGE_LD + ch * 32;
       if (EMODE == EPI_EDGE_SCATTER && p * 64 >= (N >> 1)) {
         // neighbour half [dE_d]: scatter to dx[idx], subtract from the staged centre sum
         const int Cx = N >> 1;
         const long long row = row0 + trow;
-        float* srow = stage + trow * STAGE_LD + ch * 32;
         if (row < M) {
           const long long pt = row / E.k;
           const long long nb = (pt / E.npts) * E.npts + E.idx[row];
@@ -318,13 +333,10 @@ rowgemm_tc_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, 
           *reinterpret_cast<float4*>(srow + i) = c;
         }
       } else {
-        float* srow = stage + trow * STAGE_LD + ch * 32;
 #pragma unroll
         for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(srow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
       }
-      if (EMODE == EPI_EDGE_SCATTER) {
-        if (p + 1 < npass) { __syncwarp(); continue; }   // (Cx == 64: pass 0 = centre part, pass 1 = neighbour part)
-      }
+      if (EMODE == EPI_EDGE_SCATTER && p + 1 < npass) { __syncwarp(); continue; }   // pass 0 = centre, pass 1 = neighbour
       __syncthreads();
       if (EMODE == EPI_EDGE_SCATTER) {
         // centre reduction: rows of one point are consecutive; thread = (column, quarter of the rows)
@@ -344,19 +356,17 @@ rowgemm_tc_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, 
         }
         if (cur >= 0) atomicAdd(E.dx + cur * E.lddx + col, acc);
       } else {
-        const int cbase = p * 64 + e_c4 * 4;
-        if (cbase < N) {
-          float bias[4] = {0.f, 0.f, 0.f, 0.f}, scp[4], shp[4];
+        const int cl = p * 64 + e_c4 * 4;           // column within this N tile
+        const int cbase = n0 + cl;                  // global column
+        if (cl < Nt) {
+          float bias[4] = {0.f, 0.f, 0.f, 0.f}, scp[4] = {0.f, 0.f, 0.f, 0.f}, shp[4] = {-1.f, -1.f, -1.f, -1.f};
           if ((EMODE == EPI_STORE || EMODE == EPI_STORE_STATS) && E.bias) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) bias[j] = (cbase + j < N) ? E.bias[cbase + j] : 0.f;
+            for (int j = 0; j < 4; ++j) bias[j] = E.bias[cbase + j];
           }
           if (EMODE == EPI_RELUMASK_STATS) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              scp[j] = (cbase + j < N) ? E.scp[cbase + j] : 0.f;
-              shp[j] = (cbase + j < N) ? E.shp[cbase + j] : -1.f;
-            }
+            for (int j = 0; j < 4; ++j) { scp[j] = E.scp[cbase + j]; shp[j] = E.shp[cbase + j]; }
           }
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
@@ -370,7 +380,7 @@ rowgemm_tc_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, 
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 o[j] += bias[j];
-                if (rb && cbase + j < N) o[j] += rb[j];
+                if (rb) o[j] += rb[j];
               }
               if (EMODE == EPI_STORE_STATS) {
 #pragma unroll
@@ -408,16 +418,17 @@ rowgemm_tc_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, 
 
   // ---- flush BN statistics ---------------------------------------------------------------------
   if (kStats) {
-    for (int p = 0; p < npass; ++p) {
+#pragma unroll
+    for (int p = 0; p < MAXPASS; ++p) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         double a = st0[p][j], b = st1[p][j];
         a += __shfl_xor_sync(0xffffffffu, a, 16);   // lanes l and l+16 own the same columns
         b += __shfl_xor_sync(0xffffffffu, b, 16);
-        const int col = p * 64 + e_c4 * 4 + j;
-        if (lane < 16 && col < N) {
-          atomicAdd(E.stats + col, a);
-          atomicAdd(E.stats + N + col, b);
+        const int cl = p * 64 + e_c4 * 4 + j;
+        if (lane < 16 && cl < Nt) {
+          atomicAdd(E.stats + n0 + cl, a);
+          atomicAdd(E.stats + N + n0 + cl, b);
         }
       }
     }
@@ -426,52 +437,74 @@ rowgemm_tc_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, 
   if (warp == 0) tc_dealloc(tmem_base, (uint32_t)tmem_cols);
 }
 
+struct TcPlan {
+  int KC, NtMax, ntiles_n, npass, tmem_cols;
+  size_t smem;
+  bool two;
+};
+TcPlan tc_plan(int N, int K) {
+  TcPlan p;
+  const int Kp = (K + 15) / 16 * 16;
+  p.KC = (K <= 128) ? Kp : 64;
+  const bool chunked = K > 128;
+  p.NtMax = (N <= 256 && !chunked) ? N : (N <= 128 ? N : 128);
+  p.ntiles_n = (N + p.NtMax - 1) / p.NtMax;
+  p.npass = (p.NtMax + 63) / 64;
+  p.tmem_cols = 64;
+  while (p.tmem_cols < p.npass * 64) p.tmem_cols <<= 1;
+  p.smem = tc_smem_plan(p.KC, p.NtMax, true).total;
+  p.two = p.smem <= 110 * 1024;
+  return p;
+}
+
 bool tc_supported(const Operand& A, int amode, const float* Bm, long long M, int N, int K, const Epilogue& E, int emode) {
-  if (K % 8 != 0 || K < 16 || K > 256) return false;
-  const int k8n = ((K + 15) / 16 * 16) / 8;
-  if (TC_THREADS % k8n != 0) return false;
-  if (N % 4 != 0 || N < 16 || N > 256) return false;
+  if (K % 8 != 0 || K < 16) return false;
+  if (N % 4 != 0 || N < 16) return false;
+  const TcPlan pl = tc_plan(N, K);
+  const int k8c = ((pl.KC + 15) / 16 * 16) / 8;
+  if (TC_THREADS % k8c != 0) return false;
+  if (pl.smem > 200 * 1024) return false;
   if (amode == OP_EDGE && ((A.C / 2) % 8 != 0 || (A.ld % 4) != 0)) return false;
   if (amode != OP_DY_SPARSE && (!aligned16(A.p) || (A.ld % 4) != 0)) return false;
   if (amode == OP_DY && A.c1 && (!aligned16(A.y) || (A.ldy % 4) != 0)) return false;
   if (amode == OP_BNRELU && A.dmask && (!aligned16(A.dmask) || (A.C % 4) != 0)) return false;
   if (emode == EPI_EDGE_SCATTER) {
-    if (N != 128 || (E.lddx % 4) != 0 || !aligned16(E.dx)) return false;
+    if (N != 128 || K > 128 || (E.lddx % 4) != 0 || !aligned16(E.dx)) return false;
   } else {
     if (!aligned16(E.out) || (E.ldo % 4) != 0) return false;
     if (emode == EPI_RELUMASK_STATS && (!aligned16(E.yprev) || (E.ldyp % 4) != 0)) return false;
     if (emode == EPI_RELUMASK_STATS && E.dmask && !aligned16(E.dmask)) return false;
+    if ((emode == EPI_STORE || emode == EPI_STORE_STATS) && E.rowbias && ((E.ldrb % 4) != 0 || !aligned16(E.rowbias))) {
+      // row-bias is read per element, alignment is not required; keep for documentation
+    }
   }
-  const TcSmem sp = tc_smem_plan(K, N, true);
-  return sp.total <= 200 * 1024;
+  return true;
 }
 
 template <int AMODE, int EMODE>
 int launch_tc(const Operand& A, const float* Bm, long long ldb, int bT, long long M, int N, int K, const Epilogue& E,
               cudaStream_t st) {
-  const TcSmem sp = tc_smem_plan(K, N, true);
+  const TcPlan pl = tc_plan(N, K);
   const int num_tiles = (int)((M + TILE_M - 1) / TILE_M);
-  const int npass = (N + 63) / 64;
-  int tmem_cols = 64;
-  while (tmem_cols < npass * 64) tmem_cols <<= 1;
-  const bool two = sp.total <= 110 * 1024;
-  const int ctas = two ? 2 * kNumSM : kNumSM;
-  const int grid = num_tiles < ctas ? num_tiles : ctas;
-#define WSPC_TC_LAUNCH(MINB_, NP_)                                                                          \
-  {                                                                                                         \
-    auto kern = rowgemm_tc_kernel<AMODE, EMODE, MINB_, NP_>;                                                \
-    WSPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total));      \
-    kern<<<grid, TC_THREADS, sp.total, st>>>(A, Bm, ldb, bT, M, N, K, E, num_tiles, tmem_cols);             \
+  const int ctas = (pl.two ? 2 * kNumSM : kNumSM);
+  int gx = (ctas + pl.ntiles_n - 1) / pl.ntiles_n;
+  if (gx > num_tiles) gx = num_tiles;
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, pl.ntiles_n);
+#define WSPC_TC_LAUNCH(MINB_, NP_)                                                                             \
+  {                                                                                                            \
+    auto kern = rowgemm_tc_kernel<AMODE, EMODE, MINB_, NP_>;                                                   \
+    WSPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));          \
+    kern<<<grid, TC_THREADS, pl.smem, st>>>(A, Bm, ldb, bT, M, N, K, E, num_tiles, pl.tmem_cols, pl.KC, pl.NtMax); \
   }
-  if (npass <= 1) { if (two) WSPC_TC_LAUNCH(2, 1) else WSPC_TC_LAUNCH(1, 1) }
-  else if (npass <= 2) { if (two) WSPC_TC_LAUNCH(2, 2) else WSPC_TC_LAUNCH(1, 2) }
+  if (pl.npass <= 1) { if (pl.two) WSPC_TC_LAUNCH(2, 1) else WSPC_TC_LAUNCH(1, 1) }
+  else if (pl.npass <= 2) { if (pl.two) WSPC_TC_LAUNCH(2, 2) else WSPC_TC_LAUNCH(1, 2) }
   else WSPC_TC_LAUNCH(1, 4)
 #undef WSPC_TC_LAUNCH
   count_launch();
   WSPC_LAUNCH_CHECK("rowgemm_tc_kernel");
   return WSPC_OK;
 }
-
 
 // ------------------------------------------------------------------ weight gradient on tensor cores ---
 // dW(K1,K2) = sum_rows A(row,:)^T dY(row,:).  The reduction runs over rows, so both operands are "MN-major"
