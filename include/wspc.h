@@ -215,6 +215,12 @@ int wspc_adam_tf(float* p, const float* g, float* m, float* v, long long n, floa
 int wspc_dropout_mask(float* mask, long long n, float keep, uint64_t seed, uint64_t offset, wspc_stream_t stream);
 int wspc_zero(void* ptr, size_t bytes, wspc_stream_t stream);
 
+/* X' = X (T + I) per cloud: point_cloud_transformed = tf.matmul(point_cloud, transform)
+ * (ShapeNet/DGCNN_ShapeNet.py:29) with the identity of transform_nets.py:51 added when add_eye != 0.
+ * X, Xt (B,N,3); T, dT (B,3,3).  bwd: dT[b] = X[b]^T dXt[b]. */
+int wspc_transform_points_fwd(const float* X, const float* T, int B, int N, int add_eye, float* Xt, wspc_stream_t stream);
+int wspc_transform_points_bwd(const float* X, const float* dXt, int B, int N, float* dT, wspc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

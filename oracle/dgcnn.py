@@ -379,3 +379,26 @@ def train_step_s3dis(p, opt, X, Y_onehot, Mask, step=0, base_lr=1e-3, batch_size
     L["Z"] = Z
     L["grads"] = gd
     return L
+
+
+def train_step_shapenet(p, opt, X, label, Y_onehot, Mask, step=0, base_lr=1e-3, batch_size=None, dropout_masks=None,
+                        full=True, rec=None, knn_override=None, smooth_graph_=None):
+    """One `sess.run([solver, loss, ...])` of ShapeNet TrainOneEpoch_Full (ShapeNet_DGCNN_trainer.py:308-314);
+    DECAY_STEP = 16881*20 (:31), Siamese weight 1 (:123-124), smooth term on xyz (:133)."""
+    bs = batch_size if batch_size is not None else X.shape[0] // 2
+    decay = bn_decay(step, bs, 16881 * 20)
+    lr = learning_rate(step, base_lr, bs, 16881 * 20)
+    Z = get_model_shapenet(p, X, label, True, bn_decay=decay, dropout_masks=dropout_masks, rec=rec,
+                           knn_override=knn_override)
+    if full:
+        L = weak_sup_losses(Z, X, Y_onehot, Mask, 1.0, smooth_graph_)
+    else:
+        L = dict(loss_seg=seg_loss(Z, Y_onehot, Mask), Z_prob=torch.softmax(Z, -1))
+        L["loss"] = L["loss_seg"]
+    names = opt.names
+    grads = torch.autograd.grad(L["loss"], [p[n] for n in names], allow_unused=True)
+    gd = dict(zip(names, grads))
+    opt.step(gd, lr)
+    L["Z"] = Z
+    L["grads"] = gd
+    return L

@@ -1,0 +1,92 @@
+"""ShapeNet part-seg DGCNN (T-net + category branch): CUDA engine vs the CPU oracle, same protocol and
+tolerances as tests/test_s3dis_engine_gpu.py.  Reference: ShapeNet/DGCNN_ShapeNet.py:15-113,
+Networks/dgcnn/models/transform_nets.py:10-56, ShapeNet/ShapeNet_DGCNN_trainer.py:85-133."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import dgcnn as od
+from weaksuppointcloudseg_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+@pytest.fixture(scope="module")
+def setup(cuda):
+    from weaksuppointcloudseg_b200.engine_shapenet import ShapeNetEngine
+
+    n_samples, N = 3, 320
+    X, lab, Y, M, _ = syn.shapenet_batch(n_samples, N=N, n_labelled=32, seed=21)
+    B = 2 * n_samples
+    params = od.init_params(od.SHAPENET_LAYERS, seed=8, shapenet=True)
+    rng = np.random.default_rng(2)
+    # a non-identity transform so the T-net path is exercised (the reference starts it at exactly I)
+    params["transform_net1/transform_XYZ/weights"] = rng.normal(0, 0.02, (256, 9)).astype(np.float32)
+    params["transform_net1/transform_XYZ/biases"] = rng.normal(0, 0.05, (9,)).astype(np.float32)
+    masks = [np.floor(0.6 + rng.random((B, N, 256))).astype(np.float32) for _ in range(2)]
+    p = od.to_torch(params)
+    opt = od.AdamTF(p, od.trainable_names(p))
+    rec = {}
+    out = od.train_step_shapenet(p, opt, torch.from_numpy(X), torch.from_numpy(lab), torch.from_numpy(Y),
+                                 torch.from_numpy(M), step=0, dropout_masks=[torch.from_numpy(m) for m in masks], rec=rec)
+    eng = ShapeNetEngine(params, B, N, device=cuda)
+    ov = {f"knn{i}": rec[f"knn{i}/idx"].to(torch.int32).to(cuda) for i in (1, 2, 3)}
+    losses = eng.train_step(torch.from_numpy(X).to(cuda), torch.from_numpy(lab).to(cuda), torch.from_numpy(Y).to(cuda),
+                            torch.from_numpy(M).to(cuda), lr=1e-3, bn_decay=od.bn_decay(0, n_samples, 16881 * 20),
+                            dropout_masks=[torch.from_numpy(m).to(cuda) for m in masks], knn_override=ov)
+    torch.cuda.synchronize()
+    return dict(eng=eng, out=out, rec=rec, p=p, losses=losses.cpu().numpy(), params0=params, X=X)
+
+
+def test_tnet_and_knn0(setup):
+    eng, rec = setup["eng"], setup["rec"]
+    assert np.array_equal(eng.idx[0].cpu().numpy(), rec["knn0/idx"].numpy().astype(np.int32))   # bit-exact
+    T = eng.Tm.cpu().numpy().reshape(-1, 3, 3) + np.eye(3, dtype=np.float32)
+    assert rel(T, rec["transform"].detach().numpy()) <= TOL
+    assert rel(eng.Xt.cpu().numpy(), rec["pct"].detach().numpy()) <= TOL
+
+
+def test_logits_and_losses(setup):
+    eng, out = setup["eng"], setup["out"]
+    assert rel(eng.Z.cpu().numpy(), out["Z"].detach().numpy()) <= TOL
+    for v, n in zip(setup["losses"], ["loss_seg", "loss_siamese", "loss_inexact", "loss_smooth", "loss"]):
+        ref = float(out[n].detach())
+        assert abs(v - ref) <= TOL * abs(ref), (n, v, ref)
+
+
+def test_gradients(setup):
+    eng, out = setup["eng"], setup["out"]
+    got = eng.vs.grads()
+    gmax = max(float(g.abs().max()) for g in out["grads"].values() if g is not None)
+    bad = {}
+    for name, g in out["grads"].items():
+        a, b = got[name].astype(np.float64), g.numpy().astype(np.float64)
+        if np.abs(b).max() < 1e-6 * gmax:
+            assert np.abs(a).max() < 1e-5 * gmax, name
+            continue
+        e = (rel(a, b), np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+        # Every T-net gradient is proportional to the single (B,3,3) tensor dT = X^T dX', which collects the
+        # ReLU / arg-max flip noise of the whole first EdgeConv block, and the FC layers normalise over only
+        # B=6 clouds here: the fp32 oracle itself scatters by 0.7-1 % against its fp64 run on these tensors
+        # (measured; tests/test_kernels_gpu.py pins the kernels themselves to 1e-5).
+        lim = (1e-1, 6e-2) if (name.startswith("transform_net1/") or name.startswith("adj_conv1")) else (5e-2, 1e-2)
+        if e[0] > lim[0] or e[1] > lim[1]:
+            bad[name] = e
+    assert not bad, bad
+
+
+def test_identity_transform_at_init(cuda):
+    """SURVEY §4 invariant 1: with the reference initialisation (W=0, b=0 + eye) the T-net output is exactly I,
+    so X' == X bit-exactly and kNN-1 == kNN-0."""
+    from weaksuppointcloudseg_b200.engine_shapenet import ShapeNetEngine
+    X, lab, Y, M, _ = syn.shapenet_batch(1, N=256, n_labelled=16, seed=5)
+    eng = ShapeNetEngine(od.init_params(od.SHAPENET_LAYERS, seed=1, shapenet=True), 2, 256, device=cuda)
+    eng.forward(torch.from_numpy(X).to(cuda), torch.from_numpy(lab).to(cuda), True, 0.5)
+    assert torch.equal(eng.Xt.cpu(), torch.from_numpy(X))
+    assert torch.equal(eng.idx[0], eng.idx[1])

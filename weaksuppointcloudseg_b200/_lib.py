@@ -148,6 +148,8 @@ _EXTRA_DECLS.update({
     "wspc_dropout_mask": (c_int, [_P, c_longlong, c_float, c_uint64, c_uint64, _P]),
     "wspc_zero": (c_int, [_P, c_size_t, _P]),
     "wspc_set_gemm_path": (c_int, [c_int]),
+    "wspc_transform_points_fwd": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P]),
+    "wspc_transform_points_bwd": (c_int, [_P, _P, c_int, c_int, _P, _P]),
 })
 
 

@@ -19,11 +19,11 @@ void count_launch(int n = 1);
 
 namespace {
 
-constexpr int TM = 128;      // query rows per CTA
+constexpr int TM = 64;       // query rows per CTA (two CTAs per SM overlap GEMM and selection phases)
 constexpr int TN = 128;      // candidate columns per tile
 constexpr int DLD = TN + 4;  // distance-tile leading dimension (floats)
 constexpr int NSTAGE = 3;    // bulk-copy pipeline depth
-constexpr int KNN_THREADS = 512;
+constexpr int KNN_THREADS = TM * 4;   // TM/8 warps; each warp: 8 rows x 128 columns of accumulators
 
 // ------------------------------------------------------------------ prep ---
 // x (B,N,ldx)[coff:coff+D] -> xT (B,Dp,Npad) zero padded, sq (B,Npad):
@@ -146,14 +146,14 @@ __device__ __forceinline__ float dist_value(int flavour, float sqi, float sqj, f
 // ---------------------------------------------------------------- main ------
 // MODE 0: fused top-k (idx/dist out).  MODE 1: write the full adjacency.
 //
-// 512 threads = 16 warps.  GEMM phase: thread (tx = tid%32, ty = tid/32) owns rows {ty*4+i, 64+ty*4+i}
+// TM*4 threads = TM/8 warps.  GEMM phase: thread (tx = tid%32, ty = tid/32) owns rows {ty*4+i, TM/2+ty*4+i}
 // x cols {tx*4+j} (8x4 accumulators, one sequential fmaf chain each).  Selection phase: warp w owns
 // rows w*8..w*8+7; lane l looks at columns {l, l+32, l+64, l+96} of the distance tile.  For each
 // 32-column group the warp ballots "beats the current k-th" per row and inserts the survivors with
 // warp-shuffle insertion; four rows are inserted in lock-step (independent dependency chains, padded
 // with sentinel no-op inserts) so the shuffle/ballot latency of one row hides behind the others.
 template <int KC, int KSLOT, int MODE>
-__global__ void __launch_bounds__(KNN_THREADS, 1)
+__global__ void __launch_bounds__(KNN_THREADS, 2)
 knn_tile_kernel(const float* __restrict__ xT, const float* __restrict__ sq, int N, int Npad, int Dp,
                 int k, int flavour, int32_t* __restrict__ idx_out, float* __restrict__ dist_out,
                 float* __restrict__ adj_out) {
@@ -195,11 +195,11 @@ knn_tile_kernel(const float* __restrict__ xT, const float* __restrict__ sq, int 
   }
   __syncthreads();
 
-  // per-thread row norms (rows ty*4+i and 64+ty*4+i)
+  // per-thread row norms (rows ty*4+i and TM/2+ty*4+i)
   float sqa[8];
   {
     const float4 s0 = *reinterpret_cast<const float4*>(sqb + i0 + ty * 4);
-    const float4 s1 = *reinterpret_cast<const float4*>(sqb + i0 + 64 + ty * 4);
+    const float4 s1 = *reinterpret_cast<const float4*>(sqb + i0 + TM / 2 + ty * 4);
     sqa[0] = s0.x; sqa[1] = s0.y; sqa[2] = s0.z; sqa[3] = s0.w;
     sqa[4] = s1.x; sqa[5] = s1.y; sqa[6] = s1.z; sqa[7] = s1.w;
   }
@@ -236,7 +236,7 @@ knn_tile_kernel(const float* __restrict__ xT, const float* __restrict__ sq, int 
 #pragma unroll(KC < 8 ? KC : 8)
     for (int kk = 0; kk < KC; ++kk) {
       const float4 a0 = *reinterpret_cast<const float4*>(Ap + kk * TM + ty * 4);
-      const float4 a1 = *reinterpret_cast<const float4*>(Ap + kk * TM + 64 + ty * 4);
+      const float4 a1 = *reinterpret_cast<const float4*>(Ap + kk * TM + TM / 2 + ty * 4);
       const float4 b0 = *reinterpret_cast<const float4*>(Bp + kk * TN + tx * 4);
       const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
       const float bv[4] = {b0.x, b0.y, b0.z, b0.w};
@@ -255,7 +255,7 @@ knn_tile_kernel(const float* __restrict__ xT, const float* __restrict__ sq, int 
         __syncthreads();  // every warp has finished scanning the previous distance tile
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int row = (i < 4) ? (ty * 4 + i) : (64 + ty * 4 + i - 4);
+          const int row = (i < 4) ? (ty * 4 + i) : (TM / 2 + ty * 4 + i - 4);
           float4 d0;
           d0.x = dist_value(flavour, sqa[i], sqj[0], acc[i][0]);
           d0.y = dist_value(flavour, sqa[i], sqj[1], acc[i][1]);
@@ -273,7 +273,7 @@ knn_tile_kernel(const float* __restrict__ xT, const float* __restrict__ sq, int 
       } else {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int row = i0 + ((i < 4) ? (ty * 4 + i) : (64 + ty * 4 + i - 4));
+          const int row = i0 + ((i < 4) ? (ty * 4 + i) : (TM / 2 + ty * 4 + i - 4));
           if (row < N) {
             float* orow = adj_out + ((size_t)b * N + row) * N;
 #pragma unroll

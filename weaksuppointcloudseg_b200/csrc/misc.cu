@@ -107,3 +107,72 @@ extern "C" int wspc_zero(void* ptr, size_t bytes, wspc_stream_t stream) {
   if (bytes) WSPC_CUDA(cudaMemsetAsync(ptr, 0, bytes, reinterpret_cast<cudaStream_t>(stream)));
   return WSPC_OK;
 }
+
+// ---- input transform (T-net): X' = X (T + I)    ShapeNet/DGCNN_ShapeNet.py:29, transform_nets.py:51-55 --------
+namespace wspc {
+namespace {
+__global__ void transform_fwd_kernel(const float* __restrict__ X, const float* __restrict__ T, int N, int add_eye,
+                                     float* __restrict__ Xt) {
+  const int b = blockIdx.y;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float t[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) t[i] = T[b * 9 + i] + ((add_eye && (i % 4) == 0) ? 1.f : 0.f);
+  const float* x = X + ((size_t)b * N + n) * 3;
+  float* o = Xt + ((size_t)b * N + n) * 3;
+  const float x0 = x[0], x1 = x[1], x2 = x[2];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) o[j] = fmaf(x2, t[6 + j], fmaf(x1, t[3 + j], x0 * t[j]));   // row-vector times matrix
+}
+
+// dT[b] = X[b]^T dXt[b]  (3x3 per cloud; tf.matmul gradient w.r.t. the second operand)
+__global__ void transform_bwd_kernel(const float* __restrict__ X, const float* __restrict__ dXt, int N,
+                                     float* __restrict__ dT) {
+  __shared__ float red[9][8];
+  const int b = blockIdx.x;
+  float acc[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) acc[i] = 0.f;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const float* x = X + ((size_t)b * N + n) * 3;
+    const float* g = dXt + ((size_t)b * N + n) * 3;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) acc[i * 3 + j] = fmaf(x[i], g[j], acc[i * 3 + j]);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    const float v = warp_sum(acc[i]);
+    if (lane == 0) red[i][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 9) {
+    float s = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[threadIdx.x][w];
+    dT[b * 9 + threadIdx.x] = s;
+  }
+}
+}  // namespace
+}  // namespace wspc
+
+extern "C" int wspc_transform_points_fwd(const float* X, const float* T, int B, int N, int add_eye, float* Xt,
+                                         wspc_stream_t stream) {
+  if (int rc = check_arch()) return rc;
+  WSPC_REQUIRE(X && T && Xt && B >= 1 && N >= 1, "transform_points_fwd: bad argument");
+  transform_fwd_kernel<<<dim3((N + 255) / 256, B), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(X, T, N, add_eye, Xt);
+  count_launch();
+  WSPC_LAUNCH_CHECK("transform_fwd_kernel");
+  return WSPC_OK;
+}
+
+extern "C" int wspc_transform_points_bwd(const float* X, const float* dXt, int B, int N, float* dT, wspc_stream_t stream) {
+  if (int rc = check_arch()) return rc;
+  WSPC_REQUIRE(X && dXt && dT && B >= 1 && N >= 1, "transform_points_bwd: bad argument");
+  transform_bwd_kernel<<<B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(X, dXt, N, dT);
+  count_launch();
+  WSPC_LAUNCH_CHECK("transform_bwd_kernel");
+  return WSPC_OK;
+}
