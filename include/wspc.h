@@ -221,6 +221,37 @@ int wspc_zero(void* ptr, size_t bytes, wspc_stream_t stream);
 int wspc_transform_points_fwd(const float* X, const float* T, int B, int N, int add_eye, float* Xt, wspc_stream_t stream);
 int wspc_transform_points_bwd(const float* X, const float* dXt, int B, int N, float* dT, wspc_stream_t stream);
 
+/* Stand-alone manifold smoothness loss on a kNN graph (Util/SmoothConstraint.py:155-165):
+ * loss = mean_{b,n,r} exp(-dist/gamma) * mean_c (Z[b,n,c] - Z[b,idx[b,n,r],c])^2 ; dZ (zeroed by caller) or NULL. */
+int wspc_smooth_loss(const float* Z, const int32_t* idx, const float* dist, int B, int N, int C, int knn, float gamma,
+                     float* dZ, float* loss, void* workspace, size_t workspace_bytes, wspc_stream_t stream);
+
+/* ------------------------------------------------- test-time label propagation --- */
+/* Lsym = D^-1/2 (diag(d + 1e-8) - W) D^-1/2, W = exp(-scale_xyz d_xyz) * exp(-scale_rgb d_rgb)
+ * (Tool.TF_Computation.LaplacianMatSym_XYZRGB_DirectComp, Util/Tool.py:435-468; scales 1e3 / 1e1).
+ * X (B,N,D1), RGB (B,N,D2), D <= 3; deg_ws (B,N) scratch; Lout (B,N,N). */
+int wspc_laplacian_sym(const float* X, const float* RGB, int B, int N, int D1, int D2, float scale_xyz,
+                       float scale_rgb, float* deg_ws, float* Lout, wspc_stream_t stream);
+/* LabelPropagation_TF.SolveLabelProp (Util/ProbLabelPropagation.py:19-23,38-57):
+ * w = 1 - H_2(G)/log_2 K;  Y = beta (alpha L + beta diag(w) + 1e-5 I)^-1 diag(w) G;  Yprob = Y / sum_k Y.
+ * The SPD system is solved by Jacobi-preconditioned CG on all K right-hand sides (the matvec is
+ * wspc_conv1x1_rows); iteration stops when every column's residual is below tol*||b|| or at max_iter.
+ * EXCEPTION to the no-host-sync rule: convergence is polled on the host every 50 iterations.
+ * L (N,N), G (N,K) -> Y, Yprob (N,K), w (N); N % 8 == 0, 2 <= K <= 64. */
+size_t wspc_lp_solve_workspace_bytes(int N, int K);
+int wspc_lp_solve(const float* L, const float* G, int N, int K, float alpha, float beta, int max_iter, float tol,
+                  float* Y, float* Yprob, float* w, int* iters_out, void* workspace, size_t workspace_bytes,
+                  wspc_stream_t stream);
+
+/* ----------------------------------------------------------- unfused API ops --- */
+/* edge=0: out[b,n,r,:] = X[b, idx[b,n,r], :]            Tool.batch_gather_v1 (Util/Tool.py:72-104)
+ * edge=1: out[b,n,r,:] = [X[b,n,:] | X[b,idx,:]-X[b,n,:]]  tf_util.get_edge_feature (tf_util.py:674-706) */
+int wspc_gather(const float* X, const int32_t* idx, int B, int N, int k, int C, long long ldx, int edge, float* out,
+                wspc_stream_t stream);
+/* out = y*sc + sh (relu optional): tf.nn.batch_normalization with the folded affine of wspc_bn_finalize */
+int wspc_bn_apply(const float* y, const float* sc, const float* sh, long long rows, int C, int relu, float* out,
+                  wspc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

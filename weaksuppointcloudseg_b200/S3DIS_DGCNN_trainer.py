@@ -184,6 +184,50 @@ class S3DIS_Trainer():
         loss = float(l[4]) if (full and self.weak_gate) else float(l[0])
         return loss, zp.copy()
 
+    def defLabelPropSolver(self, alpha=1e0, beta=1e0, K=10):
+        """(:139-143) Define Label Propagation Solver; the reference ignores the arguments too"""
+        from . import ProbLabelPropagation as PLP
+        self.LPSolver = PLP.LabelPropagation_TF(alpha=1e0, beta=1e0, K=10)
+        self.TFComp = {}
+        self.TFComp['Lmat'] = Tool.TF_Computation.LaplacianMatSym_XYZRGB_DirectComp()
+
+    def Test(self, Loader, PRED_PATH=None):
+        """Inference + label propagation over test rooms (Test, :499-584): per block one forward pass
+        (Is_Training=False), the symmetric Laplacian of the block (xyz, rgb) and the closed-form LP solve —
+        all on the device, without the reference's 64 MB D2H/H2D round trip per block.  `Loader` follows
+        S3DIS_Test.LoadNextTestRoomData_v1 (DataIO_S3DIS.py:288-299): returns (flag, blocks (nb,4096,9),
+        labels (nb,4096)).  Returns overall accuracy and per-class IoU with and without LP."""
+        from . import ops
+        eng = self.engine
+        C = eng.C
+        stat = {k: dict(tp=np.zeros(C), fp=np.zeros(C), fn=np.zeros(C)) for k in ('net', 'lp')}
+        while True:
+            out = Loader.LoadNextTestRoomData_v1()
+            if not out[0]:
+                break
+            blocks, labels = np.asarray(out[1], np.float32), np.asarray(out[2]).astype(np.int64)
+            for bi in range(blocks.shape[0]):
+                X = torch.from_numpy(blocks[bi:bi + 1]).to(self.device)
+                Xf = X.expand(eng.B, -1, -1).contiguous()              # graph batch is static, like the reference
+                eng.forward(Xf, False, None)
+                Yz = torch.zeros((eng.B, eng.N, C), device=self.device)
+                eng.losses_and_grad(Yz, torch.ones((eng.B, eng.N), device=self.device), full=False, want_grad=False)
+                G = eng.Zp[0].contiguous()
+                Lm = ops.laplacian_sym(X[:, :, 0:3].contiguous(), X[:, :, 3:6].contiguous())   # (:543)
+                _, Yp, _ = ops.lp_solve(Lm[0], G, 1.0, 1.0)                                   # (:544)
+                for key, prob in (('net', G), ('lp', Yp)):
+                    pred = prob.argmax(-1).cpu().numpy()
+                    gt = labels[bi]
+                    for c in range(C):                                   # vectorised (:552-555)
+                        stat[key]['tp'][c] += np.sum((pred == c) & (gt == c))
+                        stat[key]['fp'][c] += np.sum((pred == c) & (gt != c))
+                        stat[key]['fn'][c] += np.sum((pred != c) & (gt == c))
+        res = {}
+        for key, s in stat.items():
+            iou = s['tp'] / np.maximum(s['tp'] + s['fp'] + s['fn'], 1)
+            res[key] = dict(acc=float(s['tp'].sum() / max((s['tp'] + s['fn']).sum(), 1)), iou=iou, miou=float(iou.mean()))
+        return res
+
     # ------------------------------------------------------------------ epoch loops --------------
     def TrainOneEpoch_Full(self, Loader, pts_idx_list):
         '''

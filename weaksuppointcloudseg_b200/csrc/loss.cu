@@ -328,3 +328,32 @@ extern "C" int wspc_head_losses(const float* Z, const float* Y, const float* Mas
   WSPC_LAUNCH_CHECK("head_finalize_kernel");
   return WSPC_OK;
 }
+
+namespace wspc {
+namespace {
+__global__ void smooth_finish_kernel(const double* __restrict__ acc, double denom, float* __restrict__ loss) {
+  loss[0] = (float)(acc[4] / denom);
+}
+}  // namespace
+}  // namespace wspc
+
+// Stand-alone manifold smoothness term (Util/SmoothConstraint.py:155-165) on a given kNN graph.
+// dP (B,N,C) may be NULL; if given it must be zeroed by the caller and receives d loss / d Z.
+extern "C" int wspc_smooth_loss(const float* Z, const int32_t* idx, const float* dist, int B, int N, int C, int knn,
+                                float gamma, float* dZ, float* loss, void* workspace, size_t workspace_bytes,
+                                wspc_stream_t stream) {
+  if (int rc = check_arch()) return rc;
+  WSPC_REQUIRE(Z && idx && dist && loss && workspace, "smooth_loss: null pointer");
+  WSPC_REQUIRE(C >= 1 && C <= MAXC && knn >= 1, "smooth_loss: bad shape (C <= %d)", MAXC);
+  WSPC_REQUIRE(workspace_bytes >= 64, "smooth_loss: workspace needs 64 bytes");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  double* acc = static_cast<double*>(workspace);
+  WSPC_CUDA(cudaMemsetAsync(acc, 0, 64, st));
+  const long long pts = (long long)B * N;
+  const float gscale = 1.f / (float)((double)C * B * N * knn);
+  smooth_kernel<<<(unsigned)((pts + 7) / 8), 256, 0, st>>>(Z, idx, dist, B, N, C, knn, gamma, gscale, dZ, acc);
+  smooth_finish_kernel<<<1, 1, 0, st>>>(acc, (double)B * N * knn, loss);
+  count_launch(2);
+  WSPC_LAUNCH_CHECK("smooth_kernel");
+  return WSPC_OK;
+}

@@ -63,3 +63,83 @@ def topk_rows(adj: torch.Tensor, k: int, return_vals: bool = False):
     vals = torch.empty(adj.shape[:-1] + (k,), dtype=torch.float32, device=adj.device) if return_vals else None
     L.check(L.lib().wspc_topk_rows(L.ptr(adj), rows, ncols, k, L.ptr(idx), L.ptr(vals), L.stream()))
     return (idx, vals) if return_vals else idx
+
+
+def batch_gather(X: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """Tool.batch_gather_v1 (Util/Tool.py:72-104): X (B,N,D), idx (B,N,k) -> (B,N,k,D)."""
+    X = _as_bnc(X)
+    L.require_cuda(X, idx)
+    B, N, D = X.shape
+    k = idx.shape[-1]
+    idx = idx.to(torch.int32).contiguous()
+    out = torch.empty((B, N, k, D), dtype=torch.float32, device=X.device)
+    L.check(L.lib().wspc_gather(L.ptr(X), L.ptr(idx), B, N, k, D, D, 0, L.ptr(out), L.stream()))
+    return out
+
+
+def get_edge_feature(point_cloud: torch.Tensor, nn_idx: torch.Tensor, k: int = 20) -> torch.Tensor:
+    """tf_util.get_edge_feature (tf_util.py:674-706): (B,N,[1,]C) + (B,N,k) -> (B,N,k,2C) = [x_i | x_j - x_i]."""
+    X = _as_bnc(point_cloud).contiguous()
+    L.require_cuda(X, nn_idx)
+    B, N, C = X.shape
+    idx = nn_idx.to(torch.int32).contiguous()
+    out = torch.empty((B, N, idx.shape[-1], 2 * C), dtype=torch.float32, device=X.device)
+    L.check(L.lib().wspc_gather(L.ptr(X), L.ptr(idx), B, N, idx.shape[-1], C, C, 1, L.ptr(out), L.stream()))
+    return out
+
+
+def smooth_loss(Z: torch.Tensor, X: torch.Tensor, gamma: float = 1e-1, knn: int = 10, want_grad: bool = False):
+    """SmoothConstraint.Loss_SpatialColorSmooth_add_SelfContain (Util/SmoothConstraint.py:130-167)."""
+    Z, X = _as_bnc(Z).contiguous(), _as_bnc(X).contiguous()
+    L.require_cuda(Z, X)
+    B, N, C = Z.shape
+    idx, dist = knn_fused(X, knn, DIST_SMOOTH, return_dist=True)
+    loss = torch.empty(1, dtype=torch.float32, device=Z.device)
+    dZ = torch.zeros_like(Z) if want_grad else None
+    ws = L.workspace(256, Z.device, "smooth")
+    L.check(L.lib().wspc_smooth_loss(L.ptr(Z), L.ptr(idx), L.ptr(dist), B, N, C, knn, gamma, L.ptr(dZ), L.ptr(loss),
+                                     L.ptr(ws), ws.numel(), L.stream()))
+    return (loss[0], dZ) if want_grad else loss[0]
+
+
+def laplacian_sym(X, RGB, scale_xyz: float = 1e3, scale_rgb: float = 1e1) -> torch.Tensor:
+    """TF_Computation.LaplacianMatSym_XYZRGB_DirectComp.Eval (Util/Tool.py:435-468): (B,N,3),(B,N,3) -> (B,N,N)."""
+    X = torch.as_tensor(X, dtype=torch.float32)
+    RGB = torch.as_tensor(RGB, dtype=torch.float32)
+    dev = X.device if X.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    X, RGB = X.to(dev).contiguous(), RGB.to(dev).contiguous()
+    B, N, D1 = X.shape
+    D2 = RGB.shape[-1]
+    out = torch.empty((B, N, N), dtype=torch.float32, device=dev)
+    deg = torch.empty((B, N), dtype=torch.float32, device=dev)
+    L.check(L.lib().wspc_laplacian_sym(L.ptr(X), L.ptr(RGB), B, N, D1, D2, scale_xyz, scale_rgb, L.ptr(deg), L.ptr(out),
+                                       L.stream()))
+    return out
+
+
+def lp_solve(Lmat, G, alpha: float = 1.0, beta: float = 1.0, max_iter: int = 3000, tol: float = 1e-6):
+    """LabelPropagation_TF.SolveLabelProp (Util/ProbLabelPropagation.py:44-57): L (N,N), G (N,K) -> Y, Y_prob, w."""
+    import ctypes
+    Lmat = torch.as_tensor(Lmat, dtype=torch.float32)
+    G = torch.as_tensor(G, dtype=torch.float32)
+    dev = Lmat.device if Lmat.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    Lmat, G = Lmat.to(dev).contiguous(), G.to(dev).contiguous()
+    N, K = G.shape
+    pad = (-N) % 8
+    if pad:  # isolated padding nodes (identity rows) keep the system SPD and do not touch the real ones
+        Lp = torch.zeros((N + pad, N + pad), dtype=torch.float32, device=dev)
+        Lp[:N, :N] = Lmat
+        Lp[N:, N:] = torch.eye(pad, device=dev)
+        Gp = torch.full((N + pad, K), 1.0 / K, dtype=torch.float32, device=dev)
+        Gp[:N] = G
+        Y, Yp, w = lp_solve(Lp, Gp, alpha, beta, max_iter, tol)
+        return Y[:N].contiguous(), Yp[:N].contiguous(), w[:N].contiguous()
+    Y = torch.empty((N, K), dtype=torch.float32, device=dev)
+    Yp = torch.empty((N, K), dtype=torch.float32, device=dev)
+    w = torch.empty((N,), dtype=torch.float32, device=dev)
+    ws = L.workspace(L.lib().wspc_lp_solve_workspace_bytes(N, K), dev, "lp")
+    iters = ctypes.c_int(0)
+    L.check(L.lib().wspc_lp_solve(L.ptr(Lmat), L.ptr(G), N, K, alpha, beta, max_iter, tol, L.ptr(Y), L.ptr(Yp), L.ptr(w),
+                                  ctypes.byref(iters), L.ptr(ws), ws.numel(), L.stream()))
+    lp_solve.last_iters = iters.value
+    return Y, Yp, w
