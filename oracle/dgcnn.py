@@ -302,6 +302,7 @@ def smooth_loss(Z_prob, X, gamma=1e-1, knn=10, graph=None):
     """Loss_SpatialColorSmooth_add_SelfContain (Util/SmoothConstraint.py:130-167):
     mean_{b,n,j}( W * mean_c (Z_i - Z_j)^2 ); gradient w.r.t. Z only (X is an input)."""
     idx, W = graph if graph is not None else smooth_graph(X, gamma, knn)
+    knn = idx.shape[-1]
     B, N, C = Z_prob.shape
     gidx = (idx + (torch.arange(B).view(B, 1, 1) * N)).reshape(-1)
     Zt = Z_prob.reshape(B * N, C)[gidx].view(B, N, knn, C)                               # batch_gather_v1, Tool.py:72-104

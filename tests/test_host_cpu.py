@@ -1,0 +1,128 @@
+"""CPU: host-side logic of the drop-in layer — ABI surface, schedules, synthetic loaders' tensor contract,
+vectorised host helpers, data-parallel sharding over gloo (world_size 2)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shared_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "wspc.h")).read()
+    names = sorted(set(re.findall(r"\b(wspc_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 25
+    lib = ctypes.CDLL(os.path.join(ROOT, "weaksuppointcloudseg_b200", "libwspc.so"))
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    lib.wspc_version.restype = ctypes.c_int
+    assert lib.wspc_version() >= 100
+    # workspace queries are pure host functions (no GPU needed)
+    lib.wspc_knn_workspace_bytes.restype = ctypes.c_size_t
+    assert lib.wspc_knn_workspace_bytes(128, 4096, 64) >= 128 * 4096 * 64 * 4
+
+
+def test_compute_entry_points_fail_loudly_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from weaksuppointcloudseg_b200 import ops
+    from weaksuppointcloudseg_b200._lib import WspcError
+    with pytest.raises(WspcError):
+        ops.knn_fused(torch.zeros((1, 64, 3)), 8)          # CPU tensor: no fallback path
+
+
+def test_schedules_match_reference_formulas():
+    from oracle import dgcnn as od
+    from weaksuppointcloudseg_b200.S3DIS_DGCNN_trainer import S3DIS_Trainer
+
+    class FakeVS:
+        step = 0
+
+    class FakeEngine:
+        vs = FakeVS()
+    tr = S3DIS_Trainer.__new__(S3DIS_Trainer)
+    tr.SetLearningRate(1e-3, 14)
+    tr.engine = FakeEngine()
+    for step in (0, 1, 21428, 21429, 50000, 400000, 5_000_000):
+        tr.engine.vs.step = step
+        assert tr.get_learning_rate() == pytest.approx(od.learning_rate(step, 1e-3, 14, 300000))
+        assert tr.get_bn_decay() == pytest.approx(od.bn_decay(step, 14, 300000))
+    tr.engine.vs.step = 10 ** 9
+    assert tr.get_learning_rate() == 1e-5 and tr.get_bn_decay() == 0.99     # clips (:43, :53)
+
+
+def test_synthetic_tensor_contract():
+    from weaksuppointcloudseg_b200 import synthetic as syn
+    X, Y, M, seg = syn.s3dis_batch(3, N=512, n_labelled=40, seed=0)
+    assert X.shape == (6, 512, 9) and Y.shape == (6, 512, 13) and M.shape == (6, 512)
+    assert np.all(M.sum(1) == 40) and np.array_equal(M[0::2], M[1::2]) and np.array_equal(seg[0::2], seg[1::2])
+    assert np.all(Y.sum(-1) == 1) and np.array_equal(Y.argmax(-1), seg)
+    # duplicated points exist (short-block padding)
+    assert len(np.unique(X[0], axis=0)) < 512
+    Xs, lab, Ys, Ms, segs = syn.shapenet_batch(2, N=256, n_labelled=26, seed=1)
+    assert Xs.shape == (4, 256, 3) and lab.shape == (4, 16) and Ys.shape == (4, 256, 50)
+    assert np.all(np.abs(np.linalg.norm(Xs[0::2], axis=-1).max(1) - 1) < 1e-5)      # pc_normalize
+    for b in range(4):
+        lo, hi = syn.CAT_PART_RANGES[int(lab[b].argmax())]
+        assert segs[b].min() >= lo and segs[b].max() < hi
+
+
+def test_tool_helpers_match_reference_loops():
+    from weaksuppointcloudseg_b200 import Tool
+    rng = np.random.default_rng(0)
+    Yl = rng.integers(0, 13, (3, 50))
+    ref = np.zeros((3, 50, 13))
+    for b in range(3):
+        for r in range(50):
+            ref[b, r, Yl[b, r]] = 1                      # Util/Tool.py:14-17
+    assert np.array_equal(Tool.OnehotEncode(Yl, 13), ref)
+    pred = rng.integers(0, 4, (2, 100))
+    gt = rng.integers(0, 4, (2, 100))
+    iou = Tool.IoU(pred, gt, 4)
+    for b in range(2):
+        for k in range(4):
+            inter = np.sum((pred[b] == k) & (gt[b] == k))
+            union = np.sum((pred[b] == k) | (gt[b] == k))
+            assert iou[b, k] == pytest.approx(inter / (union + 1e-6))
+
+
+def test_shard_pairs():
+    from weaksuppointcloudseg_b200.parallel import shard_pairs
+    assert [shard_pairs(512, r, 8) for r in (0, 7)] == [(0, 64), (448, 512)]
+    with pytest.raises(ValueError):
+        shard_pairs(10, 0, 4)
+
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, %r)
+import torch
+from weaksuppointcloudseg_b200.parallel import DataParallel, shard_pairs
+dp = DataParallel(backend="gloo")
+g = torch.full((1000,), float(dp.rank + 1))
+dp.all_reduce(g)
+assert torch.all(g == 3.0), g[:3]
+assert dp.max_over_ranks(float(dp.rank)) == 1.0 and dp.sum_over_ranks(1.0) == 2.0
+flat = torch.arange(10.0) * (dp.rank + 1)
+dp.broadcast_params(flat)
+assert torch.equal(flat, torch.arange(10.0))
+lo, hi = shard_pairs(8, dp.rank, dp.world_size)
+assert (lo, hi) == (4 * dp.rank, 4 * dp.rank + 4)
+dp.barrier(); dp.shutdown()
+print("rank", dp.rank, "ok")
+'''
+
+
+def test_data_parallel_gloo_world_size_2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER % ROOT)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29611", str(script)]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.count("ok") == 2
