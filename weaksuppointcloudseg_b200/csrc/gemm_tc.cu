@@ -179,7 +179,10 @@ __host__ __device__ inline TcSmem tc_smem_plan(int K, int N, bool need_stage) {
   s.off_blo = o; o += (bbytes + 127) / 128 * 128;
   s.off_ahi = o; o += (abytes + 127) / 128 * 128;
   s.off_alo = o; o += (abytes + 127) / 128 * 128;
-  s.off_stage = o; o += need_stage ? (size_t)TILE_M * STAGE_LD * 4 : 0;
+  // the epilogue staging tile aliases the A buffers: A is dead once the tile's MMAs have completed
+  s.off_stage = s.off_ahi;
+  const size_t stage_end = s.off_stage + (need_stage ? (size_t)TILE_M * STAGE_LD * 4 : 0);
+  if (o < stage_end) o = (stage_end + 127) / 128 * 128;
   s.off_misc = o; o += 64;
   s.total = o;
   return s;
@@ -441,6 +444,7 @@ struct TcPlan {
   int KC, NtMax, ntiles_n, npass, tmem_cols;
   size_t smem;
   bool two;
+  int minb;
 };
 TcPlan tc_plan(int N, int K) {
   TcPlan p;
@@ -454,6 +458,9 @@ TcPlan tc_plan(int N, int K) {
   while (p.tmem_cols < p.npass * 64) p.tmem_cols <<= 1;
   p.smem = tc_smem_plan(p.KC, p.NtMax, true).total;
   p.two = p.smem <= 110 * 1024;
+  p.minb = p.smem <= 72 * 1024 ? 3 : (p.two ? 2 : 1);
+  if (p.npass == 2 && p.minb > 2) p.minb = 2;   // matches the instantiations launched below
+  if (p.npass > 2) p.minb = 1;
   return p;
 }
 
@@ -486,7 +493,7 @@ int launch_tc(const Operand& A, const float* Bm, long long ldb, int bT, long lon
               cudaStream_t st) {
   const TcPlan pl = tc_plan(N, K);
   const int num_tiles = (int)((M + TILE_M - 1) / TILE_M);
-  const int ctas = (pl.two ? 2 * kNumSM : kNumSM);
+  const int ctas = pl.minb * kNumSM;
   int gx = (ctas + pl.ntiles_n - 1) / pl.ntiles_n;
   if (gx > num_tiles) gx = num_tiles;
   if (gx < 1) gx = 1;
@@ -497,8 +504,8 @@ int launch_tc(const Operand& A, const float* Bm, long long ldb, int bT, long lon
     WSPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));          \
     kern<<<grid, TC_THREADS, pl.smem, st>>>(A, Bm, ldb, bT, M, N, K, E, num_tiles, pl.tmem_cols, pl.KC, pl.NtMax); \
   }
-  if (pl.npass <= 1) { if (pl.two) WSPC_TC_LAUNCH(2, 1) else WSPC_TC_LAUNCH(1, 1) }
-  else if (pl.npass <= 2) { if (pl.two) WSPC_TC_LAUNCH(2, 2) else WSPC_TC_LAUNCH(1, 2) }
+  if (pl.npass <= 1) { if (pl.minb == 3) WSPC_TC_LAUNCH(3, 1) else if (pl.minb == 2) WSPC_TC_LAUNCH(2, 1) else WSPC_TC_LAUNCH(1, 1) }
+  else if (pl.npass <= 2) { if (pl.minb >= 2) WSPC_TC_LAUNCH(2, 2) else WSPC_TC_LAUNCH(1, 2) }
   else WSPC_TC_LAUNCH(1, 4)
 #undef WSPC_TC_LAUNCH
   count_launch();
