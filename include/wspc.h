@@ -64,6 +64,14 @@ int wspc_knn_fused(const float* x, int B, int N, int ldx, int coff, int D, int k
                    int32_t* idx, float* dist, void* workspace, size_t workspace_bytes,
                    wspc_stream_t stream);
 
+/* Kernel selection for wspc_knn_fused: 0 = auto (16 <= D <= 64, k <= 24: tcgen05 distances with a proven error
+ * margin + exact fp32 re-scoring and a per-row exact fallback; otherwise the CUDA-core kernel), 1 = CUDA-core
+ * kernel only.  Both paths return bit-identical results; returns the previous setting. */
+int wspc_set_knn_path(int path);
+/* Telemetry (synchronises the device): rows of the last tensor-core wspc_knn_fused call on `workspace` that
+ * were recomputed by the exact per-row fallback (margin overflow or error-bound self-check). */
+int wspc_knn_fallback_rows(const void* workspace, int B, int N, int D, int* rows_out);
+
 /* Unfused API-compat pair (same arithmetic): adj (B, N, N) fp32.
  * tf_util.pairwise_distance (tf_util.py:638-657). */
 int wspc_pairwise_distance(const float* x, int B, int N, int ldx, int coff, int D, int flavour,

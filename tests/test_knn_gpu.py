@@ -124,3 +124,28 @@ def test_errors_are_loud(cuda):
         ops.knn_fused(x, 20)  # k > N
     with pytest.raises(WspcError):
         ops.knn_fused(x.cpu(), 4)  # CPU tensor: no fallback
+
+
+@pytest.mark.parametrize("path", [0, 1], ids=["tcgen05+refine", "cuda-core"])
+@pytest.mark.parametrize("B,N,D,kind", [(2, 1024, 64, "relu"), (1, 777, 64, "relu"), (2, 512, 32, "uniform"),
+                                        (2, 640, 64, "grid"), (1, 300, 16, "relu"), (1, 2048, 64, "clustered")])
+def test_wide_feature_knn_both_device_paths(cuda, path, B, N, D, kind):
+    """16 <= D <= 64: tensor-core distances + exact re-scoring must reproduce the oracle bit for bit, including
+    exact ties (grid), duplicated points and tight clusters far from the origin (stress for the error margin)."""
+    from weaksuppointcloudseg_b200 import _lib as L, ops
+
+    rng = np.random.default_rng(99 + N + D)
+    if kind == "clustered":
+        centres = rng.normal(0, 1, (8, D)) * 5 + 20.0
+        x = (centres[rng.integers(0, 8, (B, N))] + rng.normal(0, 0.01, (B, N, D))).astype(np.float32)
+    else:
+        x = _cloud(rng, B, N, D, kind=kind)
+    ref_idx, ref_d = ok.knn(x, 20, 0, return_dist=True)
+    old = L.lib().wspc_set_knn_path(path)
+    try:
+        idx, dist = ops.knn_fused(torch.from_numpy(x).to(cuda), 20, 0, return_dist=True)
+        torch.cuda.synchronize()
+    finally:
+        L.lib().wspc_set_knn_path(old)
+    assert np.array_equal(idx.cpu().numpy(), ref_idx)
+    assert np.array_equal(dist.cpu().numpy(), ref_d)

@@ -102,12 +102,18 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 
 // Loads the 8 channels [kg*8, kg*8+8) of logical row `row` of an operand (zeros if !valid).
 // pc0..2 hold the thread's per-channel constants (BNRELU: sc, sh; DY: c1, c2, c3).
+// `generic` selects the element-wise loader of operand.cuh (any alignment, any channel count).
 template <int AMODE>
 __device__ __forceinline__ void load_chunk(const Operand& A, long long row, int kg, bool valid, const float (&pc0)[8],
-                                           const float (&pc1)[8], const float (&pc2)[8], float (&v)[8]) {
+                                           const float (&pc1)[8], const float (&pc2)[8], float (&v)[8],
+                                           bool generic = false) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = 0.f;
   if (!valid) return;
+  if (generic) {
+    load8<AMODE>(A, row, kg * 8, v);
+    return;
+  }
   if (AMODE == OP_PLAIN) {
     ld8(A.p + row * A.ld + kg * 8, v);
   } else if (AMODE == OP_BNRELU) {
@@ -196,7 +202,7 @@ __host__ __device__ inline TcSmem tc_smem_plan(int K, int N, bool need_stage) {
 template <int AMODE, int EMODE, int MINB, int MAXPASS>
 __global__ void __launch_bounds__(TC_THREADS, MINB)
 rowgemm_tc_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, int bT, long long M, int N, int K,
-                  const Epilogue E, int num_tiles, int tmem_cols, int KC, int NtMax) {
+                  const Epilogue E, int num_tiles, int tmem_cols, int KC, int NtMax, int generic) {
   extern __shared__ __align__(128) unsigned char smem[];
   const TcSmem sp = tc_smem_plan(KC, NtMax, true);
   unsigned char* sBhi = smem + sp.off_bhi;
@@ -277,7 +283,7 @@ rowgemm_tc_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, 
       for (int r = r0; r < TILE_M; r += rstep) {
         const long long row = row0 + r;
         float v[8];
-        load_chunk<AMODE>(A, row, cg, row < M && kvalid, pc0, pc1, pc2, v);
+        load_chunk<AMODE>(A, row, cg, row < M && kvalid, pc0, pc1, pc2, v, generic != 0);
         uint4 hi, lo;
         split8(v, hi, lo);
         *reinterpret_cast<uint4*>(sAhi + (size_t)kg * A_GROUP_BYTES + r * 16) = hi;
@@ -464,26 +470,30 @@ TcPlan tc_plan(int N, int K) {
   return p;
 }
 
+// aligned fast path for the A operand? (otherwise the element-wise loader is used inside the same kernel)
+bool tc_operand_fast(const Operand& A, int amode, int K) {
+  if (K % 8 != 0) return false;
+  if (amode == OP_DY_SPARSE) return true;   // always element-wise inside load_chunk
+  if (!aligned16(A.p) || (A.ld % 4) != 0) return false;
+  if (amode == OP_EDGE && (A.C / 2) % 8 != 0) return false;
+  if (amode == OP_DY && A.c1 && (!aligned16(A.y) || (A.ldy % 4) != 0)) return false;
+  if (amode == OP_BNRELU && A.dmask && (!aligned16(A.dmask) || (A.C % 4) != 0)) return false;
+  return true;
+}
+
 bool tc_supported(const Operand& A, int amode, const float* Bm, long long M, int N, int K, const Epilogue& E, int emode) {
-  if (K % 8 != 0 || K < 16) return false;
+  if (K < 12) return false;
   if (N % 4 != 0 || N < 16) return false;
   const TcPlan pl = tc_plan(N, K);
   const int k8c = ((pl.KC + 15) / 16 * 16) / 8;
   if (TC_THREADS % k8c != 0) return false;
   if (pl.smem > 200 * 1024) return false;
-  if (amode == OP_EDGE && ((A.C / 2) % 8 != 0 || (A.ld % 4) != 0)) return false;
-  if (amode != OP_DY_SPARSE && (!aligned16(A.p) || (A.ld % 4) != 0)) return false;
-  if (amode == OP_DY && A.c1 && (!aligned16(A.y) || (A.ldy % 4) != 0)) return false;
-  if (amode == OP_BNRELU && A.dmask && (!aligned16(A.dmask) || (A.C % 4) != 0)) return false;
   if (emode == EPI_EDGE_SCATTER) {
     if (N != 128 || K > 128 || (E.lddx % 4) != 0 || !aligned16(E.dx)) return false;
   } else {
     if (!aligned16(E.out) || (E.ldo % 4) != 0) return false;
     if (emode == EPI_RELUMASK_STATS && (!aligned16(E.yprev) || (E.ldyp % 4) != 0)) return false;
     if (emode == EPI_RELUMASK_STATS && E.dmask && !aligned16(E.dmask)) return false;
-    if ((emode == EPI_STORE || emode == EPI_STORE_STATS) && E.rowbias && ((E.ldrb % 4) != 0 || !aligned16(E.rowbias))) {
-      // row-bias is read per element, alignment is not required; keep for documentation
-    }
   }
   return true;
 }
@@ -492,6 +502,7 @@ template <int AMODE, int EMODE>
 int launch_tc(const Operand& A, const float* Bm, long long ldb, int bT, long long M, int N, int K, const Epilogue& E,
               cudaStream_t st) {
   const TcPlan pl = tc_plan(N, K);
+  const int generic = tc_operand_fast(A, AMODE, K) ? 0 : 1;
   const int num_tiles = (int)((M + TILE_M - 1) / TILE_M);
   const int ctas = pl.minb * kNumSM;
   int gx = (ctas + pl.ntiles_n - 1) / pl.ntiles_n;
@@ -502,7 +513,7 @@ int launch_tc(const Operand& A, const float* Bm, long long ldb, int bT, long lon
   {                                                                                                            \
     auto kern = rowgemm_tc_kernel<AMODE, EMODE, MINB_, NP_>;                                                   \
     WSPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));          \
-    kern<<<grid, TC_THREADS, pl.smem, st>>>(A, Bm, ldb, bT, M, N, K, E, num_tiles, pl.tmem_cols, pl.KC, pl.NtMax); \
+    kern<<<grid, TC_THREADS, pl.smem, st>>>(A, Bm, ldb, bT, M, N, K, E, num_tiles, pl.tmem_cols, pl.KC, pl.NtMax, generic); \
   }
   if (pl.npass <= 1) { if (pl.minb == 3) WSPC_TC_LAUNCH(3, 1) else if (pl.minb == 2) WSPC_TC_LAUNCH(2, 1) else WSPC_TC_LAUNCH(1, 1) }
   else if (pl.npass <= 2) { if (pl.minb >= 2) WSPC_TC_LAUNCH(2, 2) else WSPC_TC_LAUNCH(1, 2) }
@@ -527,7 +538,7 @@ __device__ __forceinline__ uint32_t umma_idesc_mn(int N) {
 template <int AMODE, int GMODE, int MINB>
 __global__ void __launch_bounds__(TC_THREADS, MINB)
 colgemm_tc_kernel(const Operand A, const Operand G, long long M, long long rows_per_slab, int K1p, int K2p, int K2t,
-                  float* __restrict__ partial, float* __restrict__ partial_b, int tmem_cols) {
+                  float* __restrict__ partial, float* __restrict__ partial_b, int tmem_cols, int genA, int genG) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int gGroups = K2t / 8;                         // power of two, <= 32
   unsigned char* sAhi = smem;
@@ -574,7 +585,7 @@ colgemm_tc_kernel(const Operand A, const Operand G, long long M, long long rows_
     for (int r = rA0; r < TILE_M; r += 16) {
       const long long row = rb + r;
       float v[8];
-      load_chunk<AMODE>(A, row, cA, vA && row < r_end, a0, a1, a2, v);
+      load_chunk<AMODE>(A, row, cA, vA && row < r_end, a0, a1, a2, v, genA != 0);
       uint4 hi, lo;
       split8(v, hi, lo);
       *reinterpret_cast<uint4*>(sAhi + (size_t)gA * A_GROUP_BYTES + r * 16) = hi;
@@ -584,7 +595,7 @@ colgemm_tc_kernel(const Operand A, const Operand G, long long M, long long rows_
     for (int r = rG0; r < TILE_M; r += rGstep) {
       const long long row = rb + r;
       float v[8];
-      load_chunk<GMODE>(G, row, cG, vG && row < r_end, g0, g1, g2, v);
+      load_chunk<GMODE>(G, row, cG, vG && row < r_end, g0, g1, g2, v, genG != 0);
 #pragma unroll
       for (int i = 0; i < 8; ++i) bsum[i] += (double)v[i];
       uint4 hi, lo;
@@ -651,18 +662,14 @@ colgemm_tc_kernel(const Operand A, const Operand G, long long M, long long rows_
 bool wgrad_tc_supported(const Operand& A, int amode, const Operand& G, int gmode) {
   if (amode != OP_PLAIN && amode != OP_BNRELU && amode != OP_EDGE) return false;
   if (gmode != OP_DY && gmode != OP_DY_SPARSE) return false;
-  if (A.C % 8 != 0 || G.C % 8 != 0 || A.C < 16 || G.C < 16) return false;
-  if (!aligned16(A.p) || (A.ld % 4) != 0) return false;
-  if (amode == OP_EDGE && ((A.C / 2) % 8) != 0) return false;
-  if (amode == OP_BNRELU && A.dmask && (!aligned16(A.dmask) || (A.C % 4) != 0)) return false;
-  if (gmode == OP_DY && (!aligned16(G.p) || (G.ld % 4) != 0)) return false;
-  if (gmode == OP_DY && G.c1 && (!aligned16(G.y) || (G.ldy % 4) != 0)) return false;
+  if (A.C < 12 || G.C < 12) return false;
   return true;
 }
 
 template <int AMODE, int GMODE>
 int launch_wgrad_tc(const Operand& A, const Operand& G, long long M, int S, int K1p, int K2p, float* partial,
                     float* partial_b, cudaStream_t st) {
+  const int genA = tc_operand_fast(A, AMODE, A.C) ? 0 : 1, genG = tc_operand_fast(G, GMODE, G.C) ? 0 : 1;
   const int t1 = (A.C + TILE_M - 1) / TILE_M, t2 = (G.C + 255) / 256;
   int K2t = 16;
   const int k2max = G.C < 256 ? G.C : 256;
@@ -676,11 +683,11 @@ int launch_wgrad_tc(const Operand& A, const Operand& G, long long M, int S, int 
   if (smem <= 110 * 1024) {
     auto kern = colgemm_tc_kernel<AMODE, GMODE, 2>;
     WSPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, TC_THREADS, smem, st>>>(A, G, M, rps, K1p, K2p, K2t, partial, partial_b, tmem_cols);
+    kern<<<grid, TC_THREADS, smem, st>>>(A, G, M, rps, K1p, K2p, K2t, partial, partial_b, tmem_cols, genA, genG);
   } else {
     auto kern = colgemm_tc_kernel<AMODE, GMODE, 1>;
     WSPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, TC_THREADS, smem, st>>>(A, G, M, rps, K1p, K2p, K2t, partial, partial_b, tmem_cols);
+    kern<<<grid, TC_THREADS, smem, st>>>(A, G, M, rps, K1p, K2p, K2t, partial, partial_b, tmem_cols, genA, genG);
   }
   count_launch();
   WSPC_LAUNCH_CHECK("colgemm_tc_kernel");

@@ -16,6 +16,12 @@
 
 namespace wspc {
 void count_launch(int n = 1);
+bool knn_tc_eligible(int D, int k);
+size_t knn_tc_workspace_bytes(int B, int N, int D);
+int knn_tc_run(const float* x, int B, int N, int ldx, int coff, int D, int k, int flavour, int32_t* idx, float* dist,
+               void* ws, size_t ws_bytes, cudaStream_t st);
+int knn_tc_fallback_rows(const void* ws, int B, int N, int D, int* out);
+static int g_knn_path = 0;   // 0 = auto (tcgen05 distances + exact re-scoring for wide features), 1 = CUDA-core kernel only
 
 namespace {
 
@@ -455,7 +461,21 @@ using namespace wspc;
 extern "C" size_t wspc_knn_workspace_bytes(int B, int N, int D) {
   if (B < 1 || N < 1 || D < 1 || D > 128) return 0;
   const KnnPlan p = make_plan(B, N, D);
-  return p.xT_bytes + p.sq_bytes;
+  const size_t exact = p.xT_bytes + p.sq_bytes;
+  const size_t tc = knn_tc_eligible(D, 1) ? knn_tc_workspace_bytes(B, N, D) : 0;
+  return exact > tc ? exact : tc;
+}
+
+extern "C" int wspc_knn_fallback_rows(const void* workspace, int B, int N, int D, int* rows_out) {
+  WSPC_REQUIRE(workspace && rows_out, "knn_fallback_rows: null pointer");
+  if (!knn_tc_eligible(D, 1) || g_knn_path != 0) { *rows_out = 0; return WSPC_OK; }
+  return knn_tc_fallback_rows(workspace, B, N, D, rows_out);
+}
+
+extern "C" int wspc_set_knn_path(int path) {
+  const int old = wspc::g_knn_path;
+  wspc::g_knn_path = path;
+  return old;
 }
 
 extern "C" int wspc_knn_fused(const float* x, int B, int N, int ldx, int coff, int D, int k, int flavour,
@@ -466,6 +486,9 @@ extern "C" int wspc_knn_fused(const float* x, int B, int N, int ldx, int coff, i
   WSPC_REQUIRE(idx, "knn_fused: idx is null");
   WSPC_REQUIRE(k >= 1 && k <= 64 && k <= N, "knn_fused: k=%d outside [1,min(64,N=%d)]", k, N);
   WSPC_REQUIRE(flavour == WSPC_DIST_TFUTIL || flavour == WSPC_DIST_SMOOTH, "knn_fused: bad flavour %d", flavour);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (g_knn_path == 0 && knn_tc_eligible(D, k))
+    return knn_tc_run(x, B, N, ldx, coff, D, k, flavour, idx, dist, workspace, workspace_bytes, st);
   const KnnPlan p = make_plan(B, N, D);
   if (workspace_bytes < p.xT_bytes + p.sq_bytes) {
     set_error("knn_fused: workspace %zu < required %zu", workspace_bytes, p.xT_bytes + p.sq_bytes);
@@ -473,7 +496,6 @@ extern "C" int wspc_knn_fused(const float* x, int B, int N, int ldx, int coff, i
   }
   float* xT = static_cast<float*>(workspace);
   float* sq = reinterpret_cast<float*>(static_cast<char*>(workspace) + p.xT_bytes);
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (int rc = run_prep(p, x, B, N, ldx, coff, D, xT, sq, st)) return rc;
   return dispatch_tile<0>(p, B, N, k, flavour, xT, sq, idx, dist, nullptr, st);
 }
