@@ -76,15 +76,18 @@ __device__ __forceinline__ uint32_t umma_idesc(int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
 }
 
+// x = hi + lo with hi, lo in bf16: packed conversions (F2FP.BF16.PACK_AB converts two floats per instruction);
+// a bf16 is the upper half of the fp32 pattern, so the round trip back to fp32 is a shift / mask.
 __device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo) {
   uint32_t h[4], l[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * i] - __bfloat162float(h0));
-    const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(h1));
-    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    const __nv_bfloat162 hp = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    const uint32_t hb = *reinterpret_cast<const uint32_t*>(&hp);
+    const float h0 = __uint_as_float(hb << 16), h1 = __uint_as_float(hb & 0xffff0000u);
+    const __nv_bfloat162 lp = __floats2bfloat162_rn(v[2 * i] - h0, v[2 * i + 1] - h1);
+    h[i] = hb;
+    l[i] = *reinterpret_cast<const uint32_t*>(&lp);
   }
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = make_uint4(l[0], l[1], l[2], l[3]);
@@ -169,11 +172,21 @@ __device__ __forceinline__ void load_consts(const Operand& A, int kg, int K, flo
   }
 }
 
+static bool g_use_ws = false;
+static bool g_use_async = false;   // cp.async double-buffered operand prefetch in rowgemm_tc_kernel   // warp-specialised row GEMM for eligible shapes (toggle for A/B measurements)
+
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
+
 struct TcSmem {
   int Kp, Npad, b_group_bytes;
-  size_t off_bhi, off_blo, off_ahi, off_alo, off_stage, off_misc, total;
+  size_t off_bhi, off_blo, off_ahi, off_alo, off_stage, off_raw, off_misc, total;
 };
-__host__ __device__ inline TcSmem tc_smem_plan(int K, int N, bool need_stage) {
+__host__ __device__ inline TcSmem tc_smem_plan(int K, int N, bool need_stage, int raw_streams = 0) {
   TcSmem s;
   s.Kp = (K + 15) / 16 * 16;
   s.Npad = (N + 15) / 16 * 16;
@@ -189,6 +202,8 @@ __host__ __device__ inline TcSmem tc_smem_plan(int K, int N, bool need_stage) {
   s.off_stage = s.off_ahi;
   const size_t stage_end = s.off_stage + (need_stage ? (size_t)TILE_M * STAGE_LD * 4 : 0);
   if (o < stage_end) o = (stage_end + 127) / 128 * 128;
+  // raw_streams > 0: double-buffered cp.async landing zone, raw_streams x (128 rows x Kp floats) per buffer
+  s.off_raw = o; o += (size_t)2 * raw_streams * TILE_M * s.Kp * 4;
   s.off_misc = o; o += 64;
   s.total = o;
   return s;
@@ -202,9 +217,10 @@ __host__ __device__ inline TcSmem tc_smem_plan(int K, int N, bool need_stage) {
 template <int AMODE, int EMODE, int MINB, int MAXPASS>
 __global__ void __launch_bounds__(TC_THREADS, MINB)
 rowgemm_tc_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, int bT, long long M, int N, int K,
-                  const Epilogue E, int num_tiles, int tmem_cols, int KC, int NtMax, int generic) {
+                  const Epilogue E, int num_tiles, int tmem_cols, int KC, int NtMax, int generic, int raw_streams) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const TcSmem sp = tc_smem_plan(KC, NtMax, true);
+  const TcSmem sp = tc_smem_plan(KC, NtMax, true, raw_streams);
+  float* raw = reinterpret_cast<float*>(smem + sp.off_raw);
   unsigned char* sBhi = smem + sp.off_bhi;
   unsigned char* sBlo = smem + sp.off_blo;
   unsigned char* sAhi = smem + sp.off_ahi;
@@ -267,11 +283,102 @@ rowgemm_tc_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, 
       for (int j = 0; j < 4; ++j) { st0[p][j] = 0.0; st1[p][j] = 0.0; }
   }
 
+  // cp.async prefetch of the NEXT tile's raw operand rows (single-chunk shapes): every thread copies exactly the
+  // 32-byte pieces it will convert itself, so only its own cp.async group has to complete (no extra barrier).
+  const bool use_async = raw_streams > 0;
+  auto raw_ptr = [&](int buf, int q, int r) { return raw + ((size_t)(buf * raw_streams + q) * TILE_M + r) * sp.Kp + kg * 8; };
+  auto issue_async = [&](int tile, int buf) {
+    const long long row0 = (long long)tile * TILE_M;
+    const bool kv = kg * 8 < K;
+    for (int r = r0; r < TILE_M; r += rstep) {
+      const long long row = row0 + r;
+      if (row >= M || !kv) continue;
+      if (AMODE == OP_PLAIN || AMODE == OP_BNRELU || AMODE == OP_DY) {
+        const float* src = A.p + row * A.ld + kg * 8;
+        cp_async16(raw_ptr(buf, 0, r), src);
+        cp_async16(raw_ptr(buf, 0, r) + 4, src + 4);
+        if (AMODE == OP_DY && A.c1) {
+          const float* sy = A.y + row * A.ldy + kg * 8;
+          cp_async16(raw_ptr(buf, 1, r), sy);
+          cp_async16(raw_ptr(buf, 1, r) + 4, sy + 4);
+        }
+      } else if (AMODE == OP_EDGE) {
+        const int Cx = A.C >> 1;
+        if (kg * 8 >= Cx) {
+          const long long pt = row / A.k;
+          const long long nb = (pt / A.npts) * A.npts + A.idx[row];
+          const float* src = A.p + nb * A.ld + kg * 8 - Cx;
+          cp_async16(raw_ptr(buf, 0, r), src);
+          cp_async16(raw_ptr(buf, 0, r) + 4, src + 4);
+        }
+      }
+    }
+    cp_async_commit();
+  };
+  auto convert_async = [&](int tile, int buf) {
+    const long long row0 = (long long)tile * TILE_M;
+    const bool kv = kg * 8 < K;
+#pragma unroll 2
+    for (int r = r0; r < TILE_M; r += rstep) {
+      const long long row = row0 + r;
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = 0.f;
+      if (row < M && kv) {
+        float a[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = 0.f;
+        if (AMODE != OP_EDGE || kg * 8 >= (A.C >> 1)) ld8(raw_ptr(buf, 0, r), a);
+        if (AMODE == OP_PLAIN) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = a[i];
+        } else if (AMODE == OP_BNRELU) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = fmaxf(fmaf(a[i], pc0[i], pc1[i]), 0.f);
+          if (A.dmask) {
+            float m[8];
+            ld8(A.dmask + row * A.C + kg * 8, m);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] *= m[i] * A.dscale;
+          }
+        } else if (AMODE == OP_DY) {
+          if (A.c1) {
+            float y[8];
+            ld8(raw_ptr(buf, 1, r), y);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = fmaf(pc0[i], a[i], fmaf(pc2[i], y[i], pc1[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = a[i];
+          }
+        } else if (AMODE == OP_EDGE) {
+          const int Cx = A.C >> 1;
+          const long long pt = row / A.k;
+          if (kg * 8 < Cx) {
+            ld8(A.p + pt * A.ld + kg * 8, v);
+          } else {
+            float xi[8];
+            ld8(A.p + pt * A.ld + kg * 8 - Cx, xi);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = a[i] - xi[i];
+          }
+        }
+      }
+      uint4 hi, lo;
+      split8(v, hi, lo);
+      *reinterpret_cast<uint4*>(sAhi + (size_t)kg * A_GROUP_BYTES + r * 16) = hi;
+      *reinterpret_cast<uint4*>(sAlo + (size_t)kg * A_GROUP_BYTES + r * 16) = lo;
+    }
+  };
+  if (use_async && (int)blockIdx.x < num_tiles) issue_async(blockIdx.x, 0);
+
   uint32_t phase = 0;
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+  int titer = 0;
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++titer) {
     const long long row0 = (long long)tile * TILE_M;
     uint32_t accum = 0;
     for (int kc = 0; kc < nkc; ++kc) {
+
       // ------------------------------------------------------------ 1. operands -> smem ------
       const int cg = kc * (KC / 8) + kg;            // absolute channel group
       const bool kvalid = cg * 8 < K;
@@ -279,7 +386,13 @@ rowgemm_tc_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, 
         load_w(kc);
         load_consts<AMODE>(A, cg, K, pc0, pc1, pc2);
       }
-#pragma unroll 2
+      if (use_async) {
+        const int nxt = tile + gridDim.x;
+        if (nxt < num_tiles) { issue_async(nxt, (titer + 1) & 1); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        convert_async(tile, titer & 1);
+      } else
+#pragma unroll 4
       for (int r = r0; r < TILE_M; r += rstep) {
         const long long row = row0 + r;
         float v[8];
@@ -377,6 +490,7 @@ rowgemm_tc_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, 
 #pragma unroll
             for (int j = 0; j < 4; ++j) { scp[j] = E.scp[cbase + j]; shp[j] = E.shp[cbase + j]; }
           }
+          float f0[4] = {0.f, 0.f, 0.f, 0.f}, f1[4] = {0.f, 0.f, 0.f, 0.f};   // fp32 partials of this tile (8 rows)
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int r = e_r0 + 16 * it;
@@ -393,7 +507,7 @@ rowgemm_tc_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, 
               }
               if (EMODE == EPI_STORE_STATS) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) { st0[p][j] += (double)o[j]; st1[p][j] += (double)o[j] * (double)o[j]; }
+                for (int j = 0; j < 4; ++j) { f0[j] += o[j]; f1[j] = fmaf(o[j], o[j], f1[j]); }
               }
             } else if (EMODE == EPI_RELUMASK_STATS) {
               const float4 y4 = *reinterpret_cast<const float4*>(E.yprev + row * E.ldyp + cbase);
@@ -407,14 +521,18 @@ rowgemm_tc_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, 
               for (int j = 0; j < 4; ++j) {
                 const bool on = fmaf(yv[j], scp[j], shp[j]) > 0.f;
                 o[j] = on ? o[j] * dm[j] : 0.f;
-                st0[p][j] += (double)o[j];
-                st1[p][j] += (double)o[j] * (double)yv[j];
+                f0[j] += o[j];
+                f1[j] = fmaf(o[j], yv[j], f1[j]);
               }
             } else if (EMODE == EPI_ACCUM) {
               const float4 c4 = *reinterpret_cast<const float4*>(E.out + row * E.ldo + cbase);
               o[0] += c4.x; o[1] += c4.y; o[2] += c4.z; o[3] += c4.w;
             }
             *reinterpret_cast<float4*>(E.out + row * E.ldo + cbase) = make_float4(o[0], o[1], o[2], o[3]);
+          }
+          if (kStats) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { st0[p][j] += (double)f0[j]; st1[p][j] += (double)f1[j]; }
           }
         }
       }
@@ -446,13 +564,303 @@ rowgemm_tc_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, 
   if (warp == 0) tc_dealloc(tmem_base, (uint32_t)tmem_cols);
 }
 
+// ------------------------------------------------------------------ warp-specialised variant ---
+// Same math as rowgemm_tc_kernel for the single-chunk shapes (K <= 128, N <= 128: every EdgeConv layer), but the
+// three phases of a tile run concurrently on different warps of one persistent CTA per SM:
+//   warps 0-7   producers : synthesise + split the A tile into a 2-stage shared-memory ring        (full[s] / empty[s])
+//   warp  12    MMA issuer: tcgen05.mma into one of two TMEM accumulators, tcgen05.commit          (acc_full[a] / acc_empty[a])
+//   warps 8-11  epilogue  : tcgen05.ld -> private staging tile -> coalesced global stores / statistics / scatter
+// so global-load latency, the tensor core and the HBM write-back overlap tile by tile instead of alternating.
+constexpr int WS_PRODUCERS = 256;
+constexpr int WS_EPILOGUE = 128;
+constexpr int WS_THREADS = WS_PRODUCERS + WS_EPILOGUE + 32;
+constexpr int WS_STAGES = 2;
+
+struct WsSmem {
+  int Kp, Npad, b_group_bytes;
+  size_t a_stage_bytes, off_b, off_a, off_stage, off_misc, total;
+};
+__host__ __device__ inline WsSmem ws_smem_plan(int K, int N) {
+  WsSmem w;
+  w.Kp = (K + 15) / 16 * 16;
+  w.Npad = (N + 15) / 16 * 16;
+  w.b_group_bytes = w.Npad * 16 + 16;
+  const size_t bbytes = ((size_t)2 * (w.Kp / 8) * w.b_group_bytes + 127) / 128 * 128;
+  w.a_stage_bytes = ((size_t)2 * (w.Kp / 8) * A_GROUP_BYTES + 127) / 128 * 128;
+  w.off_b = 0;
+  w.off_a = bbytes;
+  w.off_stage = w.off_a + WS_STAGES * w.a_stage_bytes;
+  w.off_misc = w.off_stage + (size_t)TILE_M * STAGE_LD * 4;
+  w.total = w.off_misc + 128;
+  return w;
+}
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+template <int AMODE, int EMODE, int MAXPASS>
+__global__ void __launch_bounds__(WS_THREADS, 1)
+rowgemm_ws_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, int bT, long long M, int N, int K,
+                  const Epilogue E, int num_tiles, int tmem_cols, int generic) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const WsSmem sp = ws_smem_plan(K, N);
+  const int ngrp = sp.Kp / 8;
+  unsigned char* sBhi = smem + sp.off_b;
+  unsigned char* sBlo = sBhi + (size_t)ngrp * sp.b_group_bytes;
+  float* stage = reinterpret_cast<float*>(smem + sp.off_stage);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sp.off_misc);   // full[2], empty[2], acc_full[2], acc_empty[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* full = bars, *empty = bars + 2, *acc_full = bars + 4, *acc_empty = bars + 6;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (warp == 12) tc_alloc(tmem_slot, (uint32_t)tmem_cols);
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full[i], WS_PRODUCERS);
+      mbar_init(&empty[i], 1);
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], WS_EPILOGUE);
+    }
+    mbar_fence_init();
+  }
+  // split weights, resident for the whole kernel: element (n, k) of Bm^T -> group k/8, row n, slot k%8
+  for (int e = tid; e < sp.Npad * ngrp; e += WS_THREADS) {
+    const int n = e % sp.Npad, g = e / sp.Npad;
+    float w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = g * 8 + i;
+      w[i] = (n < N && k < K) ? (bT ? Bm[(long long)n * ldb + k] : Bm[(long long)k * ldb + n]) : 0.f;
+    }
+    uint4 hi, lo;
+    split8(w, hi, lo);
+    *reinterpret_cast<uint4*>(sBhi + (size_t)g * sp.b_group_bytes + n * 16) = hi;
+    *reinterpret_cast<uint4*>(sBlo + (size_t)g * sp.b_group_bytes + n * 16) = lo;
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int npass = (N + 63) / 64;
+
+  if (warp < 8) {
+    // =============================================================== producers ===
+    const int kg = tid % ngrp, rstep = WS_PRODUCERS / ngrp, r0 = tid / ngrp;
+    const bool kvalid = kg * 8 < K;
+    float pc0[8], pc1[8], pc2[8];
+    load_consts<AMODE>(A, kg, K, pc0, pc1, pc2);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int s = it & 1;
+      mbar_wait(&empty[s], ((it >> 1) & 1) ^ 1);
+      unsigned char* sAhi = smem + sp.off_a + (size_t)s * sp.a_stage_bytes;
+      unsigned char* sAlo = sAhi + (size_t)ngrp * A_GROUP_BYTES;
+      const long long row0 = (long long)tile * TILE_M;
+#pragma unroll 4
+      for (int r = r0; r < TILE_M; r += rstep) {
+        const long long row = row0 + r;
+        float v[8];
+        load_chunk<AMODE>(A, row, kg, row < M && kvalid, pc0, pc1, pc2, v, generic != 0);
+        uint4 hi, lo;
+        split8(v, hi, lo);
+        *reinterpret_cast<uint4*>(sAhi + (size_t)kg * A_GROUP_BYTES + r * 16) = hi;
+        *reinterpret_cast<uint4*>(sAlo + (size_t)kg * A_GROUP_BYTES + r * 16) = lo;
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&full[s]);
+    }
+  } else if (warp == 12) {
+    // =============================================================== MMA issuer ===
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(sp.Npad);
+      const uint32_t b_hi = smem_u32(sBhi), b_lo = smem_u32(sBlo);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int s = it & 1, a = it & 1;
+        mbar_wait(&full[s], (it >> 1) & 1);
+        mbar_wait(&acc_empty[a], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(smem + sp.off_a + (size_t)s * sp.a_stage_bytes);
+        const uint32_t a_lo = a_hi + (uint32_t)ngrp * A_GROUP_BYTES;
+        const uint32_t acc = tmem_base + (uint32_t)a * (uint32_t)(npass * 64);
+        uint32_t accum = 0;
+#pragma unroll 1
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t ab = (pass == 1) ? a_lo : a_hi;
+          const uint32_t bb = (pass == 2) ? b_lo : b_hi;
+          for (int kk = 0; kk < sp.Kp / 16; ++kk) {
+            tc_mma_bf16(acc, umma_desc(ab + (uint32_t)(2 * kk) * A_GROUP_BYTES, A_GROUP_BYTES, 128),
+                        umma_desc(bb + (uint32_t)(2 * kk) * sp.b_group_bytes, sp.b_group_bytes, 128), idesc, accum);
+            accum = 1;
+          }
+        }
+        tc_commit(&empty[s]);       // A stage reusable once these MMAs have read it
+        tc_commit(&acc_full[a]);    // accumulator ready for the epilogue
+      }
+    }
+  } else {
+    // =============================================================== epilogue ===
+    const int et = tid - WS_PRODUCERS;              // 0..127
+    const int q = warp - 8;                         // TMEM lane quadrant
+    const int trow = q * 32 + lane;
+    const int e_c4 = et & 15, e_r0 = et >> 4;       // coalesced pass: 4 fixed columns, 8 rows per sweep
+    constexpr bool kStats = (EMODE == EPI_STORE_STATS || EMODE == EPI_RELUMASK_STATS);
+    double st0[kStats ? MAXPASS : 1][4], st1[kStats ? MAXPASS : 1][4];
+    if (kStats) {
+#pragma unroll
+      for (int p = 0; p < MAXPASS; ++p)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { st0[p][j] = 0.0; st1[p][j] = 0.0; }
+    }
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int a = it & 1;
+      const long long row0 = (long long)tile * TILE_M;
+      mbar_wait(&acc_full[a], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)a * (uint32_t)(npass * 64);
+#pragma unroll
+      for (int p = 0; p < MAXPASS; ++p) {
+        if (p >= npass) break;
+        float* srow = stage + trow * STAGE_LD;
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          float v[32];
+          tc_ld32(acc + (uint32_t)(p * 64 + ch * 32), v);
+          if (EMODE == EPI_EDGE_SCATTER && p * 64 >= (N >> 1)) {
+            const int Cx = N >> 1;
+            const long long row = row0 + trow;
+            if (row < M) {
+              const long long pt = row / E.k;
+              const long long nb = (pt / E.npts) * E.npts + E.idx[row];
+              float* dst = E.dx + nb * E.lddx + (p * 64 - Cx) + ch * 32;
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) red_add_v4(dst + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              float4 c = *reinterpret_cast<float4*>(srow + ch * 32 + i);
+              c.x -= v[i]; c.y -= v[i + 1]; c.z -= v[i + 2]; c.w -= v[i + 3];
+              *reinterpret_cast<float4*>(srow + ch * 32 + i) = c;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+              *reinterpret_cast<float4*>(srow + ch * 32 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          }
+        }
+        if (p == npass - 1) {        // accumulator fully drained: hand it back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(&acc_empty[a]);
+        }
+        if (EMODE == EPI_EDGE_SCATTER && p + 1 < npass) { __syncwarp(); continue; }
+        epi_bar();
+        if (EMODE == EPI_EDGE_SCATTER) {
+          const int col = et & 63, h = et >> 6;
+          long long cur = -1;
+          float accv = 0.f;
+          for (int r = h * 64; r < h * 64 + 64; ++r) {
+            const long long row = row0 + r;
+            if (row >= M) break;
+            const long long pt = row / E.k;
+            if (pt != cur) {
+              if (cur >= 0) atomicAdd(E.dx + cur * E.lddx + col, accv);
+              cur = pt;
+              accv = 0.f;
+            }
+            accv += stage[r * STAGE_LD + col];
+          }
+          if (cur >= 0) atomicAdd(E.dx + cur * E.lddx + col, accv);
+        } else {
+          const int cbase = p * 64 + e_c4 * 4;
+          if (cbase < N) {
+            float bias[4] = {0.f, 0.f, 0.f, 0.f}, scp[4] = {0.f, 0.f, 0.f, 0.f}, shp[4] = {-1.f, -1.f, -1.f, -1.f};
+            if ((EMODE == EPI_STORE || EMODE == EPI_STORE_STATS) && E.bias) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) bias[j] = E.bias[cbase + j];
+            }
+            if (EMODE == EPI_RELUMASK_STATS) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { scp[j] = E.scp[cbase + j]; shp[j] = E.shp[cbase + j]; }
+            }
+            float f0[4] = {0.f, 0.f, 0.f, 0.f}, f1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+            for (int itr = 0; itr < 16; ++itr) {
+              const int r = e_r0 + 8 * itr;
+              const long long row = row0 + r;
+              if (row >= M) break;
+              const float4 s4 = *reinterpret_cast<const float4*>(stage + r * STAGE_LD + p * 0 + e_c4 * 4);
+              float o[4] = {s4.x, s4.y, s4.z, s4.w};
+              if (EMODE == EPI_STORE || EMODE == EPI_STORE_STATS) {
+                const float* rb = E.rowbias ? E.rowbias + (row / E.rb_rows) * E.ldrb + cbase : nullptr;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  o[j] += bias[j];
+                  if (rb) o[j] += rb[j];
+                }
+                if (EMODE == EPI_STORE_STATS) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) { f0[j] += o[j]; f1[j] = fmaf(o[j], o[j], f1[j]); }
+                }
+              } else if (EMODE == EPI_RELUMASK_STATS) {
+                const float4 y4 = *reinterpret_cast<const float4*>(E.yprev + row * E.ldyp + cbase);
+                const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
+                float dm[4] = {1.f, 1.f, 1.f, 1.f};
+                if (E.dmask) {
+                  const float4 m4 = *reinterpret_cast<const float4*>(E.dmask + row * N + cbase);
+                  dm[0] = m4.x * E.dscale; dm[1] = m4.y * E.dscale; dm[2] = m4.z * E.dscale; dm[3] = m4.w * E.dscale;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const bool on = fmaf(yv[j], scp[j], shp[j]) > 0.f;
+                  o[j] = on ? o[j] * dm[j] : 0.f;
+                  f0[j] += o[j];
+                  f1[j] = fmaf(o[j], yv[j], f1[j]);
+                }
+              } else if (EMODE == EPI_ACCUM) {
+                const float4 c4 = *reinterpret_cast<const float4*>(E.out + row * E.ldo + cbase);
+                o[0] += c4.x; o[1] += c4.y; o[2] += c4.z; o[3] += c4.w;
+              }
+              *reinterpret_cast<float4*>(E.out + row * E.ldo + cbase) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+            if (kStats) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { st0[p][j] += (double)f0[j]; st1[p][j] += (double)f1[j]; }
+            }
+          }
+        }
+        epi_bar();     // staging free for the next pass / tile
+      }
+    }
+    if (kStats) {
+#pragma unroll
+      for (int p = 0; p < MAXPASS; ++p) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          double sa = st0[p][j], sb = st1[p][j];
+          sa += __shfl_xor_sync(0xffffffffu, sa, 16);
+          sb += __shfl_xor_sync(0xffffffffu, sb, 16);
+          const int col = p * 64 + e_c4 * 4 + j;
+          if (lane < 16 && col < N) {
+            atomicAdd(E.stats + col, sa);
+            atomicAdd(E.stats + N + col, sb);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) tc_dealloc(tmem_base, (uint32_t)tmem_cols);
+}
+
 struct TcPlan {
-  int KC, NtMax, ntiles_n, npass, tmem_cols;
+  int KC, NtMax, ntiles_n, npass, tmem_cols, raw_streams;
   size_t smem;
   bool two;
   int minb;
 };
-TcPlan tc_plan(int N, int K) {
+TcPlan tc_plan(int N, int K, int want_raw = 0) {
   TcPlan p;
   const int Kp = (K + 15) / 16 * 16;
   p.KC = (K <= 128) ? Kp : 64;
@@ -462,7 +870,9 @@ TcPlan tc_plan(int N, int K) {
   p.npass = (p.NtMax + 63) / 64;
   p.tmem_cols = 64;
   while (p.tmem_cols < p.npass * 64) p.tmem_cols <<= 1;
-  p.smem = tc_smem_plan(p.KC, p.NtMax, true).total;
+  p.raw_streams = (!chunked && p.ntiles_n == 1) ? want_raw : 0;
+  p.smem = tc_smem_plan(p.KC, p.NtMax, true, p.raw_streams).total;
+  if (p.smem > 220 * 1024 && p.raw_streams) { p.raw_streams = 0; p.smem = tc_smem_plan(p.KC, p.NtMax, true, 0).total; }
   p.two = p.smem <= 110 * 1024;
   p.minb = p.smem <= 72 * 1024 ? 3 : (p.two ? 2 : 1);
   if (p.npass == 2 && p.minb > 2) p.minb = 2;   // matches the instantiations launched below
@@ -501,9 +911,36 @@ bool tc_supported(const Operand& A, int amode, const float* Bm, long long M, int
 template <int AMODE, int EMODE>
 int launch_tc(const Operand& A, const float* Bm, long long ldb, int bT, long long M, int N, int K, const Epilogue& E,
               cudaStream_t st) {
-  const TcPlan pl = tc_plan(N, K);
   const int generic = tc_operand_fast(A, AMODE, K) ? 0 : 1;
+  int want_raw = 0;
+  if (!generic && g_use_async && (AMODE == OP_PLAIN || AMODE == OP_BNRELU || AMODE == OP_EDGE)) want_raw = 1;
+  if (!generic && g_use_async && AMODE == OP_DY) want_raw = A.c1 ? 2 : 1;
+  const TcPlan pl = tc_plan(N, K, want_raw);
   const int num_tiles = (int)((M + TILE_M - 1) / TILE_M);
+  // warp-specialised persistent kernel for the single-chunk shapes with enough tiles to stream
+  if (K <= 128 && N <= 128 && ((((K + 15) / 16 * 16) / 8) == 2 || (((K + 15) / 16 * 16) / 8) % 4 == 0) && num_tiles >= 4 &&
+      g_use_ws) {
+    const WsSmem wp = ws_smem_plan(K, N);
+    const int ngrp = wp.Kp / 8;
+    if (wp.total <= 220 * 1024 && WS_PRODUCERS % ngrp == 0) {
+      const int npass = (N + 63) / 64;
+      int tmem_cols = 64;
+      while (tmem_cols < 2 * npass * 64) tmem_cols <<= 1;
+      const int grid = num_tiles < kNumSM ? num_tiles : kNumSM;
+      if (npass == 1) {
+        auto kern = rowgemm_ws_kernel<AMODE, EMODE, 1>;
+        WSPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wp.total));
+        kern<<<grid, WS_THREADS, wp.total, st>>>(A, Bm, ldb, bT, M, N, K, E, num_tiles, tmem_cols, generic);
+      } else {
+        auto kern = rowgemm_ws_kernel<AMODE, EMODE, 2>;
+        WSPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wp.total));
+        kern<<<grid, WS_THREADS, wp.total, st>>>(A, Bm, ldb, bT, M, N, K, E, num_tiles, tmem_cols, generic);
+      }
+      count_launch();
+      WSPC_LAUNCH_CHECK("rowgemm_ws_kernel");
+      return WSPC_OK;
+    }
+  }
   const int ctas = pl.minb * kNumSM;
   int gx = (ctas + pl.ntiles_n - 1) / pl.ntiles_n;
   if (gx > num_tiles) gx = num_tiles;
@@ -513,9 +950,9 @@ int launch_tc(const Operand& A, const float* Bm, long long ldb, int bT, long lon
   {                                                                                                            \
     auto kern = rowgemm_tc_kernel<AMODE, EMODE, MINB_, NP_>;                                                   \
     WSPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));          \
-    kern<<<grid, TC_THREADS, pl.smem, st>>>(A, Bm, ldb, bT, M, N, K, E, num_tiles, pl.tmem_cols, pl.KC, pl.NtMax, generic); \
+    kern<<<grid, TC_THREADS, pl.smem, st>>>(A, Bm, ldb, bT, M, N, K, E, num_tiles, pl.tmem_cols, pl.KC, pl.NtMax, generic, pl.raw_streams); \
   }
-  if (pl.npass <= 1) { if (pl.minb == 3) WSPC_TC_LAUNCH(3, 1) else if (pl.minb == 2) WSPC_TC_LAUNCH(2, 1) else WSPC_TC_LAUNCH(1, 1) }
+  if (pl.npass <= 1) { if (pl.minb == 4) WSPC_TC_LAUNCH(4, 1) else if (pl.minb == 3) WSPC_TC_LAUNCH(3, 1) else if (pl.minb == 2) WSPC_TC_LAUNCH(2, 1) else WSPC_TC_LAUNCH(1, 1) }
   else if (pl.npass <= 2) { if (pl.minb >= 2) WSPC_TC_LAUNCH(2, 2) else WSPC_TC_LAUNCH(1, 2) }
   else WSPC_TC_LAUNCH(1, 4)
 #undef WSPC_TC_LAUNCH
