@@ -577,20 +577,24 @@ constexpr int WS_THREADS = WS_PRODUCERS + WS_EPILOGUE + 32;
 constexpr int WS_STAGES = 2;
 
 struct WsSmem {
-  int Kp, Npad, b_group_bytes;
-  size_t a_stage_bytes, off_b, off_a, off_stage, off_misc, total;
+  int Kp, Npad, b_group_bytes, RS, AS, raw_streams, raw_w;
+  size_t a_stage_bytes, raw_buf_bytes, off_b, off_a, off_stage, off_raw, off_misc, total;
 };
-__host__ __device__ inline WsSmem ws_smem_plan(int K, int N) {
+// RS raw (cp.async landing) buffers x raw_streams x (128 rows x raw_w floats), AS converted A stages
+__host__ __device__ inline WsSmem ws_smem_plan(int K, int N, int RS, int AS, int raw_streams, int raw_w) {
   WsSmem w;
   w.Kp = (K + 15) / 16 * 16;
   w.Npad = (N + 15) / 16 * 16;
   w.b_group_bytes = w.Npad * 16 + 16;
+  w.RS = RS; w.AS = AS; w.raw_streams = raw_streams; w.raw_w = raw_w;
   const size_t bbytes = ((size_t)2 * (w.Kp / 8) * w.b_group_bytes + 127) / 128 * 128;
   w.a_stage_bytes = ((size_t)2 * (w.Kp / 8) * A_GROUP_BYTES + 127) / 128 * 128;
+  w.raw_buf_bytes = (size_t)raw_streams * TILE_M * raw_w * 4;
   w.off_b = 0;
   w.off_a = bbytes;
-  w.off_stage = w.off_a + WS_STAGES * w.a_stage_bytes;
-  w.off_misc = w.off_stage + (size_t)TILE_M * STAGE_LD * 4;
+  w.off_stage = w.off_a + AS * w.a_stage_bytes;
+  w.off_raw = w.off_stage + (size_t)TILE_M * STAGE_LD * 4;
+  w.off_misc = w.off_raw + RS * w.raw_buf_bytes;
   w.total = w.off_misc + 128;
   return w;
 }
@@ -600,9 +604,9 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: 
 template <int AMODE, int EMODE, int MAXPASS>
 __global__ void __launch_bounds__(WS_THREADS, 1)
 rowgemm_ws_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, int bT, long long M, int N, int K,
-                  const Epilogue E, int num_tiles, int tmem_cols, int generic) {
+                  const Epilogue E, int num_tiles, int tmem_cols, int RS, int AS, int raw_streams, int raw_w) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const WsSmem sp = ws_smem_plan(K, N);
+  const WsSmem sp = ws_smem_plan(K, N, RS, AS, raw_streams, raw_w);
   const int ngrp = sp.Kp / 8;
   unsigned char* sBhi = smem + sp.off_b;
   unsigned char* sBlo = sBhi + (size_t)ngrp * sp.b_group_bytes;
@@ -645,22 +649,101 @@ rowgemm_ws_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, 
 
   if (warp < 8) {
     // =============================================================== producers ===
+    // raw operand rows stream in with cp.async (RS-deep ring, prefetch distance RS-1); each thread copies and later
+    // converts exactly its own 32-byte pieces, so only its own cp.async groups need to complete.
     const int kg = tid % ngrp, rstep = WS_PRODUCERS / ngrp, r0 = tid / ngrp;
     const bool kvalid = kg * 8 < K;
+    const int Cx = A.C >> 1;
+    const bool edge_nb = (AMODE == OP_EDGE) && (kg * 8 >= Cx);
+    const int rcol = (AMODE == OP_EDGE) ? (kg * 8 - Cx) : kg * 8;          // column inside a raw row
     float pc0[8], pc1[8], pc2[8];
     load_consts<AMODE>(A, kg, K, pc0, pc1, pc2);
+    float* raw = reinterpret_cast<float*>(smem + sp.off_raw);
+    auto raw_ptr = [&](int buf, int q, int r) {
+      return raw + (size_t)buf * (sp.raw_buf_bytes / 4) + ((size_t)q * TILE_M + r) * raw_w + rcol;
+    };
+    auto issue_async = [&](int tile, int buf) {
+      if (tile < num_tiles && kvalid) {
+        const long long row0 = (long long)tile * TILE_M;
+        for (int r = r0; r < TILE_M; r += rstep) {
+          const long long row = row0 + r;
+          if (row >= M) break;
+          if (AMODE == OP_PLAIN || AMODE == OP_BNRELU || AMODE == OP_DY) {
+            const float* src = A.p + row * A.ld + kg * 8;
+            cp_async16(raw_ptr(buf, 0, r), src);
+            cp_async16(raw_ptr(buf, 0, r) + 4, src + 4);
+            if (AMODE == OP_DY && A.c1) {
+              const float* sy = A.y + row * A.ldy + kg * 8;
+              cp_async16(raw_ptr(buf, 1, r), sy);
+              cp_async16(raw_ptr(buf, 1, r) + 4, sy + 4);
+            }
+          } else if (edge_nb) {
+            const long long pt = row / A.k;
+            const long long nb = (pt / A.npts) * A.npts + A.idx[row];
+            const float* src = A.p + nb * A.ld + rcol;
+            cp_async16(raw_ptr(buf, 0, r), src);
+            cp_async16(raw_ptr(buf, 0, r) + 4, src + 4);
+          }
+        }
+      }
+      cp_async_commit();     // always commit: uniform group accounting
+    };
+    for (int j = 0; j < RS - 1; ++j) issue_async(blockIdx.x + j * gridDim.x, j);
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int s = it & 1;
-      mbar_wait(&empty[s], ((it >> 1) & 1) ^ 1);
+      issue_async(tile + (RS - 1) * gridDim.x, (it + RS - 1) % RS);
+      if (RS == 3) cp_async_wait<2>(); else cp_async_wait<1>();
+      const int s = it % AS;
+      mbar_wait(&empty[s], ((it / AS) & 1) ^ 1);
       unsigned char* sAhi = smem + sp.off_a + (size_t)s * sp.a_stage_bytes;
       unsigned char* sAlo = sAhi + (size_t)ngrp * A_GROUP_BYTES;
       const long long row0 = (long long)tile * TILE_M;
-#pragma unroll 4
+      const int buf = it % RS;
+#pragma unroll 2
       for (int r = r0; r < TILE_M; r += rstep) {
         const long long row = row0 + r;
         float v[8];
-        load_chunk<AMODE>(A, row, kg, row < M && kvalid, pc0, pc1, pc2, v, generic != 0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        if (row < M && kvalid) {
+          float a[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) a[i] = 0.f;
+          if (AMODE != OP_EDGE || edge_nb) ld8(raw_ptr(buf, 0, r), a);
+          if (AMODE == OP_PLAIN) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = a[i];
+          } else if (AMODE == OP_BNRELU) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = fmaxf(fmaf(a[i], pc0[i], pc1[i]), 0.f);
+            if (A.dmask) {
+              float m[8];
+              ld8(A.dmask + row * A.C + kg * 8, m);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] *= m[i] * A.dscale;
+            }
+          } else if (AMODE == OP_DY) {
+            if (A.c1) {
+              float y[8];
+              ld8(raw_ptr(buf, 1, r), y);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = fmaf(pc0[i], a[i], fmaf(pc2[i], y[i], pc1[i]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = a[i];
+            }
+          } else if (AMODE == OP_EDGE) {
+            const long long pt = row / A.k;
+            if (!edge_nb) {
+              ld8(A.p + pt * A.ld + kg * 8, v);
+            } else {
+              float xi[8];
+              ld8(A.p + pt * A.ld + rcol, xi);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = a[i] - xi[i];
+            }
+          }
+        }
         uint4 hi, lo;
         split8(v, hi, lo);
         *reinterpret_cast<uint4*>(sAhi + (size_t)kg * A_GROUP_BYTES + r * 16) = hi;
@@ -669,6 +752,7 @@ rowgemm_ws_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, 
       fence_proxy_async_smem();
       mbar_arrive(&full[s]);
     }
+    cp_async_wait<0>();
   } else if (warp == 12) {
     // =============================================================== MMA issuer ===
     if (lane == 0) {
@@ -676,8 +760,8 @@ rowgemm_ws_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, 
       const uint32_t b_hi = smem_u32(sBhi), b_lo = smem_u32(sBlo);
       int it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int s = it & 1, a = it & 1;
-        mbar_wait(&full[s], (it >> 1) & 1);
+        const int s = it % AS, a = it & 1;
+        mbar_wait(&full[s], (it / AS) & 1);
         mbar_wait(&acc_empty[a], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t a_hi = smem_u32(smem + sp.off_a + (size_t)s * sp.a_stage_bytes);
@@ -917,12 +1001,15 @@ int launch_tc(const Operand& A, const float* Bm, long long ldb, int bT, long lon
   if (!generic && g_use_async && AMODE == OP_DY) want_raw = A.c1 ? 2 : 1;
   const TcPlan pl = tc_plan(N, K, want_raw);
   const int num_tiles = (int)((M + TILE_M - 1) / TILE_M);
-  // warp-specialised persistent kernel for the single-chunk shapes with enough tiles to stream
-  if (K <= 128 && N <= 128 && ((((K + 15) / 16 * 16) / 8) == 2 || (((K + 15) / 16 * 16) / 8) % 4 == 0) && num_tiles >= 4 &&
-      g_use_ws) {
-    const WsSmem wp = ws_smem_plan(K, N);
-    const int ngrp = wp.Kp / 8;
-    if (wp.total <= 220 * 1024 && WS_PRODUCERS % ngrp == 0) {
+  // warp-specialised persistent kernel for the single-chunk shapes (aligned operands)
+  if (K <= 128 && N <= 128 && !generic && AMODE != OP_DY_SPARSE && num_tiles >= 4 && g_use_ws) {
+    const int Kp = (K + 15) / 16 * 16, ngrp = Kp / 8;
+    const int raw_streams = (AMODE == OP_DY && A.c1) ? 2 : 1;
+    const int raw_w = (AMODE == OP_EDGE) ? (K / 2) : Kp;
+    const int opts[3][2] = {{3, 2}, {2, 2}, {2, 1}};
+    for (int o = 0; o < 3; ++o) {
+      const WsSmem wp = ws_smem_plan(K, N, opts[o][0], opts[o][1], raw_streams, raw_w);
+      if (wp.total > 226 * 1024 || WS_PRODUCERS % ngrp != 0) continue;
       const int npass = (N + 63) / 64;
       int tmem_cols = 64;
       while (tmem_cols < 2 * npass * 64) tmem_cols <<= 1;
@@ -930,11 +1017,11 @@ int launch_tc(const Operand& A, const float* Bm, long long ldb, int bT, long lon
       if (npass == 1) {
         auto kern = rowgemm_ws_kernel<AMODE, EMODE, 1>;
         WSPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wp.total));
-        kern<<<grid, WS_THREADS, wp.total, st>>>(A, Bm, ldb, bT, M, N, K, E, num_tiles, tmem_cols, generic);
+        kern<<<grid, WS_THREADS, wp.total, st>>>(A, Bm, ldb, bT, M, N, K, E, num_tiles, tmem_cols, wp.RS, wp.AS, raw_streams, raw_w);
       } else {
         auto kern = rowgemm_ws_kernel<AMODE, EMODE, 2>;
         WSPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wp.total));
-        kern<<<grid, WS_THREADS, wp.total, st>>>(A, Bm, ldb, bT, M, N, K, E, num_tiles, tmem_cols, generic);
+        kern<<<grid, WS_THREADS, wp.total, st>>>(A, Bm, ldb, bT, M, N, K, E, num_tiles, tmem_cols, wp.RS, wp.AS, raw_streams, raw_w);
       }
       count_launch();
       WSPC_LAUNCH_CHECK("rowgemm_ws_kernel");
@@ -952,7 +1039,7 @@ int launch_tc(const Operand& A, const float* Bm, long long ldb, int bT, long lon
     WSPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));          \
     kern<<<grid, TC_THREADS, pl.smem, st>>>(A, Bm, ldb, bT, M, N, K, E, num_tiles, pl.tmem_cols, pl.KC, pl.NtMax, generic, pl.raw_streams); \
   }
-  if (pl.npass <= 1) { if (pl.minb == 4) WSPC_TC_LAUNCH(4, 1) else if (pl.minb == 3) WSPC_TC_LAUNCH(3, 1) else if (pl.minb == 2) WSPC_TC_LAUNCH(2, 1) else WSPC_TC_LAUNCH(1, 1) }
+  if (pl.npass <= 1) { if (pl.minb == 3) WSPC_TC_LAUNCH(3, 1) else if (pl.minb == 2) WSPC_TC_LAUNCH(2, 1) else WSPC_TC_LAUNCH(1, 1) }
   else if (pl.npass <= 2) { if (pl.minb >= 2) WSPC_TC_LAUNCH(2, 2) else WSPC_TC_LAUNCH(1, 2) }
   else WSPC_TC_LAUNCH(1, 4)
 #undef WSPC_TC_LAUNCH
