@@ -103,13 +103,41 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// Rows of an edge tensor are (point, neighbour) pairs, row = pt*k + j.  The 64-bit divisions are done once per
+// 128-row tile; the per-row part is one 32-bit multiply-high (exact while (k+128)*k < 2^32: k <= 32768).
+struct RowMap {
+  long long pt0, cb0;    // point of the tile's first row; first point of that point's cloud
+  uint32_t rem0, npts;   // row0 - pt0*k
+  uint64_t inv;          // floor(2^32/k)+1
+};
+__device__ __forceinline__ uint64_t rowmap_inv(int k) { return (1ull << 32) / (uint32_t)(k > 0 ? k : 1) + 1; }
+__device__ __forceinline__ long long div_pos(long long a, int b) {
+  return (a < (1ll << 31)) ? (long long)((uint32_t)a / (uint32_t)b) : a / b;
+}
+__device__ __forceinline__ RowMap rowmap_tile(long long row0, int k, int npts, uint64_t inv) {
+  RowMap m;
+  m.pt0 = div_pos(row0, k);
+  m.rem0 = (uint32_t)(row0 - m.pt0 * k);
+  m.cb0 = div_pos(m.pt0, npts) * npts;
+  m.npts = (uint32_t)npts;
+  m.inv = inv;
+  return m;
+}
+__device__ __forceinline__ void rowmap_point(const RowMap& m, int r, long long& pt, long long& cb) {
+  const uint32_t x = m.rem0 + (uint32_t)r;
+  pt = m.pt0 + (uint32_t)(((uint64_t)x * m.inv) >> 32);
+  cb = m.cb0;
+  while (pt - cb >= m.npts) cb += m.npts;
+}
+
 // Loads the 8 channels [kg*8, kg*8+8) of logical row `row` of an operand (zeros if !valid).
+// EDGE: `pt`/`cb` are the row's point and the first point of its cloud (rowmap_point).
 // pc0..2 hold the thread's per-channel constants (BNRELU: sc, sh; DY: c1, c2, c3).
 // `generic` selects the element-wise loader of operand.cuh (any alignment, any channel count).
 template <int AMODE>
 __device__ __forceinline__ void load_chunk(const Operand& A, long long row, int kg, bool valid, const float (&pc0)[8],
                                            const float (&pc1)[8], const float (&pc2)[8], float (&v)[8],
-                                           bool generic = false) {
+                                           bool generic = false, long long pt = 0, long long cb = 0) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = 0.f;
   if (!valid) return;
@@ -132,11 +160,10 @@ __device__ __forceinline__ void load_chunk(const Operand& A, long long row, int 
     }
   } else if (AMODE == OP_EDGE) {
     const int Cx = A.C >> 1;
-    const long long pt = row / A.k;
     if (kg * 8 < Cx) {
       ld8(A.p + pt * A.ld + kg * 8, v);
     } else {
-      const long long nb = (pt / A.npts) * A.npts + A.idx[row];
+      const long long nb = cb + A.idx[row];
       float xi[8], xj[8];
       ld8(A.p + pt * A.ld + kg * 8 - Cx, xi);
       ld8(A.p + nb * A.ld + kg * 8 - Cx, xj);
@@ -155,9 +182,33 @@ __device__ __forceinline__ void load_chunk(const Operand& A, long long row, int 
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = g[i];
     }
-  } else {  // OP_DY_SPARSE
-    load8<OP_DY_SPARSE>(A, row, kg * 8, v);
+  } else {  // OP_DY_SPARSE: pt = cloud of the row, cb = point index inside the cloud
+    float y[8], dg[8];
+    ld8(A.y + row * A.ldy + kg * 8, y);
+    ld8(A.dg + pt * A.C + kg * 8, dg);
+    const int4 m0 = *reinterpret_cast<const int4*>(A.amax + pt * A.C + kg * 8);
+    const int4 m1 = *reinterpret_cast<const int4*>(A.amax + pt * A.C + kg * 8 + 4);
+    const int am[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+    const int n = (int)cb;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaf(pc0[i], am[i] == n ? dg[i] : 0.f, fmaf(pc2[i], y[i], pc1[i]));
   }
+}
+
+// DY_SPARSE rows are points: (cloud, n) of tile-local row r from the tile's first row (one division per tile)
+struct CloudMap { long long cloud0; uint32_t rem0, npts; };
+__device__ __forceinline__ CloudMap cloudmap_tile(long long row0, int npts) {
+  CloudMap m;
+  m.cloud0 = div_pos(row0, npts);
+  m.rem0 = (uint32_t)(row0 - m.cloud0 * npts);
+  m.npts = (uint32_t)npts;
+  return m;
+}
+__device__ __forceinline__ void cloudmap_point(const CloudMap& m, int r, long long& cloud, long long& n) {
+  uint32_t x = m.rem0 + (uint32_t)r;
+  cloud = m.cloud0;
+  while (x >= m.npts) { x -= m.npts; ++cloud; }
+  n = x;
 }
 
 template <int AMODE>
@@ -168,25 +219,15 @@ __device__ __forceinline__ void load_consts(const Operand& A, int kg, int K, flo
     const int c = kg * 8 + i;
     pc0[i] = 0.f; pc1[i] = 0.f; pc2[i] = 0.f;
     if (AMODE == OP_BNRELU && c < K) { pc0[i] = A.sc[c]; pc1[i] = A.sh[c]; }
-    if (AMODE == OP_DY && A.c1 && c < K) { pc0[i] = A.c1[c]; pc1[i] = A.c2[c]; pc2[i] = A.c3[c]; }
+    if ((AMODE == OP_DY || AMODE == OP_DY_SPARSE) && A.c1 && c < K) { pc0[i] = A.c1[c]; pc1[i] = A.c2[c]; pc2[i] = A.c3[c]; }
   }
 }
 
-static bool g_use_ws = false;
-static bool g_use_async = false;   // cp.async double-buffered operand prefetch in rowgemm_tc_kernel   // warp-specialised row GEMM for eligible shapes (toggle for A/B measurements)
-
-__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N_>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
-
 struct TcSmem {
   int Kp, Npad, b_group_bytes;
-  size_t off_bhi, off_blo, off_ahi, off_alo, off_stage, off_raw, off_misc, total;
+  size_t off_bhi, off_blo, off_ahi, off_alo, off_stage, off_misc, total;
 };
-__host__ __device__ inline TcSmem tc_smem_plan(int K, int N, bool need_stage, int raw_streams = 0) {
+__host__ __device__ inline TcSmem tc_smem_plan(int K, int N, bool need_stage) {
   TcSmem s;
   s.Kp = (K + 15) / 16 * 16;
   s.Npad = (N + 15) / 16 * 16;
@@ -202,8 +243,6 @@ __host__ __device__ inline TcSmem tc_smem_plan(int K, int N, bool need_stage, in
   s.off_stage = s.off_ahi;
   const size_t stage_end = s.off_stage + (need_stage ? (size_t)TILE_M * STAGE_LD * 4 : 0);
   if (o < stage_end) o = (stage_end + 127) / 128 * 128;
-  // raw_streams > 0: double-buffered cp.async landing zone, raw_streams x (128 rows x Kp floats) per buffer
-  s.off_raw = o; o += (size_t)2 * raw_streams * TILE_M * s.Kp * 4;
   s.off_misc = o; o += 64;
   s.total = o;
   return s;
@@ -217,10 +256,9 @@ __host__ __device__ inline TcSmem tc_smem_plan(int K, int N, bool need_stage, in
 template <int AMODE, int EMODE, int MINB, int MAXPASS>
 __global__ void __launch_bounds__(TC_THREADS, MINB)
 rowgemm_tc_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, int bT, long long M, int N, int K,
-                  const Epilogue E, int num_tiles, int tmem_cols, int KC, int NtMax, int generic, int raw_streams) {
+                  const Epilogue E, int num_tiles, int tmem_cols, int KC, int NtMax, int generic) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const TcSmem sp = tc_smem_plan(KC, NtMax, true, raw_streams);
-  float* raw = reinterpret_cast<float*>(smem + sp.off_raw);
+  const TcSmem sp = tc_smem_plan(KC, NtMax, true);
   unsigned char* sBhi = smem + sp.off_bhi;
   unsigned char* sBlo = smem + sp.off_blo;
   unsigned char* sAhi = smem + sp.off_ahi;
@@ -283,100 +321,18 @@ rowgemm_tc_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, 
       for (int j = 0; j < 4; ++j) { st0[p][j] = 0.0; st1[p][j] = 0.0; }
   }
 
-  // cp.async prefetch of the NEXT tile's raw operand rows (single-chunk shapes): every thread copies exactly the
-  // 32-byte pieces it will convert itself, so only its own cp.async group has to complete (no extra barrier).
-  const bool use_async = raw_streams > 0;
-  auto raw_ptr = [&](int buf, int q, int r) { return raw + ((size_t)(buf * raw_streams + q) * TILE_M + r) * sp.Kp + kg * 8; };
-  auto issue_async = [&](int tile, int buf) {
-    const long long row0 = (long long)tile * TILE_M;
-    const bool kv = kg * 8 < K;
-    for (int r = r0; r < TILE_M; r += rstep) {
-      const long long row = row0 + r;
-      if (row >= M || !kv) continue;
-      if (AMODE == OP_PLAIN || AMODE == OP_BNRELU || AMODE == OP_DY) {
-        const float* src = A.p + row * A.ld + kg * 8;
-        cp_async16(raw_ptr(buf, 0, r), src);
-        cp_async16(raw_ptr(buf, 0, r) + 4, src + 4);
-        if (AMODE == OP_DY && A.c1) {
-          const float* sy = A.y + row * A.ldy + kg * 8;
-          cp_async16(raw_ptr(buf, 1, r), sy);
-          cp_async16(raw_ptr(buf, 1, r) + 4, sy + 4);
-        }
-      } else if (AMODE == OP_EDGE) {
-        const int Cx = A.C >> 1;
-        if (kg * 8 >= Cx) {
-          const long long pt = row / A.k;
-          const long long nb = (pt / A.npts) * A.npts + A.idx[row];
-          const float* src = A.p + nb * A.ld + kg * 8 - Cx;
-          cp_async16(raw_ptr(buf, 0, r), src);
-          cp_async16(raw_ptr(buf, 0, r) + 4, src + 4);
-        }
-      }
-    }
-    cp_async_commit();
-  };
-  auto convert_async = [&](int tile, int buf) {
-    const long long row0 = (long long)tile * TILE_M;
-    const bool kv = kg * 8 < K;
-#pragma unroll 2
-    for (int r = r0; r < TILE_M; r += rstep) {
-      const long long row = row0 + r;
-      float v[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = 0.f;
-      if (row < M && kv) {
-        float a[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) a[i] = 0.f;
-        if (AMODE != OP_EDGE || kg * 8 >= (A.C >> 1)) ld8(raw_ptr(buf, 0, r), a);
-        if (AMODE == OP_PLAIN) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = a[i];
-        } else if (AMODE == OP_BNRELU) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = fmaxf(fmaf(a[i], pc0[i], pc1[i]), 0.f);
-          if (A.dmask) {
-            float m[8];
-            ld8(A.dmask + row * A.C + kg * 8, m);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] *= m[i] * A.dscale;
-          }
-        } else if (AMODE == OP_DY) {
-          if (A.c1) {
-            float y[8];
-            ld8(raw_ptr(buf, 1, r), y);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = fmaf(pc0[i], a[i], fmaf(pc2[i], y[i], pc1[i]));
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = a[i];
-          }
-        } else if (AMODE == OP_EDGE) {
-          const int Cx = A.C >> 1;
-          const long long pt = row / A.k;
-          if (kg * 8 < Cx) {
-            ld8(A.p + pt * A.ld + kg * 8, v);
-          } else {
-            float xi[8];
-            ld8(A.p + pt * A.ld + kg * 8 - Cx, xi);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = a[i] - xi[i];
-          }
-        }
-      }
-      uint4 hi, lo;
-      split8(v, hi, lo);
-      *reinterpret_cast<uint4*>(sAhi + (size_t)kg * A_GROUP_BYTES + r * 16) = hi;
-      *reinterpret_cast<uint4*>(sAlo + (size_t)kg * A_GROUP_BYTES + r * 16) = lo;
-    }
-  };
-  if (use_async && (int)blockIdx.x < num_tiles) issue_async(blockIdx.x, 0);
-
   uint32_t phase = 0;
-  int titer = 0;
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++titer) {
+  const uint64_t a_inv = (AMODE == OP_EDGE) ? rowmap_inv(A.k) : 0;
+  const uint64_t e_inv = (EMODE == EPI_EDGE_SCATTER) ? rowmap_inv(E.k) : 0;
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     const long long row0 = (long long)tile * TILE_M;
     uint32_t accum = 0;
+    RowMap arm, erm;
+    CloudMap acm;
+    if (AMODE == OP_EDGE) arm = rowmap_tile(row0, A.k, A.npts, a_inv);
+    if (AMODE == OP_DY_SPARSE) acm = cloudmap_tile(row0, A.npts);
+    if (EMODE == EPI_EDGE_SCATTER) erm = rowmap_tile(row0, E.k, E.npts, e_inv);
+
     for (int kc = 0; kc < nkc; ++kc) {
 
       // ------------------------------------------------------------ 1. operands -> smem ------
@@ -386,17 +342,14 @@ rowgemm_tc_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, 
         load_w(kc);
         load_consts<AMODE>(A, cg, K, pc0, pc1, pc2);
       }
-      if (use_async) {
-        const int nxt = tile + gridDim.x;
-        if (nxt < num_tiles) { issue_async(nxt, (titer + 1) & 1); cp_async_wait<1>(); }
-        else cp_async_wait<0>();
-        convert_async(tile, titer & 1);
-      } else
 #pragma unroll 4
       for (int r = r0; r < TILE_M; r += rstep) {
         const long long row = row0 + r;
         float v[8];
-        load_chunk<AMODE>(A, row, cg, row < M && kvalid, pc0, pc1, pc2, v, generic != 0);
+        long long pt = 0, cb = 0;
+        if (AMODE == OP_EDGE) rowmap_point(arm, r, pt, cb);
+        if (AMODE == OP_DY_SPARSE) cloudmap_point(acm, r, pt, cb);
+        load_chunk<AMODE>(A, row, cg, row < M && kvalid, pc0, pc1, pc2, v, generic != 0, pt, cb);
         uint4 hi, lo;
         split8(v, hi, lo);
         *reinterpret_cast<uint4*>(sAhi + (size_t)kg * A_GROUP_BYTES + r * 16) = hi;
@@ -442,8 +395,9 @@ rowgemm_tc_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, 
         const int Cx = N >> 1;
         const long long row = row0 + trow;
         if (row < M) {
-          const long long pt = row / E.k;
-          const long long nb = (pt / E.npts) * E.npts + E.idx[row];
+          long long pt, cb;
+          rowmap_point(erm, trow, pt, cb);
+          const long long nb = cb + E.idx[row];
           float* dst = E.dx + nb * E.lddx + (p * 64 - Cx) + ch * 32;
 #pragma unroll
           for (int i = 0; i < 32; i += 4) red_add_v4(dst + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
@@ -463,20 +417,24 @@ rowgemm_tc_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, 
       if (EMODE == EPI_EDGE_SCATTER) {
         // centre reduction: rows of one point are consecutive; thread = (column, quarter of the rows)
         const int col = tid & 63, q = tid >> 6;
-        long long cur = -1;
+        long long cur, cb;
+        rowmap_point(erm, q * 32, cur, cb);
+        int left = E.k - (int)(erm.rem0 + (uint32_t)(q * 32) - (uint32_t)(cur - erm.pt0) * (uint32_t)E.k);   // rows left of point `cur`
         float acc = 0.f;
+        bool any = false;
         for (int r = q * 32; r < q * 32 + 32; ++r) {
-          const long long row = row0 + r;
-          if (row >= M) break;
-          const long long pt = row / E.k;
-          if (pt != cur) {
-            if (cur >= 0) atomicAdd(E.dx + cur * E.lddx + col, acc);
-            cur = pt;
+          if (row0 + r >= M) break;
+          if (left == 0) {
+            atomicAdd(E.dx + cur * E.lddx + col, acc);
+            ++cur;
+            left = E.k;
             acc = 0.f;
           }
           acc += stage[r * STAGE_LD + col];
+          --left;
+          any = true;
         }
-        if (cur >= 0) atomicAdd(E.dx + cur * E.lddx + col, acc);
+        if (any) atomicAdd(E.dx + cur * E.lddx + col, acc);
       } else {
         const int cl = p * 64 + e_c4 * 4;           // column within this N tile
         const int cbase = n0 + cl;                  // global column
@@ -491,6 +449,12 @@ rowgemm_tc_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, 
             for (int j = 0; j < 4; ++j) { scp[j] = E.scp[cbase + j]; shp[j] = E.shp[cbase + j]; }
           }
           float f0[4] = {0.f, 0.f, 0.f, 0.f}, f1[4] = {0.f, 0.f, 0.f, 0.f};   // fp32 partials of this tile (8 rows)
+          long long rb_cloud0 = 0;
+          uint32_t rb_rem0 = 0;
+          if ((EMODE == EPI_STORE || EMODE == EPI_STORE_STATS) && E.rowbias) {
+            rb_cloud0 = div_pos(row0, E.rb_rows);
+            rb_rem0 = (uint32_t)(row0 - rb_cloud0 * E.rb_rows);
+          }
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int r = e_r0 + 16 * it;
@@ -499,7 +463,13 @@ rowgemm_tc_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, 
             const float4 s4 = *reinterpret_cast<const float4*>(stage + r * STAGE_LD + e_c4 * 4);
             float o[4] = {s4.x, s4.y, s4.z, s4.w};
             if (EMODE == EPI_STORE || EMODE == EPI_STORE_STATS) {
-              const float* rb = E.rowbias ? E.rowbias + (row / E.rb_rows) * E.ldrb + cbase : nullptr;
+              const float* rb = nullptr;
+              if (E.rowbias) {
+                long long cl0 = rb_cloud0;
+                uint32_t x = rb_rem0 + (uint32_t)r;
+                if (x >= (uint32_t)E.rb_rows) { cl0 += x / (uint32_t)E.rb_rows; }
+                rb = E.rowbias + cl0 * E.ldrb + cbase;
+              }
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 o[j] += bias[j];
@@ -564,410 +534,34 @@ rowgemm_tc_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, 
   if (warp == 0) tc_dealloc(tmem_base, (uint32_t)tmem_cols);
 }
 
-// ------------------------------------------------------------------ warp-specialised variant ---
-// Same math as rowgemm_tc_kernel for the single-chunk shapes (K <= 128, N <= 128: every EdgeConv layer), but the
-// three phases of a tile run concurrently on different warps of one persistent CTA per SM:
-//   warps 0-7   producers : synthesise + split the A tile into a 2-stage shared-memory ring        (full[s] / empty[s])
-//   warp  12    MMA issuer: tcgen05.mma into one of two TMEM accumulators, tcgen05.commit          (acc_full[a] / acc_empty[a])
-//   warps 8-11  epilogue  : tcgen05.ld -> private staging tile -> coalesced global stores / statistics / scatter
-// so global-load latency, the tensor core and the HBM write-back overlap tile by tile instead of alternating.
-constexpr int WS_PRODUCERS = 256;
-constexpr int WS_EPILOGUE = 128;
-constexpr int WS_THREADS = WS_PRODUCERS + WS_EPILOGUE + 32;
-constexpr int WS_STAGES = 2;
-
-struct WsSmem {
-  int Kp, Npad, b_group_bytes, RS, AS, raw_streams, raw_w;
-  size_t a_stage_bytes, raw_buf_bytes, off_b, off_a, off_stage, off_raw, off_misc, total;
-};
-// RS raw (cp.async landing) buffers x raw_streams x (128 rows x raw_w floats), AS converted A stages
-__host__ __device__ inline WsSmem ws_smem_plan(int K, int N, int RS, int AS, int raw_streams, int raw_w) {
-  WsSmem w;
-  w.Kp = (K + 15) / 16 * 16;
-  w.Npad = (N + 15) / 16 * 16;
-  w.b_group_bytes = w.Npad * 16 + 16;
-  w.RS = RS; w.AS = AS; w.raw_streams = raw_streams; w.raw_w = raw_w;
-  const size_t bbytes = ((size_t)2 * (w.Kp / 8) * w.b_group_bytes + 127) / 128 * 128;
-  w.a_stage_bytes = ((size_t)2 * (w.Kp / 8) * A_GROUP_BYTES + 127) / 128 * 128;
-  w.raw_buf_bytes = (size_t)raw_streams * TILE_M * raw_w * 4;
-  w.off_b = 0;
-  w.off_a = bbytes;
-  w.off_stage = w.off_a + AS * w.a_stage_bytes;
-  w.off_raw = w.off_stage + (size_t)TILE_M * STAGE_LD * 4;
-  w.off_misc = w.off_raw + RS * w.raw_buf_bytes;
-  w.total = w.off_misc + 128;
-  return w;
-}
-
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-
-template <int AMODE, int EMODE, int MAXPASS>
-__global__ void __launch_bounds__(WS_THREADS, 1)
-rowgemm_ws_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, int bT, long long M, int N, int K,
-                  const Epilogue E, int num_tiles, int tmem_cols, int RS, int AS, int raw_streams, int raw_w) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  const WsSmem sp = ws_smem_plan(K, N, RS, AS, raw_streams, raw_w);
-  const int ngrp = sp.Kp / 8;
-  unsigned char* sBhi = smem + sp.off_b;
-  unsigned char* sBlo = sBhi + (size_t)ngrp * sp.b_group_bytes;
-  float* stage = reinterpret_cast<float*>(smem + sp.off_stage);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sp.off_misc);   // full[2], empty[2], acc_full[2], acc_empty[2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-  uint64_t* full = bars, *empty = bars + 2, *acc_full = bars + 4, *acc_empty = bars + 6;
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (warp == 12) tc_alloc(tmem_slot, (uint32_t)tmem_cols);
-  if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&full[i], WS_PRODUCERS);
-      mbar_init(&empty[i], 1);
-      mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], WS_EPILOGUE);
-    }
-    mbar_fence_init();
-  }
-  // split weights, resident for the whole kernel: element (n, k) of Bm^T -> group k/8, row n, slot k%8
-  for (int e = tid; e < sp.Npad * ngrp; e += WS_THREADS) {
-    const int n = e % sp.Npad, g = e / sp.Npad;
-    float w[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int k = g * 8 + i;
-      w[i] = (n < N && k < K) ? (bT ? Bm[(long long)n * ldb + k] : Bm[(long long)k * ldb + n]) : 0.f;
-    }
-    uint4 hi, lo;
-    split8(w, hi, lo);
-    *reinterpret_cast<uint4*>(sBhi + (size_t)g * sp.b_group_bytes + n * 16) = hi;
-    *reinterpret_cast<uint4*>(sBlo + (size_t)g * sp.b_group_bytes + n * 16) = lo;
-  }
-  fence_proxy_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const int npass = (N + 63) / 64;
-
-  if (warp < 8) {
-    // =============================================================== producers ===
-    // raw operand rows stream in with cp.async (RS-deep ring, prefetch distance RS-1); each thread copies and later
-    // converts exactly its own 32-byte pieces, so only its own cp.async groups need to complete.
-    const int kg = tid % ngrp, rstep = WS_PRODUCERS / ngrp, r0 = tid / ngrp;
-    const bool kvalid = kg * 8 < K;
-    const int Cx = A.C >> 1;
-    const bool edge_nb = (AMODE == OP_EDGE) && (kg * 8 >= Cx);
-    const int rcol = (AMODE == OP_EDGE) ? (kg * 8 - Cx) : kg * 8;          // column inside a raw row
-    float pc0[8], pc1[8], pc2[8];
-    load_consts<AMODE>(A, kg, K, pc0, pc1, pc2);
-    float* raw = reinterpret_cast<float*>(smem + sp.off_raw);
-    auto raw_ptr = [&](int buf, int q, int r) {
-      return raw + (size_t)buf * (sp.raw_buf_bytes / 4) + ((size_t)q * TILE_M + r) * raw_w + rcol;
-    };
-    auto issue_async = [&](int tile, int buf) {
-      if (tile < num_tiles && kvalid) {
-        const long long row0 = (long long)tile * TILE_M;
-        for (int r = r0; r < TILE_M; r += rstep) {
-          const long long row = row0 + r;
-          if (row >= M) break;
-          if (AMODE == OP_PLAIN || AMODE == OP_BNRELU || AMODE == OP_DY) {
-            const float* src = A.p + row * A.ld + kg * 8;
-            cp_async16(raw_ptr(buf, 0, r), src);
-            cp_async16(raw_ptr(buf, 0, r) + 4, src + 4);
-            if (AMODE == OP_DY && A.c1) {
-              const float* sy = A.y + row * A.ldy + kg * 8;
-              cp_async16(raw_ptr(buf, 1, r), sy);
-              cp_async16(raw_ptr(buf, 1, r) + 4, sy + 4);
-            }
-          } else if (edge_nb) {
-            const long long pt = row / A.k;
-            const long long nb = (pt / A.npts) * A.npts + A.idx[row];
-            const float* src = A.p + nb * A.ld + rcol;
-            cp_async16(raw_ptr(buf, 0, r), src);
-            cp_async16(raw_ptr(buf, 0, r) + 4, src + 4);
-          }
-        }
-      }
-      cp_async_commit();     // always commit: uniform group accounting
-    };
-    for (int j = 0; j < RS - 1; ++j) issue_async(blockIdx.x + j * gridDim.x, j);
-    int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      issue_async(tile + (RS - 1) * gridDim.x, (it + RS - 1) % RS);
-      if (RS == 3) cp_async_wait<2>(); else cp_async_wait<1>();
-      const int s = it % AS;
-      mbar_wait(&empty[s], ((it / AS) & 1) ^ 1);
-      unsigned char* sAhi = smem + sp.off_a + (size_t)s * sp.a_stage_bytes;
-      unsigned char* sAlo = sAhi + (size_t)ngrp * A_GROUP_BYTES;
-      const long long row0 = (long long)tile * TILE_M;
-      const int buf = it % RS;
-#pragma unroll 2
-      for (int r = r0; r < TILE_M; r += rstep) {
-        const long long row = row0 + r;
-        float v[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = 0.f;
-        if (row < M && kvalid) {
-          float a[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) a[i] = 0.f;
-          if (AMODE != OP_EDGE || edge_nb) ld8(raw_ptr(buf, 0, r), a);
-          if (AMODE == OP_PLAIN) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = a[i];
-          } else if (AMODE == OP_BNRELU) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = fmaxf(fmaf(a[i], pc0[i], pc1[i]), 0.f);
-            if (A.dmask) {
-              float m[8];
-              ld8(A.dmask + row * A.C + kg * 8, m);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] *= m[i] * A.dscale;
-            }
-          } else if (AMODE == OP_DY) {
-            if (A.c1) {
-              float y[8];
-              ld8(raw_ptr(buf, 1, r), y);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = fmaf(pc0[i], a[i], fmaf(pc2[i], y[i], pc1[i]));
-            } else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = a[i];
-            }
-          } else if (AMODE == OP_EDGE) {
-            const long long pt = row / A.k;
-            if (!edge_nb) {
-              ld8(A.p + pt * A.ld + kg * 8, v);
-            } else {
-              float xi[8];
-              ld8(A.p + pt * A.ld + rcol, xi);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = a[i] - xi[i];
-            }
-          }
-        }
-        uint4 hi, lo;
-        split8(v, hi, lo);
-        *reinterpret_cast<uint4*>(sAhi + (size_t)kg * A_GROUP_BYTES + r * 16) = hi;
-        *reinterpret_cast<uint4*>(sAlo + (size_t)kg * A_GROUP_BYTES + r * 16) = lo;
-      }
-      fence_proxy_async_smem();
-      mbar_arrive(&full[s]);
-    }
-    cp_async_wait<0>();
-  } else if (warp == 12) {
-    // =============================================================== MMA issuer ===
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc(sp.Npad);
-      const uint32_t b_hi = smem_u32(sBhi), b_lo = smem_u32(sBlo);
-      int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int s = it % AS, a = it & 1;
-        mbar_wait(&full[s], (it / AS) & 1);
-        mbar_wait(&acc_empty[a], ((it >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t a_hi = smem_u32(smem + sp.off_a + (size_t)s * sp.a_stage_bytes);
-        const uint32_t a_lo = a_hi + (uint32_t)ngrp * A_GROUP_BYTES;
-        const uint32_t acc = tmem_base + (uint32_t)a * (uint32_t)(npass * 64);
-        uint32_t accum = 0;
-#pragma unroll 1
-        for (int pass = 0; pass < 3; ++pass) {
-          const uint32_t ab = (pass == 1) ? a_lo : a_hi;
-          const uint32_t bb = (pass == 2) ? b_lo : b_hi;
-          for (int kk = 0; kk < sp.Kp / 16; ++kk) {
-            tc_mma_bf16(acc, umma_desc(ab + (uint32_t)(2 * kk) * A_GROUP_BYTES, A_GROUP_BYTES, 128),
-                        umma_desc(bb + (uint32_t)(2 * kk) * sp.b_group_bytes, sp.b_group_bytes, 128), idesc, accum);
-            accum = 1;
-          }
-        }
-        tc_commit(&empty[s]);       // A stage reusable once these MMAs have read it
-        tc_commit(&acc_full[a]);    // accumulator ready for the epilogue
-      }
-    }
-  } else {
-    // =============================================================== epilogue ===
-    const int et = tid - WS_PRODUCERS;              // 0..127
-    const int q = warp - 8;                         // TMEM lane quadrant
-    const int trow = q * 32 + lane;
-    const int e_c4 = et & 15, e_r0 = et >> 4;       // coalesced pass: 4 fixed columns, 8 rows per sweep
-    constexpr bool kStats = (EMODE == EPI_STORE_STATS || EMODE == EPI_RELUMASK_STATS);
-    double st0[kStats ? MAXPASS : 1][4], st1[kStats ? MAXPASS : 1][4];
-    if (kStats) {
-#pragma unroll
-      for (int p = 0; p < MAXPASS; ++p)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { st0[p][j] = 0.0; st1[p][j] = 0.0; }
-    }
-    int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int a = it & 1;
-      const long long row0 = (long long)tile * TILE_M;
-      mbar_wait(&acc_full[a], (it >> 1) & 1);
-      tc_fence_after();
-      const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)a * (uint32_t)(npass * 64);
-#pragma unroll
-      for (int p = 0; p < MAXPASS; ++p) {
-        if (p >= npass) break;
-        float* srow = stage + trow * STAGE_LD;
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-          float v[32];
-          tc_ld32(acc + (uint32_t)(p * 64 + ch * 32), v);
-          if (EMODE == EPI_EDGE_SCATTER && p * 64 >= (N >> 1)) {
-            const int Cx = N >> 1;
-            const long long row = row0 + trow;
-            if (row < M) {
-              const long long pt = row / E.k;
-              const long long nb = (pt / E.npts) * E.npts + E.idx[row];
-              float* dst = E.dx + nb * E.lddx + (p * 64 - Cx) + ch * 32;
-#pragma unroll
-              for (int i = 0; i < 32; i += 4) red_add_v4(dst + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
-            }
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              float4 c = *reinterpret_cast<float4*>(srow + ch * 32 + i);
-              c.x -= v[i]; c.y -= v[i + 1]; c.z -= v[i + 2]; c.w -= v[i + 3];
-              *reinterpret_cast<float4*>(srow + ch * 32 + i) = c;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4)
-              *reinterpret_cast<float4*>(srow + ch * 32 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-          }
-        }
-        if (p == npass - 1) {        // accumulator fully drained: hand it back to the MMA warp
-          tc_fence_before();
-          mbar_arrive(&acc_empty[a]);
-        }
-        if (EMODE == EPI_EDGE_SCATTER && p + 1 < npass) { __syncwarp(); continue; }
-        epi_bar();
-        if (EMODE == EPI_EDGE_SCATTER) {
-          const int col = et & 63, h = et >> 6;
-          long long cur = -1;
-          float accv = 0.f;
-          for (int r = h * 64; r < h * 64 + 64; ++r) {
-            const long long row = row0 + r;
-            if (row >= M) break;
-            const long long pt = row / E.k;
-            if (pt != cur) {
-              if (cur >= 0) atomicAdd(E.dx + cur * E.lddx + col, accv);
-              cur = pt;
-              accv = 0.f;
-            }
-            accv += stage[r * STAGE_LD + col];
-          }
-          if (cur >= 0) atomicAdd(E.dx + cur * E.lddx + col, accv);
-        } else {
-          const int cbase = p * 64 + e_c4 * 4;
-          if (cbase < N) {
-            float bias[4] = {0.f, 0.f, 0.f, 0.f}, scp[4] = {0.f, 0.f, 0.f, 0.f}, shp[4] = {-1.f, -1.f, -1.f, -1.f};
-            if ((EMODE == EPI_STORE || EMODE == EPI_STORE_STATS) && E.bias) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) bias[j] = E.bias[cbase + j];
-            }
-            if (EMODE == EPI_RELUMASK_STATS) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) { scp[j] = E.scp[cbase + j]; shp[j] = E.shp[cbase + j]; }
-            }
-            float f0[4] = {0.f, 0.f, 0.f, 0.f}, f1[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-            for (int itr = 0; itr < 16; ++itr) {
-              const int r = e_r0 + 8 * itr;
-              const long long row = row0 + r;
-              if (row >= M) break;
-              const float4 s4 = *reinterpret_cast<const float4*>(stage + r * STAGE_LD + p * 0 + e_c4 * 4);
-              float o[4] = {s4.x, s4.y, s4.z, s4.w};
-              if (EMODE == EPI_STORE || EMODE == EPI_STORE_STATS) {
-                const float* rb = E.rowbias ? E.rowbias + (row / E.rb_rows) * E.ldrb + cbase : nullptr;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  o[j] += bias[j];
-                  if (rb) o[j] += rb[j];
-                }
-                if (EMODE == EPI_STORE_STATS) {
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) { f0[j] += o[j]; f1[j] = fmaf(o[j], o[j], f1[j]); }
-                }
-              } else if (EMODE == EPI_RELUMASK_STATS) {
-                const float4 y4 = *reinterpret_cast<const float4*>(E.yprev + row * E.ldyp + cbase);
-                const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
-                float dm[4] = {1.f, 1.f, 1.f, 1.f};
-                if (E.dmask) {
-                  const float4 m4 = *reinterpret_cast<const float4*>(E.dmask + row * N + cbase);
-                  dm[0] = m4.x * E.dscale; dm[1] = m4.y * E.dscale; dm[2] = m4.z * E.dscale; dm[3] = m4.w * E.dscale;
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const bool on = fmaf(yv[j], scp[j], shp[j]) > 0.f;
-                  o[j] = on ? o[j] * dm[j] : 0.f;
-                  f0[j] += o[j];
-                  f1[j] = fmaf(o[j], yv[j], f1[j]);
-                }
-              } else if (EMODE == EPI_ACCUM) {
-                const float4 c4 = *reinterpret_cast<const float4*>(E.out + row * E.ldo + cbase);
-                o[0] += c4.x; o[1] += c4.y; o[2] += c4.z; o[3] += c4.w;
-              }
-              *reinterpret_cast<float4*>(E.out + row * E.ldo + cbase) = make_float4(o[0], o[1], o[2], o[3]);
-            }
-            if (kStats) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) { st0[p][j] += (double)f0[j]; st1[p][j] += (double)f1[j]; }
-            }
-          }
-        }
-        epi_bar();     // staging free for the next pass / tile
-      }
-    }
-    if (kStats) {
-#pragma unroll
-      for (int p = 0; p < MAXPASS; ++p) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          double sa = st0[p][j], sb = st1[p][j];
-          sa += __shfl_xor_sync(0xffffffffu, sa, 16);
-          sb += __shfl_xor_sync(0xffffffffu, sb, 16);
-          const int col = p * 64 + e_c4 * 4 + j;
-          if (lane < 16 && col < N) {
-            atomicAdd(E.stats + col, sa);
-            atomicAdd(E.stats + N + col, sb);
-          }
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 12) tc_dealloc(tmem_base, (uint32_t)tmem_cols);
-}
-
 struct TcPlan {
-  int KC, NtMax, ntiles_n, npass, tmem_cols, raw_streams;
+  int KC, NtMax, ntiles_n, npass, tmem_cols;
   size_t smem;
   bool two;
   int minb;
 };
-TcPlan tc_plan(int N, int K, int want_raw = 0) {
+TcPlan tc_plan(int N, int K) {
   TcPlan p;
   const int Kp = (K + 15) / 16 * 16;
   p.KC = (K <= 128) ? Kp : 64;
-  const bool chunked = K > 128;
-  p.NtMax = (N <= 256 && !chunked) ? N : (N <= 128 ? N : 128);
+  p.NtMax = N <= 256 ? N : 256;     // one MMA covers up to 256 columns: the A tile is synthesised once per 256
   p.ntiles_n = (N + p.NtMax - 1) / p.NtMax;
   p.npass = (p.NtMax + 63) / 64;
   p.tmem_cols = 64;
   while (p.tmem_cols < p.npass * 64) p.tmem_cols <<= 1;
-  p.raw_streams = (!chunked && p.ntiles_n == 1) ? want_raw : 0;
-  p.smem = tc_smem_plan(p.KC, p.NtMax, true, p.raw_streams).total;
-  if (p.smem > 220 * 1024 && p.raw_streams) { p.raw_streams = 0; p.smem = tc_smem_plan(p.KC, p.NtMax, true, 0).total; }
+  p.smem = tc_smem_plan(p.KC, p.NtMax, true).total;
   p.two = p.smem <= 110 * 1024;
   p.minb = p.smem <= 72 * 1024 ? 3 : (p.two ? 2 : 1);
   if (p.npass == 2 && p.minb > 2) p.minb = 2;   // matches the instantiations launched below
-  if (p.npass > 2) p.minb = 1;
+  if (p.npass > 2) p.minb = p.two ? 2 : 1;
   return p;
 }
 
 // aligned fast path for the A operand? (otherwise the element-wise loader is used inside the same kernel)
 bool tc_operand_fast(const Operand& A, int amode, int K) {
   if (K % 8 != 0) return false;
-  if (amode == OP_DY_SPARSE) return true;   // always element-wise inside load_chunk
+  if (amode == OP_DY_SPARSE)
+    return A.c1 && aligned16(A.y) && (A.ldy % 4) == 0 && aligned16(A.dg) && aligned16(A.amax) && (A.C % 8) == 0 && A.npts >= 1;
   if (!aligned16(A.p) || (A.ld % 4) != 0) return false;
   if (amode == OP_EDGE && (A.C / 2) % 8 != 0) return false;
   if (amode == OP_DY && A.c1 && (!aligned16(A.y) || (A.ldy % 4) != 0)) return false;
@@ -977,6 +571,8 @@ bool tc_operand_fast(const Operand& A, int amode, int K) {
 
 bool tc_supported(const Operand& A, int amode, const float* Bm, long long M, int N, int K, const Epilogue& E, int emode) {
   if (K < 12) return false;
+  if (amode == OP_EDGE && (A.k < 1 || A.k > 32768 || A.npts < 1)) return false;          // RowMap range
+  if (emode == EPI_EDGE_SCATTER && (E.k < 1 || E.k > 32768 || E.npts < 1)) return false;
   if (N % 4 != 0 || N < 16) return false;
   const TcPlan pl = tc_plan(N, K);
   const int k8c = ((pl.KC + 15) / 16 * 16) / 8;
@@ -996,38 +592,8 @@ template <int AMODE, int EMODE>
 int launch_tc(const Operand& A, const float* Bm, long long ldb, int bT, long long M, int N, int K, const Epilogue& E,
               cudaStream_t st) {
   const int generic = tc_operand_fast(A, AMODE, K) ? 0 : 1;
-  int want_raw = 0;
-  if (!generic && g_use_async && (AMODE == OP_PLAIN || AMODE == OP_BNRELU || AMODE == OP_EDGE)) want_raw = 1;
-  if (!generic && g_use_async && AMODE == OP_DY) want_raw = A.c1 ? 2 : 1;
-  const TcPlan pl = tc_plan(N, K, want_raw);
+  const TcPlan pl = tc_plan(N, K);
   const int num_tiles = (int)((M + TILE_M - 1) / TILE_M);
-  // warp-specialised persistent kernel for the single-chunk shapes (aligned operands)
-  if (K <= 128 && N <= 128 && !generic && AMODE != OP_DY_SPARSE && num_tiles >= 4 && g_use_ws) {
-    const int Kp = (K + 15) / 16 * 16, ngrp = Kp / 8;
-    const int raw_streams = (AMODE == OP_DY && A.c1) ? 2 : 1;
-    const int raw_w = (AMODE == OP_EDGE) ? (K / 2) : Kp;
-    const int opts[3][2] = {{3, 2}, {2, 2}, {2, 1}};
-    for (int o = 0; o < 3; ++o) {
-      const WsSmem wp = ws_smem_plan(K, N, opts[o][0], opts[o][1], raw_streams, raw_w);
-      if (wp.total > 226 * 1024 || WS_PRODUCERS % ngrp != 0) continue;
-      const int npass = (N + 63) / 64;
-      int tmem_cols = 64;
-      while (tmem_cols < 2 * npass * 64) tmem_cols <<= 1;
-      const int grid = num_tiles < kNumSM ? num_tiles : kNumSM;
-      if (npass == 1) {
-        auto kern = rowgemm_ws_kernel<AMODE, EMODE, 1>;
-        WSPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wp.total));
-        kern<<<grid, WS_THREADS, wp.total, st>>>(A, Bm, ldb, bT, M, N, K, E, num_tiles, tmem_cols, wp.RS, wp.AS, raw_streams, raw_w);
-      } else {
-        auto kern = rowgemm_ws_kernel<AMODE, EMODE, 2>;
-        WSPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wp.total));
-        kern<<<grid, WS_THREADS, wp.total, st>>>(A, Bm, ldb, bT, M, N, K, E, num_tiles, tmem_cols, wp.RS, wp.AS, raw_streams, raw_w);
-      }
-      count_launch();
-      WSPC_LAUNCH_CHECK("rowgemm_ws_kernel");
-      return WSPC_OK;
-    }
-  }
   const int ctas = pl.minb * kNumSM;
   int gx = (ctas + pl.ntiles_n - 1) / pl.ntiles_n;
   if (gx > num_tiles) gx = num_tiles;
@@ -1037,11 +603,11 @@ int launch_tc(const Operand& A, const float* Bm, long long ldb, int bT, long lon
   {                                                                                                            \
     auto kern = rowgemm_tc_kernel<AMODE, EMODE, MINB_, NP_>;                                                   \
     WSPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));          \
-    kern<<<grid, TC_THREADS, pl.smem, st>>>(A, Bm, ldb, bT, M, N, K, E, num_tiles, pl.tmem_cols, pl.KC, pl.NtMax, generic, pl.raw_streams); \
+    kern<<<grid, TC_THREADS, pl.smem, st>>>(A, Bm, ldb, bT, M, N, K, E, num_tiles, pl.tmem_cols, pl.KC, pl.NtMax, generic); \
   }
   if (pl.npass <= 1) { if (pl.minb == 3) WSPC_TC_LAUNCH(3, 1) else if (pl.minb == 2) WSPC_TC_LAUNCH(2, 1) else WSPC_TC_LAUNCH(1, 1) }
   else if (pl.npass <= 2) { if (pl.minb >= 2) WSPC_TC_LAUNCH(2, 2) else WSPC_TC_LAUNCH(1, 2) }
-  else WSPC_TC_LAUNCH(1, 4)
+  else { if (pl.minb >= 2) WSPC_TC_LAUNCH(2, 4) else WSPC_TC_LAUNCH(1, 4) }
 #undef WSPC_TC_LAUNCH
   count_launch();
   WSPC_LAUNCH_CHECK("rowgemm_tc_kernel");
@@ -1103,30 +669,44 @@ colgemm_tc_kernel(const Operand A, const Operand G, long long M, long long rows_
 
   uint32_t phase = 0, accum = 0;
   bool pending = false;
+  const uint64_t a_inv = (AMODE == OP_EDGE) ? rowmap_inv(A.k) : 0;
   for (long long rb = r_begin; rb < r_end; rb += TILE_M) {
     if (pending) { mbar_wait(mma_bar, phase); phase ^= 1; pending = false; }   // MMAs done reading smem
+    RowMap arm;
+    CloudMap gcm;
+    if (AMODE == OP_EDGE) arm = rowmap_tile(rb, A.k, A.npts, a_inv);
+    if (GMODE == OP_DY_SPARSE) gcm = cloudmap_tile(rb, G.npts);
 #pragma unroll 2
     for (int r = rA0; r < TILE_M; r += 16) {
       const long long row = rb + r;
       float v[8];
-      load_chunk<AMODE>(A, row, cA, vA && row < r_end, a0, a1, a2, v, genA != 0);
+      long long pt = 0, cb = 0;
+      if (AMODE == OP_EDGE) rowmap_point(arm, r, pt, cb);
+      load_chunk<AMODE>(A, row, cA, vA && row < r_end, a0, a1, a2, v, genA != 0, pt, cb);
       uint4 hi, lo;
       split8(v, hi, lo);
       *reinterpret_cast<uint4*>(sAhi + (size_t)gA * A_GROUP_BYTES + r * 16) = hi;
       *reinterpret_cast<uint4*>(sAlo + (size_t)gA * A_GROUP_BYTES + r * 16) = lo;
     }
+    float bs[8];                                          // fp32 partial of this tile (<= 16 rows per thread)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) bs[i] = 0.f;
 #pragma unroll 2
     for (int r = rG0; r < TILE_M; r += rGstep) {
       const long long row = rb + r;
       float v[8];
-      load_chunk<GMODE>(G, row, cG, vG && row < r_end, g0, g1, g2, v, genG != 0);
+      long long gpt = 0, gcb = 0;
+      if (GMODE == OP_DY_SPARSE) cloudmap_point(gcm, r, gpt, gcb);
+      load_chunk<GMODE>(G, row, cG, vG && row < r_end, g0, g1, g2, v, genG != 0, gpt, gcb);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) bsum[i] += (double)v[i];
+      for (int i = 0; i < 8; ++i) bs[i] += v[i];
       uint4 hi, lo;
       split8(v, hi, lo);
       *reinterpret_cast<uint4*>(sGhi + (size_t)gG * A_GROUP_BYTES + r * 16) = hi;
       *reinterpret_cast<uint4*>(sGlo + (size_t)gG * A_GROUP_BYTES + r * 16) = lo;
     }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) bsum[i] += (double)bs[i];
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -1187,6 +767,7 @@ bool wgrad_tc_supported(const Operand& A, int amode, const Operand& G, int gmode
   if (amode != OP_PLAIN && amode != OP_BNRELU && amode != OP_EDGE) return false;
   if (gmode != OP_DY && gmode != OP_DY_SPARSE) return false;
   if (A.C < 12 || G.C < 12) return false;
+  if (amode == OP_EDGE && (A.k < 1 || A.k > 32768 || A.npts < 1)) return false;          // RowMap range
   return true;
 }
 
