@@ -223,6 +223,74 @@ __device__ __forceinline__ void load_consts(const Operand& A, int kg, int K, flo
   }
 }
 
+// Split form of load_chunk for software-batched loops: fetch_chunk only issues the global loads of a chunk
+// (so a batch of chunks has all its loads in flight before the first use), finish_chunk does the arithmetic.
+struct RawChunk { float a[8], b[8]; };
+template <int AMODE>
+__device__ __forceinline__ void fetch_chunk(const Operand& A, long long row, int kg, bool valid, long long pt,
+                                            long long nb, RawChunk& w) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { w.a[i] = 0.f; w.b[i] = 0.f; }
+  if (!valid) return;
+  if (AMODE == OP_PLAIN || AMODE == OP_BNRELU) {
+    ld8(A.p + row * A.ld + kg * 8, w.a);
+  } else if (AMODE == OP_EDGE) {
+    const int Cx = A.C >> 1;
+    if (kg * 8 < Cx) {
+      ld8(A.p + pt * A.ld + kg * 8, w.a);
+    } else {
+      ld8(A.p + nb * A.ld + kg * 8 - Cx, w.a);
+      ld8(A.p + pt * A.ld + kg * 8 - Cx, w.b);
+    }
+  } else if (AMODE == OP_DY) {
+    ld8(A.p + row * A.ld + kg * 8, w.a);
+    if (A.c1) ld8(A.y + row * A.ldy + kg * 8, w.b);
+  } else {  // OP_DY_SPARSE
+    ld8(A.y + row * A.ldy + kg * 8, w.b);
+  }
+}
+template <int AMODE>
+__device__ __forceinline__ void finish_chunk(const Operand& A, long long row, int kg, bool valid, long long pt,
+                                             long long cb, const float (&pc0)[8], const float (&pc1)[8],
+                                             const float (&pc2)[8], const RawChunk& w, float (&v)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = 0.f;
+  if (!valid) return;
+  if (AMODE == OP_PLAIN) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = w.a[i];
+  } else if (AMODE == OP_BNRELU) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaxf(fmaf(w.a[i], pc0[i], pc1[i]), 0.f);
+    if (A.dmask) {
+      float m[8];
+      ld8(A.dmask + row * A.C + kg * 8, m);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] *= m[i] * A.dscale;
+    }
+  } else if (AMODE == OP_EDGE) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = w.a[i] - w.b[i];     // centre groups: b = 0
+  } else if (AMODE == OP_DY) {
+    if (A.c1) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = fmaf(pc0[i], w.a[i], fmaf(pc2[i], w.b[i], pc1[i]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = w.a[i];
+    }
+  } else {  // OP_DY_SPARSE: pt = cloud, cb = point inside the cloud
+    float dg[8];
+    ld8(A.dg + pt * A.C + kg * 8, dg);
+    const int4 m0 = *reinterpret_cast<const int4*>(A.amax + pt * A.C + kg * 8);
+    const int4 m1 = *reinterpret_cast<const int4*>(A.amax + pt * A.C + kg * 8 + 4);
+    const int am[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+    const int n = (int)cb;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaf(pc0[i], am[i] == n ? dg[i] : 0.f, fmaf(pc2[i], w.b[i], pc1[i]));
+  }
+}
+
 struct TcSmem {
   int Kp, Npad, b_group_bytes;
   size_t off_bhi, off_blo, off_ahi, off_alo, off_stage, off_misc, total;
@@ -663,9 +731,9 @@ colgemm_tc_kernel(const Operand A, const Operand G, long long M, long long rows_
   float a0[8], a1[8], a2[8], g0[8], g1[8], g2[8];
   load_consts<AMODE>(A, cA, A.C, a0, a1, a2);
   load_consts<GMODE>(G, cG, G.C, g0, g1, g2);
-  double bsum[8];
+  float bs[8];     // bias-gradient partial: <= rows_per_slab / rGstep values per thread, fp32 is ample (slabs add in fp64)
 #pragma unroll
-  for (int i = 0; i < 8; ++i) bsum[i] = 0.0;
+  for (int i = 0; i < 8; ++i) bs[i] = 0.f;
 
   uint32_t phase = 0, accum = 0;
   bool pending = false;
@@ -676,37 +744,94 @@ colgemm_tc_kernel(const Operand A, const Operand G, long long M, long long rows_
     CloudMap gcm;
     if (AMODE == OP_EDGE) arm = rowmap_tile(rb, A.k, A.npts, a_inv);
     if (GMODE == OP_DY_SPARSE) gcm = cloudmap_tile(rb, G.npts);
+    // A operand: 8 chunks per thread in batches of UB, all loads of a batch in flight before the first use
+    constexpr int UB = 4;
+    if (!genA) {
+#pragma unroll 1
+      for (int rbase = rA0; rbase < TILE_M; rbase += 16 * UB) {
+        long long pt[UB], cb[UB], nb[UB];
+        bool ok[UB];
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+          const int r = rbase + 16 * u;
+          ok[u] = vA && rb + r < r_end;
+          pt[u] = 0; cb[u] = 0; nb[u] = 0;
+          if (AMODE == OP_EDGE) {
+            rowmap_point(arm, r, pt[u], cb[u]);
+            if (ok[u] && cA * 8 >= (A.C >> 1)) nb[u] = cb[u] + A.idx[rb + r];
+          }
+        }
+        RawChunk w[UB];
+#pragma unroll
+        for (int u = 0; u < UB; ++u) fetch_chunk<AMODE>(A, rb + rbase + 16 * u, cA, ok[u], pt[u], nb[u], w[u]);
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+          const int r = rbase + 16 * u;
+          float v[8];
+          finish_chunk<AMODE>(A, rb + r, cA, ok[u], pt[u], cb[u], a0, a1, a2, w[u], v);
+          uint4 hi, lo;
+          split8(v, hi, lo);
+          *reinterpret_cast<uint4*>(sAhi + (size_t)gA * A_GROUP_BYTES + r * 16) = hi;
+          *reinterpret_cast<uint4*>(sAlo + (size_t)gA * A_GROUP_BYTES + r * 16) = lo;
+        }
+      }
+    } else {
 #pragma unroll 2
-    for (int r = rA0; r < TILE_M; r += 16) {
-      const long long row = rb + r;
-      float v[8];
-      long long pt = 0, cb = 0;
-      if (AMODE == OP_EDGE) rowmap_point(arm, r, pt, cb);
-      load_chunk<AMODE>(A, row, cA, vA && row < r_end, a0, a1, a2, v, genA != 0, pt, cb);
-      uint4 hi, lo;
-      split8(v, hi, lo);
-      *reinterpret_cast<uint4*>(sAhi + (size_t)gA * A_GROUP_BYTES + r * 16) = hi;
-      *reinterpret_cast<uint4*>(sAlo + (size_t)gA * A_GROUP_BYTES + r * 16) = lo;
+      for (int r = rA0; r < TILE_M; r += 16) {
+        const long long row = rb + r;
+        float v[8];
+        load_chunk<AMODE>(A, row, cA, vA && row < r_end, a0, a1, a2, v, true);
+        uint4 hi, lo;
+        split8(v, hi, lo);
+        *reinterpret_cast<uint4*>(sAhi + (size_t)gA * A_GROUP_BYTES + r * 16) = hi;
+        *reinterpret_cast<uint4*>(sAlo + (size_t)gA * A_GROUP_BYTES + r * 16) = lo;
+      }
     }
-    float bs[8];                                          // fp32 partial of this tile (<= 16 rows per thread)
+    if (!genG) {
+      // dY operand: TILE_M / rGstep chunks per thread (4, 8 or 16; 2 when K2t = 16), same batching
+#pragma unroll 1
+      for (int rbase = rG0; rbase < TILE_M; rbase += rGstep * UB) {
+        long long pt[UB], cb[UB];
+        bool ok[UB];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) bs[i] = 0.f;
+        for (int u = 0; u < UB; ++u) {
+          const int r = rbase + rGstep * u;
+          ok[u] = vG && r < TILE_M && rb + r < r_end;
+          pt[u] = 0; cb[u] = 0;
+          if (GMODE == OP_DY_SPARSE) cloudmap_point(gcm, r, pt[u], cb[u]);
+        }
+        RawChunk w[UB];
+#pragma unroll
+        for (int u = 0; u < UB; ++u) fetch_chunk<GMODE>(G, rb + rbase + rGstep * u, cG, ok[u], pt[u], 0, w[u]);
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+          const int r = rbase + rGstep * u;
+          if (r < TILE_M) {
+            float v[8];
+            finish_chunk<GMODE>(G, rb + r, cG, ok[u], pt[u], cb[u], g0, g1, g2, w[u], v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) bs[i] += v[i];
+            uint4 hi, lo;
+            split8(v, hi, lo);
+            *reinterpret_cast<uint4*>(sGhi + (size_t)gG * A_GROUP_BYTES + r * 16) = hi;
+            *reinterpret_cast<uint4*>(sGlo + (size_t)gG * A_GROUP_BYTES + r * 16) = lo;
+          }
+        }
+      }
+    } else {
 #pragma unroll 2
-    for (int r = rG0; r < TILE_M; r += rGstep) {
-      const long long row = rb + r;
-      float v[8];
-      long long gpt = 0, gcb = 0;
-      if (GMODE == OP_DY_SPARSE) cloudmap_point(gcm, r, gpt, gcb);
-      load_chunk<GMODE>(G, row, cG, vG && row < r_end, g0, g1, g2, v, genG != 0, gpt, gcb);
+      for (int r = rG0; r < TILE_M; r += rGstep) {
+        const long long row = rb + r;
+        float v[8];
+        load_chunk<GMODE>(G, row, cG, vG && row < r_end, g0, g1, g2, v, true);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) bs[i] += v[i];
-      uint4 hi, lo;
-      split8(v, hi, lo);
-      *reinterpret_cast<uint4*>(sGhi + (size_t)gG * A_GROUP_BYTES + r * 16) = hi;
-      *reinterpret_cast<uint4*>(sGlo + (size_t)gG * A_GROUP_BYTES + r * 16) = lo;
+        for (int i = 0; i < 8; ++i) bs[i] += v[i];
+        uint4 hi, lo;
+        split8(v, hi, lo);
+        *reinterpret_cast<uint4*>(sGhi + (size_t)gG * A_GROUP_BYTES + r * 16) = hi;
+        *reinterpret_cast<uint4*>(sGlo + (size_t)gG * A_GROUP_BYTES + r * 16) = lo;
+      }
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) bsum[i] += (double)bs[i];
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -753,7 +878,7 @@ colgemm_tc_kernel(const Operand A, const Operand G, long long M, long long rows_
   }
   if (blockIdx.y == 0 && partial_b) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) atomicAdd(&bred[gG * 8 + i], (float)bsum[i]);
+    for (int i = 0; i < 8; ++i) atomicAdd(&bred[gG * 8 + i], bs[i]);
     __syncthreads();
     for (int i = tid; i < K2t; i += TC_THREADS)
       if (k2_0 + i < K2p) partial_b[(size_t)blockIdx.x * K2p + k2_0 + i] = bred[i];
