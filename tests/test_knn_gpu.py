@@ -128,9 +128,11 @@ def test_errors_are_loud(cuda):
 
 @pytest.mark.parametrize("path", [0, 1], ids=["tcgen05+refine", "cuda-core"])
 @pytest.mark.parametrize("B,N,D,kind", [(2, 1024, 64, "relu"), (1, 777, 64, "relu"), (2, 512, 32, "uniform"),
-                                        (2, 640, 64, "grid"), (1, 300, 16, "relu"), (1, 2048, 64, "clustered")])
+                                        (2, 640, 64, "grid"), (1, 300, 16, "relu"), (1, 2048, 64, "clustered"),
+                                        (2, 1500, 3, "uniform"), (2, 900, 6, "uniform"), (1, 2048, 3, "clustered"),
+                                        (1, 1111, 9, "relu"), (3, 256, 3, "grid"), (2, 4096, 3, "uniform")])
 def test_wide_feature_knn_both_device_paths(cuda, path, B, N, D, kind):
-    """16 <= D <= 64: tensor-core distances + exact re-scoring must reproduce the oracle bit for bit, including
+    """D <= 64: tensor-core distances + exact re-scoring must reproduce the oracle bit for bit, including
     exact ties (grid), duplicated points and tight clusters far from the origin (stress for the error margin)."""
     from weaksuppointcloudseg_b200 import _lib as L, ops
 

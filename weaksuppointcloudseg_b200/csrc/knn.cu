@@ -16,7 +16,7 @@
 
 namespace wspc {
 void count_launch(int n = 1);
-bool knn_tc_eligible(int D, int k);
+bool knn_tc_eligible(int N, int D, int k);
 size_t knn_tc_workspace_bytes(int B, int N, int D);
 int knn_tc_run(const float* x, int B, int N, int ldx, int coff, int D, int k, int flavour, int32_t* idx, float* dist,
                void* ws, size_t ws_bytes, cudaStream_t st);
@@ -462,13 +462,13 @@ extern "C" size_t wspc_knn_workspace_bytes(int B, int N, int D) {
   if (B < 1 || N < 1 || D < 1 || D > 128) return 0;
   const KnnPlan p = make_plan(B, N, D);
   const size_t exact = p.xT_bytes + p.sq_bytes;
-  const size_t tc = knn_tc_eligible(D, 1) ? knn_tc_workspace_bytes(B, N, D) : 0;
+  const size_t tc = knn_tc_eligible(N, D, 1) ? knn_tc_workspace_bytes(B, N, D) : 0;
   return exact > tc ? exact : tc;
 }
 
 extern "C" int wspc_knn_fallback_rows(const void* workspace, int B, int N, int D, int* rows_out) {
   WSPC_REQUIRE(workspace && rows_out, "knn_fallback_rows: null pointer");
-  if (!knn_tc_eligible(D, 1) || g_knn_path != 0) { *rows_out = 0; return WSPC_OK; }
+  if (!knn_tc_eligible(N, D, 1) || g_knn_path != 0) { *rows_out = 0; return WSPC_OK; }
   return knn_tc_fallback_rows(workspace, B, N, D, rows_out);
 }
 
@@ -487,7 +487,7 @@ extern "C" int wspc_knn_fused(const float* x, int B, int N, int ldx, int coff, i
   WSPC_REQUIRE(k >= 1 && k <= 64 && k <= N, "knn_fused: k=%d outside [1,min(64,N=%d)]", k, N);
   WSPC_REQUIRE(flavour == WSPC_DIST_TFUTIL || flavour == WSPC_DIST_SMOOTH, "knn_fused: bad flavour %d", flavour);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (g_knn_path == 0 && knn_tc_eligible(D, k))
+  if (g_knn_path == 0 && knn_tc_eligible(N, D, k))
     return knn_tc_run(x, B, N, ldx, coff, D, k, flavour, idx, dist, workspace, workspace_bytes, st);
   const KnnPlan p = make_plan(B, N, D);
   if (workspace_bytes < p.xT_bytes + p.sq_bytes) {

@@ -1,24 +1,30 @@
-// Tensor-core kNN for wide features (D >= 16): tcgen05 distances + exact fp32 re-scoring.
+// Tensor-core kNN (D <= 64, k <= 24): tcgen05 distances, two-pass threshold selection, exact fp32 re-scoring.
 //
 // The canonical (bit-exact) distance arithmetic is a sequential fp32 FMA chain per pair, which
-// caps the CUDA-core kernel in knn.cu at the FP32 pipe.  Here the N x N dot products run on the 5th-gen tensor
-// cores instead and exactness is restored afterwards:
+// caps the CUDA-core kernel in knn.cu at the FP32 pipe, and any per-element sorted-list selection costs tens of
+// instructions per surviving candidate.  Here the N x N products run on the 5th-gen tensor cores, the selection
+// needs ~1 instruction per matrix element, and exactness is restored afterwards:
 //
 //   prep   : split every feature into bf16 hi + lo and lay 128-point tiles out in the UMMA K-major core-matrix
-//            image ([channel group][row][8], hi then lo) so that one 1-D bulk copy (UBLKCP) stages a whole operand
-//            tile; row norms with the canonical chain; per-cloud max norm.
-//   main   : CTA = 128 query rows.  For each 128-column tile: TMA ring -> 12 x tcgen05.mma (hi*hi + lo*hi + hi*lo,
-//            fp32 accumulate in TMEM) -> tcgen05.ld -> d~ = (sq_i + sq_j) - 2 dot~ -> shared distance tile ->
-//            per-row streaming selection of the 32 smallest d~ (register lists, one entry per lane).  The pass
-//            threshold is d~_(k) + 2 eps_i, where eps_i bounds |d~ - d_exact| for every pair of row i
-//            (eps_i = 2^-11.5 sqrt(sq_i smax) + 2^-20 (sq_i + smax): bf16x3 split error 2^-16 |x||y|, tensor-core
-//            fp32 accumulation of 192 products, and the fp32 roundings of both formulas, with >4x head-room).
-//            Every exact top-k member t satisfies d~_t <= d_t + eps <= d~_(k) + 2 eps, so it is in the list unless
-//            more than 32 candidates fall inside the margin — detected (entry 31 inside the margin) and the row is
-//            flagged.
+//            image ([channel group][row][8]; hi groups then lo groups) so that one 1-D bulk copy (UBLKCP) stages a
+//            whole operand tile.  Three extra "hi" channels carry a 3-way bf16 split of -sq_j/2 (canonical row
+//            norm); the query-side copy of the tile has those channels patched to 1, so the accumulator holds
+//            v_ij = x_i.x_j - sq_j/2 directly and d~_ij = sq_i - 2 v_ij: the largest v of a row are its nearest.
+//   main   : CTA = 256 query rows (two M=128 accumulators, double buffered = all 512 TMEM columns), 16 selection
+//            warps + 1 producer warp (one thread issues the bulk copies and the tcgen05.mma's:
+//            hi*hi + lo*hi + hi*lo, fp32 accumulate).  Thread = (row, 64-column half of the tile).
+//            pass 1: every thread keeps the running maximum of each of its 64 column classes (column mod 128) in
+//                    registers -- one FMNMX per element.  The k-th largest of a row's 128 class maxima, v_k, is
+//                    reached by k distinct columns, so the exact k-th distance is <= d~(v_k) + eps.
+//            pass 2: the MMAs are replayed and every column with v >= v_k - eps_i is appended to the row's
+//                    candidate list (<= 32 entries).  eps_i bounds |d~ - d_exact| for every pair of row i
+//                    (eps_i = 2^-11.5 sqrt(sq_i smax) + 2^-18 (sq_i + smax): bf16x3 split error 2^-16 |x||y|,
+//                    tensor-core fp32 accumulation, the fp32 roundings of both formulas; >4x head-room), hence
+//                    every exact top-k member t has d~_t <= d_t + eps <= d~(v_k) + 2 eps, i.e. v_t >= v_k - eps.
+//                    More than 32 candidates (heavy ties / clustered classes) flags the row.
 //   refine : each lane recomputes the canonical fp32 distance of its candidate (same fmaf chain as the oracle),
 //            the warp sorts the <= 32 (d, j) pairs lexicographically and writes the first k: bit-exact indices and
-//            distances.  |d~ - d| <= eps is verified on every candidate; a violation flags the row.
+//            distances.  d <= d~(threshold) + eps is verified on every candidate; a violation flags the row.
 //   fallback: flagged rows are recomputed by a warp-per-row exact kernel (device-side list, no host sync).
 #include "common.cuh"
 #include <cuda_bf16.h>
@@ -29,13 +35,15 @@ namespace wspc {
 void count_launch(int n = 1);
 namespace {
 
-constexpr int QT = 128;                    // query rows / candidate columns per tile
+constexpr int QT = 128;                    // points per operand tile (MMA M and N)
+constexpr int RB = 256;                    // query rows per CTA (two M blocks)
 constexpr int GROUP_BYTES = QT * 16 + 16;  // one 8-channel group of a tile image (padded, see gemm_tc.cu)
-constexpr int DLD2 = QT + 4;
-constexpr int KTC_THREADS = 1024;                 // 32 warps: 8 per scheduler hide the shuffle/ballot latency of the selection
-constexpr int RW = QT / (KTC_THREADS / 32);       // rows owned by a warp in the selection phase
-constexpr int ECOLS = QT / (KTC_THREADS / 128);   // columns read from TMEM by a warp in the epilogue
-constexpr int NST = 2;                     // candidate-tile ring depth
+constexpr int SEL_WARPS = 16;              // selection warps: (TMEM lane quadrant, M block, column half)
+constexpr int KTC_THREADS = (SEL_WARPS + 1) * 32;
+constexpr int MAXC = 32;                   // candidate slots per row (one per lane in the refine phase)
+constexpr int MAX_NST = 6;                 // candidate-tile ring depth (chosen per D from the smem budget)
+constexpr int NAUG = 3;                    // extra hi channels: 3-way bf16 split of -sq/2
+constexpr int SMEM_BUDGET = 227 * 1024;
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -49,6 +57,10 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t ad, uint64_t bd
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}" ::"r"(d_tmem),
       "l"(ad), "l"(bd), "r"(idesc), "r"(accum), "r"(0u)
       : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
 }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
@@ -65,18 +77,8 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
-
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
-      "tcgen05.wait::ld.sync.aligned;"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 __device__ __forceinline__ float exact_dist(int flavour, float sqi, float sqj, float dot) {
@@ -85,39 +87,81 @@ __device__ __forceinline__ float exact_dist(int flavour, float sqi, float sqj, f
   return d > 0.f ? d : 0.f;
 }
 
+struct TcPlan {
+  int Dp, Dl, Npad, ntile, ghi, glo, nst;
+  uint32_t tile_bytes;
+  size_t img_bytes, smem;
+};
+__host__ __device__ inline int round16(int v) { return (v + 15) / 16 * 16; }
+TcPlan make_tc_plan(int B, int N, int D, int k) {
+  TcPlan p;
+  p.Dp = round16(D + NAUG);
+  p.Dl = round16(D);
+  p.Npad = (N + QT - 1) / QT * QT;
+  p.ntile = p.Npad / QT;
+  p.ghi = p.Dp / 8;
+  p.glo = p.Dl / 8;
+  p.tile_bytes = (uint32_t)(p.ghi + p.glo) * GROUP_BYTES;
+  p.img_bytes = align_up((size_t)B * p.ntile * p.tile_bytes, 256);
+  // selection scratch: top-k exchange [k][2][RB] fp32, later aliased by the candidate lists [RB][MAXC] u16
+  const size_t kk = (size_t)(k < 1 ? 1 : k);
+  const size_t scratch = kk * 2 * RB * 4 > (size_t)RB * MAXC * 2 ? kk * 2 * RB * 4 : (size_t)RB * MAXC * 2;
+  const size_t fixed = 2 * (size_t)p.tile_bytes + scratch + RB * 4 /*cnt*/ + RB * 4 /*thr*/ + 256 /*barriers*/;
+  long nst = ((long)SMEM_BUDGET - (long)fixed) / (long)p.tile_bytes;
+  if (nst > MAX_NST) nst = MAX_NST;
+  p.nst = (int)nst;
+  p.smem = fixed + (size_t)(p.nst > 0 ? p.nst : 0) * p.tile_bytes;
+  if (p.smem < 120 * 1024) p.smem = 120 * 1024;   // one CTA per SM: each CTA owns all 512 TMEM columns
+  return p;
+}
+
 // ------------------------------------------------------------------ prep ---
-// grid (Npad/128, B), block 128: thread = point.  img: per (cloud, tile): [hi | lo] x [Dp/8 groups][128][8] bf16
+// grid (Npad/128, B), block 128: thread = point.  img per (cloud, tile): [hi: ghi groups][lo: glo groups] x [128][8] bf16
 __global__ void __launch_bounds__(128)
-knn_tc_prep_kernel(const float* __restrict__ x, int N, int ldx, int coff, int D, int Dp, int Npad,
+knn_tc_prep_kernel(const float* __restrict__ x, int N, int ldx, int coff, int D, int ghi, int glo, int Npad,
                    unsigned char* __restrict__ img, float* __restrict__ sq, unsigned* __restrict__ smax_bits) {
   const int b = blockIdx.y, tile = blockIdx.x, r = threadIdx.x;
   const int n = tile * QT + r;
-  const int ngrp = Dp / 8;
-  const size_t tile_bytes = (size_t)2 * ngrp * GROUP_BYTES;
+  const size_t tile_bytes = (size_t)(ghi + glo) * GROUP_BYTES;
   unsigned char* base = img + ((size_t)b * (Npad / QT) + tile) * tile_bytes;
   const float* xr = x + ((size_t)b * N + (n < N ? n : 0)) * ldx + coff;
   float acc = 0.f;
-  for (int g = 0; g < ngrp; ++g) {
+  for (int c = 0; c < D; ++c) {             // canonical chain
+    const float v = n < N ? xr[c] : 0.f;
+    acc = __fmaf_rn(v, v, acc);
+  }
+  // 3-way bf16 split of -sq/2 (exact to 2^-24); padded points get a huge negative value: they never win
+  const float s = n < N ? -0.5f * acc : -1.0e30f;
+  const __nv_bfloat16 a1 = __float2bfloat16_rn(s);
+  const float r1 = s - __bfloat162float(a1);
+  const __nv_bfloat16 a2 = __float2bfloat16_rn(r1);
+  const __nv_bfloat16 a3 = __float2bfloat16_rn(r1 - __bfloat162float(a2));
+  for (int g = 0; g < ghi; ++g) {
     uint32_t h[4], l[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      float v0 = 0.f, v1 = 0.f;
-      const int c = g * 8 + 2 * i;
-      if (n < N && c < D) v0 = xr[c];
-      if (n < N && c + 1 < D) v1 = xr[c + 1];
-      acc = __fmaf_rn(v0, v0, acc);          // canonical chain (zeros beyond D do not change it)
-      acc = __fmaf_rn(v1, v1, acc);
-      const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
-      const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0));
-      const __nv_bfloat16 l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
-      h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-      l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+      unsigned short hh[2], ll[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = g * 8 + 2 * i + e;
+        const float v = (n < N && c < D) ? xr[c] : 0.f;
+        __nv_bfloat16 hb = __float2bfloat16_rn(v);
+        const __nv_bfloat16 lb = __float2bfloat16_rn(v - __bfloat162float(hb));
+        if (c == D) hb = a1;
+        if (c == D + 1) hb = a2;
+        if (c == D + 2) hb = a3;
+        hh[e] = __bfloat16_as_ushort(hb);
+        ll[e] = __bfloat16_as_ushort(lb);
+      }
+      h[i] = (uint32_t)hh[0] | ((uint32_t)hh[1] << 16);
+      l[i] = (uint32_t)ll[0] | ((uint32_t)ll[1] << 16);
     }
     *reinterpret_cast<uint4*>(base + (size_t)g * GROUP_BYTES + r * 16) = make_uint4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<uint4*>(base + (size_t)(ngrp + g) * GROUP_BYTES + r * 16) = make_uint4(l[0], l[1], l[2], l[3]);
+    if (g < glo)
+      *reinterpret_cast<uint4*>(base + (size_t)(ghi + g) * GROUP_BYTES + r * 16) = make_uint4(l[0], l[1], l[2], l[3]);
   }
   if (r == 0) {   // the 16 pad bytes of every group are copied by the bulk copy: keep them defined
-    for (int g = 0; g < 2 * ngrp; ++g) *reinterpret_cast<uint4*>(base + (size_t)g * GROUP_BYTES + QT * 16) = make_uint4(0, 0, 0, 0);
+    for (int g = 0; g < ghi + glo; ++g) *reinterpret_cast<uint4*>(base + (size_t)g * GROUP_BYTES + QT * 16) = make_uint4(0, 0, 0, 0);
   }
   sq[(size_t)b * Npad + n] = acc;
   if (n < N) atomicMax(smax_bits + b, __float_as_uint(acc));   // acc >= 0: uint order == float order
@@ -154,240 +198,282 @@ __device__ __forceinline__ void warp_sort_pairs(float& d, int& j, int lane) {
   }
 }
 
+// descending bitonic sorting network over 64 registers (fully unrolled: every index is a compile-time constant)
+__device__ __forceinline__ void sort64_desc(float (&a)[64]) {
+#pragma unroll
+  for (int kk = 2; kk <= 64; kk <<= 1) {
+#pragma unroll
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        const int l = i ^ j;
+        if (l > i) {
+          const float hi = fmaxf(a[i], a[l]), lo = fminf(a[i], a[l]);
+          const bool desc = (i & kk) == 0;
+          a[i] = desc ? hi : lo;
+          a[l] = desc ? lo : hi;
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ main ---
 __global__ void __launch_bounds__(KTC_THREADS, 1)
 knn_tc_kernel(const unsigned char* __restrict__ img, const float* __restrict__ sq, const unsigned* __restrict__ smax_bits,
-              const float* __restrict__ x, int N, int Npad, int ldx, int coff, int D, int Dp, int k, int flavour,
-              int32_t* __restrict__ idx_out, float* __restrict__ dist_out, int* __restrict__ flag_count,
+              const float* __restrict__ x, int N, int Npad, int ldx, int coff, int D, int ghi, int glo, int nst, int k,
+              int flavour, int32_t* __restrict__ idx_out, float* __restrict__ dist_out, int* __restrict__ flag_count,
               int* __restrict__ flag_rows) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const int ngrp = Dp / 8;
-  const uint32_t tile_bytes = (uint32_t)2 * ngrp * GROUP_BYTES;
-  unsigned char* sA = smem;                                  // query tile image (hi | lo)
-  unsigned char* sB = sA + tile_bytes;                       // NST candidate tile images
-  float* Ds = reinterpret_cast<float*>(sB + (size_t)NST * tile_bytes);   // [128][DLD2]
-  float* sqB = Ds + QT * DLD2;                               // [NST][128] candidate norms
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sqB + NST * QT);   // full[NST], abar, mma_bar[2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NST + 3);
+  const uint32_t tile_bytes = (uint32_t)(ghi + glo) * GROUP_BYTES;
+  const size_t scratch_bytes = (size_t)k * 2 * RB * 4 > (size_t)RB * MAXC * 2 ? (size_t)k * 2 * RB * 4 : (size_t)RB * MAXC * 2;
+  unsigned char* sA = smem;                                       // two query tile images
+  unsigned char* sB = sA + 2 * (size_t)tile_bytes;                // nst candidate tile images
+  float* exch = reinterpret_cast<float*>(sB + (size_t)nst * tile_bytes);            // [k][2][RB] top-k exchange
+  unsigned short* cand = reinterpret_cast<unsigned short*>(exch);                   // [RB][MAXC], aliases exch
+  int* cnt = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(exch) + scratch_bytes);   // [RB]
+  float* thr_s = reinterpret_cast<float*>(cnt + RB);                                // [RB] pass threshold (v space)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(thr_s + RB);
+  uint64_t* full = bars;                    // [MAX_NST] candidate tile landed
+  uint64_t* bfree = bars + MAX_NST;         // [MAX_NST] MMAs reading the stage retired
+  uint64_t* accf = bars + 2 * MAX_NST;      // [2] accumulator pair ready
+  uint64_t* acce = accf + 2;                // [2] accumulator pair drained by the 16 selection warps
+  uint64_t* abar = acce + 2;                // query tiles landed
+  uint64_t* aready = abar + 1;              // query tiles patched
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aready + 1);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int b = blockIdx.y, i0 = blockIdx.x * QT;
+  const int b = blockIdx.y, i0 = blockIdx.x * RB;
   const int ntile = Npad / QT;
+  const int nm = (blockIdx.x * 2 + 1 < ntile) ? 2 : 1;            // M blocks present in this row block
   const unsigned char* imgb = img + (size_t)b * ntile * tile_bytes;
   const float* sqb = sq + (size_t)b * Npad;
+  const int total = 2 * ntile;                                    // tile visits: pass 1 then pass 2
 
-  auto issue = [&](int t) {   // thread 0: stage candidate tile t
-    const int s = t % NST;
-    mbar_expect_tx(&bars[s], tile_bytes + QT * 4);
-    bulk_g2s(sB + (size_t)s * tile_bytes, imgb + (size_t)t * tile_bytes, tile_bytes, &bars[s]);
-    bulk_g2s(sqB + s * QT, sqb + (size_t)t * QT, QT * 4, &bars[s]);
-  };
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+  if (warp == SEL_WARPS) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (tid == 32) {
-    for (int s = 0; s < NST + 3; ++s) mbar_init(&bars[s], 1);
+  if (tid == 0) {
+    for (int s = 0; s < 2 * MAX_NST; ++s) mbar_init(&bars[s], 1);
+    mbar_init(&accf[0], 1);
+    mbar_init(&accf[1], 1);
+    mbar_init(&acce[0], SEL_WARPS);
+    mbar_init(&acce[1], SEL_WARPS);
+    mbar_init(abar, 1);
+    mbar_init(aready, RB);
     mbar_fence_init();
   }
+  if (tid < RB) cnt[tid] = 0;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (tid == 0) {
-    mbar_expect_tx(&bars[NST], tile_bytes);
-    bulk_g2s(sA, imgb + (size_t)blockIdx.x * tile_bytes, tile_bytes, &bars[NST]);
-    for (int t = 0; t < NST && t < ntile; ++t) issue(t);
-  }
-  // instruction descriptor: D=f32, A=B=bf16, K-major both, M=128, N=128
-  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(QT >> 3) << 17) | ((uint32_t)(QT >> 4) << 24);
 
-  // epilogue role: TMEM lane quadrant q (rows q*32+lane), column block cb
-  const int q = warp & 3, cb = warp >> 2;
-  const int erow = q * 32 + lane;
-  const float sq_e = sqb[i0 + erow];
-  // selection role: this warp owns rows warp*RW .. +RW-1
-  float ld[RW], tau[RW], eps[RW];
-  int li[RW];
-  const float smax = __uint_as_float(smax_bits[b]);
-#pragma unroll
-  for (int r = 0; r < RW; ++r) {
-    ld[r] = CUDART_INF_F;
-    li[r] = INT_MAX;
-    tau[r] = CUDART_INF_F;
-    const float sqi = sqb[i0 + warp * RW + r];
-    eps[r] = 3.4527e-4f * sqrtf(sqi * smax) + 9.5367e-7f * (sqi + smax);   // 2^-11.5, 2^-20
-  }
-
-  auto issue_mma = [&](int t) {   // thread 0: tile t -> TMEM accumulator t & 1 (stage t % NST must have landed)
-    const int s = t % NST;
-    mbar_wait(&bars[s], (t / NST) & 1);
-    tc_fence_after();
-    const uint32_t a_hi = smem_u32(sA), a_lo = a_hi + ngrp * GROUP_BYTES;
-    const uint32_t b_hi = smem_u32(sB + (size_t)s * tile_bytes), b_lo = b_hi + ngrp * GROUP_BYTES;
-    const uint32_t acc = tmem_base + (uint32_t)(t & 1) * QT;
-    uint32_t accum = 0;
-#pragma unroll 1
-    for (int pass = 0; pass < 3; ++pass) {
-      const uint32_t ab = (pass == 1) ? a_lo : a_hi;
-      const uint32_t bb = (pass == 2) ? b_lo : b_hi;
-      for (int kk = 0; kk < Dp / 16; ++kk) {
-        tc_mma(acc, umma_desc(ab + (uint32_t)(2 * kk) * GROUP_BYTES, GROUP_BYTES, 128),
-               umma_desc(bb + (uint32_t)(2 * kk) * GROUP_BYTES, GROUP_BYTES, 128), idesc, accum);
-        accum = 1;
-      }
-    }
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[NST + 1 + (t & 1)]))
-                 : "memory");
-  };
-
-  mbar_wait(&bars[NST], 0);
-  if (tid == 0) issue_mma(0);
-  for (int t = 0; t < ntile; ++t) {
-    const int s = t % NST;
-    mbar_wait(&bars[NST + 1 + (t & 1)], (t >> 1) & 1);   // MMAs of tile t complete: accumulator t&1 ready, stage s consumed
-    tc_fence_after();
-    if (tid == 0) {
-      // accumulator (t+1)&1 was drained by the epilogue of tile t-1 (ordered by the barriers of that iteration)
-      if (t + 1 < ntile) issue_mma(t + 1);
-    }
-    mbar_wait(&bars[s], (t / NST) & 1);       // candidate norms of stage s (landed together with the tile image)
-
-    // ---- TMEM -> approximate distances -> shared tile (previous tile's scan finished at the last barrier below)
-    {
-      float v[ECOLS];
-      if (ECOLS == 32) tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((t & 1) * QT + cb * ECOLS), *reinterpret_cast<float(*)[32]>(v));
-      else             tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((t & 1) * QT + cb * ECOLS), *reinterpret_cast<float(*)[16]>(v));
-      const float* sj = sqB + s * QT + cb * ECOLS;
-      float* drow = Ds + erow * DLD2 + cb * ECOLS;
-      const int col0 = t * QT + cb * ECOLS;
-#pragma unroll
-      for (int i = 0; i < ECOLS; i += 4) {
-        const float4 s4 = *reinterpret_cast<const float4*>(sj + i);
-        float4 o;
-        o.x = (sq_e + s4.x) - 2.f * v[i];
-        o.y = (sq_e + s4.y) - 2.f * v[i + 1];
-        o.z = (sq_e + s4.z) - 2.f * v[i + 2];
-        o.w = (sq_e + s4.w) - 2.f * v[i + 3];
-        if (col0 + i + 3 >= N) {            // ragged last tile: padded columns never pass
-          const float qnan = __int_as_float(0x7fc00000);
-          if (col0 + i + 0 >= N) o.x = qnan;
-          if (col0 + i + 1 >= N) o.y = qnan;
-          if (col0 + i + 2 >= N) o.z = qnan;
-          o.w = qnan;
-        }
-        *reinterpret_cast<float4*>(drow + i) = o;
-      }
-    }
-    tc_fence_before();
-    __syncthreads();          // distance tile complete; candidate stage s and the accumulator are free
-    tc_fence_after();
-    if (tid == 0 && t + NST < ntile) issue(t + NST);
-
-    // ---- streaming selection of the 32 smallest approximate distances per row
-    {
-      float v[RW][4];
-#pragma unroll
-      for (int r = 0; r < RW; ++r) {
-        const float* drow = Ds + (warp * RW + r) * DLD2 + lane;
-#pragma unroll
-        for (int qq = 0; qq < 4; ++qq) v[r][qq] = drow[32 * qq];
-      }
-      const int col0 = t * QT;
-#pragma unroll
-      for (int qq = 0; qq < 4; ++qq) {
-        unsigned m[RW];
-#pragma unroll
-        for (int r = 0; r < RW; ++r) m[r] = __ballot_sync(0xffffffffu, v[r][qq] <= tau[r]);
-#pragma unroll
-        for (int r = 0; r < RW; ++r) {
-          if (m[r] == 0u) continue;
-          unsigned mm = m[r];
-          do {
-            const int src = __ffs(mm) - 1;
-            mm &= mm - 1u;
-            const float cd = __shfl_sync(0xffffffffu, v[r][qq], src);
-            list_insert32(ld[r], li[r], cd, col0 + 32 * qq + src, lane);
-          } while (mm);
-          // pass threshold: k-th smallest so far + margin, but never beyond what the 32-slot list can hold
-          const float kth = __shfl_sync(0xffffffffu, ld[r], k - 1);
-          const float last = __shfl_sync(0xffffffffu, ld[r], 31);
-          tau[r] = fminf(kth + 2.f * eps[r], last);
-          // if `last` is the binding term the margin may have been truncated: resolved at the end (overflow flag)
-        }
-      }
-    }
-    __syncthreads();          // every warp finished scanning Ds before the next tile overwrites it
-  }
-
-  // ---- exact re-scoring: lane e owns candidate li[r] of row r
-  const float* xb = x + (size_t)b * N * ldx + coff;
-  const bool vec_ok = ((ldx & 3) == 0) && ((coff & 3) == 0) && ((D & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-#pragma unroll 1
-  for (int r = 0; r < RW; ++r) {
-    const int row = i0 + warp * RW + r;
-    if (row >= N) continue;                                   // warp-uniform
-    const float kth = __shfl_sync(0xffffffffu, ld[r], k - 1);
-    const float last_d = __shfl_sync(0xffffffffu, ld[r], 31);
-    const int last_j = __shfl_sync(0xffffffffu, li[r], 31);
-    const float thr = kth + 2.f * eps[r];
-    bool flag = (last_j != INT_MAX) && (last_d <= thr);        // more than 32 candidates inside the margin
-    const int j = li[r];
-    const bool valid = (j != INT_MAX) && (ld[r] <= thr);
-    float d = CUDART_INF_F;
-    int jj = INT_MAX;
-    if (valid) {
-      const float* xi = xb + (size_t)row * ldx;
-      const float* xj = xb + (size_t)j * ldx;
-      float dot = 0.f;
-      if (vec_ok) {   // 16-byte aligned rows: issue all loads first, then the canonical chain (c ascending from +0)
-#pragma unroll 1
-        for (int c0 = 0; c0 < D; c0 += 16) {
-          float4 a[4], bq[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            if (c0 + 4 * u < D) {
-              a[u] = *reinterpret_cast<const float4*>(xi + c0 + 4 * u);
-              bq[u] = *reinterpret_cast<const float4*>(xj + c0 + 4 * u);
-            }
+  if (warp == SEL_WARPS) {
+    // ================================================================ producer: bulk copies + MMA issue
+    if (lane == 0) {
+      auto issue_load = [&](int u) {
+        const int s = u % nst, t = u % ntile;
+        mbar_expect_tx(&full[s], tile_bytes);
+        bulk_g2s(sB + (size_t)s * tile_bytes, imgb + (size_t)t * tile_bytes, tile_bytes, &full[s]);
+      };
+      mbar_expect_tx(abar, (uint32_t)nm * tile_bytes);
+      for (int m = 0; m < nm; ++m)
+        bulk_g2s(sA + (size_t)m * tile_bytes, imgb + (size_t)(blockIdx.x * 2 + m) * tile_bytes, tile_bytes, abar);
+      for (int u = 0; u < nst && u < total; ++u) issue_load(u);
+      // instruction descriptor: D=f32, A=B=bf16, K-major both, M=128, N=128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(QT >> 3) << 17) | ((uint32_t)(QT >> 4) << 24);
+      const int khi = ghi / 2, klo = glo / 2;                     // K=16 steps per pass
+      mbar_wait(aready, 0);
+      for (int u = 0; u < total; ++u) {
+        const int s = u % nst, a = u & 1;
+        mbar_wait(&full[s], (u / nst) & 1);
+        if (u >= 2) mbar_wait(&acce[a], ((u >> 1) - 1) & 1);
+        tc_fence_after();
+        const uint32_t b_hi = smem_u32(sB + (size_t)s * tile_bytes), b_lo = b_hi + (uint32_t)ghi * GROUP_BYTES;
+        for (int m = 0; m < nm; ++m) {
+          const uint32_t a_hi = smem_u32(sA + (size_t)m * tile_bytes), a_lo = a_hi + (uint32_t)ghi * GROUP_BYTES;
+          const uint32_t acc = tmem_base + (uint32_t)(a * 2 + m) * QT;
+          uint32_t accum = 0;
+          for (int kk = 0; kk < khi; ++kk) {                       // hi * hi (includes the -sq_j/2 channels)
+            tc_mma(acc, umma_desc(a_hi + (uint32_t)(2 * kk) * GROUP_BYTES, GROUP_BYTES, 128),
+                   umma_desc(b_hi + (uint32_t)(2 * kk) * GROUP_BYTES, GROUP_BYTES, 128), idesc, accum);
+            accum = 1;
           }
+          for (int kk = 0; kk < klo; ++kk)                         // lo * hi
+            tc_mma(acc, umma_desc(a_lo + (uint32_t)(2 * kk) * GROUP_BYTES, GROUP_BYTES, 128),
+                   umma_desc(b_hi + (uint32_t)(2 * kk) * GROUP_BYTES, GROUP_BYTES, 128), idesc, 1u);
+          for (int kk = 0; kk < klo; ++kk)                         // hi * lo
+            tc_mma(acc, umma_desc(a_hi + (uint32_t)(2 * kk) * GROUP_BYTES, GROUP_BYTES, 128),
+                   umma_desc(b_lo + (uint32_t)(2 * kk) * GROUP_BYTES, GROUP_BYTES, 128), idesc, 1u);
+        }
+        tc_commit(&accf[a]);
+        tc_commit(&bfree[s]);
+        if (u >= 1 && u - 1 + nst < total) {                      // refill the stage the previous visit used
+          const int sp = (u - 1) % nst;
+          mbar_wait(&bfree[sp], ((u - 1) / nst) & 1);
+          issue_load(u - 1 + nst);
+        }
+      }
+    }
+  } else {
+    // ================================================================ selection warps
+    const int q = warp & 3, m = (warp >> 2) & 1, h = warp >> 3;
+    const int rloc = m * QT + q * 32 + lane;                      // row within the CTA (TMEM lane q*32+lane of block m)
+    const int row = i0 + rloc;
+    const bool m_ok = m < nm;
+    const bool row_ok = row < N;
+    const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * QT + h * 64);
+
+    // ---- patch the query-side copies: channels D..D+2 of the hi image become 1 (the candidate side keeps -sq/2)
+    mbar_wait(abar, 0);
+    if (h == 0 && m_ok) {
+      unsigned char* rowp = sA + (size_t)m * tile_bytes + (size_t)(q * 32 + lane) * 16;
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            if (c0 + 4 * u < D) {
-              dot = __fmaf_rn(a[u].x, bq[u].x, dot);
-              dot = __fmaf_rn(a[u].y, bq[u].y, dot);
-              dot = __fmaf_rn(a[u].z, bq[u].z, dot);
-              dot = __fmaf_rn(a[u].w, bq[u].w, dot);
+      for (int i = 0; i < NAUG; ++i) {
+        const int c = D + i;
+        *reinterpret_cast<unsigned short*>(rowp + (size_t)(c >> 3) * GROUP_BYTES + (c & 7) * 2) = 0x3F80;   // bf16 1.0
+      }
+      fence_proxy_async_smem();
+    }
+    if (h == 0) mbar_arrive(aready);
+
+    const float sqi = sqb[m_ok ? row : i0];
+    const float smax = __uint_as_float(smax_bits[b]);
+    const float eps = 3.4527e-4f * sqrtf(sqi * smax) + 3.8147e-6f * (sqi + smax);   // 2^-11.5, 2^-18
+
+    // ---- pass 1: running maximum of each column class
+    float acc[64];
+#pragma unroll
+    for (int c = 0; c < 64; ++c) acc[c] = -CUDART_INF_F;
+    for (int u = 0; u < ntile; ++u) {
+      const int a = u & 1;
+      mbar_wait(&accf[a], (u >> 1) & 1);
+      tc_fence_after();
+      if (m_ok) {
+        float v[32];
+        tc_ld32(tbase + (uint32_t)(a * 2 * QT), v);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc[c] = fmaxf(acc[c], v[c]);
+        tc_ld32(tbase + (uint32_t)(a * 2 * QT + 32), v);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc[32 + c] = fmaxf(acc[32 + c], v[c]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acce[a]);
+    }
+
+    // ---- k-th largest class maximum of the row (both halves), pass threshold in v space
+    sort64_desc(acc);
+#pragma unroll
+    for (int s = 0; s < 24; ++s)
+      if (s < k) exch[(s * 2 + h) * RB + rloc] = acc[s];
+    named_bar_sync(1, SEL_WARPS * 32);
+    float thr = CUDART_INF_F;
+    {
+      int ia = 0, ib = 0;
+      float vk = 0.f;
+      for (int s = 0; s < k; ++s) {
+        const float va = exch[(ia * 2 + 0) * RB + rloc], vb = exch[(ib * 2 + 1) * RB + rloc];
+        if (va >= vb) { vk = va; ++ia; } else { vk = vb; ++ib; }
+      }
+      if (row_ok && m_ok) thr = vk - eps;
+      if (h == 0) thr_s[rloc] = thr;
+    }
+    named_bar_sync(1, SEL_WARPS * 32);     // every thread has read the exchange area: the candidate lists may alias it
+
+    // ---- pass 2: collect every column whose v reaches the threshold
+    for (int u = ntile; u < total; ++u) {
+      const int a = u & 1;
+      mbar_wait(&accf[a], (u >> 1) & 1);
+      tc_fence_after();
+      if (m_ok) {
+        const int col0 = (u - ntile) * QT + h * 64;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float v[32];
+          tc_ld32(tbase + (uint32_t)(a * 2 * QT + half * 32), v);
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            if (v[c] >= thr) {
+              const int slot = atomicAdd(&cnt[rloc], 1);
+              if (slot < MAXC) cand[rloc * MAXC + slot] = (unsigned short)(col0 + half * 32 + c);
             }
           }
         }
-      } else {
-        for (int c = 0; c < D; ++c) dot = __fmaf_rn(xi[c], xj[c], dot);
       }
-      d = exact_dist(flavour, sqb[row], sqb[j], dot);
-      jj = j;
-      if (!(fabsf(d - ld[r]) <= eps[r]) && flavour == WSPC_DIST_TFUTIL) flag = true;   // error-bound self check
-      if (flavour != WSPC_DIST_TFUTIL) {
-        // the clamp only moves negative values to 0: compare against the clamped approximation
-        const float da = ld[r] > 0.f ? ld[r] : 0.f;
-        if (!(fabsf(d - da) <= eps[r])) flag = true;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acce[a]);
+    }
+    named_bar_sync(1, SEL_WARPS * 32);     // all candidate lists complete
+
+    // ---- exact re-scoring: warp owns 16 rows, lane e owns candidate e
+    const float* xb = x + (size_t)b * N * ldx + coff;
+    const bool vec_ok = ((ldx & 3) == 0) && ((coff & 3) == 0) && ((D & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+#pragma unroll 1
+    for (int r = 0; r < RB / SEL_WARPS; ++r) {
+      const int rl = warp * (RB / SEL_WARPS) + r;
+      const int grow = i0 + rl;
+      if (grow >= N) continue;                                    // warp-uniform
+      const int c = cnt[rl];
+      bool flag = (c > MAXC) || (c < k);
+      const float sq_r = sqb[grow];
+      const float eps_r = 3.4527e-4f * sqrtf(sq_r * smax) + 3.8147e-6f * (sq_r + smax);
+      const float bound = (sq_r - 2.f * thr_s[rl]) + 2.f * eps_r;   // d~ of the threshold + model error (+ rounding slack)
+      float d = CUDART_INF_F;
+      int jj = INT_MAX;
+      if (lane < c && lane < MAXC) {
+        const int j = cand[rl * MAXC + lane];
+        const float* xi = xb + (size_t)grow * ldx;
+        const float* xj = xb + (size_t)j * ldx;
+        float dot = 0.f;
+        if (vec_ok) {   // 16-byte aligned rows: issue all loads first, then the canonical chain (c ascending from +0)
+#pragma unroll 1
+          for (int c0 = 0; c0 < D; c0 += 16) {
+            float4 av[4], bq[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (c0 + 4 * u < D) {
+                av[u] = *reinterpret_cast<const float4*>(xi + c0 + 4 * u);
+                bq[u] = *reinterpret_cast<const float4*>(xj + c0 + 4 * u);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (c0 + 4 * u < D) {
+                dot = __fmaf_rn(av[u].x, bq[u].x, dot);
+                dot = __fmaf_rn(av[u].y, bq[u].y, dot);
+                dot = __fmaf_rn(av[u].z, bq[u].z, dot);
+                dot = __fmaf_rn(av[u].w, bq[u].w, dot);
+              }
+            }
+          }
+        } else {
+          for (int cc = 0; cc < D; ++cc) dot = __fmaf_rn(xi[cc], xj[cc], dot);
+        }
+        d = exact_dist(flavour, sq_r, sqb[j], dot);
+        jj = j;
+        if (!(d <= bound)) flag = true;                            // error-model self check
       }
-    }
-    flag = __any_sync(0xffffffffu, flag);
-    warp_sort_pairs(d, jj, lane);
-    if (lane < k) {
-      const size_t o = ((size_t)b * N + row) * k + lane;
-      idx_out[o] = jj;
-      if (dist_out) dist_out[o] = d;
-    }
-    if (flag && lane == 0) {
-      const int slot = atomicAdd(flag_count, 1);
-      flag_rows[slot] = b * N + row;
+      flag = __any_sync(0xffffffffu, flag);
+      warp_sort_pairs(d, jj, lane);
+      if (lane < k) {
+        const size_t o = ((size_t)b * N + grow) * k + lane;
+        idx_out[o] = jj == INT_MAX ? 0 : jj;
+        if (dist_out) dist_out[o] = d;
+      }
+      if (flag && lane == 0) {
+        const int slot = atomicAdd(flag_count, 1);
+        flag_rows[slot] = b * N + grow;
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  if (warp == SEL_WARPS) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
 // ---------------------------------------------------------------- fallback ---
@@ -435,52 +521,59 @@ knn_exact_rows_kernel(const float* __restrict__ x, const float* __restrict__ sq,
 }  // namespace
 
 // ---------------------------------------------------------------- host ------
-bool knn_tc_eligible(int D, int k) { return D >= 16 && D <= 64 && k <= 24; }
+bool knn_tc_eligible(int N, int D, int k) {
+  if (!(D >= 1 && D <= 64 && k >= 1 && k <= 24 && N >= k && N <= 65535)) return false;
+  return make_tc_plan(1, N, D, k).nst >= 2;
+}
+
+namespace {
+struct TcWs { unsigned char* img; float* sq; unsigned* smax; int* flag_count; int* flag_rows; size_t total; };
+TcWs carve(void* ws, const TcPlan& p, int B, int N) {
+  TcWs w;
+  char* c = static_cast<char*>(ws);
+  w.img = reinterpret_cast<unsigned char*>(c); c += p.img_bytes;
+  w.sq = reinterpret_cast<float*>(c); c += align_up((size_t)B * p.Npad * 4, 256);
+  w.smax = reinterpret_cast<unsigned*>(c); c += align_up((size_t)B * 4, 256);
+  w.flag_count = reinterpret_cast<int*>(c); c += 256;
+  w.flag_rows = reinterpret_cast<int*>(c); c += align_up((size_t)B * N * 4, 256);
+  w.total = (size_t)(c - static_cast<char*>(ws));
+  return w;
+}
+}  // namespace
 
 size_t knn_tc_workspace_bytes(int B, int N, int D) {
-  const int Dp = (D + 15) / 16 * 16, Npad = (N + QT - 1) / QT * QT;
-  const size_t img = (size_t)B * (Npad / QT) * 2 * (Dp / 8) * GROUP_BYTES;
-  return align_up(img, 256) + align_up((size_t)B * Npad * 4, 256) + align_up((size_t)B * 4, 256) + 256 +
-         align_up((size_t)B * N * 4, 256);
+  const TcPlan p = make_tc_plan(B, N, D, 24);
+  return carve(nullptr, p, B, N).total;
 }
 
 // telemetry: number of rows the last knn_tc_run on this workspace sent to the exact fallback (synchronises)
 int knn_tc_fallback_rows(const void* ws, int B, int N, int D, int* out) {
-  const int Dp = (D + 15) / 16 * 16, Npad = (N + QT - 1) / QT * QT;
-  const char* w = static_cast<const char*>(ws);
-  w += align_up((size_t)B * (Npad / QT) * 2 * (Dp / 8) * GROUP_BYTES, 256) + align_up((size_t)B * Npad * 4, 256) +
-       align_up((size_t)B * 4, 256);
-  WSPC_CUDA(cudaMemcpy(out, w, sizeof(int), cudaMemcpyDeviceToHost));
+  const TcPlan p = make_tc_plan(B, N, D, 24);
+  const TcWs w = carve(const_cast<void*>(ws), p, B, N);
+  WSPC_CUDA(cudaMemcpy(out, w.flag_count, sizeof(int), cudaMemcpyDeviceToHost));
   return WSPC_OK;
 }
 
 int knn_tc_run(const float* x, int B, int N, int ldx, int coff, int D, int k, int flavour, int32_t* idx, float* dist,
                void* ws, size_t ws_bytes, cudaStream_t st) {
-  const int Dp = (D + 15) / 16 * 16, Npad = (N + QT - 1) / QT * QT;
+  const TcPlan p = make_tc_plan(B, N, D, k);
   if (ws_bytes < knn_tc_workspace_bytes(B, N, D)) {
     set_error("knn_fused: workspace %zu < required %zu", ws_bytes, knn_tc_workspace_bytes(B, N, D));
     return WSPC_ERR_WORKSPACE;
   }
-  char* w = static_cast<char*>(ws);
-  const size_t img_bytes = align_up((size_t)B * (Npad / QT) * 2 * (Dp / 8) * GROUP_BYTES, 256);
-  unsigned char* img = reinterpret_cast<unsigned char*>(w); w += img_bytes;
-  float* sq = reinterpret_cast<float*>(w); w += align_up((size_t)B * Npad * 4, 256);
-  unsigned* smax = reinterpret_cast<unsigned*>(w); w += align_up((size_t)B * 4, 256);
-  int* flag_count = reinterpret_cast<int*>(w); w += 256;
-  int* flag_rows = reinterpret_cast<int*>(w);
-  WSPC_CUDA(cudaMemsetAsync(smax, 0, align_up((size_t)B * 4, 256) + 256, st));
-  knn_tc_prep_kernel<<<dim3(Npad / QT, B), 128, 0, st>>>(x, N, ldx, coff, D, Dp, Npad, img, sq, smax);
-  const size_t tile_bytes = (size_t)2 * (Dp / 8) * GROUP_BYTES;
-  const size_t smem = (1 + NST) * tile_bytes + (size_t)QT * DLD2 * 4 + NST * QT * 4 + (NST + 3) * 8 + 16;
+  const TcWs w = carve(ws, p, B, N);
+  WSPC_CUDA(cudaMemsetAsync(w.smax, 0, align_up((size_t)B * 4, 256) + 256, st));
+  knn_tc_prep_kernel<<<dim3(p.ntile, B), 128, 0, st>>>(x, N, ldx, coff, D, p.ghi, p.glo, p.Npad, w.img, w.sq, w.smax);
   static thread_local size_t configured = 0;
-  if (smem > configured) {
-    WSPC_CUDA(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+  if (p.smem > configured) {
+    WSPC_CUDA(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    configured = p.smem;
   }
-  knn_tc_kernel<<<dim3(Npad / QT, B), KTC_THREADS, smem, st>>>(img, sq, smax, x, N, Npad, ldx, coff, D, Dp, k, flavour, idx,
-                                                              dist, flag_count, flag_rows);
-  knn_exact_rows_kernel<<<2 * kNumSM, 256, 0, st>>>(x, sq, N, Npad, ldx, coff, D, k, flavour, flag_count, flag_rows, idx,
-                                                    dist);
+  knn_tc_kernel<<<dim3((N + RB - 1) / RB, B), KTC_THREADS, p.smem, st>>>(w.img, w.sq, w.smax, x, N, p.Npad, ldx, coff, D, p.ghi,
+                                                                        p.glo, p.nst, k, flavour, idx, dist, w.flag_count,
+                                                                        w.flag_rows);
+  knn_exact_rows_kernel<<<2 * kNumSM, 256, 0, st>>>(x, w.sq, N, p.Npad, ldx, coff, D, k, flavour, w.flag_count, w.flag_rows,
+                                                    idx, dist);
   count_launch(3);
   WSPC_LAUNCH_CHECK("knn_tc kernels");
   return WSPC_OK;
