@@ -21,6 +21,7 @@ size_t knn_tc_workspace_bytes(int B, int N, int D);
 int knn_tc_run(const float* x, int B, int N, int ldx, int coff, int D, int k, int flavour, int32_t* idx, float* dist,
                void* ws, size_t ws_bytes, cudaStream_t st);
 int knn_tc_fallback_rows(const void* ws, int B, int N, int D, int* out);
+void knn_tc_clear_fallback_rows(void* ws, int B, int N, int D, cudaStream_t st);
 static int g_knn_path = 0;   // 0 = auto (tcgen05 distances + exact re-scoring for wide features), 1 = CUDA-core kernel only
 
 namespace {
@@ -497,7 +498,10 @@ extern "C" int wspc_knn_fused(const float* x, int B, int N, int ldx, int coff, i
   float* xT = static_cast<float*>(workspace);
   float* sq = reinterpret_cast<float*>(static_cast<char*>(workspace) + p.xT_bytes);
   if (int rc = run_prep(p, x, B, N, ldx, coff, D, xT, sq, st)) return rc;
-  return dispatch_tile<0>(p, B, N, k, flavour, xT, sq, idx, dist, nullptr, st);
+  if (int rc = dispatch_tile<0>(p, B, N, k, flavour, xT, sq, idx, dist, nullptr, st)) return rc;
+  if (knn_tc_eligible(N, D, 1) && workspace_bytes >= knn_tc_workspace_bytes(B, N, D))
+    knn_tc_clear_fallback_rows(workspace, B, N, D, st);   // wspc_knn_fallback_rows stays meaningful on this path
+  return WSPC_OK;
 }
 
 extern "C" int wspc_pairwise_distance(const float* x, int B, int N, int ldx, int coff, int D, int flavour,

@@ -395,12 +395,17 @@ knn_tc_kernel(const unsigned char* __restrict__ img, const float* __restrict__ s
         for (int half = 0; half < 2; ++half) {
           float v[32];
           tc_ld32(tbase + (uint32_t)(a * 2 * QT + half * 32), v);
+          // branch-free miss mask: the sign bit of (v - thr) is shifted in, element c lands on bit 31 - c
+          // (v == thr gives +0: a hit; thr = +inf for inactive rows gives -inf or NaN(-inf - -inf never occurs): a miss)
+          unsigned miss = 0u;
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            if (v[c] >= thr) {
-              const int slot = atomicAdd(&cnt[rloc], 1);
-              if (slot < MAXC) cand[rloc * MAXC + slot] = (unsigned short)(col0 + half * 32 + c);
-            }
+          for (int c = 0; c < 32; ++c) miss = __funnelshift_l(__float_as_uint(v[c] - thr), miss, 1);
+          unsigned hits = ~miss;
+          while (hits) {
+            const int c = __clz(hits);
+            hits &= ~(0x80000000u >> c);
+            const int slot = atomicAdd(&cnt[rloc], 1);
+            if (slot < MAXC) cand[rloc * MAXC + slot] = (unsigned short)(col0 + half * 32 + c);
           }
         }
       }
@@ -552,6 +557,11 @@ int knn_tc_fallback_rows(const void* ws, int B, int N, int D, int* out) {
   const TcWs w = carve(const_cast<void*>(ws), p, B, N);
   WSPC_CUDA(cudaMemcpy(out, w.flag_count, sizeof(int), cudaMemcpyDeviceToHost));
   return WSPC_OK;
+}
+
+void knn_tc_clear_fallback_rows(void* ws, int B, int N, int D, cudaStream_t st) {
+  const TcPlan p = make_tc_plan(B, N, D, 24);
+  cudaMemsetAsync(carve(ws, p, B, N).flag_count, 0, sizeof(int), st);
 }
 
 int knn_tc_run(const float* x, int B, int N, int ldx, int coff, int D, int k, int flavour, int32_t* idx, float* dist,
