@@ -7,7 +7,9 @@
 //
 //   prep   : split every feature into bf16 hi + lo and lay 128-point tiles out in the UMMA K-major core-matrix
 //            image ([channel group][row][8]; hi groups then lo groups) so that one 1-D bulk copy (UBLKCP) stages a
-//            whole operand tile.  Three extra "hi" channels carry a 3-way bf16 split of -sq_j/2 (canonical row
+//            whole operand tile.  The approximate pass works on coordinates CENTRED on the cloud mean (distances are
+//            translation invariant; the bf16 split error scales with the norms, so clouds far from the origin would
+//            otherwise get a margin wider than their neighbour spacing); the exact pass uses the original data.  Three extra "hi" channels carry a 3-way bf16 split of -sq_j/2 (canonical row
 //            norm); the query-side copy of the tile has those channels patched to 1, so the accumulator holds
 //            v_ij = x_i.x_j - sq_j/2 directly and d~_ij = sq_i - 2 v_ij: the largest v of a row are its nearest.
 //   main   : CTA = 256 query rows (two M=128 accumulators, double buffered = all 512 TMEM columns), 16 selection
@@ -17,9 +19,11 @@
 //                    registers -- one FMNMX per element.  The k-th largest of a row's 128 class maxima, v_k, is
 //                    reached by k distinct columns, so the exact k-th distance is <= d~(v_k) + eps.
 //            pass 2: the MMAs are replayed and every column with v >= v_k - eps_i is appended to the row's
-//                    candidate list (<= 32 entries).  eps_i bounds |d~ - d_exact| for every pair of row i
-//                    (eps_i = 2^-11.5 sqrt(sq_i smax) + 2^-18 (sq_i + smax): bf16x3 split error 2^-16 |x||y|,
-//                    tensor-core fp32 accumulation, the fp32 roundings of both formulas; >4x head-room), hence
+//                    candidate list (<= 32 entries).  eps_i bounds |d~ - d_exact| for every pair of row i:
+//                    eps_i = 2^-13 sqrt(sq'_i smax') + 2^-18 (sq'_i + smax')      [centred norms: bf16x3 split error
+//                            <= 6*2^-18 |x'||y'| = 2^-15.4, tensor-core fp32 accumulation, centring roundings]
+//                          + (D+3) 2^-23 (|x_i| + sqrt(smax))^2                    [worst-case rounding of the canonical
+//                            fp32 chain sq_i - 2 dot + sq_j on the ORIGINAL coordinates], hence
 //                    every exact top-k member t has d~_t <= d_t + eps <= d~(v_k) + 2 eps, i.e. v_t >= v_k - eps.
 //                    More than 32 candidates (heavy ties / clustered classes) flags the row.
 //   refine : each lane recomputes the canonical fp32 distance of its candidate (same fmaf chain as the oracle),
@@ -116,22 +120,46 @@ TcPlan make_tc_plan(int B, int N, int D, int k) {
 }
 
 // ------------------------------------------------------------------ prep ---
+// per-cloud centre (fp32 mean of the channel window; any vector would do, it only conditions the approximate pass)
+__global__ void __launch_bounds__(256)
+knn_tc_centre_kernel(const float* __restrict__ x, int N, int ldx, int coff, int D, float* __restrict__ centre) {
+  __shared__ float red[256];
+  const int b = blockIdx.x;
+  const float* xb = x + (size_t)b * N * ldx + coff;
+  for (int c = 0; c < D; ++c) {
+    float s = 0.f;
+    for (int n = threadIdx.x; n < N; n += 256) s += xb[(size_t)n * ldx + c];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) centre[b * 64 + c] = red[0] / (float)N;
+    __syncthreads();
+  }
+}
+
 // grid (Npad/128, B), block 128: thread = point.  img per (cloud, tile): [hi: ghi groups][lo: glo groups] x [128][8] bf16
 __global__ void __launch_bounds__(128)
 knn_tc_prep_kernel(const float* __restrict__ x, int N, int ldx, int coff, int D, int ghi, int glo, int Npad,
-                   unsigned char* __restrict__ img, float* __restrict__ sq, unsigned* __restrict__ smax_bits) {
+                   const float* __restrict__ centre, unsigned char* __restrict__ img, float* __restrict__ sq,
+                   float* __restrict__ sqc, unsigned* __restrict__ smax_bits) {
   const int b = blockIdx.y, tile = blockIdx.x, r = threadIdx.x;
   const int n = tile * QT + r;
   const size_t tile_bytes = (size_t)(ghi + glo) * GROUP_BYTES;
   unsigned char* base = img + ((size_t)b * (Npad / QT) + tile) * tile_bytes;
   const float* xr = x + ((size_t)b * N + (n < N ? n : 0)) * ldx + coff;
-  float acc = 0.f;
-  for (int c = 0; c < D; ++c) {             // canonical chain
+  const float* cb = centre + b * 64;
+  float acc = 0.f, accc = 0.f;
+  for (int c = 0; c < D; ++c) {             // canonical chain on the original data; centred norm for the approximation
     const float v = n < N ? xr[c] : 0.f;
     acc = __fmaf_rn(v, v, acc);
+    const float vc = n < N ? v - cb[c] : 0.f;
+    accc = __fmaf_rn(vc, vc, accc);
   }
-  // 3-way bf16 split of -sq/2 (exact to 2^-24); padded points get a huge negative value: they never win
-  const float s = n < N ? -0.5f * acc : -1.0e30f;
+  // 3-way bf16 split of -sq'/2 (exact to 2^-24); padded points get a huge negative value: they never win
+  const float s = n < N ? -0.5f * accc : -1.0e30f;
   const __nv_bfloat16 a1 = __float2bfloat16_rn(s);
   const float r1 = s - __bfloat162float(a1);
   const __nv_bfloat16 a2 = __float2bfloat16_rn(r1);
@@ -144,7 +172,7 @@ knn_tc_prep_kernel(const float* __restrict__ x, int N, int ldx, int coff, int D,
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int c = g * 8 + 2 * i + e;
-        const float v = (n < N && c < D) ? xr[c] : 0.f;
+        const float v = (n < N && c < D) ? xr[c] - cb[c] : 0.f;
         __nv_bfloat16 hb = __float2bfloat16_rn(v);
         const __nv_bfloat16 lb = __float2bfloat16_rn(v - __bfloat162float(hb));
         if (c == D) hb = a1;
@@ -164,7 +192,17 @@ knn_tc_prep_kernel(const float* __restrict__ x, int N, int ldx, int coff, int D,
     for (int g = 0; g < ghi + glo; ++g) *reinterpret_cast<uint4*>(base + (size_t)g * GROUP_BYTES + QT * 16) = make_uint4(0, 0, 0, 0);
   }
   sq[(size_t)b * Npad + n] = acc;
-  if (n < N) atomicMax(smax_bits + b, __float_as_uint(acc));   // acc >= 0: uint order == float order
+  sqc[(size_t)b * Npad + n] = accc;
+  if (n < N) {   // norms >= 0: uint order == float order
+    atomicMax(smax_bits + 2 * b, __float_as_uint(acc));
+    atomicMax(smax_bits + 2 * b + 1, __float_as_uint(accc));
+  }
+}
+
+// error model shared by the selection and the refine phase (see the header comment)
+__device__ __forceinline__ float knn_eps(float sq_i, float smax, float sqc_i, float smaxc, int D) {
+  const float t = sqrtf(sq_i) + sqrtf(smax);
+  return 1.2207e-4f * sqrtf(sqc_i * smaxc) + 3.8147e-6f * (sqc_i + smaxc) + (float)(D + 3) * 1.1921e-7f * t * t;
 }
 
 // ---------------------------------------------------------- register lists ---
@@ -220,8 +258,8 @@ __device__ __forceinline__ void sort64_desc(float (&a)[64]) {
 
 // ------------------------------------------------------------------ main ---
 __global__ void __launch_bounds__(KTC_THREADS, 1)
-knn_tc_kernel(const unsigned char* __restrict__ img, const float* __restrict__ sq, const unsigned* __restrict__ smax_bits,
-              const float* __restrict__ x, int N, int Npad, int ldx, int coff, int D, int ghi, int glo, int nst, int k,
+knn_tc_kernel(const unsigned char* __restrict__ img, const float* __restrict__ sq, const float* __restrict__ sqc,
+              const unsigned* __restrict__ smax_bits, const float* __restrict__ x, int N, int Npad, int ldx, int coff, int D, int ghi, int glo, int nst, int k,
               int flavour, int32_t* __restrict__ idx_out, float* __restrict__ dist_out, int* __restrict__ flag_count,
               int* __restrict__ flag_rows) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -248,6 +286,7 @@ knn_tc_kernel(const unsigned char* __restrict__ img, const float* __restrict__ s
   const int nm = (blockIdx.x * 2 + 1 < ntile) ? 2 : 1;            // M blocks present in this row block
   const unsigned char* imgb = img + (size_t)b * ntile * tile_bytes;
   const float* sqb = sq + (size_t)b * Npad;
+  const float* sqcb = sqc + (size_t)b * Npad;
   const int total = 2 * ntile;                                    // tile visits: pass 1 then pass 2
 
   if (warp == SEL_WARPS) {
@@ -339,9 +378,8 @@ knn_tc_kernel(const unsigned char* __restrict__ img, const float* __restrict__ s
     }
     if (h == 0) mbar_arrive(aready);
 
-    const float sqi = sqb[m_ok ? row : i0];
-    const float smax = __uint_as_float(smax_bits[b]);
-    const float eps = 3.4527e-4f * sqrtf(sqi * smax) + 3.8147e-6f * (sqi + smax);   // 2^-11.5, 2^-18
+    const float smax = __uint_as_float(smax_bits[2 * b]), smaxc = __uint_as_float(smax_bits[2 * b + 1]);
+    const float eps = knn_eps(sqb[m_ok ? row : i0], smax, sqcb[m_ok ? row : i0], smaxc, D);
 
     // ---- pass 1: running maximum of each column class
     float acc[64];
@@ -425,9 +463,9 @@ knn_tc_kernel(const unsigned char* __restrict__ img, const float* __restrict__ s
       if (grow >= N) continue;                                    // warp-uniform
       const int c = cnt[rl];
       bool flag = (c > MAXC) || (c < k);
-      const float sq_r = sqb[grow];
-      const float eps_r = 3.4527e-4f * sqrtf(sq_r * smax) + 3.8147e-6f * (sq_r + smax);
-      const float bound = (sq_r - 2.f * thr_s[rl]) + 2.f * eps_r;   // d~ of the threshold + model error (+ rounding slack)
+      const float sq_r = sqb[grow], sqc_r = sqcb[grow];
+      const float eps_r = knn_eps(sq_r, smax, sqc_r, smaxc, D);
+      const float bound = (sqc_r - 2.f * thr_s[rl]) + 2.f * eps_r;  // d~ of the threshold + model error (+ rounding slack)
       float d = CUDART_INF_F;
       int jj = INT_MAX;
       if (lane < c && lane < MAXC) {
@@ -532,13 +570,15 @@ bool knn_tc_eligible(int N, int D, int k) {
 }
 
 namespace {
-struct TcWs { unsigned char* img; float* sq; unsigned* smax; int* flag_count; int* flag_rows; size_t total; };
+struct TcWs { unsigned char* img; float* sq; float* sqc; float* centre; unsigned* smax; int* flag_count; int* flag_rows; size_t total; };
 TcWs carve(void* ws, const TcPlan& p, int B, int N) {
   TcWs w;
   char* c = static_cast<char*>(ws);
   w.img = reinterpret_cast<unsigned char*>(c); c += p.img_bytes;
   w.sq = reinterpret_cast<float*>(c); c += align_up((size_t)B * p.Npad * 4, 256);
-  w.smax = reinterpret_cast<unsigned*>(c); c += align_up((size_t)B * 4, 256);
+  w.sqc = reinterpret_cast<float*>(c); c += align_up((size_t)B * p.Npad * 4, 256);
+  w.centre = reinterpret_cast<float*>(c); c += align_up((size_t)B * 64 * 4, 256);
+  w.smax = reinterpret_cast<unsigned*>(c); c += align_up((size_t)B * 8, 256);
   w.flag_count = reinterpret_cast<int*>(c); c += 256;
   w.flag_rows = reinterpret_cast<int*>(c); c += align_up((size_t)B * N * 4, 256);
   w.total = (size_t)(c - static_cast<char*>(ws));
@@ -572,19 +612,21 @@ int knn_tc_run(const float* x, int B, int N, int ldx, int coff, int D, int k, in
     return WSPC_ERR_WORKSPACE;
   }
   const TcWs w = carve(ws, p, B, N);
-  WSPC_CUDA(cudaMemsetAsync(w.smax, 0, align_up((size_t)B * 4, 256) + 256, st));
-  knn_tc_prep_kernel<<<dim3(p.ntile, B), 128, 0, st>>>(x, N, ldx, coff, D, p.ghi, p.glo, p.Npad, w.img, w.sq, w.smax);
+  WSPC_CUDA(cudaMemsetAsync(w.smax, 0, align_up((size_t)B * 8, 256) + 256, st));
+  knn_tc_centre_kernel<<<B, 256, 0, st>>>(x, N, ldx, coff, D, w.centre);
+  knn_tc_prep_kernel<<<dim3(p.ntile, B), 128, 0, st>>>(x, N, ldx, coff, D, p.ghi, p.glo, p.Npad, w.centre, w.img, w.sq, w.sqc,
+                                                      w.smax);
   static thread_local size_t configured = 0;
   if (p.smem > configured) {
     WSPC_CUDA(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     configured = p.smem;
   }
-  knn_tc_kernel<<<dim3((N + RB - 1) / RB, B), KTC_THREADS, p.smem, st>>>(w.img, w.sq, w.smax, x, N, p.Npad, ldx, coff, D, p.ghi,
+  knn_tc_kernel<<<dim3((N + RB - 1) / RB, B), KTC_THREADS, p.smem, st>>>(w.img, w.sq, w.sqc, w.smax, x, N, p.Npad, ldx, coff, D, p.ghi,
                                                                         p.glo, p.nst, k, flavour, idx, dist, w.flag_count,
                                                                         w.flag_rows);
   knn_exact_rows_kernel<<<2 * kNumSM, 256, 0, st>>>(x, w.sq, N, p.Npad, ldx, coff, D, k, flavour, w.flag_count, w.flag_rows,
                                                     idx, dist);
-  count_launch(3);
+  count_launch(4);
   WSPC_LAUNCH_CHECK("knn_tc kernels");
   return WSPC_OK;
 }
