@@ -214,6 +214,27 @@ int wspc_head_losses(const float* Z, const float* Y, const float* Mask, const in
                      int B, int N, int C, int knn, float gamma, float siam_w, int full, int want_grad, float* P,
                      float* dZ, float* losses, void* workspace, size_t workspace_bytes, wspc_stream_t stream);
 
+/* ------------------------------------------- factored EdgeConv first layer --- */
+/* The first conv2d of every EdgeConv block reads e_ij = [x_i | x_j - x_i] (tf_util.get_edge_feature,
+ * tf_util.py:674-706; DGCNN_S3DIS.py:34-39,50-55,66-71; DGCNN_ShapeNet.py:24-37; transform_nets.py:17-20) with
+ * W = [W1; W2] (2*Cx, Cout).  y_ij = x_i (W1 - W2) + x_j W2 + b = u_i + v_j + b, so the P*k-row GEMM becomes one
+ * P-row GEMM [u | v] = X Wc (wspc_conv1x1_rows) plus the gather-add below; the backward pass is the transpose.
+ * Cout must be 64.
+ *   wspc_edge_split_weights : Wc (Cx, 2*Cout) = [W1 - W2 | W2]
+ *   wspc_edge_combine_fwd   : y (P*k, Cout) = U[i] + V[cloud(i)*npts + idx[i,j]] + bias; stats[2][Cout] (fp64, may be
+ *                             NULL) += column sums / sums of squares (batch-norm moments, tf_util.py:521-522)
+ *   wspc_edge_combine_bwd   : dy = c1*G + c2 + c3*y (c1 == NULL: dy = G); DUV[i, 0:Cout] = sum_j dy_ij;
+ *                             DUV[cloud(i)*npts + idx[i,j], Cout:2*Cout] += dy_ij (red.global.add.v4, caller zeroes)
+ *   wspc_edge_merge_wgrad   : dW (2*Cx, Cout) from dWc (Cx, 2*Cout): dW1 = dWa, dW2 = dWb - dWa; db = dbc[0:Cout] */
+int wspc_edge_split_weights(const float* W, int Cx, int Cout, float* Wc, wspc_stream_t stream);
+int wspc_edge_combine_fwd(const float* UV, long long ldu, const int32_t* idx, const float* bias, long long P, int k,
+                          int npts, int Cout, float* y, double* stats, wspc_stream_t stream);
+int wspc_edge_combine_bwd(const float* G, const float* y, const float* c1, const float* c2, const float* c3,
+                          const int32_t* idx, long long P, int k, int npts, int Cout, float* DUV, long long ldd,
+                          wspc_stream_t stream);
+int wspc_edge_merge_wgrad(const float* dWc, const float* dbc, int Cx, int Cout, float* dW, float* db,
+                          wspc_stream_t stream);
+
 /* ------------------------------------------------------------ optimiser --- */
 /* tf.train.AdamOptimizer update on flat fp32 buffers (eps not bias-corrected);
  * lr_t = lr*sqrt(1-b2^t)/(1-b1^t) is computed by the caller; gscale multiplies g (1/world_size). */

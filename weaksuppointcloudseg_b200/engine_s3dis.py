@@ -61,6 +61,8 @@ class S3DISEngine:
         self.losses = torch.zeros(5, **f32)
         self.zero_bias = torch.zeros(512, **f32)
         self.seed = 1234
+        # first conv2d of each EdgeConv block: factored (csrc/edge.cu) unless WSPC_EDGE=gemm asks for the gathered GEMM
+        self.es = rt.EdgeSplit(P, self.dev) if rt.EDGE_FACTORED else None
         self.prof = None   # optional list of (tag, start_event, end_event) filled around the kNN launches
 
     def _tick(self):
@@ -98,19 +100,30 @@ class S3DISEngine:
 
         # block 1: kNN on normalised xyz (ch 6:9), edge feature of all 9 channels      (:32-46)
         knn_into(0, X.data_ptr(), 9, self.knn_coff, 3)
-        rt.conv_forward(Ly["adj_conv1"], rt.op_edge(X, 9, 9, self.idx[0], k, N), R, self.y[0], 64, is_training, bn_decay)
+        if self.es is not None:
+            rt.edge_first_forward(self.es, Ly["adj_conv1"], X, 9, 9, self.idx[0], k, N, P, self.y[0], is_training, bn_decay)
+        else:
+            rt.conv_forward(Ly["adj_conv1"], rt.op_edge(X, 9, 9, self.idx[0], k, N), R, self.y[0], 64, is_training, bn_decay)
         rt.conv_forward(Ly["adj_conv2"], rt.op_bnrelu(self.y[0], Ly["adj_conv1"]), R, self.y[1], 64, is_training, bn_decay)
         rt.maxk_fwd(Ly["adj_conv2"], self.y[1], P, k, cat_a, 192)
         # block 2                                                                       (:48-62)
         knn_into(1, cat_a, 192, 0, 64)
-        rt.conv_forward(Ly["adj_conv3"], rt.op_edge(self.cat, 192, 64, self.idx[1], k, N), R, self.y[2], 64, is_training,
-                        bn_decay)
+        if self.es is not None:
+            rt.edge_first_forward(self.es, Ly["adj_conv3"], cat_a, 192, 64, self.idx[1], k, N, P, self.y[2], is_training,
+                                  bn_decay)
+        else:
+            rt.conv_forward(Ly["adj_conv3"], rt.op_edge(self.cat, 192, 64, self.idx[1], k, N), R, self.y[2], 64, is_training,
+                            bn_decay)
         rt.conv_forward(Ly["adj_conv4"], rt.op_bnrelu(self.y[2], Ly["adj_conv3"]), R, self.y[3], 64, is_training, bn_decay)
         rt.maxk_fwd(Ly["adj_conv4"], self.y[3], P, k, cat_a + 4 * 64, 192)
         # block 3                                                                       (:64-78)
         knn_into(2, cat_a, 192, 64, 64)
-        e3 = L.Operand(p=cat_a + 4 * 64, ld=192, C=128, idx=L.dptr(self.idx[2]), k=k, npts=N), L.OP_EDGE
-        rt.conv_forward(Ly["adj_conv5"], e3, R, self.y[4], 64, is_training, bn_decay)
+        if self.es is not None:
+            rt.edge_first_forward(self.es, Ly["adj_conv5"], cat_a + 4 * 64, 192, 64, self.idx[2], k, N, P, self.y[4],
+                                  is_training, bn_decay)
+        else:
+            e3 = L.Operand(p=cat_a + 4 * 64, ld=192, C=128, idx=L.dptr(self.idx[2]), k=k, npts=N), L.OP_EDGE
+            rt.conv_forward(Ly["adj_conv5"], e3, R, self.y[4], 64, is_training, bn_decay)
         rt.maxk_fwd(Ly["adj_conv5"], self.y[4], P, k, cat_a + 4 * 128, 192)
         # adj_conv7 + max over points                                                   (:80-85)
         l7 = Ly["adj_conv7"]
@@ -200,11 +213,15 @@ class S3DISEngine:
         # block 3
         rt.maxk_bwd(c5, self.y[4], P, k, cat_a + 4 * 128, 192, dcat_a + 4 * 128, 192, self.Ga)
         rt.bn_bwd_coeffs(c5, R)
-        G5 = rt.op_dy(self.Ga, 64, self.y[4], 64, c5, 64)
-        A5 = L.Operand(p=cat_a + 4 * 64, ld=192, C=128, idx=L.dptr(self.idx[2]), k=k, npts=N), L.OP_EDGE
-        rt.wgrad(A5, G5, R, c5.dW, c5.db, dev)
-        e, m = rt.epi_scatter(dcat_a + 4 * 64, 192, self.idx[2], k, N)
-        rt.rows_gemm(G5, c5.W, 64, 1, R, 128, 64, e, m)
+        if self.es is not None:
+            rt.edge_first_backward(self.es, c5, cat_a + 4 * 64, 192, 64, self.idx[2], k, N, P, self.Ga, self.y[4],
+                                   dcat_a + 4 * 64, 192)
+        else:
+            G5 = rt.op_dy(self.Ga, 64, self.y[4], 64, c5, 64)
+            A5 = L.Operand(p=cat_a + 4 * 64, ld=192, C=128, idx=L.dptr(self.idx[2]), k=k, npts=N), L.OP_EDGE
+            rt.wgrad(A5, G5, R, c5.dW, c5.db, dev)
+            e, m = rt.epi_scatter(dcat_a + 4 * 64, 192, self.idx[2], k, N)
+            rt.rows_gemm(G5, c5.W, 64, 1, R, 128, 64, e, m)
         # block 2
         rt.maxk_bwd(c4, self.y[3], P, k, cat_a + 4 * 64, 192, dcat_a + 4 * 64, 192, self.Ga)
         rt.bn_bwd_coeffs(c4, R)
@@ -213,10 +230,13 @@ class S3DISEngine:
         e, m = rt.epi_relumask(self.Gb, c3, self.y[2])
         rt.rows_gemm(G4, c4.W, 64, 1, R, 64, 64, e, m)
         rt.bn_bwd_coeffs(c3, R)
-        G3e = rt.op_dy(self.Gb, 64, self.y[2], 64, c3, 64)
-        rt.wgrad(rt.op_edge(self.cat, 192, 64, self.idx[1], k, N), G3e, R, c3.dW, c3.db, dev)
-        e, m = rt.epi_scatter(dcat_a, 192, self.idx[1], k, N)
-        rt.rows_gemm(G3e, c3.W, 64, 1, R, 128, 64, e, m)
+        if self.es is not None:
+            rt.edge_first_backward(self.es, c3, cat_a, 192, 64, self.idx[1], k, N, P, self.Gb, self.y[2], dcat_a, 192)
+        else:
+            G3e = rt.op_dy(self.Gb, 64, self.y[2], 64, c3, 64)
+            rt.wgrad(rt.op_edge(self.cat, 192, 64, self.idx[1], k, N), G3e, R, c3.dW, c3.db, dev)
+            e, m = rt.epi_scatter(dcat_a, 192, self.idx[1], k, N)
+            rt.rows_gemm(G3e, c3.W, 64, 1, R, 128, 64, e, m)
         # block 1 (no gradient w.r.t. the input cloud)
         rt.maxk_bwd(c2, self.y[1], P, k, cat_a, 192, dcat_a, 192, self.Ga)
         rt.bn_bwd_coeffs(c2, R)
@@ -225,8 +245,11 @@ class S3DISEngine:
         e, m = rt.epi_relumask(self.Gb, c1, self.y[0])
         rt.rows_gemm(G2e, c2.W, 64, 1, R, 64, 64, e, m)
         rt.bn_bwd_coeffs(c1, R)
-        G1e = rt.op_dy(self.Gb, 64, self.y[0], 64, c1, 64)
-        rt.wgrad(rt.op_edge(self.X, 9, 9, self.idx[0], k, N), G1e, R, c1.dW, c1.db, dev)
+        if self.es is not None:
+            rt.edge_first_backward(self.es, c1, self.X, 9, 9, self.idx[0], k, N, P, self.Gb, self.y[0])
+        else:
+            G1e = rt.op_dy(self.Gb, 64, self.y[0], 64, c1, 64)
+            rt.wgrad(rt.op_edge(self.X, 9, 9, self.idx[0], k, N), G1e, R, c1.dW, c1.db, dev)
 
     # ------------------------------------------------------------------------------ train step ---
     def train_step(self, X, Y, Mask, lr, bn_decay, full=True, dropout_mask=None, knn_override=None, smooth_graph=None,

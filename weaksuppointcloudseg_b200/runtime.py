@@ -7,6 +7,7 @@ device memory and the stream.
 from __future__ import annotations
 
 import ctypes
+import os
 import math
 from collections import OrderedDict
 
@@ -214,3 +215,65 @@ def maxk_bwd(layer: Layer, y, P, k, out_addr, ldo, dout_addr, lddo, G):
     L.check(L.lib().wspc_maxk_bnrelu_bwd(L.ptr(y), L.ptr(layer.sc), L.ptr(layer.sh), ctypes.c_void_p(out_addr), ldo,
                                          ctypes.c_void_p(dout_addr), lddo, P, k, layer.cout, L.ptr(G),
                                          L.ptr(layer.bstats), L.stream()))
+
+
+# ---- factored first layer of an EdgeConv block (csrc/edge.cu) ---------------------------------------
+# WSPC_EDGE=gemm keeps the gathered-operand GEMM formulation (another device kernel, used for A/B tests)
+EDGE_FACTORED = os.environ.get("WSPC_EDGE", "factored") != "gemm"
+
+
+class EdgeSplit:
+    """Scratch shared by the first conv2d of every EdgeConv block of one engine:
+    y_ij = x_i (W1 - W2) + x_j W2 + b  (tf_util.py:696-705 feeding tf_util.conv2d, e.g. DGCNN_S3DIS.py:34-39)."""
+
+    def __init__(self, P, device, max_cx=64):
+        f32 = dict(dtype=torch.float32, device=device)
+        self.P = P
+        self.UV = torch.empty((P, 128), **f32)       # [u | v] forward
+        self.DUV = torch.empty((P, 128), **f32)      # [du | dv] backward
+        self.dWc = torch.empty((max_cx, 128), **f32)
+        self.dbc = torch.empty(128, **f32)
+        self.Wc = {}                                 # per layer: [W1 - W2 | W2] of the current step
+
+    def weights(self, layer: Layer, cx):
+        w = self.Wc.get(layer.scope)
+        if w is None:
+            w = self.Wc[layer.scope] = torch.empty((cx, 128), dtype=torch.float32, device=self.UV.device)
+        L.check(L.lib().wspc_edge_split_weights(L.ptr(layer.W), cx, layer.cout, L.ptr(w), L.stream()))
+        return w
+
+
+def edge_first_forward(es: EdgeSplit, layer: Layer, x, ld, cx, idx, k, npts, P, y_out, training, decay):
+    """x: tensor or raw address of the (P, ld) point features (cx channels used).  Writes pre-BN y_out (P*k, 64) and
+    the layer's batch-norm scale/shift, exactly like conv_forward(op_edge(...))."""
+    assert layer.cout == 64 and layer.cin == 2 * cx
+    Wc = es.weights(layer, cx)
+    xa = x if isinstance(x, int) else x.data_ptr()
+    A = (L.Operand(p=xa, ld=ld, C=cx), L.OP_PLAIN)
+    rows_gemm(A, Wc, 128, 0, P, 128, cx, L.Epilogue(out=L.dptr(es.UV), ldo=128), L.EPI_STORE)
+    stats = None
+    if layer.has_bn and training:
+        zero_(layer.stats)
+        stats = layer.stats
+    L.check(L.lib().wspc_edge_combine_fwd(L.ptr(es.UV), 128, L.ptr(idx), L.ptr(layer.b), P, k, npts, 64, L.ptr(y_out),
+                                          L.ptr(stats), L.stream()))
+    if layer.has_bn:
+        bn_finalize(layer, P * k, training, decay)
+
+
+def edge_first_backward(es: EdgeSplit, layer: Layer, x, ld, cx, idx, k, npts, P, G, y, dx_addr=None, lddx=0):
+    """Gradients of the factored layer: layer.dW / layer.db, and (if dx_addr) dX accumulated into (P, lddx) at dx_addr.
+    G is the gradient w.r.t. the BN output (bn_bwd_coeffs(layer, P*k) must have run), y the saved pre-BN output."""
+    xa = x if isinstance(x, int) else x.data_ptr()
+    Wc = es.Wc[layer.scope]
+    zero_(es.DUV)
+    bn = layer.has_bn
+    L.check(L.lib().wspc_edge_combine_bwd(L.ptr(G), L.ptr(y) if bn else None, L.ptr(layer.c1) if bn else None,
+                                          L.ptr(layer.c2) if bn else None, L.ptr(layer.c3) if bn else None, L.ptr(idx), P, k,
+                                          npts, 64, L.ptr(es.DUV), 128, L.stream()))
+    D = (L.Operand(p=L.dptr(es.DUV), ld=128, C=128), L.OP_DY)
+    A = (L.Operand(p=xa, ld=ld, C=cx), L.OP_PLAIN)
+    wgrad(A, D, P, es.dWc, es.dbc, es.UV.device)
+    L.check(L.lib().wspc_edge_merge_wgrad(L.ptr(es.dWc), L.ptr(es.dbc), cx, 64, L.ptr(layer.dW), L.ptr(layer.db), L.stream()))
+    if dx_addr is not None:
+        rows_gemm(D, Wc, 128, 1, P, cx, 128, L.Epilogue(out=dx_addr, ldo=lddx), L.EPI_ACCUM)
