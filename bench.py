@@ -230,9 +230,11 @@ def run_ours(args):
     stage_bytes = 2 * knn_bytes(64, 20) + knn_bytes(3, 20) + knn_bytes(6, 10)
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
-        # dram__bytes_read+write of this kernel from the ncu --set full capture (profiles/r1_knn_d64_summary.md):
-        # 17.1 MB at B=16, linear in the number of clouds
-        "traffic": 17.08e6 * B / 16.0, "kernel": "knn_tile_kernel<32,1,0> (fused distance+top-k, D=64, k=20)",
+        # dram__bytes_read+write of this kernel from the ncu --set full capture (profiles/r1_knn_tc_d64_summary.md):
+        # 36.14 MB at B=16, linear in the number of clouds
+        "traffic": 36.14e6 * B / 16.0,
+        "kernel": "knn_tc_kernel (tcgen05 distances + two-pass threshold selection + exact re-scoring, D=64, k=20; "
+                  "launch time includes its prep/centre/fallback kernels)",
         "peak_source": peak_src, "algorithmic_bytes_per_launch": knn_bytes(64, 20), "ms_per_launch": dom_ms,
         "knn_stage": {"ms_per_step": stage_ms, "equiv_GBs": stage_bytes / stage_ms / 1e6, "frac": stage_bytes / stage_ms / 1e6 / peak,
                       "per_call_ms": {k_: statistics.mean(v) for k_, v in per_tag.items()}},

@@ -147,11 +147,16 @@ def test_s3dis_step_against_reference_code(cuda):
     # Adam on the engine's own gradients reproduces the reference's updated weights where |g| >> eps
     eng.vs.adam_step(1e-3)
     after = eng.vs.export()
+    gmax = max(np.abs(f[k_]).max() for k_ in f.files if k_.startswith("grad/"))
     for n in eng.vs.trainable_names:
         if "after/" + n not in f.files or "grad/" + n not in f.files:
             continue
         g = f["grad/" + n].reshape(params0[n].shape)
-        well = np.abs(g) > 1e-3 * np.abs(g).max()
+        if np.abs(g).max() < 1e-4 * gmax:      # analytically zero gradient (bias in front of a batch norm): pure noise
+            continue
+        # first Adam step = lr * g / (|g| + eps'): sign-like, so only elements whose sign cannot be flipped by the
+        # ~1e-2 gradient noise discussed above are compared
+        well = np.abs(g) > 0.2 * np.abs(g).max()
         if well.any():
             assert np.abs(after[n] - f["after/" + n])[well].max() <= 2e-4, n
 

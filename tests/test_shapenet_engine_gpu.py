@@ -21,7 +21,9 @@ def rel(a, b):
 def setup(cuda):
     from weaksuppointcloudseg_b200.engine_shapenet import ShapeNetEngine
 
-    n_samples, N = 3, 320
+    # 8 Siamese samples = 16 clouds: the T-net's FC layers batch-normalise over the clouds, and with a handful of
+    # clouds one ReLU flip of a near-zero pre-activation moves a whole channel's gradient by several percent
+    n_samples, N = 8, 256
     X, lab, Y, M, _ = syn.shapenet_batch(n_samples, N=N, n_labelled=32, seed=21)
     B = 2 * n_samples
     params = od.init_params(od.SHAPENET_LAYERS, seed=8, shapenet=True)

@@ -61,57 +61,92 @@ __global__ void bn_bwd_coeffs_kernel(const double* __restrict__ stats, int C, do
 }
 
 // ------------------------------------------------------------- max over k ---
-// one thread per (point, channel): channels fastest => coalesced rows of C floats
-__global__ void maxk_fwd_kernel(const float* __restrict__ y, const float* __restrict__ sc, const float* __restrict__ sh,
-                                long long P, int k, int C, float* __restrict__ out, long long ldo) {
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= P * C) return;
-  const long long p = t / C;
-  const int c = (int)(t - p * C);
-  const float s = sc[c], h = sh[c];
-  const float* yp = y + p * k * C + c;
-  float m = 0.f;  // relu output is >= 0
-  for (int r = 0; r < k; ++r) m = fmaxf(m, fmaf(yp[(size_t)r * C], s, h));
-  out[p * ldo + c] = m;
+// one thread per (point, 4 channels): float4 rows => every warp instruction moves 512 contiguous bytes
+__device__ __forceinline__ float4 bnrelu4(float4 v, float4 s, float4 h) {
+  return make_float4(fmaxf(fmaf(v.x, s.x, h.x), 0.f), fmaxf(fmaf(v.y, s.y, h.y), 0.f), fmaxf(fmaf(v.z, s.z, h.z), 0.f),
+                     fmaxf(fmaf(v.w, s.w, h.w), 0.f));
 }
 
-__global__ void maxk_bwd_kernel(const float* __restrict__ y, const float* __restrict__ sc, const float* __restrict__ sh,
-                                const float* __restrict__ out, long long ldo, const float* __restrict__ dout,
-                                long long lddo, long long P, int k, int C, float* __restrict__ G,
-                                double* __restrict__ stats) {
-  __shared__ float red[2][128];
-  const int tid = threadIdx.x;
-  // block covers (blockDim.x / C) points x C channels (C divides 256, C <= 128)
-  const long long t = (long long)blockIdx.x * blockDim.x + tid;
-  const bool valid = t < P * C;
-  const long long p = valid ? t / C : 0;
-  const int c = valid ? (int)(t - p * C) : 0;
-  (&red[0][0])[tid] = 0.f;  // blockDim.x == 256 == 2*128
-  __syncthreads();
-  float s0 = 0.f, s1 = 0.f;
-  if (valid) {
-    const float s = sc[c], h = sh[c];
-    const float m = out[p * ldo + c];
-    const float go = dout[p * lddo + c];
-    const float* yp = y + p * k * C + c;
-    float* gp = G + p * k * C + c;
-    int cnt = 0;
-    if (m > 0.f) {
-      for (int r = 0; r < k; ++r) cnt += (fmaxf(fmaf(yp[(size_t)r * C], s, h), 0.f) == m) ? 1 : 0;
-    }
-    const float share = (cnt > 0) ? go / (float)cnt : 0.f;
-    for (int r = 0; r < k; ++r) {
-      const float yv = yp[(size_t)r * C];
-      const bool hit = (m > 0.f) && (fmaxf(fmaf(yv, s, h), 0.f) == m);
-      const float g = hit ? share : 0.f;
-      gp[(size_t)r * C] = g;
-      s0 += g;
-      s1 += g * yv;
+__global__ void __launch_bounds__(256)
+maxk_fwd_kernel(const float* __restrict__ y, const float* __restrict__ sc, const float* __restrict__ sh,
+                long long P, int k, int C, float* __restrict__ out, long long ldo) {
+  const int C4 = C >> 2;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= P * C4) return;
+  const long long p = t / C4;
+  const int c = (int)(t - p * C4) * 4;
+  const float4 s = *reinterpret_cast<const float4*>(sc + c), h = *reinterpret_cast<const float4*>(sh + c);
+  const float* yp = y + p * k * C + c;
+  float4 m = make_float4(0.f, 0.f, 0.f, 0.f);  // relu output is >= 0
+  int r = 0;
+  for (; r + 4 <= k; r += 4) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = __ldcs(reinterpret_cast<const float4*>(yp + (size_t)(r + u) * C));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float4 a = bnrelu4(v[u], s, h);
+      m.x = fmaxf(m.x, a.x); m.y = fmaxf(m.y, a.y); m.z = fmaxf(m.z, a.z); m.w = fmaxf(m.w, a.w);
     }
   }
-  // channels repeat with period C inside the block (blockDim % C == 0 guaranteed by the wrapper)
-  atomicAdd(&red[0][c], s0);
-  atomicAdd(&red[1][c], s1);
+  for (; r < k; ++r) {
+    const float4 a = bnrelu4(__ldcs(reinterpret_cast<const float4*>(yp + (size_t)r * C)), s, h);
+    m.x = fmaxf(m.x, a.x); m.y = fmaxf(m.y, a.y); m.z = fmaxf(m.z, a.z); m.w = fmaxf(m.w, a.w);
+  }
+  *reinterpret_cast<float4*>(out + p * ldo + c) = m;
+}
+
+__global__ void __launch_bounds__(256)
+maxk_bwd_kernel(const float* __restrict__ y, const float* __restrict__ sc, const float* __restrict__ sh,
+                const float* __restrict__ out, long long ldo, const float* __restrict__ dout,
+                long long lddo, long long P, int k, int C, float* __restrict__ G,
+                double* __restrict__ stats) {
+  __shared__ float red[2][128];
+  const int tid = threadIdx.x;
+  const int C4 = C >> 2;
+  // block covers (256 / C4) points x C channels (C4 divides 256, C <= 128)
+  const long long t = (long long)blockIdx.x * blockDim.x + tid;
+  const bool valid = t < P * C4;
+  const long long p = valid ? t / C4 : 0;
+  const int c = valid ? (int)(t - p * C4) * 4 : 0;
+  (&red[0][0])[tid] = 0.f;  // blockDim.x == 256 == 2*128
+  __syncthreads();
+  float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+  if (valid) {
+    const float4 s = *reinterpret_cast<const float4*>(sc + c), h = *reinterpret_cast<const float4*>(sh + c);
+    const float4 m4 = *reinterpret_cast<const float4*>(out + p * ldo + c);
+    const float4 go4 = *reinterpret_cast<const float4*>(dout + p * lddo + c);
+    const float m[4] = {m4.x, m4.y, m4.z, m4.w}, go[4] = {go4.x, go4.y, go4.z, go4.w};
+    const float* yp = y + p * k * C + c;
+    float* gp = G + p * k * C + c;
+    int cnt[4] = {0, 0, 0, 0};
+    for (int r = 0; r < k; ++r) {   // tie count (reduce_max splits the gradient equally among tied maxima [TF])
+      const float4 a = bnrelu4(*reinterpret_cast<const float4*>(yp + (size_t)r * C), s, h);
+      cnt[0] += (a.x == m[0]) ? 1 : 0; cnt[1] += (a.y == m[1]) ? 1 : 0;
+      cnt[2] += (a.z == m[2]) ? 1 : 0; cnt[3] += (a.w == m[3]) ? 1 : 0;
+    }
+    float share[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) share[i] = (m[i] > 0.f && cnt[i] > 0) ? go[i] / (float)cnt[i] : 0.f;
+    for (int r = 0; r < k; ++r) {   // second visit of the same k rows: L1/L2 hits
+      const float4 yv = *reinterpret_cast<const float4*>(yp + (size_t)r * C);
+      const float4 a = bnrelu4(yv, s, h);
+      float4 g;
+      g.x = (m[0] > 0.f && a.x == m[0]) ? share[0] : 0.f;
+      g.y = (m[1] > 0.f && a.y == m[1]) ? share[1] : 0.f;
+      g.z = (m[2] > 0.f && a.z == m[2]) ? share[2] : 0.f;
+      g.w = (m[3] > 0.f && a.w == m[3]) ? share[3] : 0.f;
+      __stcs(reinterpret_cast<float4*>(gp + (size_t)r * C), g);
+      s0[0] += g.x; s0[1] += g.y; s0[2] += g.z; s0[3] += g.w;
+      s1[0] += g.x * yv.x; s1[1] += g.y * yv.y; s1[2] += g.z * yv.z; s1[3] += g.w * yv.w;
+    }
+  }
+  // channels repeat with period C inside the block (256 % C4 == 0 guaranteed by the wrapper)
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    atomicAdd(&red[0][c + i], s0[i]);
+    atomicAdd(&red[1][c + i], s1[i]);
+  }
   __syncthreads();
   if (tid < C) {
     atomicAdd(stats + tid, (double)red[0][tid]);
@@ -229,8 +264,9 @@ extern "C" int wspc_maxk_bnrelu_fwd(const float* y, const float* sc, const float
                                     float* out, long long ldo, wspc_stream_t stream) {
   if (int rc = check_arch()) return rc;
   WSPC_REQUIRE(y && sc && sh && out, "maxk_fwd: null pointer");
-  WSPC_REQUIRE(P >= 1 && k >= 1 && C >= 1 && ldo >= C, "maxk_fwd: bad shape");
-  const long long total = P * C;
+  WSPC_REQUIRE(P >= 1 && k >= 1 && C >= 4 && (C & 3) == 0 && ldo >= C && (ldo & 3) == 0, "maxk_fwd: bad shape (C, ldo multiples of 4)");
+  WSPC_REQUIRE(aligned16(y) && aligned16(sc) && aligned16(sh) && aligned16(out), "maxk_fwd: pointers must be 16-byte aligned");
+  const long long total = P * (C >> 2);
   maxk_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(y, sc, sh, P, k,
                                                                                                      C, out, ldo);
   count_launch();
@@ -243,8 +279,11 @@ extern "C" int wspc_maxk_bnrelu_bwd(const float* y, const float* sc, const float
                                     double* stats, wspc_stream_t stream) {
   if (int rc = check_arch()) return rc;
   WSPC_REQUIRE(y && sc && sh && out && dout && G && stats, "maxk_bwd: null pointer");
-  WSPC_REQUIRE(C >= 1 && C <= 128 && (256 % C) == 0, "maxk_bwd: C=%d must divide 256 and be <= 128", C);
-  const long long total = P * C;
+  WSPC_REQUIRE(C >= 4 && C <= 128 && (C & 3) == 0 && (256 % (C >> 2)) == 0 && (ldo & 3) == 0 && (lddo & 3) == 0,
+               "maxk_bwd: C=%d must be a multiple of 4, <= 128, with C/4 dividing 256; ldo/lddo multiples of 4", C);
+  WSPC_REQUIRE(aligned16(y) && aligned16(sc) && aligned16(sh) && aligned16(out) && aligned16(dout) && aligned16(G),
+               "maxk_bwd: pointers must be 16-byte aligned");
+  const long long total = P * (C >> 2);
   maxk_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       y, sc, sh, out, ldo, dout, lddo, P, k, C, G, stats);
   count_launch();

@@ -45,33 +45,45 @@ __global__ void edge_merge_wgrad_kernel(const float* __restrict__ dWc, const flo
 }
 
 // y[(i,j), :] = U[i, :] + V[cloud(i)*npts + idx[i,j], :] + bias;  per-channel sum / sum of squares for the batch norm.
-// block 256 = 16 row lanes x 16 float4 columns; persistent grid-stride loop over 64-point chunks.
+// block 256 = 16 points x 16 float4 columns: a thread owns one point (u loaded once, the k neighbour rows fetched four
+// at a time so the idx -> V gathers overlap); persistent grid-stride loop so the moments stay in registers.
 __global__ void __launch_bounds__(256)
 edge_combine_fwd_kernel(const float* __restrict__ UV, long long ldu, const int32_t* __restrict__ idx,
                         const float* __restrict__ bias, long long P, int k, int npts, float* __restrict__ y,
                         double* __restrict__ stats) {
   __shared__ float red[2][CO];
-  const int c4 = threadIdx.x & (C4 - 1), rl = threadIdx.x >> 4;
+  const int c4 = threadIdx.x & (C4 - 1), pl = threadIdx.x >> 4;
   const float4 b4 = bias ? *reinterpret_cast<const float4*>(bias + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
   float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
-  constexpr int PTS = 64;
-  for (long long p0 = (long long)blockIdx.x * PTS; p0 < P; p0 += (long long)gridDim.x * PTS) {
-    const int np = (int)((P - p0) < PTS ? (P - p0) : PTS);
-    const int rows = np * k;
-    for (int e = rl; e < rows; e += 16) {
-      const int pi = e / k;
-      const long long i = p0 + pi;
-      const long long cloud0 = (i / npts) * npts;
-      const long long er = p0 * k + e;
-      const int j = idx[er];
-      const float4 u = *reinterpret_cast<const float4*>(UV + i * ldu + c4 * 4);
-      const float4 v = *reinterpret_cast<const float4*>(UV + (cloud0 + j) * ldu + CO + c4 * 4);
+  const float* vbase = UV + CO + c4 * 4;
+  for (long long i = (long long)blockIdx.x * 16 + pl; i < P; i += (long long)gridDim.x * 16) {
+    const long long cloud0 = (i / npts) * npts;
+    float4 u = *reinterpret_cast<const float4*>(UV + i * ldu + c4 * 4);
+    u.x += b4.x; u.y += b4.y; u.z += b4.z; u.w += b4.w;
+    const int32_t* ip = idx + i * k;
+    float* yp = y + i * k * CO + c4 * 4;
+    int j = 0;
+    for (; j + 4 <= k; j += 4) {
+      int nb[4];
+      float4 v[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) nb[t] = ip[j + t];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) v[t] = *reinterpret_cast<const float4*>(vbase + (cloud0 + nb[t]) * ldu);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float4 o;
+        o.x = u.x + v[t].x; o.y = u.y + v[t].y; o.z = u.z + v[t].z; o.w = u.w + v[t].w;
+        __stcs(reinterpret_cast<float4*>(yp + (size_t)(j + t) * CO), o);
+        s1.x += o.x; s1.y += o.y; s1.z += o.z; s1.w += o.w;
+        s2.x = fmaf(o.x, o.x, s2.x); s2.y = fmaf(o.y, o.y, s2.y); s2.z = fmaf(o.z, o.z, s2.z); s2.w = fmaf(o.w, o.w, s2.w);
+      }
+    }
+    for (; j < k; ++j) {
+      const float4 v = *reinterpret_cast<const float4*>(vbase + (cloud0 + ip[j]) * ldu);
       float4 o;
-      o.x = (u.x + v.x) + b4.x;
-      o.y = (u.y + v.y) + b4.y;
-      o.z = (u.z + v.z) + b4.z;
-      o.w = (u.w + v.w) + b4.w;
-      __stcs(reinterpret_cast<float4*>(y + er * CO + c4 * 4), o);
+      o.x = u.x + v.x; o.y = u.y + v.y; o.z = u.z + v.z; o.w = u.w + v.w;
+      __stcs(reinterpret_cast<float4*>(yp + (size_t)j * CO), o);
       s1.x += o.x; s1.y += o.y; s1.z += o.z; s1.w += o.w;
       s2.x = fmaf(o.x, o.x, s2.x); s2.y = fmaf(o.y, o.y, s2.y); s2.z = fmaf(o.z, o.z, s2.z); s2.w = fmaf(o.w, o.w, s2.w);
     }
@@ -180,8 +192,8 @@ extern "C" int wspc_edge_combine_fwd(const float* UV, long long ldu, const int32
   WSPC_REQUIRE(Cout == CO && ldu >= 2 * CO && (ldu & 3) == 0, "edge_combine_fwd: Cout=%d ldu=%lld", Cout, ldu);
   WSPC_REQUIRE(P >= 1 && k >= 1 && npts >= 1 && P % npts == 0, "edge_combine_fwd: bad shape P=%lld k=%d npts=%d", P, k, npts);
   WSPC_REQUIRE(aligned16(UV) && aligned16(y) && (!bias || aligned16(bias)), "edge_combine_fwd: pointers must be 16-byte aligned");
-  const long long chunks = (P + 63) / 64;
-  const unsigned grid = (unsigned)(chunks < 4LL * kNumSM ? chunks : 4LL * kNumSM);
+  const long long chunks = (P + 15) / 16;
+  const unsigned grid = (unsigned)(chunks < 8LL * kNumSM ? chunks : 8LL * kNumSM);
   edge_combine_fwd_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(UV, ldu, idx, bias, P, k, npts, y, stats);
   count_launch();
   WSPC_LAUNCH_CHECK("edge_combine_fwd_kernel");

@@ -120,23 +120,27 @@ TcPlan make_tc_plan(int B, int N, int D, int k) {
 }
 
 // ------------------------------------------------------------------ prep ---
-// per-cloud centre (fp32 mean of the channel window; any vector would do, it only conditions the approximate pass)
+// per-cloud centre = channel sums of the window (divided by N in the prep kernel; any vector would do, it only
+// conditions the approximate pass).  grid (8, B), block 256: lane = channel, warps stride over the rows of the chunk.
 __global__ void __launch_bounds__(256)
-knn_tc_centre_kernel(const float* __restrict__ x, int N, int ldx, int coff, int D, float* __restrict__ centre) {
-  __shared__ float red[256];
-  const int b = blockIdx.x;
+knn_tc_centre_kernel(const float* __restrict__ x, int N, int ldx, int coff, int D, float* __restrict__ centre_sum) {
+  __shared__ float red[8][64];
+  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int per = (N + gridDim.x - 1) / gridDim.x;
+  const int n0 = blockIdx.x * per, n1 = min(N, n0 + per);
   const float* xb = x + (size_t)b * N * ldx + coff;
-  for (int c = 0; c < D; ++c) {
+  for (int c = lane; c < 64; c += 32) {
     float s = 0.f;
-    for (int n = threadIdx.x; n < N; n += 256) s += xb[(size_t)n * ldx + c];
-    red[threadIdx.x] = s;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-      if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) centre[b * 64 + c] = red[0] / (float)N;
-    __syncthreads();
+    if (c < D)
+      for (int n = n0 + warp; n < n1; n += 8) s += xb[(size_t)n * ldx + c];
+    red[warp][c] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < D) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    atomicAdd(centre_sum + b * 64 + threadIdx.x, s);
   }
 }
 
@@ -150,12 +154,13 @@ knn_tc_prep_kernel(const float* __restrict__ x, int N, int ldx, int coff, int D,
   const size_t tile_bytes = (size_t)(ghi + glo) * GROUP_BYTES;
   unsigned char* base = img + ((size_t)b * (Npad / QT) + tile) * tile_bytes;
   const float* xr = x + ((size_t)b * N + (n < N ? n : 0)) * ldx + coff;
-  const float* cb = centre + b * 64;
+  const float* cb = centre + b * 64;       // channel sums
+  const float inv_n = 1.f / (float)N;
   float acc = 0.f, accc = 0.f;
   for (int c = 0; c < D; ++c) {             // canonical chain on the original data; centred norm for the approximation
     const float v = n < N ? xr[c] : 0.f;
     acc = __fmaf_rn(v, v, acc);
-    const float vc = n < N ? v - cb[c] : 0.f;
+    const float vc = n < N ? v - cb[c] * inv_n : 0.f;
     accc = __fmaf_rn(vc, vc, accc);
   }
   // 3-way bf16 split of -sq'/2 (exact to 2^-24); padded points get a huge negative value: they never win
@@ -172,7 +177,7 @@ knn_tc_prep_kernel(const float* __restrict__ x, int N, int ldx, int coff, int D,
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int c = g * 8 + 2 * i + e;
-        const float v = (n < N && c < D) ? xr[c] - cb[c] : 0.f;
+        const float v = (n < N && c < D) ? xr[c] - cb[c] * inv_n : 0.f;
         __nv_bfloat16 hb = __float2bfloat16_rn(v);
         const __nv_bfloat16 lb = __float2bfloat16_rn(v - __bfloat162float(hb));
         if (c == D) hb = a1;
@@ -520,29 +525,57 @@ knn_tc_kernel(const unsigned char* __restrict__ img, const float* __restrict__ s
 }
 
 // ---------------------------------------------------------------- fallback ---
-// exact streaming kNN for the flagged rows, one warp per row (lane = candidate column within a 32-column group)
+// exact streaming kNN for the flagged rows: one CTA per row, each of the 8 warps scans an eighth of the columns
+// (lane = candidate column within a 32-column group) and keeps its own sorted list; warp 0 merges the 8 lists in
+// column order, so "equal distance -> lower index first" is preserved.
 __global__ void __launch_bounds__(256)
 knn_exact_rows_kernel(const float* __restrict__ x, const float* __restrict__ sq, int N, int Npad, int ldx, int coff, int D,
                       int k, int flavour, const int* __restrict__ flag_count, const int* __restrict__ flag_rows,
                       int32_t* __restrict__ idx_out, float* __restrict__ dist_out) {
-  const int lane = threadIdx.x & 31;
+  __shared__ float xs[64];
+  __shared__ float sd[8][32];
+  __shared__ int si[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nflag = *flag_count;
-  for (int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); f < nflag; f += gridDim.x * (blockDim.x >> 5)) {
+  const bool vec_ok = ((ldx & 3) == 0) && ((coff & 3) == 0) && ((D & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  const int per = ((N + 7) / 8 + 31) / 32 * 32;       // columns per warp, a multiple of 32
+  for (int f = blockIdx.x; f < nflag; f += gridDim.x) {
     const int grow = flag_rows[f];
     const int b = grow / N, row = grow - b * N;
     const float* xb = x + (size_t)b * N * ldx + coff;
-    const float* xi = xb + (size_t)row * ldx;
+    __syncthreads();                                   // previous row's shared state fully consumed
+    if (threadIdx.x < D) xs[threadIdx.x] = xb[(size_t)row * ldx + threadIdx.x];
+    __syncthreads();
     const float sqi = sq[(size_t)b * Npad + row];
     float ld = CUDART_INF_F;
     int li = INT_MAX;
     float tau = CUDART_INF_F;
-    for (int base = 0; base < N; base += 32) {
+    const int j0 = warp * per, j1 = min(N, j0 + per);
+    for (int base = j0; base < j1; base += 32) {
       const int j = base + lane;
       float d = __int_as_float(0x7fc00000);
-      if (j < N) {
+      if (j < j1) {
         const float* xj = xb + (size_t)j * ldx;
         float dot = 0.f;
-        for (int c = 0; c < D; ++c) dot = __fmaf_rn(xi[c], xj[c], dot);
+        if (vec_ok) {
+          for (int c0 = 0; c0 < D; c0 += 16) {
+            float4 q[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (c0 + 4 * u < D) q[u] = *reinterpret_cast<const float4*>(xj + c0 + 4 * u);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (c0 + 4 * u < D) {
+                dot = __fmaf_rn(xs[c0 + 4 * u + 0], q[u].x, dot);
+                dot = __fmaf_rn(xs[c0 + 4 * u + 1], q[u].y, dot);
+                dot = __fmaf_rn(xs[c0 + 4 * u + 2], q[u].z, dot);
+                dot = __fmaf_rn(xs[c0 + 4 * u + 3], q[u].w, dot);
+              }
+            }
+          }
+        } else {
+          for (int c = 0; c < D; ++c) dot = __fmaf_rn(xs[c], xj[c], dot);
+        }
         d = exact_dist(flavour, sqi, sq[(size_t)b * Npad + j], dot);
       }
       unsigned m = __ballot_sync(0xffffffffu, d < tau);
@@ -553,10 +586,23 @@ knn_exact_rows_kernel(const float* __restrict__ x, const float* __restrict__ sq,
       }
       tau = __shfl_sync(0xffffffffu, ld, k - 1);
     }
-    if (lane < k) {
-      const size_t o = (size_t)grow * k + lane;
-      idx_out[o] = li;
-      if (dist_out) dist_out[o] = ld;
+    sd[warp][lane] = ld;
+    si[warp][lane] = li;
+    __syncthreads();
+    if (warp == 0) {
+      for (int w = 1; w < 8; ++w) {
+        for (int e = 0; e < k; ++e) {
+          const float cd = sd[w][e];
+          if (!(cd < tau)) break;                      // that list is ascending: nothing further can enter
+          list_insert32(ld, li, cd, si[w][e], lane);
+          tau = __shfl_sync(0xffffffffu, ld, k - 1);
+        }
+      }
+      if (lane < k) {
+        const size_t o = (size_t)grow * k + lane;
+        idx_out[o] = li;
+        if (dist_out) dist_out[o] = ld;
+      }
     }
   }
 }
@@ -612,8 +658,9 @@ int knn_tc_run(const float* x, int B, int N, int ldx, int coff, int D, int k, in
     return WSPC_ERR_WORKSPACE;
   }
   const TcWs w = carve(ws, p, B, N);
-  WSPC_CUDA(cudaMemsetAsync(w.smax, 0, align_up((size_t)B * 8, 256) + 256, st));
-  knn_tc_centre_kernel<<<B, 256, 0, st>>>(x, N, ldx, coff, D, w.centre);
+  // centre sums, max norms and the flagged-row counter are contiguous
+  WSPC_CUDA(cudaMemsetAsync(w.centre, 0, align_up((size_t)B * 64 * 4, 256) + align_up((size_t)B * 8, 256) + 256, st));
+  knn_tc_centre_kernel<<<dim3(8, B), 256, 0, st>>>(x, N, ldx, coff, D, w.centre);
   knn_tc_prep_kernel<<<dim3(p.ntile, B), 128, 0, st>>>(x, N, ldx, coff, D, p.ghi, p.glo, p.Npad, w.centre, w.img, w.sq, w.sqc,
                                                       w.smax);
   static thread_local size_t configured = 0;

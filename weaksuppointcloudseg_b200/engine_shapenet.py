@@ -79,6 +79,7 @@ class ShapeNetEngine:
         self.Z, self.Zp, self.dZ = (torch.empty((B, N, part_num), **f32) for _ in range(3))
         self.losses = torch.zeros(5, **f32)
         self.seed = 4321
+        self.es = rt.EdgeSplit(self.P, self.dev) if rt.EDGE_FACTORED else None   # factored first EdgeConv layers (csrc/edge.cu)
         self.prof = None
 
     def _knn(self, i, src_addr, ld, coff, D, ov, tag):
@@ -102,7 +103,10 @@ class ShapeNetEngine:
         tr, d = is_training, bn_decay
         # ---- T-net on the edge feature of the raw cloud                      (:23-28, transform_nets.py)
         self._knn(0, X.data_ptr(), 3, 0, 3, ov, "knn0")
-        rt.conv_forward(Ly[T + "tconv1"], rt.op_edge(X, 3, 3, self.idx[0], k, N), R, self.yt1, 64, tr, d)
+        if self.es is not None:
+            rt.edge_first_forward(self.es, Ly[T + "tconv1"], X, 3, 3, self.idx[0], k, N, P, self.yt1, tr, d)
+        else:
+            rt.conv_forward(Ly[T + "tconv1"], rt.op_edge(X, 3, 3, self.idx[0], k, N), R, self.yt1, 64, tr, d)
         rt.conv_forward(Ly[T + "tconv2"], rt.op_bnrelu(self.yt1, Ly[T + "tconv1"]), R, self.yt2, 128, tr, d)
         rt.maxk_fwd(Ly[T + "tconv2"], self.yt2, P, k, self.tmax.data_ptr(), 128)
         t3 = Ly[T + "tconv3"]
@@ -116,16 +120,25 @@ class ShapeNetEngine:
         L.check(L.lib().wspc_transform_points_fwd(L.ptr(X), L.ptr(self.Tm), B, N, 1, L.ptr(self.Xt), L.stream()))  # :29
         # ---- EdgeConv blocks on the transformed cloud                        (:31-78)
         self._knn(1, self.Xt.data_ptr(), 3, 0, 3, ov, "knn1")
-        rt.conv_forward(Ly["adj_conv1"], rt.op_edge(self.Xt, 3, 3, self.idx[1], k, N), R, self.y[0], 64, tr, d)
+        if self.es is not None:
+            rt.edge_first_forward(self.es, Ly["adj_conv1"], self.Xt, 3, 3, self.idx[1], k, N, P, self.y[0], tr, d)
+        else:
+            rt.conv_forward(Ly["adj_conv1"], rt.op_edge(self.Xt, 3, 3, self.idx[1], k, N), R, self.y[0], 64, tr, d)
         rt.conv_forward(Ly["adj_conv2"], rt.op_bnrelu(self.y[0], Ly["adj_conv1"]), R, self.y[1], 64, tr, d)
         rt.maxk_fwd(Ly["adj_conv2"], self.y[1], P, k, cat_a, 192)
         self._knn(2, cat_a, 192, 0, 64, ov, "knn2")
-        rt.conv_forward(Ly["adj_conv3"], rt.op_edge(self.cat, 192, 64, self.idx[2], k, N), R, self.y[2], 64, tr, d)
+        if self.es is not None:
+            rt.edge_first_forward(self.es, Ly["adj_conv3"], cat_a, 192, 64, self.idx[2], k, N, P, self.y[2], tr, d)
+        else:
+            rt.conv_forward(Ly["adj_conv3"], rt.op_edge(self.cat, 192, 64, self.idx[2], k, N), R, self.y[2], 64, tr, d)
         rt.conv_forward(Ly["adj_conv4"], rt.op_bnrelu(self.y[2], Ly["adj_conv3"]), R, self.y[3], 64, tr, d)
         rt.maxk_fwd(Ly["adj_conv4"], self.y[3], P, k, cat_a + 4 * 64, 192)
         self._knn(3, cat_a, 192, 64, 64, ov, "knn3")
-        e3 = L.Operand(p=cat_a + 4 * 64, ld=192, C=128, idx=L.dptr(self.idx[3]), k=k, npts=N), L.OP_EDGE
-        rt.conv_forward(Ly["adj_conv5"], e3, R, self.y[4], 64, tr, d)
+        if self.es is not None:
+            rt.edge_first_forward(self.es, Ly["adj_conv5"], cat_a + 4 * 64, 192, 64, self.idx[3], k, N, P, self.y[4], tr, d)
+        else:
+            e3 = L.Operand(p=cat_a + 4 * 64, ld=192, C=128, idx=L.dptr(self.idx[3]), k=k, npts=N), L.OP_EDGE
+            rt.conv_forward(Ly["adj_conv5"], e3, R, self.y[4], 64, tr, d)
         rt.maxk_fwd(Ly["adj_conv5"], self.y[4], P, k, cat_a + 4 * 128, 192)
         l7 = Ly["adj_conv7"]
         rt.conv_forward(l7, rt.op_plain(self.cat, 192, 192), P, self.y7, 1024, tr, d)                     # :80-83
@@ -228,11 +241,15 @@ class ShapeNetEngine:
         # block 3
         rt.maxk_bwd(c5, self.y[4], P, k, cat_a + 4 * 128, 192, dcat_a + 4 * 128, 192, self.Ga)
         rt.bn_bwd_coeffs(c5, R)
-        G5 = rt.op_dy(self.Ga, 64, self.y[4], 64, c5, 64)
-        A5 = L.Operand(p=cat_a + 4 * 64, ld=192, C=128, idx=L.dptr(self.idx[3]), k=k, npts=N), L.OP_EDGE
-        rt.wgrad(A5, G5, R, c5.dW, c5.db, dev)
-        e, m = rt.epi_scatter(dcat_a + 4 * 64, 192, self.idx[3], k, N)
-        rt.rows_gemm(G5, c5.W, 64, 1, R, 128, 64, e, m)
+        if self.es is not None:
+            rt.edge_first_backward(self.es, c5, cat_a + 4 * 64, 192, 64, self.idx[3], k, N, P, self.Ga, self.y[4],
+                                   dcat_a + 4 * 64, 192)
+        else:
+            G5 = rt.op_dy(self.Ga, 64, self.y[4], 64, c5, 64)
+            A5 = L.Operand(p=cat_a + 4 * 64, ld=192, C=128, idx=L.dptr(self.idx[3]), k=k, npts=N), L.OP_EDGE
+            rt.wgrad(A5, G5, R, c5.dW, c5.db, dev)
+            e, m = rt.epi_scatter(dcat_a + 4 * 64, 192, self.idx[3], k, N)
+            rt.rows_gemm(G5, c5.W, 64, 1, R, 128, 64, e, m)
         # block 2
         rt.maxk_bwd(c4, self.y[3], P, k, cat_a + 4 * 64, 192, dcat_a + 4 * 64, 192, self.Ga)
         rt.bn_bwd_coeffs(c4, R)
@@ -241,10 +258,13 @@ class ShapeNetEngine:
         e, m = rt.epi_relumask(self.Gb, c3, self.y[2])
         rt.rows_gemm(G4e, c4.W, 64, 1, R, 64, 64, e, m)
         rt.bn_bwd_coeffs(c3, R)
-        G3e = rt.op_dy(self.Gb, 64, self.y[2], 64, c3, 64)
-        rt.wgrad(rt.op_edge(self.cat, 192, 64, self.idx[2], k, N), G3e, R, c3.dW, c3.db, dev)
-        e, m = rt.epi_scatter(dcat_a, 192, self.idx[2], k, N)
-        rt.rows_gemm(G3e, c3.W, 64, 1, R, 128, 64, e, m)
+        if self.es is not None:
+            rt.edge_first_backward(self.es, c3, cat_a, 192, 64, self.idx[2], k, N, P, self.Gb, self.y[2], dcat_a, 192)
+        else:
+            G3e = rt.op_dy(self.Gb, 64, self.y[2], 64, c3, 64)
+            rt.wgrad(rt.op_edge(self.cat, 192, 64, self.idx[2], k, N), G3e, R, c3.dW, c3.db, dev)
+            e, m = rt.epi_scatter(dcat_a, 192, self.idx[2], k, N)
+            rt.rows_gemm(G3e, c3.W, 64, 1, R, 128, 64, e, m)
         # block 1: gradient continues into the transformed cloud (dX')
         rt.maxk_bwd(c2, self.y[1], P, k, cat_a, 192, dcat_a, 192, self.Ga)
         rt.bn_bwd_coeffs(c2, R)
@@ -253,11 +273,14 @@ class ShapeNetEngine:
         e, m = rt.epi_relumask(self.Gb, c1, self.y[0])
         rt.rows_gemm(G2e, c2.W, 64, 1, R, 64, 64, e, m)
         rt.bn_bwd_coeffs(c1, R)
-        G1e = rt.op_dy(self.Gb, 64, self.y[0], 64, c1, 64)
-        rt.wgrad(rt.op_edge(self.Xt, 3, 3, self.idx[1], k, N), G1e, R, c1.dW, c1.db, dev)
         rt.zero_(self.dXt)
-        e, m = rt.epi_scatter(self.dXt.data_ptr(), 3, self.idx[1], k, N)
-        rt.rows_gemm(G1e, c1.W, 64, 1, R, 6, 64, e, m)
+        if self.es is not None:
+            rt.edge_first_backward(self.es, c1, self.Xt, 3, 3, self.idx[1], k, N, P, self.Gb, self.y[0], self.dXt.data_ptr(), 3)
+        else:
+            G1e = rt.op_dy(self.Gb, 64, self.y[0], 64, c1, 64)
+            rt.wgrad(rt.op_edge(self.Xt, 3, 3, self.idx[1], k, N), G1e, R, c1.dW, c1.db, dev)
+            e, m = rt.epi_scatter(self.dXt.data_ptr(), 3, self.idx[1], k, N)
+            rt.rows_gemm(G1e, c1.W, 64, 1, R, 6, 64, e, m)
         # ---- T-net                                                          (DGCNN_ShapeNet.py:29 backward)
         L.check(L.lib().wspc_transform_points_bwd(L.ptr(self.X), L.ptr(self.dXt), B, N, L.ptr(self.dTm), L.stream()))
         t1, t2, t3, f1, f2 = [Ly[T + n] for n in ("tconv1", "tconv2", "tconv3", "tfc1", "tfc2")]
@@ -289,8 +312,11 @@ class ShapeNetEngine:
         e, m = rt.epi_relumask(self.Ga, t1, self.yt1)
         rt.rows_gemm(Gt2, t2.W, 128, 1, R, 64, 128, e, m)
         rt.bn_bwd_coeffs(t1, R)
-        rt.wgrad(rt.op_edge(self.X, 3, 3, self.idx[0], k, N), rt.op_dy(self.Ga, 64, self.yt1, 64, t1, 64), R, t1.dW, t1.db,
-                 dev)
+        if self.es is not None:
+            rt.edge_first_backward(self.es, t1, self.X, 3, 3, self.idx[0], k, N, P, self.Ga, self.yt1)
+        else:
+            rt.wgrad(rt.op_edge(self.X, 3, 3, self.idx[0], k, N), rt.op_dy(self.Ga, 64, self.yt1, 64, t1, 64), R, t1.dW,
+                     t1.db, dev)
 
     def train_step(self, X, label, Y, Mask, lr, bn_decay, full=True, dropout_masks=None, knn_override=None,
                    smooth_graph=None, apply=True, gscale=1.0, allreduce=None):
