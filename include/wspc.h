@@ -235,6 +235,26 @@ int wspc_edge_combine_bwd(const float* G, const float* y, const float* c1, const
 int wspc_edge_merge_wgrad(const float* dWc, const float* dbc, int Cx, int Cout, float* dW, float* db,
                           wspc_stream_t stream);
 
+/* ------------------- backward of conv2d 1x1 -> BN -> ReLU -> max over the points of a cloud --- */
+/* adj_conv7 + maxpool (DGCNN_S3DIS.py:80-85, DGCNN_ShapeNet.py:80-85) and tconv3 + tmaxpool (transform_nets.py:29-34).
+ * max_pool2d's gradient is sparse (one point per cloud and channel), the BN backward is affine (dy = c1*G + c2 + c3*y)
+ * and y = A W + b is linear in the layer input A (P, cin), so
+ *   dA = A (W diag(c3) W^T) + 1 (W t)^T + sparse(c1*G) W^T,   dW = (A^T A) W diag(c3) + (A^T 1) t^T + A^T sparse(c1*G),
+ *   db = c3 * (W^T A^T 1) + P t + 1^T sparse(c1*G),           t = c2 + c3*b,
+ * i.e. (P,cin)x(cin,cin) GEMMs through wspc_conv1x1_rows / wspc_conv1x1_wgrad instead of (P,cout) ones, and no read of
+ * y.  These entry points are the glue:
+ *   wspc_poolconv_coeffs   : t (cout), Wsc (cin,cout) = W diag(c3)
+ *   wspc_poolconv_sparse   : dx[b*N + amax[b,c], :] += c1[c] dg[b,c] W[:,c] (atomics; dx may be NULL);
+ *                            sW (cin,cout) = A^T sparse(c1*G), sdb (cout) = 1^T sparse(c1*G)  (deterministic)
+ *   wspc_poolconv_finalize : dW = T + colsum t^T + sW with T = (A^T A) Wsc, colsum = A^T 1;  db as above (may be NULL) */
+int wspc_poolconv_coeffs(const float* W, const float* b, const float* c2, const float* c3, int cin, int cout, float* t,
+                         float* Wsc, wspc_stream_t stream);
+int wspc_poolconv_sparse(const float* dg, const int32_t* amax, const float* c1, const float* W, const float* A,
+                         long long lda, int B, int N, int cin, int cout, float* dx, long long lddx, float* sW, float* sdb,
+                         wspc_stream_t stream);
+int wspc_poolconv_finalize(const float* T, const float* colsum, const float* t, const float* sW, const float* sdb,
+                           const float* Wsc, int cin, int cout, double rows, float* dW, float* db, wspc_stream_t stream);
+
 /* ------------------------------------------------------------ optimiser --- */
 /* tf.train.AdamOptimizer update on flat fp32 buffers (eps not bias-corrected);
  * lr_t = lr*sqrt(1-b2^t)/(1-b1^t) is computed by the caller; gscale multiplies g (1/world_size). */

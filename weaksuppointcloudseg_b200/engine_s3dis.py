@@ -63,6 +63,7 @@ class S3DISEngine:
         self.seed = 1234
         # first conv2d of each EdgeConv block: factored (csrc/edge.cu) unless WSPC_EDGE=gemm asks for the gathered GEMM
         self.es = rt.EdgeSplit(P, self.dev) if rt.EDGE_FACTORED else None
+        self.pc7 = rt.PoolConv(self.layers["adj_conv7"], self.dev) if rt.POOLCONV_GRAM else None
         self.prof = None   # optional list of (tag, start_event, end_event) filled around the kNN launches
 
     def _tick(self):
@@ -201,15 +202,20 @@ class S3DISEngine:
         GS = rt.op_dy(self.S, 512, None, 0, None, 512)
         rt.wgrad(rt.op_plain(self.g, 1024, 1024), GS, B, s1.dW[:1024], None, dev)
         rt.rows_gemm(GS, s1.W, 512, 1, B, 1024, 512, L.Epilogue(out=L.dptr(self.dg_in), ldo=1024), L.EPI_STORE)
-        rt.rows_gemm(G1, s1.W[1024:], 512, 1, P, 192, 512, L.Epilogue(out=dcat_a, ldo=192), L.EPI_STORE)
-        # max over points + adj_conv7
+        # max over points: ReLU gate + BN-backward sums of the sparse gradient, then adj_conv7
         rt.zero_(c7.bstats)
         L.check(L.lib().wspc_maxn_bwd_gate(L.ptr(self.g), L.ptr(self.dg_in), L.ptr(self.amax), L.ptr(self.y7), B, N, 1024,
                                            L.ptr(self.dg), L.ptr(c7.bstats), L.stream()))
         rt.bn_bwd_coeffs(c7, P)
-        G7 = rt.op_dy_sparse(self.y7, c7, self.dg, self.amax, N)
-        rt.wgrad(rt.op_plain(self.cat, 192, 192), G7, P, c7.dW, c7.db, dev)
-        rt.rows_gemm(G7, c7.W, 1024, 1, P, 192, 1024, L.Epilogue(out=dcat_a, ldo=192), L.EPI_ACCUM)
+        if self.pc7 is not None:     # Gram identity (csrc/poolconv.cu): no (P,1024) operand, y7 is not read
+            r0 = self.pc7.prepare()
+            rt.rows_gemm(G1, s1.W[1024:], 512, 1, P, 192, 512, L.Epilogue(out=dcat_a, ldo=192, bias=L.dptr(r0)), L.EPI_STORE)
+            self.pc7.backward(cat_a, 192, P, B, N, self.dg, self.amax, dcat_a, 192)
+        else:
+            rt.rows_gemm(G1, s1.W[1024:], 512, 1, P, 192, 512, L.Epilogue(out=dcat_a, ldo=192), L.EPI_STORE)
+            G7 = rt.op_dy_sparse(self.y7, c7, self.dg, self.amax, N)
+            rt.wgrad(rt.op_plain(self.cat, 192, 192), G7, P, c7.dW, c7.db, dev)
+            rt.rows_gemm(G7, c7.W, 1024, 1, P, 192, 1024, L.Epilogue(out=dcat_a, ldo=192), L.EPI_ACCUM)
         # block 3
         rt.maxk_bwd(c5, self.y[4], P, k, cat_a + 4 * 128, 192, dcat_a + 4 * 128, 192, self.Ga)
         rt.bn_bwd_coeffs(c5, R)

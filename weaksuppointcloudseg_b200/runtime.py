@@ -277,3 +277,52 @@ def edge_first_backward(es: EdgeSplit, layer: Layer, x, ld, cx, idx, k, npts, P,
     L.check(L.lib().wspc_edge_merge_wgrad(L.ptr(es.dWc), L.ptr(es.dbc), cx, 64, L.ptr(layer.dW), L.ptr(layer.db), L.stream()))
     if dx_addr is not None:
         rows_gemm(D, Wc, 128, 1, P, cx, 128, L.Epilogue(out=dx_addr, ldo=lddx), L.EPI_ACCUM)
+
+
+# ---- backward of conv -> BN -> ReLU -> max over N through the Gram identity (csrc/poolconv.cu) ----------
+# WSPC_POOLCONV=dense keeps the (P, cout) formulation (dy synthesised from y through OP_DY_SPARSE) for A/B tests
+POOLCONV_GRAM = os.environ.get("WSPC_POOLCONV", "gram") != "dense"
+
+
+class PoolConv:
+    """Scratch for one `conv2d 1x1 -> BN -> ReLU -> max_pool2d([N,1])` layer (adj_conv7 / tconv3)."""
+
+    def __init__(self, layer: Layer, device):
+        cin, cout = layer.cin, layer.cout
+        f32 = dict(dtype=torch.float32, device=device)
+        self.layer = layer
+        self.t, self.sdb = torch.empty(cout, **f32), torch.empty(cout, **f32)
+        self.Wsc, self.T, self.sW = (torch.empty((cin, cout), **f32) for _ in range(3))
+        self.M, self.gram = torch.empty((cin, cin), **f32), torch.empty((cin, cin), **f32)
+        self.r0, self.colsum = torch.empty(cin, **f32), torch.empty(cin, **f32)
+
+    def prepare(self):
+        """after bn_bwd_coeffs(layer): t, W diag(c3), the constant row r0 = W t of dA and M = W diag(c3) W^T.
+        Returns r0 (cin) -- the caller adds it to every row of dA (e.g. as the bias of the GEMM that first writes dA)."""
+        ly = self.layer
+        cin, cout = ly.cin, ly.cout
+        L.check(L.lib().wspc_poolconv_coeffs(L.ptr(ly.W), L.ptr(ly.b), L.ptr(ly.c2), L.ptr(ly.c3), cin, cout, L.ptr(self.t),
+                                             L.ptr(self.Wsc), L.stream()))
+        rows_gemm(op_plain(self.t, cout, cout), ly.W, cout, 1, 1, cin, cout, L.Epilogue(out=L.dptr(self.r0), ldo=cin),
+                  L.EPI_STORE)
+        rows_gemm(op_plain(self.Wsc, cout, cout), ly.W, cout, 1, cin, cin, cout, L.Epilogue(out=L.dptr(self.M), ldo=cin),
+                  L.EPI_STORE)
+        return self.r0
+
+    def backward(self, A, lda, P, B, N, dg, amax, dx_addr, lddx):
+        """A: (P, lda) layer input (tensor or address).  Accumulates A M + sparse(c1 G) W^T into dx (r0 excluded, see
+        prepare) and writes layer.dW / layer.db."""
+        ly = self.layer
+        cin, cout = ly.cin, ly.cout
+        aa = A if isinstance(A, int) else A.data_ptr()
+        Aop = (L.Operand(p=aa, ld=lda, C=cin), L.OP_PLAIN)
+        dev = self.t.device
+        rows_gemm(Aop, self.M, cin, 0, P, cin, cin, L.Epilogue(out=dx_addr, ldo=lddx), L.EPI_ACCUM)
+        L.check(L.lib().wspc_poolconv_sparse(L.ptr(dg), L.ptr(amax), L.ptr(ly.c1), L.ptr(ly.W), ctypes.c_void_p(aa), lda, B, N,
+                                             cin, cout, ctypes.c_void_p(dx_addr), lddx, L.ptr(self.sW), L.ptr(self.sdb),
+                                             L.stream()))
+        wgrad(Aop, (L.Operand(p=aa, ld=lda, C=cin), L.OP_DY), P, self.gram, self.colsum, dev)           # A^T A, A^T 1
+        rows_gemm(op_plain(self.gram, cin, cin), self.Wsc, cout, 0, cin, cout, cin, L.Epilogue(out=L.dptr(self.T), ldo=cout),
+                  L.EPI_STORE)
+        L.check(L.lib().wspc_poolconv_finalize(L.ptr(self.T), L.ptr(self.colsum), L.ptr(self.t), L.ptr(self.sW), L.ptr(self.sdb),
+                                               L.ptr(self.Wsc), cin, cout, float(P), L.ptr(ly.dW), L.ptr(ly.db), L.stream()))
