@@ -252,6 +252,8 @@ int wspc_poolconv_coeffs(const float* W, const float* b, const float* c2, const 
 int wspc_poolconv_sparse(const float* dg, const int32_t* amax, const float* c1, const float* W, const float* A,
                          long long lda, int B, int N, int cin, int cout, float* dx, long long lddx, float* sW, float* sdb,
                          wspc_stream_t stream);
+/* out[row, 0:C] = v[0:C] for every row (the constant row of dA when no earlier GEMM writes dA) */
+int wspc_fill_rows(float* out, long long ldo, const float* v, long long rows, int C, wspc_stream_t stream);
 int wspc_poolconv_finalize(const float* T, const float* colsum, const float* t, const float* sW, const float* sdb,
                            const float* Wsc, int cin, int cout, double rows, float* dW, float* db, wspc_stream_t stream);
 

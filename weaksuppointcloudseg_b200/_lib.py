@@ -162,6 +162,7 @@ _EXTRA_DECLS.update({
     "wspc_edge_combine_fwd": (c_int, [_P, c_longlong, _P, _P, c_longlong, c_int, c_int, c_int, _P, _P, _P]),
     "wspc_edge_combine_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_longlong, c_int, c_int, c_int, _P, c_longlong, _P]),
     "wspc_edge_merge_wgrad": (c_int, [_P, _P, c_int, c_int, _P, _P, _P]),
+    "wspc_fill_rows": (c_int, [_P, c_longlong, _P, c_longlong, c_int, _P]),
     "wspc_poolconv_coeffs": (c_int, [_P, _P, _P, _P, c_int, c_int, _P, _P, _P]),
     "wspc_poolconv_sparse": (c_int, [_P, _P, _P, _P, _P, c_longlong, c_int, c_int, c_int, c_int, _P, c_longlong, _P, _P, _P]),
     "wspc_poolconv_finalize": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_double, _P, _P, _P]),

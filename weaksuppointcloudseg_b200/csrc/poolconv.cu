@@ -83,10 +83,28 @@ __global__ void poolconv_finalize_kernel(const float* __restrict__ T, const floa
   }
 }
 
+// out[row, :] = v   (the constant row r0 of dA when no earlier GEMM writes dA)
+__global__ void fill_rows_kernel(float* __restrict__ out, long long ldo, const float* __restrict__ v, long long rows, int C) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * C) return;
+  const long long r = i / C;
+  const int c = (int)(i - r * C);
+  out[r * ldo + c] = v[c];
+}
+
 }  // namespace
 }  // namespace wspc
 
 using namespace wspc;
+
+extern "C" int wspc_fill_rows(float* out, long long ldo, const float* v, long long rows, int C, wspc_stream_t stream) {
+  if (int rc = check_arch()) return rc;
+  WSPC_REQUIRE(out && v && rows >= 1 && C >= 1 && ldo >= C, "fill_rows: bad arguments");
+  fill_rows_kernel<<<(unsigned)((rows * C + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(out, ldo, v, rows, C);
+  count_launch();
+  WSPC_LAUNCH_CHECK("fill_rows_kernel");
+  return WSPC_OK;
+}
 
 extern "C" int wspc_poolconv_coeffs(const float* W, const float* b, const float* c2, const float* c3, int cin, int cout,
                                     float* t, float* Wsc, wspc_stream_t stream) {

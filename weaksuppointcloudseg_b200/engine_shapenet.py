@@ -80,6 +80,9 @@ class ShapeNetEngine:
         self.losses = torch.zeros(5, **f32)
         self.seed = 4321
         self.es = rt.EdgeSplit(self.P, self.dev) if rt.EDGE_FACTORED else None   # factored first EdgeConv layers (csrc/edge.cu)
+        # conv -> BN -> ReLU -> max over N layers: backward through the Gram identity (csrc/poolconv.cu)
+        self.pc7 = rt.PoolConv(self.layers["adj_conv7"], self.dev) if rt.POOLCONV_GRAM else None
+        self.pct3 = rt.PoolConv(self.layers["transform_net1/tconv3"], self.dev) if rt.POOLCONV_GRAM else None
         self.prof = None
 
     def _knn(self, i, src_addr, ld, coff, D, ov, tag):
@@ -226,7 +229,7 @@ class ShapeNetEngine:
         rt.rows_gemm(GS, s1.W, 256, 1, B, 1024, 256, L.Epilogue(out=L.dptr(self.dg_in), ldo=1024), L.EPI_STORE)
         e, m = rt.epi_relumask(self.Glab, lab, self.ylab)
         rt.rows_gemm(GS, s1.W[1024:1088], 256, 1, B, 64, 256, e, m)
-        rt.rows_gemm(G1, s1.W[1088:], 256, 1, P, 192, 256, L.Epilogue(out=dcat_a, ldo=192), L.EPI_STORE)
+        self._G1 = G1     # the (P,192) data gradient is written after adj_conv7's coefficients are known (constant row r0)
         # category branch
         rt.bn_bwd_coeffs(lab, B)
         rt.wgrad(rt.op_plain(self.label, 16, 16), rt.op_dy(self.Glab, 64, self.ylab, 64, lab, 64), B, lab.dW, lab.db, dev)
@@ -235,9 +238,16 @@ class ShapeNetEngine:
         L.check(L.lib().wspc_maxn_bwd_gate(L.ptr(self.g), L.ptr(self.dg_in), L.ptr(self.amax), L.ptr(self.y7), B, N, 1024,
                                            L.ptr(self.dg), L.ptr(c7.bstats), L.stream()))
         rt.bn_bwd_coeffs(c7, P)
-        G7 = rt.op_dy_sparse(self.y7, c7, self.dg, self.amax, N)
-        rt.wgrad(rt.op_plain(self.cat, 192, 192), G7, P, c7.dW, c7.db, dev)
-        rt.rows_gemm(G7, c7.W, 1024, 1, P, 192, 1024, L.Epilogue(out=dcat_a, ldo=192), L.EPI_ACCUM)
+        G1 = self._G1
+        if self.pc7 is not None:
+            r0 = self.pc7.prepare()
+            rt.rows_gemm(G1, s1.W[1088:], 256, 1, P, 192, 256, L.Epilogue(out=dcat_a, ldo=192, bias=L.dptr(r0)), L.EPI_STORE)
+            self.pc7.backward(cat_a, 192, P, B, N, self.dg, self.amax, dcat_a, 192)
+        else:
+            rt.rows_gemm(G1, s1.W[1088:], 256, 1, P, 192, 256, L.Epilogue(out=dcat_a, ldo=192), L.EPI_STORE)
+            G7 = rt.op_dy_sparse(self.y7, c7, self.dg, self.amax, N)
+            rt.wgrad(rt.op_plain(self.cat, 192, 192), G7, P, c7.dW, c7.db, dev)
+            rt.rows_gemm(G7, c7.W, 1024, 1, P, 192, 1024, L.Epilogue(out=dcat_a, ldo=192), L.EPI_ACCUM)
         # block 3
         rt.maxk_bwd(c5, self.y[4], P, k, cat_a + 4 * 128, 192, dcat_a + 4 * 128, 192, self.Ga)
         rt.bn_bwd_coeffs(c5, R)
@@ -302,9 +312,14 @@ class ShapeNetEngine:
         L.check(L.lib().wspc_maxn_bwd_gate(L.ptr(self.tg), L.ptr(self.dtg_in), L.ptr(self.tamax), L.ptr(self.yt3), B, N,
                                            1024, L.ptr(self.dtg), L.ptr(t3.bstats), L.stream()))
         rt.bn_bwd_coeffs(t3, P)
-        Gt3 = rt.op_dy_sparse(self.yt3, t3, self.dtg, self.tamax, N)
-        rt.wgrad(rt.op_plain(self.tmax, 128, 128), Gt3, P, t3.dW, t3.db, dev)
-        rt.rows_gemm(Gt3, t3.W, 1024, 1, P, 128, 1024, L.Epilogue(out=L.dptr(self.dtmax), ldo=128), L.EPI_STORE)
+        if self.pct3 is not None:
+            r0 = self.pct3.prepare()
+            L.check(L.lib().wspc_fill_rows(L.ptr(self.dtmax), 128, L.ptr(r0), P, 128, L.stream()))     # dtmax = 1 r0^T
+            self.pct3.backward(self.tmax, 128, P, B, N, self.dtg, self.tamax, self.dtmax.data_ptr(), 128)
+        else:
+            Gt3 = rt.op_dy_sparse(self.yt3, t3, self.dtg, self.tamax, N)
+            rt.wgrad(rt.op_plain(self.tmax, 128, 128), Gt3, P, t3.dW, t3.db, dev)
+            rt.rows_gemm(Gt3, t3.W, 1024, 1, P, 128, 1024, L.Epilogue(out=L.dptr(self.dtmax), ldo=128), L.EPI_STORE)
         rt.maxk_bwd(t2, self.yt2, P, k, self.tmax.data_ptr(), 128, self.dtmax.data_ptr(), 128, self.Gt2)
         rt.bn_bwd_coeffs(t2, R)
         Gt2 = rt.op_dy(self.Gt2, 128, self.yt2, 128, t2, 128)
