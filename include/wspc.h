@@ -157,6 +157,15 @@ int wspc_conv1x1_rows(const wspc_operand_t* A, int a_mode, const float* Bm, long
                       long long M, int N, int K, const wspc_epilogue_t* epi, int epi_mode,
                       wspc_stream_t stream);
 
+/* Same operation with caller-provided scratch: when K is processed in several chunks (K > 128) the tensor-core
+ * kernel stages a pre-split (bf16 hi/lo) image of the weights with one bulk copy per chunk instead of re-splitting
+ * the fp32 weights for every 128-row tile; the image lives in `workspace` (wspc_conv1x1_rows_workspace_bytes(N, K)
+ * bytes, 16-byte aligned; 0 means no scratch is needed).  workspace == NULL selects the in-kernel split. */
+size_t wspc_conv1x1_rows_workspace_bytes(int N, int K);
+int wspc_conv1x1_rows_ws(const wspc_operand_t* A, int a_mode, const float* Bm, long long ldb, int b_transposed,
+                         long long M, int N, int K, const wspc_epilogue_t* epi, int epi_mode, void* workspace,
+                         size_t workspace_bytes, wspc_stream_t stream);
+
 /* Kernel selection for wspc_conv1x1_rows: 0 = auto (tcgen05 tensor-core kernel for eligible shapes, CUDA-core
  * kernel otherwise), 1 = CUDA-core kernel only (used by the tests to A/B the two device paths).  Returns the
  * previous setting.  Both paths are sm_100a CUDA; neither is a CPU fallback. */

@@ -1,9 +1,11 @@
 """CPU oracle for the DGCNN segmentation networks, weak-supervision losses and TF-style optimiser.
 
-TEST INFRASTRUCTURE ONLY — see oracle/__init__.py.  PARITY UNPINNED: the reference has no tests or
+TEST INFRASTRUCTURE ONLY — see oracle/__init__.py for the pinning status.  The reference has no tests or
 golden vectors for this path and TensorFlow 1.14 cannot be installed here, so this module restates
 the reference's graph construction op by op (file:line cited on every function) with the TF op
-semantics of SURVEY.md App. A, on torch-CPU tensors (fp32 by default, fp64 for gradient checks).
+semantics of SURVEY.md App. A, on torch-CPU tensors (fp32 by default, fp64 for gradient checks); it is
+held to the outputs of the reference's own Python run on the op-level TF stand-in
+(tests/golden/ref_*.npz, tests/test_reference_golden_cpu.py).
 Distances / kNN go through oracle/knn_oracle.c (canonical fp32 arithmetic); everything else uses
 torch CPU ops with autograd providing the reference gradients.
 """

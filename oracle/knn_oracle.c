@@ -6,12 +6,18 @@
  * bench.py's cpu_baseline / --impl reference legs do, and only as the checker
  * or the timed CPU baseline.
  *
- * PARITY UNPINNED: the reference (alex-xun-xu/WeakSupPointCloudSeg) ships no
- * tests or golden vectors for this path and its arithmetic lives in
- * TensorFlow 1.14 (README.md:21), which is absent from /root/reference and
- * cannot be installed here.  This file therefore restates the *published*
- * semantics of the TF ops at the reference's call sites with the canonical
- * fp32 arithmetic fixed in SURVEY.md App. A:
+ * PINNING: the reference (alex-xun-xu/WeakSupPointCloudSeg) ships no tests or
+ * golden vectors for this path and its arithmetic lives in TensorFlow 1.14
+ * (README.md:21), which is absent from /root/reference and cannot be installed
+ * here.  This file restates the *published* semantics of the TF ops at the
+ * reference's call sites; it is checked against the reference's own
+ * tf_util.pairwise_distance / knn and SmoothConstraint code executed on the
+ * op-level TF stand-in (tests/golden/ref_unit_ops.npz,
+ * tests/test_reference_golden_cpu.py): distances to 1e-5 of the matrix scale,
+ * neighbour lists equal except on last-bit ties (TensorFlow's matmul summation
+ * order is unspecified, so bit-level index parity with a TF run is undefined;
+ * "bit-exact kNN" in this repository means bit-exact against the canonical
+ * fp32 arithmetic fixed in SURVEY.md App. A and implemented here):
  *
  *   pairwise distance, tf_util flavour   Networks/dgcnn/utils/tf_util.py:652-657
  *       inner = -2 * (X X^T); sq = sum(x^2); D = (sq_i + inner_ij) + sq_j

@@ -1,5 +1,5 @@
-"""CPU oracle for the test-time label propagation path (TEST INFRASTRUCTURE ONLY, PARITY UNPINNED — see
-oracle/__init__.py).  Restates Util/Tool.py:435-468 (LaplacianMatSym_XYZRGB_DirectComp) and
+"""CPU oracle for the test-time label propagation path (TEST INFRASTRUCTURE ONLY, see oracle/__init__.py for the
+pinning status).  Restates Util/Tool.py:435-468 (LaplacianMatSym_XYZRGB_DirectComp) and
 Util/ProbLabelPropagation.py:17-42 with numpy; the solve uses a dense inverse in fp64 exactly as written
 (tf.linalg.inv [TF]); distances follow the SmoothConstraint flavour of oracle/knn_oracle.c."""
 from __future__ import annotations

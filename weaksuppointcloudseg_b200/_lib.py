@@ -132,6 +132,8 @@ _OPP = ctypes.POINTER(Operand)
 _EPP = ctypes.POINTER(Epilogue)
 _EXTRA_DECLS.update({
     "wspc_conv1x1_rows": (c_int, [_OPP, c_int, _P, c_longlong, c_int, c_longlong, c_int, c_int, _EPP, c_int, _P]),
+    "wspc_conv1x1_rows_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "wspc_conv1x1_rows_ws": (c_int, [_OPP, c_int, _P, c_longlong, c_int, c_longlong, c_int, c_int, _EPP, c_int, _P, c_size_t, _P]),
     "wspc_conv1x1_wgrad_workspace_bytes": (c_size_t, [c_int, c_int]),
     "wspc_conv1x1_wgrad": (c_int, [_OPP, c_int, _OPP, c_int, c_longlong, _P, _P, _P, c_size_t, _P]),
     "wspc_bn_finalize": (c_int, [_P, c_int, c_double, _P, _P, c_float, c_float, c_int, _P, _P, _P, _P, _P, _P, _P]),

@@ -16,7 +16,8 @@ int wgrad_tc_slabs(int K1, int K2);
 int wgrad_tc_dispatch(const Operand& A, int amode, const Operand& G, int gmode, long long M, int S, int K1p, int K2p,
                       float* partial, float* partial_b, cudaStream_t st);
 int rowgemm_tc_dispatch(const Operand& A, int amode, const float* Bm, long long ldb, int bT, long long M, int N, int K,
-                        const Epilogue& E, int emode, cudaStream_t st);
+                        const Epilogue& E, int emode, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t rowgemm_tc_workspace_bytes(int N, int K);
 static int g_gemm_path = 0;   // 0 = auto (tcgen05 where eligible), 1 = CUDA-core kernels only
 namespace {
 
@@ -388,9 +389,14 @@ extern "C" int wspc_set_gemm_path(int path) {
   return old;
 }
 
-extern "C" int wspc_conv1x1_rows(const wspc_operand_t* A, int a_mode, const float* Bm, long long ldb,
-                                 int b_transposed, long long M, int N, int K, const wspc_epilogue_t* epi,
-                                 int epi_mode, wspc_stream_t stream) {
+extern "C" size_t wspc_conv1x1_rows_workspace_bytes(int N, int K) {
+  if (N < 1 || K < 1) return 0;
+  return rowgemm_tc_workspace_bytes(N, K);
+}
+
+extern "C" int wspc_conv1x1_rows_ws(const wspc_operand_t* A, int a_mode, const float* Bm, long long ldb,
+                                    int b_transposed, long long M, int N, int K, const wspc_epilogue_t* epi,
+                                    int epi_mode, void* workspace, size_t workspace_bytes, wspc_stream_t stream) {
   if (int rc = check_arch()) return rc;
   WSPC_REQUIRE(A && Bm && epi, "conv1x1_rows: null argument");
   WSPC_REQUIRE(M >= 1 && N >= 1 && K >= 1, "conv1x1_rows: bad shape M=%lld N=%d K=%d", M, N, K);
@@ -405,7 +411,7 @@ extern "C" int wspc_conv1x1_rows(const wspc_operand_t* A, int a_mode, const floa
   // tensor-core (tcgen05) path for eligible shapes; WSPC_GEMM=simt forces the CUDA-core kernels (A/B testing)
   static const bool env_simt = []() { const char* e = getenv("WSPC_GEMM"); return e && strcmp(e, "simt") == 0; }();
   if (!env_simt && g_gemm_path == 0) {
-    const int rc = rowgemm_tc_dispatch(*A, a_mode, Bm, ldb, b_transposed, M, N, K, *epi, epi_mode, st);
+    const int rc = rowgemm_tc_dispatch(*A, a_mode, Bm, ldb, b_transposed, M, N, K, *epi, epi_mode, workspace, workspace_bytes, st);
     if (rc != 0) return rc < 0 ? rc : WSPC_OK;
   }
   switch (a_mode) {
@@ -417,6 +423,12 @@ extern "C" int wspc_conv1x1_rows(const wspc_operand_t* A, int a_mode, const floa
   }
   set_error("conv1x1_rows: bad operand mode %d", a_mode);
   return WSPC_ERR_INVALID;
+}
+
+extern "C" int wspc_conv1x1_rows(const wspc_operand_t* A, int a_mode, const float* Bm, long long ldb,
+                                 int b_transposed, long long M, int N, int K, const wspc_epilogue_t* epi,
+                                 int epi_mode, wspc_stream_t stream) {
+  return wspc_conv1x1_rows_ws(A, a_mode, Bm, ldb, b_transposed, M, N, K, epi, epi_mode, nullptr, 0, stream);
 }
 
 extern "C" size_t wspc_conv1x1_wgrad_workspace_bytes(int K1, int K2) {

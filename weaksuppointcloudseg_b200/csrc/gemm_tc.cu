@@ -324,7 +324,8 @@ __host__ __device__ inline TcSmem tc_smem_plan(int K, int N, bool need_stage) {
 template <int AMODE, int EMODE, int MINB, int MAXPASS>
 __global__ void __launch_bounds__(TC_THREADS, MINB)
 rowgemm_tc_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, int bT, long long M, int N, int K,
-                  const Epilogue E, int num_tiles, int tmem_cols, int KC, int NtMax, int generic) {
+                  const Epilogue E, int num_tiles, int tmem_cols, int KC, int NtMax, int generic,
+                  const unsigned char* __restrict__ wimg) {
   extern __shared__ __align__(128) unsigned char smem[];
   const TcSmem sp = tc_smem_plan(KC, NtMax, true);
   unsigned char* sBhi = smem + sp.off_bhi;
@@ -333,6 +334,7 @@ rowgemm_tc_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, 
   unsigned char* sAlo = smem + sp.off_alo;
   float* stage = reinterpret_cast<float*>(smem + sp.off_stage);
   uint64_t* mma_bar = reinterpret_cast<uint64_t*>(smem + sp.off_misc);
+  uint64_t* w_bar = reinterpret_cast<uint64_t*>(smem + sp.off_misc + 8);      // pre-split weight block landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + sp.off_misc + 16);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -346,6 +348,7 @@ rowgemm_tc_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, 
   if (warp == 0) tc_alloc(tmem_slot, (uint32_t)tmem_cols);
   if (tid == 32) {
     mbar_init(mma_bar, 1);
+    mbar_init(w_bar, 1);
     mbar_fence_init();
   }
   // weights of chunk kc: element (n, k) of Bm^T -> group (k - kc*KC)/8, row n, slot k%8 ; zero padded
@@ -389,7 +392,11 @@ rowgemm_tc_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, 
       for (int j = 0; j < 4; ++j) { st0[p][j] = 0.0; st1[p][j] = 0.0; }
   }
 
-  uint32_t phase = 0;
+  uint32_t phase = 0, wphase = 0;
+  // chunked K with a pre-split weight image (wprep_kernel): one bulk copy per chunk stages [hi | lo] (contiguous in
+  // shared memory for 8 channel groups) while the warps synthesise the A operand
+  const uint32_t wblock_bytes = 2u * (uint32_t)k8c * (uint32_t)sp.b_group_bytes;
+  const bool w_async = !resident_w && wimg != nullptr;
   const uint64_t a_inv = (AMODE == OP_EDGE) ? rowmap_inv(A.k) : 0;
   const uint64_t e_inv = (EMODE == EPI_EDGE_SCATTER) ? rowmap_inv(E.k) : 0;
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -407,7 +414,14 @@ rowgemm_tc_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, 
       const int cg = kc * (KC / 8) + kg;            // absolute channel group
       const bool kvalid = cg * 8 < K;
       if (!resident_w) {
-        load_w(kc);
+        if (w_async) {
+          if (tid == 0) {   // the previous chunk's MMAs (the last readers of sB) retired at the mma_bar wait below
+            mbar_expect_tx(w_bar, wblock_bytes);
+            bulk_g2s(sBhi, wimg + ((size_t)blockIdx.y * nkc + kc) * wblock_bytes, wblock_bytes, w_bar);
+          }
+        } else {
+          load_w(kc);
+        }
         load_consts<AMODE>(A, cg, K, pc0, pc1, pc2);
       }
 #pragma unroll 4
@@ -428,6 +442,7 @@ rowgemm_tc_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, 
       __syncthreads();
       // ------------------------------------------------------------ 2. MMA issue --------------
       if (tid == 0) {
+        if (w_async) mbar_wait(w_bar, wphase);
         tc_fence_after();
         const uint32_t a_hi = smem_u32(sAhi), a_lo = smem_u32(sAlo), b_hi = smem_u32(sBhi), b_lo = smem_u32(sBlo);
 #pragma unroll 1
@@ -445,6 +460,7 @@ rowgemm_tc_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, 
       }
       mbar_wait(mma_bar, phase);                    // MMAs of this chunk finished (smem reusable)
       phase ^= 1;
+      wphase ^= 1;
     }
     tc_fence_after();
 
@@ -602,6 +618,39 @@ rowgemm_tc_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, 
   if (warp == 0) tc_dealloc(tmem_base, (uint32_t)tmem_cols);
 }
 
+// Pre-split weight image for chunked K: per (N tile ny, chunk kc) one block [hi | lo], each [KC/8 groups][Npad rows][8]
+// bf16 with the kernel's padded group stride, i.e. exactly the shared-memory image of load_w -- so the GEMM kernel
+// stages a chunk with ONE bulk copy instead of re-splitting (KC x Nt) fp32 weights per 128-row tile.
+__global__ void __launch_bounds__(256)
+wprep_kernel(const float* __restrict__ Bm, long long ldb, int bT, int N, int K, int KC, int NtMax,
+             unsigned char* __restrict__ img) {
+  const TcSmem sp = tc_smem_plan(KC, NtMax, true);
+  const int k8c = sp.Kp / 8;
+  const int kc = blockIdx.x, ny = blockIdx.y, nkc = gridDim.x;
+  const int n0 = ny * NtMax;
+  const int Nt = (N - n0 < NtMax) ? (N - n0) : NtMax;
+  const size_t bbytes = (size_t)k8c * sp.b_group_bytes;
+  unsigned char* hi_blk = img + ((size_t)ny * nkc + kc) * 2 * bbytes;
+  unsigned char* lo_blk = hi_blk + bbytes;
+  for (int e = threadIdx.x; e < sp.Npad * k8c; e += blockDim.x) {
+    const int n = e % sp.Npad, g = e / sp.Npad;
+    float w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = kc * KC + g * 8 + i;
+      w[i] = (n < Nt && k < K) ? (bT ? Bm[(long long)(n0 + n) * ldb + k] : Bm[(long long)k * ldb + n0 + n]) : 0.f;
+    }
+    uint4 hi, lo;
+    split8(w, hi, lo);
+    *reinterpret_cast<uint4*>(hi_blk + (size_t)g * sp.b_group_bytes + n * 16) = hi;
+    *reinterpret_cast<uint4*>(lo_blk + (size_t)g * sp.b_group_bytes + n * 16) = lo;
+  }
+  for (int g = threadIdx.x; g < k8c; g += blockDim.x) {     // the 16 pad bytes of every group travel with the bulk copy
+    *reinterpret_cast<uint4*>(hi_blk + (size_t)g * sp.b_group_bytes + sp.Npad * 16) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(lo_blk + (size_t)g * sp.b_group_bytes + sp.Npad * 16) = make_uint4(0, 0, 0, 0);
+  }
+}
+
 struct TcPlan {
   int KC, NtMax, ntiles_n, npass, tmem_cols;
   size_t smem;
@@ -623,6 +672,15 @@ TcPlan tc_plan(int N, int K) {
   if (p.npass == 2 && p.minb > 2) p.minb = 2;   // matches the instantiations launched below
   if (p.npass > 2) p.minb = p.two ? 2 : 1;
   return p;
+}
+
+// bytes of the pre-split weight image (0 when the weights stay resident in shared memory: single K chunk)
+size_t tc_wimg_bytes(int N, int K) {
+  const TcPlan p = tc_plan(N, K);
+  const int nkc = (K + p.KC - 1) / p.KC;
+  if (nkc <= 1) return 0;
+  const TcSmem sp = tc_smem_plan(p.KC, p.NtMax, true);
+  return (size_t)p.ntiles_n * nkc * 2 * (sp.Kp / 8) * sp.b_group_bytes;
 }
 
 // aligned fast path for the A operand? (otherwise the element-wise loader is used inside the same kernel)
@@ -658,9 +716,17 @@ bool tc_supported(const Operand& A, int amode, const float* Bm, long long M, int
 
 template <int AMODE, int EMODE>
 int launch_tc(const Operand& A, const float* Bm, long long ldb, int bT, long long M, int N, int K, const Epilogue& E,
-              cudaStream_t st) {
+              void* ws, size_t ws_bytes, cudaStream_t st) {
   const int generic = tc_operand_fast(A, AMODE, K) ? 0 : 1;
   const TcPlan pl = tc_plan(N, K);
+  const unsigned char* wimg = nullptr;
+  const size_t need = tc_wimg_bytes(N, K);
+  if (need && ws && ws_bytes >= need && aligned16(ws)) {     // chunked K: stage pre-split weights with bulk copies
+    const int nkc = (K + pl.KC - 1) / pl.KC;
+    wprep_kernel<<<dim3(nkc, pl.ntiles_n), 256, 0, st>>>(Bm, ldb, bT, N, K, pl.KC, pl.NtMax, static_cast<unsigned char*>(ws));
+    count_launch();
+    wimg = static_cast<const unsigned char*>(ws);
+  }
   const int num_tiles = (int)((M + TILE_M - 1) / TILE_M);
   const int ctas = pl.minb * kNumSM;
   int gx = (ctas + pl.ntiles_n - 1) / pl.ntiles_n;
@@ -671,7 +737,7 @@ int launch_tc(const Operand& A, const float* Bm, long long ldb, int bT, long lon
   {                                                                                                            \
     auto kern = rowgemm_tc_kernel<AMODE, EMODE, MINB_, NP_>;                                                   \
     WSPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));          \
-    kern<<<grid, TC_THREADS, pl.smem, st>>>(A, Bm, ldb, bT, M, N, K, E, num_tiles, pl.tmem_cols, pl.KC, pl.NtMax, generic); \
+    kern<<<grid, TC_THREADS, pl.smem, st>>>(A, Bm, ldb, bT, M, N, K, E, num_tiles, pl.tmem_cols, pl.KC, pl.NtMax, generic, wimg); \
   }
   if (pl.npass <= 1) { if (pl.minb == 3) WSPC_TC_LAUNCH(3, 1) else if (pl.minb == 2) WSPC_TC_LAUNCH(2, 1) else WSPC_TC_LAUNCH(1, 1) }
   else if (pl.npass <= 2) { if (pl.minb >= 2) WSPC_TC_LAUNCH(2, 2) else WSPC_TC_LAUNCH(1, 2) }
@@ -949,12 +1015,14 @@ namespace {
 }  // namespace
 
 // returns 1 if the tensor-core path handled the call, 0 if the shape is not eligible, <0 on error
+size_t rowgemm_tc_workspace_bytes(int N, int K) { return tc_wimg_bytes(N, K); }
+
 int rowgemm_tc_dispatch(const Operand& A, int amode, const float* Bm, long long ldb, int bT, long long M, int N, int K,
-                        const Epilogue& E, int emode, cudaStream_t st) {
+                        const Epilogue& E, int emode, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (!tc_supported(A, amode, Bm, M, N, K, E, emode)) return 0;
   int rc = -100;
 #define WSPC_TC(AM, EM) \
-  if (amode == AM && emode == EM) rc = launch_tc<AM, EM>(A, Bm, ldb, bT, M, N, K, E, st);
+  if (amode == AM && emode == EM) rc = launch_tc<AM, EM>(A, Bm, ldb, bT, M, N, K, E, ws, ws_bytes, st);
   WSPC_TC(OP_PLAIN, EPI_STORE) WSPC_TC(OP_PLAIN, EPI_STORE_STATS)
   WSPC_TC(OP_BNRELU, EPI_STORE) WSPC_TC(OP_BNRELU, EPI_STORE_STATS)
   WSPC_TC(OP_EDGE, EPI_STORE) WSPC_TC(OP_EDGE, EPI_STORE_STATS)

@@ -144,8 +144,11 @@ def _addr(t, col_off=0):
 
 def rows_gemm(A, Bm, ldb, bT, M, N, K, epi: L.Epilogue, epi_mode):
     a, amode = A
-    L.check(L.lib().wspc_conv1x1_rows(ctypes.byref(a), amode, L.ptr(Bm) if torch.is_tensor(Bm) else Bm, ldb, bT, M, N, K,
-                                      ctypes.byref(epi), epi_mode, L.stream()))
+    nbytes = L.lib().wspc_conv1x1_rows_workspace_bytes(N, K)       # pre-split weight image for chunked K (K > 128)
+    ws = L.workspace(nbytes, torch.cuda.current_device(), "gemm_w") if nbytes else None
+    L.check(L.lib().wspc_conv1x1_rows_ws(ctypes.byref(a), amode, L.ptr(Bm) if torch.is_tensor(Bm) else Bm, ldb, bT, M, N, K,
+                                         ctypes.byref(epi), epi_mode, L.ptr(ws), ws.numel() if ws is not None else 0,
+                                         L.stream()))
 
 
 def wgrad(A, G, M, dW, db, device):
