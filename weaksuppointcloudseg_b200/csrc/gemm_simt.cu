@@ -378,6 +378,86 @@ int launch_wgrad_g(const Operand& A, const Operand& G, int gmode, long long M, c
   return WSPC_OK;
 }
 
+
+// ---------------------------------------------------------------- narrow outputs (N <= 16) ---
+// seg/conv3 of the S3DIS net (256 -> 13, DGCNN_S3DIS.py:100-101) and similar heads: one warp per row, the lane owns
+// 8 input channels per 256-channel slice (coalesced operand load through load8), the transposed weights sit in
+// shared memory, and the <= 16 partial dot products are reduced with warp shuffles.  out = acc + bias (EPI_STORE).
+template <int AMODE>
+__global__ void __launch_bounds__(256)
+rows_narrow_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, int bT, long long M, int N, int K,
+                   const Epilogue E) {
+  extern __shared__ float Ws[];                 // [N][K + 4]  (row pitch keeps float4 reads conflict-light)
+  const int pitch = K + 4;
+  for (int e = threadIdx.x; e < N * K; e += blockDim.x) {
+    const int n = e / K, k = e - n * K;
+    Ws[n * pitch + k] = bT ? Bm[(long long)n * ldb + k] : Bm[(long long)k * ldb + n];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp; row < M; row += wstride) {
+    float acc[16];
+#pragma unroll
+    for (int n = 0; n < 16; ++n) acc[n] = 0.f;
+    for (int c0 = lane * 8; c0 < K; c0 += 256) {
+      float v[8];
+      load8<AMODE>(A, row, c0, v);
+#pragma unroll
+      for (int n = 0; n < 16; ++n) {
+        if (n < N) {
+          const float4 w0 = *reinterpret_cast<const float4*>(Ws + n * pitch + c0);
+          const float4 w1 = *reinterpret_cast<const float4*>(Ws + n * pitch + c0 + 4);
+          acc[n] = fmaf(v[0], w0.x, acc[n]); acc[n] = fmaf(v[1], w0.y, acc[n]);
+          acc[n] = fmaf(v[2], w0.z, acc[n]); acc[n] = fmaf(v[3], w0.w, acc[n]);
+          acc[n] = fmaf(v[4], w1.x, acc[n]); acc[n] = fmaf(v[5], w1.y, acc[n]);
+          acc[n] = fmaf(v[6], w1.z, acc[n]); acc[n] = fmaf(v[7], w1.w, acc[n]);
+        }
+      }
+    }
+    // 16 values x 32 lanes -> lane n holds the total of value n: halve the number of live values at every step
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {     // step 16: lanes with bit 4 clear keep values 0..7, the others 8..15
+      const float send = (lane & 16) ? acc[n] : acc[n + 8];
+      const float keep = (lane & 16) ? acc[n + 8] : acc[n];
+      acc[n] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      const float send = (lane & 8) ? acc[n] : acc[n + 4];
+      const float keep = (lane & 8) ? acc[n + 4] : acc[n];
+      acc[n] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int n = 0; n < 2; ++n) {
+      const float send = (lane & 4) ? acc[n] : acc[n + 2];
+      const float keep = (lane & 4) ? acc[n + 2] : acc[n];
+      acc[n] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    {
+      const float send = (lane & 2) ? acc[0] : acc[1];
+      const float keep = (lane & 2) ? acc[1] : acc[0];
+      acc[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], 1);
+    // lane l now holds value n(l) = 8*b4 + 4*b3 + 2*b2 + b1 (bits of l); lanes with bit 0 clear write
+    const int n = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+    if ((lane & 1) == 0 && n < N) E.out[row * E.ldo + n] = acc[0] + (E.bias ? E.bias[n] : 0.f);
+  }
+}
+
+template <int AMODE>
+int launch_rows_narrow(const Operand& A, const float* Bm, long long ldb, int bT, long long M, int N, int K, const Epilogue& E,
+                       cudaStream_t st) {
+  const size_t smem = (size_t)N * (K + 4) * sizeof(float);
+  long long blocks = (M + 7) / 8;
+  if (blocks > 8LL * kNumSM) blocks = 8LL * kNumSM;
+  rows_narrow_kernel<AMODE><<<(unsigned)blocks, 256, smem, st>>>(A, Bm, ldb, bT, M, N, K, E);
+  count_launch();
+  WSPC_LAUNCH_CHECK("rows_narrow_kernel");
+  return WSPC_OK;
+}
+
 }  // namespace
 }  // namespace wspc
 
@@ -413,6 +493,12 @@ extern "C" int wspc_conv1x1_rows_ws(const wspc_operand_t* A, int a_mode, const f
   if (!env_simt && g_gemm_path == 0) {
     const int rc = rowgemm_tc_dispatch(*A, a_mode, Bm, ldb, b_transposed, M, N, K, *epi, epi_mode, workspace, workspace_bytes, st);
     if (rc != 0) return rc < 0 ? rc : WSPC_OK;
+  }
+  // narrow outputs (N <= 16, K a multiple of 8): warp-per-row kernel
+  if (!env_simt && g_gemm_path == 0 && epi_mode == EPI_STORE && N <= 16 && K % 8 == 0 && K >= 64 && K <= 2048 &&
+      !epi->rowbias && (a_mode == OP_PLAIN || a_mode == OP_BNRELU) && (size_t)N * (K + 4) * 4 <= 48 * 1024) {
+    if (a_mode == OP_PLAIN) return launch_rows_narrow<OP_PLAIN>(*A, Bm, ldb, b_transposed, M, N, K, *epi, st);
+    return launch_rows_narrow<OP_BNRELU>(*A, Bm, ldb, b_transposed, M, N, K, *epi, st);
   }
   switch (a_mode) {
     case OP_PLAIN: return launch_rows_e<OP_PLAIN>(*A, Bm, ldb, b_transposed, M, N, K, *epi, epi_mode, st);

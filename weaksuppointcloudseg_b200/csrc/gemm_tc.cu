@@ -1023,7 +1023,7 @@ int rowgemm_tc_dispatch(const Operand& A, int amode, const float* Bm, long long 
   int rc = -100;
 #define WSPC_TC(AM, EM) \
   if (amode == AM && emode == EM) rc = launch_tc<AM, EM>(A, Bm, ldb, bT, M, N, K, E, ws, ws_bytes, st);
-  WSPC_TC(OP_PLAIN, EPI_STORE) WSPC_TC(OP_PLAIN, EPI_STORE_STATS)
+  WSPC_TC(OP_PLAIN, EPI_STORE) WSPC_TC(OP_PLAIN, EPI_STORE_STATS) WSPC_TC(OP_PLAIN, EPI_ACCUM)
   WSPC_TC(OP_BNRELU, EPI_STORE) WSPC_TC(OP_BNRELU, EPI_STORE_STATS)
   WSPC_TC(OP_EDGE, EPI_STORE) WSPC_TC(OP_EDGE, EPI_STORE_STATS)
   WSPC_TC(OP_DY, EPI_STORE) WSPC_TC(OP_DY, EPI_RELUMASK_STATS) WSPC_TC(OP_DY, EPI_EDGE_SCATTER) WSPC_TC(OP_DY, EPI_ACCUM)
