@@ -446,6 +446,65 @@ rows_narrow_kernel(const Operand A, const float* __restrict__ Bm, long long ldb,
   }
 }
 
+
+// ---------------------------------------------------------------- narrow reductions (K <= 16) ---
+// Data gradient of a narrow head (seg/conv3: dA (P,256) = dZ (P,13) W^T, DGCNN_S3DIS.py:100-101 backward) fused with
+// the ReLU mask / dropout of the producing layer and its BN-backward sums (EPI_RELUMASK_STATS).  Thread = 4 output
+// columns of a row; the K <= 16 gradient values of the row are a broadcast load; W^T sits in shared memory.
+__global__ void __launch_bounds__(256)
+rows_narrowk_relumask_kernel(const float* __restrict__ G, long long ldg, const float* __restrict__ Bm, long long ldb, int bT,
+                             long long M, int N, int K, const Epilogue E) {
+  extern __shared__ float sm[];
+  float* Wt = sm;                                 // [K][N]
+  float* red = sm + (size_t)K * N;                // [2][N]
+  for (int e = threadIdx.x; e < K * N; e += blockDim.x) {
+    const int k = e / N, n = e - k * N;
+    Wt[e] = bT ? Bm[(long long)n * ldb + k] : Bm[(long long)k * ldb + n];
+  }
+  for (int e = threadIdx.x; e < 2 * N; e += blockDim.x) red[e] = 0.f;
+  __syncthreads();
+  const int n4 = N >> 2;
+  const int c = (threadIdx.x % n4) * 4;
+  const int rpb = blockDim.x / n4;                // rows per block sweep
+  const float4 sc = *reinterpret_cast<const float4*>(E.scp + c), sh = *reinterpret_cast<const float4*>(E.shp + c);
+  float f0[4] = {0.f, 0.f, 0.f, 0.f}, f1[4] = {0.f, 0.f, 0.f, 0.f};
+  for (long long row = (long long)blockIdx.x * rpb + threadIdx.x / n4; row < M; row += (long long)gridDim.x * rpb) {
+    const float* g = G + row * ldg;
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < K; ++k) {
+      const float gv = g[k];
+      const float4 w = *reinterpret_cast<const float4*>(Wt + (size_t)k * N + c);
+      o[0] = fmaf(gv, w.x, o[0]); o[1] = fmaf(gv, w.y, o[1]); o[2] = fmaf(gv, w.z, o[2]); o[3] = fmaf(gv, w.w, o[3]);
+    }
+    const float4 y4 = *reinterpret_cast<const float4*>(E.yprev + row * E.ldyp + c);
+    const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
+    const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+    float dm[4] = {1.f, 1.f, 1.f, 1.f};
+    if (E.dmask) {
+      const float4 m4 = *reinterpret_cast<const float4*>(E.dmask + row * N + c);
+      dm[0] = m4.x * E.dscale; dm[1] = m4.y * E.dscale; dm[2] = m4.z * E.dscale; dm[3] = m4.w * E.dscale;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool on = fmaf(yv[j], scv[j], shv[j]) > 0.f;
+      o[j] = on ? o[j] * dm[j] : 0.f;
+      f0[j] += o[j];
+      f1[j] = fmaf(o[j], yv[j], f1[j]);
+    }
+    *reinterpret_cast<float4*>(E.out + row * E.ldo + c) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    atomicAdd(&red[c + j], f0[j]);
+    atomicAdd(&red[N + c + j], f1[j]);
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < N; e += blockDim.x) {
+    atomicAdd(E.stats + e, (double)red[e]);
+    atomicAdd(E.stats + N + e, (double)red[N + e]);
+  }
+}
+
 template <int AMODE>
 int launch_rows_narrow(const Operand& A, const float* Bm, long long ldb, int bT, long long M, int N, int K, const Epilogue& E,
                        cudaStream_t st) {
@@ -499,6 +558,19 @@ extern "C" int wspc_conv1x1_rows_ws(const wspc_operand_t* A, int a_mode, const f
       !epi->rowbias && (a_mode == OP_PLAIN || a_mode == OP_BNRELU) && (size_t)N * (K + 4) * 4 <= 48 * 1024) {
     if (a_mode == OP_PLAIN) return launch_rows_narrow<OP_PLAIN>(*A, Bm, ldb, b_transposed, M, N, K, *epi, st);
     return launch_rows_narrow<OP_BNRELU>(*A, Bm, ldb, b_transposed, M, N, K, *epi, st);
+  }
+  // narrow reductions (K <= 16): data gradient of a narrow head fused with the ReLU-mask / BN-sum epilogue
+  if (!env_simt && g_gemm_path == 0 && epi_mode == EPI_RELUMASK_STATS && a_mode == OP_DY && !A->c1 && K <= 16 && N % 4 == 0 &&
+      N <= 1024 && 256 % (N / 4) == 0 && aligned16(epi->out) && (epi->ldo % 4) == 0 && aligned16(epi->yprev) &&
+      (epi->ldyp % 4) == 0 && aligned16(epi->scp) && aligned16(epi->shp) && (!epi->dmask || aligned16(epi->dmask))) {
+    const size_t smem = ((size_t)K * N + 2 * (size_t)N) * sizeof(float);
+    const int rpb = 256 / (N / 4);
+    long long blocks = (M + rpb - 1) / rpb;
+    if (blocks > 8LL * kNumSM) blocks = 8LL * kNumSM;
+    rows_narrowk_relumask_kernel<<<(unsigned)blocks, 256, smem, st>>>(A->p, A->ld, Bm, ldb, b_transposed, M, N, K, *epi);
+    count_launch();
+    WSPC_LAUNCH_CHECK("rows_narrowk_relumask_kernel");
+    return WSPC_OK;
   }
   switch (a_mode) {
     case OP_PLAIN: return launch_rows_e<OP_PLAIN>(*A, Bm, ldb, b_transposed, M, N, K, *epi, epi_mode, st);
