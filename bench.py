@@ -35,7 +35,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--samples", type=int, default=64, help="Siamese samples per GPU (network clouds = 2x)")
     ap.add_argument("--points", type=int, default=4096)
-    ap.add_argument("--cpu-clouds", type=int, default=2, help="clouds per CPU-baseline step (bounded sample)")
+    ap.add_argument("--cpu-clouds", type=int, default=8, help="clouds per CPU-baseline step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 

@@ -99,17 +99,21 @@ int wspc_topk_rows(const float* adj, long long rows, int ncols, int k, int32_t* 
 #define WSPC_OP_EDGE 2      /* row=(point i, slot r): [x_i | x_idx[i,r] - x_i], C = 2*Cx            tf_util.py:696-705 */
 #define WSPC_OP_DY 3        /* c1[c]*p[row,c] + c2[c] + c3[c]*y[row,c]  (BN backward as an affine map; c1==NULL: p) */
 #define WSPC_OP_DY_SPARSE 4 /* as DY with G[row,c] = (amax[cloud,c]==row%npts) ? dg[cloud,c] : 0   (max_pool2d grad) */
+#define WSPC_OP_DY_MAXK 5   /* as DY with G synthesised from the max over k (tf.reduce_max grad, equal split among ties):
+                               row=(point i, slot r); a = relu(y*sc+sh); p = MS (points, 2C) = [max_r a | dout/ties] from
+                               wspc_maxk_bnrelu_bwd_stats; G = (a == MS[i,c] && MS[i,c] > 0) ? MS[i,C+c] : 0 */
 
 typedef struct wspc_operand {
-  const float* p;   /* PLAIN: matrix; BNRELU: pre-BN activation; EDGE: point features; DY: upstream gradient G */
+  const float* p;   /* PLAIN: matrix; BNRELU: pre-BN activation; EDGE: point features; DY: upstream gradient G;
+                       DY_MAXK: MS (points, 2C) */
   long long ld;     /* leading dimension of p (floats) */
   int C;            /* logical channels */
-  const float* sc;  /* BNRELU: gamma*rsqrt(var+eps) */
-  const float* sh;  /* BNRELU: beta - mean*sc */
+  const float* sc;  /* BNRELU, DY_MAXK: gamma*rsqrt(var+eps) of the layer whose activation is formed */
+  const float* sh;  /* BNRELU, DY_MAXK: beta - mean*sc */
   const float* dmask; /* BNRELU: optional dropout mask (rows, C) of 0/1 floats, or NULL */
   float dscale;     /* BNRELU: 1/keep_prob */
   const int32_t* idx; /* EDGE: (points, k) neighbour ids, local to the cloud */
-  int k;            /* EDGE: neighbours per point */
+  int k;            /* EDGE, DY_MAXK: neighbours (rows) per point */
   int npts;         /* EDGE / DY_SPARSE: points per cloud */
   const float* y;   /* DY*: pre-BN output of the layer being differentiated */
   long long ldy;
@@ -201,6 +205,11 @@ int wspc_maxk_bnrelu_fwd(const float* y, const float* sc, const float* sh, long 
 int wspc_maxk_bnrelu_bwd(const float* y, const float* sc, const float* sh, const float* out, long long ldo,
                          const float* dout, long long lddo, long long P, int k, int C, float* G, double* stats,
                          wspc_stream_t stream);
+/* Statistics-only variant: writes MS (P, 2C) = [max over k of relu(bn(y)) | dout / #ties] and the BN-backward sums instead of
+ * the (P*k, C) gradient; the consumers synthesise G on load (WSPC_OP_DY_MAXK, wspc_edge_combine_bwd_maxk). */
+int wspc_maxk_bnrelu_bwd_stats(const float* y, const float* sc, const float* sh, const float* out, long long ldo,
+                               const float* dout, long long lddo, long long P, int k, int C, float* MS, double* stats,
+                               wspc_stream_t stream);
 /* g[b,c] = max_n relu(bn(y[b,n,c])), amax = first arg-max  == tf_util.max_pool2d([N,1]) (tf_util.py:357-380) */
 int wspc_maxn_bnrelu_fwd(const float* y, const float* sc, const float* sh, int B, int N, int C, float* g,
                          int32_t* amax, wspc_stream_t stream);
@@ -241,6 +250,10 @@ int wspc_edge_combine_fwd(const float* UV, long long ldu, const int32_t* idx, co
 int wspc_edge_combine_bwd(const float* G, const float* y, const float* c1, const float* c2, const float* c3,
                           const int32_t* idx, long long P, int k, int npts, int Cout, float* DUV, long long ldd,
                           wspc_stream_t stream);
+/* as wspc_edge_combine_bwd with G synthesised from the max over k (WSPC_OP_DY_MAXK; MS from wspc_maxk_bnrelu_bwd_stats) */
+int wspc_edge_combine_bwd_maxk(const float* y, const float* c1, const float* c2, const float* c3, const float* sc,
+                               const float* sh, const float* MS, const int32_t* idx, long long P, int k, int npts, int Cout,
+                               float* DUV, long long ldd, wspc_stream_t stream);
 int wspc_edge_merge_wgrad(const float* dWc, const float* dbc, int Cx, int Cout, float* dW, float* db,
                           wspc_stream_t stream);
 

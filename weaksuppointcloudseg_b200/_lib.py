@@ -125,7 +125,7 @@ class Epilogue(ctypes.Structure):
                 ("npts", c_int)]
 
 
-OP_PLAIN, OP_BNRELU, OP_EDGE, OP_DY, OP_DY_SPARSE = range(5)
+OP_PLAIN, OP_BNRELU, OP_EDGE, OP_DY, OP_DY_SPARSE, OP_DY_MAXK = range(6)
 EPI_STORE, EPI_STORE_STATS, EPI_RELUMASK_STATS, EPI_ACCUM, EPI_EDGE_SCATTER = range(5)
 
 _OPP = ctypes.POINTER(Operand)
@@ -140,6 +140,8 @@ _EXTRA_DECLS.update({
     "wspc_bn_bwd_coeffs": (c_int, [_P, c_int, c_double, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "wspc_maxk_bnrelu_fwd": (c_int, [_P, _P, _P, c_longlong, c_int, c_int, _P, c_longlong, _P]),
     "wspc_maxk_bnrelu_bwd": (c_int, [_P, _P, _P, _P, c_longlong, _P, c_longlong, c_longlong, c_int, c_int, _P, _P, _P]),
+    "wspc_maxk_bnrelu_bwd_stats": (c_int, [_P, _P, _P, _P, c_longlong, _P, c_longlong, c_longlong, c_int, c_int, _P, _P, _P]),
+    "wspc_edge_combine_bwd_maxk": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_longlong, c_int, c_int, c_int, _P, c_longlong, _P]),
     "wspc_maxn_bnrelu_fwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P, _P]),
     "wspc_maxn_bwd_gate": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P]),
     "wspc_cloud_colsum": (c_int, [_OPP, c_int, c_int, _P, _P]),

@@ -154,6 +154,75 @@ maxk_bwd_kernel(const float* __restrict__ y, const float* __restrict__ sc, const
   }
 }
 
+// Statistics-only backward of the max over k: instead of materialising G (P*k, C) it writes, per point, the pooled maximum
+// and the tie-split share  MS[p, 0:C] = max_r a,  MS[p, C:2C] = dout / #ties  (0 when the maximum is not positive), from
+// which the GEMM loaders synthesise G on the fly (WSPC_OP_DY_MAXK), and accumulates the BN-backward sums
+// stats[0] += sum G, stats[1] += sum G*y.  One read of y.
+__global__ void __launch_bounds__(256)
+maxk_bwd_stats_kernel(const float* __restrict__ y, const float* __restrict__ sc, const float* __restrict__ sh,
+                      const float* __restrict__ out, long long ldo, const float* __restrict__ dout, long long lddo,
+                      long long P, int k, int C, float* __restrict__ MS, double* __restrict__ stats) {
+  __shared__ float red[2][128];
+  const int tid = threadIdx.x;
+  const int C4 = C >> 2;
+  const long long t = (long long)blockIdx.x * blockDim.x + tid;
+  const bool valid = t < P * C4;
+  const long long p = valid ? t / C4 : 0;
+  const int c = valid ? (int)(t - p * C4) * 4 : 0;
+  (&red[0][0])[tid] = 0.f;
+  __syncthreads();
+  float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+  if (valid) {
+    const float4 s = *reinterpret_cast<const float4*>(sc + c), h = *reinterpret_cast<const float4*>(sh + c);
+    const float4 m4 = *reinterpret_cast<const float4*>(out + p * ldo + c);
+    const float4 go4 = *reinterpret_cast<const float4*>(dout + p * lddo + c);
+    const float m[4] = {m4.x, m4.y, m4.z, m4.w}, go[4] = {go4.x, go4.y, go4.z, go4.w};
+    const float* yp = y + p * k * C + c;
+    float cnt[4] = {0.f, 0.f, 0.f, 0.f}, ys[4] = {0.f, 0.f, 0.f, 0.f};
+    int r = 0;
+    for (; r + 4 <= k; r += 4) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldcs(reinterpret_cast<const float4*>(yp + (size_t)(r + u) * C));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float4 a = bnrelu4(v[u], s, h);
+        if (a.x == m[0]) { cnt[0] += 1.f; ys[0] += v[u].x; }
+        if (a.y == m[1]) { cnt[1] += 1.f; ys[1] += v[u].y; }
+        if (a.z == m[2]) { cnt[2] += 1.f; ys[2] += v[u].z; }
+        if (a.w == m[3]) { cnt[3] += 1.f; ys[3] += v[u].w; }
+      }
+    }
+    for (; r < k; ++r) {
+      const float4 v = __ldcs(reinterpret_cast<const float4*>(yp + (size_t)r * C));
+      const float4 a = bnrelu4(v, s, h);
+      if (a.x == m[0]) { cnt[0] += 1.f; ys[0] += v.x; }
+      if (a.y == m[1]) { cnt[1] += 1.f; ys[1] += v.y; }
+      if (a.z == m[2]) { cnt[2] += 1.f; ys[2] += v.z; }
+      if (a.w == m[3]) { cnt[3] += 1.f; ys[3] += v.w; }
+    }
+    float share[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      share[i] = (m[i] > 0.f && cnt[i] > 0.f) ? go[i] / cnt[i] : 0.f;
+      s0[i] = share[i] * cnt[i];
+      s1[i] = share[i] * ys[i];
+    }
+    *reinterpret_cast<float4*>(MS + p * 2 * C + c) = m4;
+    *reinterpret_cast<float4*>(MS + p * 2 * C + C + c) = make_float4(share[0], share[1], share[2], share[3]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    atomicAdd(&red[0][c + i], s0[i]);
+    atomicAdd(&red[1][c + i], s1[i]);
+  }
+  __syncthreads();
+  if (tid < C) {
+    atomicAdd(stats + tid, (double)red[0][tid]);
+    atomicAdd(stats + C + tid, (double)red[1][tid]);
+  }
+}
+
 // ------------------------------------------------------------- max over N ---
 // grid (C/32, B); block 32 x 8: lane = channel, 8 point groups
 __global__ void maxn_fwd_kernel(const float* __restrict__ y, const float* __restrict__ sc, const float* __restrict__ sh,
@@ -288,6 +357,23 @@ extern "C" int wspc_maxk_bnrelu_bwd(const float* y, const float* sc, const float
       y, sc, sh, out, ldo, dout, lddo, P, k, C, G, stats);
   count_launch();
   WSPC_LAUNCH_CHECK("maxk_bwd_kernel");
+  return WSPC_OK;
+}
+
+extern "C" int wspc_maxk_bnrelu_bwd_stats(const float* y, const float* sc, const float* sh, const float* out, long long ldo,
+                                          const float* dout, long long lddo, long long P, int k, int C, float* MS,
+                                          double* stats, wspc_stream_t stream) {
+  if (int rc = check_arch()) return rc;
+  WSPC_REQUIRE(y && sc && sh && out && dout && MS && stats, "maxk_bwd_stats: null pointer");
+  WSPC_REQUIRE(C >= 4 && C <= 128 && (C & 3) == 0 && (256 % (C >> 2)) == 0 && (ldo & 3) == 0 && (lddo & 3) == 0,
+               "maxk_bwd_stats: C=%d must be a multiple of 4, <= 128, with C/4 dividing 256; ldo/lddo multiples of 4", C);
+  WSPC_REQUIRE(aligned16(y) && aligned16(sc) && aligned16(sh) && aligned16(out) && aligned16(dout) && aligned16(MS),
+               "maxk_bwd_stats: pointers must be 16-byte aligned");
+  const long long total = P * (C >> 2);
+  maxk_bwd_stats_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      y, sc, sh, out, ldo, dout, lddo, P, k, C, MS, stats);
+  count_launch();
+  WSPC_LAUNCH_CHECK("maxk_bwd_stats_kernel");
   return WSPC_OK;
 }
 

@@ -8,7 +8,7 @@
 //     du_i = sum_j dy_ij,   dv_p = sum_{(i,j): idx_ij = p} dy_ij,   dX = [du | dv] [W1 - W2 | W2]^T,
 //     d[W1 - W2 | W2] = X^T [du | dv]   =>   dW1 = dWa,  dW2 = dWb - dWa.
 // Both kernels are HBM-bound on the (R, 64) tensors (y written once forward; G and y read once backward).
-#include "common.cuh"
+#include "operand.cuh"
 
 namespace wspc {
 void count_launch(int n = 1);
@@ -105,13 +105,23 @@ edge_combine_fwd_kernel(const float* __restrict__ UV, long long ldu, const int32
 // dy = c1*G + c2 + c3*y (batch-norm backward folded to an affine map; c1 == NULL: dy = G);
 // DUV[i, 0:64] = sum_j dy[(i,j), :];  DUV[cloud(i)*npts + idx[i,j], 64:128] += dy[(i,j), :]  (vector reductions).
 // block 256 = 16 points x 16 float4 columns.
+// MAXK: G is not read but synthesised from the max over k (WSPC_OP_DY_MAXK): G = (relu(y*sc+sh) == MS[i,c]) ? MS[i,64+c] : 0.
+template <bool MAXK>
 __global__ void __launch_bounds__(256)
 edge_combine_bwd_kernel(const float* __restrict__ G, const float* __restrict__ y, const float* __restrict__ c1,
                         const float* __restrict__ c2, const float* __restrict__ c3, const int32_t* __restrict__ idx,
-                        long long P, int k, int npts, float* __restrict__ DUV, long long ldd) {
+                        long long P, int k, int npts, float* __restrict__ DUV, long long ldd,
+                        const float* __restrict__ sc, const float* __restrict__ sh, const float* __restrict__ MS) {
   const int c4 = threadIdx.x & (C4 - 1), pl = threadIdx.x >> 4;
   const long long i = (long long)blockIdx.x * 16 + pl;
   if (i >= P) return;
+  float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), h4 = s4, m4 = s4, q4 = s4;
+  if (MAXK) {
+    s4 = *reinterpret_cast<const float4*>(sc + c4 * 4);
+    h4 = *reinterpret_cast<const float4*>(sh + c4 * 4);
+    m4 = *reinterpret_cast<const float4*>(MS + i * 2 * CO + c4 * 4);
+    q4 = *reinterpret_cast<const float4*>(MS + i * 2 * CO + CO + c4 * 4);
+  }
   float4 a1 = make_float4(1.f, 1.f, 1.f, 1.f), a2 = make_float4(0.f, 0.f, 0.f, 0.f), a3 = a2;
   if (c1) {
     a1 = *reinterpret_cast<const float4*>(c1 + c4 * 4);
@@ -130,8 +140,13 @@ edge_combine_bwd_kernel(const float* __restrict__ G, const float* __restrict__ y
     int nb[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      g[u] = __ldcs(reinterpret_cast<const float4*>(gp + (size_t)(j + u) * CO));
       yy[u] = c1 ? __ldcs(reinterpret_cast<const float4*>(yp + (size_t)(j + u) * CO)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (MAXK) {
+        g[u] = make_float4(maxk_grad(yy[u].x, s4.x, h4.x, m4.x, q4.x), maxk_grad(yy[u].y, s4.y, h4.y, m4.y, q4.y),
+                           maxk_grad(yy[u].z, s4.z, h4.z, m4.z, q4.z), maxk_grad(yy[u].w, s4.w, h4.w, m4.w, q4.w));
+      } else {
+        g[u] = __ldcs(reinterpret_cast<const float4*>(gp + (size_t)(j + u) * CO));
+      }
       nb[u] = ip[j + u];
     }
 #pragma unroll
@@ -146,8 +161,10 @@ edge_combine_bwd_kernel(const float* __restrict__ G, const float* __restrict__ y
     }
   }
   for (; j < k; ++j) {
-    const float4 g = __ldcs(reinterpret_cast<const float4*>(gp + (size_t)j * CO));
     const float4 yy = c1 ? __ldcs(reinterpret_cast<const float4*>(yp + (size_t)j * CO)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 g = MAXK ? make_float4(maxk_grad(yy.x, s4.x, h4.x, m4.x, q4.x), maxk_grad(yy.y, s4.y, h4.y, m4.y, q4.y),
+                                        maxk_grad(yy.z, s4.z, h4.z, m4.z, q4.z), maxk_grad(yy.w, s4.w, h4.w, m4.w, q4.w))
+                          : __ldcs(reinterpret_cast<const float4*>(gp + (size_t)j * CO));
     float4 d;
     d.x = fmaf(a3.x, yy.x, fmaf(a1.x, g.x, a2.x));
     d.y = fmaf(a3.y, yy.y, fmaf(a1.y, g.y, a2.y));
@@ -210,9 +227,25 @@ extern "C" int wspc_edge_combine_bwd(const float* G, const float* y, const float
   WSPC_REQUIRE(P >= 1 && k >= 1 && npts >= 1 && P % npts == 0, "edge_combine_bwd: bad shape P=%lld k=%d npts=%d", P, k, npts);
   WSPC_REQUIRE(aligned16(G) && aligned16(DUV) && (!y || aligned16(y)) && (!c1 || (aligned16(c1) && aligned16(c2) && aligned16(c3))),
                "edge_combine_bwd: pointers must be 16-byte aligned");
-  edge_combine_bwd_kernel<<<(unsigned)((P + 15) / 16), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(G, y, c1, c2, c3, idx, P,
-                                                                                                        k, npts, DUV, ldd);
+  edge_combine_bwd_kernel<false><<<(unsigned)((P + 15) / 16), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      G, y, c1, c2, c3, idx, P, k, npts, DUV, ldd, nullptr, nullptr, nullptr);
   count_launch();
   WSPC_LAUNCH_CHECK("edge_combine_bwd_kernel");
+  return WSPC_OK;
+}
+
+extern "C" int wspc_edge_combine_bwd_maxk(const float* y, const float* c1, const float* c2, const float* c3, const float* sc,
+                                          const float* sh, const float* MS, const int32_t* idx, long long P, int k, int npts,
+                                          int Cout, float* DUV, long long ldd, wspc_stream_t stream) {
+  if (int rc = check_arch()) return rc;
+  WSPC_REQUIRE(y && c1 && c2 && c3 && sc && sh && MS && idx && DUV, "edge_combine_bwd_maxk: null pointer");
+  WSPC_REQUIRE(Cout == CO && ldd >= 2 * CO && (ldd & 3) == 0, "edge_combine_bwd_maxk: Cout=%d ldd=%lld", Cout, ldd);
+  WSPC_REQUIRE(P >= 1 && k >= 1 && npts >= 1 && P % npts == 0, "edge_combine_bwd_maxk: bad shape P=%lld k=%d npts=%d", P, k, npts);
+  WSPC_REQUIRE(aligned16(y) && aligned16(DUV) && aligned16(MS) && aligned16(c1) && aligned16(c2) && aligned16(c3) &&
+               aligned16(sc) && aligned16(sh), "edge_combine_bwd_maxk: pointers must be 16-byte aligned");
+  edge_combine_bwd_kernel<true><<<(unsigned)((P + 15) / 16), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      nullptr, y, c1, c2, c3, idx, P, k, npts, DUV, ldd, sc, sh, MS);
+  count_launch();
+  WSPC_LAUNCH_CHECK("edge_combine_bwd_kernel<maxk>");
   return WSPC_OK;
 }

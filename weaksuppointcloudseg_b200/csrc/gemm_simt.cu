@@ -369,6 +369,8 @@ int launch_wgrad_g(const Operand& A, const Operand& G, int gmode, long long M, c
     colgemm_kernel<AMODE, OP_DY><<<grid, 256, 0, st>>>(A, G, M, rps, p.K1p, p.K2p, partial, partial_b);
   else if (gmode == OP_DY_SPARSE)
     colgemm_kernel<AMODE, OP_DY_SPARSE><<<grid, 256, 0, st>>>(A, G, M, rps, p.K1p, p.K2p, partial, partial_b);
+  else if (gmode == OP_DY_MAXK)
+    colgemm_kernel<AMODE, OP_DY_MAXK><<<grid, 256, 0, st>>>(A, G, M, rps, p.K1p, p.K2p, partial, partial_b);
   else {
     set_error("conv1x1_wgrad: bad gradient operand mode %d", gmode);
     return WSPC_ERR_INVALID;
@@ -540,6 +542,8 @@ extern "C" int wspc_conv1x1_rows_ws(const wspc_operand_t* A, int a_mode, const f
   WSPC_REQUIRE(A && Bm && epi, "conv1x1_rows: null argument");
   WSPC_REQUIRE(M >= 1 && N >= 1 && K >= 1, "conv1x1_rows: bad shape M=%lld N=%d K=%d", M, N, K);
   WSPC_REQUIRE(A->p || a_mode == OP_DY_SPARSE, "conv1x1_rows: operand pointer is null");
+  WSPC_REQUIRE(a_mode != OP_DY_MAXK || (A->y && A->c1 && A->c2 && A->c3 && A->sc && A->sh && A->k >= 1 && A->ld >= 2 * A->C),
+               "conv1x1_rows: incomplete DY_MAXK operand");
   WSPC_REQUIRE(A->C == K, "conv1x1_rows: operand channels %d != K %d", A->C, K);
   if (epi_mode == EPI_EDGE_SCATTER) WSPC_REQUIRE(epi->dx && epi->idx && epi->k > 0 && epi->npts > 0 && (N % 2) == 0,
                                                  "conv1x1_rows: incomplete scatter epilogue");
@@ -578,6 +582,7 @@ extern "C" int wspc_conv1x1_rows_ws(const wspc_operand_t* A, int a_mode, const f
     case OP_EDGE: return launch_rows_e<OP_EDGE>(*A, Bm, ldb, b_transposed, M, N, K, *epi, epi_mode, st);
     case OP_DY: return launch_rows_e<OP_DY>(*A, Bm, ldb, b_transposed, M, N, K, *epi, epi_mode, st);
     case OP_DY_SPARSE: return launch_rows_e<OP_DY_SPARSE>(*A, Bm, ldb, b_transposed, M, N, K, *epi, epi_mode, st);
+    case OP_DY_MAXK: return launch_rows_e<OP_DY_MAXK>(*A, Bm, ldb, b_transposed, M, N, K, *epi, epi_mode, st);
   }
   set_error("conv1x1_rows: bad operand mode %d", a_mode);
   return WSPC_ERR_INVALID;

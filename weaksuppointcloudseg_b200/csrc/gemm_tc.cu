@@ -182,6 +182,15 @@ __device__ __forceinline__ void load_chunk(const Operand& A, long long row, int 
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = g[i];
     }
+  } else if (AMODE == OP_DY_MAXK) {   // pt = point of the row
+    float y[8], m[8], sh8[8], sc8[8], hh[8];
+    ld8(A.y + row * A.ldy + kg * 8, y);
+    ld8(A.p + pt * A.ld + kg * 8, m);
+    ld8(A.p + pt * A.ld + A.C + kg * 8, sh8);
+    ld8(A.sc + kg * 8, sc8);
+    ld8(A.sh + kg * 8, hh);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaf(pc0[i], maxk_grad(y[i], sc8[i], hh[i], m[i], sh8[i]), fmaf(pc2[i], y[i], pc1[i]));
   } else {  // OP_DY_SPARSE: pt = cloud of the row, cb = point index inside the cloud
     float y[8], dg[8];
     ld8(A.y + row * A.ldy + kg * 8, y);
@@ -219,7 +228,9 @@ __device__ __forceinline__ void load_consts(const Operand& A, int kg, int K, flo
     const int c = kg * 8 + i;
     pc0[i] = 0.f; pc1[i] = 0.f; pc2[i] = 0.f;
     if (AMODE == OP_BNRELU && c < K) { pc0[i] = A.sc[c]; pc1[i] = A.sh[c]; }
-    if ((AMODE == OP_DY || AMODE == OP_DY_SPARSE) && A.c1 && c < K) { pc0[i] = A.c1[c]; pc1[i] = A.c2[c]; pc2[i] = A.c3[c]; }
+    if ((AMODE == OP_DY || AMODE == OP_DY_SPARSE || AMODE == OP_DY_MAXK) && A.c1 && c < K) {
+      pc0[i] = A.c1[c]; pc1[i] = A.c2[c]; pc2[i] = A.c3[c];
+    }
   }
 }
 
@@ -245,6 +256,9 @@ __device__ __forceinline__ void fetch_chunk(const Operand& A, long long row, int
   } else if (AMODE == OP_DY) {
     ld8(A.p + row * A.ld + kg * 8, w.a);
     if (A.c1) ld8(A.y + row * A.ldy + kg * 8, w.b);
+  } else if (AMODE == OP_DY_MAXK) {
+    ld8(A.p + pt * A.ld + kg * 8, w.a);            // pooled maximum of the row's point
+    ld8(A.y + row * A.ldy + kg * 8, w.b);
   } else {  // OP_DY_SPARSE
     ld8(A.y + row * A.ldy + kg * 8, w.b);
   }
@@ -279,6 +293,14 @@ __device__ __forceinline__ void finish_chunk(const Operand& A, long long row, in
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = w.a[i];
     }
+  } else if (AMODE == OP_DY_MAXK) {
+    float sh8[8], sc8[8], hh[8];
+    ld8(A.p + pt * A.ld + A.C + kg * 8, sh8);
+    ld8(A.sc + kg * 8, sc8);
+    ld8(A.sh + kg * 8, hh);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      v[i] = fmaf(pc0[i], maxk_grad(w.b[i], sc8[i], hh[i], w.a[i], sh8[i]), fmaf(pc2[i], w.b[i], pc1[i]));
   } else {  // OP_DY_SPARSE: pt = cloud, cb = point inside the cloud
     float dg[8];
     ld8(A.dg + pt * A.C + kg * 8, dg);
@@ -397,14 +419,14 @@ rowgemm_tc_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, 
   // shared memory for 8 channel groups) while the warps synthesise the A operand
   const uint32_t wblock_bytes = 2u * (uint32_t)k8c * (uint32_t)sp.b_group_bytes;
   const bool w_async = !resident_w && wimg != nullptr;
-  const uint64_t a_inv = (AMODE == OP_EDGE) ? rowmap_inv(A.k) : 0;
+  const uint64_t a_inv = (AMODE == OP_EDGE || AMODE == OP_DY_MAXK) ? rowmap_inv(A.k) : 0;
   const uint64_t e_inv = (EMODE == EPI_EDGE_SCATTER) ? rowmap_inv(E.k) : 0;
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     const long long row0 = (long long)tile * TILE_M;
     uint32_t accum = 0;
     RowMap arm, erm;
     CloudMap acm;
-    if (AMODE == OP_EDGE) arm = rowmap_tile(row0, A.k, A.npts, a_inv);
+    if (AMODE == OP_EDGE || AMODE == OP_DY_MAXK) arm = rowmap_tile(row0, A.k, A.npts, a_inv);
     if (AMODE == OP_DY_SPARSE) acm = cloudmap_tile(row0, A.npts);
     if (EMODE == EPI_EDGE_SCATTER) erm = rowmap_tile(row0, E.k, E.npts, e_inv);
 
@@ -429,7 +451,7 @@ rowgemm_tc_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, 
         const long long row = row0 + r;
         float v[8];
         long long pt = 0, cb = 0;
-        if (AMODE == OP_EDGE) rowmap_point(arm, r, pt, cb);
+        if (AMODE == OP_EDGE || AMODE == OP_DY_MAXK) rowmap_point(arm, r, pt, cb);
         if (AMODE == OP_DY_SPARSE) cloudmap_point(acm, r, pt, cb);
         load_chunk<AMODE>(A, row, cg, row < M && kvalid, pc0, pc1, pc2, v, generic != 0, pt, cb);
         uint4 hi, lo;
@@ -688,6 +710,9 @@ bool tc_operand_fast(const Operand& A, int amode, int K) {
   if (K % 8 != 0) return false;
   if (amode == OP_DY_SPARSE)
     return A.c1 && aligned16(A.y) && (A.ldy % 4) == 0 && aligned16(A.dg) && aligned16(A.amax) && (A.C % 8) == 0 && A.npts >= 1;
+  if (amode == OP_DY_MAXK)
+    return A.c1 && aligned16(A.y) && (A.ldy % 4) == 0 && aligned16(A.p) && (A.ld % 4) == 0 && (A.C % 8) == 0 &&
+           aligned16(A.sc) && aligned16(A.sh);
   if (!aligned16(A.p) || (A.ld % 4) != 0) return false;
   if (amode == OP_EDGE && (A.C / 2) % 8 != 0) return false;
   if (amode == OP_DY && A.c1 && (!aligned16(A.y) || (A.ldy % 4) != 0)) return false;
@@ -697,7 +722,7 @@ bool tc_operand_fast(const Operand& A, int amode, int K) {
 
 bool tc_supported(const Operand& A, int amode, const float* Bm, long long M, int N, int K, const Epilogue& E, int emode) {
   if (K < 12) return false;
-  if (amode == OP_EDGE && (A.k < 1 || A.k > 32768 || A.npts < 1)) return false;          // RowMap range
+  if ((amode == OP_EDGE || amode == OP_DY_MAXK) && (A.k < 1 || A.k > 32768 || A.npts < 1)) return false;   // RowMap range
   if (emode == EPI_EDGE_SCATTER && (E.k < 1 || E.k > 32768 || E.npts < 1)) return false;
   if (N % 4 != 0 || N < 16) return false;
   const TcPlan pl = tc_plan(N, K);
@@ -804,12 +829,14 @@ colgemm_tc_kernel(const Operand A, const Operand G, long long M, long long rows_
   uint32_t phase = 0, accum = 0;
   bool pending = false;
   const uint64_t a_inv = (AMODE == OP_EDGE) ? rowmap_inv(A.k) : 0;
+  const uint64_t g_inv = (GMODE == OP_DY_MAXK) ? rowmap_inv(G.k) : 0;
   for (long long rb = r_begin; rb < r_end; rb += TILE_M) {
     if (pending) { mbar_wait(mma_bar, phase); phase ^= 1; pending = false; }   // MMAs done reading smem
-    RowMap arm;
+    RowMap arm, grm;
     CloudMap gcm;
     if (AMODE == OP_EDGE) arm = rowmap_tile(rb, A.k, A.npts, a_inv);
     if (GMODE == OP_DY_SPARSE) gcm = cloudmap_tile(rb, G.npts);
+    if (GMODE == OP_DY_MAXK) grm = rowmap_tile(rb, G.k, G.npts, g_inv);
     // A operand: 8 chunks per thread in batches of UB, all loads of a batch in flight before the first use
     constexpr int UB = 4;
     if (!genA) {
@@ -865,6 +892,7 @@ colgemm_tc_kernel(const Operand A, const Operand G, long long M, long long rows_
           ok[u] = vG && r < TILE_M && rb + r < r_end;
           pt[u] = 0; cb[u] = 0;
           if (GMODE == OP_DY_SPARSE) cloudmap_point(gcm, r, pt[u], cb[u]);
+          if (GMODE == OP_DY_MAXK && r < TILE_M) rowmap_point(grm, r, pt[u], cb[u]);
         }
         RawChunk w[UB];
 #pragma unroll
@@ -956,9 +984,10 @@ colgemm_tc_kernel(const Operand A, const Operand G, long long M, long long rows_
 
 bool wgrad_tc_supported(const Operand& A, int amode, const Operand& G, int gmode) {
   if (amode != OP_PLAIN && amode != OP_BNRELU && amode != OP_EDGE) return false;
-  if (gmode != OP_DY && gmode != OP_DY_SPARSE) return false;
+  if (gmode != OP_DY && gmode != OP_DY_SPARSE && gmode != OP_DY_MAXK) return false;
   if (A.C < 12 || G.C < 12) return false;
   if (amode == OP_EDGE && (A.k < 1 || A.k > 32768 || A.npts < 1)) return false;          // RowMap range
+  if (gmode == OP_DY_MAXK && (G.k < 1 || G.k > 32768 || G.npts < 1)) return false;
   return true;
 }
 
@@ -1006,6 +1035,7 @@ int wgrad_tc_dispatch(const Operand& A, int amode, const Operand& G, int gmode, 
 #define WSPC_WG(AM, GM) \
   if (amode == AM && gmode == GM) rc = launch_wgrad_tc<AM, GM>(A, G, M, S, K1p, K2p, partial, partial_b, st);
   WSPC_WG(OP_PLAIN, OP_DY) WSPC_WG(OP_BNRELU, OP_DY) WSPC_WG(OP_EDGE, OP_DY) WSPC_WG(OP_PLAIN, OP_DY_SPARSE)
+  WSPC_WG(OP_BNRELU, OP_DY_MAXK)
 #undef WSPC_WG
   if (rc == -100) return 0;
   return rc == WSPC_OK ? 1 : rc;
@@ -1028,6 +1058,7 @@ int rowgemm_tc_dispatch(const Operand& A, int amode, const float* Bm, long long 
   WSPC_TC(OP_EDGE, EPI_STORE) WSPC_TC(OP_EDGE, EPI_STORE_STATS)
   WSPC_TC(OP_DY, EPI_STORE) WSPC_TC(OP_DY, EPI_RELUMASK_STATS) WSPC_TC(OP_DY, EPI_EDGE_SCATTER) WSPC_TC(OP_DY, EPI_ACCUM)
   WSPC_TC(OP_DY_SPARSE, EPI_STORE) WSPC_TC(OP_DY_SPARSE, EPI_ACCUM)
+  WSPC_TC(OP_DY_MAXK, EPI_RELUMASK_STATS)
 #undef WSPC_TC
   if (rc == -100) return 0;
   return rc == WSPC_OK ? 1 : rc;

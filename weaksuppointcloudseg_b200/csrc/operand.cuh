@@ -10,13 +10,19 @@
 //   OP_EDGE       [x_i | x_j - x_i] for row = (point i, neighbour slot r)
 //   OP_DY         c1[c]*G[row,c] + c2[c] + c3[c]*y[row,c]   (BN backward folded to an affine map)
 //   OP_DY_SPARSE  same, with G given as the per-cloud arg-max scatter of max_pool2d's gradient
+//   OP_DY_MAXK    same, with G synthesised from the max over k: G = (relu(bn(y)) == max) ? dout / #ties : 0
 #pragma once
 #include "common.cuh"
 
 namespace wspc {
 
 enum OpMode : int { OP_PLAIN = WSPC_OP_PLAIN, OP_BNRELU = WSPC_OP_BNRELU, OP_EDGE = WSPC_OP_EDGE, OP_DY = WSPC_OP_DY,
-                    OP_DY_SPARSE = WSPC_OP_DY_SPARSE };
+                    OP_DY_SPARSE = WSPC_OP_DY_SPARSE, OP_DY_MAXK = WSPC_OP_DY_MAXK };
+
+// gradient of tf.reduce_max over k at one element: a = relu(y*sc+sh) is the activation, m the pooled maximum, share = dout/#ties
+__device__ __forceinline__ float maxk_grad(float y, float sc, float sh, float m, float share) {
+  return (m > 0.f && fmaxf(fmaf(y, sc, sh), 0.f) == m) ? share : 0.f;
+}
 
 using Operand = wspc_operand_t;   // declared in include/wspc.h
 
@@ -68,6 +74,20 @@ __device__ __forceinline__ void load8(const Operand& o, long long row, int c0, f
       const int c = c0 + i;
       float t = 0.f;
       if (c < o.C) t = o.c1 ? fmaf(o.c1[c], g[c], fmaf(o.c3[c], y[c], o.c2[c])) : g[c];
+      v[i] = t;
+    }
+  } else if (MODE == OP_DY_MAXK) {
+    const long long pt = row / o.k;
+    const float* y = o.y + row * o.ldy;
+    const float* ms = o.p + pt * o.ld;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = c0 + i;
+      float t = 0.f;
+      if (c < o.C) {
+        const float g = maxk_grad(y[c], o.sc[c], o.sh[c], ms[c], ms[o.C + c]);
+        t = fmaf(o.c1[c], g, fmaf(o.c3[c], y[c], o.c2[c]));
+      }
       v[i] = t;
     }
   } else {  // OP_DY_SPARSE

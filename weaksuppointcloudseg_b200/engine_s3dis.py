@@ -63,6 +63,7 @@ class S3DISEngine:
         self.seed = 1234
         # first conv2d of each EdgeConv block: factored (csrc/edge.cu) unless WSPC_EDGE=gemm asks for the gathered GEMM
         self.es = rt.EdgeSplit(P, self.dev) if rt.EDGE_FACTORED else None
+        self.MS = torch.empty((P, 128), **f32) if rt.MAXK_SYNTH else None     # [pooled max | dout / #ties] per point
         self.pc7 = rt.PoolConv(self.layers["adj_conv7"], self.dev) if rt.POOLCONV_GRAM else None
         self.prof = None   # optional list of (tag, start_event, end_event) filled around the kNN launches
 
@@ -217,21 +218,33 @@ class S3DISEngine:
             rt.wgrad(rt.op_plain(self.cat, 192, 192), G7, P, c7.dW, c7.db, dev)
             rt.rows_gemm(G7, c7.W, 1024, 1, P, 192, 1024, L.Epilogue(out=dcat_a, ldo=192), L.EPI_ACCUM)
         # block 3
-        rt.maxk_bwd(c5, self.y[4], P, k, cat_a + 4 * 128, 192, dcat_a + 4 * 128, 192, self.Ga)
-        rt.bn_bwd_coeffs(c5, R)
-        if self.es is not None:
-            rt.edge_first_backward(self.es, c5, cat_a + 4 * 64, 192, 64, self.idx[2], k, N, P, self.Ga, self.y[4],
-                                   dcat_a + 4 * 64, 192)
+        synth = self.MS is not None
+        if synth and self.es is not None:
+            rt.maxk_bwd_stats(c5, self.y[4], P, k, cat_a + 4 * 128, 192, dcat_a + 4 * 128, 192, self.MS)
+            rt.bn_bwd_coeffs(c5, R)
+            rt.edge_first_backward(self.es, c5, cat_a + 4 * 64, 192, 64, self.idx[2], k, N, P, None, self.y[4],
+                                   dcat_a + 4 * 64, 192, MS=self.MS)
         else:
-            G5 = rt.op_dy(self.Ga, 64, self.y[4], 64, c5, 64)
-            A5 = L.Operand(p=cat_a + 4 * 64, ld=192, C=128, idx=L.dptr(self.idx[2]), k=k, npts=N), L.OP_EDGE
-            rt.wgrad(A5, G5, R, c5.dW, c5.db, dev)
-            e, m = rt.epi_scatter(dcat_a + 4 * 64, 192, self.idx[2], k, N)
-            rt.rows_gemm(G5, c5.W, 64, 1, R, 128, 64, e, m)
+            rt.maxk_bwd(c5, self.y[4], P, k, cat_a + 4 * 128, 192, dcat_a + 4 * 128, 192, self.Ga)
+            rt.bn_bwd_coeffs(c5, R)
+            if self.es is not None:
+                rt.edge_first_backward(self.es, c5, cat_a + 4 * 64, 192, 64, self.idx[2], k, N, P, self.Ga, self.y[4],
+                                       dcat_a + 4 * 64, 192)
+            else:
+                G5 = rt.op_dy(self.Ga, 64, self.y[4], 64, c5, 64)
+                A5 = L.Operand(p=cat_a + 4 * 64, ld=192, C=128, idx=L.dptr(self.idx[2]), k=k, npts=N), L.OP_EDGE
+                rt.wgrad(A5, G5, R, c5.dW, c5.db, dev)
+                e, m = rt.epi_scatter(dcat_a + 4 * 64, 192, self.idx[2], k, N)
+                rt.rows_gemm(G5, c5.W, 64, 1, R, 128, 64, e, m)
         # block 2
-        rt.maxk_bwd(c4, self.y[3], P, k, cat_a + 4 * 64, 192, dcat_a + 4 * 64, 192, self.Ga)
-        rt.bn_bwd_coeffs(c4, R)
-        G4 = rt.op_dy(self.Ga, 64, self.y[3], 64, c4, 64)
+        if synth:
+            rt.maxk_bwd_stats(c4, self.y[3], P, k, cat_a + 4 * 64, 192, dcat_a + 4 * 64, 192, self.MS)
+            rt.bn_bwd_coeffs(c4, R)
+            G4 = rt.op_dy_maxk(c4, self.y[3], self.MS, k, N)
+        else:
+            rt.maxk_bwd(c4, self.y[3], P, k, cat_a + 4 * 64, 192, dcat_a + 4 * 64, 192, self.Ga)
+            rt.bn_bwd_coeffs(c4, R)
+            G4 = rt.op_dy(self.Ga, 64, self.y[3], 64, c4, 64)
         rt.wgrad(rt.op_bnrelu(self.y[2], c3), G4, R, c4.dW, c4.db, dev)
         e, m = rt.epi_relumask(self.Gb, c3, self.y[2])
         rt.rows_gemm(G4, c4.W, 64, 1, R, 64, 64, e, m)
@@ -244,9 +257,14 @@ class S3DISEngine:
             e, m = rt.epi_scatter(dcat_a, 192, self.idx[1], k, N)
             rt.rows_gemm(G3e, c3.W, 64, 1, R, 128, 64, e, m)
         # block 1 (no gradient w.r.t. the input cloud)
-        rt.maxk_bwd(c2, self.y[1], P, k, cat_a, 192, dcat_a, 192, self.Ga)
-        rt.bn_bwd_coeffs(c2, R)
-        G2e = rt.op_dy(self.Ga, 64, self.y[1], 64, c2, 64)
+        if synth:
+            rt.maxk_bwd_stats(c2, self.y[1], P, k, cat_a, 192, dcat_a, 192, self.MS)
+            rt.bn_bwd_coeffs(c2, R)
+            G2e = rt.op_dy_maxk(c2, self.y[1], self.MS, k, N)
+        else:
+            rt.maxk_bwd(c2, self.y[1], P, k, cat_a, 192, dcat_a, 192, self.Ga)
+            rt.bn_bwd_coeffs(c2, R)
+            G2e = rt.op_dy(self.Ga, 64, self.y[1], 64, c2, 64)
         rt.wgrad(rt.op_bnrelu(self.y[0], c1), G2e, R, c2.dW, c2.db, dev)
         e, m = rt.epi_relumask(self.Gb, c1, self.y[0])
         rt.rows_gemm(G2e, c2.W, 64, 1, R, 64, 64, e, m)

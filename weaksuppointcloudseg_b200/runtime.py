@@ -213,6 +213,28 @@ def maxk_fwd(layer: Layer, y, P, k, out_addr, ldo):
                                          ctypes.c_void_p(out_addr), ldo, L.stream()))
 
 
+# Gradient of the max over k: by default the (P*k, C) tensor G is materialised (wspc_maxk_bnrelu_bwd).  WSPC_MAXK=synth
+# keeps statistics only and lets the consumers synthesise G on load (WSPC_OP_DY_MAXK / wspc_edge_combine_bwd_maxk): 8 GB less
+# HBM traffic per step at cfg-3 but more loader work -- measured equal (46.7 vs 46.5 ms), so it stays an option
+# (tests/test_maxk_synth_gpu.py holds the two paths together).
+MAXK_SYNTH = os.environ.get("WSPC_MAXK", "materialise") == "synth"
+
+
+def maxk_bwd_stats(layer: Layer, y, P, k, out_addr, ldo, dout_addr, lddo, MS):
+    """tf.reduce_max(axis=-2) backward without materialising G: MS (P, 2C) = [pooled max | dout / #ties] + BN sums."""
+    zero_(layer.bstats)
+    L.check(L.lib().wspc_maxk_bnrelu_bwd_stats(L.ptr(y), L.ptr(layer.sc), L.ptr(layer.sh), ctypes.c_void_p(out_addr), ldo,
+                                               ctypes.c_void_p(dout_addr), lddo, P, k, layer.cout, L.ptr(MS),
+                                               L.ptr(layer.bstats), L.stream()))
+
+
+def op_dy_maxk(layer: Layer, y, MS, k, npts):
+    """gradient w.r.t. the layer's pre-BN output when its activation feeds a max over k (after bn_bwd_coeffs)."""
+    C = layer.cout
+    return (L.Operand(p=L.dptr(MS), ld=2 * C, C=C, sc=L.dptr(layer.sc), sh=L.dptr(layer.sh), k=k, npts=npts, y=L.dptr(y), ldy=C,
+                      c1=L.dptr(layer.c1), c2=L.dptr(layer.c2), c3=L.dptr(layer.c3)), L.OP_DY_MAXK)
+
+
 def maxk_bwd(layer: Layer, y, P, k, out_addr, ldo, dout_addr, lddo, G):
     zero_(layer.bstats)
     L.check(L.lib().wspc_maxk_bnrelu_bwd(L.ptr(y), L.ptr(layer.sc), L.ptr(layer.sh), ctypes.c_void_p(out_addr), ldo,
@@ -264,16 +286,22 @@ def edge_first_forward(es: EdgeSplit, layer: Layer, x, ld, cx, idx, k, npts, P, 
         bn_finalize(layer, P * k, training, decay)
 
 
-def edge_first_backward(es: EdgeSplit, layer: Layer, x, ld, cx, idx, k, npts, P, G, y, dx_addr=None, lddx=0):
+def edge_first_backward(es: EdgeSplit, layer: Layer, x, ld, cx, idx, k, npts, P, G, y, dx_addr=None, lddx=0, MS=None):
     """Gradients of the factored layer: layer.dW / layer.db, and (if dx_addr) dX accumulated into (P, lddx) at dx_addr.
-    G is the gradient w.r.t. the BN output (bn_bwd_coeffs(layer, P*k) must have run), y the saved pre-BN output."""
+    G is the gradient w.r.t. the BN output (bn_bwd_coeffs(layer, P*k) must have run), y the saved pre-BN output;
+    with MS (from maxk_bwd_stats) G is None and synthesised from the max over k."""
     xa = x if isinstance(x, int) else x.data_ptr()
     Wc = es.Wc[layer.scope]
     zero_(es.DUV)
     bn = layer.has_bn
-    L.check(L.lib().wspc_edge_combine_bwd(L.ptr(G), L.ptr(y) if bn else None, L.ptr(layer.c1) if bn else None,
-                                          L.ptr(layer.c2) if bn else None, L.ptr(layer.c3) if bn else None, L.ptr(idx), P, k,
-                                          npts, 64, L.ptr(es.DUV), 128, L.stream()))
+    if MS is not None:
+        L.check(L.lib().wspc_edge_combine_bwd_maxk(L.ptr(y), L.ptr(layer.c1), L.ptr(layer.c2), L.ptr(layer.c3), L.ptr(layer.sc),
+                                                   L.ptr(layer.sh), L.ptr(MS), L.ptr(idx), P, k, npts, 64, L.ptr(es.DUV), 128,
+                                                   L.stream()))
+    else:
+        L.check(L.lib().wspc_edge_combine_bwd(L.ptr(G), L.ptr(y) if bn else None, L.ptr(layer.c1) if bn else None,
+                                              L.ptr(layer.c2) if bn else None, L.ptr(layer.c3) if bn else None, L.ptr(idx), P,
+                                              k, npts, 64, L.ptr(es.DUV), 128, L.stream()))
     D = (L.Operand(p=L.dptr(es.DUV), ld=128, C=128), L.OP_DY)
     A = (L.Operand(p=xa, ld=ld, C=cx), L.OP_PLAIN)
     wgrad(A, D, P, es.dWc, es.dbc, es.UV.device)
