@@ -103,8 +103,15 @@ class S3DIS_Trainer():
         return True
 
     # ------------------------------------------------------------------ one sess.run -------------
-    def _to_device(self, name, arr):
-        """feed_dict H2D: host arrays go through a persistent pinned staging buffer."""
+    def _copy_stream(self):
+        """side stream for the feed/fetch copies that are not on the critical path (labels in, probabilities out)"""
+        if getattr(self, '_cstream', None) is None:
+            self._cstream = torch.cuda.Stream(device=self.device)
+        return self._cstream
+
+    def _to_device(self, name, arr, side=False):
+        """feed_dict H2D: host arrays go through a persistent pinned staging buffer.  side=True issues the copy on the
+        copy stream (overlapping the forward pass); the caller makes the compute stream wait before the first use."""
         if torch.is_tensor(arr) and arr.is_cuda:
             return arr.contiguous()
         t = torch.as_tensor(arr)
@@ -118,7 +125,13 @@ class S3DIS_Trainer():
         if not (t.is_pinned() and t.is_contiguous()):
             stage[0].copy_(t)
             t = stage[0]
-        stage[1].copy_(t, non_blocking=True)
+        if side:
+            cs = self._copy_stream()
+            cs.wait_stream(torch.cuda.current_stream())      # the previous step's readers of this buffer are done
+            with torch.cuda.stream(cs):
+                stage[1].copy_(t, non_blocking=True)
+        else:
+            stage[1].copy_(t, non_blocking=True)
         return stage[1]
 
     def train_batch(self, data_feed, seg_onehot_feed, Mask_bin_feed, fetch_prob=True, dropout_mask=None):
@@ -126,11 +139,12 @@ class S3DIS_Trainer():
         Is_Training_ph=True (:317-323).  Returns (loss, loss_siamese, loss_inexact, loss_smooth, Z_prob)."""
         eng = self.engine
         X = self._to_device('X', data_feed)
-        Y = self._to_device('Y', seg_onehot_feed)
-        M = self._to_device('Mask', Mask_bin_feed)
+        Y = self._to_device('Y', seg_onehot_feed, side=True)       # only the loss block reads the labels: the 27 MB copy
+        M = self._to_device('Mask', Mask_bin_feed, side=True)      # overlaps the forward pass
         lr, decay = self.get_learning_rate(), self.get_bn_decay()
         full = self.style == 'Full'
         eng.forward(X, True, decay, dropout_mask)
+        torch.cuda.current_stream().wait_stream(self._copy_stream())
         if full and not self.weak_gate:
             # Full graph, gate closed: the weak terms are evaluated (and printed) but multiplied by 0 (:100-102)
             eng.losses_and_grad(Y, M, full=True, want_grad=False)
@@ -139,10 +153,12 @@ class S3DIS_Trainer():
         else:
             weak = None
             eng.losses_and_grad(Y, M, full=full, want_grad=True)
+        zp = self._fetch_prob(side=True) if fetch_prob else None    # D2H of Z_prob overlaps the backward pass
         eng.backward()
         self._allreduce_and_step(lr)
-        zp = self._fetch_prob() if fetch_prob else None
         l = self._fetch_losses()          # synchronises the stream: the step is complete on return
+        if fetch_prob:
+            self._copy_stream().synchronize()
         if weak is not None:
             return float(l[0]), float(weak[1]), float(weak[2]), float(weak[3]), zp
         return float(l[4]), float(l[1]), float(l[2]), float(l[3]), zp
@@ -156,11 +172,17 @@ class S3DIS_Trainer():
         torch.cuda.current_stream().synchronize()
         return h.numpy().copy()
 
-    def _fetch_prob(self):
+    def _fetch_prob(self, side=False):
         eng = self.engine
         if 'Zp' not in self.pinned:
             self.pinned['Zp'] = torch.empty(tuple(eng.Zp.shape), dtype=torch.float32, pin_memory=True)
-        self.pinned['Zp'].copy_(eng.Zp, non_blocking=True)
+        if side:      # Z_prob is final once the loss block has run; nothing in the backward pass writes it
+            cs = self._copy_stream()
+            cs.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(cs):
+                self.pinned['Zp'].copy_(eng.Zp, non_blocking=True)
+        else:
+            self.pinned['Zp'].copy_(eng.Zp, non_blocking=True)
         return self.pinned['Zp'].numpy()
 
     def _allreduce_and_step(self, lr):
