@@ -158,3 +158,30 @@ def test_siamese_zero_for_identical_pairs(setup, cuda):
     l = eng.losses_and_grad(Y, M, full=True, want_grad=True).cpu().numpy()
     assert l[1] == 0.0
     assert l[3] >= 0.0
+
+
+def test_cfg4_stress_shape_properties(cuda):
+    """BASELINE cfg-4 (N=8192, k=40; one Siamese pair): size-independent properties of a full train step --
+    neighbour lists sorted / self-inclusive / duplicate-free, finite losses, Siamese term > 0, every gradient finite,
+    and the weights move.  (k=40 exercises the two-slot CUDA-core kNN and the generic k of every edge kernel.)"""
+    from weaksuppointcloudseg_b200.engine_s3dis import S3DISEngine
+    from weaksuppointcloudseg_b200 import ops
+    N, k = 8192, 40
+    X, Y, M, _ = syn.s3dis_batch(1, N=N, n_labelled=81, seed=44, dup_frac=0.0)
+    eng = S3DISEngine(od.init_params(od.S3DIS_LAYERS, seed=3), 2, N, device=cuda, k=k)
+    Xd, Yd, Md = (torch.from_numpy(a).to(cuda) for a in (X, Y, M))
+    before = eng.vs.theta.clone()
+    losses = eng.train_step(Xd, Yd, Md, lr=1e-3, bn_decay=0.5).cpu().numpy()
+    torch.cuda.synchronize()
+    assert np.isfinite(losses).all() and losses[1] > 0 and losses[4] > 0
+    idx = eng.idx[0]
+    _, dist = ops.knn_fused(Xd, k, ops.DIST_TFUTIL, coff=6, D=3, return_dist=True)
+    assert bool((dist[..., 1:] >= dist[..., :-1]).all())
+    # with the reference's formula (sq_i - 2 x_i.x_j) + sq_j a close neighbour can come out at a slightly negative
+    # distance and precede the point itself (d_ii == 0 exactly), so only self-INCLUSION is a property of the lists
+    me = torch.arange(N, device=cuda, dtype=torch.int32).view(1, N, 1)
+    assert float((idx == me).any(-1).float().mean()) >= 0.999
+    s = torch.sort(idx, dim=-1).values
+    assert bool((s[..., 1:] != s[..., :-1]).all())
+    assert bool(torch.isfinite(eng.vs.grad).all())
+    assert float((eng.vs.theta - before).abs().max()) > 0
