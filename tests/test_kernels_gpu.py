@@ -292,3 +292,49 @@ def test_rows_gemm_chunked_shapes(cuda, gemm_path, K, N, kind):
         Gd.scatter_(1, amax.long().unsqueeze(1), dg.double().unsqueeze(1))
         dy = c1.double() * Gd.reshape(M, K) + c2.double() + c3.double() * y.double()
         assert rel(out, out0 + dy @ Wl.double().T) <= _tol(gemm_path)
+
+
+# ---- narrow heads (seg/conv3 of the S3DIS net: 256 -> 13, DGCNN_S3DIS.py:100-101) ------------------------------------
+@pytest.mark.parametrize("K,N,dropout", [(256, 13, True), (128, 16, False), (64, 9, False)])
+def test_narrow_head_forward(cuda, gemm_path, K, N, dropout):
+    """warp-per-row kernel (auto path) / generic CUDA-core kernel: relu(bn(y)) (* dropout) @ W + b for N <= 16."""
+    from weaksuppointcloudseg_b200 import _lib as L, runtime as rt
+    g = torch.Generator(device="cuda").manual_seed(7)
+    M = 1000 + 37
+    y = torch.randn((M, K), device=cuda, generator=g)
+    sc = torch.rand(K, device=cuda, generator=g) + 0.5
+    sh = torch.randn(K, device=cuda, generator=g) * 0.2
+    W = torch.randn((K, N), device=cuda, generator=g) * 0.2
+    b = torch.randn(N, device=cuda, generator=g)
+    mask = (torch.rand((M, K), device=cuda, generator=g) < 0.7).float() if dropout else None
+    out = torch.empty((M, N), device=cuda)
+    A = (L.Operand(p=y.data_ptr(), ld=K, C=K, sc=sc.data_ptr(), sh=sh.data_ptr(), dmask=L.dptr(mask), dscale=1.0 / 0.7), L.OP_BNRELU)
+    rt.rows_gemm(A, W, N, 0, M, N, K, L.Epilogue(out=out.data_ptr(), ldo=N, bias=b.data_ptr()), L.EPI_STORE)
+    a = torch.relu(y.double() * sc.double() + sh.double())
+    if dropout:
+        a = a * mask.double() / 0.7
+    assert rel(out, a @ W.double() + b.double()) <= 2e-5
+
+
+def test_narrow_head_data_gradient(cuda, gemm_path):
+    """dA (M,256) = dZ (M,13) W^T with the ReLU mask / dropout of the producing layer and its BN-backward sums."""
+    from weaksuppointcloudseg_b200 import _lib as L, runtime as rt
+    g = torch.Generator(device="cuda").manual_seed(8)
+    M, K, N = 777, 13, 256
+    dZ = torch.randn((M, K), device=cuda, generator=g)
+    W = torch.randn((N, K), device=cuda, generator=g) * 0.2           # the layer's own (256, 13) weight, used transposed
+    yprev = torch.randn((M, N), device=cuda, generator=g)
+    sc = torch.rand(N, device=cuda, generator=g) + 0.5
+    sh = torch.randn(N, device=cuda, generator=g) * 0.2
+    mask = (torch.rand((M, N), device=cuda, generator=g) < 0.7).float()
+    out = torch.empty((M, N), device=cuda)
+    stats = torch.zeros((2, N), dtype=torch.float64, device=cuda)
+    A = (L.Operand(p=dZ.data_ptr(), ld=K, C=K), L.OP_DY)
+    epi = L.Epilogue(out=out.data_ptr(), ldo=N, stats=stats.data_ptr(), yprev=yprev.data_ptr(), ldyp=N, scp=sc.data_ptr(),
+                     shp=sh.data_ptr(), dmask=mask.data_ptr(), dscale=1.0 / 0.7)
+    rt.rows_gemm(A, W, K, 1, M, N, K, epi, L.EPI_RELUMASK_STATS)
+    on = (yprev.double() * sc.double() + sh.double()) > 0
+    ref = (dZ.double() @ W.double().t()) * on * mask.double() / 0.7
+    assert rel(out, ref) <= 2e-5
+    assert rel(stats[0], ref.sum(0)) <= 1e-5
+    assert rel(stats[1], (ref * yprev.double()).sum(0)) <= 1e-5
