@@ -446,18 +446,54 @@ rowgemm_tc_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, 
         }
         load_consts<AMODE>(A, cg, K, pc0, pc1, pc2);
       }
+      if ((AMODE == OP_PLAIN || AMODE == OP_BNRELU) && !generic) {
+        // batches of UB rows: all global loads of a batch are in flight before the first use (the kernel is
+        // latency-bound on these loads: 16 resident warps per SM).  Measured: forward layers 18.8 -> 17.9 ms per
+        // step; the gradient operands (two loads per row already) lose 1 ms with the same batching, so they keep
+        // the plain loop below.
+        constexpr int UB = 4;
+#pragma unroll 1
+        for (int rbase = r0; rbase < TILE_M; rbase += rstep * UB) {
+          long long pt[UB], cb[UB];
+          bool ok[UB];
+          RawChunk w[UB];
+#pragma unroll
+          for (int u = 0; u < UB; ++u) {
+            const int r = rbase + rstep * u;
+            ok[u] = r < TILE_M && row0 + r < M && kvalid;
+            pt[u] = 0; cb[u] = 0;
+            if (AMODE == OP_DY_MAXK && r < TILE_M) rowmap_point(arm, r, pt[u], cb[u]);
+            if (AMODE == OP_DY_SPARSE && r < TILE_M) cloudmap_point(acm, r, pt[u], cb[u]);
+          }
+#pragma unroll
+          for (int u = 0; u < UB; ++u) fetch_chunk<AMODE>(A, row0 + rbase + rstep * u, cg, ok[u], pt[u], 0, w[u]);
+#pragma unroll
+          for (int u = 0; u < UB; ++u) {
+            const int r = rbase + rstep * u;
+            if (r < TILE_M) {
+              float v[8];
+              finish_chunk<AMODE>(A, row0 + r, cg, ok[u], pt[u], cb[u], pc0, pc1, pc2, w[u], v);
+              uint4 hi, lo;
+              split8(v, hi, lo);
+              *reinterpret_cast<uint4*>(sAhi + (size_t)kg * A_GROUP_BYTES + r * 16) = hi;
+              *reinterpret_cast<uint4*>(sAlo + (size_t)kg * A_GROUP_BYTES + r * 16) = lo;
+            }
+          }
+        }
+      } else {
 #pragma unroll 4
-      for (int r = r0; r < TILE_M; r += rstep) {
-        const long long row = row0 + r;
-        float v[8];
-        long long pt = 0, cb = 0;
-        if (AMODE == OP_EDGE || AMODE == OP_DY_MAXK) rowmap_point(arm, r, pt, cb);
-        if (AMODE == OP_DY_SPARSE) cloudmap_point(acm, r, pt, cb);
-        load_chunk<AMODE>(A, row, cg, row < M && kvalid, pc0, pc1, pc2, v, generic != 0, pt, cb);
-        uint4 hi, lo;
-        split8(v, hi, lo);
-        *reinterpret_cast<uint4*>(sAhi + (size_t)kg * A_GROUP_BYTES + r * 16) = hi;
-        *reinterpret_cast<uint4*>(sAlo + (size_t)kg * A_GROUP_BYTES + r * 16) = lo;
+        for (int r = r0; r < TILE_M; r += rstep) {
+          const long long row = row0 + r;
+          float v[8];
+          long long pt = 0, cb = 0;
+          if (AMODE == OP_EDGE || AMODE == OP_DY_MAXK) rowmap_point(arm, r, pt, cb);
+          if (AMODE == OP_DY_SPARSE) cloudmap_point(acm, r, pt, cb);
+          load_chunk<AMODE>(A, row, cg, row < M && kvalid, pc0, pc1, pc2, v, generic != 0, pt, cb);
+          uint4 hi, lo;
+          split8(v, hi, lo);
+          *reinterpret_cast<uint4*>(sAhi + (size_t)kg * A_GROUP_BYTES + r * 16) = hi;
+          *reinterpret_cast<uint4*>(sAlo + (size_t)kg * A_GROUP_BYTES + r * 16) = lo;
+        }
       }
       fence_proxy_async_smem();
       tc_fence_before();
