@@ -247,6 +247,13 @@ int wspc_head_losses(const float* Z, const float* Y, const float* Mask, const in
 int wspc_edge_split_weights(const float* W, int Cx, int Cout, float* Wc, wspc_stream_t stream);
 int wspc_edge_combine_fwd(const float* UV, long long ldu, const int32_t* idx, const float* bias, long long P, int k,
                           int npts, int Cout, float* y, double* stats, wspc_stream_t stream);
+/* as wspc_edge_combine_fwd, additionally writing MM (P, 2*Cout) = [max_r y | min_r y] over each point's k rows; when the
+ * layer's activation goes straight into tf.reduce_max over k (adj_conv5, DGCNN_S3DIS.py:66-78) wspc_maxk_from_extrema
+ * turns it into max_r relu(sc*y_r + sh) without re-reading y (bit-identical: fmaf(y, sc, sh) is monotone in y). */
+int wspc_edge_combine_fwd_extrema(const float* UV, long long ldu, const int32_t* idx, const float* bias, long long P, int k,
+                                  int npts, int Cout, float* y, double* stats, float* MM, wspc_stream_t stream);
+int wspc_maxk_from_extrema(const float* MM, const float* sc, const float* sh, long long P, int C, float* out, long long ldo,
+                           wspc_stream_t stream);
 int wspc_edge_combine_bwd(const float* G, const float* y, const float* c1, const float* c2, const float* c3,
                           const int32_t* idx, long long P, int k, int npts, int Cout, float* DUV, long long ldd,
                           wspc_stream_t stream);

@@ -164,6 +164,8 @@ _EXTRA_DECLS.update({
     "wspc_transform_points_bwd": (c_int, [_P, _P, c_int, c_int, _P, _P]),
     "wspc_edge_split_weights": (c_int, [_P, c_int, c_int, _P, _P]),
     "wspc_edge_combine_fwd": (c_int, [_P, c_longlong, _P, _P, c_longlong, c_int, c_int, c_int, _P, _P, _P]),
+    "wspc_edge_combine_fwd_extrema": (c_int, [_P, c_longlong, _P, _P, c_longlong, c_int, c_int, c_int, _P, _P, _P, _P]),
+    "wspc_maxk_from_extrema": (c_int, [_P, _P, _P, c_longlong, c_int, _P, c_longlong, _P]),
     "wspc_edge_combine_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_longlong, c_int, c_int, c_int, _P, c_longlong, _P]),
     "wspc_edge_merge_wgrad": (c_int, [_P, _P, c_int, c_int, _P, _P, _P]),
     "wspc_fill_rows": (c_int, [_P, c_longlong, _P, c_longlong, c_int, _P]),

@@ -50,7 +50,7 @@ __global__ void edge_merge_wgrad_kernel(const float* __restrict__ dWc, const flo
 __global__ void __launch_bounds__(256)
 edge_combine_fwd_kernel(const float* __restrict__ UV, long long ldu, const int32_t* __restrict__ idx,
                         const float* __restrict__ bias, long long P, int k, int npts, float* __restrict__ y,
-                        double* __restrict__ stats) {
+                        double* __restrict__ stats, float* __restrict__ MM) {
   __shared__ float red[2][CO];
   const int c4 = threadIdx.x & (C4 - 1), pl = threadIdx.x >> 4;
   const float4 b4 = bias ? *reinterpret_cast<const float4*>(bias + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -62,6 +62,7 @@ edge_combine_fwd_kernel(const float* __restrict__ UV, long long ldu, const int32
     u.x += b4.x; u.y += b4.y; u.z += b4.z; u.w += b4.w;
     const int32_t* ip = idx + i * k;
     float* yp = y + i * k * CO + c4 * 4;
+    float4 mx = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY), mn = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
     int j = 0;
     for (; j + 4 <= k; j += 4) {
       int nb[4];
@@ -75,6 +76,8 @@ edge_combine_fwd_kernel(const float* __restrict__ UV, long long ldu, const int32
         float4 o;
         o.x = u.x + v[t].x; o.y = u.y + v[t].y; o.z = u.z + v[t].z; o.w = u.w + v[t].w;
         __stcs(reinterpret_cast<float4*>(yp + (size_t)(j + t) * CO), o);
+        mx.x = fmaxf(mx.x, o.x); mx.y = fmaxf(mx.y, o.y); mx.z = fmaxf(mx.z, o.z); mx.w = fmaxf(mx.w, o.w);
+        mn.x = fminf(mn.x, o.x); mn.y = fminf(mn.y, o.y); mn.z = fminf(mn.z, o.z); mn.w = fminf(mn.w, o.w);
         s1.x += o.x; s1.y += o.y; s1.z += o.z; s1.w += o.w;
         s2.x = fmaf(o.x, o.x, s2.x); s2.y = fmaf(o.y, o.y, s2.y); s2.z = fmaf(o.z, o.z, s2.z); s2.w = fmaf(o.w, o.w, s2.w);
       }
@@ -84,8 +87,14 @@ edge_combine_fwd_kernel(const float* __restrict__ UV, long long ldu, const int32
       float4 o;
       o.x = u.x + v.x; o.y = u.y + v.y; o.z = u.z + v.z; o.w = u.w + v.w;
       __stcs(reinterpret_cast<float4*>(yp + (size_t)j * CO), o);
+      mx.x = fmaxf(mx.x, o.x); mx.y = fmaxf(mx.y, o.y); mx.z = fmaxf(mx.z, o.z); mx.w = fmaxf(mx.w, o.w);
+      mn.x = fminf(mn.x, o.x); mn.y = fminf(mn.y, o.y); mn.z = fminf(mn.z, o.z); mn.w = fminf(mn.w, o.w);
       s1.x += o.x; s1.y += o.y; s1.z += o.z; s1.w += o.w;
       s2.x = fmaf(o.x, o.x, s2.x); s2.y = fmaf(o.y, o.y, s2.y); s2.z = fmaf(o.z, o.z, s2.z); s2.w = fmaf(o.w, o.w, s2.w);
+    }
+    if (MM) {   // per-point max / min over the k rows of the pre-BN output: the max over k of relu(bn(.)) follows from them
+      *reinterpret_cast<float4*>(MM + i * 2 * CO + c4 * 4) = mx;
+      *reinterpret_cast<float4*>(MM + i * 2 * CO + CO + c4 * 4) = mn;
     }
   }
   if (!stats) return;
@@ -100,6 +109,19 @@ edge_combine_fwd_kernel(const float* __restrict__ UV, long long ldu, const int32
     atomicAdd(stats + threadIdx.x, (double)red[0][threadIdx.x]);
     atomicAdd(stats + CO + threadIdx.x, (double)red[1][threadIdx.x]);
   }
+}
+
+// out[p, c] = max_r relu(sc*y_r + sh) from the per-point extrema of y: fmaf(y, sc, sh) is monotone in y (rounding preserves
+// monotonicity), so the maximum is attained at max_r y (sc >= 0) or min_r y (sc < 0) -- bit-identical to maxk_fwd_kernel.
+__global__ void maxk_from_extrema_kernel(const float* __restrict__ MM, const float* __restrict__ sc, const float* __restrict__ sh,
+                                         long long P, float* __restrict__ out, long long ldo) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= P * CO) return;
+  const long long p = t / CO;
+  const int c = (int)(t - p * CO);
+  const float s = sc[c];
+  const float ye = s >= 0.f ? MM[p * 2 * CO + c] : MM[p * 2 * CO + CO + c];
+  out[p * ldo + c] = fmaxf(fmaf(ye, s, sh[c]), 0.f);
 }
 
 // dy = c1*G + c2 + c3*y (batch-norm backward folded to an affine map; c1 == NULL: dy = G);
@@ -204,6 +226,23 @@ extern "C" int wspc_edge_merge_wgrad(const float* dWc, const float* dbc, int Cx,
 
 extern "C" int wspc_edge_combine_fwd(const float* UV, long long ldu, const int32_t* idx, const float* bias, long long P,
                                      int k, int npts, int Cout, float* y, double* stats, wspc_stream_t stream) {
+  return wspc_edge_combine_fwd_extrema(UV, ldu, idx, bias, P, k, npts, Cout, y, stats, nullptr, stream);
+}
+
+extern "C" int wspc_maxk_from_extrema(const float* MM, const float* sc, const float* sh, long long P, int C, float* out,
+                                      long long ldo, wspc_stream_t stream) {
+  if (int rc = check_arch()) return rc;
+  WSPC_REQUIRE(MM && sc && sh && out && P >= 1 && C == CO && ldo >= C, "maxk_from_extrema: bad arguments (C must be %d)", CO);
+  maxk_from_extrema_kernel<<<(unsigned)((P * CO + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(MM, sc, sh, P, out,
+                                                                                                              ldo);
+  count_launch();
+  WSPC_LAUNCH_CHECK("maxk_from_extrema_kernel");
+  return WSPC_OK;
+}
+
+extern "C" int wspc_edge_combine_fwd_extrema(const float* UV, long long ldu, const int32_t* idx, const float* bias, long long P,
+                                             int k, int npts, int Cout, float* y, double* stats, float* MM,
+                                             wspc_stream_t stream) {
   if (int rc = check_arch()) return rc;
   WSPC_REQUIRE(UV && idx && y, "edge_combine_fwd: null pointer");
   WSPC_REQUIRE(Cout == CO && ldu >= 2 * CO && (ldu & 3) == 0, "edge_combine_fwd: Cout=%d ldu=%lld", Cout, ldu);
@@ -211,7 +250,8 @@ extern "C" int wspc_edge_combine_fwd(const float* UV, long long ldu, const int32
   WSPC_REQUIRE(aligned16(UV) && aligned16(y) && (!bias || aligned16(bias)), "edge_combine_fwd: pointers must be 16-byte aligned");
   const long long chunks = (P + 15) / 16;
   const unsigned grid = (unsigned)(chunks < 8LL * kNumSM ? chunks : 8LL * kNumSM);
-  edge_combine_fwd_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(UV, ldu, idx, bias, P, k, npts, y, stats);
+  WSPC_REQUIRE(!MM || aligned16(MM), "edge_combine_fwd: MM must be 16-byte aligned");
+  edge_combine_fwd_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(UV, ldu, idx, bias, P, k, npts, y, stats, MM);
   count_launch();
   WSPC_LAUNCH_CHECK("edge_combine_fwd_kernel");
   return WSPC_OK;

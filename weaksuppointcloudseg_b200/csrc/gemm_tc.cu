@@ -446,12 +446,12 @@ rowgemm_tc_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, 
         }
         load_consts<AMODE>(A, cg, K, pc0, pc1, pc2);
       }
-      if ((AMODE == OP_PLAIN || AMODE == OP_BNRELU) && !generic) {
+      if (AMODE != OP_EDGE && AMODE != OP_DY_MAXK && !generic) {
         // batches of UB rows: all global loads of a batch are in flight before the first use (the kernel is
         // latency-bound on these loads: 16 resident warps per SM).  Measured: forward layers 18.8 -> 17.9 ms per
         // step; the gradient operands (two loads per row already) lose 1 ms with the same batching, so they keep
         // the plain loop below.
-        constexpr int UB = 4;
+        constexpr int UB = (AMODE == OP_PLAIN || AMODE == OP_BNRELU) ? 4 : 2;   // gradient operands: two loads per row
 #pragma unroll 1
         for (int rbase = r0; rbase < TILE_M; rbase += rstep * UB) {
           long long pt[UB], cb[UB];

@@ -122,11 +122,11 @@ class S3DISEngine:
         knn_into(2, cat_a, 192, 64, 64)
         if self.es is not None:
             rt.edge_first_forward(self.es, Ly["adj_conv5"], cat_a + 4 * 64, 192, 64, self.idx[2], k, N, P, self.y[4],
-                                  is_training, bn_decay)
+                                  is_training, bn_decay, pool_out=cat_a + 4 * 128, pool_ld=192)
         else:
             e3 = L.Operand(p=cat_a + 4 * 64, ld=192, C=128, idx=L.dptr(self.idx[2]), k=k, npts=N), L.OP_EDGE
             rt.conv_forward(Ly["adj_conv5"], e3, R, self.y[4], 64, is_training, bn_decay)
-        rt.maxk_fwd(Ly["adj_conv5"], self.y[4], P, k, cat_a + 4 * 128, 192)
+            rt.maxk_fwd(Ly["adj_conv5"], self.y[4], P, k, cat_a + 4 * 128, 192)
         # adj_conv7 + max over points                                                   (:80-85)
         l7 = Ly["adj_conv7"]
         rt.conv_forward(l7, rt.op_plain(self.cat, 192, 192), P, self.y7, 1024, is_training, bn_decay)

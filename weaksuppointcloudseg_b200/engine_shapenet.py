@@ -138,11 +138,12 @@ class ShapeNetEngine:
         rt.maxk_fwd(Ly["adj_conv4"], self.y[3], P, k, cat_a + 4 * 64, 192)
         self._knn(3, cat_a, 192, 64, 64, ov, "knn3")
         if self.es is not None:
-            rt.edge_first_forward(self.es, Ly["adj_conv5"], cat_a + 4 * 64, 192, 64, self.idx[3], k, N, P, self.y[4], tr, d)
+            rt.edge_first_forward(self.es, Ly["adj_conv5"], cat_a + 4 * 64, 192, 64, self.idx[3], k, N, P, self.y[4], tr, d,
+                                  pool_out=cat_a + 4 * 128, pool_ld=192)
         else:
             e3 = L.Operand(p=cat_a + 4 * 64, ld=192, C=128, idx=L.dptr(self.idx[3]), k=k, npts=N), L.OP_EDGE
             rt.conv_forward(Ly["adj_conv5"], e3, R, self.y[4], 64, tr, d)
-        rt.maxk_fwd(Ly["adj_conv5"], self.y[4], P, k, cat_a + 4 * 128, 192)
+            rt.maxk_fwd(Ly["adj_conv5"], self.y[4], P, k, cat_a + 4 * 128, 192)
         l7 = Ly["adj_conv7"]
         rt.conv_forward(l7, rt.op_plain(self.cat, 192, 192), P, self.y7, 1024, tr, d)                     # :80-83
         L.check(L.lib().wspc_maxn_bnrelu_fwd(L.ptr(self.y7), L.ptr(l7.sc), L.ptr(l7.sh), B, N, 1024, L.ptr(self.g),

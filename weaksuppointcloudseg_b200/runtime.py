@@ -268,9 +268,11 @@ class EdgeSplit:
         return w
 
 
-def edge_first_forward(es: EdgeSplit, layer: Layer, x, ld, cx, idx, k, npts, P, y_out, training, decay):
+def edge_first_forward(es: EdgeSplit, layer: Layer, x, ld, cx, idx, k, npts, P, y_out, training, decay, pool_out=None,
+                       pool_ld=0):
     """x: tensor or raw address of the (P, ld) point features (cx channels used).  Writes pre-BN y_out (P*k, 64) and
-    the layer's batch-norm scale/shift, exactly like conv_forward(op_edge(...))."""
+    the layer's batch-norm scale/shift, exactly like conv_forward(op_edge(...)).  pool_out (address, leading dimension
+    pool_ld): also write max over k of relu(bn(y)) there (a block whose only conv feeds tf.reduce_max: no second read of y)."""
     assert layer.cout == 64 and layer.cin == 2 * cx
     Wc = es.weights(layer, cx)
     xa = x if isinstance(x, int) else x.data_ptr()
@@ -280,10 +282,14 @@ def edge_first_forward(es: EdgeSplit, layer: Layer, x, ld, cx, idx, k, npts, P, 
     if layer.has_bn and training:
         zero_(layer.stats)
         stats = layer.stats
-    L.check(L.lib().wspc_edge_combine_fwd(L.ptr(es.UV), 128, L.ptr(idx), L.ptr(layer.b), P, k, npts, 64, L.ptr(y_out),
-                                          L.ptr(stats), L.stream()))
+    mm = es.DUV if pool_out is not None else None        # (P, 128) scratch, free during the forward pass
+    L.check(L.lib().wspc_edge_combine_fwd_extrema(L.ptr(es.UV), 128, L.ptr(idx), L.ptr(layer.b), P, k, npts, 64, L.ptr(y_out),
+                                                  L.ptr(stats), L.ptr(mm), L.stream()))
     if layer.has_bn:
         bn_finalize(layer, P * k, training, decay)
+    if pool_out is not None:
+        L.check(L.lib().wspc_maxk_from_extrema(L.ptr(mm), L.ptr(layer.sc), L.ptr(layer.sh), P, 64, ctypes.c_void_p(pool_out),
+                                               pool_ld, L.stream()))
 
 
 def edge_first_backward(es: EdgeSplit, layer: Layer, x, ld, cx, idx, k, npts, P, G, y, dx_addr=None, lddx=0, MS=None):
