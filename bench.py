@@ -55,10 +55,22 @@ def workload_config(args, world):
 # --------------------------------------------------------------------------------------------------
 # CPU oracle arm (reference's CPU path: TF-1.14 cannot be installed; the oracle port is timed instead)
 # --------------------------------------------------------------------------------------------------
+def _use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every core this process may run on."""
+    import torch
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
 def cpu_oracle_steps(n_clouds, N, steps, warmup):
     import numpy as np
     import torch
     from oracle import dgcnn as od
+    _use_all_host_threads()
     from weaksuppointcloudseg_b200 import synthetic as syn
 
     X, Y, M, _ = syn.s3dis_batch(max(n_clouds // 2, 1), N=N, n_labelled=40, seed=1234)
@@ -80,7 +92,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = torch.get_num_threads()
+    cores = _use_all_host_threads()
     n, times = cpu_oracle_steps(args.cpu_clouds, args.points, args.steps, args.warmup)
     total = sum(times)
     v = n * len(times) / total
