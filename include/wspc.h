@@ -182,6 +182,15 @@ size_t wspc_conv1x1_wgrad_workspace_bytes(int K1, int K2);
 int wspc_conv1x1_wgrad(const wspc_operand_t* A, int a_mode, const wspc_operand_t* G, int g_mode, long long M,
                        float* dW, float* db, void* workspace, size_t workspace_bytes, wspc_stream_t stream);
 
+/* Weight gradient and data gradient of one conv2d in a single pass over the rows (Conv2DBackpropFilter + BiasAddGrad +
+ * Conv2DBackpropInput [TF]): dW(K1,K2), db(K2) as wspc_conv1x1_wgrad; dA(M,K1) = dY * W^T with W the layer's (K1,K2) weight
+ * matrix (leading dimension ldw), written through `epi` exactly as wspc_conv1x1_rows would with WSPC_EPI_RELUMASK_STATS.
+ * The tensor-core kernel stages G / y / the previous activation once for both products (A = BNRELU, G = DY or DY_MAXK,
+ * K1 <= 64, K2 <= 256); other shapes run the two separate kernels.  Workspace as wspc_conv1x1_wgrad_workspace_bytes. */
+int wspc_conv1x1_bwd_fused(const wspc_operand_t* A, int a_mode, const wspc_operand_t* G, int g_mode, long long M,
+                           const float* W, long long ldw, const wspc_epilogue_t* epi, float* dW, float* db,
+                           void* workspace, size_t workspace_bytes, wspc_stream_t stream);
+
 /* ------------------------------------------------- batch norm + pooling --- */
 /* batch_norm_dist_template (tf_util.py:502-535).  stats = (2,C) fp64 (sum, sum of squares) produced by
  * WSPC_EPI_STORE_STATS over `rows` rows.  training: mean/biased var from stats, pop <- pop*decay +

@@ -338,3 +338,48 @@ def test_narrow_head_data_gradient(cuda, gemm_path):
     assert rel(out, ref) <= 2e-5
     assert rel(stats[0], ref.sum(0)) <= 1e-5
     assert rel(stats[1], (ref * yprev.double()).sum(0)) <= 1e-5
+
+
+@pytest.mark.parametrize("K1,K2", [(64, 64), (64, 128)])
+def test_fused_weight_and_data_gradient(cuda, K1, K2):
+    """wspc_conv1x1_bwd_fused == wspc_conv1x1_wgrad + wspc_conv1x1_rows(RELUMASK_STATS) on the same operands."""
+    from weaksuppointcloudseg_b200 import _lib as L, runtime as rt
+    g = torch.Generator(device="cuda").manual_seed(21 + K2)
+    M = 128 * 11 + 77
+    ya = torch.randn((M, K1), device=cuda, generator=g)          # pre-BN output of the previous layer
+    sca = torch.rand(K1, device=cuda, generator=g) + 0.5
+    sha = torch.randn(K1, device=cuda, generator=g) * 0.3
+    G = torch.randn((M, K2), device=cuda, generator=g)
+    yb = torch.randn((M, K2), device=cuda, generator=g)
+    c1, c2, c3 = (torch.randn(K2, device=cuda, generator=g) * 0.5 for _ in range(3))
+    W = torch.randn((K1, K2), device=cuda, generator=g) * 0.2
+    A = (L.Operand(p=ya.data_ptr(), ld=K1, C=K1, sc=sca.data_ptr(), sh=sha.data_ptr(), dscale=1.0), L.OP_BNRELU)
+    Gop = (L.Operand(p=G.data_ptr(), ld=K2, C=K2, y=yb.data_ptr(), ldy=K2, c1=c1.data_ptr(), c2=c2.data_ptr(), c3=c3.data_ptr()),
+           L.OP_DY)
+    outs = []
+    for fused in (False, True):
+        dW, db = torch.empty((K1, K2), device=cuda), torch.empty(K2, device=cuda)
+        dA = torch.empty((M, K1), device=cuda)
+        st = torch.zeros((2, K1), dtype=torch.float64, device=cuda)
+        epi = L.Epilogue(out=dA.data_ptr(), ldo=K1, stats=st.data_ptr(), yprev=ya.data_ptr(), ldyp=K1, scp=sca.data_ptr(),
+                         shp=sha.data_ptr(), dscale=1.0)
+        if fused:
+            ws = L.workspace(L.lib().wspc_conv1x1_wgrad_workspace_bytes(K1, K2), cuda, "wgrad")
+            L.check(L.lib().wspc_conv1x1_bwd_fused(ctypes.byref(A[0]), A[1], ctypes.byref(Gop[0]), Gop[1], M, L.ptr(W), K2,
+                                                   ctypes.byref(epi), L.ptr(dW), L.ptr(db), L.ptr(ws), ws.numel(), L.stream()))
+        else:
+            rt.wgrad(A, Gop, M, dW, db, cuda)
+            rt.rows_gemm(Gop, W, K2, 1, M, K1, K2, epi, L.EPI_RELUMASK_STATS)
+        torch.cuda.synchronize()
+        outs.append((dW, db, dA, st))
+    # fp64 reference
+    a = torch.relu(ya.double() * sca.double() + sha.double())
+    dy = c1.double() * G.double() + c2.double() + c3.double() * yb.double()
+    dA_ref = (dy @ W.double().t()) * (a > 0)
+    for dW, db, dA, st in outs:
+        assert rel(dW, a.t() @ dy) <= 2e-4
+        assert rel(db, dy.sum(0)) <= 2e-4
+        assert rel(dA, dA_ref) <= 2e-4
+        assert rel(st[0], dA_ref.sum(0)) <= 2e-4
+        assert rel(st[1], (dA_ref * ya.double()).sum(0)) <= 2e-4
+    assert rel(outs[1][2], outs[0][2].double()) <= 1e-5      # same tensor-core arithmetic in both formulations

@@ -136,6 +136,7 @@ _EXTRA_DECLS.update({
     "wspc_conv1x1_rows_ws": (c_int, [_OPP, c_int, _P, c_longlong, c_int, c_longlong, c_int, c_int, _EPP, c_int, _P, c_size_t, _P]),
     "wspc_conv1x1_wgrad_workspace_bytes": (c_size_t, [c_int, c_int]),
     "wspc_conv1x1_wgrad": (c_int, [_OPP, c_int, _OPP, c_int, c_longlong, _P, _P, _P, c_size_t, _P]),
+    "wspc_conv1x1_bwd_fused": (c_int, [_OPP, c_int, _OPP, c_int, c_longlong, _P, c_longlong, _EPP, _P, _P, _P, c_size_t, _P]),
     "wspc_bn_finalize": (c_int, [_P, c_int, c_double, _P, _P, c_float, c_float, c_int, _P, _P, _P, _P, _P, _P, _P]),
     "wspc_bn_bwd_coeffs": (c_int, [_P, c_int, c_double, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "wspc_maxk_bnrelu_fwd": (c_int, [_P, _P, _P, c_longlong, c_int, c_int, _P, c_longlong, _P]),

@@ -13,6 +13,9 @@
 namespace wspc {
 void count_launch(int n = 1);
 int wgrad_tc_slabs(int K1, int K2);
+int bwd_fused_tc_dispatch(const Operand& A, int amode, const Operand& G, int gmode, long long M, int S, int K1p, int K2p,
+                          float* partial, float* partial_b, const float* Wf, long long ldw, int Nf, const Epilogue& E,
+                          cudaStream_t st);
 int wgrad_tc_dispatch(const Operand& A, int amode, const Operand& G, int gmode, long long M, int S, int K1p, int K2p,
                       float* partial, float* partial_b, cudaStream_t st);
 int rowgemm_tc_dispatch(const Operand& A, int amode, const float* Bm, long long ldb, int bT, long long M, int N, int K,
@@ -660,4 +663,40 @@ reduce:
   count_launch();
   WSPC_LAUNCH_CHECK("slab_reduce_kernel");
   return WSPC_OK;
+}
+
+// Weight gradient AND data gradient of one conv2d in a single pass over the rows (tcgen05 path; shapes it does not cover
+// run the two separate kernels).  dW(K1,K2), db(K2) as wspc_conv1x1_wgrad; dA(M, K1) = dY W^T through `epi`
+// (WSPC_EPI_RELUMASK_STATS: ReLU mask / dropout of the producing layer + its BN-backward sums).
+extern "C" int wspc_conv1x1_bwd_fused(const wspc_operand_t* A, int a_mode, const wspc_operand_t* G, int g_mode, long long M,
+                                      const float* W, long long ldw, const wspc_epilogue_t* epi, float* dW, float* db,
+                                      void* workspace, size_t workspace_bytes, wspc_stream_t stream) {
+  if (int rc = check_arch()) return rc;
+  WSPC_REQUIRE(A && G && W && epi && dW && workspace, "conv1x1_bwd_fused: null argument");
+  WSPC_REQUIRE(M >= 1 && A->C >= 1 && G->C >= 1, "conv1x1_bwd_fused: bad shape");
+  WSPC_REQUIRE(epi->out && epi->stats && epi->yprev && epi->scp && epi->shp, "conv1x1_bwd_fused: incomplete epilogue");
+  const WgradPlan p = wgrad_plan(A->C, G->C);
+  if (workspace_bytes < p.partial_bytes + p.bias_bytes) {
+    set_error("conv1x1_bwd_fused: workspace %zu < required %zu", workspace_bytes, p.partial_bytes + p.bias_bytes);
+    return WSPC_ERR_WORKSPACE;
+  }
+  float* partial = static_cast<float*>(workspace);
+  float* partial_b = reinterpret_cast<float*>(static_cast<char*>(workspace) + p.partial_bytes);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  static const bool env_simt = []() { const char* e = getenv("WSPC_GEMM"); return e && strcmp(e, "simt") == 0; }();
+  if (!env_simt && g_gemm_path == 0) {
+    const int rc = bwd_fused_tc_dispatch(*A, a_mode, *G, g_mode, M, p.S_tc, p.K1p, p.K2p, partial, db ? partial_b : nullptr, W, ldw,
+                                         A->C, *epi, st);
+    if (rc < 0) return rc;
+    if (rc == 1) {
+      const int total = A->C * G->C + (db ? G->C : 0);
+      slab_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(partial, partial_b, p.S_tc, A->C, G->C, p.K1p, p.K2p, dW, db);
+      count_launch();
+      WSPC_LAUNCH_CHECK("slab_reduce_kernel");
+      return WSPC_OK;
+    }
+  }
+  // not eligible: the two separate kernels
+  if (int rc = wspc_conv1x1_wgrad(A, a_mode, G, g_mode, M, dW, db, workspace, workspace_bytes, stream)) return rc;
+  return wspc_conv1x1_rows(G, g_mode, W, ldw, 1, M, A->C, G->C, epi, EPI_RELUMASK_STATS, stream);
 }

@@ -820,17 +820,33 @@ __device__ __forceinline__ uint32_t umma_idesc_mn(int N) {
          ((uint32_t)(TILE_M >> 4) << 24);
 }
 
-template <int AMODE, int GMODE, int MINB>
+// FUSE: the same pass over the rows also produces the layer's DATA gradient dA(row, 0:Nf) = dY(row,:) * Wf^T (Wf = the
+// layer's (Nf, K2) weight matrix) with the ReLU-mask / BN-sum epilogue of the producing layer (EPI_RELUMASK_STATS) -- the
+// dY tile staged for the weight gradient is read a second time K-major by the tensor core, so G, y and the previous
+// activation are read from HBM once for both gradients (Conv2DBackpropFilter + Conv2DBackpropInput of one conv2d).
+struct FuseArgs {
+  const float* Wf;      // (Nf, K2) row-major, leading dimension ldw
+  long long ldw;
+  int Nf;               // columns of dA (= the layer's input channels), Nf % 16 == 0, Nf <= 128
+  Epilogue E;           // out, ldo, stats, yprev, ldyp, scp, shp (, dmask, dscale)
+};
+
+template <int AMODE, int GMODE, int MINB, bool FUSE>
 __global__ void __launch_bounds__(TC_THREADS, MINB)
 colgemm_tc_kernel(const Operand A, const Operand G, long long M, long long rows_per_slab, int K1p, int K2p, int K2t,
-                  float* __restrict__ partial, float* __restrict__ partial_b, int tmem_cols, int genA, int genG) {
+                  float* __restrict__ partial, float* __restrict__ partial_b, int tmem_cols, int genA, int genG,
+                  const FuseArgs F) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int gGroups = K2t / 8;                         // power of two, <= 32
   unsigned char* sAhi = smem;
   unsigned char* sAlo = sAhi + 16 * A_GROUP_BYTES;
   unsigned char* sGhi = sAlo + 16 * A_GROUP_BYTES;
   unsigned char* sGlo = sGhi + (size_t)gGroups * A_GROUP_BYTES;
-  unsigned char* misc = sGlo + (size_t)gGroups * A_GROUP_BYTES;
+  const int w_group_bytes = FUSE ? F.Nf * 16 + 16 : 0;                  // fused data gradient: resident weight image
+  unsigned char* sWhi = sGlo + (size_t)gGroups * A_GROUP_BYTES;
+  unsigned char* sWlo = sWhi + (size_t)gGroups * w_group_bytes;
+  unsigned char* misc = sWlo + (size_t)gGroups * w_group_bytes;
+  float* stage = reinterpret_cast<float*>(sAhi);                        // epilogue staging aliases the A images
   uint64_t* mma_bar = reinterpret_cast<uint64_t*>(misc);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 16);
   float* bred = reinterpret_cast<float*>(misc + 32);   // [K2t] bias-gradient reduction
@@ -843,11 +859,30 @@ colgemm_tc_kernel(const Operand A, const Operand G, long long M, long long rows_
   if (warp == 0) tc_alloc(tmem_slot, (uint32_t)tmem_cols);
   if (tid == 32) { mbar_init(mma_bar, 1); mbar_fence_init(); }
   for (int i = tid; i < K2t; i += TC_THREADS) bred[i] = 0.f;
+  if (FUSE) {   // Wf^T as the K-major B operand: element (n, c) -> group c/8, row n, slot c%8 (as load_w of the row GEMM)
+    for (int e = tid; e < F.Nf * gGroups; e += TC_THREADS) {
+      const int n = e % F.Nf, g = e / F.Nf;
+      float w[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = g * 8 + i;
+        w[i] = (c < G.C) ? F.Wf[(long long)n * F.ldw + c] : 0.f;
+      }
+      uint4 hi, lo;
+      split8(w, hi, lo);
+      *reinterpret_cast<uint4*>(sWhi + (size_t)g * w_group_bytes + n * 16) = hi;
+      *reinterpret_cast<uint4*>(sWlo + (size_t)g * w_group_bytes + n * 16) = lo;
+    }
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t idesc = umma_idesc_mn(K2t);
+  const uint32_t idesc_f = FUSE ? umma_idesc(F.Nf) : 0u;
+  const int e_c4 = tid & 15, e_r0 = tid >> 4;          // fused epilogue: 4 fixed columns, 16 rows per sweep
+  double fst0[4] = {0.0, 0.0, 0.0, 0.0}, fst1[4] = {0.0, 0.0, 0.0, 0.0};
 
   // fixed per-thread channel groups
   const int gA = tid & 15, rA0 = tid >> 4;                 // A: 16 groups, 16 rows per sweep
@@ -980,9 +1015,90 @@ colgemm_tc_kernel(const Operand A, const Operand G, long long M, long long rows_
           accum = 1;
         }
       }
+      if (FUSE) {   // dA tile = dY * Wf^T : the dY image read K-major, accumulator at TMEM column K2t
+        const uint32_t wh = smem_u32(sWhi), wl = smem_u32(sWlo);
+        uint32_t acc2 = 0;
+#pragma unroll 1
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t gb = (pass == 1) ? gl : gh;
+          const uint32_t wb = (pass == 2) ? wl : wh;
+          for (int kk = 0; kk < gGroups / 2; ++kk) {
+            const uint64_t ad = umma_desc(gb + (uint32_t)(2 * kk) * A_GROUP_BYTES, A_GROUP_BYTES, 128);
+            const uint64_t bd = umma_desc(wb + (uint32_t)(2 * kk) * w_group_bytes, w_group_bytes, 128);
+            tc_mma_bf16(tmem_base + (uint32_t)K2t, ad, bd, idesc_f, acc2);
+            acc2 = 1;
+          }
+        }
+      }
       tc_commit(mma_bar);
     }
     pending = true;
+    if (FUSE) {
+      mbar_wait(mma_bar, phase);
+      phase ^= 1;
+      pending = false;
+      tc_fence_after();
+      // ---- fused epilogue (EPI_RELUMASK_STATS of the row GEMM): TMEM -> staging -> masked rows of dA + BN-backward sums
+      const Epilogue& E = F.E;
+      const int lq = warp & 3, ch = warp >> 2;
+      const int trow = lq * 32 + lane;
+      const int npass = (F.Nf + 63) / 64;
+      for (int p = 0; p < npass; ++p) {
+        float v[32];
+        tc_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(K2t + p * 64 + ch * 32), v);
+        float* srow = stage + trow * STAGE_LD + ch * 32;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(srow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        __syncthreads();
+        const int cl = p * 64 + e_c4 * 4;
+        if (cl < F.Nf) {
+          float scp[4], shp[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { scp[j] = E.scp[cl + j]; shp[j] = E.shp[cl + j]; }
+          float f0[4] = {0.f, 0.f, 0.f, 0.f}, f1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int r = e_r0 + 16 * it;
+            const long long row = rb + r;
+            if (row >= r_end) break;
+            const float4 s4 = *reinterpret_cast<const float4*>(stage + r * STAGE_LD + e_c4 * 4);
+            float o[4] = {s4.x, s4.y, s4.z, s4.w};
+            const float4 y4 = *reinterpret_cast<const float4*>(E.yprev + row * E.ldyp + cl);
+            const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
+            float dm[4] = {1.f, 1.f, 1.f, 1.f};
+            if (E.dmask) {
+              const float4 m4 = *reinterpret_cast<const float4*>(E.dmask + row * F.Nf + cl);
+              dm[0] = m4.x * E.dscale; dm[1] = m4.y * E.dscale; dm[2] = m4.z * E.dscale; dm[3] = m4.w * E.dscale;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const bool on = fmaf(yv[j], scp[j], shp[j]) > 0.f;
+              o[j] = on ? o[j] * dm[j] : 0.f;
+              f0[j] += o[j];
+              f1[j] = fmaf(o[j], yv[j], f1[j]);
+            }
+            *reinterpret_cast<float4*>(E.out + row * E.ldo + cl) = make_float4(o[0], o[1], o[2], o[3]);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { fst0[j] += (double)f0[j]; fst1[j] += (double)f1[j]; }
+        }
+        __syncthreads();   // staging (= the A images) free for the next pass / tile
+      }
+      tc_fence_before();
+    }
+  }
+  if (FUSE) {   // flush the BN-backward sums of the data gradient (Nf <= 64 per pass; lanes l and l+16 own the same columns)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      double a = fst0[j], b = fst1[j];
+      a += __shfl_xor_sync(0xffffffffu, a, 16);
+      b += __shfl_xor_sync(0xffffffffu, b, 16);
+      const int cl = e_c4 * 4 + j;
+      if (lane < 16 && cl < F.Nf) {
+        atomicAdd(F.E.stats + cl, a);
+        atomicAdd(F.E.stats + F.Nf + cl, b);
+      }
+    }
   }
   if (pending) { mbar_wait(mma_bar, phase); phase ^= 1; }
   tc_fence_after();
@@ -1027,28 +1143,29 @@ bool wgrad_tc_supported(const Operand& A, int amode, const Operand& G, int gmode
   return true;
 }
 
-template <int AMODE, int GMODE>
+template <int AMODE, int GMODE, bool FUSE>
 int launch_wgrad_tc(const Operand& A, const Operand& G, long long M, int S, int K1p, int K2p, float* partial,
-                    float* partial_b, cudaStream_t st) {
+                    float* partial_b, const FuseArgs& F, cudaStream_t st) {
   const int genA = tc_operand_fast(A, AMODE, A.C) ? 0 : 1, genG = tc_operand_fast(G, GMODE, G.C) ? 0 : 1;
   const int t1 = (A.C + TILE_M - 1) / TILE_M, t2 = (G.C + 255) / 256;
   int K2t = 16;
   const int k2max = G.C < 256 ? G.C : 256;
   while (K2t < k2max) K2t <<= 1;
   int tmem_cols = 64;
-  while (tmem_cols < K2t) tmem_cols <<= 1;
-  const size_t smem = (size_t)(32 + 2 * (K2t / 8)) * A_GROUP_BYTES + 32 + (size_t)K2t * 4 + 64;
+  while (tmem_cols < K2t + (FUSE ? F.Nf : 0)) tmem_cols <<= 1;
+  const size_t wimg = FUSE ? (size_t)2 * (K2t / 8) * (F.Nf * 16 + 16) : 0;
+  const size_t smem = (size_t)(32 + 2 * (K2t / 8)) * A_GROUP_BYTES + wimg + 32 + (size_t)K2t * 4 + 64;
   long long rps = (M + S - 1) / S;
   rps = (rps + TILE_M - 1) / TILE_M * TILE_M;
   dim3 grid(S, t1, t2);
   if (smem <= 110 * 1024) {
-    auto kern = colgemm_tc_kernel<AMODE, GMODE, 2>;
+    auto kern = colgemm_tc_kernel<AMODE, GMODE, 2, FUSE>;
     WSPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, TC_THREADS, smem, st>>>(A, G, M, rps, K1p, K2p, K2t, partial, partial_b, tmem_cols, genA, genG);
+    kern<<<grid, TC_THREADS, smem, st>>>(A, G, M, rps, K1p, K2p, K2t, partial, partial_b, tmem_cols, genA, genG, F);
   } else {
-    auto kern = colgemm_tc_kernel<AMODE, GMODE, 1>;
+    auto kern = colgemm_tc_kernel<AMODE, GMODE, 1, FUSE>;
     WSPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, TC_THREADS, smem, st>>>(A, G, M, rps, K1p, K2p, K2t, partial, partial_b, tmem_cols, genA, genG);
+    kern<<<grid, TC_THREADS, smem, st>>>(A, G, M, rps, K1p, K2p, K2t, partial, partial_b, tmem_cols, genA, genG, F);
   }
   count_launch();
   WSPC_LAUNCH_CHECK("colgemm_tc_kernel");
@@ -1068,12 +1185,31 @@ int wgrad_tc_dispatch(const Operand& A, int amode, const Operand& G, int gmode, 
                       float* partial, float* partial_b, cudaStream_t st) {
   if (!wgrad_tc_supported(A, amode, G, gmode)) return 0;
   int rc = -100;
+  const FuseArgs none{};
 #define WSPC_WG(AM, GM) \
-  if (amode == AM && gmode == GM) rc = launch_wgrad_tc<AM, GM>(A, G, M, S, K1p, K2p, partial, partial_b, st);
+  if (amode == AM && gmode == GM) rc = launch_wgrad_tc<AM, GM, false>(A, G, M, S, K1p, K2p, partial, partial_b, none, st);
   WSPC_WG(OP_PLAIN, OP_DY) WSPC_WG(OP_BNRELU, OP_DY) WSPC_WG(OP_EDGE, OP_DY) WSPC_WG(OP_PLAIN, OP_DY_SPARSE)
   WSPC_WG(OP_BNRELU, OP_DY_MAXK)
 #undef WSPC_WG
   if (rc == -100) return 0;
+  return rc == WSPC_OK ? 1 : rc;
+}
+
+// fused weight + data gradient of one conv2d (see FuseArgs): eligible when dW is a single (<=128 x <=256) tile, so every
+// row tile is visited exactly once, and dA has at most 64 columns.  returns 1 if handled, 0 if not eligible, <0 on error
+int bwd_fused_tc_dispatch(const Operand& A, int amode, const Operand& G, int gmode, long long M, int S, int K1p, int K2p,
+                          float* partial, float* partial_b, const float* Wf, long long ldw, int Nf, const Epilogue& E,
+                          cudaStream_t st) {
+  if (!wgrad_tc_supported(A, amode, G, gmode)) return 0;
+  if (amode != OP_BNRELU || (gmode != OP_DY && gmode != OP_DY_MAXK)) return 0;
+  if (A.C > TILE_M || G.C > 256 || G.C % 16 != 0 || Nf % 16 != 0 || Nf < 16 || Nf > 64) return 0;
+  if (!aligned16(E.out) || (E.ldo % 4) != 0 || !aligned16(E.yprev) || (E.ldyp % 4) != 0 || !E.stats || !E.scp || !E.shp) return 0;
+  if (E.dmask && !aligned16(E.dmask)) return 0;
+  FuseArgs F;
+  F.Wf = Wf; F.ldw = ldw; F.Nf = Nf; F.E = E;
+  int rc = -100;
+  if (gmode == OP_DY) rc = launch_wgrad_tc<OP_BNRELU, OP_DY, true>(A, G, M, S, K1p, K2p, partial, partial_b, F, st);
+  else rc = launch_wgrad_tc<OP_BNRELU, OP_DY_MAXK, true>(A, G, M, S, K1p, K2p, partial, partial_b, F, st);
   return rc == WSPC_OK ? 1 : rc;
 }
 

@@ -245,9 +245,7 @@ class S3DISEngine:
             rt.maxk_bwd(c4, self.y[3], P, k, cat_a + 4 * 64, 192, dcat_a + 4 * 64, 192, self.Ga)
             rt.bn_bwd_coeffs(c4, R)
             G4 = rt.op_dy(self.Ga, 64, self.y[3], 64, c4, 64)
-        rt.wgrad(rt.op_bnrelu(self.y[2], c3), G4, R, c4.dW, c4.db, dev)
-        e, m = rt.epi_relumask(self.Gb, c3, self.y[2])
-        rt.rows_gemm(G4, c4.W, 64, 1, R, 64, 64, e, m)
+        rt.conv_bwd(rt.op_bnrelu(self.y[2], c3), G4, R, c4, rt.epi_relumask(self.Gb, c3, self.y[2]), dev)
         rt.bn_bwd_coeffs(c3, R)
         if self.es is not None:
             rt.edge_first_backward(self.es, c3, cat_a, 192, 64, self.idx[1], k, N, P, self.Gb, self.y[2], dcat_a, 192)
@@ -265,9 +263,7 @@ class S3DISEngine:
             rt.maxk_bwd(c2, self.y[1], P, k, cat_a, 192, dcat_a, 192, self.Ga)
             rt.bn_bwd_coeffs(c2, R)
             G2e = rt.op_dy(self.Ga, 64, self.y[1], 64, c2, 64)
-        rt.wgrad(rt.op_bnrelu(self.y[0], c1), G2e, R, c2.dW, c2.db, dev)
-        e, m = rt.epi_relumask(self.Gb, c1, self.y[0])
-        rt.rows_gemm(G2e, c2.W, 64, 1, R, 64, 64, e, m)
+        rt.conv_bwd(rt.op_bnrelu(self.y[0], c1), G2e, R, c2, rt.epi_relumask(self.Gb, c1, self.y[0]), dev)
         rt.bn_bwd_coeffs(c1, R)
         if self.es is not None:
             rt.edge_first_backward(self.es, c1, self.X, 9, 9, self.idx[0], k, N, P, self.Gb, self.y[0])

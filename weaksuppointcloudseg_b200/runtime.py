@@ -161,6 +161,26 @@ def wgrad(A, G, M, dW, db, device):
                                        ws.numel(), L.stream()))
 
 
+# WSPC_BWD=split runs the weight gradient and the data gradient of a conv2d as two kernels (A/B tests)
+BWD_FUSED = os.environ.get("WSPC_BWD", "fused") != "split"
+
+
+def conv_bwd(A, G, M, layer: Layer, epi_pair, device):
+    """weight gradient (layer.dW, layer.db) and data gradient (through the RELUMASK epilogue `epi_pair` from epi_relumask)
+    of one conv2d: A = the layer's input operand, G = gradient w.r.t. its pre-BN output."""
+    e, m = epi_pair
+    if not BWD_FUSED:
+        wgrad(A, G, M, layer.dW, layer.db, device)
+        rows_gemm(G, layer.W, layer.cout, 1, M, layer.cin, layer.cout, e, m)
+        return
+    a, amode = A
+    g, gmode = G
+    nbytes = L.lib().wspc_conv1x1_wgrad_workspace_bytes(a.C, g.C)
+    ws = L.workspace(nbytes, device, "wgrad")
+    L.check(L.lib().wspc_conv1x1_bwd_fused(ctypes.byref(a), amode, ctypes.byref(g), gmode, M, L.ptr(layer.W), layer.cout,
+                                           ctypes.byref(e), L.ptr(layer.dW), L.ptr(layer.db), L.ptr(ws), ws.numel(), L.stream()))
+
+
 def zero_(t):
     L.check(L.lib().wspc_zero(L.ptr(t), t.numel() * t.element_size(), L.stream()))
 
