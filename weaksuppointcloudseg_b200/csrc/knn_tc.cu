@@ -198,9 +198,12 @@ knn_tc_prep_kernel(const float* __restrict__ x, int N, int ldx, int coff, int D,
   }
   sq[(size_t)b * Npad + n] = acc;
   sqc[(size_t)b * Npad + n] = accc;
-  if (n < N) {   // norms >= 0: uint order == float order
-    atomicMax(smax_bits + 2 * b, __float_as_uint(acc));
-    atomicMax(smax_bits + 2 * b + 1, __float_as_uint(accc));
+  // per-cloud maximum norms (norms >= 0: uint order == float order): one atomic per warp instead of one per point
+  const unsigned m0 = __reduce_max_sync(0xffffffffu, n < N ? __float_as_uint(acc) : 0u);
+  const unsigned m1 = __reduce_max_sync(0xffffffffu, n < N ? __float_as_uint(accc) : 0u);
+  if ((r & 31) == 0) {
+    atomicMax(smax_bits + 2 * b, m0);
+    atomicMax(smax_bits + 2 * b + 1, m1);
   }
 }
 
