@@ -835,12 +835,14 @@ template <int AMODE, int GMODE, int MINB, bool FUSE>
 __global__ void __launch_bounds__(TC_THREADS, MINB)
 colgemm_tc_kernel(const Operand A, const Operand G, long long M, long long rows_per_slab, int K1p, int K2p, int K2t,
                   float* __restrict__ partial, float* __restrict__ partial_b, int tmem_cols, int genA, int genG,
-                  const FuseArgs F) {
+                  int aGroups, const FuseArgs F) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int gGroups = K2t / 8;                         // power of two, <= 32
+  // A images: aGroups = 8 when the operand has <= 64 channels (the M=128 MMA then also reads the 8 groups that follow --
+  // the lo image / the dY image -- into accumulator lanes 64..127, which are never stored), else 16
   unsigned char* sAhi = smem;
-  unsigned char* sAlo = sAhi + 16 * A_GROUP_BYTES;
-  unsigned char* sGhi = sAlo + 16 * A_GROUP_BYTES;
+  unsigned char* sAlo = sAhi + (size_t)aGroups * A_GROUP_BYTES;
+  unsigned char* sGhi = sAlo + (size_t)aGroups * A_GROUP_BYTES;
   unsigned char* sGlo = sGhi + (size_t)gGroups * A_GROUP_BYTES;
   const int w_group_bytes = FUSE ? F.Nf * 16 + 16 : 0;                  // fused data gradient: resident weight image
   unsigned char* sWhi = sGlo + (size_t)gGroups * A_GROUP_BYTES;
@@ -890,6 +892,7 @@ colgemm_tc_kernel(const Operand A, const Operand G, long long M, long long rows_
   const int rGstep = TC_THREADS / gGroups;
   const int cA = k1_0 / 8 + gA, cG = k2_0 / 8 + gG;        // absolute channel groups
   const bool vA = cA * 8 < A.C, vG = cG * 8 < G.C;
+  const bool wA = gA < aGroups;                             // this thread's A group exists in shared memory
   float a0[8], a1[8], a2[8], g0[8], g1[8], g2[8];
   load_consts<AMODE>(A, cA, A.C, a0, a1, a2);
   load_consts<GMODE>(G, cG, G.C, g0, g1, g2);
@@ -935,8 +938,10 @@ colgemm_tc_kernel(const Operand A, const Operand G, long long M, long long rows_
           finish_chunk<AMODE>(A, rb + r, cA, ok[u], pt[u], cb[u], a0, a1, a2, w[u], v);
           uint4 hi, lo;
           split8(v, hi, lo);
-          *reinterpret_cast<uint4*>(sAhi + (size_t)gA * A_GROUP_BYTES + r * 16) = hi;
-          *reinterpret_cast<uint4*>(sAlo + (size_t)gA * A_GROUP_BYTES + r * 16) = lo;
+          if (wA) {
+            *reinterpret_cast<uint4*>(sAhi + (size_t)gA * A_GROUP_BYTES + r * 16) = hi;
+            *reinterpret_cast<uint4*>(sAlo + (size_t)gA * A_GROUP_BYTES + r * 16) = lo;
+          }
         }
       }
     } else {
@@ -947,8 +952,10 @@ colgemm_tc_kernel(const Operand A, const Operand G, long long M, long long rows_
         load_chunk<AMODE>(A, row, cA, vA && row < r_end, a0, a1, a2, v, true);
         uint4 hi, lo;
         split8(v, hi, lo);
-        *reinterpret_cast<uint4*>(sAhi + (size_t)gA * A_GROUP_BYTES + r * 16) = hi;
-        *reinterpret_cast<uint4*>(sAlo + (size_t)gA * A_GROUP_BYTES + r * 16) = lo;
+        if (wA) {
+          *reinterpret_cast<uint4*>(sAhi + (size_t)gA * A_GROUP_BYTES + r * 16) = hi;
+          *reinterpret_cast<uint4*>(sAlo + (size_t)gA * A_GROUP_BYTES + r * 16) = lo;
+        }
       }
     }
     if (!genG) {
@@ -1154,18 +1161,21 @@ int launch_wgrad_tc(const Operand& A, const Operand& G, long long M, int S, int 
   int tmem_cols = 64;
   while (tmem_cols < K2t + (FUSE ? F.Nf : 0)) tmem_cols <<= 1;
   const size_t wimg = FUSE ? (size_t)2 * (K2t / 8) * (F.Nf * 16 + 16) : 0;
-  const size_t smem = (size_t)(32 + 2 * (K2t / 8)) * A_GROUP_BYTES + wimg + 32 + (size_t)K2t * 4 + 64;
+  // <= 64 operand channels: 8-group A images, provided the 16 groups an M=128 MMA reads from each image base stay inside
+  // the A + dY region (2*8 + 2*(K2t/8) >= 24 groups) and the fused epilogue's staging tile fits in it
+  const int aGroups = (A.C <= 64 && K2t >= 32) ? 8 : 16;
+  const size_t smem = (size_t)(2 * aGroups + 2 * (K2t / 8)) * A_GROUP_BYTES + wimg + 32 + (size_t)K2t * 4 + 64;
   long long rps = (M + S - 1) / S;
   rps = (rps + TILE_M - 1) / TILE_M * TILE_M;
   dim3 grid(S, t1, t2);
   if (smem <= 110 * 1024) {
     auto kern = colgemm_tc_kernel<AMODE, GMODE, 2, FUSE>;
     WSPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, TC_THREADS, smem, st>>>(A, G, M, rps, K1p, K2p, K2t, partial, partial_b, tmem_cols, genA, genG, F);
+    kern<<<grid, TC_THREADS, smem, st>>>(A, G, M, rps, K1p, K2p, K2t, partial, partial_b, tmem_cols, genA, genG, aGroups, F);
   } else {
     auto kern = colgemm_tc_kernel<AMODE, GMODE, 1, FUSE>;
     WSPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, TC_THREADS, smem, st>>>(A, G, M, rps, K1p, K2p, K2t, partial, partial_b, tmem_cols, genA, genG, F);
+    kern<<<grid, TC_THREADS, smem, st>>>(A, G, M, rps, K1p, K2p, K2t, partial, partial_b, tmem_cols, genA, genG, aGroups, F);
   }
   count_launch();
   WSPC_LAUNCH_CHECK("colgemm_tc_kernel");
