@@ -1,0 +1,117 @@
+"""The trainer classes as drop-ins: the epoch loops of the reference (`TrainOneEpoch_Full`, `EvalOneEpoch_Full`, `Test`,
+checkpoint save / restore; S3DIS/S3DIS_DGCNN_trainer.py:221-349, :401-497, :499-584, :586-629) driven by loaders that follow
+the reference's loader contracts (DataIO_S3DIS.py:127-154, :288-299) on synthetic blocks."""
+import numpy as np
+import pytest
+import torch
+
+from weaksuppointcloudseg_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+
+class FakeTrainLoader:
+    """S3DIS_IO.NextBatch_TrainSet_v1 / NextBatch_ValSet contract: (flag, data, seg, weak_seg_onehot, mb_size, data_idx)."""
+
+    def __init__(self, n_batches, bs, N, seed):
+        self.n, self.bs, self.N, self.i = n_batches, bs, N, 0
+        X, _, _, seg = syn.s3dis_batch(n_batches * bs, N=N, n_labelled=8, seed=seed)
+        self.X, self.seg = X[0::2], seg[0::2]                    # originals only; the trainer builds the Siamese partner
+
+    def _next(self):
+        if self.i >= self.n:
+            return None
+        lo = self.i * self.bs
+        self.i += 1
+        return self.X[lo:lo + self.bs], self.seg[lo:lo + self.bs], np.arange(lo, lo + self.bs)
+
+    def NextBatch_TrainSet_v1(self):
+        o = self._next()
+        if o is None:
+            return False, None, None, None, 0, None
+        return True, o[0], o[1], None, self.bs, o[2]
+
+    def NextBatch_ValSet(self):
+        o = self._next()
+        if o is None:
+            return False, None, None, None, 0
+        return True, o[0], o[1], None, self.bs
+
+
+class FakeTestLoader:
+    """S3DIS_Test.LoadNextTestRoomData_v1 contract: (flag, blocks (nb,N,9), labels (nb,N))."""
+
+    def __init__(self, rooms, nb, N):
+        self.rooms, self.nb, self.N, self.i = rooms, nb, N, 0
+
+    def LoadNextTestRoomData_v1(self):
+        if self.i >= self.rooms:
+            return False, None, None
+        X, _, _, seg = syn.s3dis_batch(self.nb, N=self.N, n_labelled=8, seed=900 + self.i)
+        self.i += 1
+        return True, X[0::2], seg[0::2]
+
+
+def test_s3dis_trainer_epoch_loops_and_checkpoint(cuda, tmp_path):
+    from weaksuppointcloudseg_b200.S3DIS_DGCNN_trainer import S3DIS_Trainer
+    bs, N = 2, 256
+    tr = S3DIS_Trainer(test_area=5, device=cuda, seed=3)
+    tr.SetLearningRate(1e-3, bs)
+    tr.defineNetwork(2 * bs, N, style='Full', rampup=0)
+    pts_idx = [np.random.default_rng(i).choice(N, 8, replace=False) for i in range(3 * bs)]
+    w0 = tr.engine.vs.theta.clone()
+    loss, acc = tr.TrainOneEpoch_Full(FakeTrainLoader(3, bs, N, seed=5), pts_idx)
+    assert np.isfinite(loss) and 0.0 <= acc <= 1.0
+    assert tr.epoch == 1 and tr.batch == 3                          # global step advanced once per mini-batch (:110)
+    assert float((tr.engine.vs.theta - w0).abs().max()) > 0
+    vloss, vacc, miou, iou = tr.EvalOneEpoch_Full(FakeTrainLoader(2, bs, N, seed=6))
+    assert np.isfinite(vloss) and 0.0 <= vacc <= 1.0 and iou.shape == (13,) and 0.0 <= miou <= 1.0
+    # checkpoint round trip: variables under their TF names, global step, Adam slots
+    path = str(tmp_path / "Checkpoint_epoch-1")
+    tr.SaveCheckPoint(path)
+    blob = np.load(path + ".npz")
+    assert "adj_conv1/weights" in blob.files and "seg/conv3/biases" in blob.files and "adj_conv7/bn/pop_mean" in blob.files
+    assert int(blob["Variable"]) == 3
+    tr2 = S3DIS_Trainer(test_area=5, device=cuda, seed=99)
+    tr2.SetLearningRate(1e-3, bs)
+    tr2.defineNetwork(2 * bs, N, style='Full', rampup=0)
+    tr2.RestoreCheckPoint(path)
+    assert torch.equal(tr2.engine.vs.theta, tr.engine.vs.theta) and torch.equal(tr2.engine.vs.state, tr.engine.vs.state)
+    assert tr2.batch == 3
+    # same input -> same inference logits after the restore
+    X, Y, M, _ = syn.s3dis_batch(bs, N=N, n_labelled=8, seed=7)
+    l1, z1 = tr.eval_batch(X, Y, M)
+    l2, z2 = tr2.eval_batch(X, Y, M)
+    assert l1 == l2 and np.array_equal(z1, z2)
+
+
+def test_s3dis_trainer_test_time_label_propagation(cuda):
+    from weaksuppointcloudseg_b200.S3DIS_DGCNN_trainer import S3DIS_Trainer
+    N = 256
+    tr = S3DIS_Trainer(test_area=5, device=cuda, seed=4)
+    tr.SetLearningRate(1e-3, 1)
+    tr.defineNetwork(2, N, style='Full', rampup=0)
+    tr.defLabelPropSolver()
+    res = tr.Test(FakeTestLoader(rooms=2, nb=2, N=N))
+    for key in ('net', 'lp'):
+        assert 0.0 <= res[key]['acc'] <= 1.0 and res[key]['iou'].shape == (13,) and 0.0 <= res[key]['miou'] <= 1.0
+
+
+def test_plain_style_and_closed_rampup_gate(cuda):
+    """Plain style optimises the seg term only; Full style with epoch < rampup evaluates the weak terms but multiplies
+    them by 0 (the gate is a constant of the graph, S3DIS_DGCNN_trainer.py:93-102)."""
+    from weaksuppointcloudseg_b200.S3DIS_DGCNN_trainer import S3DIS_Trainer
+    bs, N = 2, 256
+    X, Y, M, _ = syn.s3dis_batch(bs, N=N, n_labelled=8, seed=11)
+    out = {}
+    for name, style, rampup in (("plain", "Plain", 101), ("closed", "Full", 101), ("open", "Full", 0)):
+        tr = S3DIS_Trainer(test_area=5, device=cuda, seed=5)
+        tr.SetLearningRate(1e-3, bs)
+        tr.defineNetwork(2 * bs, N, style=style, rampup=rampup)
+        out[name] = (tr.train_batch(X, Y, M), tr.engine.vs.grad.clone())
+    # closed gate: the reported weak terms are those of the open graph, the gradient is the Plain one (compared in L2:
+    # the first Adam step is sign-like, so weights amplify last-bit differences of the atomics' summation order)
+    l2 = lambda a, b: float((a - b).norm() / b.norm())   # noqa: E731
+    assert np.allclose(out["closed"][0][1:4], out["open"][0][1:4], rtol=1e-5)
+    assert l2(out["closed"][1], out["plain"][1]) <= 1e-4
+    assert l2(out["open"][1], out["plain"][1]) >= 1e-2
