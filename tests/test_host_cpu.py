@@ -126,3 +126,20 @@ def test_data_parallel_gloo_world_size_2(tmp_path):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stderr[-2000:]
     assert out.stdout.count("ok") == 2
+
+
+def test_evaluation_iou_matches_reference_loop():
+    """Evaluation.Eval.EvalIoU (Util/Evaluation.py:13-36): per-part IoU averaged over the category's part ids, absent
+    parts count as 1 -- checked against the reference's scalar loop restated inline."""
+    from weaksuppointcloudseg_b200.Evaluation import Eval
+    rng = np.random.default_rng(0)
+    for oids in ([0, 1, 2, 3], [12, 13, 14, 15], [47, 48, 49]):
+        pred = rng.choice(oids + [5], 300)
+        gt = rng.choice(oids[:-1], 300)          # the last part never occurs in the ground truth
+        total = 0.0
+        for oid in oids:
+            n_pred, n_gt = np.sum(pred == oid), np.sum(gt == oid)
+            n_int = np.sum((gt == oid) & (pred == gt))
+            n_uni = n_pred + n_gt - n_int
+            total += 1.0 if n_uni == 0 else n_int / n_uni
+        assert abs(Eval().EvalIoU(pred, gt, oids) - total / len(oids)) < 1e-12

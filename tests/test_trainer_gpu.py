@@ -113,5 +113,54 @@ def test_plain_style_and_closed_rampup_gate(cuda):
     # the first Adam step is sign-like, so weights amplify last-bit differences of the atomics' summation order)
     l2 = lambda a, b: float((a - b).norm() / b.norm())   # noqa: E731
     assert np.allclose(out["closed"][0][1:4], out["open"][0][1:4], rtol=1e-5)
-    assert l2(out["closed"][1], out["plain"][1]) <= 1e-4
-    assert l2(out["open"][1], out["plain"][1]) >= 1e-2
+    # (two runs of the same graph differ by ~3e-4: the fp64 atomics of the BN statistics commute only up to the last
+    # bit, which moves a few ReLU / arg-max decisions)
+    assert l2(out["closed"][1], out["plain"][1]) <= 3e-3
+    assert l2(out["open"][1], out["plain"][1]) >= 3e-2
+
+
+class FakeShapeNetLoader:
+    """ShapeNetIO contract (DataIO_ShapeNet.py:145-193): NextBatch_TrainSet / NextBatch_ValSet return
+    (flag, data (b,N,3), label (b,1), seg (b,N), weak_seg_onehot, mb_size, file_idx, data_idx)."""
+    NUM_CATEGORIES = 16
+
+    def __init__(self, n_batches, bs, N, seed, last_short=False):
+        self.n, self.bs, self.N, self.i, self.last_short = n_batches, bs, N, 0, last_short
+        X, lab, _, _, seg = syn.shapenet_batch(n_batches * bs, N=N, n_labelled=16, seed=seed)
+        self.X, self.lab, self.seg = X[0::2], lab[0::2].argmax(-1)[:, None], seg[0::2]
+        self.objcats = list(range(16))
+        self.object2setofoid = {c: list(range(*syn.CAT_PART_RANGES[c])) for c in range(16)}
+
+    def _next(self):
+        if self.i >= self.n:
+            return (False, None, None, None, None, 0, None, None)
+        lo = self.i * self.bs
+        self.i += 1
+        mb = self.bs - 1 if (self.last_short and self.i == self.n) else self.bs
+        sl = slice(lo, lo + mb)
+        return (True, self.X[sl], self.lab[sl], self.seg[sl], None, mb, np.zeros(mb, np.int64), np.arange(lo, lo + mb))
+
+    def NextBatch_TrainSet(self, shuffle_flag=True):
+        return self._next()
+
+    def NextBatch_ValSet(self):
+        return self._next()
+
+
+def test_shapenet_trainer_epoch_loops(cuda):
+    from weaksuppointcloudseg_b200.ShapeNet_DGCNN_trainer import ShapeNet_Trainer
+    from weaksuppointcloudseg_b200.Evaluation import Eval
+    bs, N = 3, 256
+    tr = ShapeNet_Trainer(device=cuda, seed=2)
+    tr.SetLearningRate(1e-3, bs)
+    tr.defineNetwork(2 * bs, point_num=N, style='Full', rampup=0)
+    n_train = 2 * bs
+    file_idx_list, data_idx_list = np.zeros(n_train, np.int64), np.arange(n_train)
+    pts_idx_list = np.stack([np.random.default_rng(i).choice(N, 16, replace=False) for i in range(n_train)])
+    w0 = tr.engine.vs.theta.clone()
+    loss, acc = tr.TrainOneEpoch_Full(FakeShapeNetLoader(2, bs, N, seed=31), file_idx_list, data_idx_list, pts_idx_list)
+    assert np.isfinite(loss) and 0.0 <= acc <= 1.0 and tr.epoch == 1 and tr.batch == 2
+    assert float((tr.engine.vs.theta - w0).abs().max()) > 0
+    # validation with a short last batch (padded with sample 0, :434-441)
+    vloss, vacc, perdata, pershape = tr.EvalOneEpoch_Full(FakeShapeNetLoader(2, bs, N, seed=32, last_short=True), Eval())
+    assert np.isfinite(vloss) and 0.0 <= vacc <= 1.0 and 0.0 <= perdata <= 1.0 and pershape.shape == (16,)

@@ -84,3 +84,103 @@ class ShapeNet_Trainer(S3DIS_Trainer):
         from . import ProbLabelPropagation as PLP
         self.LPSolver = PLP.LabelPropagation_TF(alpha=1e0, beta=1e0, K=10)
         self.TFComp = {'Lmat': Tool.TF_Computation.LaplacianMatSym_XYZRGB_DirectComp()}
+
+    # ------------------------------------------------------------------ epoch loops --------------
+    @staticmethod
+    def _restrict_to_category(Z_prob, iou_oids):
+        """the prediction is taken among the part ids of the shape's category (reference :319-323, :486-489)"""
+        z = np.array(Z_prob, copy=True)
+        z[:, list(iou_oids)] += 1
+        return np.argmax(z, axis=-1)
+
+    def TrainOneEpoch_Full(self, Loader, file_idx_list, data_idx_list, pts_idx_list=None):
+        """One training epoch (ShapeNet_DGCNN_trainer.py:220-341).  `Loader` follows ShapeNetIO.NextBatch_TrainSet
+        (DataIO_ShapeNet.py:145-193): (flag, data (b,N,3), label (b,1), seg (b,N), weak_seg_onehot, mb_size, file_idx,
+        data_idx) and exposes NUM_CATEGORIES, objcats, object2setofoid.  Mask from (file_idx_list, data_idx_list,
+        pts_idx_list) as in :243-251; Siamese partner = jitter 2e-3 * extent + random mirror of axis 2 once the ramp-up
+        epoch is reached (:260-275), a plain copy before; rows interleaved [sample, partner]."""
+        batch_cnt, data_cnt, avg_loss, avg_acc = 1, 0, 0., 0.
+        rng = np.random.default_rng(1000 + self.epoch)
+        file_idx_list = None if file_idx_list is None else np.asarray(file_idx_list)
+        data_idx_list = None if data_idx_list is None else np.asarray(data_idx_list)
+        while True:
+            SuccessFlag, data, label, seg, _, mb_size, file_idx, data_idx = Loader.NextBatch_TrainSet(shuffle_flag=True)
+            if not SuccessFlag:
+                break
+            if mb_size < self.BATCH_SIZE:                 # short batches are skipped, not padded (:239-240)
+                continue
+            data = np.asarray(data, np.float32)
+            label = np.asarray(label).astype(np.int64).reshape(mb_size, -1)
+            seg = np.asarray(seg).astype(np.int64)
+            N = data.shape[1]
+            mask = np.zeros((mb_size, N), np.float32)
+            if pts_idx_list is not None:
+                for b_i in range(mb_size):
+                    hit = np.where((file_idx_list == file_idx[b_i]) & (data_idx_list == data_idx[b_i]))[0]
+                    mask[b_i, np.asarray(pts_idx_list[hit][0]).astype(np.int64)] = 1
+            partner = data.copy()
+            if self.epoch >= self.rampup:
+                extent = data.max(axis=1, keepdims=True) - data.min(axis=1, keepdims=True)
+                partner = data + (2e-3 * extent * rng.standard_normal(data.shape)).astype(np.float32)
+                flip = rng.integers(0, 2, mb_size).astype(bool)
+                partner[flip, :, 2] *= -1
+            data_feed = np.empty((2 * mb_size, N, 3), np.float32)
+            data_feed[0::2], data_feed[1::2] = data, partner
+            label_onehot_feed = np.repeat(Tool.OnehotEncode(label[:, 0], Loader.NUM_CATEGORIES), 2, axis=0)
+            seg_onehot_feed = Tool.OnehotEncode(np.repeat(seg, 2, axis=0), 50)
+            loss_mb, _, _, _, Z_prob_mb = self.train_batch(data_feed, label_onehot_feed, seg_onehot_feed,
+                                                           np.repeat(mask, 2, axis=0))
+            pred = np.stack([self._restrict_to_category(Z_prob_mb[2 * b_i],
+                                                        Loader.object2setofoid[Loader.objcats[label[b_i, 0]]])
+                             for b_i in range(mb_size)])
+            avg_loss = (avg_loss * data_cnt + loss_mb * mb_size) / (data_cnt + mb_size)
+            avg_acc = (avg_acc * data_cnt + float(np.mean(pred == seg)) * mb_size) / (data_cnt + mb_size)
+            data_cnt += mb_size
+            print('\rBatch {:d} TrainedSamp {:d}  Avg Loss {:.4f} Avg Acc {:.2f}%'.format(batch_cnt, data_cnt, avg_loss,
+                                                                                         100 * avg_acc), end='')
+            batch_cnt += 1
+        self.epoch += 1
+        return avg_loss, avg_acc
+
+    def EvalOneEpoch_Full(self, Loader, Eval):
+        """Validation pass (ShapeNet_DGCNN_trainer.py:417-507): short batches are padded with sample 0, every sample is
+        duplicated to fill the Siamese graph, Is_Training=False, Z_prob[0::2] is scored with Eval.EvalIoU over the part ids
+        of the shape's category.  Returns (avg_loss, avg_acc, perdata_miou, pershape_miou)."""
+        data_cnt = 0
+        shape_cnt = np.zeros(Loader.NUM_CATEGORIES)
+        pershape_miou = np.zeros(Loader.NUM_CATEGORIES)
+        avg_loss = avg_acc = perdata_miou = 0.
+        while True:
+            SuccessFlag, data, label, seg, _, mb_size, _, _ = Loader.NextBatch_ValSet()
+            if not SuccessFlag:
+                break
+            data = np.asarray(data, np.float32)
+            label = np.asarray(label).astype(np.int64).reshape(mb_size, -1)
+            seg = np.asarray(seg).astype(np.int64)
+            pad = self.BATCH_SIZE - mb_size
+            if pad > 0:
+                data_f = np.concatenate([data, np.repeat(data[0:1], pad, 0)], 0)
+                seg_f = np.concatenate([seg, np.repeat(seg[0:1], pad, 0)], 0)
+                label_f = np.concatenate([label, np.repeat(label[0:1], pad, 0)], 0)
+            else:
+                data_f, seg_f, label_f = data, seg, label
+            N = data_f.shape[1]
+            loss_mb, Z_prob_mb = self.eval_batch(np.repeat(data_f, 2, axis=0),
+                                                 np.repeat(Tool.OnehotEncode(label_f[:, 0], Loader.NUM_CATEGORIES), 2, axis=0),
+                                                 Tool.OnehotEncode(np.repeat(seg_f, 2, axis=0), 50),
+                                                 np.ones((2 * data_f.shape[0], N), np.float32))
+            Z_prob_mb = Z_prob_mb[0:2 * mb_size:2]
+            for b_i in range(mb_size):
+                shape_label = int(label[b_i, 0])
+                iou_oids = Loader.object2setofoid[Loader.objcats[shape_label]]
+                pred = self._restrict_to_category(Z_prob_mb[b_i], iou_oids)
+                avg_iou = Eval.EvalIoU(pred, seg[b_i], iou_oids)
+                perdata_miou = (perdata_miou * data_cnt + avg_iou) / (data_cnt + 1)
+                pershape_miou[shape_label] = (pershape_miou[shape_label] * shape_cnt[shape_label] + avg_iou) / \
+                    (shape_cnt[shape_label] + 1)
+                avg_acc = (avg_acc * data_cnt + float(np.mean(pred == seg[b_i]))) / (data_cnt + 1)
+                avg_loss = (avg_loss * data_cnt + loss_mb) / (data_cnt + 1)
+                data_cnt += 1
+                shape_cnt[shape_label] += 1
+        return avg_loss, avg_acc, perdata_miou, pershape_miou
+
