@@ -835,17 +835,19 @@ template <int AMODE, int GMODE, int MINB, bool FUSE>
 __global__ void __launch_bounds__(TC_THREADS, MINB)
 colgemm_tc_kernel(const Operand A, const Operand G, long long M, long long rows_per_slab, int K1p, int K2p, int K2t,
                   float* __restrict__ partial, float* __restrict__ partial_b, int tmem_cols, int genA, int genG,
-                  int aGroups, const FuseArgs F) {
+                  int aGroups, int RT, const FuseArgs F) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int gGroups = K2t / 8;                         // power of two, <= 32
+  // RT = rows per tile (the K extent of one accumulation step): 128, or 64 when that lets two CTAs share an SM
+  const int agb = RT * 16 + 16;                        // bytes of one 8-channel group of a row-tile image
   // A images: aGroups = 8 when the operand has <= 64 channels (the M=128 MMA then also reads the 8 groups that follow --
   // the lo image / the dY image -- into accumulator lanes 64..127, which are never stored), else 16
   unsigned char* sAhi = smem;
-  unsigned char* sAlo = sAhi + (size_t)aGroups * A_GROUP_BYTES;
-  unsigned char* sGhi = sAlo + (size_t)aGroups * A_GROUP_BYTES;
-  unsigned char* sGlo = sGhi + (size_t)gGroups * A_GROUP_BYTES;
+  unsigned char* sAlo = sAhi + (size_t)aGroups * agb;
+  unsigned char* sGhi = sAlo + (size_t)aGroups * agb;
+  unsigned char* sGlo = sGhi + (size_t)gGroups * agb;
   const int w_group_bytes = FUSE ? F.Nf * 16 + 16 : 0;                  // fused data gradient: resident weight image
-  unsigned char* sWhi = sGlo + (size_t)gGroups * A_GROUP_BYTES;
+  unsigned char* sWhi = sGlo + (size_t)gGroups * agb;
   unsigned char* sWlo = sWhi + (size_t)gGroups * w_group_bytes;
   unsigned char* misc = sWlo + (size_t)gGroups * w_group_bytes;
   float* stage = reinterpret_cast<float*>(sAhi);                        // epilogue staging aliases the A images
@@ -854,7 +856,7 @@ colgemm_tc_kernel(const Operand A, const Operand G, long long M, long long rows_
   float* bred = reinterpret_cast<float*>(misc + 32);   // [K2t] bias-gradient reduction
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int k1_0 = blockIdx.y * TILE_M, k2_0 = blockIdx.z * 256;
+  const int k1_0 = blockIdx.y * 128 /*channels per dW tile = MMA M*/, k2_0 = blockIdx.z * 256;
   const long long r_begin = (long long)blockIdx.x * rows_per_slab;
   const long long r_end = (r_begin + rows_per_slab < M) ? r_begin + rows_per_slab : M;
 
@@ -904,7 +906,7 @@ colgemm_tc_kernel(const Operand A, const Operand G, long long M, long long rows_
   bool pending = false;
   const uint64_t a_inv = (AMODE == OP_EDGE) ? rowmap_inv(A.k) : 0;
   const uint64_t g_inv = (GMODE == OP_DY_MAXK) ? rowmap_inv(G.k) : 0;
-  for (long long rb = r_begin; rb < r_end; rb += TILE_M) {
+  for (long long rb = r_begin; rb < r_end; rb += RT) {
     if (pending) { mbar_wait(mma_bar, phase); phase ^= 1; pending = false; }   // MMAs done reading smem
     RowMap arm, grm;
     CloudMap gcm;
@@ -915,7 +917,7 @@ colgemm_tc_kernel(const Operand A, const Operand G, long long M, long long rows_
     constexpr int UB = 4;
     if (!genA) {
 #pragma unroll 1
-      for (int rbase = rA0; rbase < TILE_M; rbase += 16 * UB) {
+      for (int rbase = rA0; rbase < RT; rbase += 16 * UB) {
         long long pt[UB], cb[UB], nb[UB];
         bool ok[UB];
 #pragma unroll
@@ -939,38 +941,38 @@ colgemm_tc_kernel(const Operand A, const Operand G, long long M, long long rows_
           uint4 hi, lo;
           split8(v, hi, lo);
           if (wA) {
-            *reinterpret_cast<uint4*>(sAhi + (size_t)gA * A_GROUP_BYTES + r * 16) = hi;
-            *reinterpret_cast<uint4*>(sAlo + (size_t)gA * A_GROUP_BYTES + r * 16) = lo;
+            *reinterpret_cast<uint4*>(sAhi + (size_t)gA * agb + r * 16) = hi;
+            *reinterpret_cast<uint4*>(sAlo + (size_t)gA * agb + r * 16) = lo;
           }
         }
       }
     } else {
 #pragma unroll 2
-      for (int r = rA0; r < TILE_M; r += 16) {
+      for (int r = rA0; r < RT; r += 16) {
         const long long row = rb + r;
         float v[8];
         load_chunk<AMODE>(A, row, cA, vA && row < r_end, a0, a1, a2, v, true);
         uint4 hi, lo;
         split8(v, hi, lo);
         if (wA) {
-          *reinterpret_cast<uint4*>(sAhi + (size_t)gA * A_GROUP_BYTES + r * 16) = hi;
-          *reinterpret_cast<uint4*>(sAlo + (size_t)gA * A_GROUP_BYTES + r * 16) = lo;
+          *reinterpret_cast<uint4*>(sAhi + (size_t)gA * agb + r * 16) = hi;
+          *reinterpret_cast<uint4*>(sAlo + (size_t)gA * agb + r * 16) = lo;
         }
       }
     }
     if (!genG) {
-      // dY operand: TILE_M / rGstep chunks per thread (4, 8 or 16; 2 when K2t = 16), same batching
+      // dY operand: RT / rGstep chunks per thread (4, 8 or 16; 2 when K2t = 16), same batching
 #pragma unroll 1
-      for (int rbase = rG0; rbase < TILE_M; rbase += rGstep * UB) {
+      for (int rbase = rG0; rbase < RT; rbase += rGstep * UB) {
         long long pt[UB], cb[UB];
         bool ok[UB];
 #pragma unroll
         for (int u = 0; u < UB; ++u) {
           const int r = rbase + rGstep * u;
-          ok[u] = vG && r < TILE_M && rb + r < r_end;
+          ok[u] = vG && r < RT && rb + r < r_end;
           pt[u] = 0; cb[u] = 0;
           if (GMODE == OP_DY_SPARSE) cloudmap_point(gcm, r, pt[u], cb[u]);
-          if (GMODE == OP_DY_MAXK && r < TILE_M) rowmap_point(grm, r, pt[u], cb[u]);
+          if (GMODE == OP_DY_MAXK && r < RT) rowmap_point(grm, r, pt[u], cb[u]);
         }
         RawChunk w[UB];
 #pragma unroll
@@ -978,21 +980,21 @@ colgemm_tc_kernel(const Operand A, const Operand G, long long M, long long rows_
 #pragma unroll
         for (int u = 0; u < UB; ++u) {
           const int r = rbase + rGstep * u;
-          if (r < TILE_M) {
+          if (r < RT) {
             float v[8];
             finish_chunk<GMODE>(G, rb + r, cG, ok[u], pt[u], cb[u], g0, g1, g2, w[u], v);
 #pragma unroll
             for (int i = 0; i < 8; ++i) bs[i] += v[i];
             uint4 hi, lo;
             split8(v, hi, lo);
-            *reinterpret_cast<uint4*>(sGhi + (size_t)gG * A_GROUP_BYTES + r * 16) = hi;
-            *reinterpret_cast<uint4*>(sGlo + (size_t)gG * A_GROUP_BYTES + r * 16) = lo;
+            *reinterpret_cast<uint4*>(sGhi + (size_t)gG * agb + r * 16) = hi;
+            *reinterpret_cast<uint4*>(sGlo + (size_t)gG * agb + r * 16) = lo;
           }
         }
       }
     } else {
 #pragma unroll 2
-      for (int r = rG0; r < TILE_M; r += rGstep) {
+      for (int r = rG0; r < RT; r += rGstep) {
         const long long row = rb + r;
         float v[8];
         load_chunk<GMODE>(G, row, cG, vG && row < r_end, g0, g1, g2, v, true);
@@ -1000,8 +1002,8 @@ colgemm_tc_kernel(const Operand A, const Operand G, long long M, long long rows_
         for (int i = 0; i < 8; ++i) bs[i] += v[i];
         uint4 hi, lo;
         split8(v, hi, lo);
-        *reinterpret_cast<uint4*>(sGhi + (size_t)gG * A_GROUP_BYTES + r * 16) = hi;
-        *reinterpret_cast<uint4*>(sGlo + (size_t)gG * A_GROUP_BYTES + r * 16) = lo;
+        *reinterpret_cast<uint4*>(sGhi + (size_t)gG * agb + r * 16) = hi;
+        *reinterpret_cast<uint4*>(sGlo + (size_t)gG * agb + r * 16) = lo;
       }
     }
     fence_proxy_async_smem();
@@ -1014,10 +1016,10 @@ colgemm_tc_kernel(const Operand A, const Operand G, long long M, long long rows_
       for (int pass = 0; pass < 3; ++pass) {
         const uint32_t ab = (pass == 1) ? al : ah;
         const uint32_t gb = (pass == 2) ? gl : gh;
-        for (int j = 0; j < TILE_M / 16; ++j) {
-          // rows 16j..16j+15 = one K=16 slice: k-groups of 8 rows are 128 B apart, channel groups A_GROUP_BYTES apart
-          const uint64_t ad = umma_desc(ab + (uint32_t)j * 256, 128, A_GROUP_BYTES);
-          const uint64_t gd = umma_desc(gb + (uint32_t)j * 256, 128, A_GROUP_BYTES);
+        for (int j = 0; j < RT / 16; ++j) {
+          // rows 16j..16j+15 = one K=16 slice: k-groups of 8 rows are 128 B apart, channel groups agb apart
+          const uint64_t ad = umma_desc(ab + (uint32_t)j * 256, 128, agb);
+          const uint64_t gd = umma_desc(gb + (uint32_t)j * 256, 128, agb);
           tc_mma_bf16(tmem_base, ad, gd, idesc, accum);
           accum = 1;
         }
@@ -1030,7 +1032,7 @@ colgemm_tc_kernel(const Operand A, const Operand G, long long M, long long rows_
           const uint32_t gb = (pass == 1) ? gl : gh;
           const uint32_t wb = (pass == 2) ? wl : wh;
           for (int kk = 0; kk < gGroups / 2; ++kk) {
-            const uint64_t ad = umma_desc(gb + (uint32_t)(2 * kk) * A_GROUP_BYTES, A_GROUP_BYTES, 128);
+            const uint64_t ad = umma_desc(gb + (uint32_t)(2 * kk) * agb, agb, 128);
             const uint64_t bd = umma_desc(wb + (uint32_t)(2 * kk) * w_group_bytes, w_group_bytes, 128);
             tc_mma_bf16(tmem_base + (uint32_t)K2t, ad, bd, idesc_f, acc2);
             acc2 = 1;
@@ -1164,18 +1166,22 @@ int launch_wgrad_tc(const Operand& A, const Operand& G, long long M, int S, int 
   // <= 64 operand channels: 8-group A images, provided the 16 groups an M=128 MMA reads from each image base stay inside
   // the A + dY region (2*8 + 2*(K2t/8) >= 24 groups) and the fused epilogue's staging tile fits in it
   const int aGroups = (A.C <= 64 && K2t >= 32) ? 8 : 16;
-  const size_t smem = (size_t)(2 * aGroups + 2 * (K2t / 8)) * A_GROUP_BYTES + wimg + 32 + (size_t)K2t * 4 + 64;
+  auto smem_for = [&](int rt) { return (size_t)(2 * aGroups + 2 * (K2t / 8)) * (rt * 16 + 16) + wimg + 32 + (size_t)K2t * 4 + 64; };
+  // 64-row tiles when the 128-row images would leave one CTA (8 warps) per SM: the kernel is latency-bound on its loads
+  static const bool rt64 = []() { const char* e = getenv("WSPC_WGRAD_RT"); return !(e && strcmp(e, "128") == 0); }();
+  const int RT = (rt64 && !FUSE && smem_for(128) > 110 * 1024 && smem_for(64) <= 110 * 1024) ? 64 : 128;
+  const size_t smem = smem_for(RT);
   long long rps = (M + S - 1) / S;
   rps = (rps + TILE_M - 1) / TILE_M * TILE_M;
   dim3 grid(S, t1, t2);
   if (smem <= 110 * 1024) {
     auto kern = colgemm_tc_kernel<AMODE, GMODE, 2, FUSE>;
     WSPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, TC_THREADS, smem, st>>>(A, G, M, rps, K1p, K2p, K2t, partial, partial_b, tmem_cols, genA, genG, aGroups, F);
+    kern<<<grid, TC_THREADS, smem, st>>>(A, G, M, rps, K1p, K2p, K2t, partial, partial_b, tmem_cols, genA, genG, aGroups, RT, F);
   } else {
     auto kern = colgemm_tc_kernel<AMODE, GMODE, 1, FUSE>;
     WSPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, TC_THREADS, smem, st>>>(A, G, M, rps, K1p, K2p, K2t, partial, partial_b, tmem_cols, genA, genG, aGroups, F);
+    kern<<<grid, TC_THREADS, smem, st>>>(A, G, M, rps, K1p, K2p, K2t, partial, partial_b, tmem_cols, genA, genG, aGroups, RT, F);
   }
   count_launch();
   WSPC_LAUNCH_CHECK("colgemm_tc_kernel");
