@@ -164,3 +164,25 @@ def test_shapenet_trainer_epoch_loops(cuda):
     # validation with a short last batch (padded with sample 0, :434-441)
     vloss, vacc, perdata, pershape = tr.EvalOneEpoch_Full(FakeShapeNetLoader(2, bs, N, seed=32, last_short=True), Eval())
     assert np.isfinite(vloss) and 0.0 <= vacc <= 1.0 and 0.0 <= perdata <= 1.0 and pershape.shape == (16,)
+
+
+def test_shapenet_trainer_test_time_label_propagation(cuda):
+    """ShapeNet_Trainer.Test: one shape per call (NextSamp_TestSet), resampled to the graph's point count, LP with RGB := XYZ."""
+    from weaksuppointcloudseg_b200.ShapeNet_DGCNN_trainer import ShapeNet_Trainer
+    from weaksuppointcloudseg_b200.Evaluation import Eval
+
+    class OneShapeLoader(FakeShapeNetLoader):
+        def NextSamp_TestSet(self):
+            o = self._next()
+            if not o[0]:
+                return o
+            n0 = 200                                            # fewer points than the graph: resampled with replacement
+            return (True, o[1][:, :n0], o[2], o[3][:, :n0], None, 1, o[6], o[7])
+
+    N = 256
+    tr = ShapeNet_Trainer(device=cuda, seed=6)
+    tr.SetLearningRate(1e-3, 1)
+    tr.defineNetwork(1, point_num=N, style='Full', rampup=0)      # the reference builds its test graph with batch 1
+    tr.defLabelPropSolver()
+    loss, acc, perdata, pershape = tr.Test(OneShapeLoader(3, 1, N, seed=41), Eval())
+    assert np.isfinite(loss) and 0.0 <= acc <= 1.0 and 0.0 <= perdata <= 1.0 and pershape.shape == (16,)

@@ -184,3 +184,48 @@ class ShapeNet_Trainer(S3DIS_Trainer):
                 shape_cnt[shape_label] += 1
         return avg_loss, avg_acc, perdata_miou, pershape_miou
 
+    def Test(self, Loader, Eval, style='Full'):
+        """Test-time pass with label propagation (ShapeNet_DGCNN_trainer.py:511-596): one shape at a time
+        (`Loader.NextSamp_TestSet`), resampled with replacement to the graph's point count (:531-534), inference
+        (Is_Training=False), the symmetric Laplacian with RGB := XYZ (:551) and the closed-form LP solve on the device;
+        the propagated probabilities of the ORIGINAL points are scored.  The graph is the one built by defineNetwork
+        (the reference builds it with batch 1, 3000 points); a larger graph batch is filled with copies."""
+        from . import ops
+        eng = self.engine
+        data_cnt = 0
+        shape_cnt = np.zeros(Loader.NUM_CATEGORIES)
+        pershape_miou = np.zeros(Loader.NUM_CATEGORIES)
+        avg_loss = avg_acc = perdata_miou = 0.
+        rng = np.random.default_rng(0)
+        while True:
+            SuccessFlag, data, label, seg, _, mb_size, _, _ = Loader.NextSamp_TestSet()
+            if not SuccessFlag:
+                break
+            data = np.asarray(data, np.float32)
+            label = np.asarray(label).astype(np.int64).reshape(mb_size, -1)
+            seg = np.asarray(seg).astype(np.int64)
+            n0 = data.shape[1]
+            assert mb_size == 1 and n0 <= eng.N, "Test feeds one shape of at most num_point points per call (:524-534)"
+            idx = np.concatenate([np.arange(n0), rng.choice(n0, eng.N - n0, replace=True)]).astype(np.int64)
+            data_feed = np.repeat(data[:, idx, :], eng.B, axis=0)
+            seg_feed = np.repeat(seg[:, idx], eng.B, axis=0)
+            label_feed = np.repeat(Tool.OnehotEncode(label[:, 0], Loader.NUM_CATEGORIES), eng.B, axis=0)
+            loss_mb, _ = self.eval_batch(data_feed, label_feed, Tool.OnehotEncode(seg_feed, 50),
+                                         np.ones((eng.B, eng.N), np.float32))
+            X0 = eng.X[0:1].contiguous()
+            Lm = ops.laplacian_sym(X0, X0)                                       # (:551)
+            _, Yp, _ = ops.lp_solve(Lm[0], eng.Zp[0].contiguous(), 1.0, 1.0)     # (:552)
+            Z_prob = Yp[:n0].cpu().numpy()
+            shape_label = int(label[0, 0])
+            iou_oids = Loader.object2setofoid[Loader.objcats[shape_label]]
+            pred = self._restrict_to_category(Z_prob, iou_oids)
+            avg_iou = Eval.EvalIoU(pred, seg[0], iou_oids)
+            perdata_miou = (perdata_miou * data_cnt + avg_iou) / (data_cnt + 1)
+            pershape_miou[shape_label] = (pershape_miou[shape_label] * shape_cnt[shape_label] + avg_iou) / \
+                (shape_cnt[shape_label] + 1)
+            avg_acc = (avg_acc * data_cnt + float(np.mean(pred == seg[0]))) / (data_cnt + 1)
+            avg_loss = (avg_loss * data_cnt + loss_mb) / (data_cnt + 1)
+            data_cnt += 1
+            shape_cnt[shape_label] += 1
+        return avg_loss, avg_acc, perdata_miou, pershape_miou
+
