@@ -1,0 +1,97 @@
+"""Loaders: the same call scripts that tests/golden/make_dataio_golden.py ran on the REFERENCE's
+DataIO_S3DIS / DataIO_ShapeNet classes are run on ours, on the same fabricated files and numpy seeds; every returned
+array must be identical.  Plus the HDF5 subset round trip (`_h5`: parity unpinned against libhdf5, see its header)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+
+import dataio_fab as fab  # noqa: E402
+from weaksuppointcloudseg_b200 import _h5  # noqa: E402
+from weaksuppointcloudseg_b200.DataIO_S3DIS import S3DIS_IO, S3DIS_Test  # noqa: E402
+from weaksuppointcloudseg_b200.DataIO_ShapeNet import ShapeNetIO  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(os.path.join(HERE, "golden", "ref_dataio.npz"))
+
+
+def _same(golden, prefix, got):
+    want = {k[len(prefix):]: golden[k] for k in golden.files if k.startswith(prefix)}
+    assert sorted(want) == sorted(got), (sorted(set(want) ^ set(got)))
+    for k, w in want.items():
+        g = np.asarray(got[k])
+        assert g.shape == w.shape, (k, g.shape, w.shape)
+        if w.dtype.kind == 'f':
+            np.testing.assert_allclose(g, w, rtol=0, atol=1e-12, err_msg=k)
+        else:
+            assert np.array_equal(g, w), k
+
+
+def test_h5_round_trip_dtypes_and_ragged_chunks(tmp_path):
+    rng = np.random.default_rng(0)
+    d = {'data': rng.standard_normal((150, 64, 9)).astype(np.float32),
+         'label': rng.integers(0, 13, (150, 64)).astype(np.uint8),
+         'pid': rng.integers(-5, 50, (150, 64)).astype(np.int64),
+         'w': rng.standard_normal(7),
+         'one': np.arange(3, dtype=np.int32).reshape(3, 1)}
+    p = str(tmp_path / 'a.h5')
+    _h5.write(p, d, chunk_rows=64)                               # 150 rows -> 2 full chunks + a ragged one
+    back = _h5.read(p)
+    assert sorted(back) == sorted(d)
+    for k in d:
+        assert back[k].dtype == d[k].dtype and np.array_equal(back[k], d[k]), k
+    with _h5.File(p) as f:                                       # the h5py idiom of the reference's loaders
+        assert f['data'][:].shape == (150, 64, 9) and f['label'].dtype == np.uint8
+
+
+def test_h5_rejects_what_it_does_not_restate(tmp_path):
+    p = str(tmp_path / 'bad.h5')
+    open(p, 'wb').write(b'not hdf5 at all' * 10)
+    with pytest.raises(ValueError):
+        _h5.read(p)
+    blob = bytearray(open(_mk(tmp_path), 'rb').read())
+    blob[8] = 2                                                  # superblock v2 (libver='latest')
+    open(p, 'wb').write(bytes(blob))
+    with pytest.raises(NotImplementedError):
+        _h5.read(p)
+
+
+def _mk(tmp_path):
+    p = str(tmp_path / 'ok.h5')
+    _h5.write(p, {'x': np.arange(10, dtype=np.float32)})
+    return p
+
+
+def test_s3dis_io_matches_reference_loader(tmp_path, golden):
+    got = fab.trace_s3dis_io(S3DIS_IO, fab.make_s3dis(str(tmp_path / 's3dis')))
+    _same(golden, 's3dis_io/', got)
+    assert got['train0.0.3'].shape == (4, 13) and int(got['train0.steps']) == 3   # 11 train blocks = 4 + 4 + 3
+
+
+def test_s3dis_room_to_blocks_matches_reference(tmp_path, golden):
+    root = fab.make_s3dis_room(str(tmp_path / 'rooms'))
+    t = S3DIS_Test('area5', NUM_POINT=128, data_path=root)
+    assert [os.path.basename(p) for p in t.ROOM_PATH_LIST] == ['Area_5_office_1.npy', 'Area_5_office_2.txt']
+    got = fab.trace_s3dis_test(t)
+    _same(golden, 's3dis_test/', got)
+    d = got['room0.data']
+    assert d.shape[1:] == (128, 9) and d[..., 6:9].max() <= 1.0 and abs(d[..., 0]).max() <= 0.5 + 1e-9
+
+
+def test_shapenet_io_matches_reference_loader(tmp_path, golden):
+    got = fab.trace_shapenet(ShapeNetIO, fab.make_shapenet(str(tmp_path / 'shapenet')))
+    _same(golden, 'shapenet/', got)
+    assert int(got['NUM_PART_CATS']) == 8 and int(got['te.steps']) == 2
+
+
+def test_missing_files_are_loud(tmp_path):
+    with pytest.raises(FileNotFoundError):
+        S3DIS_IO(str(tmp_path / 'nowhere'))
+    with pytest.raises(FileNotFoundError):
+        ShapeNetIO(str(tmp_path / 'nowhere'))

@@ -1,83 +1,64 @@
 """The trainer classes as drop-ins: the epoch loops of the reference (`TrainOneEpoch_Full`, `EvalOneEpoch_Full`, `Test`,
 checkpoint save / restore; S3DIS/S3DIS_DGCNN_trainer.py:221-349, :401-497, :499-584, :586-629) driven by loaders that follow
 the reference's loader contracts (DataIO_S3DIS.py:127-154, :288-299) on synthetic blocks."""
+import os
+import sys
+
 import numpy as np
 import pytest
 import torch
 
 from weaksuppointcloudseg_b200 import synthetic as syn
 
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+import dataio_fab as fab  # noqa: E402
+
 pytestmark = pytest.mark.gpu
 
 
-class FakeTrainLoader:
-    """S3DIS_IO.NextBatch_TrainSet_v1 / NextBatch_ValSet contract: (flag, data, seg, weak_seg_onehot, mb_size, data_idx)."""
-
-    def __init__(self, n_batches, bs, N, seed):
-        self.n, self.bs, self.N, self.i = n_batches, bs, N, 0
-        X, _, _, seg = syn.s3dis_batch(n_batches * bs, N=N, n_labelled=8, seed=seed)
-        self.X, self.seg = X[0::2], seg[0::2]                    # originals only; the trainer builds the Siamese partner
-
-    def _next(self):
-        if self.i >= self.n:
-            return None
-        lo = self.i * self.bs
-        self.i += 1
-        return self.X[lo:lo + self.bs], self.seg[lo:lo + self.bs], np.arange(lo, lo + self.bs)
-
-    def NextBatch_TrainSet_v1(self):
-        o = self._next()
-        if o is None:
-            return False, None, None, None, 0, None
-        return True, o[0], o[1], None, self.bs, o[2]
-
-    def NextBatch_ValSet(self):
-        o = self._next()
-        if o is None:
-            return False, None, None, None, 0
-        return True, o[0], o[1], None, self.bs
-
-
-class FakeTestLoader:
-    """S3DIS_Test.LoadNextTestRoomData_v1 contract: (flag, blocks (nb,N,9), labels (nb,N))."""
-
-    def __init__(self, rooms, nb, N):
-        self.rooms, self.nb, self.N, self.i = rooms, nb, N, 0
-
-    def LoadNextTestRoomData_v1(self):
-        if self.i >= self.rooms:
-            return False, None, None
-        X, _, _, seg = syn.s3dis_batch(self.nb, N=self.N, n_labelled=8, seed=900 + self.i)
-        self.i += 1
-        return True, X[0::2], seg[0::2]
+def _s3dis_loader(tmp_path, bs, N):
+    """The real S3DIS_IO on a fabricated h5 dataset: 13 blocks, 2 of them in Area_5 (the test split)."""
+    from weaksuppointcloudseg_b200.DataIO_S3DIS import S3DIS_IO
+    ld = S3DIS_IO(fab.make_s3dis(str(tmp_path / 's3dis'), n_point=N), 13, batchsize=bs, NUM_POINT=N)
+    ld.LoadS3DIS_AllData()
+    ld.CreateDataSplit(5)
+    ld.ResetLoader_TrainSet()
+    return ld
 
 
 def test_s3dis_trainer_epoch_loops_and_checkpoint(cuda, tmp_path):
+    """train_S3DIS.py's call sequence (:52-140) with the reference's positional arguments and return arities."""
     from weaksuppointcloudseg_b200.S3DIS_DGCNN_trainer import S3DIS_Trainer
     bs, N = 2, 256
-    tr = S3DIS_Trainer(test_area=5, device=cuda, seed=3)
-    tr.SetLearningRate(1e-3, bs)
-    tr.defineNetwork(2 * bs, N, style='Full', rampup=0)
-    pts_idx = [np.random.default_rng(i).choice(N, 8, replace=False) for i in range(3 * bs)]
+    Loader = _s3dis_loader(tmp_path, bs, N)
+    tr = S3DIS_Trainer(5, device=cuda, seed=3)
+    tr.SetLearningRate(LearningRate=1e-3, BatchSize=bs)
+    tr.defineNetwork(batch_size=2 * bs, num_points=N, style='Full', rampup=0)
+    pts_idx_list = np.stack([np.random.default_rng(i).choice(N, 8, replace=False) for i in range(13)])
     w0 = tr.engine.vs.theta.clone()
-    loss, acc = tr.TrainOneEpoch_Full(FakeTrainLoader(3, bs, N, seed=5), pts_idx)
+    np.random.seed(0)
+    Loader.Shuffle_TrainSet()
+    loss, acc = tr.TrainOneEpoch_Full(Loader, pts_idx_list, bs)
     assert np.isfinite(loss) and 0.0 <= acc <= 1.0
-    assert tr.epoch == 1 and tr.batch == 3                          # global step advanced once per mini-batch (:110)
+    assert tr.epoch == 1 and tr.batch == 5            # 11 train blocks: 5 full mini-batches, the short one dropped (:242)
+    assert Loader.train_samp_ptr == 0                 # the loop resets the loader (:343)
     assert float((tr.engine.vs.theta - w0).abs().max()) > 0
-    vloss, vacc, miou, iou = tr.EvalOneEpoch_Full(FakeTrainLoader(2, bs, N, seed=6))
-    assert np.isfinite(vloss) and 0.0 <= vacc <= 1.0 and iou.shape == (13,) and 0.0 <= miou <= 1.0
-    # checkpoint round trip: variables under their TF names, global step, Adam slots
-    path = str(tmp_path / "Checkpoint_epoch-1")
-    tr.SaveCheckPoint(path)
+    vloss, vacc, miou = tr.EvalOneEpoch_Full(Loader)  # 2 Area_5 blocks = one full batch
+    assert np.isfinite(vloss) and 0.0 <= vacc <= 1.0 and 0.0 <= miou <= 1.0 and tr.eval_iou.shape == (13,)
+    assert Loader.test_samp_ptr == 0
+    # checkpoint round trip: variables under their TF names, global step, Adam slots; best copy next to it (:586-624)
+    path = str(tmp_path / "ck" / "Checkpoint_epoch-0")
+    tr.SaveCheckPoint(path, 'Checkpoint_epoch-best', miou + 0.5)
+    assert (tmp_path / "ck" / "Checkpoint_epoch-best.npz").exists() and tr.bestValCorrect == miou + 0.5
     blob = np.load(path + ".npz")
     assert "adj_conv1/weights" in blob.files and "seg/conv3/biases" in blob.files and "adj_conv7/bn/pop_mean" in blob.files
-    assert int(blob["Variable"]) == 3
-    tr2 = S3DIS_Trainer(test_area=5, device=cuda, seed=99)
+    assert int(blob["Variable"]) == 5
+    tr2 = S3DIS_Trainer(5, device=cuda, seed=99)
     tr2.SetLearningRate(1e-3, bs)
     tr2.defineNetwork(2 * bs, N, style='Full', rampup=0)
     tr2.RestoreCheckPoint(path)
     assert torch.equal(tr2.engine.vs.theta, tr.engine.vs.theta) and torch.equal(tr2.engine.vs.state, tr.engine.vs.state)
-    assert tr2.batch == 3
+    assert tr2.batch == 5
     # same input -> same inference logits after the restore
     X, Y, M, _ = syn.s3dis_batch(bs, N=N, n_labelled=8, seed=7)
     l1, z1 = tr.eval_batch(X, Y, M)
@@ -85,16 +66,42 @@ def test_s3dis_trainer_epoch_loops_and_checkpoint(cuda, tmp_path):
     assert l1 == l2 and np.array_equal(z1, z2)
 
 
-def test_s3dis_trainer_test_time_label_propagation(cuda):
+def test_s3dis_plain_style_epoch_loops(cuda, tmp_path):
+    """-sty Plain: TrainOneEpoch / EvalOneEpoch (train_S3DIS.py:116-129) on a graph of `batchsize` clouds."""
+    from weaksuppointcloudseg_b200.S3DIS_DGCNN_trainer import S3DIS_Trainer
+    bs, N = 4, 256
+    Loader = _s3dis_loader(tmp_path, bs, N)
+    tr = S3DIS_Trainer(5, device=cuda, seed=8)
+    tr.SetLearningRate(1e-3, bs)
+    tr.defineNetwork(batch_size=bs, num_points=N, style='Plain', rampup=101)
+    pts_idx_list = np.stack([np.random.default_rng(i).choice(N, 8, replace=False) for i in range(13)])
+    Loader.Shuffle_TrainSet()
+    loss, acc = tr.TrainOneEpoch(Loader, pts_idx_list, bs)
+    assert np.isfinite(loss) and 0.0 <= acc <= 1.0 and tr.batch == 2       # 11 blocks -> 2 full batches of 4
+    vloss, vacc, miou = tr.EvalOneEpoch(Loader)                            # 2 test blocks: padded to 4 with block 0
+    assert np.isfinite(vloss) and 0.0 <= vacc <= 1.0 and 0.0 <= miou <= 1.0
+
+
+def test_s3dis_trainer_test_time_label_propagation(cuda, tmp_path):
+    """test_S3DIS.py's sequence (:60-97): S3DIS_Test rooms -> blocks, batch-1 graph, LP, per-room .mat, three counters."""
+    import scipy.io as scio
+    from weaksuppointcloudseg_b200.DataIO_S3DIS import S3DIS_Test
     from weaksuppointcloudseg_b200.S3DIS_DGCNN_trainer import S3DIS_Trainer
     N = 256
-    tr = S3DIS_Trainer(test_area=5, device=cuda, seed=4)
+    np.random.seed(1)
+    Loader = S3DIS_Test('area5', NUM_POINT=N, data_path=fab.make_s3dis_room(str(tmp_path / 'rooms')))
+    tr = S3DIS_Trainer(5, device=cuda, seed=4)
     tr.SetLearningRate(1e-3, 1)
-    tr.defineNetwork(2, N, style='Full', rampup=0)
+    tr.defineNetwork(batch_size=1, num_points=N, style='Plain', rampup=101)
     tr.defLabelPropSolver()
-    res = tr.Test(FakeTestLoader(rooms=2, nb=2, N=N))
-    for key in ('net', 'lp'):
-        assert 0.0 <= res[key]['acc'] <= 1.0 and res[key]['iou'].shape == (13,) and 0.0 <= res[key]['miou'] <= 1.0
+    pred_path = tmp_path / 'Prediction'
+    pred_path.mkdir()
+    tp, pos, gt = tr.Test(Loader, str(pred_path))
+    assert tp.shape == pos.shape == gt.shape == (13,)
+    assert pos.sum() == gt.sum() and gt.sum() % N == 0 and np.all(tp <= np.minimum(pos, gt))
+    m = scio.loadmat(str(pred_path / 'Area_5_office_1_pred_gt.mat'))
+    assert m['pred'].size == m['gt'].size == m['data'].shape[0] * N and (pred_path / 'Area_5_office_2_pred_gt.mat').exists()
+    assert sum(c.sum() for c in tr.test_stats_net[1:]) == 2 * gt.sum()      # network-only counters saw the same points
 
 
 def test_plain_style_and_closed_rampup_gate(cuda):
@@ -186,3 +193,39 @@ def test_shapenet_trainer_test_time_label_propagation(cuda):
     tr.defLabelPropSolver()
     loss, acc, perdata, pershape = tr.Test(OneShapeLoader(3, 1, N, seed=41), Eval())
     assert np.isfinite(loss) and 0.0 <= acc <= 1.0 and 0.0 <= perdata <= 1.0 and pershape.shape == (16,)
+
+
+def test_shapenet_trainer_with_the_real_loader(cuda, tmp_path):
+    """train_ShapeNet.py's sequence (:45-142) on a fabricated hdf5_data directory: ShapeNetIO -> Full and Plain loops."""
+    from weaksuppointcloudseg_b200.DataIO_ShapeNet import ShapeNetIO
+    from weaksuppointcloudseg_b200.ShapeNet_DGCNN_trainer import ShapeNet_Trainer
+    from weaksuppointcloudseg_b200.Evaluation import Eval
+    bs, N = 2, 256
+    Loader = ShapeNetIO(fab.make_shapenet(str(tmp_path / 'shapenet'), n_point=N), batchsize=bs)
+    Loader.LoadTrainValFiles()
+    n_train = Loader.num_train                                                # 11 shapes
+    file_idx_list, data_idx_list = np.zeros(n_train, np.int64), np.arange(n_train)
+    pts_idx_list = np.stack([np.random.default_rng(i).choice(N, 16, replace=False) for i in range(n_train)])
+    for style, nb in (('Full', 2 * bs), ('Plain', bs)):
+        tr = ShapeNet_Trainer(device=cuda, seed=12)
+        tr.SetLearningRate(LearningRate=1e-3, BatchSize=bs)
+        tr.defineNetwork(batch_size=nb, point_num=N, style=style, rampup=0)
+        np.random.seed(3)
+        Loader.Shuffle_TrainSet()
+        if style == 'Full':
+            loss, acc = tr.TrainOneEpoch_Full(Loader, file_idx_list, data_idx_list, pts_idx_list)
+            out = tr.EvalOneEpoch_Full(Loader, Eval())
+        else:
+            loss, acc = tr.TrainOneEpoch(Loader, file_idx_list, data_idx_list, pts_idx_list)
+            out = tr.EvalOneEpoch(Loader, Eval())
+        assert np.isfinite(loss) and 0.0 <= acc <= 1.0 and tr.batch == 5      # 11 shapes: 5 full batches, tail skipped
+        vloss, vacc, perdata, pershape = out
+        assert np.isfinite(vloss) and 0.0 <= vacc <= 1.0 and 0.0 <= perdata <= 1.0 and pershape.shape == (16,)
+    # test_ShapeNet.py: one .pts/.seg shape per call, batch-1 graph
+    Loader.LoadTestFiles()
+    tr = ShapeNet_Trainer(device=cuda, seed=13)
+    tr.SetLearningRate(BatchSize=1)
+    tr.defineNetwork(batch_size=1, point_num=64, style='Plain')
+    tr.defLabelPropSolver()
+    loss, acc, perdata, pershape = tr.Test(Loader, Eval(), 'Full')
+    assert np.isfinite(loss) and 0.0 <= acc <= 1.0 and 0.0 <= perdata <= 1.0

@@ -213,129 +213,208 @@ class S3DIS_Trainer():
         self.TFComp = {}
         self.TFComp['Lmat'] = Tool.TF_Computation.LaplacianMatSym_XYZRGB_DirectComp()
 
+    # ------------------------------------------------------------------ test rooms (:499-584) ----
+    @staticmethod
+    def _count_classes(pred, gt, C, positive, true_positive, gt_count):
+        """The reference's per-point python counters (:473-477, :552-555) as three bincounts."""
+        pred, gt = np.asarray(pred).reshape(-1).astype(np.int64), np.asarray(gt).reshape(-1).astype(np.int64)
+        positive += np.bincount(pred, minlength=C)[:C]
+        gt_count += np.bincount(gt, minlength=C)[:C]
+        true_positive += np.bincount(gt[pred == gt], minlength=C)[:C]
+
     def Test(self, Loader, PRED_PATH=None):
-        """Inference + label propagation over test rooms (Test, :499-584): per block one forward pass
-        (Is_Training=False), the symmetric Laplacian of the block (xyz, rgb) and the closed-form LP solve —
-        all on the device, without the reference's 64 MB D2H/H2D round trip per block.  `Loader` follows
-        S3DIS_Test.LoadNextTestRoomData_v1 (DataIO_S3DIS.py:288-299): returns (flag, blocks (nb,4096,9),
-        labels (nb,4096)).  Returns overall accuracy and per-class IoU with and without LP."""
+        """Inference + label propagation over the test rooms (Test, :499-584).  `Loader` is a DataIO_S3DIS.S3DIS_Test:
+        `LoadNextTestRoomData_v1()` -> (blocks (nb,N,9), labels (nb,N), room_path), blocks None after the last room.
+        Per block: one forward pass (Is_Training=False), the symmetric Laplacian of the block (xyz, rgb) and the
+        closed-form LP solve — all on the device, without the reference's 64 MB D2H/H2D round trip per block.  The
+        LP-propagated prediction is scored; per room `<room>_pred_gt.mat` {data, pred, gt} is written to PRED_PATH (:571-580)
+        when given.  Returns (true_positive_classes, positive_classes, gt_classes) like the reference; the network-only
+        counters (no LP) are kept in `self.test_stats_net`."""
         from . import ops
         eng = self.engine
         C = eng.C
-        stat = {k: dict(tp=np.zeros(C), fp=np.zeros(C), fn=np.zeros(C)) for k in ('net', 'lp')}
+        true_positive_classes, positive_classes, gt_classes = np.zeros(C), np.zeros(C), np.zeros(C)
+        net = [np.zeros(C), np.zeros(C), np.zeros(C)]
+        total_correct = total_seen = 0.
+        room_cnt = 0
+        ones = torch.ones((eng.B, eng.N), device=self.device)
         while True:
-            out = Loader.LoadNextTestRoomData_v1()
-            if not out[0]:
+            data, label, room_path = Loader.LoadNextTestRoomData_v1()
+            if data is None:
                 break
-            blocks, labels = np.asarray(out[1], np.float32), np.asarray(out[2]).astype(np.int64)
+            blocks, labels = np.asarray(data, np.float32), np.asarray(label).astype(np.int64)
+            allPred = []
             for bi in range(blocks.shape[0]):
                 X = torch.from_numpy(blocks[bi:bi + 1]).to(self.device)
                 Xf = X.expand(eng.B, -1, -1).contiguous()              # graph batch is static, like the reference
                 eng.forward(Xf, False, None)
                 Yz = torch.zeros((eng.B, eng.N, C), device=self.device)
-                eng.losses_and_grad(Yz, torch.ones((eng.B, eng.N), device=self.device), full=False, want_grad=False)
+                eng.losses_and_grad(Yz, ones, full=False, want_grad=False)
                 G = eng.Zp[0].contiguous()
                 Lm = ops.laplacian_sym(X[:, :, 0:3].contiguous(), X[:, :, 3:6].contiguous())   # (:543)
                 _, Yp, _ = ops.lp_solve(Lm[0], G, 1.0, 1.0)                                   # (:544)
-                for key, prob in (('net', G), ('lp', Yp)):
-                    pred = prob.argmax(-1).cpu().numpy()
-                    gt = labels[bi]
-                    for c in range(C):                                   # vectorised (:552-555)
-                        stat[key]['tp'][c] += np.sum((pred == c) & (gt == c))
-                        stat[key]['fp'][c] += np.sum((pred == c) & (gt != c))
-                        stat[key]['fn'][c] += np.sum((pred != c) & (gt == c))
-        res = {}
-        for key, s in stat.items():
-            iou = s['tp'] / np.maximum(s['tp'] + s['fp'] + s['fn'], 1)
-            res[key] = dict(acc=float(s['tp'].sum() / max((s['tp'] + s['fn']).sum(), 1)), iou=iou, miou=float(iou.mean()))
-        return res
+                both = torch.stack([Yp.argmax(-1), G.argmax(-1)]).cpu().numpy()
+                pred = both[0]
+                self._count_classes(pred, labels[bi], C, positive_classes, true_positive_classes, gt_classes)
+                self._count_classes(both[1], labels[bi], C, net[1], net[0], net[2])
+                total_correct += float(np.sum(pred == labels[bi]))
+                total_seen += labels[bi].size
+                allPred.append(pred)
+                iou = true_positive_classes / (gt_classes + positive_classes - true_positive_classes + 1e-5)
+                print('\rroom {:d}  acc {:.2f}%  iou: {:.2f}%'.format(room_cnt, 100 * total_correct / total_seen,
+                                                                      100 * np.mean(iou)), end='')
+            if PRED_PATH is not None:
+                import scipy.io as scio
+                room_name = os.path.basename(room_path).split('.')[0]
+                scio.savemat(os.path.join(PRED_PATH, '{}_pred_gt.mat'.format(room_name)),
+                             {'data': data, 'pred': np.concatenate(allPred, 0), 'gt': labels.reshape(-1)})
+            room_cnt += 1
+        self.test_stats_net = tuple(net)
+        return true_positive_classes, positive_classes, gt_classes
 
     # ------------------------------------------------------------------ epoch loops --------------
-    def TrainOneEpoch_Full(self, Loader, pts_idx_list):
-        '''
-        Function to train one epoch (TrainOneEpoch_Full, :221-349).  `Loader` follows the contract of
-        S3DIS_IO.NextBatch_TrainSet_v1 (DataIO_S3DIS.py:127-154); the mini-batch assembly (mask from
-        pts_idx_list, Siamese partner, interleaving, one-hot) is vectorised instead of the per-point loops.
-        '''
-        batch_cnt = 1
-        data_cnt = 0
-        avg_loss = 0.
-        avg_acc = 0.
-        B = self.engine.B
-        rng = np.random.default_rng(self.epoch)
+    @staticmethod
+    def _mask_from_idx(pts_idx_list, data_idx, mb_size, N):
+        """Mask_bin (mb,N): 1 at the labelled points of each sample, all zero without a list (:246-252)."""
+        mask = np.zeros((mb_size, N), np.float32)
+        if pts_idx_list is not None:
+            for b_i in range(mb_size):
+                mask[b_i, np.asarray(pts_idx_list[data_idx[b_i]]).reshape(-1).astype(np.int64)] = 1
+        return mask
+
+    # aug_choice -> (swap x/y, mirror x, mirror y), the eight cases of :265-296
+    _AUG = ((0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1), (0, 1, 1), (1, 1, 0), (1, 0, 1), (1, 1, 1))
+
+    @classmethod
+    def _augment(cls, aug):
+        """One of the 8 axis-swap / mirror augmentations per block, drawn with the reference's `np.random.choice` call.
+        Channels 6:8 (room-normalised xy) follow: swapped with the axes, mirrored as 1 - v."""
+        for b_i in range(aug.shape[0]):
+            swap, mx, my = cls._AUG[int(np.random.choice([0, 1, 2, 3, 4, 5, 6, 7], 1)[0])]
+            blk = aug[b_i]
+            if swap:
+                blk[:, [0, 1, 6, 7]] = blk[:, [1, 0, 7, 6]]
+            if mx:
+                blk[:, 0] = -blk[:, 0]
+                blk[:, 6] = 1 - blk[:, 6]
+            if my:
+                blk[:, 1] = -blk[:, 1]
+                blk[:, 7] = 1 - blk[:, 7]
+        return aug
+
+    def _end_train_epoch(self, Loader):
+        if hasattr(Loader, 'ResetLoader_TrainSet'):
+            Loader.ResetLoader_TrainSet()                # (:213, :343)
+        self.epoch += 1
+
+    def TrainOneEpoch(self, Loader, pts_idx_list=None, batch_size=12):
+        """Plain-style epoch (TrainOneEpoch, :146-219): `batch_size` clouds per step, segmentation loss on the labelled
+        points only.  -> (avg_loss, avg_acc)."""
+        batch_cnt, data_cnt, avg_loss, avg_acc = 1, 0, 0., 0.
         while True:
             SuccessFlag, data, seg, weak_seg_onehot, mb_size, data_idx = Loader.NextBatch_TrainSet_v1()
-            if not SuccessFlag or mb_size < B // 2:      # short last batch is dropped (:242-243)
+            if not SuccessFlag or mb_size < self.engine.B:   # the short last batch is dropped (:167-168); static graph batch
                 break
             data = np.asarray(data, np.float32)
+            seg = np.asarray(seg).astype(np.int64)
+            Mask_bin_feed = self._mask_from_idx(pts_idx_list, data_idx, mb_size, data.shape[1])
+            loss_mb, _, _, _, Z_prob_mb = self.train_batch(data, Tool.OnehotEncode(seg, 13), Mask_bin_feed)
+            acc = float(np.mean(np.argmax(Z_prob_mb, axis=-1) == seg))
+            avg_loss = (avg_loss * data_cnt + loss_mb * mb_size) / (data_cnt + mb_size)
+            avg_acc = (avg_acc * data_cnt + acc * mb_size) / (data_cnt + mb_size)
+            data_cnt += mb_size
+            print('\rBatch {:d} TrainedSamp {:d}  mbLoss {:.4f} Avg Acc {:.2f}%'.format(batch_cnt, data_cnt, loss_mb,
+                                                                                      100 * avg_acc), end='')
+            batch_cnt += 1
+        self._end_train_epoch(Loader)
+        return avg_loss, avg_acc
+
+    def TrainOneEpoch_Full(self, Loader, pts_idx_list=None, batch_size=12):
+        '''
+        Function to train one epoch (TrainOneEpoch_Full, :221-349).  `Loader` follows S3DIS_IO.NextBatch_TrainSet_v1
+        (DataIO_S3DIS.py:127-154); the mini-batch assembly (mask from pts_idx_list, Siamese partner, interleaving, one-hot)
+        is vectorised instead of the per-point loops.  `batch_size` = samples per step (half the graph's clouds).
+        '''
+        batch_cnt, data_cnt, avg_loss, avg_acc = 1, 0, 0., 0.
+        half = self.engine.B // 2
+        while True:
+            SuccessFlag, data, seg, weak_seg_onehot, mb_size, data_idx = Loader.NextBatch_TrainSet_v1()
+            if not SuccessFlag or mb_size < half:        # short last batch dropped (:242-243); the graph batch is static
+                break
+            data = np.asarray(data, np.float32)
+            seg = np.asarray(seg).astype(np.int64)
             N = data.shape[1]
-            mask = np.zeros((mb_size, N), np.float32)
-            for b_i in range(mb_size):                   # (:246-252)
-                mask[b_i, np.asarray(pts_idx_list[data_idx[b_i]]).reshape(-1).astype(np.int64)] = 1
-            aug = data.copy()                            # a true copy (the reference aliases, App. C-2)
-            if self.epoch >= self.rampup:                # host-side augmentation switch (:261)
-                for b_i in range(mb_size):
-                    mode = rng.integers(0, 8)
-                    if mode & 1:
-                        aug[b_i][:, [0, 1]] = aug[b_i][:, [1, 0]]
-                        aug[b_i][:, [6, 7]] = aug[b_i][:, [7, 6]]
-                    if mode & 2:
-                        aug[b_i][:, 0] *= -1
-                    if mode & 4:
-                        aug[b_i][:, 1] *= -1
+            mask = self._mask_from_idx(pts_idx_list, data_idx, mb_size, N)
             data_feed = np.empty((2 * mb_size, N, 9), np.float32)
-            data_feed[0::2], data_feed[1::2] = data, aug
-            seg_feed = np.repeat(np.asarray(seg).astype(np.int64), 2, axis=0)
-            seg_onehot_feed = Tool.OnehotEncode(seg_feed, 13)
+            data_feed[0::2] = data
+            # The partner is an augmented COPY once the ramp-up epoch is reached (:261); the reference augments in place
+            # through an alias, so both rows of its pair end up augmented (SURVEY App. C-2) — consciously not kept.
+            data_feed[1::2] = self._augment(data.copy()) if self.epoch >= self.rampup else data
+            seg_onehot_feed = Tool.OnehotEncode(np.repeat(seg, 2, axis=0), 13)
             Mask_bin_feed = np.repeat(mask, 2, axis=0)
             loss_mb, loss_siam, loss_inex, loss_smooth, Z_prob_mb = self.train_batch(data_feed, seg_onehot_feed,
                                                                                     Mask_bin_feed)
             pred = np.argmax(Z_prob_mb[0::2], axis=-1)   # (:326-339)
-            acc = float(np.mean(pred == np.asarray(seg)))
+            acc = float(np.mean(pred == seg))
             avg_loss = (avg_loss * data_cnt + loss_mb * mb_size) / (data_cnt + mb_size)
             avg_acc = (avg_acc * data_cnt + acc * mb_size) / (data_cnt + mb_size)
             data_cnt += mb_size
-            print('\rBatch {}  loss {:.4f} siam {:.4f} inexact {:.4f} smooth {:.5f} acc {:.3f}'.format(
-                batch_cnt, loss_mb, loss_siam, loss_inex, loss_smooth, acc), end='')
+            print('\rBatch {:d} TrainedSamp {:d}  mbLoss {:.4f} SiamLoss {:.3f} MILLoss {:.3f} SmoothLoss {:.3f} '
+                  'Avg Acc {:.2f}%'.format(batch_cnt, data_cnt, loss_mb, loss_siam, loss_inex, loss_smooth, 100 * avg_acc),
+                  end='')
             batch_cnt += 1
-        self.epoch += 1
+        self._end_train_epoch(Loader)
         return avg_loss, avg_acc
 
-    def EvalOneEpoch_Full(self, Loader, pts_idx_list=None):
-        '''Validation pass (EvalOneEpoch_Full, :401-497): samples are duplicated to fill the 2B Siamese
-        graph (:445-455), evaluated with Is_Training=False, and Z_prob[0::2] is scored.'''
-        B = self.engine.B
-        inter = np.zeros(13)
-        union = np.zeros(13)
-        correct = 0
-        total = 0
-        avg_loss, cnt = 0., 0
+    def _eval_epoch(self, Loader, siamese):
+        """Shared validation loop over `Loader.NextBatch_TestSet()` (the held-out area).  A short last batch is padded by
+        repeating its first block (:429-436); `siamese` duplicates every block to fill the 2B graph (:445-455) and scores
+        Z_prob[0::2].  Running averages follow the reference's formulas, including its loss average that adds the batch
+        loss unweighted (:488).  -> (avg_loss, avg_correct_rate, mean IoU over the 13 classes)."""
+        C = 13
+        per_step = self.engine.B // 2 if siamese else self.engine.B
+        true_positive, positive, gt_count = np.zeros(C), np.zeros(C), np.zeros(C)
+        batch_cnt, samp_cnt, avg_loss, avg_correct_rate = 1, 0, 0., 0.
+        iou = np.zeros(C)
         while True:
-            SuccessFlag, data, seg, weak_seg_onehot, mb_size = Loader.NextBatch_ValSet()[:5]
+            SuccessFlag, data, seg_mb, weak_seg_onehot, mb_size = Loader.NextBatch_TestSet()[:5]
             if not SuccessFlag:
                 break
             data = np.asarray(data, np.float32)
-            seg = np.asarray(seg).astype(np.int64)
-            if mb_size < B // 2:                         # pad by repeating sample 0 (:429-436)
-                pad = B // 2 - mb_size
-                data = np.concatenate([data, np.repeat(data[0:1], pad, 0)], 0)
-                seg = np.concatenate([seg, np.repeat(seg[0:1], pad, 0)], 0)
-            data_feed = np.repeat(data, 2, axis=0)
-            seg_feed = np.repeat(seg, 2, axis=0)
-            N = data.shape[1]
-            loss_mb, Z_prob_mb = self.eval_batch(data_feed, Tool.OnehotEncode(seg_feed, 13),
-                                                 np.ones((2 * data.shape[0], N), np.float32))
-            pred = np.argmax(Z_prob_mb[0:2 * mb_size:2], axis=-1)
-            gt = seg[:mb_size]
-            correct += int(np.sum(pred == gt))
-            total += gt.size
-            for c in range(13):                          # vectorised IoU counters (:473-477)
-                inter[c] += np.sum((pred == c) & (gt == c))
-                union[c] += np.sum((pred == c) | (gt == c))
-            avg_loss = (avg_loss * cnt + loss_mb * mb_size) / (cnt + mb_size)
-            cnt += mb_size
-        iou = inter / np.maximum(union, 1)
-        return avg_loss, correct / max(total, 1), float(np.mean(iou)), iou
+            seg_mb = np.asarray(seg_mb).astype(np.int64)
+            if mb_size > per_step:
+                raise ValueError("loader batch %d exceeds the graph's %d samples per step" % (mb_size, per_step))
+            pad = per_step - mb_size
+            data_feed = np.concatenate([data, np.repeat(data[0:1], pad, 0)], 0) if pad else data
+            seg_feed = np.concatenate([seg_mb, np.repeat(seg_mb[0:1], pad, 0)], 0) if pad else seg_mb
+            if siamese:
+                data_feed, seg_feed = np.repeat(data_feed, 2, axis=0), np.repeat(seg_feed, 2, axis=0)
+            loss_mb, Z_prob_mb = self.eval_batch(data_feed, Tool.OnehotEncode(seg_feed, C),
+                                                 np.ones(seg_feed.shape, np.float32))
+            Z_prob_mb = Z_prob_mb[0:2 * mb_size:2] if siamese else Z_prob_mb[0:mb_size]
+            pred_mb = np.argmax(Z_prob_mb, axis=-1)
+            acc = float(np.mean(pred_mb == seg_mb))
+            self._count_classes(pred_mb, seg_mb, C, positive, true_positive, gt_count)
+            iou = true_positive / (gt_count + positive - true_positive + 1e-5)
+            avg_loss = (avg_loss * samp_cnt + loss_mb) / (samp_cnt + mb_size)
+            avg_correct_rate = (avg_correct_rate * samp_cnt + acc * mb_size) / (samp_cnt + mb_size)
+            samp_cnt += mb_size
+            print('\rBatch {:d} EvaluatedSamp {:d}  Avg Loss {:.4f}  Avg Correct Rate {:.3f}%  mIoU {:.3f}%'.format(
+                batch_cnt, samp_cnt, avg_loss, 100 * avg_correct_rate, 100 * np.mean(iou)), end='')
+            batch_cnt += 1
+        if hasattr(Loader, 'ResetLoader_TestSet'):
+            Loader.ResetLoader_TestSet()
+        self.eval_iou = iou                              # per-class IoU of the pass
+        return avg_loss, avg_correct_rate, float(np.mean(iou))
+
+    def EvalOneEpoch(self, Loader):
+        """Plain-style validation (EvalOneEpoch, :351-399).  The reference's version feeds integer labels to the one-hot
+        placeholder and Is_Training=True; here it is the Full loop without the Siamese duplication (inference mode)."""
+        return self._eval_epoch(Loader, siamese=False)
+
+    def EvalOneEpoch_Full(self, Loader):
+        '''Validation pass (EvalOneEpoch_Full, :401-497) -> (avg_loss, avg_correct_rate, mIoU).'''
+        return self._eval_epoch(Loader, siamese=True)
 
     # ------------------------------------------------------------------ checkpoints (:586-629) ---
     def SaveCheckPoint(self, save_filepath, best_filename=None, eval_avg_correct_rate=None):
@@ -349,9 +428,10 @@ class S3DIS_Trainer():
         blob['__adam_v'] = vs.adam_v.cpu().numpy()
         np.savez(save_filepath + '.npz', **blob)
         if best_filename is not None and eval_avg_correct_rate is not None and \
-                eval_avg_correct_rate > self.bestValCorrect:
-            self.bestValCorrect = eval_avg_correct_rate
-            np.savez(best_filename + '.npz', **blob)
+                np.mean(eval_avg_correct_rate) > self.bestValCorrect:
+            self.bestValCorrect = np.mean(eval_avg_correct_rate)
+            # the best copy lives next to the checkpoint, under `best_filename` (:592-601)
+            np.savez(os.path.join(os.path.dirname(os.path.abspath(save_filepath)), best_filename + '.npz'), **blob)
 
     def RestoreCheckPoint(self, filepath):
         blob = np.load(filepath if filepath.endswith('.npz') else filepath + '.npz')

@@ -93,7 +93,14 @@ class ShapeNet_Trainer(S3DIS_Trainer):
         z[:, list(iou_oids)] += 1
         return np.argmax(z, axis=-1)
 
+    def TrainOneEpoch(self, Loader, file_idx_list, data_idx_list, pts_idx_list=None):
+        """Plain-style epoch (ShapeNet_DGCNN_trainer.py:143-218): the same loop without the Siamese partner."""
+        return self._train_epoch(Loader, file_idx_list, data_idx_list, pts_idx_list, siamese=False)
+
     def TrainOneEpoch_Full(self, Loader, file_idx_list, data_idx_list, pts_idx_list=None):
+        return self._train_epoch(Loader, file_idx_list, data_idx_list, pts_idx_list, siamese=True)
+
+    def _train_epoch(self, Loader, file_idx_list, data_idx_list, pts_idx_list, siamese):
         """One training epoch (ShapeNet_DGCNN_trainer.py:220-341).  `Loader` follows ShapeNetIO.NextBatch_TrainSet
         (DataIO_ShapeNet.py:145-193): (flag, data (b,N,3), label (b,1), seg (b,N), weak_seg_onehot, mb_size, file_idx,
         data_idx) and exposes NUM_CATEGORIES, objcats, object2setofoid.  Mask from (file_idx_list, data_idx_list,
@@ -107,7 +114,7 @@ class ShapeNet_Trainer(S3DIS_Trainer):
             SuccessFlag, data, label, seg, _, mb_size, file_idx, data_idx = Loader.NextBatch_TrainSet(shuffle_flag=True)
             if not SuccessFlag:
                 break
-            if mb_size < self.BATCH_SIZE:                 # short batches are skipped, not padded (:239-240)
+            if mb_size < (self.engine.B // 2 if siamese else self.engine.B):   # short batches are skipped (:239-240)
                 continue
             data = np.asarray(data, np.float32)
             label = np.asarray(label).astype(np.int64).reshape(mb_size, -1)
@@ -119,18 +126,21 @@ class ShapeNet_Trainer(S3DIS_Trainer):
                     hit = np.where((file_idx_list == file_idx[b_i]) & (data_idx_list == data_idx[b_i]))[0]
                     mask[b_i, np.asarray(pts_idx_list[hit][0]).astype(np.int64)] = 1
             partner = data.copy()
-            if self.epoch >= self.rampup:
+            if siamese and self.epoch >= self.rampup:
                 extent = data.max(axis=1, keepdims=True) - data.min(axis=1, keepdims=True)
                 partner = data + (2e-3 * extent * rng.standard_normal(data.shape)).astype(np.float32)
                 flip = rng.integers(0, 2, mb_size).astype(bool)
                 partner[flip, :, 2] *= -1
-            data_feed = np.empty((2 * mb_size, N, 3), np.float32)
-            data_feed[0::2], data_feed[1::2] = data, partner
-            label_onehot_feed = np.repeat(Tool.OnehotEncode(label[:, 0], Loader.NUM_CATEGORIES), 2, axis=0)
-            seg_onehot_feed = Tool.OnehotEncode(np.repeat(seg, 2, axis=0), 50)
+            rep = 2 if siamese else 1
+            data_feed = np.empty((rep * mb_size, N, 3), np.float32)
+            data_feed[0::rep] = data
+            if siamese:
+                data_feed[1::2] = partner
+            label_onehot_feed = np.repeat(Tool.OnehotEncode(label[:, 0], Loader.NUM_CATEGORIES), rep, axis=0)
+            seg_onehot_feed = Tool.OnehotEncode(np.repeat(seg, rep, axis=0), 50)
             loss_mb, _, _, _, Z_prob_mb = self.train_batch(data_feed, label_onehot_feed, seg_onehot_feed,
-                                                           np.repeat(mask, 2, axis=0))
-            pred = np.stack([self._restrict_to_category(Z_prob_mb[2 * b_i],
+                                                           np.repeat(mask, rep, axis=0))
+            pred = np.stack([self._restrict_to_category(Z_prob_mb[rep * b_i],
                                                         Loader.object2setofoid[Loader.objcats[label[b_i, 0]]])
                              for b_i in range(mb_size)])
             avg_loss = (avg_loss * data_cnt + loss_mb * mb_size) / (data_cnt + mb_size)
@@ -142,7 +152,14 @@ class ShapeNet_Trainer(S3DIS_Trainer):
         self.epoch += 1
         return avg_loss, avg_acc
 
+    def EvalOneEpoch(self, Loader, Eval):
+        """Plain-style validation (ShapeNet_DGCNN_trainer.py:343-413): no Siamese duplication."""
+        return self._eval_epoch(Loader, Eval, siamese=False)
+
     def EvalOneEpoch_Full(self, Loader, Eval):
+        return self._eval_epoch(Loader, Eval, siamese=True)
+
+    def _eval_epoch(self, Loader, Eval, siamese):
         """Validation pass (ShapeNet_DGCNN_trainer.py:417-507): short batches are padded with sample 0, every sample is
         duplicated to fill the Siamese graph, Is_Training=False, Z_prob[0::2] is scored with Eval.EvalIoU over the part ids
         of the shape's category.  Returns (avg_loss, avg_acc, perdata_miou, pershape_miou)."""
@@ -157,7 +174,8 @@ class ShapeNet_Trainer(S3DIS_Trainer):
             data = np.asarray(data, np.float32)
             label = np.asarray(label).astype(np.int64).reshape(mb_size, -1)
             seg = np.asarray(seg).astype(np.int64)
-            pad = self.BATCH_SIZE - mb_size
+            rep = 2 if siamese else 1
+            pad = self.engine.B // rep - mb_size
             if pad > 0:
                 data_f = np.concatenate([data, np.repeat(data[0:1], pad, 0)], 0)
                 seg_f = np.concatenate([seg, np.repeat(seg[0:1], pad, 0)], 0)
@@ -165,11 +183,11 @@ class ShapeNet_Trainer(S3DIS_Trainer):
             else:
                 data_f, seg_f, label_f = data, seg, label
             N = data_f.shape[1]
-            loss_mb, Z_prob_mb = self.eval_batch(np.repeat(data_f, 2, axis=0),
-                                                 np.repeat(Tool.OnehotEncode(label_f[:, 0], Loader.NUM_CATEGORIES), 2, axis=0),
-                                                 Tool.OnehotEncode(np.repeat(seg_f, 2, axis=0), 50),
-                                                 np.ones((2 * data_f.shape[0], N), np.float32))
-            Z_prob_mb = Z_prob_mb[0:2 * mb_size:2]
+            loss_mb, Z_prob_mb = self.eval_batch(np.repeat(data_f, rep, axis=0),
+                                                 np.repeat(Tool.OnehotEncode(label_f[:, 0], Loader.NUM_CATEGORIES), rep, axis=0),
+                                                 Tool.OnehotEncode(np.repeat(seg_f, rep, axis=0), 50),
+                                                 np.ones((rep * data_f.shape[0], N), np.float32))
+            Z_prob_mb = Z_prob_mb[0:rep * mb_size:rep]
             for b_i in range(mb_size):
                 shape_label = int(label[b_i, 0])
                 iou_oids = Loader.object2setofoid[Loader.objcats[shape_label]]
