@@ -214,7 +214,6 @@ class ShapeNet_Trainer(S3DIS_Trainer):
         shape_cnt = np.zeros(Loader.NUM_CATEGORIES)
         pershape_miou = np.zeros(Loader.NUM_CATEGORIES)
         avg_loss = avg_acc = perdata_miou = 0.
-        rng = np.random.default_rng(0)
         while True:
             SuccessFlag, data, label, seg, _, mb_size, _, _ = Loader.NextSamp_TestSet()
             if not SuccessFlag:
@@ -224,7 +223,7 @@ class ShapeNet_Trainer(S3DIS_Trainer):
             seg = np.asarray(seg).astype(np.int64)
             n0 = data.shape[1]
             assert mb_size == 1 and n0 <= eng.N, "Test feeds one shape of at most num_point points per call (:524-534)"
-            idx = np.concatenate([np.arange(n0), rng.choice(n0, eng.N - n0, replace=True)]).astype(np.int64)
+            idx = np.concatenate([np.arange(n0), np.random.choice(np.arange(n0), eng.N - n0, True)]).astype(np.int64)   # (:531-533)
             data_feed = np.repeat(data[:, idx, :], eng.B, axis=0)
             seg_feed = np.repeat(seg[:, idx], eng.B, axis=0)
             label_feed = np.repeat(Tool.OnehotEncode(label[:, 0], Loader.NUM_CATEGORIES), eng.B, axis=0)
