@@ -597,6 +597,18 @@ rowgemm_tc_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, 
             rb_cloud0 = div_pos(row0, E.rb_rows);
             rb_rem0 = (uint32_t)(row0 - rb_cloud0 * E.rb_rows);
           }
+          // global operands of the epilogue (previous pre-activations / the accumulation target) for the thread's 8 rows:
+          // all loads in flight before the first use instead of one dependent round trip per row
+          float4 pre[8];
+          if (EMODE == EPI_RELUMASK_STATS || EMODE == EPI_ACCUM) {
+            const float* src = (EMODE == EPI_RELUMASK_STATS) ? E.yprev : E.out;
+            const long long lds = (EMODE == EPI_RELUMASK_STATS) ? E.ldyp : E.ldo;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const long long row = row0 + e_r0 + 16 * it;
+              pre[it] = (row < M) ? *reinterpret_cast<const float4*>(src + row * lds + cbase) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int r = e_r0 + 16 * it;
@@ -622,7 +634,7 @@ rowgemm_tc_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, 
                 for (int j = 0; j < 4; ++j) { f0[j] += o[j]; f1[j] = fmaf(o[j], o[j], f1[j]); }
               }
             } else if (EMODE == EPI_RELUMASK_STATS) {
-              const float4 y4 = *reinterpret_cast<const float4*>(E.yprev + row * E.ldyp + cbase);
+              const float4 y4 = pre[it];
               const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
               float dm[4] = {1.f, 1.f, 1.f, 1.f};
               if (E.dmask) {
@@ -637,7 +649,7 @@ rowgemm_tc_kernel(const Operand A, const float* __restrict__ Bm, long long ldb, 
                 f1[j] = fmaf(o[j], yv[j], f1[j]);
               }
             } else if (EMODE == EPI_ACCUM) {
-              const float4 c4 = *reinterpret_cast<const float4*>(E.out + row * E.ldo + cbase);
+              const float4 c4 = pre[it];
               o[0] += c4.x; o[1] += c4.y; o[2] += c4.z; o[3] += c4.w;
             }
             *reinterpret_cast<float4*>(E.out + row * E.ldo + cbase) = make_float4(o[0], o[1], o[2], o[3]);
@@ -889,12 +901,12 @@ colgemm_tc_kernel(const Operand A, const Operand G, long long M, long long rows_
   double fst0[4] = {0.0, 0.0, 0.0, 0.0}, fst1[4] = {0.0, 0.0, 0.0, 0.0};
 
   // fixed per-thread channel groups
-  const int gA = tid & 15, rA0 = tid >> 4;                 // A: 16 groups, 16 rows per sweep
+  const int gA = tid & (aGroups - 1), rA0 = tid / aGroups; // A: aGroups (8 or 16) groups, every thread owns one that exists
+  const int rAstep = TC_THREADS / aGroups;                 // rows per sweep: 32 or 16
   const int gG = tid % gGroups, rG0 = tid / gGroups;       // dY: gGroups groups
   const int rGstep = TC_THREADS / gGroups;
   const int cA = k1_0 / 8 + gA, cG = k2_0 / 8 + gG;        // absolute channel groups
   const bool vA = cA * 8 < A.C, vG = cG * 8 < G.C;
-  const bool wA = gA < aGroups;                             // this thread's A group exists in shared memory
   float a0[8], a1[8], a2[8], g0[8], g1[8], g2[8];
   load_consts<AMODE>(A, cA, A.C, a0, a1, a2);
   load_consts<GMODE>(G, cG, G.C, g0, g1, g2);
@@ -917,30 +929,30 @@ colgemm_tc_kernel(const Operand A, const Operand G, long long M, long long rows_
     constexpr int UB = 4;
     if (!genA) {
 #pragma unroll 1
-      for (int rbase = rA0; rbase < RT; rbase += 16 * UB) {
+      for (int rbase = rA0; rbase < RT; rbase += rAstep * UB) {
         long long pt[UB], cb[UB], nb[UB];
         bool ok[UB];
 #pragma unroll
         for (int u = 0; u < UB; ++u) {
-          const int r = rbase + 16 * u;
-          ok[u] = vA && rb + r < r_end;
+          const int r = rbase + rAstep * u;
+          ok[u] = vA && r < RT && rb + r < r_end;
           pt[u] = 0; cb[u] = 0; nb[u] = 0;
-          if (AMODE == OP_EDGE) {
+          if (AMODE == OP_EDGE && r < RT) {
             rowmap_point(arm, r, pt[u], cb[u]);
             if (ok[u] && cA * 8 >= (A.C >> 1)) nb[u] = cb[u] + A.idx[rb + r];
           }
         }
         RawChunk w[UB];
 #pragma unroll
-        for (int u = 0; u < UB; ++u) fetch_chunk<AMODE>(A, rb + rbase + 16 * u, cA, ok[u], pt[u], nb[u], w[u]);
+        for (int u = 0; u < UB; ++u) fetch_chunk<AMODE>(A, rb + rbase + rAstep * u, cA, ok[u], pt[u], nb[u], w[u]);
 #pragma unroll
         for (int u = 0; u < UB; ++u) {
-          const int r = rbase + 16 * u;
-          float v[8];
-          finish_chunk<AMODE>(A, rb + r, cA, ok[u], pt[u], cb[u], a0, a1, a2, w[u], v);
-          uint4 hi, lo;
-          split8(v, hi, lo);
-          if (wA) {
+          const int r = rbase + rAstep * u;
+          if (r < RT) {
+            float v[8];
+            finish_chunk<AMODE>(A, rb + r, cA, ok[u], pt[u], cb[u], a0, a1, a2, w[u], v);
+            uint4 hi, lo;
+            split8(v, hi, lo);
             *reinterpret_cast<uint4*>(sAhi + (size_t)gA * agb + r * 16) = hi;
             *reinterpret_cast<uint4*>(sAlo + (size_t)gA * agb + r * 16) = lo;
           }
@@ -948,16 +960,14 @@ colgemm_tc_kernel(const Operand A, const Operand G, long long M, long long rows_
       }
     } else {
 #pragma unroll 2
-      for (int r = rA0; r < RT; r += 16) {
+      for (int r = rA0; r < RT; r += rAstep) {
         const long long row = rb + r;
         float v[8];
         load_chunk<AMODE>(A, row, cA, vA && row < r_end, a0, a1, a2, v, true);
         uint4 hi, lo;
         split8(v, hi, lo);
-        if (wA) {
-          *reinterpret_cast<uint4*>(sAhi + (size_t)gA * agb + r * 16) = hi;
-          *reinterpret_cast<uint4*>(sAlo + (size_t)gA * agb + r * 16) = lo;
-        }
+        *reinterpret_cast<uint4*>(sAhi + (size_t)gA * agb + r * 16) = hi;
+        *reinterpret_cast<uint4*>(sAlo + (size_t)gA * agb + r * 16) = lo;
       }
     }
     if (!genG) {
@@ -1065,14 +1075,21 @@ colgemm_tc_kernel(const Operand A, const Operand G, long long M, long long rows_
 #pragma unroll
           for (int j = 0; j < 4; ++j) { scp[j] = E.scp[cl + j]; shp[j] = E.shp[cl + j]; }
           float f0[4] = {0.f, 0.f, 0.f, 0.f}, f1[4] = {0.f, 0.f, 0.f, 0.f};
+          float4 yq[8];     // the previous layer's pre-activations of the thread's 8 rows: all loads in flight at once
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const long long row = rb + e_r0 + 16 * it;
+            yq[it] = (e_r0 + 16 * it < RT && row < r_end) ? *reinterpret_cast<const float4*>(E.yprev + row * E.ldyp + cl)
+                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int r = e_r0 + 16 * it;
             const long long row = rb + r;
-            if (row >= r_end) break;
+            if (r >= RT || row >= r_end) break;
             const float4 s4 = *reinterpret_cast<const float4*>(stage + r * STAGE_LD + e_c4 * 4);
             float o[4] = {s4.x, s4.y, s4.z, s4.w};
-            const float4 y4 = *reinterpret_cast<const float4*>(E.yprev + row * E.ldyp + cl);
+            const float4 y4 = yq[it];
             const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
             float dm[4] = {1.f, 1.f, 1.f, 1.f};
             if (E.dmask) {
