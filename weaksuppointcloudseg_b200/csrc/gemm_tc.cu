@@ -17,6 +17,7 @@
 // phases of different tiles when shared memory allows (K<=64).
 #include "operand.cuh"
 #include <cuda_bf16.h>
+#include <type_traits>
 
 namespace wspc {
 void count_launch(int n = 1);
@@ -901,8 +902,7 @@ colgemm_tc_kernel(const Operand A, const Operand G, long long M, long long rows_
   double fst0[4] = {0.0, 0.0, 0.0, 0.0}, fst1[4] = {0.0, 0.0, 0.0, 0.0};
 
   // fixed per-thread channel groups
-  const int gA = tid & (aGroups - 1), rA0 = tid / aGroups; // A: aGroups (8 or 16) groups, every thread owns one that exists
-  const int rAstep = TC_THREADS / aGroups;                 // rows per sweep: 32 or 16
+  const int gA = tid & (aGroups - 1), rA0 = (aGroups == 8) ? tid >> 3 : tid >> 4;   // A: aGroups (8 or 16) channel groups
   const int gG = tid % gGroups, rG0 = tid / gGroups;       // dY: gGroups groups
   const int rGstep = TC_THREADS / gGroups;
   const int cA = k1_0 / 8 + gA, cG = k2_0 / 8 + gG;        // absolute channel groups
@@ -925,51 +925,61 @@ colgemm_tc_kernel(const Operand A, const Operand G, long long M, long long rows_
     if (AMODE == OP_EDGE) arm = rowmap_tile(rb, A.k, A.npts, a_inv);
     if (GMODE == OP_DY_SPARSE) gcm = cloudmap_tile(rb, G.npts);
     if (GMODE == OP_DY_MAXK) grm = rowmap_tile(rb, G.k, G.npts, g_inv);
-    // A operand: 8 chunks per thread in batches of UB, all loads of a batch in flight before the first use
+    // A operand: RT / rAstep chunks per thread in batches of UB, all loads of a batch in flight before the first use.
+    // The group count is a compile-time constant of each copy of the loop (16: 16 rows per sweep, the batch of 4 never
+    // leaves the tile; 8: 32 rows per sweep, every thread owns a group that exists).
     constexpr int UB = 4;
-    if (!genA) {
+    auto stage_A = [&](auto ag_tag) {
+      constexpr int AG = decltype(ag_tag)::value;
+      constexpr int rAstep = TC_THREADS / AG;
+      constexpr bool guard = rAstep * UB > 64;               // a batch may reach past a 64-row tile
+      if (!genA) {
 #pragma unroll 1
-      for (int rbase = rA0; rbase < RT; rbase += rAstep * UB) {
-        long long pt[UB], cb[UB], nb[UB];
-        bool ok[UB];
+        for (int rbase = rA0; rbase < RT; rbase += rAstep * UB) {
+          long long pt[UB], cb[UB], nb[UB];
+          bool ok[UB];
 #pragma unroll
-        for (int u = 0; u < UB; ++u) {
-          const int r = rbase + rAstep * u;
-          ok[u] = vA && r < RT && rb + r < r_end;
-          pt[u] = 0; cb[u] = 0; nb[u] = 0;
-          if (AMODE == OP_EDGE && r < RT) {
-            rowmap_point(arm, r, pt[u], cb[u]);
-            if (ok[u] && cA * 8 >= (A.C >> 1)) nb[u] = cb[u] + A.idx[rb + r];
+          for (int u = 0; u < UB; ++u) {
+            const int r = rbase + rAstep * u;
+            const bool in = !guard || r < RT;
+            ok[u] = vA && in && rb + r < r_end;
+            pt[u] = 0; cb[u] = 0; nb[u] = 0;
+            if (AMODE == OP_EDGE && in) {
+              rowmap_point(arm, r, pt[u], cb[u]);
+              if (ok[u] && cA * 8 >= (A.C >> 1)) nb[u] = cb[u] + A.idx[rb + r];
+            }
+          }
+          RawChunk w[UB];
+#pragma unroll
+          for (int u = 0; u < UB; ++u) fetch_chunk<AMODE>(A, rb + rbase + rAstep * u, cA, ok[u], pt[u], nb[u], w[u]);
+#pragma unroll
+          for (int u = 0; u < UB; ++u) {
+            const int r = rbase + rAstep * u;
+            if (!guard || r < RT) {
+              float v[8];
+              finish_chunk<AMODE>(A, rb + r, cA, ok[u], pt[u], cb[u], a0, a1, a2, w[u], v);
+              uint4 hi, lo;
+              split8(v, hi, lo);
+              *reinterpret_cast<uint4*>(sAhi + (size_t)gA * agb + r * 16) = hi;
+              *reinterpret_cast<uint4*>(sAlo + (size_t)gA * agb + r * 16) = lo;
+            }
           }
         }
-        RawChunk w[UB];
-#pragma unroll
-        for (int u = 0; u < UB; ++u) fetch_chunk<AMODE>(A, rb + rbase + rAstep * u, cA, ok[u], pt[u], nb[u], w[u]);
-#pragma unroll
-        for (int u = 0; u < UB; ++u) {
-          const int r = rbase + rAstep * u;
-          if (r < RT) {
-            float v[8];
-            finish_chunk<AMODE>(A, rb + r, cA, ok[u], pt[u], cb[u], a0, a1, a2, w[u], v);
-            uint4 hi, lo;
-            split8(v, hi, lo);
-            *reinterpret_cast<uint4*>(sAhi + (size_t)gA * agb + r * 16) = hi;
-            *reinterpret_cast<uint4*>(sAlo + (size_t)gA * agb + r * 16) = lo;
-          }
-        }
-      }
-    } else {
+      } else {
 #pragma unroll 2
-      for (int r = rA0; r < RT; r += rAstep) {
-        const long long row = rb + r;
-        float v[8];
-        load_chunk<AMODE>(A, row, cA, vA && row < r_end, a0, a1, a2, v, true);
-        uint4 hi, lo;
-        split8(v, hi, lo);
-        *reinterpret_cast<uint4*>(sAhi + (size_t)gA * agb + r * 16) = hi;
-        *reinterpret_cast<uint4*>(sAlo + (size_t)gA * agb + r * 16) = lo;
+        for (int r = rA0; r < RT; r += rAstep) {
+          const long long row = rb + r;
+          float v[8];
+          load_chunk<AMODE>(A, row, cA, vA && row < r_end, a0, a1, a2, v, true);
+          uint4 hi, lo;
+          split8(v, hi, lo);
+          *reinterpret_cast<uint4*>(sAhi + (size_t)gA * agb + r * 16) = hi;
+          *reinterpret_cast<uint4*>(sAlo + (size_t)gA * agb + r * 16) = lo;
+        }
       }
-    }
+    };
+    if (aGroups == 8) stage_A(std::integral_constant<int, 8>{});
+    else stage_A(std::integral_constant<int, 16>{});
     if (!genG) {
       // dY operand: RT / rGstep chunks per thread (4, 8 or 16; 2 when K2t = 16), same batching
 #pragma unroll 1
