@@ -223,6 +223,30 @@ def run_ours(args):
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
+    # ---- label-propagation stage of cfg-3 ("LP on 64 blocks as a separately timed stage") ----------------
+    # test-time path of S3DIS_Trainer.Test: symmetric Laplacian of each block (xyz, rgb) + closed-form LP solve on the
+    # network's probabilities, all on the device; timed apart from the training step, never part of `value`.
+    from weaksuppointcloudseg_b200 import ops
+    Xo, Zo = devt[0][0::2], eng.Zp[0::2]
+    nblk = Xo.shape[0]
+
+    def lp_block(b):
+        Lm = ops.laplacian_sym(Xo[b:b + 1, :, 0:3].contiguous(), Xo[b:b + 1, :, 3:6].contiguous())
+        return ops.lp_solve(Lm[0], Zo[b].contiguous(), 1.0, 1.0)
+
+    lp_block(0)
+    torch.cuda.synchronize()
+    e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e4.record()
+    for b in range(nblk):
+        lp_block(b)
+    e5.record()
+    torch.cuda.synchronize()
+    ms_lp = dp.max_over_ranks(e4.elapsed_time(e5), dev)
+    lp_stage = {"blocks_per_gpu": nblk, "ms_per_block": ms_lp / nblk, "blocks_per_s": nblk * world / (ms_lp / 1e3),
+                "includes": "Laplacian (N x N, xyz+rgb kernels, symmetric normalisation) + LP solve (Jacobi-PCG on "
+                            "(alpha*L + beta*diag(w)) Y = beta*diag(w) G), N=%d, 13 classes" % N}
+
     # ---- roofline of the dominant kNN kernel (D=64) -----------------------------------------------
     def knn_bytes(D, k):  # materialised-equivalent bytes of pairwise_distance + knn
         return B * (2 * N * N * 4 + N * D * 4 + N * k * 4)
@@ -260,7 +284,7 @@ def run_ours(args):
         "e2e": {"value": clouds * K / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / K, "api": "S3DIS_Trainer.train_batch(host X, Y one-hot, Mask) -> losses, Z_prob"},
         "gpu_launches": int(launches), "roofline": roofline, "clocks": sampler.summary(),
-        "loss": loss_val, "e2e_loss": last[0],
+        "loss": loss_val, "e2e_loss": last[0], "lp_stage": lp_stage,
     }
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -270,6 +294,11 @@ def run_ours(args):
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": _t.get_num_threads(), "kind": "port",
                                "sample": "%d-cloud mini-batch, N=%d, same losses, 2 timed steps after 1 warm-up "
                                          "(oracle/ port on torch-CPU fp32)" % (n, N)}
+        from oracle import lp as olp                      # the reference's dense-inverse LP on one block (bounded sample)
+        zb = np.random.default_rng(0).dirichlet(np.ones(13), N)
+        t0 = time.perf_counter()
+        olp.solve(olp.laplacian_sym(X[0:1, :, 0:3], X[0:1, :, 3:6])[0], zb)
+        out["cpu_baseline"]["lp_ms_per_block"] = 1e3 * (time.perf_counter() - t0)
     if rank == 0:
         print(json.dumps(out), flush=True)
     dp.shutdown()

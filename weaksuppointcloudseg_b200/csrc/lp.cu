@@ -25,52 +25,78 @@ __device__ __forceinline__ float sqdist_smooth(const float* a, const float* b, f
   return d > 0.f ? d : 0.f;
 }
 
-// pass 1: degree d_i = sum_j W_ij.   grid (N/128, B), block 128: one thread per row i, columns staged in smem
+// Symmetric normalised Laplacian in two passes over the N x N pair kernel (it is never stored unnormalised):
+// pass 1 (WRITE = false): degree d_i = sum_j W_ij;  pass 2: L_ij = ((i == j) (d_i + 1e-8) - W_ij) d_i^-1/2 d_j^-1/2.
+// grid (N/16, B), block 256: a CTA owns 16 rows (2 per warp); 128 columns at a time are staged in shared memory and a
+// lane evaluates columns lane, lane+32, lane+64, lane+96 of the tile -- four independent exp chains per thread, 16 warps
+// per SM with two resident CTAs, and pass 2 stores 128 contiguous bytes per warp and row.  The row sums are reduced by a
+// fixed-order butterfly, so the result does not depend on scheduling.
+constexpr int LAP_ROWS = 16;
 template <bool WRITE>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 laplacian_kernel(const float* __restrict__ X, const float* __restrict__ RGB, int N, int D1, int D2, float s1, float s2,
                  float* __restrict__ deg, float* __restrict__ Lout) {
   __shared__ float sx[128][3], sc[128][3], ssx[128], ssc[128], sdeg[128];
   const int b = blockIdx.y;
-  const int i = blockIdx.x * 128 + threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* Xb = X + (size_t)b * N * D1;
   const float* Cb = RGB + (size_t)b * N * D2;
-  float xi[3] = {0.f, 0.f, 0.f}, ci[3] = {0.f, 0.f, 0.f};
-  float sxi = 0.f, sci = 0.f, di = 0.f;
-  if (i < N) {
-    for (int c = 0; c < D1; ++c) { xi[c] = Xb[(size_t)i * D1 + c]; sxi = __fmaf_rn(xi[c], xi[c], sxi); }
-    for (int c = 0; c < D2; ++c) { ci[c] = Cb[(size_t)i * D2 + c]; sci = __fmaf_rn(ci[c], ci[c], sci); }
-    if (WRITE) di = deg[(size_t)b * N + i];
+  float xi[2][3], ci[2][3], sxi[2], sci[2], di[2], acc[2];
+  int row[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int i = blockIdx.x * LAP_ROWS + warp * 2 + r;
+    row[r] = i;
+    sxi[r] = 0.f; sci[r] = 0.f; di[r] = 1.f; acc[r] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { xi[r][c] = 0.f; ci[r][c] = 0.f; }
+    if (i < N) {
+      for (int c = 0; c < D1; ++c) { xi[r][c] = Xb[(size_t)i * D1 + c]; sxi[r] = __fmaf_rn(xi[r][c], xi[r][c], sxi[r]); }
+      for (int c = 0; c < D2; ++c) { ci[r][c] = Cb[(size_t)i * D2 + c]; sci[r] = __fmaf_rn(ci[r][c], ci[r][c], sci[r]); }
+      if (WRITE) di[r] = deg[(size_t)b * N + i];
+    }
   }
-  float acc = 0.f;
   for (int j0 = 0; j0 < N; j0 += 128) {
-    const int j = j0 + threadIdx.x;
     __syncthreads();
-    if (j < N) {
+    if (tid < 128) {
+      const int j = j0 + tid;
       float a = 0.f, c2 = 0.f;
-      for (int c = 0; c < D1; ++c) { const float v = Xb[(size_t)j * D1 + c]; sx[threadIdx.x][c] = v; a = __fmaf_rn(v, v, a); }
-      for (int c = 0; c < D2; ++c) { const float v = Cb[(size_t)j * D2 + c]; sc[threadIdx.x][c] = v; c2 = __fmaf_rn(v, v, c2); }
-      ssx[threadIdx.x] = a;
-      ssc[threadIdx.x] = c2;
-      if (WRITE) sdeg[threadIdx.x] = deg[(size_t)b * N + j];
+      if (j < N) {
+        for (int c = 0; c < D1; ++c) { const float v = Xb[(size_t)j * D1 + c]; sx[tid][c] = v; a = __fmaf_rn(v, v, a); }
+        for (int c = 0; c < D2; ++c) { const float v = Cb[(size_t)j * D2 + c]; sc[tid][c] = v; c2 = __fmaf_rn(v, v, c2); }
+        if (WRITE) sdeg[tid] = deg[(size_t)b * N + j];
+      }
+      ssx[tid] = a;
+      ssc[tid] = c2;
     }
     __syncthreads();
-    if (i < N) {
-      const int jn = (N - j0 < 128) ? N - j0 : 128;
-      for (int jj = 0; jj < jn; ++jj) {
-        const float w = expf(-sqdist_smooth(xi, sx[jj], sxi, ssx[jj], D1) * s1) *
-                        expf(-sqdist_smooth(ci, sc[jj], sci, ssc[jj], D2) * s2);     // Tool.py:449,457,459
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      if (row[r] >= N) continue;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int jj = lane + 32 * t, j2 = j0 + jj;
+        if (j2 >= N) continue;
+        const float w = expf(-sqdist_smooth(xi[r], sx[jj], sxi[r], ssx[jj], D1) * s1) *
+                        expf(-sqdist_smooth(ci[r], sc[jj], sci[r], ssc[jj], D2) * s2);   // Tool.py:449,457,459
         if (WRITE) {
-          const int j2 = j0 + jj;
-          const float num = ((j2 == i) ? (di + 1e-8f) : 0.f) - w;                     // D - W  (:462,:464)
-          Lout[((size_t)b * N + i) * N + j2] = num * rsqrtf(di) * rsqrtf(sdeg[jj]);   // D^-1/2 . D^-1/2 (:463,:465)
+          const float num = ((j2 == row[r]) ? (di[r] + 1e-8f) : 0.f) - w;                 // D - W  (:462,:464)
+          Lout[((size_t)b * N + row[r]) * N + j2] = num * rsqrtf(di[r]) * rsqrtf(sdeg[jj]);   // D^-1/2 . D^-1/2 (:463,:465)
         } else {
-          acc += w;
+          acc[r] += w;
         }
       }
     }
   }
-  if (!WRITE && i < N) deg[(size_t)b * N + i] = acc;
+  if (!WRITE) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      float v = acc[r];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0 && row[r] < N) deg[(size_t)b * N + row[r]] = v;
+    }
+  }
 }
 
 // w = 1 - H_2(G)/log_2 K ; A = alpha L + beta diag(w) + 1e-5 I (in place over a copy of L) ; rhs = beta w G ;
@@ -136,6 +162,33 @@ __global__ void cg_update_kernel(const float* __restrict__ q, const float* __res
   atomicAdd(&scal[2 * Kc + c], (double)rv * (double)zv);
   atomicAdd(&scal[3 * Kc + c], (double)rv * (double)rv);
 }
+// Same update for Kc dividing the block size (N * Kc a multiple of 256): the two dot products are reduced inside the block
+// first -- 2 Kc fp64 atomics per block instead of 2 per element (4096 per address and iteration at N = 4096).
+__global__ void __launch_bounds__(256)
+cg_update_blockred_kernel(const float* __restrict__ q, const float* __restrict__ dinv, int Kc, float* __restrict__ x,
+                          float* __restrict__ r, float* __restrict__ z, const float* __restrict__ p,
+                          double* __restrict__ scal) {
+  __shared__ double s_rz[256], s_rr[256];
+  const int tid = threadIdx.x;
+  const int t = blockIdx.x * 256 + tid;
+  const int n = t / Kc, c = t % Kc;
+  const double pq = scal[Kc + c];
+  const float alpha = (pq != 0.0) ? (float)(scal[c] / pq) : 0.f;
+  x[t] += alpha * p[t];
+  const float rv = r[t] - alpha * q[t];
+  const float zv = rv * dinv[n];
+  r[t] = rv;
+  z[t] = zv;
+  s_rz[tid] = (double)rv * (double)zv;
+  s_rr[tid] = (double)rv * (double)rv;
+  __syncthreads();
+  if (tid < Kc) {            // 256 % Kc == 0: entries tid, tid + Kc, ... share the column
+    double a = 0.0, b = 0.0;
+    for (int i = tid; i < 256; i += Kc) { a += s_rz[i]; b += s_rr[i]; }
+    atomicAdd(&scal[2 * Kc + tid], a);
+    atomicAdd(&scal[3 * Kc + tid], b);
+  }
+}
 __global__ void cg_dir_kernel(const float* __restrict__ z, int N, int Kc, float* __restrict__ p, double* __restrict__ scal,
                               double* __restrict__ resid_out) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -157,6 +210,103 @@ __global__ void cg_roll_kernel(int Kc, double* __restrict__ scal, double* __rest
     scal[3 * Kc + c] = 0.0;
   }
 }
+// q = A p for the CG loop, A (N, N) row-major, p / q (N, 16) row-major, plus the dot products pq[c] = sum_n p[n,c] q[n,c]
+// (fp64 atomics into scal_pq[0:16]).  A CTA owns 32 rows (4 per warp); 256 columns of A and the matching 256 rows of p are
+// staged in shared memory while the next chunk's global loads are already in flight in registers.  A lane accumulates
+// 4 rows x 16 columns over the columns j = lane (mod 32) of every chunk; a butterfly sums the lanes at the end.
+// (The tcgen05 row GEMM runs this shape -- 4096 x 4096 x 16 -- on 32 CTAs with a serial chunk pipeline: 213 us; this
+// kernel: every SM busy, A streamed once.)
+constexpr int MV_ROWS = 32, MV_JC = 256, MV_PLD = 20;
+constexpr size_t MV_SMEM = sizeof(float) * (MV_ROWS * MV_JC + MV_JC * MV_PLD + 8 * 16);
+__global__ void __launch_bounds__(256, 1)
+lp_matvec16_kernel(const float* __restrict__ A, const float* __restrict__ p, int N, float* __restrict__ q,
+                   double* __restrict__ scal_pq) {
+  extern __shared__ __align__(16) unsigned char mv_smem[];
+  float (*sA)[MV_JC] = reinterpret_cast<float (*)[MV_JC]>(mv_smem);
+  float (*sP)[MV_PLD] = reinterpret_cast<float (*)[MV_PLD]>(mv_smem + sizeof(float) * MV_ROWS * MV_JC);
+  float (*sdot)[16] = reinterpret_cast<float (*)[16]>(mv_smem + sizeof(float) * (MV_ROWS * MV_JC + MV_JC * MV_PLD));
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n0 = blockIdx.x * MV_ROWS;
+  float acc[4][16];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[r][c] = 0.f;
+  float4 ra[8], rp[4];
+  auto fetch = [&](int j0) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int f = tid + 256 * u, r = f >> 6, c4 = f & 63;
+      const int n = n0 + r, j = j0 + c4 * 4;
+      ra[u] = (n < N && j < N) ? *reinterpret_cast<const float4*>(A + (size_t)n * N + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int f = tid + 256 * u, jr = f >> 2, q4 = f & 3;
+      const int j = j0 + jr;
+      rp[u] = (j < N) ? *reinterpret_cast<const float4*>(p + (size_t)j * 16 + q4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  fetch(0);
+  for (int j0 = 0; j0 < N; j0 += MV_JC) {
+    __syncthreads();                                   // the previous chunk has been consumed
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int f = tid + 256 * u;
+      *reinterpret_cast<float4*>(&sA[f >> 6][(f & 63) * 4]) = ra[u];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int f = tid + 256 * u;
+      *reinterpret_cast<float4*>(&sP[f >> 2][(f & 3) * 4]) = rp[u];
+    }
+    __syncthreads();
+    if (j0 + MV_JC < N) fetch(j0 + MV_JC);             // in flight during the FMAs below
+#pragma unroll 2
+    for (int i = 0; i < MV_JC / 32; ++i) {
+      const int j = 32 * i + lane;
+      float pv[16];
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const float4 v = *reinterpret_cast<const float4*>(&sP[j][c4 * 4]);
+        pv[c4 * 4] = v.x; pv[c4 * 4 + 1] = v.y; pv[c4 * 4 + 2] = v.z; pv[c4 * 4 + 3] = v.w;
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float a = sA[warp * 4 + r][j];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) acc[r][c] = fmaf(a, pv[c], acc[r][c]);
+      }
+    }
+  }
+  // lanes -> one value per (row, column): fixed-order butterfly, then lane c keeps column c
+  float dotc = 0.f;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    float mine = 0.f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      float v = acc[r][c];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == c) mine = v;
+    }
+    const int n = n0 + warp * 4 + r;
+    if (lane < 16 && n < N) {
+      q[(size_t)n * 16 + lane] = mine;
+      dotc = fmaf(mine, p[(size_t)n * 16 + lane], dotc);
+    }
+  }
+  if (lane < 16) sdot[warp][lane] = dotc;
+  __syncthreads();
+  if (tid < 16) {
+    double d = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) d += (double)sdot[w][tid];
+    atomicAdd(scal_pq + tid, d);
+  }
+}
+
 __global__ void lp_finish_kernel(const float* __restrict__ x, int N, int K, int Kc, float* __restrict__ Y,
                                  float* __restrict__ Yp) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -206,9 +356,9 @@ extern "C" int wspc_laplacian_sym(const float* X, const float* RGB, int B, int N
   WSPC_REQUIRE(X && RGB && deg_ws && Lout, "laplacian_sym: null pointer");
   WSPC_REQUIRE(B >= 1 && N >= 1 && D1 >= 1 && D1 <= 3 && D2 >= 1 && D2 <= 3, "laplacian_sym: bad shape (D <= 3)");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  dim3 grid((N + 127) / 128, B);
-  laplacian_kernel<false><<<grid, 128, 0, st>>>(X, RGB, N, D1, D2, scale_xyz, scale_rgb, deg_ws, nullptr);
-  laplacian_kernel<true><<<grid, 128, 0, st>>>(X, RGB, N, D1, D2, scale_xyz, scale_rgb, deg_ws, Lout);
+  dim3 grid((N + LAP_ROWS - 1) / LAP_ROWS, B);
+  laplacian_kernel<false><<<grid, 256, 0, st>>>(X, RGB, N, D1, D2, scale_xyz, scale_rgb, deg_ws, nullptr);
+  laplacian_kernel<true><<<grid, 256, 0, st>>>(X, RGB, N, D1, D2, scale_xyz, scale_rgb, deg_ws, Lout);
   count_launch(2);
   WSPC_LAUNCH_CHECK("laplacian_kernel");
   return WSPC_OK;
@@ -243,6 +393,9 @@ extern "C" int wspc_lp_solve(const float* Lm, const float* G, int N, int K, floa
   float* dinv = reinterpret_cast<float*>(wsp); wsp += align_up((size_t)N * 4, 256);
   double* scal = reinterpret_cast<double*>(wsp);           // 4*Kc doubles (Kc <= 64 -> 2 KB) + residuals (512 B)
   double* resid = scal + 4 * 64;
+  static const cudaError_t mv_attr =
+      cudaFuncSetAttribute(lp_matvec16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MV_SMEM);
+  WSPC_CUDA(mv_attr);
   lp_setup_kernel<<<N, 128, 0, st>>>(Lm, G, N, K, Kc, alpha, beta, A, w, rhs, dinv);
   WSPC_CUDA(cudaMemsetAsync(scal, 0, 4096, st));
   const int nt = N * Kc;
@@ -259,13 +412,18 @@ extern "C" int wspc_lp_solve(const float* Lm, const float* G, int N, int K, floa
   bool have_b2 = false;
   const int check_every = 50;
   for (; it < max_iter; ++it) {
-    if (int rc = wspc_conv1x1_rows(&Aop, WSPC_OP_PLAIN, p, Kc, 0, N, Kc, N, &ep, WSPC_EPI_STORE, stream)) return rc;   // q = A p
-    cg_dot_kernel<<<(nt + 255) / 256, 256, 0, st>>>(p, q, N, Kc, scal);
-    cg_update_kernel<<<(nt + 255) / 256, 256, 0, st>>>(q, dinv, N, Kc, x, r, z, p, scal);
+    if (Kc == 16) {   // q = A p and the p.q dots in one pass over A
+      lp_matvec16_kernel<<<(N + MV_ROWS - 1) / MV_ROWS, 256, MV_SMEM, st>>>(A, p, N, q, scal + Kc);
+    } else {
+      if (int rc = wspc_conv1x1_rows(&Aop, WSPC_OP_PLAIN, p, Kc, 0, N, Kc, N, &ep, WSPC_EPI_STORE, stream)) return rc;
+      cg_dot_kernel<<<(nt + 255) / 256, 256, 0, st>>>(p, q, N, Kc, scal);
+    }
+    if (256 % Kc == 0 && nt % 256 == 0) cg_update_blockred_kernel<<<nt / 256, 256, 0, st>>>(q, dinv, Kc, x, r, z, p, scal);
+    else cg_update_kernel<<<(nt + 255) / 256, 256, 0, st>>>(q, dinv, N, Kc, x, r, z, p, scal);
     cg_dir_kernel<<<(nt + 255) / 256, 256, 0, st>>>(z, N, Kc, p, scal, nullptr);
     cg_roll_kernel<<<1, 64, 0, st>>>(Kc, scal, resid);
     count_launch(4);
-    if ((it + 1) % check_every == 0 || it + 1 == max_iter) {
+    if ((it + 1) % check_every == 0 || (it + 1 <= check_every && (it + 1) % 10 == 0) || it + 1 == max_iter) {
       if (!have_b2) {   // ||b||^2 per column, once (host-side convergence control only)
         std::vector<float> hb((size_t)N * Kc);
         WSPC_CUDA(cudaMemcpyAsync(hb.data(), rhs, hb.size() * 4, cudaMemcpyDeviceToHost, st));
