@@ -143,3 +143,79 @@ def test_evaluation_iou_matches_reference_loop():
             n_uni = n_pred + n_gt - n_int
             total += 1.0 if n_uni == 0 else n_int / n_uni
         assert abs(Eval().EvalIoU(pred, gt, oids) - total / len(oids)) < 1e-12
+
+
+def test_trainer_minibatch_helpers_match_reference_loops():
+    """The vectorised pieces of the epoch loops against the reference's per-sample / per-point python
+    (S3DIS_DGCNN_trainer.py:246-252 mask, :265-296 augmentation cases, :473-477 class counters)."""
+    from weaksuppointcloudseg_b200.S3DIS_DGCNN_trainer import S3DIS_Trainer as T
+
+    rng = np.random.default_rng(3)
+    # labelled-point mask
+    pts_idx_list = np.stack([rng.choice(32, 5, replace=False) for _ in range(10)])
+    data_idx = np.array([7, 2, 9])
+    mask = T._mask_from_idx(pts_idx_list, data_idx, 3, 32)
+    for b in range(3):
+        assert sorted(np.flatnonzero(mask[b])) == sorted(pts_idx_list[data_idx[b]])
+    assert T._mask_from_idx(None, data_idx, 3, 32).sum() == 0
+    # the eight augmentation cases: (swap xy, mirror x, mirror y); normalised channels follow (swap / 1 - v)
+    blk = rng.random((1, 16, 9)).astype(np.float32)
+
+    def expect(choice):
+        d = blk[0].copy()
+        swap = choice in (1, 5, 6, 7)
+        mx = choice in (2, 4, 5, 7)
+        my = choice in (3, 4, 6, 7)
+        if swap:
+            d[:, 0], d[:, 1] = blk[0][:, 1], blk[0][:, 0]
+            d[:, 6], d[:, 7] = blk[0][:, 7], blk[0][:, 6]
+        if mx:
+            d[:, 0] = -d[:, 0]
+            d[:, 6] = -d[:, 6] + 1
+        if my:
+            d[:, 1] = -d[:, 1]
+            d[:, 7] = -d[:, 7] + 1
+        return d
+
+    seen = set()
+    for seed in range(40):
+        np.random.seed(seed)
+        choice = int(np.random.choice([0, 1, 2, 3, 4, 5, 6, 7], 1)[0])
+        np.random.seed(seed)                                       # the helper draws with the same call
+        got = T._augment(blk.copy())[0]
+        assert np.allclose(got, expect(choice), atol=1e-7), choice
+        assert np.array_equal(got[:, [2, 3, 4, 5, 8]], blk[0][:, [2, 3, 4, 5, 8]])
+        seen.add(choice)
+    assert seen == set(range(8))
+    # class counters
+    pred, gt = rng.integers(0, 13, (3, 50)), rng.integers(0, 13, (3, 50))
+    pos, tp, cnt = np.zeros(13), np.zeros(13), np.zeros(13)
+    T._count_classes(pred, gt, 13, pos, tp, cnt)
+    pos_r, tp_r, cnt_r = np.zeros(13), np.zeros(13), np.zeros(13)
+    for p_row, l_row in zip(pred, gt):
+        for i in range(50):
+            pos_r[p_row[i]] += 1
+            tp_r[l_row[i]] += float(p_row[i] == l_row[i])
+            cnt_r[l_row[i]] += 1
+    assert np.array_equal(pos, pos_r) and np.array_equal(tp, tp_r) and np.array_equal(cnt, cnt_r)
+
+
+def test_tool_numpy_helpers():
+    from weaksuppointcloudseg_b200 import Tool
+    rng = np.random.default_rng(4)
+    X = rng.standard_normal((20, 3))
+    D = Tool.pdist_np(X)
+    ref = np.sqrt(((X[:, None] - X[None]) ** 2).sum(-1))
+    assert np.allclose(D, ref, atol=1e-6) and np.all(D >= 0)
+    v = rng.random(7) + 0.1
+    assert np.isclose(np.abs(Tool.L1NormVec(v)).sum(), 1.0)
+    assert np.allclose(Tool.L2NormVec(v), np.sqrt(v / np.sum(v ** 2)))
+    for target, replace in ((12, False), (33, True), (20, None)):
+        np.random.seed(9)
+        pts, idx = Tool.ResamplePointCloud(X, target)
+        assert pts.shape == (target, 3) and np.array_equal(pts, X[idx])
+        if replace is False:
+            assert len(set(idx.tolist())) == target
+        if replace is not None:
+            np.random.seed(9)
+            assert np.array_equal(idx, np.random.choice(np.arange(0, 20), target, replace))

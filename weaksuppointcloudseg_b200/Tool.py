@@ -51,6 +51,45 @@ def printout(str, write_flag=False, fid=None, end=''):
         fid.write(str + end)
 
 
+def pdist_np(X):
+    "Euclidean distance matrix of the rows of X (N*D) -> N*N, negatives from cancellation clamped (Util/Tool.py:57-70)"
+    X = np.asarray(X)
+    sq = np.sum(X ** 2, axis=-1, keepdims=True)
+    return np.sqrt(np.maximum(sq + sq.T - 2 * (X @ X.T), 0.))
+
+
+def L2NormVec(x):
+    "The reference's `L2 normalize` (Util/Tool.py:197-204) -- note it returns sqrt(x / sum(x^2)), kept as written"
+    return np.sqrt(x / np.sum(x ** 2))
+
+
+def L1NormVec(x):
+    "x / sum(|x|) (Util/Tool.py:206-213)"
+    return x / np.sum(np.abs(x))
+
+
+def ResamplePointCloud(X, target_num_pts):
+    """Resample N*D points to target_num_pts rows: without replacement when shrinking, with replacement when growing
+    (Util/Tool.py:270-289; same np.random.choice calls).  -> (points, sample indices)"""
+    N = X.shape[0]
+    if N == target_num_pts:
+        return X, np.arange(0, N)
+    samp_idx = np.random.choice(np.arange(0, N), target_num_pts, N < target_num_pts)
+    return X[samp_idx, :], samp_idx
+
+
+def pdist2(X, Y):
+    "Squared distances between the rows of X (B*N*D) and Y (B*M*D) -> B*N*M, CUDA tensors (Util/Tool.py:30-42)"
+    import torch
+    return (X ** 2).sum(-1, keepdim=True) + (Y ** 2).sum(-1).unsqueeze(1) - 2 * torch.einsum('ijk,ilk->ijl', X, Y)
+
+
+def pdist(X):
+    "Euclidean distance matrix per cloud, X B*N*D -> B*N*N (Util/Tool.py:44-55); squared distances from the wspc kernel"
+    from . import ops
+    return ops.pairwise_distance(X, ops.DIST_SMOOTH).sqrt()
+
+
 def batch_gather_v1(X, idx):
     '''
     batch gather function (Util/Tool.py:72-104)
