@@ -95,3 +95,27 @@ def test_missing_files_are_loud(tmp_path):
         S3DIS_IO(str(tmp_path / 'nowhere'))
     with pytest.raises(FileNotFoundError):
         ShapeNetIO(str(tmp_path / 'nowhere'))
+
+
+def test_samp_index_mat_layouts(tmp_path):
+    """SampIndex_m-*.mat: dense matrix for m > 0, (1, n) object array of (1, n_i) rows for m == 0 (the layouts of the
+    reference's Dataset/*/Preprocess fixtures), unpacked as train_S3DIS.py:92-101 / train_ShapeNet.py:91-96 do."""
+    import scipy.io as scio
+    from weaksuppointcloudseg_b200 import DataIO_S3DIS, DataIO_ShapeNet
+    from weaksuppointcloudseg_b200.S3DIS_DGCNN_trainer import S3DIS_Trainer
+    rng = np.random.default_rng(2)
+    dense = np.stack([rng.choice(64, 4, replace=False) for _ in range(9)]).astype(np.int64)
+    scio.savemat(str(tmp_path / 'SampIndex_m-0.010.mat'), {'pts_idx_list': dense})
+    got = DataIO_S3DIS.LoadSampIndex(str(tmp_path / 'SampIndex_m-0.010.mat'), 0.01)
+    assert np.array_equal(got, dense)
+    ragged = np.empty((1, 9), dtype=object)
+    rows = [rng.choice(64, int(n), replace=False).astype(np.int64) for n in rng.integers(1, 6, 9)]
+    for i, r in enumerate(rows):
+        ragged[0, i] = r[None, :]
+    scio.savemat(str(tmp_path / 'SampIndex_m-0.000.mat'), {'pts_idx_list': ragged})
+    got0 = DataIO_S3DIS.LoadSampIndex(str(tmp_path / 'SampIndex_m-0.000.mat'), 0)
+    assert len(got0) == 9 and all(np.array_equal(a, b) for a, b in zip(got0, rows))
+    mask = S3DIS_Trainer._mask_from_idx(got0, np.array([3, 8]), 2, 64)          # what the epoch loop builds from it
+    assert mask.sum() == len(rows[3]) + len(rows[8]) and mask[1, rows[8]].all()
+    f, d, p = DataIO_ShapeNet.LoadSampIndex(str(tmp_path / 'SampIndex_m-0.010.mat'))
+    assert f.shape == (9,) and not f.any() and np.array_equal(d, np.arange(9)) and np.array_equal(p, dense)

@@ -231,3 +231,15 @@ class S3DIS_Test:
     def sample_data_label(self, data, label, num_sample):
         new_data, idx = self.sample_data(data, num_sample)
         return new_data, label[idx]
+
+
+def LoadSampIndex(save_filepath, m=None):
+    """The labelled-point lists `Dataset/S3DIS/Preprocess/SampIndex_m-<m>.mat` exactly as train_S3DIS.py:92-101 unpacks them:
+    a dense (n_blocks, n_labelled) int matrix for m > 0; for m == 0 (one point per class present in the block) the .mat
+    holds a (1, n_blocks) object array of (1, n_i) rows, returned as a list of 1-D arrays.  Indexable by the loader's
+    `data_idx`, which is what `TrainOneEpoch(_Full)` does."""
+    import scipy.io as scio
+    pts = scio.loadmat(save_filepath)['pts_idx_list']
+    if pts.dtype == object or (m is not None and m == 0):
+        return [np.asarray(pts[0, b_i][0]).reshape(-1) for b_i in range(pts.shape[1])]
+    return pts

@@ -158,3 +158,12 @@ class ShapeNetIO:
     def pc_normalize(self, pc):
         pc = pc - np.mean(pc, axis=0)
         return pc / np.max(np.sqrt(np.sum(pc ** 2, axis=1)))
+
+
+def LoadSampIndex(save_filepath):
+    """`Dataset/ShapeNet/Preprocess/SampIndex_m-<m>.mat` as train_ShapeNet.py:91-96 uses it: the (n_shapes, n_labelled)
+    matrix of labelled point indices, with file index 0 and data index i for row i (the single concatenated training array
+    of ShapeNetIO.LoadTrainValFiles).  -> (file_idx_list, data_idx_list, pts_idx_list)"""
+    import scipy.io as scio
+    pts_idx_list = scio.loadmat(save_filepath)['pts_idx_list']
+    return np.zeros(shape=[pts_idx_list.shape[0]]), np.arange(0, pts_idx_list.shape[0]), pts_idx_list
