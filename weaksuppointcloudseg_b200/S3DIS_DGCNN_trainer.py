@@ -434,8 +434,15 @@ class S3DIS_Trainer():
             np.savez(os.path.join(os.path.dirname(os.path.abspath(save_filepath)), best_filename + '.npz'), **blob)
 
     def RestoreCheckPoint(self, filepath):
-        blob = np.load(filepath if filepath.endswith('.npz') else filepath + '.npz')
+        """`<filepath>.npz` written by SaveCheckPoint, or -- when `<filepath>.index` / `.data-00000-of-00001` exist -- a
+        checkpoint written by the reference's tf.train.Saver (same variable names; tf_checkpoint.py)."""
+        from . import tf_checkpoint
         vs = self.engine.vs
+        if not os.path.exists(filepath if filepath.endswith('.npz') else filepath + '.npz') and tf_checkpoint.exists(filepath):
+            shapes = {k: tuple(vs.get(k).shape) for k in vs.trainable_names + vs.state_names}
+            blob = tf_checkpoint.to_store_blob(tf_checkpoint.read(filepath), vs.trainable_names, vs.state_names, shapes)
+        else:
+            blob = np.load(filepath if filepath.endswith('.npz') else filepath + '.npz')
         vs.load({k: blob[k] for k in vs.trainable_names + vs.state_names})
         vs.step = int(blob['Variable'])
         vs.adam_m.copy_(torch.from_numpy(blob['__adam_m']))
