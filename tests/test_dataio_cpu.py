@@ -119,3 +119,17 @@ def test_samp_index_mat_layouts(tmp_path):
     assert mask.sum() == len(rows[3]) + len(rows[8]) and mask[1, rows[8]].all()
     f, d, p = DataIO_ShapeNet.LoadSampIndex(str(tmp_path / 'SampIndex_m-0.010.mat'))
     assert f.shape == (9,) and not f.any() and np.array_equal(d, np.arange(9)) and np.array_equal(p, dense)
+
+
+def test_h5_multidimensional_chunks_shuffle_and_two_level_btree(tmp_path):
+    """The shapes h5py's auto-chunking produces for the reference's files: chunks over every axis with ragged edges, the
+    byte-shuffle filter in front of deflate, and more chunks than one B-tree node holds (a level-1 node over leaves)."""
+    rng = np.random.default_rng(1)
+    d = {'data': rng.standard_normal((37, 130, 9)).astype(np.float32),
+         'label': rng.integers(0, 13, (37, 130)).astype(np.uint8),
+         'pid': rng.integers(0, 50, (300,)).astype(np.int32)}
+    p = str(tmp_path / 'b.h5')
+    _h5.write(p, d, chunk_shape={3: (8, 50, 4), 2: (5, 64), 1: (7,)}, shuffle=True, node_entries=6)
+    back = _h5.read(p)                                           # data: 5 x 3 x 3 = 45 chunks -> 8 leaves under one node
+    for k in d:
+        assert back[k].dtype == d[k].dtype and np.array_equal(back[k], d[k]), k

@@ -311,9 +311,11 @@ def _dtype_msg(dt):
     raise NotImplementedError("dtype %s" % dt)
 
 
-def write(path, arrays, chunk_rows=64, level=4):
-    """Write {name: ndarray} as chunked, gzip-compressed datasets (chunks span `chunk_rows` of axis 0 and all of the rest;
-    the chunks of data_prep_util.py:64-77 are h5py's auto-chunks — any chunk shape reads back the same)."""
+def write(path, arrays, chunk_rows=64, level=4, chunk_shape=None, shuffle=False, node_entries=64):
+    """Write {name: ndarray} as chunked, gzip-compressed datasets.  Default chunks span `chunk_rows` of axis 0 and all of the
+    rest; `chunk_shape` (a tuple per rank, e.g. {3: (8, 100, 2)}) gives multi-dimensional chunks with ragged edges like
+    h5py's auto-chunking of data_prep_util.py:64-77; `shuffle` adds the byte-shuffle filter in front of deflate; more than
+    `node_entries` chunks make a two-level chunk B-tree (HDF5's own nodes hold 64 entries)."""
     names = sorted(arrays)
     blob = bytearray(b"\0" * 96)                                 # superblock v0 (56 + 40-byte root entry)
 
@@ -330,24 +332,55 @@ def write(path, arrays, chunk_rows=64, level=4):
         a = a.astype(a.dtype.newbyteorder("<"), copy=False)
         rank = a.ndim
         cdims = (min(chunk_rows, max(a.shape[0], 1)),) + a.shape[1:]
+        if chunk_shape and rank in chunk_shape:
+            cdims = tuple(chunk_shape[rank])
         entries = []
-        for r0 in range(0, a.shape[0], cdims[0]):
+        grid = [range(0, max(s_, 1), c) for s_, c in zip(a.shape, cdims)]
+        for offs in np.ndindex(*[len(g) for g in grid]):
+            o = tuple(g[i] for g, i in zip(grid, offs))
             ch = np.zeros(cdims, a.dtype)
-            part = a[r0:r0 + cdims[0]]
-            ch[:part.shape[0]] = part
-            z = zlib.compress(ch.tobytes(), level)
-            entries.append(((r0,) + (0,) * (rank - 1), len(z), alloc(z)))
-        # one leaf chunk B-tree node: n keys + children + the closing key
-        node = bytearray(b"TREE" + struct.pack("<BBHQQ", 1, 0, len(entries), _UNDEF, _UNDEF))
-        for offs, size, addr in entries:
-            node += struct.pack("<II", size, 0) + struct.pack("<%dQ" % (rank + 1), *offs, 0) + struct.pack("<Q", addr)
-        node += struct.pack("<II", 0, 0) + struct.pack("<%dQ" % (rank + 1), a.shape[0], *([0] * rank))
-        bt = alloc(node)
+            part = a[tuple(slice(x, x + c) for x, c in zip(o, cdims))]
+            ch[tuple(slice(0, n) for n in part.shape)] = part
+            raw = ch.tobytes()
+            if shuffle:
+                raw = np.frombuffer(raw, np.uint8).reshape(-1, a.dtype.itemsize).T.tobytes()
+            z = zlib.compress(raw, level)
+            entries.append((o, len(z), alloc(z)))
+
+        def key(offs, size):
+            return struct.pack("<II", size, 0) + struct.pack("<%dQ" % (rank + 1), *offs, 0)
+
+        closing = key(tuple(a.shape), 0)
+
+        def leaf(part, last_key):
+            node = bytearray(b"TREE" + struct.pack("<BBHQQ", 1, 0, len(part), _UNDEF, _UNDEF))
+            for offs, size, addr in part:
+                node += key(offs, size) + struct.pack("<Q", addr)
+            return alloc(node + last_key)
+
+        if len(entries) <= node_entries:
+            node = None
+            bt_addr = leaf(entries, closing)
+        else:                                                    # level-1 node over leaves of `node_entries` chunks
+            groups = [entries[i:i + node_entries] for i in range(0, len(entries), node_entries)]
+            kids = []
+            for gi, g in enumerate(groups):
+                nxt = key(groups[gi + 1][0][0], groups[gi + 1][0][1]) if gi + 1 < len(groups) else closing
+                kids.append((g[0], leaf(g, nxt)))
+            node = bytearray(b"TREE" + struct.pack("<BBHQQ", 1, 1, len(kids), _UNDEF, _UNDEF))
+            for (offs, size, _a), addr in kids:
+                node += key(offs, size) + struct.pack("<Q", addr)
+            bt_addr = alloc(node + closing)
+        bt = bt_addr
         msgs = _msg(0x01, struct.pack("<BBB5x", 1, rank, 1) + struct.pack("<%dQ" % rank, *a.shape)
                     + struct.pack("<%dQ" % rank, *a.shape))
         msgs += _msg(0x03, _dtype_msg(a.dtype), flags=1)
-        msgs += _msg(0x0B, struct.pack("<BB6x", 1, 1) + struct.pack("<HHHH", 1, 8, 1, 1) + b"deflate\0"
-                     + struct.pack("<II", level, 0))
+        deflate = struct.pack("<HHHH", 1, 8, 1, 1) + b"deflate\0" + struct.pack("<II", level, 0)
+        if shuffle:
+            msgs += _msg(0x0B, struct.pack("<BB6x", 1, 2) + struct.pack("<HHHH", 2, 8, 1, 1) + b"shuffle\0"
+                         + struct.pack("<II", a.dtype.itemsize, 0) + deflate)
+        else:
+            msgs += _msg(0x0B, struct.pack("<BB6x", 1, 1) + deflate)
         msgs += _msg(0x08, struct.pack("<BBB", 3, 2, rank + 1) + struct.pack("<Q", bt)
                      + struct.pack("<%dI" % (rank + 1), *cdims, a.dtype.itemsize))
         hdr_addr[name] = alloc(struct.pack("<BBHII4x", 1, 0, 4, 1, len(msgs)) + msgs)
