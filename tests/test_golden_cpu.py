@@ -94,3 +94,29 @@ def test_oracle_loss_gradients_by_finite_differences():
         d[b, n, c] = eps
         fd = (total(Z.detach() + d) - total(Z.detach() - d)) / (2 * eps)
         assert abs(float(fd) - float(g[b, n, c])) <= 1e-6 + 1e-5 * abs(float(fd))
+
+
+def test_cfg1_shapenet_airplane_one_cloud_forward_ce():
+    """BASELINE cfg-1, the reference's CPU-runnable plumbing case: one Airplane cloud, N=2048, k=20, Plain style
+    (forward + masked cross-entropy + backward) through the oracle at full size; properties only (no TF to compare with):
+    identity input transform at initialisation, self-inclusive kNN, CE near ln 50 for Xavier weights, finite gradients."""
+    import torch
+    from oracle import dgcnn as od
+    from weaksuppointcloudseg_b200 import synthetic as syn
+
+    X, lab, Y, M, seg = syn.shapenet_batch(1, N=2048, n_labelled=204, seed=7, category=0)
+    X, lab, Y, M = (torch.from_numpy(a[0:1]) for a in (X, lab, Y, M))
+    assert int(lab.argmax()) == 0 and set(np.unique(seg[0])) <= {0, 1, 2, 3} and int(M.sum()) == 204
+    p = od.to_torch(od.init_params(od.SHAPENET_LAYERS, seed=1234, shapenet=True))
+    rec = {}
+    Z = od.get_model_shapenet(p, X, lab, True, bn_decay=0.5, dropout_masks=(torch.ones(1, 2048, 256), torch.ones(1, 2048, 256)),
+                              rec=rec)
+    assert Z.shape == (1, 2048, 50)
+    assert torch.allclose(rec["transform"][0], torch.eye(3), atol=1e-6)            # T-net: W = 0, b = eye (transform_nets.py:41-50)
+    idx0 = rec["knn0/idx"]
+    assert idx0.shape == (1, 2048, 20) and bool((idx0[0, :, 0] == torch.arange(2048)).all())
+    loss = od.seg_loss(Z, Y, M)
+    assert abs(float(loss.detach()) - np.log(50.0)) < 1.5
+    loss.backward()
+    g = p["adj_conv1/weights"].grad
+    assert g is not None and bool(torch.isfinite(g).all()) and float(g.abs().max()) > 0
