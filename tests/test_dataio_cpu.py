@@ -133,3 +133,28 @@ def test_h5_multidimensional_chunks_shuffle_and_two_level_btree(tmp_path):
     back = _h5.read(p)                                           # data: 5 x 3 x 3 = 45 chunks -> 8 leaves under one node
     for k in d:
         assert back[k].dtype == d[k].dtype and np.array_equal(back[k], d[k]), k
+
+
+def test_h5_round_trip_property(tmp_path):
+    """Randomised shapes, dtypes and chunk shapes (ragged edges, more chunks than a node holds) read back bit-identically."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    dtypes = [np.float32, np.float64, np.uint8, np.int8, np.int16, np.int32, np.int64, np.uint16]
+
+    @settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+    @given(st.integers(0, 2 ** 31 - 1), st.integers(1, 3), st.integers(0, len(dtypes) - 1), st.booleans(), st.integers(2, 9))
+    def run(seed, rank, dt_i, shuffle, node_entries):
+        rng = np.random.default_rng(seed)
+        shape = tuple(int(x) for x in rng.integers(1, 23, rank))
+        chunk = tuple(int(rng.integers(1, s + 3)) for s in shape)
+        dt = np.dtype(dtypes[dt_i])
+        a = (rng.standard_normal(shape) * 100).astype(dt) if dt.kind == 'f' else \
+            rng.integers(np.iinfo(dt).min, np.iinfo(dt).max, shape, dtype=dt, endpoint=True)
+        p = str(tmp_path / ('p%d.h5' % (seed % 7)))
+        _h5.write(p, {'x': a, 'second/name'.replace('/', '_'): a[:1]}, chunk_shape={rank: chunk}, shuffle=shuffle,
+                  node_entries=node_entries)
+        back = _h5.read(p)
+        assert back['x'].dtype == dt and back['x'].shape == shape and np.array_equal(back['x'], a)
+        assert np.array_equal(back['second_name'], a[:1])
+
+    run()

@@ -104,3 +104,31 @@ def test_restore_checkpoint_reads_a_tf_bundle(tmp_path):
         n = int(np.prod(shape))
         assert np.array_equal(dst.adam_m[o:o + n].numpy(), tf_vars[k + '/Adam'].reshape(-1)), k
         assert np.array_equal(dst.adam_v[o:o + n].numpy(), tf_vars[k + '/Adam_1'].reshape(-1)), k
+
+
+def test_bundle_round_trip_property(tmp_path):
+    """Randomised variable sets: names with shared prefixes across block boundaries, scalars, several dtypes."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    dtypes = [np.float32, np.float64, np.int32, np.int64, np.uint8, np.float16]
+
+    @settings(max_examples=30, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+    @given(st.integers(0, 2 ** 31 - 1), st.integers(1, 60), st.integers(1, 20))
+    def run(seed, n_vars, per_block):
+        rng = np.random.default_rng(seed)
+        v = {}
+        for i in range(n_vars):
+            scope = 'layer%d' % rng.integers(0, 6) + '/' * int(rng.integers(0, 2)) + 'bn' * int(rng.integers(0, 2))
+            name = '%s/v%d' % (scope, i)
+            rank = int(rng.integers(0, 4))
+            shape = tuple(int(x) for x in rng.integers(1, 6, rank))
+            dt = np.dtype(dtypes[int(rng.integers(0, len(dtypes)))])
+            v[name] = (rng.standard_normal(shape) * 10).astype(dt)
+        prefix = str(tmp_path / ('c%d' % (seed % 5)))
+        tfc.write(prefix, v, entries_per_block=per_block)
+        back = tfc.read(prefix)
+        assert sorted(back) == sorted(v)
+        for k in v:
+            assert back[k].dtype == v[k].dtype and back[k].shape == v[k].shape and np.array_equal(back[k], v[k]), k
+
+    run()
