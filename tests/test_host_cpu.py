@@ -219,3 +219,109 @@ def test_tool_numpy_helpers():
         if replace is not None:
             np.random.seed(9)
             assert np.array_equal(idx, np.random.choice(np.arange(0, 20), target, replace))
+
+
+def test_train_epoch_loop_feeds_with_and_without_prefetch(tmp_path, monkeypatch):
+    """TrainOneEpoch_Full on the real S3DIS_IO loader with the device step replaced by a recorder: the worker-thread
+    prefetch delivers exactly the feeds of the in-line loop (same numpy random stream), in order; fp32 one-hot feeds;
+    interleaved [sample, partner] rows; an exception in the assembly surfaces in the caller."""
+    import types
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import dataio_fab as fab
+    from weaksuppointcloudseg_b200 import S3DIS_DGCNN_trainer as T
+    from weaksuppointcloudseg_b200.DataIO_S3DIS import S3DIS_IO
+
+    root = fab.make_s3dis(str(tmp_path / 's3dis'), n_point=32)
+    pts_idx_list = np.stack([np.random.default_rng(i).choice(32, 4, replace=False) for i in range(13)])
+
+    def run(prefetch):
+        monkeypatch.setenv('WSPC_PREFETCH', '1' if prefetch else '0')
+        ld = S3DIS_IO(root, 13, batchsize=2, NUM_POINT=32)
+        ld.LoadS3DIS_AllData()
+        ld.CreateDataSplit(5)
+        tr = T.S3DIS_Trainer(5, device='cpu', seed=0)
+        tr.engine = types.SimpleNamespace(B=4)
+        tr.epoch, tr.rampup = 3, 0                                  # augmentation on
+        feeds = []
+
+        def fake_train_batch(data_feed, seg_onehot_feed, Mask_bin_feed):
+            feeds.append((data_feed.copy(), seg_onehot_feed.copy(), Mask_bin_feed.copy()))
+            z = np.zeros(seg_onehot_feed.shape, np.float32)
+            z[..., 3] = 1                                           # predicts class 3 everywhere
+            return 1.0 + len(feeds), 0.1, 0.2, 0.3, z
+
+        tr.train_batch = fake_train_batch
+        np.random.seed(11)
+        ld.Shuffle_TrainSet()
+        loss, acc = tr.TrainOneEpoch_Full(ld, pts_idx_list, 2)
+        assert tr.epoch == 4 and ld.train_samp_ptr == 0
+        return feeds, loss, acc
+
+    f1, l1, a1 = run(True)
+    f0, l0, a0 = run(False)
+    assert len(f1) == len(f0) == 5 and l1 == l0 and a1 == a0
+    for (d1, y1, m1), (d0, y0, m0) in zip(f1, f0):
+        assert np.array_equal(d1, d0) and np.array_equal(y1, y0) and np.array_equal(m1, m0)
+        assert y1.dtype == np.float32 and d1.dtype == np.float32 and d1.shape == (4, 32, 9) and y1.shape == (4, 32, 13)
+        assert np.array_equal(y1[0::2], y1[1::2]) and np.array_equal(m1[0::2], m1[1::2]) and m1.sum() == 4 * 4
+        assert np.array_equal(d1[0::2, :, 2:6], d1[1::2, :, 2:6])    # z and rgb are untouched by the augmentation
+    assert any(not np.array_equal(d[0::2], d[1::2]) for d, _, _ in f1)
+
+    def boom():
+        yield 1
+        raise RuntimeError("assembly failed")
+
+    got = []
+    with pytest.raises(RuntimeError, match="assembly failed"):
+        for x in T.prefetched(boom(), enabled=True):
+            got.append(x)
+    assert got == [1]
+
+
+def test_shapenet_train_epoch_loop_feeds(tmp_path, monkeypatch):
+    """ShapeNet `_train_epoch` (Full and Plain) on the real ShapeNetIO with a recording device step: prefetched == in-line,
+    the tail batch is skipped, feeds are fp32 with the Siamese rows interleaved."""
+    import types
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import dataio_fab as fab
+    from weaksuppointcloudseg_b200.DataIO_ShapeNet import ShapeNetIO
+    from weaksuppointcloudseg_b200.ShapeNet_DGCNN_trainer import ShapeNet_Trainer
+
+    root = fab.make_shapenet(str(tmp_path / 'shapenet'), n_point=24)
+    pts_idx_list = np.stack([np.random.default_rng(i).choice(24, 3, replace=False) for i in range(11)])
+    file_idx_list, data_idx_list = np.zeros(11, np.int64), np.arange(11)
+
+    def run(prefetch, siamese):
+        monkeypatch.setenv('WSPC_PREFETCH', '1' if prefetch else '0')
+        ld = ShapeNetIO(root, batchsize=2)
+        ld.LoadTrainValFiles()
+        tr = ShapeNet_Trainer(device='cpu', seed=0)
+        tr.engine = types.SimpleNamespace(B=4 if siamese else 2)
+        tr.epoch, tr.rampup = 2, 0
+        feeds = []
+
+        def fake_train_batch(data_feed, label_onehot_feed, seg_onehot_feed, Mask_bin_feed):
+            feeds.append(tuple(np.array(a) for a in (data_feed, label_onehot_feed, seg_onehot_feed, Mask_bin_feed)))
+            return 2.0, 0., 0., 0., np.zeros(seg_onehot_feed.shape, np.float32)
+
+        tr.train_batch = fake_train_batch
+        np.random.seed(4)
+        ld.Shuffle_TrainSet()
+        fn = tr.TrainOneEpoch_Full if siamese else tr.TrainOneEpoch
+        loss, acc = fn(ld, file_idx_list, data_idx_list, pts_idx_list)
+        assert tr.epoch == 3 and loss == 2.0
+        return feeds, acc
+
+    for siamese in (True, False):
+        f1, a1 = run(True, siamese)
+        f0, a0 = run(False, siamese)
+        rep = 2 if siamese else 1
+        assert len(f1) == len(f0) == 5 and a1 == a0                  # 11 shapes, batches of 2, the tail of 1 is skipped
+        for x1, x0 in zip(f1, f0):
+            assert all(np.array_equal(p, q) and p.dtype == np.float32 for p, q in zip(x1, x0))
+            d, lab, y, m = x1
+            assert d.shape == (2 * rep, 24, 3) and lab.shape == (2 * rep, 16) and y.shape == (2 * rep, 24, 50)
+            assert m.sum() == 2 * rep * 3
+            if siamese:
+                assert np.array_equal(y[0::2], y[1::2]) and np.array_equal(lab[0::2], lab[1::2])
+                assert np.abs(np.abs(d[1::2]) - np.abs(d[0::2])).max() < 0.05     # jitter (+ optional mirror of axis 2)

@@ -39,6 +39,40 @@ def xavier_params(layers, seed=None, shapenet=False):
     return p
 
 
+def prefetched(gen, enabled=None):
+    """Iterate `gen` one item ahead on a worker thread: the host-side assembly of mini-batch i+1 (tens of ms of numpy) runs
+    while the device executes step i (the main thread then sits in a stream synchronise with the GIL released).  Items come
+    out in order; an exception in the generator is re-raised at the consumer.  WSPC_PREFETCH=0 turns it off."""
+    if enabled is None:
+        enabled = os.environ.get('WSPC_PREFETCH', '1') != '0'
+    if not enabled:
+        yield from gen
+        return
+    import queue
+    import threading
+    q = queue.Queue(maxsize=1)
+    end = object()
+
+    def work():
+        try:
+            for item in gen:
+                q.put((None, item))
+            q.put((None, end))
+        except BaseException as exc:      # noqa: BLE001  (handed to the consumer)
+            q.put((exc, None))
+
+    worker = threading.Thread(target=work, name='wspc-prefetch', daemon=True)
+    worker.start()
+    while True:
+        exc, item = q.get()
+        if exc is not None:
+            raise exc
+        if item is end:
+            break
+        yield item
+    worker.join()
+
+
 class S3DIS_Trainer():
 
     def __init__(self, test_area=5, device=None, seed=None):
@@ -318,7 +352,7 @@ class S3DIS_Trainer():
             data = np.asarray(data, np.float32)
             seg = np.asarray(seg).astype(np.int64)
             Mask_bin_feed = self._mask_from_idx(pts_idx_list, data_idx, mb_size, data.shape[1])
-            loss_mb, _, _, _, Z_prob_mb = self.train_batch(data, Tool.OnehotEncode(seg, 13), Mask_bin_feed)
+            loss_mb, _, _, _, Z_prob_mb = self.train_batch(data, Tool.OnehotEncode(seg, 13, np.float32), Mask_bin_feed)
             acc = float(np.mean(np.argmax(Z_prob_mb, axis=-1) == seg))
             avg_loss = (avg_loss * data_cnt + loss_mb * mb_size) / (data_cnt + mb_size)
             avg_acc = (avg_acc * data_cnt + acc * mb_size) / (data_cnt + mb_size)
@@ -329,18 +363,14 @@ class S3DIS_Trainer():
         self._end_train_epoch(Loader)
         return avg_loss, avg_acc
 
-    def TrainOneEpoch_Full(self, Loader, pts_idx_list=None, batch_size=12):
-        '''
-        Function to train one epoch (TrainOneEpoch_Full, :221-349).  `Loader` follows S3DIS_IO.NextBatch_TrainSet_v1
-        (DataIO_S3DIS.py:127-154); the mini-batch assembly (mask from pts_idx_list, Siamese partner, interleaving, one-hot)
-        is vectorised instead of the per-point loops.  `batch_size` = samples per step (half the graph's clouds).
-        '''
-        batch_cnt, data_cnt, avg_loss, avg_acc = 1, 0, 0., 0.
+    def _full_batches(self, Loader, pts_idx_list):
+        """Generator of the Full-style feeds of one epoch: (data_feed (2b,N,9), seg_onehot_feed (2b,N,13) fp32,
+        Mask_bin_feed (2b,N), seg (b,N), mb_size), rows interleaved [sample, Siamese partner] (:237-315)."""
         half = self.engine.B // 2
         while True:
             SuccessFlag, data, seg, weak_seg_onehot, mb_size, data_idx = Loader.NextBatch_TrainSet_v1()
             if not SuccessFlag or mb_size < half:        # short last batch dropped (:242-243); the graph batch is static
-                break
+                return
             data = np.asarray(data, np.float32)
             seg = np.asarray(seg).astype(np.int64)
             N = data.shape[1]
@@ -350,8 +380,18 @@ class S3DIS_Trainer():
             # The partner is an augmented COPY once the ramp-up epoch is reached (:261); the reference augments in place
             # through an alias, so both rows of its pair end up augmented — consciously not kept.
             data_feed[1::2] = self._augment(data.copy()) if self.epoch >= self.rampup else data
-            seg_onehot_feed = Tool.OnehotEncode(np.repeat(seg, 2, axis=0), 13)
-            Mask_bin_feed = np.repeat(mask, 2, axis=0)
+            seg_onehot_feed = Tool.OnehotEncode(np.repeat(seg, 2, axis=0), 13, np.float32)
+            yield data_feed, seg_onehot_feed, np.repeat(mask, 2, axis=0), seg, mb_size
+
+    def TrainOneEpoch_Full(self, Loader, pts_idx_list=None, batch_size=12):
+        '''
+        Function to train one epoch (TrainOneEpoch_Full, :221-349).  `Loader` follows S3DIS_IO.NextBatch_TrainSet_v1
+        (DataIO_S3DIS.py:127-154); the mini-batch assembly (mask from pts_idx_list, Siamese partner, interleaving, one-hot)
+        is vectorised instead of the per-point loops and runs one batch ahead on a worker thread, under the device step of
+        the previous batch (`prefetched`).  `batch_size` = samples per step (half the graph's clouds).
+        '''
+        batch_cnt, data_cnt, avg_loss, avg_acc = 1, 0, 0., 0.
+        for data_feed, seg_onehot_feed, Mask_bin_feed, seg, mb_size in prefetched(self._full_batches(Loader, pts_idx_list)):
             loss_mb, loss_siam, loss_inex, loss_smooth, Z_prob_mb = self.train_batch(data_feed, seg_onehot_feed,
                                                                                     Mask_bin_feed)
             pred = np.argmax(Z_prob_mb[0::2], axis=-1)   # (:326-339)
@@ -389,7 +429,7 @@ class S3DIS_Trainer():
             seg_feed = np.concatenate([seg_mb, np.repeat(seg_mb[0:1], pad, 0)], 0) if pad else seg_mb
             if siamese:
                 data_feed, seg_feed = np.repeat(data_feed, 2, axis=0), np.repeat(seg_feed, 2, axis=0)
-            loss_mb, Z_prob_mb = self.eval_batch(data_feed, Tool.OnehotEncode(seg_feed, C),
+            loss_mb, Z_prob_mb = self.eval_batch(data_feed, Tool.OnehotEncode(seg_feed, C, np.float32),
                                                  np.ones(seg_feed.shape, np.float32))
             Z_prob_mb = Z_prob_mb[0:2 * mb_size:2] if siamese else Z_prob_mb[0:mb_size]
             pred_mb = np.argmax(Z_prob_mb, axis=-1)

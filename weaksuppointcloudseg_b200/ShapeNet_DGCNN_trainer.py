@@ -13,7 +13,7 @@ import torch
 
 from . import Tool
 from .engine_shapenet import LAYERS, ShapeNetEngine
-from .S3DIS_DGCNN_trainer import S3DIS_Trainer, xavier_params
+from .S3DIS_DGCNN_trainer import S3DIS_Trainer, prefetched, xavier_params
 
 
 class ShapeNet_Trainer(S3DIS_Trainer):
@@ -107,13 +107,32 @@ class ShapeNet_Trainer(S3DIS_Trainer):
         pts_idx_list) as in :243-251; Siamese partner = jitter 2e-3 * extent + random mirror of axis 2 once the ramp-up
         epoch is reached (:260-275), a plain copy before; rows interleaved [sample, partner]."""
         batch_cnt, data_cnt, avg_loss, avg_acc = 1, 0, 0., 0.
+        rep = 2 if siamese else 1
+        feeds = prefetched(self._train_batches(Loader, file_idx_list, data_idx_list, pts_idx_list, siamese))
+        for data_feed, label_onehot_feed, seg_onehot_feed, Mask_bin_feed, label, seg, mb_size in feeds:
+            loss_mb, _, _, _, Z_prob_mb = self.train_batch(data_feed, label_onehot_feed, seg_onehot_feed, Mask_bin_feed)
+            pred = np.stack([self._restrict_to_category(Z_prob_mb[rep * b_i],
+                                                        Loader.object2setofoid[Loader.objcats[label[b_i, 0]]])
+                             for b_i in range(mb_size)])
+            avg_loss = (avg_loss * data_cnt + loss_mb * mb_size) / (data_cnt + mb_size)
+            avg_acc = (avg_acc * data_cnt + float(np.mean(pred == seg)) * mb_size) / (data_cnt + mb_size)
+            data_cnt += mb_size
+            print('\rBatch {:d} TrainedSamp {:d}  Avg Loss {:.4f} Avg Acc {:.2f}%'.format(batch_cnt, data_cnt, avg_loss,
+                                                                                         100 * avg_acc), end='')
+            batch_cnt += 1
+        self.epoch += 1
+        return avg_loss, avg_acc
+
+    def _train_batches(self, Loader, file_idx_list, data_idx_list, pts_idx_list, siamese):
+        """Generator of one epoch's feeds (host numpy only; runs one batch ahead of the device step under `prefetched`):
+        (data_feed, label_onehot_feed, seg_onehot_feed, Mask_bin_feed, label (b,1), seg (b,N), mb_size)."""
         rng = np.random.default_rng(1000 + self.epoch)
         file_idx_list = None if file_idx_list is None else np.asarray(file_idx_list)
         data_idx_list = None if data_idx_list is None else np.asarray(data_idx_list)
         while True:
             SuccessFlag, data, label, seg, _, mb_size, file_idx, data_idx = Loader.NextBatch_TrainSet(shuffle_flag=True)
             if not SuccessFlag:
-                break
+                return
             if mb_size < (self.engine.B // 2 if siamese else self.engine.B):   # short batches are skipped (:239-240)
                 continue
             data = np.asarray(data, np.float32)
@@ -136,21 +155,9 @@ class ShapeNet_Trainer(S3DIS_Trainer):
             data_feed[0::rep] = data
             if siamese:
                 data_feed[1::2] = partner
-            label_onehot_feed = np.repeat(Tool.OnehotEncode(label[:, 0], Loader.NUM_CATEGORIES), rep, axis=0)
-            seg_onehot_feed = Tool.OnehotEncode(np.repeat(seg, rep, axis=0), 50)
-            loss_mb, _, _, _, Z_prob_mb = self.train_batch(data_feed, label_onehot_feed, seg_onehot_feed,
-                                                           np.repeat(mask, rep, axis=0))
-            pred = np.stack([self._restrict_to_category(Z_prob_mb[rep * b_i],
-                                                        Loader.object2setofoid[Loader.objcats[label[b_i, 0]]])
-                             for b_i in range(mb_size)])
-            avg_loss = (avg_loss * data_cnt + loss_mb * mb_size) / (data_cnt + mb_size)
-            avg_acc = (avg_acc * data_cnt + float(np.mean(pred == seg)) * mb_size) / (data_cnt + mb_size)
-            data_cnt += mb_size
-            print('\rBatch {:d} TrainedSamp {:d}  Avg Loss {:.4f} Avg Acc {:.2f}%'.format(batch_cnt, data_cnt, avg_loss,
-                                                                                         100 * avg_acc), end='')
-            batch_cnt += 1
-        self.epoch += 1
-        return avg_loss, avg_acc
+            label_onehot_feed = np.repeat(Tool.OnehotEncode(label[:, 0], Loader.NUM_CATEGORIES, np.float32), rep, axis=0)
+            seg_onehot_feed = Tool.OnehotEncode(np.repeat(seg, rep, axis=0), 50, np.float32)
+            yield data_feed, label_onehot_feed, seg_onehot_feed, np.repeat(mask, rep, axis=0), label, seg, mb_size
 
     def EvalOneEpoch(self, Loader, Eval):
         """Plain-style validation (ShapeNet_DGCNN_trainer.py:343-413): no Siamese duplication."""
@@ -184,8 +191,8 @@ class ShapeNet_Trainer(S3DIS_Trainer):
                 data_f, seg_f, label_f = data, seg, label
             N = data_f.shape[1]
             loss_mb, Z_prob_mb = self.eval_batch(np.repeat(data_f, rep, axis=0),
-                                                 np.repeat(Tool.OnehotEncode(label_f[:, 0], Loader.NUM_CATEGORIES), rep, axis=0),
-                                                 Tool.OnehotEncode(np.repeat(seg_f, rep, axis=0), 50),
+                                                 np.repeat(Tool.OnehotEncode(label_f[:, 0], Loader.NUM_CATEGORIES, np.float32), rep, axis=0),
+                                                 Tool.OnehotEncode(np.repeat(seg_f, rep, axis=0), 50, np.float32),
                                                  np.ones((rep * data_f.shape[0], N), np.float32))
             Z_prob_mb = Z_prob_mb[0:rep * mb_size:rep]
             for b_i in range(mb_size):
@@ -226,8 +233,8 @@ class ShapeNet_Trainer(S3DIS_Trainer):
             idx = np.concatenate([np.arange(n0), np.random.choice(np.arange(n0), eng.N - n0, True)]).astype(np.int64)   # (:531-533)
             data_feed = np.repeat(data[:, idx, :], eng.B, axis=0)
             seg_feed = np.repeat(seg[:, idx], eng.B, axis=0)
-            label_feed = np.repeat(Tool.OnehotEncode(label[:, 0], Loader.NUM_CATEGORIES), eng.B, axis=0)
-            loss_mb, _ = self.eval_batch(data_feed, label_feed, Tool.OnehotEncode(seg_feed, 50),
+            label_feed = np.repeat(Tool.OnehotEncode(label[:, 0], Loader.NUM_CATEGORIES, np.float32), eng.B, axis=0)
+            loss_mb, _ = self.eval_batch(data_feed, label_feed, Tool.OnehotEncode(seg_feed, 50, np.float32),
                                          np.ones((eng.B, eng.N), np.float32))
             X0 = eng.X[0:1].contiguous()
             Lm = ops.laplacian_sym(X0, X0)                                       # (:551)
