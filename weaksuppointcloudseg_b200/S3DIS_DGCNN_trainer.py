@@ -52,25 +52,39 @@ def prefetched(gen, enabled=None):
     import threading
     q = queue.Queue(maxsize=1)
     end = object()
+    stop = threading.Event()
+
+    def hand_over(msg):
+        while not stop.is_set():              # a consumer that went away (exception, early break) releases the worker
+            try:
+                q.put(msg, timeout=0.1)
+                return True
+            except queue.Full:
+                pass
+        return False
 
     def work():
         try:
             for item in gen:
-                q.put((None, item))
-            q.put((None, end))
+                if not hand_over((None, item)):
+                    return
+            hand_over((None, end))
         except BaseException as exc:      # noqa: BLE001  (handed to the consumer)
-            q.put((exc, None))
+            hand_over((exc, None))
 
     worker = threading.Thread(target=work, name='wspc-prefetch', daemon=True)
     worker.start()
-    while True:
-        exc, item = q.get()
-        if exc is not None:
-            raise exc
-        if item is end:
-            break
-        yield item
-    worker.join()
+    try:
+        while True:
+            exc, item = q.get()
+            if exc is not None:
+                raise exc
+            if item is end:
+                break
+            yield item
+    finally:
+        stop.set()
+        worker.join(timeout=5)
 
 
 class S3DIS_Trainer():
@@ -341,18 +355,22 @@ class S3DIS_Trainer():
             Loader.ResetLoader_TrainSet()                # (:213, :343)
         self.epoch += 1
 
+    def _plain_batches(self, Loader, pts_idx_list):
+        while True:
+            SuccessFlag, data, seg, weak_seg_onehot, mb_size, data_idx = Loader.NextBatch_TrainSet_v1()
+            if not SuccessFlag or mb_size < self.engine.B:   # the short last batch is dropped (:167-168); static graph batch
+                return
+            data = np.asarray(data, np.float32)
+            seg = np.asarray(seg).astype(np.int64)
+            yield (data, Tool.OnehotEncode(seg, 13, np.float32), self._mask_from_idx(pts_idx_list, data_idx, mb_size, data.shape[1]),
+                   seg, mb_size)
+
     def TrainOneEpoch(self, Loader, pts_idx_list=None, batch_size=12):
         """Plain-style epoch (TrainOneEpoch, :146-219): `batch_size` clouds per step, segmentation loss on the labelled
         points only.  -> (avg_loss, avg_acc)."""
         batch_cnt, data_cnt, avg_loss, avg_acc = 1, 0, 0., 0.
-        while True:
-            SuccessFlag, data, seg, weak_seg_onehot, mb_size, data_idx = Loader.NextBatch_TrainSet_v1()
-            if not SuccessFlag or mb_size < self.engine.B:   # the short last batch is dropped (:167-168); static graph batch
-                break
-            data = np.asarray(data, np.float32)
-            seg = np.asarray(seg).astype(np.int64)
-            Mask_bin_feed = self._mask_from_idx(pts_idx_list, data_idx, mb_size, data.shape[1])
-            loss_mb, _, _, _, Z_prob_mb = self.train_batch(data, Tool.OnehotEncode(seg, 13, np.float32), Mask_bin_feed)
+        for data, seg_onehot_feed, Mask_bin_feed, seg, mb_size in prefetched(self._plain_batches(Loader, pts_idx_list)):
+            loss_mb, _, _, _, Z_prob_mb = self.train_batch(data, seg_onehot_feed, Mask_bin_feed)
             acc = float(np.mean(np.argmax(Z_prob_mb, axis=-1) == seg))
             avg_loss = (avg_loss * data_cnt + loss_mb * mb_size) / (data_cnt + mb_size)
             avg_acc = (avg_acc * data_cnt + acc * mb_size) / (data_cnt + mb_size)
