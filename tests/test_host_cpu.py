@@ -325,3 +325,45 @@ def test_shapenet_train_epoch_loop_feeds(tmp_path, monkeypatch):
             if siamese:
                 assert np.array_equal(y[0::2], y[1::2]) and np.array_equal(lab[0::2], lab[1::2])
                 assert np.abs(np.abs(d[1::2]) - np.abs(d[0::2])).max() < 0.05     # jitter (+ optional mirror of axis 2)
+
+
+def test_ctypes_signatures_match_the_header():
+    """ABI drift guard: every prototype of include/wspc.h has ctypes argtypes of the same arity and scalar kinds
+    (int / long long / float / double / size_t / uint64_t / pointer) in weaksuppointcloudseg_b200/_lib.py."""
+    import ctypes as C
+    from weaksuppointcloudseg_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    h = open(os.path.join(root, "include", "wspc.h")).read()
+    h = re.sub(r"/\*.*?\*/", "", h, flags=re.S)
+    h = re.sub(r"//[^\n]*", "", h)
+    protos = re.findall(r"\b(wspc_\w+)\s*\(([^;{]*?)\)\s*;", h)
+    assert len(protos) >= 40
+    lib = _lib.lib()
+
+    def kind_of_c(param):
+        p = " ".join(param.split())
+        if "*" in p or p.startswith("wspc_stream_t"):
+            return "ptr"
+        for key, kind in (("long long", "i64"), ("uint64_t", "u64"), ("size_t", "size"), ("double", "f64"), ("float", "f32"),
+                          ("int32_t", "i32"), ("int", "i32")):
+            if re.search(r"\b%s\b" % key, p):
+                return kind
+        raise AssertionError("unclassified parameter: " + p)
+
+    def kind_of_ctypes(t):
+        if t in (C.c_void_p, C.c_char_p) or hasattr(t, "contents") or (isinstance(t, type) and issubclass(t, C._Pointer)):
+            return "ptr"
+        return {C.c_int: "i32", C.c_longlong: "i64", C.c_uint64: "u64", C.c_size_t: "size", C.c_double: "f64",
+                C.c_float: "f32"}[t]
+
+    same_width = {frozenset(("u64", "size"))}                      # c_uint64 and c_size_t are one ctypes class on LP64
+    for name, params in protos:
+        fn = getattr(lib, name)
+        plist = [p for p in (q.strip() for q in params.split(",")) if p and p != "void"]
+        if fn.argtypes is None:
+            assert not plist, "%s takes %d parameters but has no argtypes" % (name, len(plist))
+            continue
+        assert len(fn.argtypes) == len(plist), (name, len(fn.argtypes), len(plist))
+        for i, (p, t) in enumerate(zip(plist, fn.argtypes)):
+            a, b = kind_of_c(p), kind_of_ctypes(t)
+            assert a == b or frozenset((a, b)) in same_width, (name, i, p, t)
