@@ -158,3 +158,39 @@ def test_h5_round_trip_property(tmp_path):
         assert np.array_equal(back['second_name'], a[:1])
 
     run()
+
+
+@pytest.mark.parametrize("stride,random_sample", [(1.0, False), (0.5, False), (1.0, True), (0.7, True)])
+def test_room2blocks_binning_equals_whole_room_masks(stride, random_sample):
+    """The binned block membership against the reference's formulation (a mask over every point of the room per block,
+    DataIO_S3DIS.py:398-404), for overlapping strides and randomly placed blocks (negative corners included)."""
+    rng = np.random.default_rng(12)
+    n = 6000
+    data = np.concatenate([rng.random((n, 3)) * np.array([3.3, 2.4, 3.0]), rng.random((n, 3))], 1)
+    data[:50, 0] = np.round(data[:50, 0])                          # points exactly on block borders (inclusive both sides)
+    label = rng.integers(0, 13, n).astype(np.uint8)
+    t = S3DIS_Test.__new__(S3DIS_Test)
+    np.random.seed(3)
+    got_d, got_l = t.room2blocks(data, label, 64, block_size=1.0, stride=stride, random_sample=random_sample, sample_num=None)
+
+    # the reference's formulation, restated: same corner lists, same random draws
+    np.random.seed(3)
+    limit = data.max(0)[0:3]
+    if not random_sample:
+        nx = int(np.ceil((limit[0] - 1.0) / stride)) + 1
+        ny = int(np.ceil((limit[1] - 1.0) / stride)) + 1
+        corners = [(i * stride, j * stride) for i in range(nx) for j in range(ny)]
+    else:
+        nb = int(np.ceil(limit[0])) * int(np.ceil(limit[1]))
+        corners = [(np.random.uniform(-1.0, limit[0]), np.random.uniform(-1.0, limit[1])) for _ in range(nb)]
+    want_d, want_l = [], []
+    for xb, yb in corners:
+        cond = (data[:, 0] <= xb + 1.0) & (data[:, 0] >= xb) & (data[:, 1] <= yb + 1.0) & (data[:, 1] >= yb)
+        if cond.sum() < 100:
+            continue
+        idx = np.flatnonzero(cond)
+        pick = idx[S3DIS_Test._sample_indices(idx.size, 64)]
+        want_d.append(data[pick])
+        want_l.append(label[pick])
+    assert len(want_d) > 3 and got_d.shape == (len(want_d), 64, 6)
+    assert np.array_equal(got_d, np.stack(want_d)) and np.array_equal(got_l, np.stack(want_l))

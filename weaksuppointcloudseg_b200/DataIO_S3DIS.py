@@ -206,8 +206,26 @@ class S3DIS_Test:
             ybeg = np.array([c[1] for c in corners])
         x, y = data[:, 0], data[:, 1]
         block_data, block_label = [], []
+        # Points are binned once on the stride grid; a block then tests only the bins it can touch instead of the whole
+        # room (the reference masks all points per block).  Same inclusive bounds, same ascending point order inside a block.
+        bx = np.floor(x / stride).astype(np.int64)
+        by = np.floor(y / stride).astype(np.int64)
+        ox, oy = int(bx.min()), int(by.min())
+        ny_bins = int(by.max()) - oy + 1
+        key = (bx - ox) * ny_bins + (by - oy)
+        order = np.argsort(key, kind='stable')
+        starts = np.searchsorted(key[order], np.arange((int(bx.max()) - ox + 1) * ny_bins + 1))
+        reach = int(np.ceil(block_size / stride))
         for xb, yb in zip(xbeg, ybeg):
-            inside = np.flatnonzero((x <= xb + block_size) & (x >= xb) & (y <= yb + block_size) & (y >= yb))
+            i0, j0 = int(np.floor(xb / stride)) - ox, int(np.floor(yb / stride)) - oy
+            cand = []
+            for i in range(max(i0 - 1, 0), min(i0 + reach + 1, int(bx.max()) - ox) + 1):   # one bin of slack for rounding
+                lo_j, hi_j = max(j0 - 1, 0), min(j0 + reach + 1, ny_bins - 1)
+                if lo_j <= hi_j:
+                    cand.append(order[starts[i * ny_bins + lo_j]:starts[i * ny_bins + hi_j + 1]])
+            cand = np.sort(np.concatenate(cand)) if cand else np.zeros(0, np.int64)
+            cx, cy = x[cand], y[cand]
+            inside = cand[(cx <= xb + block_size) & (cx >= xb) & (cy <= yb + block_size) & (cy >= yb)]
             if inside.size < 100:
                 continue
             pick = inside[self._sample_indices(inside.size, num_point)]
