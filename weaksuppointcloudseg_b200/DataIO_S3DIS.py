@@ -223,9 +223,9 @@ class S3DIS_Test:
                 lo_j, hi_j = max(j0 - 1, 0), min(j0 + reach + 1, ny_bins - 1)
                 if lo_j <= hi_j:
                     cand.append(order[starts[i * ny_bins + lo_j]:starts[i * ny_bins + hi_j + 1]])
-            cand = np.sort(np.concatenate(cand)) if cand else np.zeros(0, np.int64)
+            cand = np.concatenate(cand) if cand else np.zeros(0, np.int64)
             cx, cy = x[cand], y[cand]
-            inside = cand[(cx <= xb + block_size) & (cx >= xb) & (cy <= yb + block_size) & (cy >= yb)]
+            inside = np.sort(cand[(cx <= xb + block_size) & (cx >= xb) & (cy <= yb + block_size) & (cy >= yb)])
             if inside.size < 100:
                 continue
             pick = inside[self._sample_indices(inside.size, num_point)]
