@@ -273,6 +273,60 @@ int wspc_edge_combine_bwd_maxk(const float* y, const float* c1, const float* c2,
 int wspc_edge_merge_wgrad(const float* dWc, const float* dbc, int Cx, int Cout, float* dW, float* db,
                           wspc_stream_t stream);
 
+/* ----------------------------------------- fused EdgeConv blocks (no (B*N*k, C) tensor in HBM) --- */
+/* One EdgeConv block of the reference graphs is  get_edge_feature -> conv2d + BN + ReLU [-> conv2d + BN + ReLU] ->
+ * tf.reduce_max over k  (tf_util.py:674-706,115-173,502-535; DGCNN_S3DIS.py:32-46,48-62,64-78; DGCNN_ShapeNet.py:32-78).
+ * With the factored first layer (above) every edge row y1_ij = u_i + v_j + b1 is a function of two rows of the
+ * L2-resident UV (P, 128) = [u | v], so forward and backward recompute the edge tensors on chip instead of storing
+ * them.  All channel counts are 64.  P*k < 2^31, P % npts == 0.
+ *
+ *   wspc_edge_gather_stats      one gather sweep over the edges: stats (2,64) fp64 += (sum y1, sum y1^2)  [tf.nn.moments];
+ *                               MM (P,128) = [max_j y1 | min_j y1] (single-conv block: feeds wspc_maxk_from_extrema);
+ *                               SS (P,128) = [S_i = sum_j v_j | SU_p += u_i for every edge i->p] and deg (P) += 1 per
+ *                               incoming edge (caller zeroes SS[:,64:] and deg; needed by the backward pass only).
+ *                               Any of stats / MM / (SS, deg) may be NULL.
+ *   wspc_edgeconv2_fwd          two-conv block: a1 = relu(bn1(y1)) (sc1/sh1 from wspc_bn_finalize) -> y2 = a1 W2 + b2 on
+ *                               tcgen05 (bf16 hi/lo split, 3 passes, fp32 accumulate) -> MM (P,128) = [max_j y2 | min_j y2]
+ *                               and stats2 (2,64) fp64 += (sum y2, sum y2^2) (NULL at inference); 2 <= k <= 128.
+ *                               reduce_max(relu(bn2(y2))) = wspc_maxk_from_extrema(MM, sc2, sh2).
+ *   wspc_maxk_extrema_bwd_prep  MS (P,128) = [out > 0 ? out : -1 | out > 0 ? dout : 0] and the BN-2 backward sums
+ *                               stats (2,64) += (sum G, sum G*y2) of the max-over-k gradient G (it lives on the extremal rows).
+ *   wspc_edgeconv2_bwd          recomputes a1, y2 per tile (bit-identical to the forward), G = tie-split reduce_max gradient
+ *                               [TF _MinOrMaxGrad], dy2 = c1 G + c2 + c3 y2 (wspc_bn_bwd_coeffs of layer 2);
+ *                               dW2 (64,64) = a1^T dy2;  g1 = (dy2 W2^T) * [a1 > 0];
+ *                               TS (P,128): TS[i,0:64] = sum_j g1_ij,  TS[p,64:128] += g1_ij for every edge i->p
+ *                               (red.global.add, caller zeroes that half).
+ *   wspc_edge1_bwd              single-conv block: the same TS from (out, dout) of the max over k directly (k <= 64).
+ *   wspc_edge_bwd_stats         BN-1 backward sums from TS: bstats (2,64) fp64 += (sum g1, sum g1*y1).
+ *   wspc_edge_bwd_finalize      DUV (P,128) = [du | dv] of dy1 = c1 g1 + c2 + c3 y1 (closed form from TS, SS, deg, UV);
+ *                               the P-row GEMMs of the factored layer (wspc_conv1x1_wgrad / _rows) finish the block.
+ *   wspc_bn_bias_grad           db = c1 sum G + rows c2 + c3 sum y  (bias of a conv followed by BN; fstats = forward moments) */
+int wspc_edge_gather_stats(const float* UV, long long ldu, const int32_t* idx, const float* bias, long long P, int k,
+                           int npts, int Cout, double* stats, float* MM, float* SS, float* deg, wspc_stream_t stream);
+int wspc_edgeconv2_fwd(const float* UV, long long ldu, const int32_t* idx, const float* bias1, const float* sc1,
+                       const float* sh1, const float* W2, const float* bias2, long long P, int k, int npts, int C1, int C2,
+                       double* stats2, float* MM, wspc_stream_t stream);
+int wspc_maxk_extrema_bwd_prep(const float* MM, const float* sc, const float* out, long long ldo, const float* dout,
+                               long long lddo, long long P, int C, float* MS, double* stats, wspc_stream_t stream);
+size_t wspc_edgeconv2_bwd_workspace_bytes(void);
+int wspc_edgeconv2_bwd(const float* UV, long long ldu, const int32_t* idx, const float* bias1, const float* sc1,
+                       const float* sh1, const float* W2, const float* bias2, const float* sc2, const float* sh2,
+                       const float* c1, const float* c2, const float* c3, const float* MS, long long P, int k, int npts,
+                       int C1, int C2, float* TS, float* dW2, void* workspace, size_t workspace_bytes,
+                       wspc_stream_t stream);
+int wspc_edge1_bwd(const float* UV, long long ldu, const int32_t* idx, const float* bias, const float* sc, const float* sh,
+                   const float* out, long long ldo, const float* dout, long long lddo, long long P, int k, int npts,
+                   int Cout, float* TS, wspc_stream_t stream);
+int wspc_edge_bwd_stats(const float* TS, const float* UV, long long ldu, const float* bias, long long P, int Cout,
+                        double* bstats, wspc_stream_t stream);
+int wspc_edge_bwd_finalize(const float* TS, const float* SS, const float* deg, const float* UV, long long ldu,
+                           const float* bias, const float* c1, const float* c2, const float* c3, long long P, int k,
+                           int Cout, float* DUV, long long ldd, wspc_stream_t stream);
+/* p[r, col0:col0+ncols] = 0 for r < rows of a (rows, ld) fp32 matrix (the scatter halves of SS / TS above) */
+int wspc_zero_cols(float* p, long long ld, int col0, int ncols, long long rows, wspc_stream_t stream);
+int wspc_bn_bias_grad(const double* fstats, const double* bstats, const float* c1, const float* c2, const float* c3, int C,
+                      double rows, float* db, wspc_stream_t stream);
+
 /* ------------------- backward of conv2d 1x1 -> BN -> ReLU -> max over the points of a cloud --- */
 /* adj_conv7 + maxpool (DGCNN_S3DIS.py:80-85, DGCNN_ShapeNet.py:80-85) and tconv3 + tmaxpool (transform_nets.py:29-34).
  * max_pool2d's gradient is sparse (one point per cloud and channel), the BN backward is affine (dy = c1*G + c2 + c3*y)

@@ -173,6 +173,18 @@ _EXTRA_DECLS.update({
     "wspc_poolconv_coeffs": (c_int, [_P, _P, _P, _P, c_int, c_int, _P, _P, _P]),
     "wspc_poolconv_sparse": (c_int, [_P, _P, _P, _P, _P, c_longlong, c_int, c_int, c_int, c_int, _P, c_longlong, _P, _P, _P]),
     "wspc_poolconv_finalize": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_double, _P, _P, _P]),
+    "wspc_edge_gather_stats": (c_int, [_P, c_longlong, _P, _P, c_longlong, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
+    "wspc_edgeconv2_fwd": (c_int, [_P, c_longlong, _P, _P, _P, _P, _P, _P, c_longlong, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "wspc_maxk_extrema_bwd_prep": (c_int, [_P, _P, _P, c_longlong, _P, c_longlong, c_longlong, c_int, _P, _P, _P]),
+    "wspc_edgeconv2_bwd_workspace_bytes": (c_size_t, []),
+    "wspc_edgeconv2_bwd": (c_int, [_P, c_longlong, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_longlong, c_int, c_int,
+                                   c_int, c_int, _P, _P, _P, c_size_t, _P]),
+    "wspc_edge1_bwd": (c_int, [_P, c_longlong, _P, _P, _P, _P, _P, c_longlong, _P, c_longlong, c_longlong, c_int, c_int, c_int,
+                               _P, _P]),
+    "wspc_edge_bwd_stats": (c_int, [_P, _P, c_longlong, _P, c_longlong, c_int, _P, _P]),
+    "wspc_edge_bwd_finalize": (c_int, [_P, _P, _P, _P, c_longlong, _P, _P, _P, _P, c_longlong, c_int, c_int, _P, c_longlong, _P]),
+    "wspc_zero_cols": (c_int, [_P, c_longlong, c_int, c_int, c_longlong, _P]),
+    "wspc_bn_bias_grad": (c_int, [_P, _P, _P, _P, _P, c_int, c_double, _P, _P]),
 })
 
 

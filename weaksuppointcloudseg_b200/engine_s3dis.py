@@ -47,8 +47,16 @@ class S3DISEngine:
         self.idx = [torch.empty((B, N, k), **i32) for _ in range(3)]
         self.idxS = torch.empty((B, N, SMOOTH_KNN), **i32)
         self.dS = torch.empty((B, N, SMOOTH_KNN), **f32)
-        self.y = [torch.empty((R, 64), **f32) for _ in range(5)]
-        self.Ga, self.Gb = torch.empty((R, 64), **f32), torch.empty((R, 64), **f32)
+        # fused EdgeConv blocks (csrc/edgeconv.cu) keep per-point state only; WSPC_EDGECONV=unfused materialises the
+        # pre-BN outputs y1..y5 and the max-over-k gradient (round-1 formulation, kept as a second device path)
+        self.fused = rt.EDGE_FUSED
+        if self.fused:
+            self.ef = rt.EdgeFused(P, self.dev)
+            self.eb = [rt.EdgeBlockState(P, self.dev) for _ in range(3)]
+            self.y, self.Ga, self.Gb = None, None, None
+        else:
+            self.y = [torch.empty((R, 64), **f32) for _ in range(5)]
+            self.Ga, self.Gb = torch.empty((R, 64), **f32), torch.empty((R, 64), **f32)
         self.cat, self.dcat = torch.empty((P, 192), **f32), torch.empty((P, 192), **f32)
         self.y7 = torch.empty((P, 1024), **f32)
         self.g, self.dg_in, self.dg = (torch.empty((B, 1024), **f32) for _ in range(3))
@@ -62,8 +70,8 @@ class S3DISEngine:
         self.zero_bias = torch.zeros(512, **f32)
         self.seed = 1234
         # first conv2d of each EdgeConv block: factored (csrc/edge.cu) unless WSPC_EDGE=gemm asks for the gathered GEMM
-        self.es = rt.EdgeSplit(P, self.dev) if rt.EDGE_FACTORED else None
-        self.MS = torch.empty((P, 128), **f32) if rt.MAXK_SYNTH else None     # [pooled max | dout / #ties] per point
+        self.es = rt.EdgeSplit(P, self.dev) if (rt.EDGE_FACTORED and not self.fused) else None
+        self.MS = torch.empty((P, 128), **f32) if (rt.MAXK_SYNTH and not self.fused) else None   # [pooled max | dout / #ties]
         self.pc7 = rt.PoolConv(self.layers["adj_conv7"], self.dev) if rt.POOLCONV_GRAM else None
         self.prof = None   # optional list of (tag, start_event, end_event) filled around the kNN launches
 
@@ -100,6 +108,18 @@ class S3DISEngine:
                                            L.ptr(self.idx[i]), None, L.ptr(ws), ws.numel(), L.stream()))
             self._tock(f"knn_D{D}_k{k}", t0)
 
+        if self.fused:
+            c = [Ly[f"adj_conv{i}"] for i in (1, 2, 3, 4, 5)]
+            knn_into(0, X.data_ptr(), 9, self.knn_coff, 3)                                    # block 1 (:32-46)
+            rt.edgeblock_forward(self.ef, self.eb[0], c[0], c[1], X, 9, 9, self.idx[0], k, N, P, is_training, bn_decay,
+                                 cat_a, 192)
+            knn_into(1, cat_a, 192, 0, 64)                                                    # block 2 (:48-62)
+            rt.edgeblock_forward(self.ef, self.eb[1], c[2], c[3], cat_a, 192, 64, self.idx[1], k, N, P, is_training, bn_decay,
+                                 cat_a + 4 * 64, 192)
+            knn_into(2, cat_a, 192, 64, 64)                                                   # block 3 (:64-78)
+            rt.edgeblock_forward(self.ef, self.eb[2], c[4], None, cat_a + 4 * 64, 192, 64, self.idx[2], k, N, P, is_training,
+                                 bn_decay, cat_a + 4 * 128, 192)
+            return self._forward_head(X, is_training, bn_decay, dropout_mask)
         # block 1: kNN on normalised xyz (ch 6:9), edge feature of all 9 channels      (:32-46)
         knn_into(0, X.data_ptr(), 9, self.knn_coff, 3)
         if self.es is not None:
@@ -127,6 +147,11 @@ class S3DISEngine:
             e3 = L.Operand(p=cat_a + 4 * 64, ld=192, C=128, idx=L.dptr(self.idx[2]), k=k, npts=N), L.OP_EDGE
             rt.conv_forward(Ly["adj_conv5"], e3, R, self.y[4], 64, is_training, bn_decay)
             rt.maxk_fwd(Ly["adj_conv5"], self.y[4], P, k, cat_a + 4 * 128, 192)
+        return self._forward_head(X, is_training, bn_decay, dropout_mask)
+
+    def _forward_head(self, X, is_training, bn_decay, dropout_mask):
+        B, N, P = self.B, self.N, self.P
+        Ly = self.layers
         # adj_conv7 + max over points                                                   (:80-85)
         l7 = Ly["adj_conv7"]
         rt.conv_forward(l7, rt.op_plain(self.cat, 192, 192), P, self.y7, 1024, is_training, bn_decay)
@@ -217,6 +242,14 @@ class S3DISEngine:
             G7 = rt.op_dy_sparse(self.y7, c7, self.dg, self.amax, N)
             rt.wgrad(rt.op_plain(self.cat, 192, 192), G7, P, c7.dW, c7.db, dev)
             rt.rows_gemm(G7, c7.W, 1024, 1, P, 192, 1024, L.Epilogue(out=dcat_a, ldo=192), L.EPI_ACCUM)
+        if self.fused:
+            ef, eb = self.ef, self.eb
+            rt.edgeblock_backward(ef, eb[2], c5, None, cat_a + 4 * 64, 192, 64, self.idx[2], k, N, P, cat_a + 4 * 128, 192,
+                                  dcat_a + 4 * 128, 192, dcat_a + 4 * 64, 192)
+            rt.edgeblock_backward(ef, eb[1], c3, c4, cat_a, 192, 64, self.idx[1], k, N, P, cat_a + 4 * 64, 192,
+                                  dcat_a + 4 * 64, 192, dcat_a, 192)
+            rt.edgeblock_backward(ef, eb[0], c1, c2, self.X, 9, 9, self.idx[0], k, N, P, cat_a, 192, dcat_a, 192)
+            return
         # block 3
         synth = self.MS is not None
         if synth and self.es is not None:

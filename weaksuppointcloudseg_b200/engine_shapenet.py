@@ -64,8 +64,17 @@ class ShapeNetEngine:
         self.yf2, self.Gf2 = torch.empty((B, 256), **f32), torch.empty((B, 256), **f32)
         self.Tm, self.dTm = torch.empty((B, 9), **f32), torch.empty((B, 9), **f32)
         self.Xt, self.dXt = torch.empty((B, N, 3), **f32), torch.empty((B, N, 3), **f32)
-        self.y = [torch.empty((R, 64), **f32) for _ in range(5)]
-        self.Ga, self.Gb = torch.empty((R, 64), **f32), torch.empty((R, 64), **f32)
+        # the three EdgeConv blocks of the segmentation trunk run fused (csrc/edgeconv.cu, per-point state only); the T-net's
+        # 64 -> 128 block keeps the materialised formulation (its second layer is 128 wide)
+        self.fused = rt.EDGE_FUSED
+        if self.fused:
+            self.ef = rt.EdgeFused(P, self.dev)
+            self.eb = [rt.EdgeBlockState(P, self.dev) for _ in range(3)]
+            self.y, self.Gb = None, None
+        else:
+            self.y = [torch.empty((R, 64), **f32) for _ in range(5)]
+            self.Gb = torch.empty((R, 64), **f32)
+        self.Ga = torch.empty((R, 64), **f32)
         self.cat, self.dcat = torch.empty((P, 192), **f32), torch.empty((P, 192), **f32)
         self.y7 = torch.empty((P, 1024), **f32)
         self.g, self.dg_in, self.dg = (torch.empty((B, 1024), **f32) for _ in range(3))
@@ -122,6 +131,16 @@ class ShapeNetEngine:
         rt.conv_forward(self.tx, rt.op_bnrelu(self.yf2, f2), B, self.Tm, 9, tr, None)
         L.check(L.lib().wspc_transform_points_fwd(L.ptr(X), L.ptr(self.Tm), B, N, 1, L.ptr(self.Xt), L.stream()))  # :29
         # ---- EdgeConv blocks on the transformed cloud                        (:31-78)
+        if self.fused:
+            c = [Ly[f"adj_conv{i}"] for i in (1, 2, 3, 4, 5)]
+            self._knn(1, self.Xt.data_ptr(), 3, 0, 3, ov, "knn1")
+            rt.edgeblock_forward(self.ef, self.eb[0], c[0], c[1], self.Xt, 3, 3, self.idx[1], k, N, P, tr, d, cat_a, 192)
+            self._knn(2, cat_a, 192, 0, 64, ov, "knn2")
+            rt.edgeblock_forward(self.ef, self.eb[1], c[2], c[3], cat_a, 192, 64, self.idx[2], k, N, P, tr, d, cat_a + 4 * 64, 192)
+            self._knn(3, cat_a, 192, 64, 64, ov, "knn3")
+            rt.edgeblock_forward(self.ef, self.eb[2], c[4], None, cat_a + 4 * 64, 192, 64, self.idx[3], k, N, P, tr, d,
+                                 cat_a + 4 * 128, 192)
+            return self._forward_head(tr, d, dropout_masks)
         self._knn(1, self.Xt.data_ptr(), 3, 0, 3, ov, "knn1")
         if self.es is not None:
             rt.edge_first_forward(self.es, Ly["adj_conv1"], self.Xt, 3, 3, self.idx[1], k, N, P, self.y[0], tr, d)
@@ -144,6 +163,11 @@ class ShapeNetEngine:
             e3 = L.Operand(p=cat_a + 4 * 64, ld=192, C=128, idx=L.dptr(self.idx[3]), k=k, npts=N), L.OP_EDGE
             rt.conv_forward(Ly["adj_conv5"], e3, R, self.y[4], 64, tr, d)
             rt.maxk_fwd(Ly["adj_conv5"], self.y[4], P, k, cat_a + 4 * 128, 192)
+        return self._forward_head(tr, d, dropout_masks)
+
+    def _forward_head(self, tr, d, dropout_masks):
+        B, N, P = self.B, self.N, self.P
+        Ly = self.layers
         l7 = Ly["adj_conv7"]
         rt.conv_forward(l7, rt.op_plain(self.cat, 192, 192), P, self.y7, 1024, tr, d)                     # :80-83
         L.check(L.lib().wspc_maxn_bnrelu_fwd(L.ptr(self.y7), L.ptr(l7.sc), L.ptr(l7.sh), B, N, 1024, L.ptr(self.g),
@@ -249,6 +273,16 @@ class ShapeNetEngine:
             G7 = rt.op_dy_sparse(self.y7, c7, self.dg, self.amax, N)
             rt.wgrad(rt.op_plain(self.cat, 192, 192), G7, P, c7.dW, c7.db, dev)
             rt.rows_gemm(G7, c7.W, 1024, 1, P, 192, 1024, L.Epilogue(out=dcat_a, ldo=192), L.EPI_ACCUM)
+        if self.fused:
+            ef, eb = self.ef, self.eb
+            rt.edgeblock_backward(ef, eb[2], c5, None, cat_a + 4 * 64, 192, 64, self.idx[3], k, N, P, cat_a + 4 * 128, 192,
+                                  dcat_a + 4 * 128, 192, dcat_a + 4 * 64, 192)
+            rt.edgeblock_backward(ef, eb[1], c3, c4, cat_a, 192, 64, self.idx[2], k, N, P, cat_a + 4 * 64, 192,
+                                  dcat_a + 4 * 64, 192, dcat_a, 192)
+            rt.zero_(self.dXt)
+            rt.edgeblock_backward(ef, eb[0], c1, c2, self.Xt, 3, 3, self.idx[1], k, N, P, cat_a, 192, dcat_a, 192,
+                                  self.dXt.data_ptr(), 3)
+            return self._backward_tnet()
         # block 3
         rt.maxk_bwd(c5, self.y[4], P, k, cat_a + 4 * 128, 192, dcat_a + 4 * 128, 192, self.Ga)
         rt.bn_bwd_coeffs(c5, R)
@@ -288,6 +322,12 @@ class ShapeNetEngine:
             rt.wgrad(rt.op_edge(self.Xt, 3, 3, self.idx[1], k, N), G1e, R, c1.dW, c1.db, dev)
             e, m = rt.epi_scatter(self.dXt.data_ptr(), 3, self.idx[1], k, N)
             rt.rows_gemm(G1e, c1.W, 64, 1, R, 6, 64, e, m)
+        return self._backward_tnet()
+
+    def _backward_tnet(self):
+        B, N, k, P, R = self.B, self.N, self.k, self.P, self.R
+        Ly, dev = self.layers, self.dev
+        T = "transform_net1/"
         # ---- T-net                                                          (DGCNN_ShapeNet.py:29 backward)
         L.check(L.lib().wspc_transform_points_bwd(L.ptr(self.X), L.ptr(self.dXt), B, N, L.ptr(self.dTm), L.stream()))
         t1, t2, t3, f1, f2 = [Ly[T + n] for n in ("tconv1", "tconv2", "tconv3", "tfc1", "tfc2")]

@@ -383,3 +383,119 @@ class PoolConv:
                   L.EPI_STORE)
         L.check(L.lib().wspc_poolconv_finalize(L.ptr(self.T), L.ptr(self.colsum), L.ptr(self.t), L.ptr(self.sW), L.ptr(self.sdb),
                                                L.ptr(self.Wsc), cin, cout, float(P), L.ptr(ly.dW), L.ptr(ly.db), L.stream()))
+
+
+# ---- fused EdgeConv blocks (csrc/edgeconv.cu): no (P*k, C) tensor in HBM ------------------------------------
+# WSPC_EDGECONV=unfused keeps the round-1 formulation (pre-BN outputs y1..y5 and the max-over-k gradient materialised)
+# as a second device path for A/B tests; both need the factored first layer.
+EDGE_FUSED = EDGE_FACTORED and os.environ.get("WSPC_EDGECONV", "fused") != "unfused"
+
+
+class EdgeBlockState:
+    """What one EdgeConv block keeps between its forward and its backward pass (all per point, never per edge)."""
+
+    def __init__(self, P, device):
+        f32 = dict(dtype=torch.float32, device=device)
+        self.UV = torch.empty((P, 128), **f32)      # [u | v] = X [W1 - W2 | W2]
+        self.SS = torch.empty((P, 128), **f32)      # [S_i = sum_j v_j | SU_p = sum_{i->p} u_i]
+        self.MM = torch.empty((P, 128), **f32)      # [max_j y | min_j y] of the block's last pre-BN output
+        self.deg = torch.empty((P,), **f32)         # in-degree of every point in the kNN graph
+
+
+class EdgeFused:
+    """Scratch shared by the EdgeConv blocks of one engine."""
+
+    def __init__(self, P, device, max_cx=64):
+        f32 = dict(dtype=torch.float32, device=device)
+        self.P, self.device = P, device
+        self.TS = torch.empty((P, 128), **f32)      # [SG_i = sum_j g_ij | TG_p = sum_{i->p} g_ij]
+        self.MS = torch.empty((P, 128), **f32)      # [out > 0 ? out : -1 | gated dout] of the max over k
+        self.DUV = torch.empty((P, 128), **f32)     # [du | dv]
+        self.dWc = torch.empty((max_cx, 128), **f32)
+        self.dbc = torch.empty(128, **f32)
+        self.Wc = {}
+
+    def weights(self, layer: Layer, cx):
+        w = self.Wc.get(layer.scope)
+        if w is None:
+            w = self.Wc[layer.scope] = torch.empty((cx, 128), dtype=torch.float32, device=self.device)
+        L.check(L.lib().wspc_edge_split_weights(L.ptr(layer.W), cx, layer.cout, L.ptr(w), L.stream()))
+        return w
+
+
+def _zero_cols(t, col0, ncols):
+    L.check(L.lib().wspc_zero_cols(L.ptr(t), t.shape[1], col0, ncols, t.shape[0], L.stream()))
+
+
+def edgeblock_forward(ef: EdgeFused, st: EdgeBlockState, l1: Layer, l2, x, ld, cx, idx, k, npts, P, training, decay,
+                      out_addr, out_ld):
+    """get_edge_feature -> conv2d(l1) [-> conv2d(l2)] -> reduce_max over k, written to (P, out_ld) at out_addr.
+    x: tensor or raw address of the (P, ld) point features (cx channels used); l2 = None for a single-conv block."""
+    assert l1.cout == 64 and l1.cin == 2 * cx and l1.has_bn and (l2 is None or (l2.cin == 64 and l2.cout == 64 and l2.has_bn))
+    lib = L.lib()
+    Wc = ef.weights(l1, cx)
+    xa = x if isinstance(x, int) else x.data_ptr()
+    rows_gemm((L.Operand(p=xa, ld=ld, C=cx), L.OP_PLAIN), Wc, 128, 0, P, 128, cx, L.Epilogue(out=L.dptr(st.UV), ldo=128),
+              L.EPI_STORE)
+    R = P * k
+    single = l2 is None
+    if training:
+        zero_(l1.stats)
+        _zero_cols(st.SS, 64, 64)
+        zero_(st.deg)
+        L.check(lib.wspc_edge_gather_stats(L.ptr(st.UV), 128, L.ptr(idx), L.ptr(l1.b), P, k, npts, 64, L.ptr(l1.stats),
+                                           L.ptr(st.MM) if single else None, L.ptr(st.SS), L.ptr(st.deg), L.stream()))
+    elif single:
+        L.check(lib.wspc_edge_gather_stats(L.ptr(st.UV), 128, L.ptr(idx), L.ptr(l1.b), P, k, npts, 64, None, L.ptr(st.MM), None,
+                                           None, L.stream()))
+    bn_finalize(l1, R, training, decay)
+    last = l1
+    if not single:
+        if training:
+            zero_(l2.stats)
+        L.check(lib.wspc_edgeconv2_fwd(L.ptr(st.UV), 128, L.ptr(idx), L.ptr(l1.b), L.ptr(l1.sc), L.ptr(l1.sh), L.ptr(l2.W),
+                                       L.ptr(l2.b), P, k, npts, 64, 64, L.ptr(l2.stats) if training else None, L.ptr(st.MM),
+                                       L.stream()))
+        bn_finalize(l2, R, training, decay)
+        last = l2
+    L.check(lib.wspc_maxk_from_extrema(L.ptr(st.MM), L.ptr(last.sc), L.ptr(last.sh), P, 64, ctypes.c_void_p(out_addr), out_ld,
+                                       L.stream()))
+
+
+def edgeblock_backward(ef: EdgeFused, st: EdgeBlockState, l1: Layer, l2, x, ld, cx, idx, k, npts, P, out_addr, out_ld,
+                       dout_addr, dout_ld, dx_addr=None, lddx=0):
+    """Gradients of every variable of the block (l1, l2: dW, db, dgamma, dbeta) and, if dx_addr, dX accumulated into
+    (P, lddx) at dx_addr.  (out, dout): the block's pooled output and the gradient w.r.t. it."""
+    lib = L.lib()
+    R = P * k
+    xa = x if isinstance(x, int) else x.data_ptr()
+    out_p, dout_p = ctypes.c_void_p(out_addr), ctypes.c_void_p(dout_addr)
+    _zero_cols(ef.TS, 64, 64)
+    if l2 is None:
+        L.check(lib.wspc_edge1_bwd(L.ptr(st.UV), 128, L.ptr(idx), L.ptr(l1.b), L.ptr(l1.sc), L.ptr(l1.sh), out_p, out_ld, dout_p,
+                                   dout_ld, P, k, npts, 64, L.ptr(ef.TS), L.stream()))
+    else:
+        zero_(l2.bstats)
+        L.check(lib.wspc_maxk_extrema_bwd_prep(L.ptr(st.MM), L.ptr(l2.sc), out_p, out_ld, dout_p, dout_ld, P, 64, L.ptr(ef.MS),
+                                               L.ptr(l2.bstats), L.stream()))
+        bn_bwd_coeffs(l2, R)
+        L.check(lib.wspc_bn_bias_grad(L.ptr(l2.stats), L.ptr(l2.bstats), L.ptr(l2.c1), L.ptr(l2.c2), L.ptr(l2.c3), 64, float(R),
+                                      L.ptr(l2.db), L.stream()))
+        nbytes = lib.wspc_edgeconv2_bwd_workspace_bytes()
+        ws = L.workspace(nbytes, ef.device, "edgeconv_bwd")
+        L.check(lib.wspc_edgeconv2_bwd(L.ptr(st.UV), 128, L.ptr(idx), L.ptr(l1.b), L.ptr(l1.sc), L.ptr(l1.sh), L.ptr(l2.W),
+                                       L.ptr(l2.b), L.ptr(l2.sc), L.ptr(l2.sh), L.ptr(l2.c1), L.ptr(l2.c2), L.ptr(l2.c3),
+                                       L.ptr(ef.MS), P, k, npts, 64, 64, L.ptr(ef.TS), L.ptr(l2.dW), L.ptr(ws), ws.numel(),
+                                       L.stream()))
+    zero_(l1.bstats)
+    L.check(lib.wspc_edge_bwd_stats(L.ptr(ef.TS), L.ptr(st.UV), 128, L.ptr(l1.b), P, 64, L.ptr(l1.bstats), L.stream()))
+    bn_bwd_coeffs(l1, R)
+    L.check(lib.wspc_edge_bwd_finalize(L.ptr(ef.TS), L.ptr(st.SS), L.ptr(st.deg), L.ptr(st.UV), 128, L.ptr(l1.b), L.ptr(l1.c1),
+                                       L.ptr(l1.c2), L.ptr(l1.c3), P, k, 64, L.ptr(ef.DUV), 128, L.stream()))
+    Wc = ef.Wc[l1.scope]
+    D = (L.Operand(p=L.dptr(ef.DUV), ld=128, C=128), L.OP_DY)
+    A = (L.Operand(p=xa, ld=ld, C=cx), L.OP_PLAIN)
+    wgrad(A, D, P, ef.dWc, ef.dbc, ef.device)
+    L.check(lib.wspc_edge_merge_wgrad(L.ptr(ef.dWc), L.ptr(ef.dbc), cx, 64, L.ptr(l1.dW), L.ptr(l1.db), L.stream()))
+    if dx_addr is not None:
+        rows_gemm(D, Wc, 128, 1, P, cx, 128, L.Epilogue(out=dx_addr, ldo=lddx), L.EPI_ACCUM)
