@@ -368,6 +368,18 @@ int wspc_transform_points_bwd(const float* X, const float* dXt, int B, int N, fl
  * loss = mean_{b,n,r} exp(-dist/gamma) * mean_c (Z[b,n,c] - Z[b,idx[b,n,r],c])^2 ; dZ (zeroed by caller) or NULL. */
 int wspc_smooth_loss(const float* Z, const int32_t* idx, const float* dist, int B, int N, int C, int knn, float gamma,
                      float* dZ, float* loss, void* workspace, size_t workspace_bytes, wspc_stream_t stream);
+/* The sibling variants of Util/SmoothConstraint.py on the same kernel.  flags:
+ *   WSPC_SMOOTH_SUM_C      sum_c instead of mean_c of the squared differences (:31, :118-122, :215)
+ *   WSPC_SMOOTH_WEIGHTS    `dist` already holds the edge weights W (Loss_SpatialSmooth, :9-33); gamma is ignored
+ *   WSPC_SMOOTH_GLOBAL_SS  Loss_SpatialSmooth_SelfContain (:64-65): every weight multiplies the sum of squared differences over
+ *                          ALL edges and channels: loss = (sum W)(sum ss) / (B N knn); forward only (dZ must be NULL)
+ * idx_match (B,N,knn) or NULL: an edge slot counts only where idx_match == idx (knn_mask = equal(Ind_xyz, Ind_rgb), :113). */
+#define WSPC_SMOOTH_SUM_C 1
+#define WSPC_SMOOTH_WEIGHTS 2
+#define WSPC_SMOOTH_GLOBAL_SS 4
+int wspc_smooth_loss_ex(const float* Z, const int32_t* idx, const float* dist, const int32_t* idx_match, int B, int N, int C,
+                        int knn, float gamma, int flags, float* dZ, float* loss, void* workspace, size_t workspace_bytes,
+                        wspc_stream_t stream);
 
 /* ------------------------------------------------- test-time label propagation --- */
 /* Lsym = D^-1/2 (diag(d + 1e-8) - W) D^-1/2, W = exp(-scale_xyz d_xyz) * exp(-scale_rgb d_rgb)

@@ -315,6 +315,7 @@ def unstack(x, num=None, axis=0, name=None):
 
 def gather(params, indices, axis=0, name=None):
     idx = _t(indices).long()
+    axis = axis % params.dim()          # tf.gather accepts negative axes (Util/Loss.py:143)
     return _torch.index_select(_t(params), axis, idx.reshape(-1)).reshape(
         tuple(params.shape[:axis]) + tuple(idx.shape) + tuple(params.shape[axis + 1:])).as_subclass(Tensor)
 

@@ -289,9 +289,15 @@ def test_engine_fused_matches_unfused(cuda, monkeypatch):
     assert rel(a["Z"], b["Z"]) <= 5e-4
     assert rel(a["losses"], b["losses"]) <= 2e-4
     bad = []
+    gmax = max(float(np.abs(g).max()) for g in b["grads"].values())
     for name, gb in b["grads"].items():
         if name.endswith("biases") and not name.startswith("seg/conv3"):
             continue   # bias of a BN'd conv: analytically zero, rounding noise in both paths
+        if np.abs(gb).max() < 1e-6 * gmax:
+            # analytically zero as well: adj_conv7's beta shifts the tiled global feature by the same amount in every cloud and
+            # seg/conv1's batch norm removes that shift again -- both paths hold rounding noise
+            assert np.abs(a["grads"][name]).max() < 1e-5 * gmax, name
+            continue
         ga = a["grads"][name]
         l2 = np.linalg.norm(ga - gb) / max(np.linalg.norm(gb), 1e-30)
         if l2 > 2e-2:     # (routing through ReLU / max differs on a few last-bit cases at this tiny size)

@@ -156,6 +156,7 @@ _EXTRA_DECLS.update({
     "wspc_set_knn_path": (c_int, [c_int]),
     "wspc_knn_fallback_rows": (c_int, [_P, c_int, c_int, c_int, ctypes.POINTER(c_int)]),
     "wspc_smooth_loss": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, c_size_t, _P]),
+    "wspc_smooth_loss_ex": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_int, _P, _P, _P, c_size_t, _P]),
     "wspc_laplacian_sym": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_float, c_float, _P, _P, _P]),
     "wspc_lp_solve_workspace_bytes": (c_size_t, [c_int, c_int]),
     "wspc_lp_solve": (c_int, [_P, _P, c_int, c_int, c_float, c_float, c_int, c_float, _P, _P, _P, ctypes.POINTER(c_int), _P, c_size_t, _P]),

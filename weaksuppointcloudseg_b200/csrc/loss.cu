@@ -107,12 +107,15 @@ __global__ void head_tiecount_kernel(const float* __restrict__ Z, int B, int N, 
 // dP_i += g, dP_j -= g with g = 2 W (P_i - P_j) / (C * B*N*knn)   (App. E)
 __global__ void __launch_bounds__(256)
 smooth_kernel(const float* __restrict__ P, const int32_t* __restrict__ idx, const float* __restrict__ dist, int B, int N,
-              int C, int knn, float gamma, float gscale, float* __restrict__ dP, double* __restrict__ acc) {
-  __shared__ float sred[8];
+              int C, int knn, float gamma, float gscale, float* __restrict__ dP, double* __restrict__ acc,
+              float cinv /* 1/C (mean over channels) or 1 (sum) */ = -1.f, const int32_t* __restrict__ idx_match = nullptr,
+              int weights_direct = 0, int want_global = 0) {
+  __shared__ float sred[8], sred_w[8], sred_s[8];
+  if (cinv < 0.f) cinv = 1.f / (float)C;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long pt = (long long)blockIdx.x * 8 + warp;
   const long long total = (long long)B * N;
-  float lsum = 0.f;
+  float lsum = 0.f, wsum = 0.f, sssum = 0.f;
   if (pt < total) {
     const long long base = (pt / N) * N;
     const float* pi = P + pt * C;
@@ -121,12 +124,16 @@ smooth_kernel(const float* __restrict__ P, const int32_t* __restrict__ idx, cons
     float gi0 = 0.f, gi1 = 0.f;
     for (int r = 0; r < knn; ++r) {
       const long long j = base + idx[pt * knn + r];
-      const float w = expf((-dist[pt * knn + r]) / gamma);
+      float w = weights_direct ? dist[pt * knn + r] : expf((-dist[pt * knn + r]) / gamma);
+      // knn_mask of SmoothConstraint.py:113: the slot counts only where a second graph holds the same neighbour
+      if (idx_match && idx_match[pt * knn + r] != idx[pt * knn + r]) w = 0.f;
       const float* pj = P + j * C;
       const float d0 = (lane < C) ? zi0 - pj[lane] : 0.f;
       const float d1 = (lane + 32 < C) ? zi1 - pj[lane + 32] : 0.f;
       const float ss = warp_sum(d0 * d0 + d1 * d1);
-      lsum += w * (ss / (float)C);
+      lsum += w * (ss * cinv);
+      wsum += w;
+      sssum += ss;
       if (dP) {
         const float g0 = 2.f * w * d0 * gscale, g1 = 2.f * w * d1 * gscale;
         gi0 += g0;
@@ -142,12 +149,16 @@ smooth_kernel(const float* __restrict__ P, const int32_t* __restrict__ idx, cons
       if (lane + 32 < C) atomicAdd(dP + pt * C + lane + 32, gi1);
     }
   }
-  if (lane == 0) sred[warp] = lsum;
+  if (lane == 0) { sred[warp] = lsum; sred_w[warp] = wsum; sred_s[warp] = sssum; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    float a = 0.f;
-    for (int w = 0; w < 8; ++w) a += sred[w];
+    float a = 0.f, aw = 0.f, as = 0.f;
+    for (int w = 0; w < 8; ++w) { a += sred[w]; aw += sred_w[w]; as += sred_s[w]; }
     atomicAdd(&acc[4], (double)a);
+    if (want_global) {   // SmoothConstraint.py:64-65 multiplies every weight by the sum over ALL edges and channels
+      atomicAdd(&acc[5], (double)aw);
+      atomicAdd(&acc[6], (double)as);
+    }
   }
 }
 
@@ -331,29 +342,40 @@ extern "C" int wspc_head_losses(const float* Z, const float* Y, const float* Mas
 
 namespace wspc {
 namespace {
-__global__ void smooth_finish_kernel(const double* __restrict__ acc, double denom, float* __restrict__ loss) {
-  loss[0] = (float)(acc[4] / denom);
+__global__ void smooth_finish_kernel(const double* __restrict__ acc, double denom, int global_form, float* __restrict__ loss) {
+  loss[0] = (float)((global_form ? acc[5] * acc[6] : acc[4]) / denom);
 }
 }  // namespace
 }  // namespace wspc
 
-// Stand-alone manifold smoothness term (Util/SmoothConstraint.py:155-165) on a given kNN graph.
-// dP (B,N,C) may be NULL; if given it must be zeroed by the caller and receives d loss / d Z.
-extern "C" int wspc_smooth_loss(const float* Z, const int32_t* idx, const float* dist, int B, int N, int C, int knn,
-                                float gamma, float* dZ, float* loss, void* workspace, size_t workspace_bytes,
-                                wspc_stream_t stream) {
+// Stand-alone manifold smoothness terms of Util/SmoothConstraint.py on a given kNN graph (see include/wspc.h).
+// dZ (B,N,C) may be NULL; if given it must be zeroed by the caller and receives d loss / d Z.
+extern "C" int wspc_smooth_loss_ex(const float* Z, const int32_t* idx, const float* dist, const int32_t* idx_match, int B, int N,
+                                   int C, int knn, float gamma, int flags, float* dZ, float* loss, void* workspace,
+                                   size_t workspace_bytes, wspc_stream_t stream) {
   if (int rc = check_arch()) return rc;
   WSPC_REQUIRE(Z && idx && dist && loss && workspace, "smooth_loss: null pointer");
-  WSPC_REQUIRE(C >= 1 && C <= MAXC && knn >= 1, "smooth_loss: bad shape (C <= %d)", MAXC);
+  WSPC_REQUIRE(C >= 1 && C <= MAXC && knn >= 1 && B >= 1 && N >= 1, "smooth_loss: bad shape (C <= %d)", MAXC);
   WSPC_REQUIRE(workspace_bytes >= 64, "smooth_loss: workspace needs 64 bytes");
+  WSPC_REQUIRE((flags & ~(WSPC_SMOOTH_SUM_C | WSPC_SMOOTH_WEIGHTS | WSPC_SMOOTH_GLOBAL_SS)) == 0, "smooth_loss: unknown flags %d", flags);
+  const bool global_form = (flags & WSPC_SMOOTH_GLOBAL_SS) != 0;
+  WSPC_REQUIRE(!(global_form && dZ), "smooth_loss: the WSPC_SMOOTH_GLOBAL_SS form is forward-only (dZ must be NULL)");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   double* acc = static_cast<double*>(workspace);
   WSPC_CUDA(cudaMemsetAsync(acc, 0, 64, st));
   const long long pts = (long long)B * N;
-  const float gscale = 1.f / (float)((double)C * B * N * knn);
-  smooth_kernel<<<(unsigned)((pts + 7) / 8), 256, 0, st>>>(Z, idx, dist, B, N, C, knn, gamma, gscale, dZ, acc);
-  smooth_finish_kernel<<<1, 1, 0, st>>>(acc, (double)B * N * knn, loss);
+  const float cinv = (flags & WSPC_SMOOTH_SUM_C) ? 1.f : 1.f / (float)C;
+  const float gscale = (float)((double)cinv / ((double)B * N * knn));
+  smooth_kernel<<<(unsigned)((pts + 7) / 8), 256, 0, st>>>(Z, idx, dist, B, N, C, knn, gamma, gscale, dZ, acc, cinv, idx_match,
+                                                           (flags & WSPC_SMOOTH_WEIGHTS) ? 1 : 0, global_form ? 1 : 0);
+  smooth_finish_kernel<<<1, 1, 0, st>>>(acc, (double)B * N * knn, global_form ? 1 : 0, loss);
   count_launch(2);
   WSPC_LAUNCH_CHECK("smooth_kernel");
   return WSPC_OK;
+}
+
+extern "C" int wspc_smooth_loss(const float* Z, const int32_t* idx, const float* dist, int B, int N, int C, int knn,
+                                float gamma, float* dZ, float* loss, void* workspace, size_t workspace_bytes,
+                                wspc_stream_t stream) {
+  return wspc_smooth_loss_ex(Z, idx, dist, nullptr, B, N, C, knn, gamma, 0, dZ, loss, workspace, workspace_bytes, stream);
 }

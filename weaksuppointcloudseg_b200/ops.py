@@ -102,6 +102,34 @@ def smooth_loss(Z: torch.Tensor, X: torch.Tensor, gamma: float = 1e-1, knn: int 
     return (loss[0], dZ) if want_grad else loss[0]
 
 
+SMOOTH_SUM_C, SMOOTH_WEIGHTS, SMOOTH_GLOBAL_SS = 1, 2, 4     # include/wspc.h WSPC_SMOOTH_*
+
+
+def smooth_loss_graph(Z: torch.Tensor, idx: torch.Tensor, dist_or_w: torch.Tensor, gamma: float = 1e-1, flags: int = 0,
+                      idx_match: torch.Tensor = None, want_grad: bool = False):
+    """The smoothness term on a GIVEN kNN graph (wspc_smooth_loss_ex): the variants of Util/SmoothConstraint.py differ in
+    channel reduction (sum / mean), where the weights come from and an optional slot mask."""
+    Z = _as_bnc(Z).contiguous()
+    idx = idx.to(torch.int32).contiguous()
+    dist_or_w = dist_or_w.to(torch.float32).contiguous()
+    L.require_cuda(Z, idx, dist_or_w)
+    B, N, C = Z.shape
+    knn = idx.shape[-1]
+    if tuple(idx.shape) != (B, N, knn) or tuple(dist_or_w.shape) != (B, N, knn):
+        raise L.WspcError(f"smooth_loss_graph: idx {tuple(idx.shape)} / weights {tuple(dist_or_w.shape)} do not match Z {tuple(Z.shape)}")
+    if idx_match is not None:
+        idx_match = idx_match.to(torch.int32).contiguous()
+        L.require_cuda(idx_match)
+        if idx_match.shape != idx.shape:
+            raise L.WspcError("smooth_loss_graph: idx_match must have the shape of idx")
+    loss = torch.empty(1, dtype=torch.float32, device=Z.device)
+    dZ = torch.zeros_like(Z) if want_grad else None
+    ws = L.workspace(256, Z.device, "smooth")
+    L.check(L.lib().wspc_smooth_loss_ex(L.ptr(Z), L.ptr(idx), L.ptr(dist_or_w), L.ptr(idx_match), B, N, C, knn, float(gamma),
+                                        int(flags), L.ptr(dZ), L.ptr(loss), L.ptr(ws), ws.numel(), L.stream()))
+    return (loss[0], dZ) if want_grad else loss[0]
+
+
 def laplacian_sym(X, RGB, scale_xyz: float = 1e3, scale_rgb: float = 1e1) -> torch.Tensor:
     """TF_Computation.LaplacianMatSym_XYZRGB_DirectComp.Eval (Util/Tool.py:435-468): (B,N,3),(B,N,3) -> (B,N,N)."""
     X = torch.as_tensor(X, dtype=torch.float32)
