@@ -1,14 +1,20 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark: point-clouds/sec, forward + weak losses + backward (+ Adam) of the S3DIS
-segmentation DGCNN at N=4096, k=20 (BASELINE.json cfg-3: 64 Siamese samples = 128 network clouds per GPU),
-plus the kNN stage's achieved "materialised-equivalent" GB/s against the measured HBM peak.
+"""bench.py — point-clouds/sec for forward + weak losses + backward (+ TF-Adam) of the weakly supervised DGCNN, plus the
+kNN stage's achieved "materialised-equivalent" GB/s against the measured HBM peak and the tcgen05 EdgeConv kernels against
+the measured bf16 peak.
 
-  python bench.py --gpus N --steps K --warmup W           (N>1: launched under torch.distributed.run)
-  python bench.py --impl reference ...                     (the CPU oracle port on the host cores)
+  python bench.py [--config cfg3|cfg2|cfg4] --gpus N --steps K --warmup W      (N>1: launched under torch.distributed.run)
+  python bench.py --impl reference ...                                           (the CPU oracle port on the host cores)
 
-Prints ONE JSON line (contract in the round brief): value = clouds/s with inputs resident in HBM,
-e2e = the same metric through the public trainer API with pinned HOST buffers (H2D + D2H inside the timed
-region), roofline for the dominant kNN kernel, cpu_baseline (oracle port, bounded sample), clocks, launches.
+  cfg3 (default, BASELINE.json configs[2], the config the metric is quoted on): S3DIS blocks N=4096 k=20, 1 % labels,
+        Full weak losses, 64 Siamese samples = 128 network clouds per GPU (+ the label-propagation stage, timed apart)
+  cfg2 (configs[1]): ShapeNet part segmentation N=2048 k=20, 10 % labels, Siamese + smooth losses, 32 samples = 64 clouds
+  cfg4 (configs[3]): S3DIS stress shape N=8192 k=40, 32 samples = 64 clouds (the same number of points per step as cfg3)
+
+Prints ONE JSON line (contract in the round brief): value = clouds/s with inputs resident in HBM; e2e = the same metric
+through the public trainer API fed NUMPY host arrays like the loaders hand over (pageable -> pinned staging, H2D and the D2H
+of losses + Z_prob inside the timed region); roofline = the dominant kNN launch (HBM); roofline_tensor = the fused EdgeConv
+backward kernel (tensor); cpu_baseline = the oracle port on a bounded sample; clocks; launches.
 """
 from __future__ import annotations
 
@@ -23,8 +29,21 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "point-clouds/sec fwd+loss+bwd at N=4096 k=20"
 UNIT = "clouds/s"
+CONFIGS = {
+    # name: model, points, k, Siamese samples per GPU, labelled points per cloud, metric string
+    "cfg3": dict(model="s3dis", points=4096, k=20, samples=64, n_labelled=40,
+                 metric="point-clouds/sec fwd+loss+bwd at N=4096 k=20",
+                 what="S3DIS-like blocks (BASELINE cfg-3): N=4096 k=20, 1% labels (40/cloud), Full weak losses "
+                      "(seg+Siamese+inexact+smooth)"),
+    "cfg2": dict(model="shapenet", points=2048, k=20, samples=32, n_labelled=204,
+                 metric="point-clouds/sec fwd+loss+bwd at N=2048 k=20 (ShapeNet part segmentation)",
+                 what="ShapeNet-like clouds (BASELINE cfg-2): N=2048 k=20, 16 categories / 50 parts, 10% labels (204/cloud), "
+                      "Full weak losses (seg+Siamese+inexact+smooth), T-net included"),
+    "cfg4": dict(model="s3dis", points=8192, k=40, samples=32, n_labelled=82,
+                 metric="point-clouds/sec fwd+loss+bwd at N=8192 k=40 (S3DIS stress shape)",
+                 what="S3DIS-like blocks (BASELINE cfg-4 stress shape): N=8192 k=40, 1% labels (82/cloud), Full weak losses"),
+}
 
 
 def parse():
@@ -33,21 +52,31 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--samples", type=int, default=64, help="Siamese samples per GPU (network clouds = 2x)")
-    ap.add_argument("--points", type=int, default=4096)
-    ap.add_argument("--cpu-clouds", type=int, default=8, help="clouds per CPU-baseline step (bounded sample)")
+    ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS))
+    ap.add_argument("--samples", type=int, default=None, help="Siamese samples per GPU (network clouds = 2x)")
+    ap.add_argument("--points", type=int, default=None)
+    ap.add_argument("--cpu-clouds", type=int, default=None, help="clouds per CPU-baseline step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-lp", action="store_true", help="skip the separately timed label-propagation stage (cfg3)")
+    args = ap.parse_args()
+    cfg = dict(CONFIGS[args.config], name=args.config)
+    if args.samples is not None:
+        cfg["samples"] = args.samples
+    if args.points is not None:
+        cfg["points"] = args.points
+    if args.cpu_clouds is None:      # bounded CPU sample: ~2.5 s / cloud at N=4096 on 16 cores, quadratic in N
+        args.cpu_clouds = {"cfg3": 8, "cfg2": 16, "cfg4": 4}[args.config]
+    args.cfg = cfg
+    return args
 
 
-def workload_config(args, world):
+def workload_config(cfg, world, clouds_per_gpu=None):
+    cpg = clouds_per_gpu if clouds_per_gpu is not None else 2 * cfg["samples"]
     return {
-        "workload": "S3DIS-like blocks (BASELINE cfg-3): N=%d k=20, 1%% labels (40/cloud), Full weak losses "
-                    "(seg+Siamese+inexact+smooth), batch %d samples = %d network clouds per GPU" %
-                    (args.points, args.samples, 2 * args.samples),
-        "points": args.points, "k": 20, "clouds_per_gpu": 2 * args.samples, "global_clouds": 2 * args.samples * world,
+        "workload": "%s, batch %d samples = %d network clouds per GPU" % (cfg["what"], cpg // 2, cpg),
+        "config": cfg["name"], "points": cfg["points"], "k": cfg["k"], "clouds_per_gpu": cpg, "global_clouds": cpg * world,
         "parallelism": "dp%d (clouds sharded, one NCCL grad all-reduce/step)" % world if world > 1 else "single GPU",
-        "l2": "per-step working set ~26 GB >> 126 MB L2 (no flush needed)",
+        "l2": "per-step working set of several GB >> 126 MB L2 (no flush needed)",
         "includes": "forward, 4 losses, backward, TF-Adam",
     }
 
@@ -66,21 +95,29 @@ def _use_all_host_threads():
     return torch.get_num_threads()
 
 
-def cpu_oracle_steps(n_clouds, N, steps, warmup):
-    import numpy as np
+def cpu_oracle_steps(cfg, n_clouds, steps, warmup):
+    """the oracle's train step (fwd + 4 losses + bwd + TF-Adam) of the same model / N / k on `n_clouds` clouds"""
     import torch
     from oracle import dgcnn as od
     _use_all_host_threads()
     from weaksuppointcloudseg_b200 import synthetic as syn
 
-    X, Y, M, _ = syn.s3dis_batch(max(n_clouds // 2, 1), N=N, n_labelled=40, seed=1234)
-    Xt, Yt, Mt = (torch.from_numpy(a) for a in (X, Y, M))
-    p = od.to_torch(od.init_params(od.S3DIS_LAYERS, seed=1234))
+    ns, N, k = max(n_clouds // 2, 1), cfg["points"], cfg["k"]
+    if cfg["model"] == "s3dis":
+        X, Y, M, _ = syn.s3dis_batch(ns, N=N, n_labelled=cfg["n_labelled"], seed=1234)
+        feed = [torch.from_numpy(a) for a in (X, Y, M)]
+        p = od.to_torch(od.init_params(od.S3DIS_LAYERS, seed=1234))
+        step_fn = od.train_step_s3dis
+    else:
+        X, lab, Y, M, _ = syn.shapenet_batch(ns, N=N, n_labelled=cfg["n_labelled"], seed=1234)
+        feed = [torch.from_numpy(a) for a in (X, lab, Y, M)]
+        p = od.to_torch(od.init_params(od.SHAPENET_LAYERS, seed=1234, shapenet=True))
+        step_fn = od.train_step_shapenet
     opt = od.AdamTF(p, od.trainable_names(p))
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        od.train_step_s3dis(p, opt, Xt, Yt, Mt, step=i, batch_size=max(n_clouds // 2, 1))
+        step_fn(p, opt, *feed, step=i, batch_size=ns, k=k)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
@@ -88,19 +125,22 @@ def cpu_oracle_steps(n_clouds, N, steps, warmup):
 
 
 def run_reference(args):
-    import torch
+    cfg = args.cfg
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = _use_all_host_threads()
-    n, times = cpu_oracle_steps(args.cpu_clouds, args.points, args.steps, args.warmup)
+    n, times = cpu_oracle_steps(cfg, args.cpu_clouds, args.steps, args.warmup)
     total = sum(times)
     v = n * len(times) / total
-    sample = "%d-cloud mini-batches (N=%d, k=20, Full losses, fwd+bwd+Adam), %d timed steps" % (n, args.points, len(times))
+    sample = "%d-cloud mini-batches (N=%d, k=%d, Full losses, fwd+bwd+Adam), %d timed steps" % (n, cfg["points"], cfg["k"], len(times))
+    wc = workload_config(cfg, 1, clouds_per_gpu=n)       # the clouds this arm actually steps over (a bounded sample)
+    wc["parallelism"] = "host CPU, %d threads" % cores
+    wc["bounded_sample_of"] = workload_config(cfg, 1)["workload"]
     out = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": cfg["metric"], "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, 1),
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": wc,
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                          "note": "oracle/ restatement on torch-CPU fp32 (TF-1.14 reference not installable here)"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -153,34 +193,55 @@ class ClockSampler(threading.Thread):
 # --------------------------------------------------------------------------------------------------
 # CUDA arm
 # --------------------------------------------------------------------------------------------------
+def _profile_numbers():
+    """per-kernel DRAM traffic / tensor-pipe activity read from committed ncu captures (profiles/r2_ncu_metrics.json)"""
+    path = os.path.join(ROOT, "profiles", "r2_ncu_metrics.json")
+    if os.path.exists(path):
+        return json.load(open(path))
+    return {}
+
+
 def run_ours(args):
     import numpy as np
     import torch
     from weaksuppointcloudseg_b200 import _lib as L
-    from weaksuppointcloudseg_b200 import parallel, synthetic as syn
-    from weaksuppointcloudseg_b200.S3DIS_DGCNN_trainer import S3DIS_Trainer
+    from weaksuppointcloudseg_b200 import parallel, runtime as rt, synthetic as syn
 
+    cfg = args.cfg
     dp = parallel.DataParallel()
     rank, world = dp.rank, dp.world_size
     dev = torch.device("cuda", dp.local_rank)
     torch.cuda.set_device(dev)
-    B, N, K, W = 2 * args.samples, args.points, args.steps, max(args.warmup, 3)
+    ns, N, k = cfg["samples"], cfg["points"], cfg["k"]
+    B, K, W = 2 * ns, args.steps, max(args.warmup, 3)
 
-    tr = S3DIS_Trainer(device=dev, seed=1234)
-    tr.SetLearningRate(1e-3, args.samples * world)
-    tr.defineNetwork(B, N, style="Full", rampup=0)       # ramp-up gate open: all weak losses optimised
+    if cfg["model"] == "s3dis":
+        from weaksuppointcloudseg_b200.S3DIS_DGCNN_trainer import S3DIS_Trainer
+        tr = S3DIS_Trainer(device=dev, seed=1234)
+        tr.SetLearningRate(1e-3, ns * world)
+        tr.defineNetwork(B, N, style="Full", rampup=0, k=k)      # ramp-up gate open: all weak losses optimised
+        X, Y, M, _ = syn.s3dis_batch(ns, N=N, n_labelled=cfg["n_labelled"], seed=1234 + rank)
+        host = [X, Y, M]                                           # numpy, pageable: what the loaders hand over
+        api = "S3DIS_Trainer.train_batch(numpy X, Y one-hot, Mask) -> losses, Z_prob"
+        smooth_D, ncls = 6, 13
+    else:
+        from weaksuppointcloudseg_b200.ShapeNet_DGCNN_trainer import ShapeNet_Trainer
+        tr = ShapeNet_Trainer(device=dev, seed=1234)
+        tr.SetLearningRate(1e-3, ns * world)
+        tr.defineNetwork(B, point_num=N, style="Full", rampup=0)
+        X, lab, Y, M, _ = syn.shapenet_batch(ns, N=N, n_labelled=cfg["n_labelled"], seed=1234 + rank)
+        host = [X, lab, Y, M]
+        api = "ShapeNet_Trainer.train_batch(numpy X, category one-hot, Y one-hot, Mask) -> losses, Z_prob"
+        smooth_D, ncls = 3, 50
     parallel.attach(tr, dp)
     eng = tr.engine
-
-    X, Y, M, _ = syn.s3dis_batch(args.samples, N=N, n_labelled=40, seed=1234 + rank)
-    host = [torch.from_numpy(a).pin_memory() for a in (X, Y, M)]
-    devt = [t.to(dev) for t in host]
-    h2d = sum(t.numel() * 4 for t in host)
-    d2h = 5 * 4 + B * N * 13 * 4
+    devt = [torch.from_numpy(a).to(dev) for a in host]
+    h2d = sum(a.size * 4 for a in host)
+    d2h = 5 * 4 + B * N * ncls * 4
 
     def step_resident():
-        eng.forward(devt[0], True, tr.get_bn_decay())
-        eng.losses_and_grad(devt[1], devt[2], full=True, want_grad=True)
+        eng.forward(*devt[:-2], True, tr.get_bn_decay())
+        eng.losses_and_grad(devt[-2], devt[-1], full=True, want_grad=True)
         eng.backward()
         tr._allreduce_and_step(tr.get_learning_rate())
 
@@ -192,6 +253,7 @@ def run_ours(args):
     sampler = ClockSampler(dp.local_rank)
     sampler.start()
     eng.prof = []
+    rt.PROF = eng.prof
     dp.barrier()
     torch.cuda.synchronize()
     l0 = L.launch_count()
@@ -204,18 +266,18 @@ def run_ours(args):
     dp.barrier()
     launches = L.launch_count() - l0
     ms_total = dp.max_over_ranks(e0.elapsed_time(e1), dev)
-    prof, eng.prof = eng.prof, None
+    prof, eng.prof, rt.PROF = eng.prof, None, None
     loss_val = float(eng.losses[4])
 
-    # ---- end-to-end through the public trainer API with host buffers -------------------------------
+    # ---- end-to-end through the public trainer API with numpy host buffers --------------------------
     for _ in range(2):
-        tr.train_batch(host[0], host[1], host[2])
+        tr.train_batch(*host)
     dp.barrier()
     torch.cuda.synchronize()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     for _ in range(K):
-        last = tr.train_batch(host[0], host[1], host[2])
+        last = tr.train_batch(*host)
     e3.record()
     torch.cuda.synchronize()
     dp.barrier()
@@ -226,79 +288,121 @@ def run_ours(args):
     # ---- label-propagation stage of cfg-3 ("LP on 64 blocks as a separately timed stage") ----------------
     # test-time path of S3DIS_Trainer.Test: symmetric Laplacian of each block (xyz, rgb) + closed-form LP solve on the
     # network's probabilities, all on the device; timed apart from the training step, never part of `value`.
-    from weaksuppointcloudseg_b200 import ops
-    Xo, Zo = devt[0][0::2], eng.Zp[0::2]
-    nblk = Xo.shape[0]
+    lp_stage = None
+    if cfg["name"] == "cfg3" and not args.no_lp:
+        from weaksuppointcloudseg_b200 import ops
+        Xo, Zo = devt[0][0::2], eng.Zp[0::2]
+        nblk = Xo.shape[0]
+        xyz, rgb = Xo[:, :, 0:3].contiguous(), Xo[:, :, 3:6].contiguous()
+        Zc = Zo.contiguous()
 
-    def lp_block(b):
-        Lm = ops.laplacian_sym(Xo[b:b + 1, :, 0:3].contiguous(), Xo[b:b + 1, :, 3:6].contiguous())
-        return ops.lp_solve(Lm[0], Zo[b].contiguous(), 1.0, 1.0)
+        def lp_all():
+            return ops.lp_blocks(xyz, rgb, Zc, 1.0, 1.0)
 
-    lp_block(0)
-    torch.cuda.synchronize()
-    e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e4.record()
-    for b in range(nblk):
-        lp_block(b)
-    e5.record()
-    torch.cuda.synchronize()
-    ms_lp = dp.max_over_ranks(e4.elapsed_time(e5), dev)
-    lp_stage = {"blocks_per_gpu": nblk, "ms_per_block": ms_lp / nblk, "blocks_per_s": nblk * world / (ms_lp / 1e3),
-                "includes": "Laplacian (N x N, xyz+rgb kernels, symmetric normalisation) + LP solve (Jacobi-PCG on "
-                            "(alpha*L + beta*diag(w)) Y = beta*diag(w) G), N=%d, 13 classes" % N}
+        lp_all()
+        torch.cuda.synchronize()
+        e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e4.record()
+        _, _, _, info = lp_all()
+        e5.record()
+        torch.cuda.synchronize()
+        ms_lp = dp.max_over_ranks(e4.elapsed_time(e5), dev)
+        lp_stage = {"blocks_per_gpu": nblk, "ms_per_block": ms_lp / nblk, "blocks_per_s": nblk * world / (ms_lp / 1e3),
+                    "iterations_max": int(info["iters"].max()), "converged": bool(info["converged"].all()),
+                    "includes": "Laplacian (N x N, xyz+rgb kernels, symmetric normalisation) + LP solve (Jacobi-PCG on "
+                                "(alpha*L + beta*diag(w)) Y = beta*diag(w) G, convergence decided on the device), "
+                                "N=%d, 13 classes, all blocks of the batch in flight" % N}
 
-    # ---- roofline of the dominant kNN kernel (D=64) -----------------------------------------------
-    def knn_bytes(D, k):  # materialised-equivalent bytes of pairwise_distance + knn
-        return B * (2 * N * N * 4 + N * D * 4 + N * k * 4)
+    # ---- rooflines -----------------------------------------------------------------------------------
+    def knn_bytes(D, kk):  # materialised-equivalent bytes of pairwise_distance + knn
+        return B * (2 * N * N * 4 + N * D * 4 + N * kk * 4)
 
     per_tag = {}
     for tag, a, b in prof:
         per_tag.setdefault(tag, []).append(a.elapsed_time(b))
+    mean_ms = {t: statistics.mean(v) for t, v in per_tag.items()}
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
-        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (sustained copy)"
+        pk = json.load(open(peaks_path))
+        peak, peak_src = pk["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+        tpeak, tpeak_src = pk["bf16_tflops_sustained"], "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    dom = "knn_D64_k20"
-    dom_ms = statistics.mean(per_tag[dom]) if dom in per_tag else None
-    achieved = knn_bytes(64, 20) / dom_ms / 1e6 if dom_ms else None
-    stage_ms = sum(statistics.mean(v) * (len(v) / K) for v in per_tag.values())
-    stage_bytes = 2 * knn_bytes(64, 20) + knn_bytes(3, 20) + knn_bytes(6, 10)
+        tpeak, tpeak_src = 1400.0, "fallback (B200_PROFILING.md, sustained)"
+    prof_json = _profile_numbers()
+    dom = "knn_D64_k%d" % k
+    dom_ms = mean_ms.get(dom)
+    achieved = knn_bytes(64, k) / dom_ms / 1e6 if dom_ms else None
+    knn_tags = {t: v for t, v in per_tag.items() if t.startswith("knn_")}
+    stage_ms = sum(statistics.mean(v) * (len(v) / K) for v in knn_tags.values())
+    stage_bytes = 0
+    for t, v in knn_tags.items():
+        D_, k_ = int(t.split("_")[1][1:]), int(t.split("_")[2][1:])
+        stage_bytes += knn_bytes(D_, k_) * (len(v) / K)
+    kt = prof_json.get("knn_tc_kernel_D64", {})
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
-        # dram__bytes_read+write of this kernel from the ncu --set full capture (profiles/r1_knn_tc_d64_summary.md):
-        # 36.14 MB at B=16, linear in the number of clouds
-        "traffic": 36.14e6 * B / 16.0,
-        "kernel": "knn_tc_kernel (tcgen05 distances + two-pass threshold selection + exact re-scoring, D=64, k=20; "
-                  "launch time includes its prep/centre/fallback kernels)",
-        "peak_source": peak_src, "algorithmic_bytes_per_launch": knn_bytes(64, 20), "ms_per_launch": dom_ms,
-        "knn_stage": {"ms_per_step": stage_ms, "equiv_GBs": stage_bytes / stage_ms / 1e6, "frac": stage_bytes / stage_ms / 1e6 / peak,
-                      "per_call_ms": {k_: statistics.mean(v) for k_, v in per_tag.items()}},
+        # dram__bytes_read+write per launch from the committed ncu --set full capture, scaled linearly in clouds
+        "traffic": (kt["dram_bytes_per_cloud"] * B * (N / kt["points"]) ** 2 if N != kt.get("points") else kt["dram_bytes_per_cloud"] * B)
+        if kt else None,
+        "traffic_source": kt.get("source"),
+        "kernel": "knn_tc_kernel (tcgen05 distances + two-pass threshold selection + exact re-scoring, D=64, k=%d; "
+                  "launch time includes its prep/centre/fallback kernels)" % k,
+        "peak_source": peak_src, "algorithmic_bytes_per_launch": knn_bytes(64, k), "ms_per_launch": dom_ms,
+        "knn_stage": {"ms_per_step": stage_ms, "equiv_GBs": stage_bytes / stage_ms / 1e6 if stage_ms else None,
+                      "frac": stage_bytes / stage_ms / 1e6 / peak if stage_ms else None,
+                      "per_call_ms": {t: mean_ms[t] for t in knn_tags}},
     }
+    # tensor roofline of the EdgeConv MLP: the fused backward kernel (the reference's Conv2DBackpropFilter + Conv2DBackpropInput
+    # of adj_conv2/4: two (R x 64 x 64) GEMMs = 4*R*64*64 flop) and the fused forward kernel (one such GEMM).  The kernels
+    # execute more than that: bf16x3 split products and the recomputation of y2 (10 resp. 3 single-pass GEMM equivalents).
+    R = B * N * k
+    roofline_tensor = None
+    if "edgeconv2_bwd" in mean_ms:
+        bwd_ms, fwd_ms = mean_ms["edgeconv2_bwd"], mean_ms.get("edgeconv2_fwd")
+        alg = 4.0 * R * 64 * 64
+        eb = prof_json.get("edgeconv2_bwd_kernel", {})
+        roofline_tensor = {
+            "bound": "tensor", "kernel": "edgeconv2_bwd_kernel (recompute a1,y2 -> dy2 -> dW2 += a1^T dy2, da1 = dy2 W2^T -> "
+                                         "ReLU mask -> row sums + neighbour scatter), per launch",
+            "achieved": alg / bwd_ms / 1e9, "peak": tpeak, "unit": "TFLOP/s", "frac": alg / bwd_ms / 1e9 / tpeak,
+            "executed_TFLOPs": 10 * 2.0 * R * 64 * 64 / bwd_ms / 1e9, "executed_frac": 10 * 2.0 * R * 64 * 64 / bwd_ms / 1e9 / tpeak,
+            "algorithmic_flops_per_launch": alg, "ms_per_launch": bwd_ms, "peak_source": tpeak_src,
+            "ncu_tensor_pipe_pct": eb.get("tensor_pipe_pct"), "traffic": eb.get("dram_bytes_per_point", 0) * B * N or None,
+            "traffic_source": eb.get("source"),
+            "forward_kernel": None if fwd_ms is None else {
+                "kernel": "edgeconv2_fwd_kernel", "ms_per_launch": fwd_ms, "achieved": 2.0 * R * 64 * 64 / fwd_ms / 1e9,
+                "frac": 2.0 * R * 64 * 64 / fwd_ms / 1e9 / tpeak, "executed_frac": 3 * 2.0 * R * 64 * 64 / fwd_ms / 1e9 / tpeak,
+                "ncu_tensor_pipe_pct": prof_json.get("edgeconv2_fwd_kernel", {}).get("tensor_pipe_pct")},
+        }
 
     clouds = B * world
     out = {
-        "metric": METRIC, "value": clouds * K / (ms_total / 1e3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "metric": cfg["metric"], "value": clouds * K / (ms_total / 1e3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": workload_config(args, world),
+        "data": "synthetic", "config": workload_config(cfg, world),
         "e2e": {"value": clouds * K / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e / K, "api": "S3DIS_Trainer.train_batch(host X, Y one-hot, Mask) -> losses, Z_prob"},
-        "gpu_launches": int(launches), "roofline": roofline, "clocks": sampler.summary(),
-        "loss": loss_val, "e2e_loss": last[0], "lp_stage": lp_stage,
+                "ms_per_step": ms_e2e / K, "api": api,
+                "host_buffers": "numpy (pageable); staged through pinned memory inside the timed region"},
+        "gpu_launches": int(launches), "roofline": roofline, "roofline_tensor": roofline_tensor, "clocks": sampler.summary(),
+        "loss": loss_val, "e2e_loss": last[0],
     }
+    if lp_stage is not None:
+        out["lp_stage"] = lp_stage
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import torch as _t
-        n, times = cpu_oracle_steps(args.cpu_clouds, N, steps=2, warmup=1)
+        n, times = cpu_oracle_steps(cfg, args.cpu_clouds, steps=2, warmup=1)
         v = n * len(times) / sum(times)
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": _t.get_num_threads(), "kind": "port",
-                               "sample": "%d-cloud mini-batch, N=%d, same losses, 2 timed steps after 1 warm-up "
-                                         "(oracle/ port on torch-CPU fp32)" % (n, N)}
-        from oracle import lp as olp                      # the reference's dense-inverse LP on one block (bounded sample)
-        zb = np.random.default_rng(0).dirichlet(np.ones(13), N)
-        t0 = time.perf_counter()
-        olp.solve(olp.laplacian_sym(X[0:1, :, 0:3], X[0:1, :, 3:6])[0], zb)
-        out["cpu_baseline"]["lp_ms_per_block"] = 1e3 * (time.perf_counter() - t0)
+                               "sample": "%d-cloud mini-batch, N=%d, k=%d, same losses, 2 timed steps after 1 warm-up "
+                                         "(oracle/ port on torch-CPU fp32)" % (n, N, k)}
+        if lp_stage is not None:
+            from oracle import lp as olp                  # the reference's dense-inverse LP on one block (bounded sample)
+            zb = np.random.default_rng(0).dirichlet(np.ones(13), N)
+            t0 = time.perf_counter()
+            olp.solve(olp.laplacian_sym(X[0:1, :, 0:3], X[0:1, :, 3:6])[0], zb)
+            out["cpu_baseline"]["lp_ms_per_block"] = 1e3 * (time.perf_counter() - t0)
     if rank == 0:
         print(json.dumps(out), flush=True)
     dp.shutdown()

@@ -387,12 +387,22 @@ int wspc_smooth_loss_ex(const float* Z, const int32_t* idx, const float* dist, c
  * X (B,N,D1), RGB (B,N,D2), D <= 3; deg_ws (B,N) scratch; Lout (B,N,N). */
 int wspc_laplacian_sym(const float* X, const float* RGB, int B, int N, int D1, int D2, float scale_xyz,
                        float scale_rgb, float* deg_ws, float* Lout, wspc_stream_t stream);
-/* LabelPropagation_TF.SolveLabelProp (Util/ProbLabelPropagation.py:19-23,38-57):
- * w = 1 - H_2(G)/log_2 K;  Y = beta (alpha L + beta diag(w) + 1e-5 I)^-1 diag(w) G;  Yprob = Y / sum_k Y.
- * The SPD system is solved by Jacobi-preconditioned CG on all K right-hand sides (the matvec is
- * wspc_conv1x1_rows); iteration stops when every column's residual is below tol*||b|| or at max_iter.
- * EXCEPTION to the no-host-sync rule: convergence is polled on the host every 50 iterations.
- * L (N,N), G (N,K) -> Y, Yprob (N,K), w (N); N % 8 == 0, 2 <= K <= 64. */
+/* LabelPropagation_TF.SolveLabelProp (Util/ProbLabelPropagation.py:19-23,38-57) for B independent blocks at once
+ * (the reference's Test loop calls it block by block, S3DIS_DGCNN_trainer.py:541-544):
+ *   w = 1 - H_2(G)/log_2 K;  Y = beta (alpha L + beta diag(w) + 1e-5 I)^-1 diag(w) G;  Yprob = Y / sum_k Y.
+ * Each SPD system is solved by Jacobi-preconditioned CG on all K right-hand sides; the matrix alpha L + diag is never formed
+ * (q = alpha L p + d p).  A block stops when every class column has |r| <= tol |b|; the decision is taken ON THE DEVICE per
+ * block and the call never waits for the GPU: iterations are enqueued in chunks, the host only looks (cudaEventQuery) at
+ * convergence counters that have already landed in pinned memory and stops enqueuing once all B blocks are done.
+ *   L (B,N,N), G (B,N,K) -> Y, Yprob (B,N,K), w (B,N); 2 <= K <= 64, any N (N % 4 == 0 takes the vector loads)
+ *   iters (B) iterations used; resid (B) max_c |r_c|/|b_c| at exit; done (B) 1 = converged, 0 = stopped at max_iter
+ *   (device arrays: the caller checks them when it reads the result). */
+size_t wspc_lp_blocks_workspace_bytes(int B, int N, int K, int max_iter);
+int wspc_lp_blocks(const float* L, const float* G, int B, int N, int K, float alpha, float beta, int max_iter, float tol,
+                   float* Y, float* Yprob, float* w, int32_t* iters, float* resid, int32_t* done, void* workspace,
+                   size_t workspace_bytes, wspc_stream_t stream);
+/* One system = wspc_lp_blocks with B = 1.  iters_out != NULL asks for the iteration count on the host and costs one
+ * copy + stream wait at the END of the call; NULL keeps it asynchronous.  max_iter is capped at 4096. */
 size_t wspc_lp_solve_workspace_bytes(int N, int K);
 int wspc_lp_solve(const float* L, const float* G, int N, int K, float alpha, float beta, int max_iter, float tol,
                   float* Y, float* Yprob, float* w, int* iters_out, void* workspace, size_t workspace_bytes,

@@ -118,6 +118,30 @@ def batch_norm(y, p, scope, is_training, bn_decay, axes):
     return y * inv + (beta - mean * inv)
 
 
+# Forced routing (gradient parity tests): the graph is piecewise linear in its ReLUs / max pools, and two correct fp32
+# implementations may take different branches where a value sits within rounding of a threshold.  With ROUTE set to a dict
+# of decisions exported from the implementation under test (tests/routing.py) every branch is taken as THAT implementation
+# took it, so the remaining difference is arithmetic only and a 1e-3 bound on every gradient tensor means something.
+#   "relu/<scope>"  0/1 mask shaped like the layer output         "maxk/<knn tag>"  (B,N,k,C) weights of the max over k
+#   "maxn/<scope>"  ((B,C) arg-max rows, (B,C) 0/1 ReLU gate)     "inexact"         (B,N,C) weights of the max over points
+ROUTE = None
+
+
+class forced_routing:
+    def __init__(self, route):
+        self.route = route
+
+    def __enter__(self):
+        global ROUTE
+        self.prev, ROUTE = ROUTE, self.route
+        return self.route
+
+    def __exit__(self, *exc):
+        global ROUTE
+        ROUTE = self.prev
+        return False
+
+
 def conv2d(x, p, scope, is_training, bn=True, bn_decay=None, act=True, rec=None):
     """tf_util.conv2d with a [1,1] kernel (tf_util.py:115-173): x W + b -> BN -> ReLU over the last axis."""
     y = x @ p[f"{scope}/weights"] + p[f"{scope}/biases"]                  # :160-165
@@ -126,7 +150,10 @@ def conv2d(x, p, scope, is_training, bn=True, bn_decay=None, act=True, rec=None)
     if bn:
         y = batch_norm(y, p, scope, is_training, bn_decay, tuple(range(y.dim() - 1)))  # :167-169, axes [0,1,2]
     if act:
-        y = torch.relu(y)                                                 # :171-172
+        if ROUTE is not None and f"relu/{scope}" in ROUTE:
+            y = y * ROUTE[f"relu/{scope}"].to(y.dtype).reshape(y.shape)
+        else:
+            y = torch.relu(y)                                             # :171-172
     return y
 
 
@@ -184,8 +211,12 @@ def _edge_block(x_feat, knn_src, p, scopes, is_training, bn_decay, k, rec, tag, 
     if rec is not None:
         rec[f"{tag}/idx"] = idx
     net = get_edge_feature(x_feat, idx)
+    forced = ROUTE.get(f"maxk/{tag}") if ROUTE is not None else None
     for s in scopes:
-        net = conv2d(net, p, s, is_training, bn=True, bn_decay=bn_decay, rec=rec)
+        last = s == scopes[-1]
+        net = conv2d(net, p, s, is_training, bn=True, bn_decay=bn_decay, rec=rec, act=not (last and forced is not None))
+    if forced is not None:      # ReLU + max over k as one routed selection (weights are zero where the ReLU clipped the maximum)
+        return (net * forced.to(net.dtype)).sum(dim=-2)
     return reduce_max_k(net)
 
 
@@ -200,8 +231,12 @@ def get_model_s3dis(p, point_cloud, is_training, bn_decay=None, k=20, dropout_ma
                         knn_override)                                                  # :48-62
     net_3 = _edge_block(net_2, net_2, p, ["adj_conv5"], is_training, bn_decay, k, rec, "knn3", knn_override)  # :64-78
     cat = torch.cat([net_1, net_2, net_3], dim=-1)
-    out7 = conv2d(cat, p, "adj_conv7", is_training, bn=True, bn_decay=bn_decay, rec=rec)     # :80-83
-    out_max = max_pool_points(out7)                                                    # :85
+    mn = ROUTE.get("maxn/adj_conv7") if ROUTE is not None else None
+    out7 = conv2d(cat, p, "adj_conv7", is_training, bn=True, bn_decay=bn_decay, rec=rec, act=mn is None)   # :80-83
+    if mn is None:
+        out_max = max_pool_points(out7)                                                # :85
+    else:
+        out_max = torch.gather(out7, 1, mn[0].long().unsqueeze(1)).squeeze(1) * mn[1].to(out7.dtype)
     expand = out_max.unsqueeze(1).expand(B, N, out_max.shape[-1])                      # :87
     concat = torch.cat([expand, net_1, net_2, net_3], dim=-1)                          # :89-92
     net = conv2d(concat, p, "seg/conv1", is_training, bn=True, bn_decay=None, rec=rec)  # :95-96 (decay 0.9)
@@ -286,7 +321,10 @@ def inexact_loss(Z, Y_onehot):
     """S3DIS_DGCNN_trainer.py:131-134: L_gt = max_n Y; L = max_n Z; mean sigmoid_cross_entropy_with_logits
     = max(x,0) - x*z + log(1 + exp(-|x|)) [TF]; reduce_max gradient: equal split among ties [TF]."""
     L_gt = Y_onehot.to(Z.dtype).amax(dim=1)
-    L = torch.amax(Z, dim=1)
+    if ROUTE is not None and "inexact" in ROUTE:
+        L = (Z * ROUTE["inexact"].to(Z.dtype)).sum(dim=1)
+    else:
+        L = torch.amax(Z, dim=1)
     l = torch.clamp(L, min=0) - L * L_gt + torch.log1p(torch.exp(-L.abs()))
     return l.mean()
 
@@ -364,12 +402,12 @@ class AdamTF:
 
 
 def train_step_s3dis(p, opt, X, Y_onehot, Mask, step=0, base_lr=1e-3, batch_size=None, dropout_mask=None,
-                     full=True, rec=None, knn_override=None, smooth_graph_=None):
+                     full=True, rec=None, knn_override=None, smooth_graph_=None, k=20):
     """One `sess.run([solver, loss, ...])` of TrainOneEpoch_Full (S3DIS_DGCNN_trainer.py:317-323)."""
     bs = batch_size if batch_size is not None else X.shape[0] // 2
     decay = bn_decay(step, bs, 300000)
     lr = learning_rate(step, base_lr, bs, 300000)
-    Z = get_model_s3dis(p, X, True, bn_decay=decay, dropout_mask=dropout_mask, rec=rec, knn_override=knn_override)
+    Z = get_model_s3dis(p, X, True, bn_decay=decay, k=k, dropout_mask=dropout_mask, rec=rec, knn_override=knn_override)
     if full:
         L = weak_sup_losses(Z, X[:, :, 0:6], Y_onehot, Mask, 10.0, smooth_graph_)
     else:
@@ -385,13 +423,13 @@ def train_step_s3dis(p, opt, X, Y_onehot, Mask, step=0, base_lr=1e-3, batch_size
 
 
 def train_step_shapenet(p, opt, X, label, Y_onehot, Mask, step=0, base_lr=1e-3, batch_size=None, dropout_masks=None,
-                        full=True, rec=None, knn_override=None, smooth_graph_=None):
+                        full=True, rec=None, knn_override=None, smooth_graph_=None, k=20):
     """One `sess.run([solver, loss, ...])` of ShapeNet TrainOneEpoch_Full (ShapeNet_DGCNN_trainer.py:308-314);
     DECAY_STEP = 16881*20 (:31), Siamese weight 1 (:123-124), smooth term on xyz (:133)."""
     bs = batch_size if batch_size is not None else X.shape[0] // 2
     decay = bn_decay(step, bs, 16881 * 20)
     lr = learning_rate(step, base_lr, bs, 16881 * 20)
-    Z = get_model_shapenet(p, X, label, True, bn_decay=decay, dropout_masks=dropout_masks, rec=rec,
+    Z = get_model_shapenet(p, X, label, True, bn_decay=decay, k=k, dropout_masks=dropout_masks, rec=rec,
                            knn_override=knn_override)
     if full:
         L = weak_sup_losses(Z, X, Y_onehot, Mask, 1.0, smooth_graph_)

@@ -1,0 +1,90 @@
+"""Worker of tests/test_multigpu_gpu.py: one rank of a 2-GPU data-parallel step (torch.distributed.run, NCCL).
+
+Checks SURVEY §8(e): shard-wise logits against the oracle, the all-reduced update against the oracle's average of the two
+shard gradients, and bit-identical variables on both ranks after the step."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import dgcnn as od  # noqa: E402
+from weaksuppointcloudseg_b200 import parallel, synthetic as syn  # noqa: E402
+from weaksuppointcloudseg_b200.S3DIS_DGCNN_trainer import S3DIS_Trainer  # noqa: E402
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def main():
+    dp = parallel.DataParallel()
+    assert dp.world_size == 2 and dp.backend == "nccl"
+    dev = torch.device("cuda", dp.local_rank)
+    torch.cuda.set_device(dev)
+    ns_global, N = 4, 512
+    X, Y, M, _ = syn.s3dis_batch(ns_global, N=N, n_labelled=12, seed=77)
+    lo, hi = parallel.shard_pairs(ns_global, dp.rank, dp.world_size)
+    sl = slice(2 * lo, 2 * hi)                       # interleaved Siamese rows of this rank's samples
+    B = 2 * (hi - lo)
+    params = od.init_params(od.S3DIS_LAYERS, seed=78 + dp.rank)     # ranks start DIFFERENT: attach() must broadcast rank 0's
+    params0 = od.init_params(od.S3DIS_LAYERS, seed=78)
+    masks = np.floor(0.7 + np.random.default_rng(79).random((2 * ns_global, N, 256))).astype(np.float32)
+
+    tr = S3DIS_Trainer(device=dev, seed=5)
+    tr.SetLearningRate(1e-3, ns_global)
+    tr.defineNetwork(B, N, style="Full", rampup=0, params=params)
+    parallel.attach(tr, dp)
+    loss = tr.train_batch(X[sl], Y[sl], M[sl], dropout_mask=torch.from_numpy(masks[sl]).to(dev))
+    torch.cuda.synchronize()
+
+    # oracle: both shards on their own batch statistics (BN stays per rank), gradients averaged, one TF-Adam step
+    grads, Zs = [], []
+    for r in range(2):
+        l2, h2 = parallel.shard_pairs(ns_global, r, 2)
+        s2 = slice(2 * l2, 2 * h2)
+        p = od.to_torch(params0)
+        opt = od.AdamTF(p, od.trainable_names(p))
+        ov = None
+        if r == dp.rank:      # feature-space neighbour lists of this rank's engine (ties in the last bits)
+            ov = {f"knn{i + 1}": tr.engine.idx[i].cpu().long() for i in (1, 2)}
+        out = od.train_step_s3dis(p, opt, torch.from_numpy(X[s2]), torch.from_numpy(Y[s2]), torch.from_numpy(M[s2]), step=0,
+                                  batch_size=ns_global, dropout_mask=torch.from_numpy(masks[s2]), knn_override=ov)
+        grads.append({k: (v.detach().numpy() if v is not None else None) for k, v in out["grads"].items()})
+        Zs.append(out["Z"].detach().numpy())
+    zerr = rel(tr.engine.Z.cpu().numpy(), Zs[dp.rank])
+    assert zerr <= 1e-3, zerr
+    p = od.to_torch(params0)
+    opt = od.AdamTF(p, od.trainable_names(p))
+    avg = {k: (None if grads[0][k] is None else torch.from_numpy(0.5 * (grads[0][k] + grads[1][k]))) for k in grads[0]}
+    opt.step(avg, od.learning_rate(0, 1e-3, ns_global, 300000))
+    got = tr.engine.vs.export()
+    gmax = max(float(np.abs(g).max()) for g in avg.values() if g is not None)
+    checked = 0
+    for name in od.trainable_names(p):
+        g = avg[name]
+        if g is None or float(g.abs().max()) < 1e-6 * gmax:
+            continue                                 # analytically-zero gradients: the sign of rounding noise
+        sig = np.abs(g.numpy()) > 1e-2 * float(g.abs().max())
+        d_ref = p[name].detach().numpy() - params0[name]
+        d_got = got[name] - params0[name]
+        assert np.mean(np.abs(d_got[sig] - d_ref[sig]) <= 2e-5) >= 0.995, name     # first Adam step = lr * sign(g)
+        checked += 1
+    assert checked >= 20
+
+    # identical variables (and Adam state) on both ranks after the step
+    theta = tr.engine.vs.theta.clone()
+    other = [torch.empty_like(theta) for _ in range(2)]
+    dist.all_gather(other, theta)
+    assert torch.equal(other[0], other[1]), "ranks diverged"
+    print(f"rank {dp.rank} ok: shard logits err {zerr:.2e}, loss {loss[0]:.5f}, {checked} tensors updated like the oracle", flush=True)
+    dp.shutdown()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,120 @@
+"""Batched test-time label propagation (wspc_lp_blocks) against the reference formulation (dense fp64 inverse, oracle/lp.py)
+at the shapes the trainers use: S3DIS blocks N = 4096 (13 classes), ShapeNet shapes N = 3000 (50 classes), several blocks in
+flight with different conditioning, near-uniform predictions (w ~ 0, the ill-conditioned end), a point count that is not a
+multiple of 4, and the per-block convergence report.  Reference: Util/Tool.py:435-468, Util/ProbLabelPropagation.py:19-42,
+S3DIS_DGCNN_trainer.py:541-544, ShapeNet_DGCNN_trainer.py:551-552.  Tolerance: 1e-3 on Y_prob."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import lp as olp
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+def s3dis_like(rng, B, N):
+    """1 m x 1 m x 3 m blocks with N points, colours in [0,1] (DataIO_S3DIS.py:431-433)"""
+    xyz = np.concatenate([rng.uniform(-0.5, 0.5, (B, N, 2)), rng.uniform(0, 3, (B, N, 1))], -1).astype(np.float32)
+    rgb = rng.uniform(0, 1, (B, N, 3)).astype(np.float32)
+    return xyz, rgb
+
+
+def probs(rng, B, N, K, sharp):
+    z = rng.normal(0, 1, (B, N, K)) * np.asarray(sharp, np.float64).reshape(-1, 1, 1)
+    e = np.exp(z - z.max(-1, keepdims=True))
+    return (e / e.sum(-1, keepdims=True)).astype(np.float32)
+
+
+def run_blocks(cuda, xyz, rgb, G, **kw):
+    from weaksuppointcloudseg_b200 import ops
+    Y, Yp, w, info = ops.lp_blocks(torch.from_numpy(xyz).to(cuda), torch.from_numpy(rgb).to(cuda), torch.from_numpy(G).to(cuda),
+                                   1.0, 1.0, **kw)
+    return Y.cpu().numpy(), Yp.cpu().numpy(), w.cpu().numpy(), {k: v.cpu().numpy() for k, v in info.items()}
+
+
+def test_s3dis_blocks_n4096_mixed_conditioning(cuda):
+    """four blocks in flight: confident, medium, near-uniform (w ~ 1e-3) and exactly uniform predictions"""
+    rng = np.random.default_rng(11)
+    B, N, K = 4, 4096, 13
+    xyz, rgb = s3dis_like(rng, B, N)
+    G = probs(rng, B, N, K, [8.0, 2.0, 0.05, 0.0])
+    Y, Yp, w, info = run_blocks(cuda, xyz, rgb, G)
+    Lref = olp.laplacian_sym(xyz, rgb)
+    errs = []
+    for b in range(B):
+        Yref, Ypref, wref = olp.solve(Lref[b], G[b])
+        assert np.abs(w[b] - wref).max() <= 2e-5, b
+        errs.append((rel(Yp[b], Ypref), rel(Y[b], Yref)))
+    print("iters", info["iters"], "resid", info["resid"], "errs", errs)
+    assert info["converged"].all(), info
+    assert max(e[0] for e in errs) <= TOL, errs
+    assert max(e[1] for e in errs[:2]) <= TOL, errs          # Y itself where the system is well conditioned
+    # the confident block needs far fewer iterations than the near-uniform one: per-block stopping
+    assert info["iters"][0] < info["iters"][2]
+    assert info["iters"].max() <= 600
+
+
+def test_shapenet_shape_n3000_k50(cuda):
+    """ShapeNet test shapes: 3000 resampled points (duplicates!), RGB := XYZ, 50 part classes (four 16-column slabs)"""
+    rng = np.random.default_rng(12)
+    N0, N, K = 2400, 3000, 50
+    pts = rng.uniform(-1, 1, (1, N0, 3)).astype(np.float32)
+    pts /= np.sqrt((pts ** 2).sum(-1)).max()
+    idx = np.concatenate([np.arange(N0), rng.choice(N0, N - N0, True)])
+    xyz = pts[:, idx]
+    G = probs(rng, 1, N, K, [3.0])
+    Y, Yp, w, info = run_blocks(cuda, xyz, xyz, G)
+    Yref, Ypref, wref = olp.solve(olp.laplacian_sym(xyz, xyz)[0], G[0])
+    print("iters", info["iters"], "resid", info["resid"])
+    assert info["converged"].all()
+    assert rel(w[0], wref) <= 1e-4
+    assert rel(Yp[0], Ypref) <= TOL
+    # duplicated points receive identical propagated probabilities
+    assert np.abs(Yp[0, N0:] - Yp[0, idx[N0:]]).max() <= 1e-5
+
+
+@pytest.mark.parametrize("N,K", [(301, 13), (1023, 7), (130, 2)])
+def test_ragged_point_counts(cuda, N, K):
+    """N not a multiple of 4 / 32 / 256: scalar-load path and partial tiles of the mat-vec"""
+    rng = np.random.default_rng(N)
+    xyz, rgb = s3dis_like(rng, 2, N)
+    xyz *= 0.3
+    G = probs(rng, 2, N, K, [4.0, 1.0])
+    Y, Yp, w, info = run_blocks(cuda, xyz, rgb, G)
+    Lref = olp.laplacian_sym(xyz, rgb)
+    for b in range(2):
+        _, Ypref, _ = olp.solve(Lref[b], G[b])
+        assert rel(Yp[b], Ypref) <= TOL, (b, info)
+    assert info["converged"].all()
+
+
+def test_max_iter_is_reported_not_hidden(cuda):
+    """a solve that is cut short says so: converged = 0, iters = max_iter, the residual it stopped at"""
+    rng = np.random.default_rng(13)
+    xyz, rgb = s3dis_like(rng, 2, 512)
+    G = probs(rng, 2, 512, 13, [8.0, 0.02])
+    _, _, _, info = run_blocks(cuda, xyz * 0.2, rgb, G, max_iter=3)
+    assert (info["iters"] == 3).all() and (info["converged"] == 0).all() and (info["resid"] > 1e-6).all()
+    _, _, _, info2 = run_blocks(cuda, xyz * 0.2, rgb, G)
+    assert info2["converged"].all() and (info2["resid"] <= 1.01e-6).all()
+
+
+def test_single_system_wrapper_and_class_api(cuda):
+    """ops.lp_solve / LabelPropagation_TF.SolveLabelProp = a batch of one"""
+    from weaksuppointcloudseg_b200 import ops
+    from weaksuppointcloudseg_b200.ProbLabelPropagation import LabelPropagation_TF
+    rng = np.random.default_rng(14)
+    xyz, rgb = s3dis_like(rng, 1, 640)
+    G = probs(rng, 1, 640, 13, [2.0])
+    Lm = olp.laplacian_sym(xyz * 0.2, rgb)[0]
+    _, Ypref, wref = olp.solve(Lm, G[0])
+    _, Yp, w = ops.lp_solve(torch.from_numpy(Lm).to(cuda), torch.from_numpy(G[0]).to(cuda))
+    assert rel(Yp.cpu().numpy(), Ypref) <= TOL and int(ops.lp_solve.last_info["converged"][0]) == 1
+    Yv, Ypv, wv = LabelPropagation_TF(1.0, 1.0, 10).SolveLabelProp(None, Lm, G[0])
+    assert rel(Ypv, Ypref) <= TOL and rel(wv, wref) <= 1e-4

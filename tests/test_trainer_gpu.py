@@ -104,6 +104,44 @@ def test_s3dis_trainer_test_time_label_propagation(cuda, tmp_path):
     assert sum(c.sum() for c in tr.test_stats_net[1:]) == 2 * gt.sum()      # network-only counters saw the same points
 
 
+def test_s3dis_test_predictions_match_the_oracle_pipeline(cuda, tmp_path):
+    """Test() on a graph of 4 blocks (rooms of 6 and 4 blocks: full chunks and a padded tail) against the reference pipeline
+    restated on the CPU -- inference logits (oracle/dgcnn.py) -> softmax -> Laplacian -> dense-inverse label propagation
+    (oracle/lp.py) -> argmax, block by block as S3DIS_DGCNN_trainer.py:527-555 does -- and against a batch-1 graph."""
+    import scipy.io as scio
+    from oracle import dgcnn as od
+    from oracle import lp as olp
+    from weaksuppointcloudseg_b200.DataIO_S3DIS import S3DIS_Test
+    from weaksuppointcloudseg_b200.S3DIS_DGCNN_trainer import S3DIS_Trainer
+    N = 256
+    root = fab.make_s3dis_room(str(tmp_path / 'rooms'))
+    preds = {}
+    for gb in (4, 1):
+        np.random.seed(1)                                   # room -> block sampling draws from the global numpy stream
+        Loader = S3DIS_Test('area5', NUM_POINT=N, data_path=root)
+        tr = S3DIS_Trainer(5, device=cuda, seed=4)
+        tr.SetLearningRate(1e-3, 1)
+        tr.defineNetwork(batch_size=gb, num_points=N, style='Plain', rampup=101)
+        tr.defLabelPropSolver()
+        out = tmp_path / ('pred%d' % gb)
+        out.mkdir()
+        tp, pos, gt = tr.Test(Loader, str(out))
+        preds[gb] = {r: scio.loadmat(str(out / (r + '_pred_gt.mat'))) for r in ('Area_5_office_1', 'Area_5_office_2')}
+        assert all(bool(np.all(res <= 1.01e-6)) for (_, _, _, res) in tr.test_lp_info)
+    params = od.to_torch(tr.engine.vs.export(), requires_grad=False)
+    agree, total = 0, 0
+    for room, m in preds[4].items():
+        data = m['data'].astype(np.float32)
+        assert np.array_equal(m['pred'], preds[1][room]['pred']), "a block's prediction must not depend on its batch mates"
+        Z = od.get_model_s3dis(params, torch.from_numpy(data), False)
+        G = torch.softmax(Z, -1).numpy()
+        Lm = olp.laplacian_sym(data[:, :, 0:3], data[:, :, 3:6])
+        ref = np.concatenate([olp.solve(Lm[b], G[b])[1].argmax(-1) for b in range(data.shape[0])])
+        agree += int((ref == m['pred'].reshape(-1)).sum())
+        total += ref.size
+    assert total >= 8 * N and agree / total >= 0.995, (agree, total)      # arg-max flips only on last-bit ties
+
+
 def test_plain_style_and_closed_rampup_gate(cuda):
     """Plain style optimises the seg term only; Full style with epoch < rampup evaluates the weak terms but multiplies
     them by 0 (the gate is a constant of the graph, S3DIS_DGCNN_trainer.py:93-102)."""

@@ -27,4 +27,4 @@ for sharp in (0.2, 2.0, 8.0):                     # how peaked the network's pro
         if b:
             print("sharp %.1f block %d: laplacian %.3f ms, solve %.3f ms (host %.3f ms), iters %d, mean w %.3f" % (
                 sharp, b, ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), 1e3 * (time.perf_counter() - t0),
-                ops.lp_solve.last_iters, float(w.mean())))
+                int(ops.lp_solve.last_info['iters'][0]), float(w.mean())))

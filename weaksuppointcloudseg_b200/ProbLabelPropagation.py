@@ -1,7 +1,7 @@
 """Drop-in for Util/ProbLabelPropagation.py (reference :3-62): closed-form label propagation.
 
 Same class / method names; `sess` arguments are accepted and ignored.  The solve runs on the GPU through
-wspc_lp_solve (SPD system solved with preconditioned CG instead of the reference's dense inverse)."""
+wspc_lp_blocks (SPD system solved with preconditioned CG instead of the reference's dense inverse)."""
 from __future__ import annotations
 
 import torch
@@ -10,9 +10,9 @@ from . import ops
 
 
 class LabelPropagation_TF():
-    '''
-    The baseline method for label propagation. The closed-form solution is adopted for label propagation.
-    '''
+    '''Propagates per-point class probabilities over a graph Laplacian by solving the regularised linear system
+    (alpha L + beta diag(w) + 1e-5 I) Y = beta diag(w) G once; w is the confidence 1 - normalised entropy of G.
+    Mirrors the reference class of the same name (constructor and method signatures).'''
 
     def __init__(self, alpha, beta, K):
         self.alpha = alpha
@@ -26,22 +26,16 @@ class LabelPropagation_TF():
         self.beta = beta
 
     def SolveLabelProp(self, sess, L, G):
-        '''
-        Solve label propagation with closed-form solution
-        :param L:   Laplacian matrix N*N
-        :param G:   network prediction N*K (dense)
-        :return: Y, Y_prob, w   (numpy, like sess.run)
-        '''
+        '''One propagation.  L: (N,N) symmetric normalised Laplacian, G: (N,K) network probabilities (numpy or tensor).
+        Returns numpy Y (N,K), Y_prob = Y / row sums, w (N,) -- the fetch list of the reference's sess.run (:44-57).'''
         Y, Yp, w = ops.lp_solve(L, G, float(self.alpha), float(self.beta))
         self.Y_val, self.Y_prob_val, self.w_val = Y.cpu().numpy(), Yp.cpu().numpy(), w.cpu().numpy()
         return self.Y_val, self.Y_prob_val, self.w_val
 
     def EvalWeight4EachPoint(self, sess, G):
+        """w = 1 - H_2(G)/log_2 K for every point (reference :59-62)"""
         G = torch.as_tensor(G, dtype=torch.float32)
         N, K = G.shape
-        Lz = torch.zeros((N + (-N) % 8, N + (-N) % 8))
-        Gp = torch.full((Lz.shape[0], K), 1.0 / K)
-        Gp[:N] = G
-        _, _, w = ops.lp_solve(Lz, Gp, 0.0, 1.0, max_iter=1)
-        self.w_val = [w[:N].cpu().numpy()]
+        _, _, w = ops.lp_solve(torch.zeros((N, N)), G, 0.0, 1.0, max_iter=1)
+        self.w_val = [w.cpu().numpy()]
         return self.w_val

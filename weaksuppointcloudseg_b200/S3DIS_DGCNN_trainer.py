@@ -124,7 +124,7 @@ class S3DIS_Trainer():
         return self.engine.vs.step
 
     # ------------------------------------------------------------------ graph (:56-118) ----------
-    def defineNetwork(self, batch_size, num_points, style='Full', rampup=101, params=None):
+    def defineNetwork(self, batch_size, num_points, style='Full', rampup=101, params=None, k=None):
         '''
         define DGCNN network for incomplete labels as supervision
         Args:
@@ -132,6 +132,8 @@ class S3DIS_Trainer():
             num_points: number of points for each point cloud sample
             style: model style, use full model or plain model
             rampup: rampup epoch for training
+            k: neighbours per point of the EdgeConv graphs (the reference hard-codes 20, DGCNN_S3DIS.py:30; BASELINE's
+               stress configuration uses 40)
         '''
         self.rampup = rampup
         self.style = style
@@ -142,7 +144,9 @@ class S3DIS_Trainer():
         if params is None:
             from .engine_s3dis import LAYERS
             params = xavier_params(LAYERS, self.seed)
-        self.engine = S3DISEngine(params, batch_size, num_points, device=self.device)
+        self.engine = S3DISEngine(params, batch_size, num_points, device=self.device, **({} if k is None else {'k': int(k)}))
+        if self.seed is not None:      # tf.nn.dropout draws from the graph-level seed: one mask sequence per trainer seed
+            self.engine.seed = 1234 + 7919 * int(self.seed)
         self.epoch = 0
         # The reference evaluates `epoch >= rampup` once, at graph-build time (:93,:101): the gate is a
         # constant of the graph.  Same here.
@@ -157,7 +161,7 @@ class S3DIS_Trainer():
             self._cstream = torch.cuda.Stream(device=self.device)
         return self._cstream
 
-    def _to_device(self, name, arr, side=False):
+    def _to_device(self, name, arr, side=False, after_forward=False):
         """feed_dict H2D: host arrays go through a persistent pinned staging buffer.  side=True issues the copy on the
         copy stream (overlapping the forward pass); the caller makes the compute stream wait before the first use."""
         if torch.is_tensor(arr) and arr.is_cuda:
@@ -175,7 +179,10 @@ class S3DIS_Trainer():
             t = stage[0]
         if side:
             cs = self._copy_stream()
-            cs.wait_stream(torch.cuda.current_stream())      # the previous step's readers of this buffer are done
+            if not after_forward:  # (after_forward: the only work in flight is this step's forward pass, which never touches
+                                   #  the label buffers; their previous readers finished before the last step returned --
+                                   #  every step ends with the stream synchronisation of _fetch_losses)
+                cs.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(cs):
                 stage[1].copy_(t, non_blocking=True)
         else:
@@ -187,11 +194,13 @@ class S3DIS_Trainer():
         Is_Training_ph=True (:317-323).  Returns (loss, loss_siamese, loss_inexact, loss_smooth, Z_prob)."""
         eng = self.engine
         X = self._to_device('X', data_feed)
-        Y = self._to_device('Y', seg_onehot_feed, side=True)       # only the loss block reads the labels: the 27 MB copy
-        M = self._to_device('Mask', Mask_bin_feed, side=True)      # overlaps the forward pass
         lr, decay = self.get_learning_rate(), self.get_bn_decay()
         full = self.style == 'Full'
-        eng.forward(X, True, decay, dropout_mask)
+        eng.forward(X, True, decay, dropout_mask)                  # enqueued; the device is busy from here on
+        # only the loss block reads the labels: their pageable -> pinned staging (host memcpy, 29 MB at cfg-3) and the H2D
+        # copy on the side stream both run under the forward pass
+        Y = self._to_device('Y', seg_onehot_feed, side=True, after_forward=True)
+        M = self._to_device('Mask', Mask_bin_feed, side=True, after_forward=True)
         torch.cuda.current_stream().wait_stream(self._copy_stream())
         if full and not self.weak_gate:
             # Full graph, gate closed: the weak terms are evaluated (and printed) but multiplied by 0 (:100-102)
@@ -221,17 +230,22 @@ class S3DIS_Trainer():
         return h.numpy().copy()
 
     def _fetch_prob(self, side=False):
+        """D2H of Z_prob into one of TWO pinned buffers used in turn: the array handed back by a step stays valid while the
+        next step runs (the epoch loops read it there) and is overwritten by the step after that."""
         eng = self.engine
         if 'Zp' not in self.pinned:
-            self.pinned['Zp'] = torch.empty(tuple(eng.Zp.shape), dtype=torch.float32, pin_memory=True)
+            self.pinned['Zp'] = [torch.empty(tuple(eng.Zp.shape), dtype=torch.float32, pin_memory=True) for _ in range(2)]
+            self._zp_turn = 0
+        self._zp_turn ^= 1
+        dst = self.pinned['Zp'][self._zp_turn]
         if side:      # Z_prob is final once the loss block has run; nothing in the backward pass writes it
             cs = self._copy_stream()
             cs.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(cs):
-                self.pinned['Zp'].copy_(eng.Zp, non_blocking=True)
+                dst.copy_(eng.Zp, non_blocking=True)
         else:
-            self.pinned['Zp'].copy_(eng.Zp, non_blocking=True)
-        return self.pinned['Zp'].numpy()
+            dst.copy_(eng.Zp, non_blocking=True)
+        return dst.numpy()
 
     def _allreduce_and_step(self, lr):
         gscale = 1.0
@@ -273,41 +287,55 @@ class S3DIS_Trainer():
     def Test(self, Loader, PRED_PATH=None):
         """Inference + label propagation over the test rooms (Test, :499-584).  `Loader` is a DataIO_S3DIS.S3DIS_Test:
         `LoadNextTestRoomData_v1()` -> (blocks (nb,N,9), labels (nb,N), room_path), blocks None after the last room.
-        Per block: one forward pass (Is_Training=False), the symmetric Laplacian of the block (xyz, rgb) and the
-        closed-form LP solve — all on the device, without the reference's 64 MB D2H/H2D round trip per block.  The
-        LP-propagated prediction is scored; per room `<room>_pred_gt.mat` {data, pred, gt} is written to PRED_PATH (:571-580)
-        when given.  Returns (true_positive_classes, positive_classes, gt_classes) like the reference; the network-only
-        counters (no LP) are kept in `self.test_stats_net`."""
+        The reference runs three `sess.run`s per block (:530-544); here the blocks of a room go through the network
+        `engine.B` at a time (inference-mode batch norm uses the population statistics, so a block's logits do not depend on
+        which blocks share its batch), and the Laplacians + label-propagation solves of those blocks run concurrently on the
+        device (`ops.lp_blocks`, convergence decided on the device).  The LP-propagated prediction is scored; per room
+        `<room>_pred_gt.mat` {data, pred, gt} is written to PRED_PATH (:571-580) when given.  Returns
+        (true_positive_classes, positive_classes, gt_classes) like the reference; the network-only counters (no LP) are kept
+        in `self.test_stats_net`, the LP solver's per-block iteration counts / residuals in `self.test_lp_info`."""
         from . import ops
         eng = self.engine
-        C = eng.C
+        C, EB = eng.C, eng.B
         true_positive_classes, positive_classes, gt_classes = np.zeros(C), np.zeros(C), np.zeros(C)
         net = [np.zeros(C), np.zeros(C), np.zeros(C)]
         total_correct = total_seen = 0.
         room_cnt = 0
-        ones = torch.ones((eng.B, eng.N), device=self.device)
+        ones = torch.ones((EB, eng.N), device=self.device)
+        Yz = torch.zeros((EB, eng.N, C), device=self.device)
+        self.test_lp_info = []
         while True:
             data, label, room_path = Loader.LoadNextTestRoomData_v1()
             if data is None:
                 break
             blocks, labels = np.asarray(data, np.float32), np.asarray(label).astype(np.int64)
+            nb = blocks.shape[0]
             allPred = []
-            for bi in range(blocks.shape[0]):
-                X = torch.from_numpy(blocks[bi:bi + 1]).to(self.device)
-                Xf = X.expand(eng.B, -1, -1).contiguous()              # graph batch is static, like the reference
-                eng.forward(Xf, False, None)
-                Yz = torch.zeros((eng.B, eng.N, C), device=self.device)
+            for b0 in range(0, nb, EB):
+                n = min(EB, nb - b0)
+                chunk = blocks[b0:b0 + n]
+                if n < EB:          # the graph batch is static: the tail of a room is padded with its last block
+                    chunk = np.concatenate([chunk, np.repeat(chunk[-1:], EB - n, axis=0)], 0)
+                X = self._to_device('X', np.ascontiguousarray(chunk))
+                eng.forward(X, False, None)
                 eng.losses_and_grad(Yz, ones, full=False, want_grad=False)
-                G = eng.Zp[0].contiguous()
-                Lm = ops.laplacian_sym(X[:, :, 0:3].contiguous(), X[:, :, 3:6].contiguous())   # (:543)
-                _, Yp, _ = ops.lp_solve(Lm[0], G, 1.0, 1.0)                                   # (:544)
+                G = eng.Zp[:n].contiguous()
+                _, Yp, _, info = ops.lp_blocks(X[:n, :, 0:3], X[:n, :, 3:6], G, 1.0, 1.0)       # (:543-544)
                 both = torch.stack([Yp.argmax(-1), G.argmax(-1)]).cpu().numpy()
-                pred = both[0]
-                self._count_classes(pred, labels[bi], C, positive_classes, true_positive_classes, gt_classes)
-                self._count_classes(both[1], labels[bi], C, net[1], net[0], net[2])
-                total_correct += float(np.sum(pred == labels[bi]))
-                total_seen += labels[bi].size
-                allPred.append(pred)
+                conv, its, res = (info[k_].cpu().numpy() for k_ in ("converged", "iters", "resid"))
+                self.test_lp_info.append((room_cnt, b0, its, res))
+                if not conv.all():
+                    print('\nwarning: label propagation stopped at {} iterations for {} block(s) of room {} '
+                          '(relative residual up to {:.1e})'.format(int(its.max()), int((conv == 0).sum()), room_cnt,
+                                                                    float(res.max())))
+                for j in range(n):
+                    bi = b0 + j
+                    pred = both[0][j]
+                    self._count_classes(pred, labels[bi], C, positive_classes, true_positive_classes, gt_classes)
+                    self._count_classes(both[1][j], labels[bi], C, net[1], net[0], net[2])
+                    total_correct += float(np.sum(pred == labels[bi]))
+                    total_seen += labels[bi].size
+                    allPred.append(pred)
                 iou = true_positive_classes / (gt_classes + positive_classes - true_positive_classes + 1e-5)
                 print('\rroom {:d}  acc {:.2f}%  iou: {:.2f}%'.format(room_cnt, 100 * total_correct / total_seen,
                                                                       100 * np.mean(iou)), end='')

@@ -36,6 +36,8 @@ class ShapeNet_Trainer(S3DIS_Trainer):
         if params is None:
             params = xavier_params(LAYERS, self.seed, shapenet=True)
         self.engine = ShapeNetEngine(params, batch_size, point_num, device=self.device)
+        if self.seed is not None:
+            self.engine.seed = 4321 + 7919 * int(self.seed)
         self.epoch = 0
         self.weak_gate = (style == 'Full') and (self.epoch >= self.rampup)   # frozen at build time (:92,:100)
         self.pinned = {}
@@ -210,46 +212,71 @@ class ShapeNet_Trainer(S3DIS_Trainer):
         return avg_loss, avg_acc, perdata_miou, pershape_miou
 
     def Test(self, Loader, Eval, style='Full'):
-        """Test-time pass with label propagation (ShapeNet_DGCNN_trainer.py:511-596): one shape at a time
-        (`Loader.NextSamp_TestSet`), resampled with replacement to the graph's point count (:531-534), inference
-        (Is_Training=False), the symmetric Laplacian with RGB := XYZ (:551) and the closed-form LP solve on the device;
-        the propagated probabilities of the ORIGINAL points are scored.  The graph is the one built by defineNetwork
-        (the reference builds it with batch 1, 3000 points); a larger graph batch is filled with copies."""
+        """Test-time pass with label propagation (ShapeNet_DGCNN_trainer.py:511-596).  Shapes come one at a time from
+        `Loader.NextSamp_TestSet`; each is resampled with replacement to the graph's point count with the reference's
+        np.random calls in the reference's order (:531-534).  `engine.B` shapes then share one inference pass
+        (Is_Training=False: population batch-norm statistics, so a shape's logits do not depend on its batch mates; the
+        reference's graph has batch 1), and their Laplacians (RGB := XYZ, :551) and closed-form LP solves run
+        concurrently on the device; the propagated probabilities of the ORIGINAL points are scored.  `loss_mb` is the
+        segmentation loss of the batch (its mean over shapes equals the mean of the per-shape losses)."""
         from . import ops
         eng = self.engine
+        EB = eng.B
         data_cnt = 0
         shape_cnt = np.zeros(Loader.NUM_CATEGORIES)
         pershape_miou = np.zeros(Loader.NUM_CATEGORIES)
         avg_loss = avg_acc = perdata_miou = 0.
-        while True:
-            SuccessFlag, data, label, seg, _, mb_size, _, _ = Loader.NextSamp_TestSet()
-            if not SuccessFlag:
+        self.test_lp_info = []
+        exhausted = False
+        while not exhausted:
+            pend = []
+            while len(pend) < EB:
+                SuccessFlag, data, label, seg, _, mb_size, _, _ = Loader.NextSamp_TestSet()
+                if not SuccessFlag:
+                    exhausted = True
+                    break
+                data = np.asarray(data, np.float32)
+                label = np.asarray(label).astype(np.int64).reshape(mb_size, -1)
+                seg = np.asarray(seg).astype(np.int64)
+                n0 = data.shape[1]
+                assert mb_size == 1 and n0 <= eng.N, "Test feeds one shape of at most num_point points per call (:524-534)"
+                idx = np.concatenate([np.arange(n0), np.random.choice(np.arange(n0), eng.N - n0, True)]).astype(np.int64)  # (:531-533)
+                pend.append((data[0, idx, :], seg[0, idx], int(label[0, 0]), seg[0], n0))
+            if not pend:
                 break
-            data = np.asarray(data, np.float32)
-            label = np.asarray(label).astype(np.int64).reshape(mb_size, -1)
-            seg = np.asarray(seg).astype(np.int64)
-            n0 = data.shape[1]
-            assert mb_size == 1 and n0 <= eng.N, "Test feeds one shape of at most num_point points per call (:524-534)"
-            idx = np.concatenate([np.arange(n0), np.random.choice(np.arange(n0), eng.N - n0, True)]).astype(np.int64)   # (:531-533)
-            data_feed = np.repeat(data[:, idx, :], eng.B, axis=0)
-            seg_feed = np.repeat(seg[:, idx], eng.B, axis=0)
-            label_feed = np.repeat(Tool.OnehotEncode(label[:, 0], Loader.NUM_CATEGORIES, np.float32), eng.B, axis=0)
-            loss_mb, _ = self.eval_batch(data_feed, label_feed, Tool.OnehotEncode(seg_feed, 50, np.float32),
-                                         np.ones((eng.B, eng.N), np.float32))
-            X0 = eng.X[0:1].contiguous()
-            Lm = ops.laplacian_sym(X0, X0)                                       # (:551)
-            _, Yp, _ = ops.lp_solve(Lm[0], eng.Zp[0].contiguous(), 1.0, 1.0)     # (:552)
-            Z_prob = Yp[:n0].cpu().numpy()
-            shape_label = int(label[0, 0])
-            iou_oids = Loader.object2setofoid[Loader.objcats[shape_label]]
-            pred = self._restrict_to_category(Z_prob, iou_oids)
-            avg_iou = Eval.EvalIoU(pred, seg[0], iou_oids)
-            perdata_miou = (perdata_miou * data_cnt + avg_iou) / (data_cnt + 1)
-            pershape_miou[shape_label] = (pershape_miou[shape_label] * shape_cnt[shape_label] + avg_iou) / \
-                (shape_cnt[shape_label] + 1)
-            avg_acc = (avg_acc * data_cnt + float(np.mean(pred == seg[0]))) / (data_cnt + 1)
-            avg_loss = (avg_loss * data_cnt + loss_mb) / (data_cnt + 1)
-            data_cnt += 1
-            shape_cnt[shape_label] += 1
+            n = len(pend)
+            pad = [pend[-1]] * (EB - n)
+            data_feed = np.stack([q[0] for q in pend + pad]).astype(np.float32)
+            seg_feed = np.stack([q[1] for q in pend + pad])
+            label_feed = Tool.OnehotEncode(np.array([q[2] for q in pend + pad]), Loader.NUM_CATEGORIES, np.float32)
+            mask = np.zeros((EB, eng.N), np.float32)
+            mask[:n] = 1                                         # padding clouds carry no loss
+            X = self._to_device('X', data_feed)
+            Lb = self._to_device('Label', label_feed)
+            Y = self._to_device('Y', Tool.OnehotEncode(seg_feed, 50, np.float32))
+            M = self._to_device('Mask', mask)
+            eng.forward(X, Lb, False, None)
+            eng.losses_and_grad(Y, M, full=False, want_grad=False)
+            Xn = eng.X[:n].contiguous()
+            _, Yp, _, info = ops.lp_blocks(Xn, Xn, eng.Zp[:n].contiguous(), 1.0, 1.0)            # (:551-552)
+            Yp_h = Yp.cpu().numpy()
+            loss_mb = float(self._fetch_losses()[0])
+            conv, its, res = (info[k_].cpu().numpy() for k_ in ("converged", "iters", "resid"))
+            self.test_lp_info.append((data_cnt, its, res))
+            if not conv.all():
+                print('warning: label propagation stopped at {} iterations for {} shape(s) (relative residual up to '
+                      '{:.1e})'.format(int(its.max()), int((conv == 0).sum()), float(res.max())))
+            for j, (_, _, shape_label, seg0, n0) in enumerate(pend):
+                Z_prob = Yp_h[j, :n0]
+                iou_oids = Loader.object2setofoid[Loader.objcats[shape_label]]
+                pred = self._restrict_to_category(Z_prob, iou_oids)
+                avg_iou = Eval.EvalIoU(pred, seg0, iou_oids)
+                perdata_miou = (perdata_miou * data_cnt + avg_iou) / (data_cnt + 1)
+                pershape_miou[shape_label] = (pershape_miou[shape_label] * shape_cnt[shape_label] + avg_iou) / \
+                    (shape_cnt[shape_label] + 1)
+                avg_acc = (avg_acc * data_cnt + float(np.mean(pred == seg0))) / (data_cnt + 1)
+                avg_loss = (avg_loss * data_cnt + loss_mb) / (data_cnt + 1)
+                data_cnt += 1
+                shape_cnt[shape_label] += 1
         return avg_loss, avg_acc, perdata_miou, pershape_miou
 

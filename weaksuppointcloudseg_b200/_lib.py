@@ -158,6 +158,9 @@ _EXTRA_DECLS.update({
     "wspc_smooth_loss": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, c_size_t, _P]),
     "wspc_smooth_loss_ex": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_int, _P, _P, _P, c_size_t, _P]),
     "wspc_laplacian_sym": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_float, c_float, _P, _P, _P]),
+    "wspc_lp_blocks_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "wspc_lp_blocks": (c_int, [_P, _P, c_int, c_int, c_int, c_float, c_float, c_int, c_float, _P, _P, _P, _P, _P, _P, _P,
+                               c_size_t, _P]),
     "wspc_lp_solve_workspace_bytes": (c_size_t, [c_int, c_int]),
     "wspc_lp_solve": (c_int, [_P, _P, c_int, c_int, c_float, c_float, c_int, c_float, _P, _P, _P, ctypes.POINTER(c_int), _P, c_size_t, _P]),
     "wspc_gather": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_longlong, c_int, _P, _P]),

@@ -99,134 +99,82 @@ laplacian_kernel(const float* __restrict__ X, const float* __restrict__ RGB, int
   }
 }
 
-// w = 1 - H_2(G)/log_2 K ; A = alpha L + beta diag(w) + 1e-5 I (in place over a copy of L) ; rhs = beta w G ;
-// dinv = 1 / diag(A)   (ProbLabelPropagation.py:19-22,38-40)
-__global__ void lp_setup_kernel(const float* __restrict__ Lm, const float* __restrict__ G, int N, int K, int Kc,
-                                float alpha, float beta, float* __restrict__ A, float* __restrict__ w,
-                                float* __restrict__ rhs, float* __restrict__ dinv) {
-  const int n = blockIdx.x;
-  __shared__ float sw;
-  if (threadIdx.x == 0) {
-    float h = 0.f;
-    for (int c = 0; c < K; ++c) {
-      const float g = G[(size_t)n * K + c];
-      h += g * logf(g + 1e-5f) / logf(2.f);
-    }
-    const float ww = 1.f - (-h) / (logf((float)K) / logf(2.f));
-    sw = ww;
-    w[n] = ww;
-  }
-  __syncthreads();
-  const float ww = sw;
-  for (int j = threadIdx.x; j < N; j += blockDim.x) {
-    float a = alpha * Lm[(size_t)n * N + j];
-    if (j == n) {
-      a += beta * ww + 1e-5f;
-      dinv[n] = 1.f / a;
-    }
-    A[(size_t)n * N + j] = a;
-  }
-  for (int c = threadIdx.x; c < Kc; c += blockDim.x) rhs[(size_t)n * Kc + c] = (c < K) ? beta * ww * G[(size_t)n * K + c] : 0.f;
-}
-
-// CG state vectors are (N, Kc) row-major; scal = [rz(Kc) | pq(Kc) | rz_new(Kc) | rr(Kc)] fp64
-__global__ void cg_init_kernel(const float* __restrict__ rhs, const float* __restrict__ dinv, int N, int Kc,
-                               float* __restrict__ x, float* __restrict__ r, float* __restrict__ z, float* __restrict__ p,
-                               double* __restrict__ scal) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= N * Kc) return;
-  const int n = t / Kc, c = t % Kc;
-  const float rv = rhs[t], zv = rv * dinv[n];
-  x[t] = 0.f; r[t] = rv; z[t] = zv; p[t] = zv;
-  atomicAdd(&scal[c], (double)rv * (double)zv);
-}
-__global__ void cg_dot_kernel(const float* __restrict__ p, const float* __restrict__ q, int N, int Kc,
-                              double* __restrict__ scal) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= N * Kc) return;
-  atomicAdd(&scal[Kc + t % Kc], (double)p[t] * (double)q[t]);
-}
-__global__ void cg_update_kernel(const float* __restrict__ q, const float* __restrict__ dinv, int N, int Kc,
-                                 float* __restrict__ x, float* __restrict__ r, float* __restrict__ z,
-                                 const float* __restrict__ p, double* __restrict__ scal) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= N * Kc) return;
-  const int n = t / Kc, c = t % Kc;
-  const double pq = scal[Kc + c];
-  const float alpha = (pq != 0.0) ? (float)(scal[c] / pq) : 0.f;
-  x[t] += alpha * p[t];
-  const float rv = r[t] - alpha * q[t];
-  const float zv = rv * dinv[n];
-  r[t] = rv;
-  z[t] = zv;
-  atomicAdd(&scal[2 * Kc + c], (double)rv * (double)zv);
-  atomicAdd(&scal[3 * Kc + c], (double)rv * (double)rv);
-}
-// Same update for Kc dividing the block size (N * Kc a multiple of 256): the two dot products are reduced inside the block
-// first -- 2 Kc fp64 atomics per block instead of 2 per element (4096 per address and iteration at N = 4096).
-__global__ void __launch_bounds__(256)
-cg_update_blockred_kernel(const float* __restrict__ q, const float* __restrict__ dinv, int Kc, float* __restrict__ x,
-                          float* __restrict__ r, float* __restrict__ z, const float* __restrict__ p,
-                          double* __restrict__ scal) {
-  __shared__ double s_rz[256], s_rr[256];
-  const int tid = threadIdx.x;
-  const int t = blockIdx.x * 256 + tid;
-  const int n = t / Kc, c = t % Kc;
-  const double pq = scal[Kc + c];
-  const float alpha = (pq != 0.0) ? (float)(scal[c] / pq) : 0.f;
-  x[t] += alpha * p[t];
-  const float rv = r[t] - alpha * q[t];
-  const float zv = rv * dinv[n];
-  r[t] = rv;
-  z[t] = zv;
-  s_rz[tid] = (double)rv * (double)zv;
-  s_rr[tid] = (double)rv * (double)rv;
-  __syncthreads();
-  if (tid < Kc) {            // 256 % Kc == 0: entries tid, tid + Kc, ... share the column
-    double a = 0.0, b = 0.0;
-    for (int i = tid; i < 256; i += Kc) { a += s_rz[i]; b += s_rr[i]; }
-    atomicAdd(&scal[2 * Kc + tid], a);
-    atomicAdd(&scal[3 * Kc + tid], b);
-  }
-}
-__global__ void cg_dir_kernel(const float* __restrict__ z, int N, int Kc, float* __restrict__ p, double* __restrict__ scal,
-                              double* __restrict__ resid_out) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < N * Kc) {
-    const int c = t % Kc;
-    const double rz = scal[c];
-    const float beta = (rz != 0.0) ? (float)(scal[2 * Kc + c] / rz) : 0.f;
-    p[t] = z[t] + beta * p[t];
-  }
-}
-// roll the scalars after every thread of cg_dir has read them (separate launch => ordering by the stream)
-__global__ void cg_roll_kernel(int Kc, double* __restrict__ scal, double* __restrict__ resid_out) {
-  const int c = threadIdx.x;
-  if (c < Kc) {
-    scal[c] = scal[2 * Kc + c];
-    if (resid_out) resid_out[c] = scal[3 * Kc + c];
-    scal[Kc + c] = 0.0;
-    scal[2 * Kc + c] = 0.0;
-    scal[3 * Kc + c] = 0.0;
-  }
-}
-// q = A p for the CG loop, A (N, N) row-major, p / q (N, 16) row-major, plus the dot products pq[c] = sum_n p[n,c] q[n,c]
-// (fp64 atomics into scal_pq[0:16]).  A CTA owns 32 rows (4 per warp); 256 columns of A and the matching 256 rows of p are
-// staged in shared memory while the next chunk's global loads are already in flight in registers.  A lane accumulates
-// 4 rows x 16 columns over the columns j = lane (mod 32) of every chunk; a butterfly sums the lanes at the end.
-// (The tcgen05 row GEMM runs this shape -- 4096 x 4096 x 16 -- on 32 CTAs with a serial chunk pipeline: 213 us; this
-// kernel: every SM busy, A streamed once.)
+// mat-vec tiling: a CTA owns 32 rows (4 per warp); 256 columns of L and the matching 256 rows of p are staged in shared
+// memory while the next chunk's global loads are already in flight in registers.  A lane accumulates 4 rows x 16 columns over
+// the columns j = lane (mod 32) of every chunk; a butterfly sums the lanes at the end.
 constexpr int MV_ROWS = 32, MV_JC = 256, MV_PLD = 20;
 constexpr size_t MV_SMEM = sizeof(float) * (MV_ROWS * MV_JC + MV_JC * MV_PLD + 8 * 16);
+
+// ================================================= batched label propagation: every block of a room in flight =========
+// One set of launches solves B independent systems (alpha L_b + diag(d_b)) Y_b = rhs_b; A is never formed (q = alpha L p + d p).
+// Scalars live in per-iteration slots  scal[b][it][{rz, pq, rr}][64]  (zeroed once), so no kernel has to roll or re-zero them:
+//   matvec(it)  pq[it]  += p.q
+//   update(it)  alpha = rz[it] / pq[it];  x += alpha p;  r -= alpha q;  z = dinv r;   rz[it+1] += r.z;  rr[it] += r.r
+//   dir(it)     converged (rr[it] <= tol^2 |b|^2 for every class) -> done[b] = 1, iters[b] = it + 1;  else p = z + (rz[it+1]/rz[it]) p
+// Every kernel returns at once for a block whose done flag is set: convergence is decided on the device, per block.
+constexpr int LPB_SC = 64;                       // scalar slot pitch (Kc <= 64)
+__device__ __forceinline__ double* lpb_slot(double* scal, int b, int it, int which, int iters_alloc) {
+  return scal + (((size_t)b * iters_alloc + it) * 3 + which) * LPB_SC;
+}
+
+// w, diagonal d = beta w + 1e-5, dinv = 1 / (alpha L_nn + d), rhs = beta w G, x = 0, r = rhs, z = p = dinv r, rz[0], |b|^2
+__global__ void __launch_bounds__(128)
+lpb_setup_kernel(const float* __restrict__ Lm, const float* __restrict__ G, int N, int K, int Kc, float alpha, float beta,
+                 float* __restrict__ w, float* __restrict__ diag, float* __restrict__ dinv, float* __restrict__ x,
+                 float* __restrict__ r, float* __restrict__ z, float* __restrict__ p, double* __restrict__ scal,
+                 double* __restrict__ b2, int iters_alloc) {
+  const int b = blockIdx.y;
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 4), c0 = threadIdx.x & 15;   // 16 threads per point
+  __shared__ double s_rz[8][LPB_SC], s_b2[8][LPB_SC];
+  const int pl = threadIdx.x >> 4;
+  for (int c = c0; c < Kc; c += 16) { s_rz[pl][c] = 0.0; s_b2[pl][c] = 0.0; }
+  const bool valid = n < N;
+  const size_t row = (size_t)b * N + (valid ? n : 0);
+  const float* g = G + row * K;
+  float h = 0.f;
+  if (valid)
+    for (int c = c0; c < K; c += 16) h += g[c] * logf(g[c] + 1e-5f) / logf(2.f);       // ProbLabelPropagation.py:38-39
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o, 16);
+  if (valid) {
+    const float ww = 1.f - (-h) / (logf((float)K) / logf(2.f));                           // :40
+    const float d = beta * ww + 1e-5f;                                                      // :21-22
+    const float di = 1.f / (alpha * Lm[row * N + n] + d);
+    if (c0 == 0) { w[row] = ww; diag[row] = d; dinv[row] = di; }
+    for (int c = c0; c < Kc; c += 16) {
+      const float rv = (c < K) ? beta * ww * g[c] : 0.f;
+      const float zv = rv * di;
+      const size_t t = row * Kc + c;
+      x[t] = 0.f; r[t] = rv; z[t] = zv; p[t] = zv;
+      s_rz[pl][c] = (double)rv * (double)zv;
+      s_b2[pl][c] = (double)rv * (double)rv;
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < Kc; c += 128) {
+    double a = 0.0, e = 0.0;
+    for (int i = 0; i < 8; ++i) { a += s_rz[i][c]; e += s_b2[i][c]; }
+    atomicAdd(lpb_slot(scal, b, 0, 0, iters_alloc) + c, a);
+    atomicAdd(b2 + (size_t)b * LPB_SC + c, e);
+  }
+}
+
+// q = alpha L p + d p for one 16-column slab of one block (grid: row tiles x slabs x blocks), dots pq[it] += p.q
 __global__ void __launch_bounds__(256, 1)
-lp_matvec16_kernel(const float* __restrict__ A, const float* __restrict__ p, int N, float* __restrict__ q,
-                   double* __restrict__ scal_pq) {
+lpb_matvec_kernel(const float* __restrict__ Lm, const float* __restrict__ p, const float* __restrict__ diag, float alpha, int N,
+                  int Kc, int it, int iters_alloc, float* __restrict__ q, double* __restrict__ scal,
+                  const int* __restrict__ done) {
+  const int b = blockIdx.z, slab = blockIdx.y;
+  if (done[b]) return;
   extern __shared__ __align__(16) unsigned char mv_smem[];
   float (*sA)[MV_JC] = reinterpret_cast<float (*)[MV_JC]>(mv_smem);
   float (*sP)[MV_PLD] = reinterpret_cast<float (*)[MV_PLD]>(mv_smem + sizeof(float) * MV_ROWS * MV_JC);
   float (*sdot)[16] = reinterpret_cast<float (*)[16]>(mv_smem + sizeof(float) * (MV_ROWS * MV_JC + MV_JC * MV_PLD));
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n0 = blockIdx.x * MV_ROWS;
+  const float* A = Lm + (size_t)b * N * N;
+  const float* pb = p + (size_t)b * N * Kc + slab * 16;
+  const bool vec = (N & 3) == 0;
   float acc[4][16];
 #pragma unroll
   for (int r = 0; r < 4; ++r)
@@ -238,13 +186,25 @@ lp_matvec16_kernel(const float* __restrict__ A, const float* __restrict__ p, int
     for (int u = 0; u < 8; ++u) {
       const int f = tid + 256 * u, r = f >> 6, c4 = f & 63;
       const int n = n0 + r, j = j0 + c4 * 4;
-      ra[u] = (n < N && j < N) ? *reinterpret_cast<const float4*>(A + (size_t)n * N + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (n < N) {
+        const float* src = A + (size_t)n * N + j;
+        if (vec) {
+          if (j < N) v = *reinterpret_cast<const float4*>(src);
+        } else {
+          if (j < N) v.x = src[0];
+          if (j + 1 < N) v.y = src[1];
+          if (j + 2 < N) v.z = src[2];
+          if (j + 3 < N) v.w = src[3];
+        }
+      }
+      ra[u] = v;
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int f = tid + 256 * u, jr = f >> 2, q4 = f & 3;
       const int j = j0 + jr;
-      rp[u] = (j < N) ? *reinterpret_cast<const float4*>(p + (size_t)j * 16 + q4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      rp[u] = (j < N) ? *reinterpret_cast<const float4*>(pb + (size_t)j * Kc + q4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
   fetch(0);
@@ -279,7 +239,6 @@ lp_matvec16_kernel(const float* __restrict__ A, const float* __restrict__ p, int
       }
     }
   }
-  // lanes -> one value per (row, column): fixed-order butterfly, then lane c keeps column c
   float dotc = 0.f;
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
@@ -293,8 +252,10 @@ lp_matvec16_kernel(const float* __restrict__ A, const float* __restrict__ p, int
     }
     const int n = n0 + warp * 4 + r;
     if (lane < 16 && n < N) {
-      q[(size_t)n * 16 + lane] = mine;
-      dotc = fmaf(mine, p[(size_t)n * 16 + lane], dotc);
+      const float pn = pb[(size_t)n * Kc + lane];
+      const float qv = fmaf(alpha, mine, diag[(size_t)b * N + n] * pn);
+      q[((size_t)b * N + n) * Kc + slab * 16 + lane] = qv;
+      dotc = fmaf(qv, pn, dotc);
     }
   }
   if (lane < 16) sdot[warp][lane] = dotc;
@@ -303,20 +264,107 @@ lp_matvec16_kernel(const float* __restrict__ A, const float* __restrict__ p, int
     double d = 0.0;
 #pragma unroll
     for (int w = 0; w < 8; ++w) d += (double)sdot[w][tid];
-    atomicAdd(scal_pq + tid, d);
+    atomicAdd(lpb_slot(scal, b, it, 1, iters_alloc) + slab * 16 + tid, d);
   }
 }
 
-__global__ void lp_finish_kernel(const float* __restrict__ x, int N, int K, int Kc, float* __restrict__ Y,
-                                 float* __restrict__ Yp) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
-  float s = 0.f;
-  for (int c = 0; c < K; ++c) s += x[(size_t)n * Kc + c];
+// grid (ceil(N*Kc/256), B); Kc in {16, 32, 64} divides the block size, so entries tid, tid + Kc, ... share a column and the
+// two dot products are reduced inside the block first (2 Kc fp64 atomics per block)
+__global__ void __launch_bounds__(256)
+lpb_update_kernel(const float* __restrict__ q, const float* __restrict__ dinv, int N, int Kc, int it, int iters_alloc,
+                  float* __restrict__ x, float* __restrict__ r, float* __restrict__ z, const float* __restrict__ p,
+                  double* __restrict__ scal, const int* __restrict__ done) {
+  const int b = blockIdx.y;
+  if (done[b]) return;
+  __shared__ double s_rz[256], s_rr[256];
+  const int tid = threadIdx.x;
+  const int e = blockIdx.x * 256 + tid;
+  double vrz = 0.0, vrr = 0.0;
+  if (e < N * Kc) {
+    const int n = e / Kc, c = e - n * Kc;
+    const size_t t = (size_t)b * N * Kc + e;
+    const double pq = lpb_slot(scal, b, it, 1, iters_alloc)[c];
+    const float a = (pq != 0.0) ? (float)(lpb_slot(scal, b, it, 0, iters_alloc)[c] / pq) : 0.f;
+    x[t] += a * p[t];
+    const float rv = r[t] - a * q[t];
+    const float zv = rv * dinv[(size_t)b * N + n];
+    r[t] = rv;
+    z[t] = zv;
+    vrz = (double)rv * (double)zv;
+    vrr = (double)rv * (double)rv;
+  }
+  s_rz[tid] = vrz;
+  s_rr[tid] = vrr;
+  __syncthreads();
+  if (tid < Kc) {
+    double a = 0.0, c2 = 0.0;
+    for (int i = tid; i < 256; i += Kc) { a += s_rz[i]; c2 += s_rr[i]; }
+    atomicAdd(lpb_slot(scal, b, it + 1, 0, iters_alloc) + tid, a);
+    atomicAdd(lpb_slot(scal, b, it, 2, iters_alloc) + tid, c2);
+  }
+}
+
+__device__ __forceinline__ bool lpb_converged(const double* rr, const double* b2, int K, float tol, float* worst) {
+  bool ok = true;
+  float wr = 0.f;
   for (int c = 0; c < K; ++c) {
-    const float v = x[(size_t)n * Kc + c];
-    Y[(size_t)n * K + c] = v;
-    Yp[(size_t)n * K + c] = v / s;          // ProbLabelPropagation.py:23
+    const double ref = b2[c] > 0.0 ? b2[c] : 1.0;
+    if (rr[c] > (double)tol * tol * ref) ok = false;
+    wr = fmaxf(wr, (float)sqrt(rr[c] / ref));
+  }
+  *worst = wr;
+  return ok;
+}
+
+__global__ void __launch_bounds__(256)
+lpb_dir_kernel(const float* __restrict__ z, int N, int K, int Kc, int it, int iters_alloc, float tol, float* __restrict__ p,
+               const double* __restrict__ scal_c, const double* __restrict__ b2, const int* __restrict__ done) {
+  const int b = blockIdx.y;
+  if (done[b]) return;             // (set by an earlier launch; this launch's own decision is taken below by every CTA alike)
+  double* scal = const_cast<double*>(scal_c);
+  float worst;
+  const bool conv = lpb_converged(lpb_slot(scal, b, it, 2, iters_alloc), b2 + (size_t)b * LPB_SC, K, tol, &worst);
+  if (conv) return;                // every CTA of the block reads the same completed sums -> the same decision; the flag is
+                                   // written by lpb_flag_kernel, a separate launch
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  if (e < N * Kc) {
+    const int c = e % Kc;
+    const size_t t = (size_t)b * N * Kc + e;
+    const double rz = lpb_slot(scal, b, it, 0, iters_alloc)[c];
+    const float bt = (rz != 0.0) ? (float)(lpb_slot(scal, b, it + 1, 0, iters_alloc)[c] / rz) : 0.f;
+    p[t] = z[t] + bt * p[t];
+  }
+}
+// one thread per block: records convergence after dir(it) (a separate launch, so no CTA of dir(it) can see a flag that another
+// CTA of the same launch has just set and skip its part of p)
+__global__ void lpb_flag_kernel(int B, int K, int it, int iters_alloc, float tol, const double* __restrict__ scal_c,
+                                const double* __restrict__ b2, int* __restrict__ done, int* __restrict__ iters,
+                                float* __restrict__ resid, int* __restrict__ n_done, int last) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B || done[b]) return;
+  double* scal = const_cast<double*>(scal_c);
+  float worst;
+  const bool conv = lpb_converged(lpb_slot(scal, b, it, 2, iters_alloc), b2 + (size_t)b * LPB_SC, K, tol, &worst);
+  if (conv || last) {
+    iters[b] = it + 1;
+    resid[b] = worst;
+    if (conv) {
+      done[b] = 1;
+      atomicAdd(n_done, 1);
+    }
+  }
+}
+
+__global__ void lpb_finish_kernel(const float* __restrict__ x, long long rows, int K, int Kc, float* __restrict__ Y,
+                                  float* __restrict__ Yp) {
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= rows) return;
+  float s = 0.f;
+  for (int c = 0; c < K; ++c) s += x[n * Kc + c];
+  for (int c = 0; c < K; ++c) {
+    const float v = x[n * Kc + c];
+    Y[n * K + c] = v;
+    Yp[n * K + c] = v / s;          // ProbLabelPropagation.py:23
   }
 }
 
@@ -364,86 +412,145 @@ extern "C" int wspc_laplacian_sym(const float* X, const float* RGB, int B, int N
   return WSPC_OK;
 }
 
-extern "C" size_t wspc_lp_solve_workspace_bytes(int N, int K) {
-  const int Kc = ((K + 3) / 4 * 4) < 16 ? 16 : (K + 3) / 4 * 4;
-  return align_up((size_t)N * N * 4, 256) + 6 * align_up((size_t)N * Kc * 4, 256) + align_up((size_t)N * 4, 256) + 4096;
+static int lpb_kc(int K) { return K <= 16 ? 16 : (K <= 32 ? 32 : 64); }   // divides the 256-thread blocks
+
+extern "C" size_t wspc_lp_blocks_workspace_bytes(int B, int N, int K, int max_iter) {
+  const int Kc = lpb_kc(K);
+  const size_t vec = align_up((size_t)B * N * Kc * 4, 256);
+  return 5 * vec + 2 * align_up((size_t)B * N * 4, 256) + align_up((size_t)B * (max_iter + 1) * 3 * LPB_SC * 8, 256) +
+         align_up((size_t)B * LPB_SC * 8, 256) + align_up((size_t)B * 4, 256) + 256;
 }
 
-extern "C" int wspc_lp_solve(const float* Lm, const float* G, int N, int K, float alpha, float beta, int max_iter,
-                             float tol, float* Y, float* Yprob, float* w, int* iters_out, void* workspace,
-                             size_t workspace_bytes, wspc_stream_t stream) {
+// All B systems advance together; nothing here blocks the host.  Iterations are enqueued in chunks of LPB_CHUNK; after each
+// chunk the number of converged blocks is copied to pinned host memory, and before enqueuing a later chunk the host LOOKS at
+// the copies that have already landed (cudaEventQuery, never a wait): once every block has converged it stops enqueuing.
+// A host that runs ahead of the device simply enqueues up to max_iter iterations, which return at once for finished blocks.
+extern "C" int wspc_lp_blocks(const float* Lm, const float* G, int B, int N, int K, float alpha, float beta, int max_iter,
+                              float tol, float* Y, float* Yprob, float* w, int32_t* iters, float* resid, int32_t* done,
+                              void* workspace, size_t workspace_bytes, wspc_stream_t stream) {
   if (int rc = check_arch()) return rc;
-  WSPC_REQUIRE(Lm && G && Y && Yprob && w && workspace, "lp_solve: null pointer");
-  WSPC_REQUIRE(N >= 1 && K >= 2 && K <= 64 && (N % 8) == 0, "lp_solve: need 2 <= K <= 64 and N %% 8 == 0");
-  if (workspace_bytes < wspc_lp_solve_workspace_bytes(N, K)) {
-    set_error("lp_solve: workspace too small");
+  WSPC_REQUIRE(Lm && G && Y && Yprob && w && iters && resid && done && workspace, "lp_blocks: null pointer");
+  WSPC_REQUIRE(B >= 1 && B <= 65535 && N >= 1 && K >= 2 && K <= 64 && max_iter >= 1 && max_iter <= 100000,
+               "lp_blocks: need 1 <= B <= 65535, 2 <= K <= 64, 1 <= max_iter <= 100000");
+  WSPC_REQUIRE(aligned16(Lm), "lp_blocks: L must be 16-byte aligned");
+  if (workspace_bytes < wspc_lp_blocks_workspace_bytes(B, N, K, max_iter)) {
+    set_error("lp_blocks: workspace %zu < required %zu", workspace_bytes, wspc_lp_blocks_workspace_bytes(B, N, K, max_iter));
     return WSPC_ERR_WORKSPACE;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int Kc = ((K + 3) / 4 * 4) < 16 ? 16 : (K + 3) / 4 * 4;
+  const int Kc = lpb_kc(K), IA = max_iter + 1;
   char* wsp = static_cast<char*>(workspace);
-  const size_t vb = align_up((size_t)N * Kc * 4, 256);
-  float* A = reinterpret_cast<float*>(wsp); wsp += align_up((size_t)N * N * 4, 256);
-  float* rhs = reinterpret_cast<float*>(wsp); wsp += vb;
+  const size_t vb = align_up((size_t)B * N * Kc * 4, 256), nb = align_up((size_t)B * N * 4, 256);
   float* x = reinterpret_cast<float*>(wsp); wsp += vb;
   float* r = reinterpret_cast<float*>(wsp); wsp += vb;
   float* z = reinterpret_cast<float*>(wsp); wsp += vb;
   float* p = reinterpret_cast<float*>(wsp); wsp += vb;
   float* q = reinterpret_cast<float*>(wsp); wsp += vb;
-  float* dinv = reinterpret_cast<float*>(wsp); wsp += align_up((size_t)N * 4, 256);
-  double* scal = reinterpret_cast<double*>(wsp);           // 4*Kc doubles (Kc <= 64 -> 2 KB) + residuals (512 B)
-  double* resid = scal + 4 * 64;
-  static const cudaError_t mv_attr =
-      cudaFuncSetAttribute(lp_matvec16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MV_SMEM);
-  WSPC_CUDA(mv_attr);
-  lp_setup_kernel<<<N, 128, 0, st>>>(Lm, G, N, K, Kc, alpha, beta, A, w, rhs, dinv);
-  WSPC_CUDA(cudaMemsetAsync(scal, 0, 4096, st));
-  const int nt = N * Kc;
-  cg_init_kernel<<<(nt + 255) / 256, 256, 0, st>>>(rhs, dinv, N, Kc, x, r, z, p, scal);
-  count_launch(2);
-  wspc_operand_t Aop;
-  memset(&Aop, 0, sizeof(Aop));
-  Aop.p = A; Aop.ld = N; Aop.C = N;
-  wspc_epilogue_t ep;
-  memset(&ep, 0, sizeof(ep));
-  ep.out = q; ep.ldo = Kc; ep.rb_rows = 1;
-  double h_res[64], h_b2[64];
-  int it = 0;
-  bool have_b2 = false;
-  const int check_every = 50;
-  for (; it < max_iter; ++it) {
-    if (Kc == 16) {   // q = A p and the p.q dots in one pass over A
-      lp_matvec16_kernel<<<(N + MV_ROWS - 1) / MV_ROWS, 256, MV_SMEM, st>>>(A, p, N, q, scal + Kc);
-    } else {
-      if (int rc = wspc_conv1x1_rows(&Aop, WSPC_OP_PLAIN, p, Kc, 0, N, Kc, N, &ep, WSPC_EPI_STORE, stream)) return rc;
-      cg_dot_kernel<<<(nt + 255) / 256, 256, 0, st>>>(p, q, N, Kc, scal);
-    }
-    if (256 % Kc == 0 && nt % 256 == 0) cg_update_blockred_kernel<<<nt / 256, 256, 0, st>>>(q, dinv, Kc, x, r, z, p, scal);
-    else cg_update_kernel<<<(nt + 255) / 256, 256, 0, st>>>(q, dinv, N, Kc, x, r, z, p, scal);
-    cg_dir_kernel<<<(nt + 255) / 256, 256, 0, st>>>(z, N, Kc, p, scal, nullptr);
-    cg_roll_kernel<<<1, 64, 0, st>>>(Kc, scal, resid);
-    count_launch(4);
-    if ((it + 1) % check_every == 0 || (it + 1 <= check_every && (it + 1) % 10 == 0) || it + 1 == max_iter) {
-      if (!have_b2) {   // ||b||^2 per column, once (host-side convergence control only)
-        std::vector<float> hb((size_t)N * Kc);
-        WSPC_CUDA(cudaMemcpyAsync(hb.data(), rhs, hb.size() * 4, cudaMemcpyDeviceToHost, st));
-        WSPC_CUDA(cudaStreamSynchronize(st));
-        for (int c = 0; c < Kc; ++c) h_b2[c] = 0.0;
-        for (size_t i = 0; i < hb.size(); ++i) h_b2[i % Kc] += (double)hb[i] * hb[i];
-        have_b2 = true;
+  float* diag = reinterpret_cast<float*>(wsp); wsp += nb;
+  float* dinv = reinterpret_cast<float*>(wsp); wsp += nb;
+  double* scal = reinterpret_cast<double*>(wsp);
+  const size_t scal_bytes = align_up((size_t)B * IA * 3 * LPB_SC * 8, 256);
+  wsp += scal_bytes;
+  double* b2 = reinterpret_cast<double*>(wsp); wsp += align_up((size_t)B * LPB_SC * 8, 256);
+  int* n_done = reinterpret_cast<int*>(wsp);
+
+  int dev = 0;
+  WSPC_CUDA(cudaGetDevice(&dev));
+  static bool attr_set[64] = {};
+  if (dev < 64 && !attr_set[dev]) {       // the opt-in shared-memory size is a per-device attribute
+    WSPC_CUDA(cudaFuncSetAttribute(lpb_matvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MV_SMEM));
+    attr_set[dev] = true;
+  }
+  constexpr int LPB_CHUNK = 16, LPB_SLOTS = 8;
+  struct Poll { int* host; cudaEvent_t ev[LPB_SLOTS]; bool pending[LPB_SLOTS]; bool ok; };
+  static thread_local Poll poll = {nullptr, {}, {}, false};
+  if (!poll.host) {
+    if (cudaHostAlloc(reinterpret_cast<void**>(&poll.host), LPB_SLOTS * sizeof(int), cudaHostAllocDefault) == cudaSuccess) {
+      poll.ok = true;
+      for (int i = 0; i < LPB_SLOTS; ++i) {
+        poll.pending[i] = false;
+        if (cudaEventCreateWithFlags(&poll.ev[i], cudaEventDisableTiming) != cudaSuccess) poll.ok = false;
       }
-      WSPC_CUDA(cudaMemcpyAsync(h_res, resid, Kc * 8, cudaMemcpyDeviceToHost, st));
-      WSPC_CUDA(cudaStreamSynchronize(st));
-      bool done = true;
-      for (int c = 0; c < K; ++c)
-        if (h_res[c] > (double)tol * tol * (h_b2[c] > 0 ? h_b2[c] : 1.0)) done = false;
-      if (done) { ++it; break; }
+    }
+    (void)cudaGetLastError();
+  }
+  bool can_poll = poll.ok;
+  if (can_poll) {     // copies of an earlier call that are still in flight would be mistaken for this call's counters
+    for (int i = 0; i < LPB_SLOTS; ++i)
+      if (poll.pending[i]) {
+        if (cudaEventQuery(poll.ev[i]) == cudaSuccess) poll.pending[i] = false;
+        else { (void)cudaGetLastError(); can_poll = false; }
+      }
+    if (can_poll) for (int i = 0; i < LPB_SLOTS; ++i) poll.host[i] = 0;
+  }
+
+  WSPC_CUDA(cudaMemsetAsync(scal, 0, scal_bytes + align_up((size_t)B * LPB_SC * 8, 256) + 256, st));   // scal, b2, n_done
+  WSPC_CUDA(cudaMemsetAsync(done, 0, (size_t)B * 4, st));
+  WSPC_CUDA(cudaMemsetAsync(iters, 0, (size_t)B * 4, st));
+  lpb_setup_kernel<<<dim3((N + 7) / 8, B), 128, 0, st>>>(Lm, G, N, K, Kc, alpha, beta, w, diag, dinv, x, r, z, p, scal, b2, IA);
+  count_launch();
+  const dim3 gmv((N + MV_ROWS - 1) / MV_ROWS, Kc / 16, B), gvec((N * Kc + 255) / 256, B);
+  int chunk = 0;
+  bool stop = false;
+  for (int it = 0; it < max_iter && !stop; ++it) {
+    const int last = (it + 1 == max_iter) ? 1 : 0;
+    lpb_matvec_kernel<<<gmv, 256, MV_SMEM, st>>>(Lm, p, diag, alpha, N, Kc, it, IA, q, scal, done);
+    lpb_update_kernel<<<gvec, 256, 0, st>>>(q, dinv, N, Kc, it, IA, x, r, z, p, scal, done);
+    lpb_dir_kernel<<<gvec, 256, 0, st>>>(z, N, K, Kc, it, IA, tol, p, scal, b2, done);
+    lpb_flag_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, K, it, IA, tol, scal, b2, done, iters, resid, n_done, last);
+    count_launch(4);
+    if (!can_poll || last || (it + 1) % LPB_CHUNK != 0) continue;
+    const int slot = chunk++ % LPB_SLOTS;
+    if (poll.pending[slot]) {               // the host is a full ring ahead of the device: skip this sample
+      if (cudaEventQuery(poll.ev[slot]) != cudaSuccess) { (void)cudaGetLastError(); continue; }
+      poll.pending[slot] = false;
+      if (poll.host[slot] >= B) { stop = true; continue; }
+    }
+    WSPC_CUDA(cudaMemcpyAsync(poll.host + slot, n_done, sizeof(int), cudaMemcpyDeviceToHost, st));
+    WSPC_CUDA(cudaEventRecord(poll.ev[slot], st));
+    poll.pending[slot] = true;
+    for (int s2 = 0; s2 < LPB_SLOTS; ++s2) {   // look at whatever has landed, never wait (the counter only grows)
+      if (!poll.pending[s2]) continue;
+      if (cudaEventQuery(poll.ev[s2]) == cudaSuccess) {
+        poll.pending[s2] = false;
+        if (poll.host[s2] >= B) stop = true;
+      } else {
+        (void)cudaGetLastError();
+      }
     }
   }
-  lp_finish_kernel<<<(N + 127) / 128, 128, 0, st>>>(x, N, K, Kc, Y, Yprob);
+  lpb_finish_kernel<<<(unsigned)(((long long)B * N + 127) / 128), 128, 0, st>>>(x, (long long)B * N, K, Kc, Y, Yprob);
   count_launch();
-  WSPC_LAUNCH_CHECK("lp kernels");
-  if (iters_out) *iters_out = it;
+  WSPC_LAUNCH_CHECK("lp_blocks kernels");
+  return WSPC_OK;
+}
+
+// single system = a batch of one (kept for Util/ProbLabelPropagation.LabelPropagation_TF.SolveLabelProp callers)
+extern "C" size_t wspc_lp_solve_workspace_bytes(int N, int K) {
+  return wspc_lp_blocks_workspace_bytes(1, N, K, 4096) + 256;
+}
+
+extern "C" int wspc_lp_solve(const float* Lm, const float* G, int N, int K, float alpha, float beta, int max_iter,
+                             float tol, float* Y, float* Yprob, float* w, int* iters_out, void* workspace,
+                             size_t workspace_bytes, wspc_stream_t stream) {
+  WSPC_REQUIRE(workspace, "lp_solve: null pointer");
+  if (max_iter > 4096) max_iter = 4096;
+  if (workspace_bytes < wspc_lp_solve_workspace_bytes(N, K)) {
+    set_error("lp_solve: workspace too small");
+    return WSPC_ERR_WORKSPACE;
+  }
+  int32_t* flags = static_cast<int32_t*>(workspace);          // [iters, done] + resid
+  float* resid = reinterpret_cast<float*>(flags + 2);
+  if (int rc = wspc_lp_blocks(Lm, G, 1, N, K, alpha, beta, max_iter, tol, Y, Yprob, w, flags, resid, flags + 1,
+                              static_cast<char*>(workspace) + 256, workspace_bytes - 256, stream))
+    return rc;
+  if (iters_out) {     // the caller asked for a host-side count: one copy + wait at the very end (NULL keeps the call asynchronous)
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int32_t h = 0;
+    WSPC_CUDA(cudaMemcpyAsync(&h, flags, sizeof(h), cudaMemcpyDeviceToHost, st));
+    WSPC_CUDA(cudaStreamSynchronize(st));
+    *iters_out = h;
+  }
   return WSPC_OK;
 }
 

@@ -100,8 +100,9 @@ class ShapeNetEngine:
             self.idx[i].copy_(ov[tag])
             return
         ws = L.workspace(L.lib().wspc_knn_workspace_bytes(B, N, D), self.dev, "knn")
-        L.check(L.lib().wspc_knn_fused(ctypes.c_void_p(src_addr), B, N, ld, coff, D, k, L.DIST_TFUTIL, L.ptr(self.idx[i]),
-                                       None, L.ptr(ws), ws.numel(), L.stream()))
+        with rt._timed(f"knn_D{D}_k{k}"):
+            L.check(L.lib().wspc_knn_fused(ctypes.c_void_p(src_addr), B, N, ld, coff, D, k, L.DIST_TFUTIL, L.ptr(self.idx[i]),
+                                           None, L.ptr(ws), ws.numel(), L.stream()))
 
     # -------------------------------------------------------------------------------- forward ----
     def forward(self, X, label_onehot, is_training, bn_decay=None, dropout_masks=None, knn_override=None):
@@ -208,8 +209,9 @@ class ShapeNetEngine:
                 self.dS.copy_(smooth_graph[1])
             else:   # smooth term on X_ph xyz (ShapeNet_DGCNN_trainer.py:133)
                 ws = L.workspace(L.lib().wspc_knn_workspace_bytes(B, N, 3), self.dev, "knn")
-                L.check(L.lib().wspc_knn_fused(L.ptr(self.X), B, N, 3, 0, 3, SMOOTH_KNN, L.DIST_SMOOTH, L.ptr(self.idxS),
-                                               L.ptr(self.dS), L.ptr(ws), ws.numel(), L.stream()))
+                with rt._timed(f"knn_D3_k{SMOOTH_KNN}"):
+                    L.check(L.lib().wspc_knn_fused(L.ptr(self.X), B, N, 3, 0, 3, SMOOTH_KNN, L.DIST_SMOOTH, L.ptr(self.idxS),
+                                                   L.ptr(self.dS), L.ptr(ws), ws.numel(), L.stream()))
         ws = L.workspace(L.lib().wspc_head_losses_workspace_bytes(B, N, C), self.dev, "head")
         L.check(L.lib().wspc_head_losses(L.ptr(self.Z), L.ptr(Y), L.ptr(Mask), L.ptr(self.idxS) if full else None,
                                          L.ptr(self.dS) if full else None, B, N, C, SMOOTH_KNN, SMOOTH_GAMMA, SIAMESE_W,

@@ -145,29 +145,53 @@ def laplacian_sym(X, RGB, scale_xyz: float = 1e3, scale_rgb: float = 1e1) -> tor
     return out
 
 
-def lp_solve(Lmat, G, alpha: float = 1.0, beta: float = 1.0, max_iter: int = 3000, tol: float = 1e-6):
-    """LabelPropagation_TF.SolveLabelProp (Util/ProbLabelPropagation.py:44-57): L (N,N), G (N,K) -> Y, Y_prob, w."""
-    import ctypes
+LP_MAX_ITER = 600      # Jacobi-PCG needs 10-20 iterations on confident predictions and ~150 when w ~ 0 (near-uniform G)
+
+
+def lp_blocks_on_graph(Lmat, G, alpha: float = 1.0, beta: float = 1.0, max_iter: int = LP_MAX_ITER, tol: float = 1e-6):
+    """LabelPropagation_TF.SolveLabelProp (Util/ProbLabelPropagation.py:44-57) for a batch of blocks: L (B,N,N), G (B,N,K) ->
+    Y, Y_prob (B,N,K), w (B,N), info {iters, resid, converged} (device tensors; nothing here waits for the GPU)."""
+    L.require_cuda(Lmat, G)
+    Lmat, G = Lmat.contiguous(), G.to(torch.float32).contiguous()
+    B, N, K = G.shape
+    if tuple(Lmat.shape) != (B, N, N):
+        raise L.WspcError(f"lp_blocks: L {tuple(Lmat.shape)} does not match G {tuple(G.shape)}")
+    dev = G.device
+    Y = torch.empty((B, N, K), dtype=torch.float32, device=dev)
+    Yp = torch.empty((B, N, K), dtype=torch.float32, device=dev)
+    w = torch.empty((B, N), dtype=torch.float32, device=dev)
+    iters = torch.empty((B,), dtype=torch.int32, device=dev)
+    done = torch.empty((B,), dtype=torch.int32, device=dev)
+    resid = torch.empty((B,), dtype=torch.float32, device=dev)
+    ws = L.workspace(L.lib().wspc_lp_blocks_workspace_bytes(B, N, K, max_iter), dev, "lp")
+    L.check(L.lib().wspc_lp_blocks(L.ptr(Lmat), L.ptr(G), B, N, K, alpha, beta, max_iter, tol, L.ptr(Y), L.ptr(Yp), L.ptr(w),
+                                   L.ptr(iters), L.ptr(resid), L.ptr(done), L.ptr(ws), ws.numel(), L.stream()))
+    return Y, Yp, w, {"iters": iters, "resid": resid, "converged": done}
+
+
+def lp_blocks(xyz, rgb, G, alpha: float = 1.0, beta: float = 1.0, max_iter: int = LP_MAX_ITER, tol: float = 1e-6,
+              scale_xyz: float = 1e3, scale_rgb: float = 1e1):
+    """The test-time stage of S3DIS_Trainer.Test / ShapeNet_Trainer.Test for every block of a batch at once: symmetric
+    Laplacian of (xyz, rgb) (Util/Tool.py:435-468) -> label propagation of the network's probabilities G.  The (B,N,N)
+    Laplacians live in a cached workspace (67 MB per block at N = 4096)."""
+    L.require_cuda(xyz, rgb, G)
+    xyz, rgb = xyz.to(torch.float32).contiguous(), rgb.to(torch.float32).contiguous()
+    B, N, D1 = xyz.shape
+    D2 = rgb.shape[-1]
+    buf = L.workspace(B * N * N * 4 + B * N * 4, xyz.device, "lp_laplacian")
+    Lm = buf[:B * N * N * 4].view(torch.float32).view(B, N, N)
+    deg = buf[B * N * N * 4:B * N * N * 4 + B * N * 4].view(torch.float32)
+    L.check(L.lib().wspc_laplacian_sym(L.ptr(xyz), L.ptr(rgb), B, N, D1, D2, scale_xyz, scale_rgb, L.ptr(deg), L.ptr(Lm),
+                                       L.stream()))
+    return lp_blocks_on_graph(Lm, G, alpha, beta, max_iter, tol)
+
+
+def lp_solve(Lmat, G, alpha: float = 1.0, beta: float = 1.0, max_iter: int = LP_MAX_ITER, tol: float = 1e-6):
+    """LabelPropagation_TF.SolveLabelProp (Util/ProbLabelPropagation.py:44-57): L (N,N), G (N,K) -> Y, Y_prob, w.
+    `lp_solve.last_info` holds the device-side {iters, resid, converged} of the call."""
     Lmat = torch.as_tensor(Lmat, dtype=torch.float32)
     G = torch.as_tensor(G, dtype=torch.float32)
     dev = Lmat.device if Lmat.is_cuda else torch.device("cuda", torch.cuda.current_device())
-    Lmat, G = Lmat.to(dev).contiguous(), G.to(dev).contiguous()
-    N, K = G.shape
-    pad = (-N) % 8
-    if pad:  # isolated padding nodes (identity rows) keep the system SPD and do not touch the real ones
-        Lp = torch.zeros((N + pad, N + pad), dtype=torch.float32, device=dev)
-        Lp[:N, :N] = Lmat
-        Lp[N:, N:] = torch.eye(pad, device=dev)
-        Gp = torch.full((N + pad, K), 1.0 / K, dtype=torch.float32, device=dev)
-        Gp[:N] = G
-        Y, Yp, w = lp_solve(Lp, Gp, alpha, beta, max_iter, tol)
-        return Y[:N].contiguous(), Yp[:N].contiguous(), w[:N].contiguous()
-    Y = torch.empty((N, K), dtype=torch.float32, device=dev)
-    Yp = torch.empty((N, K), dtype=torch.float32, device=dev)
-    w = torch.empty((N,), dtype=torch.float32, device=dev)
-    ws = L.workspace(L.lib().wspc_lp_solve_workspace_bytes(N, K), dev, "lp")
-    iters = ctypes.c_int(0)
-    L.check(L.lib().wspc_lp_solve(L.ptr(Lmat), L.ptr(G), N, K, alpha, beta, max_iter, tol, L.ptr(Y), L.ptr(Yp), L.ptr(w),
-                                  ctypes.byref(iters), L.ptr(ws), ws.numel(), L.stream()))
-    lp_solve.last_iters = iters.value
-    return Y, Yp, w
+    Y, Yp, w, info = lp_blocks_on_graph(Lmat.to(dev)[None], G.to(dev)[None], alpha, beta, max_iter, tol)
+    lp_solve.last_info = info
+    return Y[0], Yp[0], w[0]

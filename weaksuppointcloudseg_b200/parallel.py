@@ -77,6 +77,8 @@ def shard_pairs(n_samples_global: int, rank: int, world_size: int):
 def attach(trainer, dp: DataParallel) -> None:
     """make `trainer.train_batch` all-reduce its gradients; synchronise the initial variables."""
     trainer.dist = dp
+    # every rank draws its own dropout masks (one Philox stream per rank), as independent tf.nn.dropout ops would
+    trainer.engine.seed = int(trainer.engine.seed) + 104729 * dp.rank
     if dp.enabled:
         dp.broadcast_params(trainer.engine.vs.theta)
         dp.broadcast_params(trainer.engine.vs.state)

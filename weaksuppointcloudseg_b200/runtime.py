@@ -423,6 +423,29 @@ class EdgeFused:
         return w
 
 
+PROF = None      # optional list of (tag, start_event, end_event): bench.py times the tcgen05 EdgeConv kernels inside the step
+
+
+class _timed:
+    """CUDA events around one launch on the current stream when PROF is a list; free otherwise."""
+
+    def __init__(self, tag):
+        self.tag = tag
+
+    def __enter__(self):
+        self.e0 = None
+        if PROF is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if self.e0 is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            PROF.append((self.tag, self.e0, e1))
+        return False
+
+
 def _zero_cols(t, col0, ncols):
     L.check(L.lib().wspc_zero_cols(L.ptr(t), t.shape[1], col0, ncols, t.shape[0], L.stream()))
 
@@ -453,9 +476,10 @@ def edgeblock_forward(ef: EdgeFused, st: EdgeBlockState, l1: Layer, l2, x, ld, c
     if not single:
         if training:
             zero_(l2.stats)
-        L.check(lib.wspc_edgeconv2_fwd(L.ptr(st.UV), 128, L.ptr(idx), L.ptr(l1.b), L.ptr(l1.sc), L.ptr(l1.sh), L.ptr(l2.W),
-                                       L.ptr(l2.b), P, k, npts, 64, 64, L.ptr(l2.stats) if training else None, L.ptr(st.MM),
-                                       L.stream()))
+        with _timed("edgeconv2_fwd"):
+            L.check(lib.wspc_edgeconv2_fwd(L.ptr(st.UV), 128, L.ptr(idx), L.ptr(l1.b), L.ptr(l1.sc), L.ptr(l1.sh), L.ptr(l2.W),
+                                           L.ptr(l2.b), P, k, npts, 64, 64, L.ptr(l2.stats) if training else None,
+                                           L.ptr(st.MM), L.stream()))
         bn_finalize(l2, R, training, decay)
         last = l2
     L.check(lib.wspc_maxk_from_extrema(L.ptr(st.MM), L.ptr(last.sc), L.ptr(last.sh), P, 64, ctypes.c_void_p(out_addr), out_ld,
@@ -483,10 +507,11 @@ def edgeblock_backward(ef: EdgeFused, st: EdgeBlockState, l1: Layer, l2, x, ld, 
                                       L.ptr(l2.db), L.stream()))
         nbytes = lib.wspc_edgeconv2_bwd_workspace_bytes()
         ws = L.workspace(nbytes, ef.device, "edgeconv_bwd")
-        L.check(lib.wspc_edgeconv2_bwd(L.ptr(st.UV), 128, L.ptr(idx), L.ptr(l1.b), L.ptr(l1.sc), L.ptr(l1.sh), L.ptr(l2.W),
-                                       L.ptr(l2.b), L.ptr(l2.sc), L.ptr(l2.sh), L.ptr(l2.c1), L.ptr(l2.c2), L.ptr(l2.c3),
-                                       L.ptr(ef.MS), P, k, npts, 64, 64, L.ptr(ef.TS), L.ptr(l2.dW), L.ptr(ws), ws.numel(),
-                                       L.stream()))
+        with _timed("edgeconv2_bwd"):
+            L.check(lib.wspc_edgeconv2_bwd(L.ptr(st.UV), 128, L.ptr(idx), L.ptr(l1.b), L.ptr(l1.sc), L.ptr(l1.sh), L.ptr(l2.W),
+                                           L.ptr(l2.b), L.ptr(l2.sc), L.ptr(l2.sh), L.ptr(l2.c1), L.ptr(l2.c2), L.ptr(l2.c3),
+                                           L.ptr(ef.MS), P, k, npts, 64, 64, L.ptr(ef.TS), L.ptr(l2.dW), L.ptr(ws), ws.numel(),
+                                           L.stream()))
     zero_(l1.bstats)
     L.check(lib.wspc_edge_bwd_stats(L.ptr(ef.TS), L.ptr(st.UV), 128, L.ptr(l1.b), P, 64, L.ptr(l1.bstats), L.stream()))
     bn_bwd_coeffs(l1, R)
