@@ -6,16 +6,18 @@ The fused engine never stores an edge tensor, so the per-edge decisions are re-d
   first conv of a block   a1 = relu(v_j*sc + (u_i*sc + (b*sc + sh))) from the stored UV = [u | v] and the folded BN affine
                           (the expression csrc/edgeconv.cu evaluates; plain torch rounds the products separately from the
                           fused multiply-adds, which can only matter for values within an ulp of zero)
-  max over k              the row(s) whose post-ReLU value is closest to the pooled output the engine wrote (equally close rows
+  max over k              the row(s) whose pre-ReLU value is closest to the pooled output the engine wrote (equally close rows
                           = exact ties, e.g. duplicated neighbours, share the gradient as tf.reduce_max does); no row where
                           the pooled value is 0 (clipped by the ReLU)
 """
 import torch
 
 
-def _maxk_weights(val, out):
-    """val (P,k,C) candidate post-ReLU values, out (P,C) pooled output of the engine -> (P,k,C) weights"""
-    diff = (val - out.unsqueeze(1)).abs()
+def _maxk_weights(pre, out):
+    """pre (P,k,C) candidate PRE-ReLU values, out (P,C) pooled post-ReLU output of the engine -> (P,k,C) weights.
+    Where out > 0 the row that produced it is the one whose value is closest to it (a value the engine saw as +1e-7 may be
+    -1e-5 here: comparing before the ReLU still finds its row); where out == 0 the ReLU clipped the maximum: no row."""
+    diff = (pre - out.unsqueeze(1)).abs()
     best = diff.min(dim=1, keepdim=True).values
     scale = out.abs().max().clamp_min(1e-30)
     sel = (diff <= best + 1e-7 * scale).to(torch.float64)
@@ -39,14 +41,14 @@ def export_s3dis(eng):
         out = cat[:, col:col + 64].double()
         if s2 is None:
             y = ((u + l1.b).unsqueeze(1) + v[gi])                             # pre-BN y1 as edge_gather_stats forms it
-            val = torch.relu(y * l1.sc + l1.sh).double()
+            val = (y * l1.sc + l1.sh).double()
             route[f"maxk/knn{i + 1}"] = _maxk_weights(val, out).view(B, N, k, 64).cpu()
         else:
             l2 = Ly[s2]
             route[f"relu/{s1}"] = (pre1 > 0).view(B, N, k, 64).cpu()
             a1 = torch.relu(pre1).double()
             y2 = a1 @ l2.W.double() + l2.b.double()
-            val = torch.relu(y2 * l2.sc.double() + l2.sh.double())
+            val = y2 * l2.sc.double() + l2.sh.double()
             route[f"maxk/knn{i + 1}"] = _maxk_weights(val, out).view(B, N, k, 64).cpu()
             del a1, y2
         del pre1, val

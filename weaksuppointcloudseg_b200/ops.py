@@ -151,8 +151,8 @@ LP_MAX_ITER = 600      # Jacobi-PCG needs 10-20 iterations on confident predicti
 def lp_blocks_on_graph(Lmat, G, alpha: float = 1.0, beta: float = 1.0, max_iter: int = LP_MAX_ITER, tol: float = 1e-6):
     """LabelPropagation_TF.SolveLabelProp (Util/ProbLabelPropagation.py:44-57) for a batch of blocks: L (B,N,N), G (B,N,K) ->
     Y, Y_prob (B,N,K), w (B,N), info {iters, resid, converged} (device tensors; nothing here waits for the GPU)."""
-    L.require_cuda(Lmat, G)
     Lmat, G = Lmat.contiguous(), G.to(torch.float32).contiguous()
+    L.require_cuda(Lmat, G)
     B, N, K = G.shape
     if tuple(Lmat.shape) != (B, N, N):
         raise L.WspcError(f"lp_blocks: L {tuple(Lmat.shape)} does not match G {tuple(G.shape)}")
@@ -174,8 +174,8 @@ def lp_blocks(xyz, rgb, G, alpha: float = 1.0, beta: float = 1.0, max_iter: int 
     """The test-time stage of S3DIS_Trainer.Test / ShapeNet_Trainer.Test for every block of a batch at once: symmetric
     Laplacian of (xyz, rgb) (Util/Tool.py:435-468) -> label propagation of the network's probabilities G.  The (B,N,N)
     Laplacians live in a cached workspace (67 MB per block at N = 4096)."""
+    xyz, rgb, G = xyz.to(torch.float32).contiguous(), rgb.to(torch.float32).contiguous(), G.to(torch.float32).contiguous()
     L.require_cuda(xyz, rgb, G)
-    xyz, rgb = xyz.to(torch.float32).contiguous(), rgb.to(torch.float32).contiguous()
     B, N, D1 = xyz.shape
     D2 = rgb.shape[-1]
     buf = L.workspace(B * N * N * 4 + B * N * 4, xyz.device, "lp_laplacian")
