@@ -314,6 +314,17 @@ int wspc_edgeconv2_bwd(const float* UV, long long ldu, const int32_t* idx, const
                        const float* c1, const float* c2, const float* c3, const float* MS, long long P, int k, int npts,
                        int C1, int C2, float* TS, float* dW2, void* workspace, size_t workspace_bytes,
                        wspc_stream_t stream);
+/* The same two calls with a routing export for parity tests (NULL = off): which rows attained each pooled maximum.
+ *   edgeconv2: routing_out (P*k, 2) uint32, bit c of word h = row attains the maximum of channel 32 h + c (k >= 8)
+ *   edge1:     routing_out (P, 64) uint64, bit j = row j of the point attains the maximum of that channel */
+int wspc_edgeconv2_bwd_ex(const float* UV, long long ldu, const int32_t* idx, const float* bias1, const float* sc1,
+                          const float* sh1, const float* W2, const float* bias2, const float* sc2, const float* sh2,
+                          const float* c1, const float* c2, const float* c3, const float* MS, long long P, int k, int npts,
+                          int C1, int C2, float* TS, float* dW2, uint32_t* routing_out, void* workspace,
+                          size_t workspace_bytes, wspc_stream_t stream);
+int wspc_edge1_bwd_ex(const float* UV, long long ldu, const int32_t* idx, const float* bias, const float* sc, const float* sh,
+                      const float* out, long long ldo, const float* dout, long long lddo, long long P, int k, int npts,
+                      int Cout, float* TS, uint64_t* routing_out, wspc_stream_t stream);
 int wspc_edge1_bwd(const float* UV, long long ldu, const int32_t* idx, const float* bias, const float* sc, const float* sh,
                    const float* out, long long ldo, const float* dout, long long lddo, long long P, int k, int npts,
                    int Cout, float* TS, wspc_stream_t stream);

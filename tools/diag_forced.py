@@ -16,10 +16,13 @@ params = od.init_params(od.S3DIS_LAYERS, seed=122)
 rng = np.random.default_rng(123)
 mask = np.floor(0.7 + rng.random((B, N, 256))).astype(np.float32)
 eng = S3DISEngine(params, B, N, device=cuda)
+from weaksuppointcloudseg_b200 import runtime as rt
+rt.ROUTING = {}
 eng.train_step(torch.from_numpy(X).to(cuda), torch.from_numpy(Y).to(cuda), torch.from_numpy(M).to(cuda), lr=1e-3,
                bn_decay=od.bn_decay(0, ns, 300000), dropout_mask=torch.from_numpy(mask).to(cuda), apply=False)
 torch.cuda.synchronize()
-route = routing.export_s3dis(eng)
+route = routing.export_s3dis(eng, rt.ROUTING)
+rt.ROUTING = None
 ov = {f"knn{i + 1}": eng.idx[i].cpu().long() for i in range(3)}
 rel = lambda a, b: float((a.double() - b.double()).abs().max() / b.double().abs().max())
 for forced in (False, True):

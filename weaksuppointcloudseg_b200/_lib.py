@@ -185,6 +185,10 @@ _EXTRA_DECLS.update({
                                    c_int, c_int, _P, _P, _P, c_size_t, _P]),
     "wspc_edge1_bwd": (c_int, [_P, c_longlong, _P, _P, _P, _P, _P, c_longlong, _P, c_longlong, c_longlong, c_int, c_int, c_int,
                                _P, _P]),
+    "wspc_edgeconv2_bwd_ex": (c_int, [_P, c_longlong, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_longlong, c_int, c_int,
+                                      c_int, c_int, _P, _P, _P, _P, c_size_t, _P]),
+    "wspc_edge1_bwd_ex": (c_int, [_P, c_longlong, _P, _P, _P, _P, _P, c_longlong, _P, c_longlong, c_longlong, c_int, c_int,
+                                  c_int, _P, _P, _P]),
     "wspc_edge_bwd_stats": (c_int, [_P, _P, c_longlong, _P, c_longlong, c_int, _P, _P]),
     "wspc_edge_bwd_finalize": (c_int, [_P, _P, _P, _P, c_longlong, _P, _P, _P, _P, c_longlong, c_int, c_int, _P, c_longlong, _P]),
     "wspc_zero_cols": (c_int, [_P, c_longlong, c_int, c_int, c_longlong, _P]),

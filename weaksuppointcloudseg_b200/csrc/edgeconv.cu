@@ -27,6 +27,7 @@
 #include "operand.cuh"
 #include "tc.cuh"
 #include <math_constants.h>
+#include <stdlib.h>
 
 namespace wspc {
 void count_launch(int n = 1);
@@ -134,7 +135,8 @@ edge_gather_stats_kernel(const float* __restrict__ UV, long long ldu, const int3
 __global__ void __launch_bounds__(256)
 edge1_bwd_kernel(const float* __restrict__ UV, long long ldu, const int32_t* __restrict__ idx, const float* __restrict__ bias,
                  const float* __restrict__ sc, const float* __restrict__ sh, const float* __restrict__ out, long long ldo,
-                 const float* __restrict__ dout, long long lddo, long long P, int k, int npts, float* __restrict__ TS) {
+                 const float* __restrict__ dout, long long lddo, long long P, int k, int npts, float* __restrict__ TS,
+                 unsigned long long* __restrict__ flags_out) {
   const int c4 = threadIdx.x & (C4 - 1), pl = threadIdx.x >> 4;
   const long long i = (long long)blockIdx.x * 16 + pl;
   if (i >= P) return;
@@ -167,6 +169,10 @@ edge1_bwd_kernel(const float* __restrict__ UV, long long ldu, const int32_t* __r
       if (fmaxf(fmaf(y.z, s4.z, h4.z), 0.f) == o.z) e2 |= bit;
       if (fmaxf(fmaf(y.w, s4.w, h4.w), 0.f) == o.w) e3 |= bit;
     }
+  }
+  if (flags_out) {   // routing export (tests): bit j of word (point, channel) = row j attains the pooled maximum
+    flags_out[i * CO + c4 * 4 + 0] = e0; flags_out[i * CO + c4 * 4 + 1] = e1;
+    flags_out[i * CO + c4 * 4 + 2] = e2; flags_out[i * CO + c4 * 4 + 3] = e3;
   }
   const int n0 = __popcll(e0), n1 = __popcll(e1), n2 = __popcll(e2), n3 = __popcll(e3);
   float4 share;   // tf.reduce_max splits the gradient equally among tied maxima [TF _MinOrMaxGrad]
@@ -725,6 +731,408 @@ edgeconv2_bwd_kernel(const float* __restrict__ UV, long long ldu, const int32_t*
   if (warp == 0) tc::dealloc(tmem_base, 128);
 }
 
+// =========================================================== warp-specialised backward (k >= 8) =======================
+// The serial kernels above run build -> MMA -> epilogue one after the other inside a CTA and rely on 2-3 co-resident CTAs for
+// overlap.  Here ONE persistent CTA per SM splits the backward tile by role:
+//   warps 0-7    epilogue   TMEM -> registers -> (arg-max routing, BN backward, operand image | ReLU mask, scatter, row sums);
+//                           thread 0 also issues tcgen05.mma / tcgen05.commit between its phases (a 17th warp would cost the
+//                           register file of 20: allocation is per four warps)
+//   warps 8-15   builders   the TMA engine gathers the tile's raw rows: one 1-D bulk copy (cp.async.bulk) per neighbour row,
+//                           issued by that row's thread, completing on an mbarrier; a1 = relu(bn1(u_i + v_j + b1)) is then
+//                           formed from shared memory into the bf16 hi / lo operand image
+// Buffers: two a1 operand images, two dy2 images, two y2 and two da1 accumulators (tile parity), one raw staging tile; the
+// forward weight image doubles as W2^T (read MN-major).  Roles talk through mbarriers (full / empty per buffer, parity = use
+// count); each group also has a named barrier.  The a1 expression and the MMA sequence of y2 are those of the serial kernels:
+// forward and backward obtain bit-identical y2.
+//
+// Measured (cfg-3, B200, profiles/r2_edgeconv_summary.md): the block is GATHER-bound, not tensor-bound.  One launch gathers
+// 10.5 M rows of 256 B; with everything else removed the bulk-copy gather alone takes 0.71 ms per launch (~18 cycles per
+// copy and SM), per-thread vector loads are bound by L1 wavefronts / miss latency at a similar level, and the tensor work
+// of the tile (1280 cycles of tcgen05.mma for the backward, 384 for the forward) is 10-15 % of the tile time in every
+// variant tried (serial 3.82 ms, per-thread gathers + 3 operand buffers 3.42 ms, this kernel 3.65 ms per backward launch;
+// forward: serial 1.12-1.21 ms, warp-specialised 1.4-2.4 ms -> the forward stays on the serial kernel).
+constexpr int WS_EPI_THREADS = 256, WS_BUILD_THREADS = 256;
+constexpr int WS_THREADS = WS_EPI_THREADS + WS_BUILD_THREADS;
+constexpr int WS_PTMAX = 16;                                            // points per tile: k >= 8
+constexpr int WSB_NA = 2;                                                // a1 operand images in flight
+constexpr int WS_VBYTES = TILE_M * 2 * CO * 2, WS_UBYTES = WS_PTMAX * 2 * CO * 2;   // raw v rows / u rows of one tile (256 B each)
+
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void bar_sync_epi() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// A K-major (rows x channels image), B MN-major: the forward weight image [cin group][cout row][8 cin] read with the
+// reduction over its rows is W2^T -- one image serves y2 = a1 W2 and da1 = dy2 W2^T
+__device__ __forceinline__ uint32_t idesc_a_k_b_mn(int N) { return tc::idesc_kmajor(N) | (1u << 16); }
+
+// Gather by the TMA engine: builder thread r < 128 owns tile row r and issues ONE 1-D bulk copy (cp.async.bulk, SASS UBLKCP)
+// of its neighbour's 256-byte v row into the raw staging tile; threads 128.. copy the u rows of the tile's points.  The copies
+// complete on an mbarrier (expect_tx = total bytes); nothing is held in registers and the L1 miss queue is not involved
+// (with per-thread loads the kernel was bound by gather latency / L1 wavefronts: ncu, 49 % long-scoreboard stalls).
+// Afterwards builder thread = (16-byte piece c16 of a row, rows rr, rr + 16, ..): a1 = relu(bn1(u_i + v_j + b1)) from shared
+// memory -> bf16 hi / lo operand image.
+__device__ __forceinline__ void ws_issue_gather(const float* __restrict__ UV, long long ldu, const TileGeom& g, int k, uint32_t kinv,
+                                                int nb, int bt, unsigned char* sV, unsigned char* sU, uint64_t* fullV) {
+  if (bt < TILE_M) {
+    if (bt < g.rows) bulk_g2s(sV + bt * (2 * CO * 2), UV + (long long)nb * ldu + CO, 2 * CO * 2, fullV);
+  } else if (bt - TILE_M < g.npt) {
+    bulk_g2s(sU + (bt - TILE_M) * (2 * CO * 2), UV + (g.pt0 + (bt - TILE_M)) * ldu, 2 * CO * 2, fullV);
+  } else if (bt == WS_BUILD_THREADS - 1) {
+    mbar_expect_tx(fullV, (uint32_t)(g.rows + g.npt) * (2 * CO * 2));
+  }
+}
+__device__ __forceinline__ void ws_build_rows(const unsigned char* sV, const unsigned char* sU, int rows, uint32_t kinv, float4 sc4,
+                                              float4 tg4, unsigned char* sAhi, unsigned char* sAlo, int rr, int c16) {
+  const int off = (c16 >> 1) * AGB + (c16 & 1) * 8;
+#pragma unroll
+  for (int s = 0; s < TILE_M / 16; ++s) {
+    const int r = rr + 16 * s;
+    uint2 hi = make_uint2(0, 0), lo = hi;
+    if (r < rows) {
+      const float4 u = *reinterpret_cast<const float4*>(sU + __umulhi((uint32_t)r, kinv) * (2 * CO * 2) + c16 * 16);
+      const float4 v = *reinterpret_cast<const float4*>(sV + r * (2 * CO * 2) + c16 * 16);
+      const float a0 = fmaxf(fmaf(v.x, sc4.x, fmaf(u.x, sc4.x, tg4.x)), 0.f);
+      const float a1 = fmaxf(fmaf(v.y, sc4.y, fmaf(u.y, sc4.y, tg4.y)), 0.f);
+      const float a2 = fmaxf(fmaf(v.z, sc4.z, fmaf(u.z, sc4.z, tg4.z)), 0.f);
+      const float a3 = fmaxf(fmaf(v.w, sc4.w, fmaf(u.w, sc4.w, tg4.w)), 0.f);
+      const __nv_bfloat162 h01 = __floats2bfloat162_rn(a0, a1), h23 = __floats2bfloat162_rn(a2, a3);
+      const uint32_t b01 = *reinterpret_cast<const uint32_t*>(&h01), b23 = *reinterpret_cast<const uint32_t*>(&h23);
+      const __nv_bfloat162 l01 = __floats2bfloat162_rn(a0 - __uint_as_float(b01 << 16), a1 - __uint_as_float(b01 & 0xffff0000u));
+      const __nv_bfloat162 l23 = __floats2bfloat162_rn(a2 - __uint_as_float(b23 << 16), a3 - __uint_as_float(b23 & 0xffff0000u));
+      hi = make_uint2(b01, b23);
+      lo = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+    }
+    *reinterpret_cast<uint2*>(sAhi + off + r * 16) = hi;
+    *reinterpret_cast<uint2*>(sAlo + off + r * 16) = lo;
+  }
+}
+__device__ __forceinline__ void bar_sync_build() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------ backward ---
+constexpr int WSB_OFF_A = 2 * 8 * WGB;
+constexpr int WSB_OFF_G = WSB_OFF_A + WSB_NA * IMG_BYTES;
+constexpr int WSB_OFF_CF = WSB_OFF_G + 2 * BWD_G_REGION;                // [8][64] floats: b2, sc2, sh2, c1, c2, c3, sc1, tg1
+constexpr int WSB_OFF_MS = WSB_OFF_CF + 8 * CO * 4;                     // [WSB_NA][WS_PTMAX][128] floats
+constexpr int WSB_OFF_CNT = WSB_OFF_MS + WSB_NA * WS_PTMAX * 2 * CO * 4; // [2][WS_PTMAX][64] ints
+constexpr int WSB_OFF_NB = WSB_OFF_CNT + 2 * WS_PTMAX * CO * 4;         // [WSB_NA][128] ints
+constexpr int WSB_OFF_V = WSB_OFF_NB + WSB_NA * TILE_M * 4;
+constexpr int WSB_OFF_U = WSB_OFF_V + WS_VBYTES;
+constexpr int WSB_OFF_BAR = WSB_OFF_U + WS_UBYTES;
+constexpr int WSB_SMEM = WSB_OFF_BAR + 128;
+static_assert(WSB_SMEM <= 227 * 1024, "edgeconv2_bwd_ws_kernel: shared memory budget");
+static_assert(WSB_NA == 2, "the MMA issue order of edgeconv2_bwd_ws_kernel assumes two operand images");
+
+// da1 (128 x 64) = dy2 (K-major image) * W2^T (the forward weight image read MN-major): hi*hi + lo*hi + hi*lo
+__device__ __forceinline__ void issue_da_gemm(uint32_t d_tmem, uint32_t g_hi, uint32_t g_lo, uint32_t w_hi, uint32_t w_lo,
+                                              uint32_t idesc_mix) {
+  uint32_t accum = 0;
+#pragma unroll 1
+  for (int pass = 0; pass < 3; ++pass) {
+    const uint32_t ab = (pass == 1) ? g_lo : g_hi;
+    const uint32_t bb = (pass == 2) ? w_lo : w_hi;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {      // 16 output channels of layer 2 per step: two channel groups of dy2, 16 rows of the W image
+      const uint64_t ad = tc::smem_desc(ab + (uint32_t)(2 * kk) * AGB, AGB, 128);
+      const uint64_t bd = tc::smem_desc(bb + (uint32_t)kk * 256, 128, WGB);
+      tc::mma_bf16(d_tmem, ad, bd, idesc_mix, accum);
+      accum = 1;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(WS_THREADS, 1)
+edgeconv2_bwd_ws_kernel(const float* __restrict__ UV, long long ldu, const int32_t* __restrict__ idx,
+                        const float* __restrict__ b1, const float* __restrict__ sc1, const float* __restrict__ sh1,
+                        const float* __restrict__ W2, const float* __restrict__ b2, const float* __restrict__ sc2,
+                        const float* __restrict__ sh2, const float* __restrict__ c1, const float* __restrict__ c2,
+                        const float* __restrict__ c3, const float* __restrict__ MS, long long P, int k, int npts, int PT,
+                        int num_tiles, float* __restrict__ TS, float* __restrict__ partial, uint32_t* __restrict__ flags_out) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* sWhi = smem;
+  unsigned char* sWlo = sWhi + 8 * WGB;
+  float* s_cf = reinterpret_cast<float*>(smem + WSB_OFF_CF);
+  float* s_ms = reinterpret_cast<float*>(smem + WSB_OFF_MS);
+  int* s_cnt = reinterpret_cast<int*>(smem + WSB_OFF_CNT);
+  int* s_nb = reinterpret_cast<int*>(smem + WSB_OFF_NB);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WSB_OFF_BAR);
+  uint64_t *fullA = bars, *emptyA = bars + WSB_NA, *fullG = bars + 2 * WSB_NA, *barY = fullG + 2, *barD = barY + 2, *fullV = barD + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (warp == 0) tc::alloc(tmem_slot, 512);
+  if (tid == 32) {
+    for (int i = 0; i < WSB_NA; ++i) {
+      mbar_init(fullA + i, WS_BUILD_THREADS);
+      mbar_init(emptyA + i, WS_EPI_THREADS);
+    }
+    mbar_init(fullV, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(fullG + i, WS_EPI_THREADS);
+      mbar_init(barY + i, 1);
+      mbar_init(barD + i, 1);
+    }
+    mbar_fence_init();
+  }
+  for (int e = tid; e < CO * 8; e += WS_THREADS) {
+    const int n = e & (CO - 1), g = e >> 6;
+    float w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = W2[(g * 8 + i) * CO + n];
+    uint4 hi, lo;
+    tc::split8(w, hi, lo);
+    *reinterpret_cast<uint4*>(sWhi + g * WGB + n * 16) = hi;
+    *reinterpret_cast<uint4*>(sWlo + g * WGB + n * 16) = lo;
+  }
+  if (tid < CO) {
+    s_cf[0 * CO + tid] = b2 ? b2[tid] : 0.f;
+    s_cf[1 * CO + tid] = sc2[tid];
+    s_cf[2 * CO + tid] = sh2[tid];
+    s_cf[3 * CO + tid] = c1[tid];
+    s_cf[4 * CO + tid] = c2[tid];
+    s_cf[5 * CO + tid] = c3[tid];
+    s_cf[6 * CO + tid] = sc1[tid];
+    s_cf[7 * CO + tid] = fmaf(b1 ? b1[tid] : 0.f, sc1[tid], sh1[tid]);
+  }
+  for (int i = tid; i < 2 * WS_PTMAX * CO; i += WS_THREADS) s_cnt[i] = 0;
+  fence_proxy_async_smem();
+  tc::fence_before();
+  __syncthreads();
+  tc::fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // tensor memory: y2 of tile parity 0/1 at columns 0/64, da1 at 128/192, dW2 (persistent over the CTA's tiles) at 256
+  const uint32_t acc_w = tmem_base + 256;
+  const uint32_t idesc = tc::idesc_kmajor(CO), idesc_mn = tc::idesc_mnmajor(CO), idesc_mix = idesc_a_k_b_mn(CO);
+  const uint32_t kinv = (uint32_t)((1ull << 32) / (uint32_t)k + 1);
+  const int n_my = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp < 8) {
+    const int lq = warp & 3, ch = warp >> 2;
+    const int trow = lq * 32 + lane;
+    const int c4 = lane & 15, hh = lane >> 4;
+    const uint32_t lane_addr = (uint32_t)(lq * 32) << 16;
+    const int pl = (int)__umulhi((uint32_t)trow, kinv);           // tile-local point of this thread's row
+
+    // ---- y2 -> arg-max flags -> tie split -> dy2 = c1 G + c2 + c3 y2 -> operand image G[t & 1]
+    auto epi1 = [&](int t) {
+      const int s = t % WSB_NA, sg = t & 1;
+      const TileGeom g = tile_geom((int)blockIdx.x + t * (int)gridDim.x, PT, k, P);
+      unsigned char* sGhi = smem + WSB_OFF_G + sg * BWD_G_REGION;
+      unsigned char* sGlo = sGhi + 8 * AGB;
+      mbar_wait(fullA + s, (uint32_t)(t / WSB_NA) & 1u);          // the builders' MS rows of this tile are visible
+      mbar_wait(barY + sg, (uint32_t)(t >> 1) & 1u);
+      tc::fence_after();
+      float y[32];
+      tc::ld32(tmem_base + (uint32_t)(sg * CO) + lane_addr + (uint32_t)(ch * 32), y);
+      const bool valid = trow < g.rows;
+      const float* ms = s_ms + (s * WS_PTMAX + (valid ? pl : 0)) * (2 * CO) + ch * 32;
+      int* cnt = s_cnt + (sg * WS_PTMAX + (valid ? pl : 0)) * CO + ch * 32;
+      uint32_t mine = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 o = ld4(ms + 4 * q);
+        const float4 bb = ld4(s_cf + 0 * CO + ch * 32 + 4 * q), ss = ld4(s_cf + 1 * CO + ch * 32 + 4 * q),
+                     hs = ld4(s_cf + 2 * CO + ch * 32 + 4 * q);
+        y[4 * q + 0] += bb.x; y[4 * q + 1] += bb.y; y[4 * q + 2] += bb.z; y[4 * q + 3] += bb.w;
+        if (fmaxf(fmaf(y[4 * q + 0], ss.x, hs.x), 0.f) == o.x) mine |= 1u << (4 * q + 0);
+        if (fmaxf(fmaf(y[4 * q + 1], ss.y, hs.y), 0.f) == o.y) mine |= 1u << (4 * q + 1);
+        if (fmaxf(fmaf(y[4 * q + 2], ss.z, hs.z), 0.f) == o.z) mine |= 1u << (4 * q + 2);
+        if (fmaxf(fmaf(y[4 * q + 3], ss.w, hs.w), 0.f) == o.w) mine |= 1u << (4 * q + 3);
+      }
+      if (!valid) mine = 0;
+      if (flags_out && valid) flags_out[((size_t)g.pt0 * k + trow) * 2 + ch] = mine;
+      for (uint32_t m = mine; m; m &= m - 1) atomicAdd(cnt + (__ffs((int)m) - 1), 1);   // rows attaining the maximum, per channel
+      bar_sync_epi();
+      // every epilogue thread has left the previous tile's epi1: its counters may be cleared for the tile after this one
+      // (t == 0: the other buffer is still zero from the prologue, and tile 1 may already be counting into it)
+      if (t > 0) reinterpret_cast<int4*>(s_cnt + (sg ^ 1) * WS_PTMAX * CO)[tid] = make_int4(0, 0, 0, 0);
+      uint32_t dup = 0;
+      for (uint32_t m = mine; m; m &= m - 1) {
+        const int c = __ffs((int)m) - 1;
+        if (cnt[c] > 1) dup |= 1u << c;
+      }
+#pragma unroll
+      for (int gg = 0; gg < 4; ++gg) {
+        float dy[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dy[e] = 0.f;
+        if (valid) {
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const int c0 = gg * 8 + h2 * 4;
+            const float4 d = ld4(ms + CO + c0);
+            const float4 k1 = ld4(s_cf + 3 * CO + ch * 32 + c0), k2 = ld4(s_cf + 4 * CO + ch * 32 + c0),
+                         k3 = ld4(s_cf + 5 * CO + ch * 32 + c0);
+            const float dd[4] = {d.x, d.y, d.z, d.w}, kk1[4] = {k1.x, k1.y, k1.z, k1.w}, kk2[4] = {k2.x, k2.y, k2.z, k2.w},
+                        kk3[4] = {k3.x, k3.y, k3.z, k3.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int c = c0 + e;
+              const float gv = ((mine >> c) & 1u) ? dd[e] : 0.f;
+              dy[h2 * 4 + e] = fmaf(kk1[e], gv, fmaf(kk3[e], y[c], kk2[e]));
+            }
+          }
+          if ((dup >> (gg * 8)) & 0xffu) {          // tf.reduce_max: equal split among tied maxima (rare: duplicated neighbours)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int c = gg * 8 + e;
+              if ((dup >> c) & 1u)
+                dy[e] = fmaf(s_cf[3 * CO + ch * 32 + c], ms[CO + c] / (float)cnt[c],
+                             fmaf(s_cf[5 * CO + ch * 32 + c], y[c], s_cf[4 * CO + ch * 32 + c]));
+            }
+          }
+        }
+        uint4 hi, lo;
+        tc::split8(dy, hi, lo);
+        *reinterpret_cast<uint4*>(sGhi + (ch * 4 + gg) * AGB + trow * 16) = hi;
+        *reinterpret_cast<uint4*>(sGlo + (ch * 4 + gg) * AGB + trow * 16) = lo;
+      }
+      fence_proxy_async_smem();
+      tc::fence_before();
+      mbar_arrive(fullG + sg);
+    };
+
+    // ---- da1 -> ReLU mask of a1 -> neighbour scatter (TG) and per-point row sums (SG)
+    auto epi2 = [&](int t) {
+      const int s = t % WSB_NA, sg = t & 1;
+      const TileGeom g = tile_geom((int)blockIdx.x + t * (int)gridDim.x, PT, k, P);
+      const unsigned char* sAhi = smem + WSB_OFF_A + s * IMG_BYTES;
+      float* stage = reinterpret_cast<float*>(smem + WSB_OFF_G + sg * BWD_G_REGION);   // the dy2 image is dead: its MMAs are done
+      mbar_wait(barD + sg, (uint32_t)(t >> 1) & 1u);
+      tc::fence_after();
+      float da[32];
+      tc::ld32(tmem_base + (uint32_t)(2 * CO + sg * CO) + lane_addr + (uint32_t)(ch * 32), da);
+#pragma unroll
+      for (int gg = 0; gg < 4; ++gg) {
+        const uint4 h = *reinterpret_cast<const uint4*>(sAhi + (ch * 4 + gg) * AGB + trow * 16);
+        const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {      // a1 > 0 <=> its bf16 hi part is non-zero
+          if ((hw[e] & 0x0000ffffu) == 0u) da[gg * 8 + 2 * e] = 0.f;
+          if ((hw[e] & 0xffff0000u) == 0u) da[gg * 8 + 2 * e + 1] = 0.f;
+        }
+      }
+      float* srow = stage + trow * STAGE_LD + ch * 32;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) st4(srow + i, make_float4(da[i], da[i + 1], da[i + 2], da[i + 3]));
+      bar_sync_epi();
+      // neighbour scatter from the staged tile: sixteen lanes add one contiguous 256-byte row (lane = row would spread every
+      // reduction instruction over 32 cache lines)
+#pragma unroll
+      for (int pass = 0; pass < TILE_M / 16; ++pass) {
+        const int row = pass * 16 + (tid >> 4);
+        if (row < g.rows) {
+          const float4 v4 = ld4(stage + row * STAGE_LD + c4 * 4);
+          tc::red_add_v4(TS + (long long)s_nb[s * TILE_M + row] * (2 * CO) + CO + c4 * 4, v4.x, v4.y, v4.z, v4.w);
+        }
+      }
+      tc::fence_before();
+      mbar_arrive(emptyA + s);                        // the operand image, its neighbour list and MS rows may be overwritten
+      for (int p = warp; p < g.npt; p += 8) {
+        float4 sm = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* base = stage + (p * k) * STAGE_LD + c4 * 4;
+        for (int j = hh; j < k; j += 2) sm = f4add(sm, ld4(base + j * STAGE_LD));
+        sm = f4add(sm, f4shfl16(sm));
+        if (hh == 0) st4(TS + (g.pt0 + p) * (2 * CO) + c4 * 4, sm);
+      }
+    };
+
+    // thread 0 between its epilogue phases: y2 of the next tile first (keeps the tensor pipe ahead of epi1), then this tile's
+    // gradients.  Accumulator / image reuse is ordered by program order plus the barriers the waits below imply.
+    uint32_t accum_w = 0;
+    auto mma1 = [&](int t) {
+      const int s = t % WSB_NA, sg = t & 1;
+      mbar_wait(fullA + s, (uint32_t)(t / WSB_NA) & 1u);
+      tc::fence_after();
+      const uint32_t a_hi = smem_u32(smem + WSB_OFF_A + s * IMG_BYTES);
+      issue_rows_gemm(tmem_base + (uint32_t)(sg * CO), a_hi, a_hi + 8 * AGB, smem_u32(sWhi), smem_u32(sWlo), idesc);
+      tc::commit(barY + sg);
+    };
+    auto mma2 = [&](int t) {
+      const int s = t % WSB_NA, sg = t & 1;
+      mbar_wait(fullG + sg, (uint32_t)(t >> 1) & 1u);
+      tc::fence_after();
+      const uint32_t ah = smem_u32(smem + WSB_OFF_A + s * IMG_BYTES);
+      const uint32_t gh = smem_u32(smem + WSB_OFF_G + sg * BWD_G_REGION), gl = gh + 8 * AGB;
+      // dW2 += a1^T dy2: both images read MN-major (reduction over the 128 rows); M = 128 spans [a1_hi ; a1_lo]
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {
+        const uint32_t gb = pass ? gl : gh;
+#pragma unroll
+        for (int j = 0; j < TILE_M / 16; ++j) {
+          const uint64_t ad = tc::smem_desc(ah + (uint32_t)j * 256, 128, AGB);
+          const uint64_t gd = tc::smem_desc(gb + (uint32_t)j * 256, 128, AGB);
+          tc::mma_bf16(acc_w, ad, gd, idesc_mn, accum_w);
+          accum_w = 1;
+        }
+      }
+      issue_da_gemm(tmem_base + (uint32_t)(2 * CO + sg * CO), gh, gl, smem_u32(sWhi), smem_u32(sWlo), idesc_mix);
+      tc::commit(barD + sg);
+    };
+    // Issue order (tensor queue): y2(0), y2(1), grad(0), | grad(t+1), y2(t+2) per iteration.  With two operand images y2(t+2) can
+    // only be issued once tile t has released its image (end of epi2(t)); issuing it earlier would wait for this very thread.
+    if (n_my > 0) {
+      if (tid == 0) {
+        mma1(0);
+        if (n_my > 1) mma1(1);
+      }
+      epi1(0);
+      if (tid == 0) mma2(0);
+    }
+    for (int t = 0; t < n_my; ++t) {
+      if (t + 1 < n_my) {
+        epi1(t + 1);                                  // runs while the tensor pipe works on tile t's gradients
+        if (tid == 0) mma2(t + 1);
+      }
+      epi2(t);
+      if (tid == 0 && t + 2 < n_my) mma1(t + 2);
+    }
+    // dW2 partial of this CTA: slab 2*cta = a1_hi^T dy2, slab 2*cta + 1 = a1_lo^T dy2 (summed in fp64 by ec_slab_reduce)
+    {
+      float v[32];
+      tc::ld32(acc_w + lane_addr + (uint32_t)(ch * 32), v);
+      const int half = trow >> 6, cin = trow & 63;
+      float* dst = partial + (((size_t)(2 * blockIdx.x + half) * CO + cin) * CO) + ch * 32;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) st4(dst + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+    }
+  } else {
+    const int bt = tid - WS_EPI_THREADS, c16 = bt & 15, rr = bt >> 4;
+    const float4 sc4 = ld4(s_cf + 6 * CO + c16 * 4), tg4 = ld4(s_cf + 7 * CO + c16 * 4);
+    unsigned char* sV = smem + WSB_OFF_V;
+    unsigned char* sU = smem + WSB_OFF_U;
+    int tile = blockIdx.x;
+    TileGeom g = tile_geom(tile, PT, k, P);
+    int nb = (bt < TILE_M) ? fetch_neighbour(idx, tile, num_tiles, PT, k, kinv, npts, P, bt) : 0;
+    if (n_my > 0) ws_issue_gather(UV, ldu, g, k, kinv, nb, bt, sV, sU, fullV);
+    int nb_next = (bt < TILE_M) ? fetch_neighbour(idx, tile + gridDim.x, num_tiles, PT, k, kinv, npts, P, bt) : 0;
+    for (int t = 0; t < n_my; ++t) {
+      const int s = t % WSB_NA, use = t / WSB_NA;
+      if (use >= 1) mbar_wait(emptyA + s, (uint32_t)(use - 1) & 1u);
+      if (bt < TILE_M) s_nb[s * TILE_M + bt] = nb;
+      for (int e = bt; e < g.npt * 32; e += WS_BUILD_THREADS)     // MS rows of the tile's points: npt * 32 16-byte pieces
+        cp_async16(s_ms + (size_t)s * WS_PTMAX * 2 * CO + e * 4, MS + g.pt0 * (2 * CO) + e * 4);
+      mbar_wait(fullV, (uint32_t)t & 1u);            // the tile's raw rows have landed
+      unsigned char* sAhi = smem + WSB_OFF_A + s * IMG_BYTES;
+      ws_build_rows(sV, sU, g.rows, kinv, sc4, tg4, sAhi, sAhi + 8 * AGB, rr, c16);
+      cp_async_wait_all();
+      fence_proxy_async_smem();
+      mbar_arrive(fullA + s);
+      bar_sync_build();                              // every builder has consumed the staging tile: refill it
+      tile += gridDim.x;
+      nb = nb_next;
+      if (t + 1 < n_my) {
+        g = tile_geom(tile, PT, k, P);
+        ws_issue_gather(UV, ldu, g, k, kinv, nb, bt, sV, sU, fullV);
+      }
+      nb_next = (bt < TILE_M) ? fetch_neighbour(idx, tile + gridDim.x, num_tiles, PT, k, kinv, npts, P, bt) : 0;
+    }
+  }
+  tc::fence_before();
+  __syncthreads();
+  if (warp == 0) tc::dealloc(tmem_base, 512);
+}
+
 // p[row, col0 : col0 + 4*n4] = 0 for a (rows, ld) matrix (the scatter halves of SS / TS)
 __global__ void zero_cols_kernel(float* __restrict__ p, long long ld, int col0, int n4, long long rows) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -746,6 +1154,16 @@ int ec_tiles(long long P, int k, int* PT_out) {
   const int PT = TILE_M / k;
   *PT_out = PT;
   return (int)((P + PT - 1) / PT);
+}
+
+// k >= 8 (<= 16 points per 128-row tile): persistent warp-specialised kernels; smaller k or WSPC_EDGECONV_KERNEL=serial: the
+// serial-phase kernels (kept as the second device path for A/B runs)
+bool ec_use_ws(int k) {
+  static const bool serial = [] {
+    const char* e = getenv("WSPC_EDGECONV_KERNEL");
+    return e && strcmp(e, "serial") == 0;
+  }();
+  return !serial && k >= 8;
 }
 
 bool ec_shape_ok(long long P, int k, int npts, const char* who) {
@@ -783,6 +1201,13 @@ extern "C" int wspc_edge_gather_stats(const float* UV, long long ldu, const int3
 extern "C" int wspc_edge1_bwd(const float* UV, long long ldu, const int32_t* idx, const float* bias, const float* sc,
                               const float* sh, const float* out, long long ldo, const float* dout, long long lddo, long long P,
                               int k, int npts, int Cout, float* TS, wspc_stream_t stream) {
+  return wspc_edge1_bwd_ex(UV, ldu, idx, bias, sc, sh, out, ldo, dout, lddo, P, k, npts, Cout, TS, nullptr, stream);
+}
+
+extern "C" int wspc_edge1_bwd_ex(const float* UV, long long ldu, const int32_t* idx, const float* bias, const float* sc,
+                                 const float* sh, const float* out, long long ldo, const float* dout, long long lddo,
+                                 long long P, int k, int npts, int Cout, float* TS, uint64_t* routing_out,
+                                 wspc_stream_t stream) {
   if (int rc = check_arch()) return rc;
   WSPC_REQUIRE(UV && idx && sc && sh && out && dout && TS, "edge1_bwd: null pointer");
   WSPC_REQUIRE(Cout == CO && ldu >= 2 * CO && (ldu & 3) == 0 && (ldo & 3) == 0 && (lddo & 3) == 0,
@@ -792,7 +1217,7 @@ extern "C" int wspc_edge1_bwd(const float* UV, long long ldu, const int32_t* idx
   WSPC_REQUIRE(aligned16(UV) && (!bias || aligned16(bias)) && aligned16(sc) && aligned16(sh) && aligned16(out) &&
                aligned16(dout) && aligned16(TS), "edge1_bwd: pointers must be 16-byte aligned");
   edge1_bwd_kernel<<<(unsigned)((P + 15) / 16), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      UV, ldu, idx, bias, sc, sh, out, ldo, dout, lddo, P, k, npts, TS);
+      UV, ldu, idx, bias, sc, sh, out, ldo, dout, lddo, P, k, npts, TS, reinterpret_cast<unsigned long long*>(routing_out));
   count_launch();
   WSPC_LAUNCH_CHECK("edge1_bwd_kernel");
   return WSPC_OK;
@@ -865,8 +1290,8 @@ extern "C" int wspc_edgeconv2_fwd(const float* UV, long long ldu, const int32_t*
   WSPC_REQUIRE(aligned16(UV) && aligned16(MM) && (!bias2 || aligned16(bias2)), "edgeconv2_fwd: pointers must be 16-byte aligned");
   int PT;
   const int tiles = ec_tiles(P, k, &PT);
-  const int grid = tiles < 3 * kNumSM ? tiles : 3 * kNumSM;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = tiles < 3 * kNumSM ? tiles : 3 * kNumSM;
   if (stats2) {
     auto kern = edgeconv2_fwd_kernel<true>;
     WSPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
@@ -888,6 +1313,15 @@ extern "C" int wspc_edgeconv2_bwd(const float* UV, long long ldu, const int32_t*
                                   const float* c1, const float* c2, const float* c3, const float* MS, long long P, int k, int npts,
                                   int C1, int C2, float* TS, float* dW2, void* workspace, size_t workspace_bytes,
                                   wspc_stream_t stream) {
+  return wspc_edgeconv2_bwd_ex(UV, ldu, idx, bias1, sc1, sh1, W2, bias2, sc2, sh2, c1, c2, c3, MS, P, k, npts, C1, C2, TS, dW2,
+                               nullptr, workspace, workspace_bytes, stream);
+}
+
+extern "C" int wspc_edgeconv2_bwd_ex(const float* UV, long long ldu, const int32_t* idx, const float* bias1, const float* sc1,
+                                     const float* sh1, const float* W2, const float* bias2, const float* sc2, const float* sh2,
+                                     const float* c1, const float* c2, const float* c3, const float* MS, long long P, int k,
+                                     int npts, int C1, int C2, float* TS, float* dW2, uint32_t* routing_out, void* workspace,
+                                     size_t workspace_bytes, wspc_stream_t stream) {
   if (int rc = check_arch()) return rc;
   WSPC_REQUIRE(UV && idx && sc1 && sh1 && W2 && sc2 && sh2 && c1 && c2 && c3 && MS && TS && dW2 && workspace,
                "edgeconv2_bwd: null pointer");
@@ -903,9 +1337,23 @@ extern "C" int wspc_edgeconv2_bwd(const float* UV, long long ldu, const int32_t*
   }
   int PT;
   const int tiles = ec_tiles(P, k, &PT);
-  const int grid = tiles < 2 * kNumSM ? tiles : 2 * kNumSM;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   float* partial = static_cast<float*>(workspace);
+  if (ec_use_ws(k)) {
+    const int wgrid = tiles < kNumSM ? tiles : kNumSM;
+    auto kern = edgeconv2_bwd_ws_kernel;
+    WSPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WSB_SMEM));
+    kern<<<wgrid, WS_THREADS, WSB_SMEM, st>>>(UV, ldu, idx, bias1, sc1, sh1, W2, bias2, sc2, sh2, c1, c2, c3, MS, P, k, npts, PT,
+                                              tiles, TS, partial, routing_out);
+    count_launch();
+    WSPC_LAUNCH_CHECK("edgeconv2_bwd_ws_kernel");
+    ec_slab_reduce_kernel<<<(CO * CO + 255) / 256, 256, 0, st>>>(partial, 2 * wgrid, dW2);
+    count_launch();
+    WSPC_LAUNCH_CHECK("ec_slab_reduce_kernel");
+    return WSPC_OK;
+  }
+  WSPC_REQUIRE(routing_out == nullptr, "edgeconv2_bwd: the routing export needs the warp-specialised kernel (k >= 8)");
+  const int grid = tiles < 2 * kNumSM ? tiles : 2 * kNumSM;
   auto kern = edgeconv2_bwd_kernel;
   WSPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
   kern<<<grid, EC_THREADS, BWD_SMEM, st>>>(UV, ldu, idx, bias1, sc1, sh1, W2, bias2, sc2, sh2, c1, c2, c3, MS, P, k, npts, PT, tiles,

@@ -424,6 +424,8 @@ class EdgeFused:
 
 
 PROF = None      # optional list of (tag, start_event, end_event): bench.py times the tcgen05 EdgeConv kernels inside the step
+ROUTING = None   # optional dict (parity tests): the backward kernels export which rows attained each max over k, keyed by the
+                 # scope of the block's last conv layer ((P*k, 2) int32 bit words for two-conv blocks, (P, 64) int64 for one-conv)
 
 
 class _timed:
@@ -496,8 +498,11 @@ def edgeblock_backward(ef: EdgeFused, st: EdgeBlockState, l1: Layer, l2, x, ld, 
     out_p, dout_p = ctypes.c_void_p(out_addr), ctypes.c_void_p(dout_addr)
     _zero_cols(ef.TS, 64, 64)
     if l2 is None:
-        L.check(lib.wspc_edge1_bwd(L.ptr(st.UV), 128, L.ptr(idx), L.ptr(l1.b), L.ptr(l1.sc), L.ptr(l1.sh), out_p, out_ld, dout_p,
-                                   dout_ld, P, k, npts, 64, L.ptr(ef.TS), L.stream()))
+        rout = None
+        if ROUTING is not None:
+            rout = ROUTING[l1.scope] = torch.zeros((P, 64), dtype=torch.int64, device=ef.device)
+        L.check(lib.wspc_edge1_bwd_ex(L.ptr(st.UV), 128, L.ptr(idx), L.ptr(l1.b), L.ptr(l1.sc), L.ptr(l1.sh), out_p, out_ld, dout_p,
+                                      dout_ld, P, k, npts, 64, L.ptr(ef.TS), L.ptr(rout), L.stream()))
     else:
         zero_(l2.bstats)
         L.check(lib.wspc_maxk_extrema_bwd_prep(L.ptr(st.MM), L.ptr(l2.sc), out_p, out_ld, dout_p, dout_ld, P, 64, L.ptr(ef.MS),
@@ -507,11 +512,14 @@ def edgeblock_backward(ef: EdgeFused, st: EdgeBlockState, l1: Layer, l2, x, ld, 
                                       L.ptr(l2.db), L.stream()))
         nbytes = lib.wspc_edgeconv2_bwd_workspace_bytes()
         ws = L.workspace(nbytes, ef.device, "edgeconv_bwd")
+        rout = None
+        if ROUTING is not None:
+            rout = ROUTING[l2.scope] = torch.zeros((P * k, 2), dtype=torch.int32, device=ef.device)
         with _timed("edgeconv2_bwd"):
-            L.check(lib.wspc_edgeconv2_bwd(L.ptr(st.UV), 128, L.ptr(idx), L.ptr(l1.b), L.ptr(l1.sc), L.ptr(l1.sh), L.ptr(l2.W),
-                                           L.ptr(l2.b), L.ptr(l2.sc), L.ptr(l2.sh), L.ptr(l2.c1), L.ptr(l2.c2), L.ptr(l2.c3),
-                                           L.ptr(ef.MS), P, k, npts, 64, 64, L.ptr(ef.TS), L.ptr(l2.dW), L.ptr(ws), ws.numel(),
-                                           L.stream()))
+            L.check(lib.wspc_edgeconv2_bwd_ex(L.ptr(st.UV), 128, L.ptr(idx), L.ptr(l1.b), L.ptr(l1.sc), L.ptr(l1.sh), L.ptr(l2.W),
+                                              L.ptr(l2.b), L.ptr(l2.sc), L.ptr(l2.sh), L.ptr(l2.c1), L.ptr(l2.c2), L.ptr(l2.c3),
+                                              L.ptr(ef.MS), P, k, npts, 64, 64, L.ptr(ef.TS), L.ptr(l2.dW), L.ptr(rout), L.ptr(ws),
+                                              ws.numel(), L.stream()))
     zero_(l1.bstats)
     L.check(lib.wspc_edge_bwd_stats(L.ptr(ef.TS), L.ptr(st.UV), 128, L.ptr(l1.b), P, 64, L.ptr(l1.bstats), L.stream()))
     bn_bwd_coeffs(l1, R)
