@@ -44,6 +44,14 @@ CASES = [
     (1, 20, 3, 20, 0, "uniform"),       # N < tile, k == N
     (4, 2048, 3, 20, 0, "uniform"),
     (1, 4096, 64, 20, 0, "relu"),       # one full-size S3DIS cloud
+    # 24 < k <= 64 on the tensor-core kernel: bisection threshold, three candidates per lane, rank-ordered output
+    (2, 1024, 3, 25, 0, "uniform"),
+    (2, 1024, 64, 32, 0, "relu"),
+    (2, 777, 6, 33, 1, "uniform"),      # ragged N, clamped flavour
+    (2, 1024, 64, 40, 0, "relu"),       # cfg-4's k
+    (1, 2048, 3, 64, 0, "uniform"),     # the largest k of the kernel
+    (2, 512, 3, 40, 0, "grid"),         # massive exact ties: rows overflow the candidate slots -> k > 32 fallback kernel
+    (1, 96, 3, 64, 0, "uniform"),       # N < tile
 ]
 
 

@@ -1,4 +1,4 @@
-// Tensor-core kNN (D <= 64, k <= 24): tcgen05 distances, two-pass threshold selection, exact fp32 re-scoring.
+// Tensor-core kNN (D <= 64, k <= 64): tcgen05 distances, two-pass threshold selection, exact fp32 re-scoring.
 //
 // The canonical (bit-exact) distance arithmetic is a sequential fp32 FMA chain per pair, which
 // caps the CUDA-core kernel in knn.cu at the FP32 pipe, and any per-element sorted-list selection costs tens of
@@ -44,7 +44,9 @@ constexpr int RB = 256;                    // query rows per CTA (two M blocks)
 constexpr int GROUP_BYTES = QT * 16 + 16;  // one 8-channel group of a tile image (padded, see gemm_tc.cu)
 constexpr int SEL_WARPS = 16;              // selection warps: (TMEM lane quadrant, M block, column half)
 constexpr int KTC_THREADS = (SEL_WARPS + 1) * 32;
-constexpr int MAXC = 32;                   // candidate slots per row (one per lane in the refine phase)
+constexpr int MAXC = 32;                   // candidate slots per row for k <= 24 (one per lane in the refine phase)
+constexpr int MAXC_BIG = 96;               // ... for 24 < k <= 64 (three per lane, ranked instead of sorted)
+constexpr int KSORT = 24;                  // largest k of the register-sort threshold / one-candidate-per-lane refine path
 constexpr int MAX_NST = 6;                 // candidate-tile ring depth (chosen per D from the smem budget)
 constexpr int NAUG = 3;                    // extra hi channels: 3-way bf16 split of -sq/2
 constexpr int SMEM_BUDGET = 227 * 1024;
@@ -91,6 +93,13 @@ __device__ __forceinline__ float exact_dist(int flavour, float sqi, float sqj, f
   return d > 0.f ? d : 0.f;
 }
 
+__host__ __device__ inline int tc_maxc(int k) { return k <= KSORT ? MAXC : MAXC_BIG; }
+__host__ __device__ inline size_t tc_scratch_bytes(int k) {
+  const size_t kk = (size_t)(k < 1 ? 1 : k);
+  if (k <= KSORT) return kk * 2 * RB * 4 > (size_t)RB * MAXC * 2 ? kk * 2 * RB * 4 : (size_t)RB * MAXC * 2;
+  return (size_t)RB * MAXC_BIG * 2 + (size_t)SEL_WARPS * MAXC_BIG * 8;
+}
+
 struct TcPlan {
   int Dp, Dl, Npad, ntile, ghi, glo, nst;
   uint32_t tile_bytes;
@@ -107,9 +116,9 @@ TcPlan make_tc_plan(int B, int N, int D, int k) {
   p.glo = p.Dl / 8;
   p.tile_bytes = (uint32_t)(p.ghi + p.glo) * GROUP_BYTES;
   p.img_bytes = align_up((size_t)B * p.ntile * p.tile_bytes, 256);
-  // selection scratch: top-k exchange [k][2][RB] fp32, later aliased by the candidate lists [RB][MAXC] u16
-  const size_t kk = (size_t)(k < 1 ? 1 : k);
-  const size_t scratch = kk * 2 * RB * 4 > (size_t)RB * MAXC * 2 ? kk * 2 * RB * 4 : (size_t)RB * MAXC * 2;
+  // selection scratch.  k <= 24: top-k exchange [k][2][RB] fp32, later aliased by the candidate lists [RB][MAXC] u16.
+  // k > 24: count exchange [2][2][RB] int (bisection), aliased by the lists [RB][MAXC_BIG] u16, + per-warp refine scratch
+  const size_t scratch = tc_scratch_bytes(k);
   const size_t fixed = 2 * (size_t)p.tile_bytes + scratch + RB * 4 /*cnt*/ + RB * 4 /*thr*/ + 256 /*barriers*/;
   long nst = ((long)SMEM_BUDGET - (long)fixed) / (long)p.tile_bytes;
   if (nst > MAX_NST) nst = MAX_NST;
@@ -265,6 +274,7 @@ __device__ __forceinline__ void sort64_desc(float (&a)[64]) {
 }
 
 // ------------------------------------------------------------------ main ---
+template <bool BIGK>
 __global__ void __launch_bounds__(KTC_THREADS, 1)
 knn_tc_kernel(const unsigned char* __restrict__ img, const float* __restrict__ sq, const float* __restrict__ sqc,
               const unsigned* __restrict__ smax_bits, const float* __restrict__ x, int N, int Npad, int ldx, int coff, int D, int ghi, int glo, int nst, int k,
@@ -272,7 +282,8 @@ knn_tc_kernel(const unsigned char* __restrict__ img, const float* __restrict__ s
               int* __restrict__ flag_rows) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t tile_bytes = (uint32_t)(ghi + glo) * GROUP_BYTES;
-  const size_t scratch_bytes = (size_t)k * 2 * RB * 4 > (size_t)RB * MAXC * 2 ? (size_t)k * 2 * RB * 4 : (size_t)RB * MAXC * 2;
+  const size_t scratch_bytes = tc_scratch_bytes(k);
+  constexpr int maxc = BIGK ? MAXC_BIG : MAXC;
   unsigned char* sA = smem;                                       // two query tile images
   unsigned char* sB = sA + 2 * (size_t)tile_bytes;                // nst candidate tile images
   float* exch = reinterpret_cast<float*>(sB + (size_t)nst * tile_bytes);            // [k][2][RB] top-k exchange
@@ -412,13 +423,13 @@ knn_tc_kernel(const unsigned char* __restrict__ img, const float* __restrict__ s
     }
 
     // ---- k-th largest class maximum of the row (both halves), pass threshold in v space
-    sort64_desc(acc);
-#pragma unroll
-    for (int s = 0; s < 24; ++s)
-      if (s < k) exch[(s * 2 + h) * RB + rloc] = acc[s];
-    named_bar_sync(1, SEL_WARPS * 32);
     float thr = CUDART_INF_F;
-    {
+    if (!BIGK) {
+      sort64_desc(acc);
+#pragma unroll
+      for (int s = 0; s < KSORT; ++s)
+        if (s < k) exch[(s * 2 + h) * RB + rloc] = acc[s];
+      named_bar_sync(1, SEL_WARPS * 32);
       int ia = 0, ib = 0;
       float vk = 0.f;
       for (int s = 0; s < k; ++s) {
@@ -426,8 +437,33 @@ knn_tc_kernel(const unsigned char* __restrict__ img, const float* __restrict__ s
         if (va >= vb) { vk = va; ++ia; } else { vk = vb; ++ib; }
       }
       if (row_ok && m_ok) thr = vk - eps;
-      if (h == 0) thr_s[rloc] = thr;
+    } else {
+      // No sort and no list exchange (64 values x 2 halves x 256 rows would not fit): bit-wise bisection on the order-preserving
+      // integer image of the floats.  T grows from the top bit down while at least k of the row's 128 class maxima are >= T, so
+      // it ends on the k-th largest value exactly; every step exchanges one count per half through shared memory.
+      int* cx = reinterpret_cast<int*>(exch);                        // [2 parities][2 halves][RB]
+      unsigned key[64];
+#pragma unroll
+      for (int c = 0; c < 64; ++c) {
+        const unsigned u = __float_as_uint(acc[c]);
+        key[c] = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+      }
+      unsigned T = 0u;
+#pragma unroll 1
+      for (int bit = 31; bit >= 0; --bit) {
+        const unsigned cand_t = T | (1u << bit);
+        int n = 0;
+#pragma unroll
+        for (int c = 0; c < 64; ++c) n += key[c] >= cand_t ? 1 : 0;
+        int* slot = cx + (bit & 1) * 2 * RB;
+        slot[h * RB + rloc] = n;
+        named_bar_sync(1, SEL_WARPS * 32);
+        if (slot[rloc] + slot[RB + rloc] >= k) T = cand_t;
+      }
+      const float vk = __uint_as_float((T & 0x80000000u) ? (T & 0x7fffffffu) : ~T);
+      if (row_ok && m_ok) thr = vk - eps;
     }
+    if (h == 0) thr_s[rloc] = thr;
     named_bar_sync(1, SEL_WARPS * 32);     // every thread has read the exchange area: the candidate lists may alias it
 
     // ---- pass 2: collect every column whose v reaches the threshold
@@ -451,7 +487,7 @@ knn_tc_kernel(const unsigned char* __restrict__ img, const float* __restrict__ s
             const int c = __clz(hits);
             hits &= ~(0x80000000u >> c);
             const int slot = atomicAdd(&cnt[rloc], 1);
-            if (slot < MAXC) cand[rloc * MAXC + slot] = (unsigned short)(col0 + half * 32 + c);
+            if (slot < maxc) cand[rloc * maxc + slot] = (unsigned short)(col0 + half * 32 + c);
           }
         }
       }
@@ -470,14 +506,86 @@ knn_tc_kernel(const unsigned char* __restrict__ img, const float* __restrict__ s
       const int grow = i0 + rl;
       if (grow >= N) continue;                                    // warp-uniform
       const int c = cnt[rl];
-      bool flag = (c > MAXC) || (c < k);
+      bool flag = (c > maxc) || (c < k);
       const float sq_r = sqb[grow], sqc_r = sqcb[grow];
       const float eps_r = knn_eps(sq_r, smax, sqc_r, smaxc, D);
       const float bound = (sqc_r - 2.f * thr_s[rl]) + 2.f * eps_r;  // d~ of the threshold + model error (+ rounding slack)
+      if (BIGK) {
+        // 24 < k <= 64: up to three candidates per lane.  Their canonical distances go to the warp's scratch; the position of a
+        // candidate in the answer is its lexicographic (d, j) rank among the row's candidates (indices are distinct, so the
+        // ranks are a permutation).
+        float* sd = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(exch) + (size_t)RB * MAXC_BIG * 2) +
+                    (size_t)warp * MAXC_BIG * 2;
+        int* sj = reinterpret_cast<int*>(sd + MAXC_BIG);
+        const int cc = c < maxc ? c : maxc;
+        const float* xi = xb + (size_t)grow * ldx;
+        float dm[MAXC_BIG / 32];
+        int jm[MAXC_BIG / 32];
+#pragma unroll
+        for (int e = 0; e < MAXC_BIG / 32; ++e) {
+          const int ci = lane + 32 * e;
+          dm[e] = CUDART_INF_F;
+          jm[e] = INT_MAX;
+          if (ci < cc) {
+            const int j = cand[rl * maxc + ci];
+            const float* xj = xb + (size_t)j * ldx;
+            float dot = 0.f;
+            if (vec_ok) {
+#pragma unroll 1
+              for (int c0 = 0; c0 < D; c0 += 16) {
+                float4 av[4], bq[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  if (c0 + 4 * u < D) {
+                    av[u] = *reinterpret_cast<const float4*>(xi + c0 + 4 * u);
+                    bq[u] = *reinterpret_cast<const float4*>(xj + c0 + 4 * u);
+                  }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  if (c0 + 4 * u < D) {
+                    dot = __fmaf_rn(av[u].x, bq[u].x, dot);
+                    dot = __fmaf_rn(av[u].y, bq[u].y, dot);
+                    dot = __fmaf_rn(av[u].z, bq[u].z, dot);
+                    dot = __fmaf_rn(av[u].w, bq[u].w, dot);
+                  }
+                }
+              }
+            } else {
+              for (int q2 = 0; q2 < D; ++q2) dot = __fmaf_rn(xi[q2], xj[q2], dot);
+            }
+            dm[e] = exact_dist(flavour, sq_r, sqb[j], dot);
+            jm[e] = j;
+            if (!(dm[e] <= bound)) flag = true;                      // error-model self check
+            sd[ci] = dm[e];
+            sj[ci] = j;
+          }
+        }
+        flag = __any_sync(0xffffffffu, flag);
+        __syncwarp();
+#pragma unroll
+        for (int e = 0; e < MAXC_BIG / 32; ++e) {
+          if (lane + 32 * e < cc) {
+            int rank = 0;
+            for (int m2 = 0; m2 < cc; ++m2) rank += lex_less(sd[m2], sj[m2], dm[e], jm[e]) ? 1 : 0;
+            if (rank < k) {
+              const size_t o = ((size_t)b * N + grow) * k + rank;
+              idx_out[o] = jm[e];
+              if (dist_out) dist_out[o] = dm[e];
+            }
+          }
+        }
+        __syncwarp();                                                // the scratch is reused by the warp's next row
+        if (flag && lane == 0) {
+          const int slot = atomicAdd(flag_count, 1);
+          flag_rows[slot] = b * N + grow;
+        }
+        continue;
+      }
       float d = CUDART_INF_F;
       int jj = INT_MAX;
       if (lane < c && lane < MAXC) {
-        const int j = cand[rl * MAXC + lane];
+        const int j = cand[rl * maxc + lane];
         const float* xi = xb + (size_t)grow * ldx;
         const float* xj = xb + (size_t)j * ldx;
         float dot = 0.f;
@@ -610,11 +718,69 @@ knn_exact_rows_kernel(const float* __restrict__ x, const float* __restrict__ sq,
   }
 }
 
+// the same for k > 32 (the register list above holds one entry per lane): one CTA per flagged row selects the answers one
+// after the other -- the lexicographically smallest (d, j) above the previous one, canonical distances recomputed on the fly.
+// Flagged rows are rare (rows with more than MAXC_BIG candidates or a violated error bound), so the k passes do not matter.
+__global__ void __launch_bounds__(256)
+knn_exact_rows_bigk_kernel(const float* __restrict__ x, const float* __restrict__ sq, int N, int Npad, int ldx, int coff, int D,
+                           int k, int flavour, const int* __restrict__ flag_count, const int* __restrict__ flag_rows,
+                           int32_t* __restrict__ idx_out, float* __restrict__ dist_out) {
+  __shared__ float xs[64];
+  __shared__ float rd[8];
+  __shared__ int rj[8];
+  __shared__ float best_d;
+  __shared__ int best_j;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nflag = *flag_count;
+  for (int f = blockIdx.x; f < nflag; f += gridDim.x) {
+    const int grow = flag_rows[f];
+    const int b = grow / N, row = grow - b * N;
+    const float* xb = x + (size_t)b * N * ldx + coff;
+    __syncthreads();
+    if (threadIdx.x < D) xs[threadIdx.x] = xb[(size_t)row * ldx + threadIdx.x];
+    __syncthreads();
+    const float sqi = sq[(size_t)b * Npad + row];
+    float pd = -CUDART_INF_F;
+    int pj = -1;
+    for (int sel = 0; sel < k; ++sel) {
+      float md = CUDART_INF_F;
+      int mj = INT_MAX;
+      for (int j = threadIdx.x; j < N; j += 256) {
+        const float* xj = xb + (size_t)j * ldx;
+        float dot = 0.f;
+        for (int c = 0; c < D; ++c) dot = __fmaf_rn(xs[c], xj[c], dot);
+        const float d = exact_dist(flavour, sqi, sq[(size_t)b * Npad + j], dot);
+        if (lex_less(pd, pj, d, j) && lex_less(d, j, md, mj)) { md = d; mj = j; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float od = __shfl_xor_sync(0xffffffffu, md, o);
+        const int oj = __shfl_xor_sync(0xffffffffu, mj, o);
+        if (lex_less(od, oj, md, mj)) { md = od; mj = oj; }
+      }
+      if (lane == 0) { rd[warp] = md; rj[warp] = mj; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w)
+          if (lex_less(rd[w], rj[w], md, mj)) { md = rd[w]; mj = rj[w]; }
+        best_d = md;
+        best_j = mj;
+        const size_t o = (size_t)grow * k + sel;
+        idx_out[o] = mj == INT_MAX ? 0 : mj;
+        if (dist_out) dist_out[o] = md;
+      }
+      __syncthreads();
+      pd = best_d;
+      pj = best_j;
+    }
+  }
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------- host ------
 bool knn_tc_eligible(int N, int D, int k) {
-  if (!(D >= 1 && D <= 64 && k >= 1 && k <= 24 && N >= k && N <= 65535)) return false;
+  if (!(D >= 1 && D <= 64 && k >= 1 && k <= 64 && N >= k && N <= 65535)) return false;
   return make_tc_plan(1, N, D, k).nst >= 2;
 }
 
@@ -666,16 +832,21 @@ int knn_tc_run(const float* x, int B, int N, int ldx, int coff, int D, int k, in
   knn_tc_centre_kernel<<<dim3(8, B), 256, 0, st>>>(x, N, ldx, coff, D, w.centre);
   knn_tc_prep_kernel<<<dim3(p.ntile, B), 128, 0, st>>>(x, N, ldx, coff, D, p.ghi, p.glo, p.Npad, w.centre, w.img, w.sq, w.sqc,
                                                       w.smax);
-  static thread_local size_t configured = 0;
-  if (p.smem > configured) {
-    WSPC_CUDA(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-    configured = p.smem;
+  static thread_local size_t configured[2] = {0, 0};
+  const int big = k > KSORT ? 1 : 0;
+  auto kern = big ? knn_tc_kernel<true> : knn_tc_kernel<false>;
+  if (p.smem > configured[big]) {
+    WSPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    configured[big] = p.smem;
   }
-  knn_tc_kernel<<<dim3((N + RB - 1) / RB, B), KTC_THREADS, p.smem, st>>>(w.img, w.sq, w.sqc, w.smax, x, N, p.Npad, ldx, coff, D, p.ghi,
-                                                                        p.glo, p.nst, k, flavour, idx, dist, w.flag_count,
-                                                                        w.flag_rows);
-  knn_exact_rows_kernel<<<2 * kNumSM, 256, 0, st>>>(x, w.sq, N, p.Npad, ldx, coff, D, k, flavour, w.flag_count, w.flag_rows,
-                                                    idx, dist);
+  kern<<<dim3((N + RB - 1) / RB, B), KTC_THREADS, p.smem, st>>>(w.img, w.sq, w.sqc, w.smax, x, N, p.Npad, ldx, coff, D, p.ghi, p.glo,
+                                                               p.nst, k, flavour, idx, dist, w.flag_count, w.flag_rows);
+  if (k <= 32)
+    knn_exact_rows_kernel<<<2 * kNumSM, 256, 0, st>>>(x, w.sq, N, p.Npad, ldx, coff, D, k, flavour, w.flag_count, w.flag_rows,
+                                                      idx, dist);
+  else
+    knn_exact_rows_bigk_kernel<<<2 * kNumSM, 256, 0, st>>>(x, w.sq, N, p.Npad, ldx, coff, D, k, flavour, w.flag_count,
+                                                           w.flag_rows, idx, dist);
   count_launch(4);
   WSPC_LAUNCH_CHECK("knn_tc kernels");
   return WSPC_OK;
