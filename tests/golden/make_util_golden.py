@@ -80,10 +80,31 @@ def loss_module(out):
     out.update(OverwhelmLoss=_np(l3), OverwhelmLoss_full=_np(f3))
 
 
+def unnorm_xyz_model(out):
+    """DGCNN_S3DIS.get_model_unnormXYZ (S3DIS/DGCNN_S3DIS.py:106-186): the first graph is built on the metric xyz channels
+    0:3 instead of the room-normalised 6:9; inference mode on seeded variables, neighbour lists recorded."""
+    sys.path.insert(1, os.path.join(REF, "S3DIS"))
+    sys.path.insert(1, os.path.join(REF, "Networks/dgcnn/utils"))
+    sys.path.insert(1, os.path.dirname(os.path.dirname(HERE)))
+    sys.path.insert(1, HERE)
+    import DGCNN_S3DIS as network
+    from refgen_common import S3DIS_LAYERS, xavier_params
+    from weaksuppointcloudseg_b200 import synthetic as syn
+    X, _, _, _ = syn.s3dis_batch(1, N=192, n_labelled=8, seed=421)
+    params0 = xavier_params(S3DIS_LAYERS, seed=422)
+    tf.reset()
+    tf.preset_variables(params0)
+    Z = network.get_model_unnormXYZ(tf.constant(X), tf.constant(False), weight_decay=0., bn_decay=None)
+    tk = tf.RECORD["top_k"][-3:]
+    out.update(ux_X=X, ux_param_seed=np.array([422]), ux_Z=_np(Z), ux_knn1=tk[0].astype(np.int16), ux_knn2=tk[1].astype(np.int16),
+               ux_knn3=tk[2].astype(np.int16))
+
+
 if __name__ == "__main__":
     out = {}
     smooth_variants(out)
     loss_module(out)
+    unnorm_xyz_model(out)
     np.savez_compressed(os.path.join(HERE, "ref_util_variants.npz"), **out)
     for k, v in out.items():
         if v.size == 1:

@@ -75,3 +75,27 @@ def test_smooth_graph_errors_are_loud():
         ops.smooth_loss_graph(P, idx, dist, 0.1, 64)                                        # unknown flag
     with pytest.raises(L.WspcError):
         ops.smooth_loss_graph(P, idx[:, :, :3], dist, 0.1)                                  # shape mismatch
+
+
+def test_get_model_unnormxyz_matches_reference_code(cuda):
+    """DGCNN_S3DIS.get_model_unnormXYZ (S3DIS/DGCNN_S3DIS.py:106-186) as run by the reference's own module on the TF shim:
+    first graph on channels 0:3, inference mode; the first neighbour lists are computed by the kernel and must be identical."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import refgen_common as rc
+    from weaksuppointcloudseg_b200 import DGCNN_S3DIS
+    from weaksuppointcloudseg_b200.engine_s3dis import S3DISEngine
+    dev = cuda
+    X = cu("ux_X")
+    B, N, _ = X.shape
+    params0 = rc.xavier_params(rc.S3DIS_LAYERS, int(G["ux_param_seed"][0]))
+    eng = S3DISEngine(params0, B, N, device=dev, unnorm_xyz=True)
+    ov = {k_: torch.from_numpy(G["ux_" + k_].astype(np.int32)).to(dev) for k_ in ("knn2", "knn3")}
+    Z = eng.forward(X, False, knn_override=ov).cpu().numpy()
+    assert np.array_equal(eng.idx[0].cpu().numpy(), G["ux_knn1"].astype(np.int32))
+    assert np.abs(Z - G["ux_Z"]).max() <= TOL * np.abs(G["ux_Z"]).max()
+    # the normalised-coordinate model on the same variables is a different function: the flag is not a no-op
+    eng2 = S3DISEngine(params0, B, N, device=dev)
+    Z2 = eng2.forward(X, False).cpu().numpy()
+    assert np.abs(Z2 - G["ux_Z"]).max() > 10 * TOL * np.abs(G["ux_Z"]).max()
+    assert hasattr(DGCNN_S3DIS, "get_model_unnormXYZ")

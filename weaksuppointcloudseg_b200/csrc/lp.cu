@@ -160,7 +160,7 @@ lpb_setup_kernel(const float* __restrict__ Lm, const float* __restrict__ G, int 
 }
 
 // q = alpha L p + d p for one 16-column slab of one block (grid: row tiles x slabs x blocks), dots pq[it] += p.q
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(256, 2)
 lpb_matvec_kernel(const float* __restrict__ Lm, const float* __restrict__ p, const float* __restrict__ diag, float alpha, int N,
                   int Kc, int it, int iters_alloc, float* __restrict__ q, double* __restrict__ scal,
                   const int* __restrict__ done) {
