@@ -113,6 +113,24 @@ dp.broadcast_params(flat)
 assert torch.equal(flat, torch.arange(10.0))
 lo, hi = shard_pairs(8, dp.rank, dp.world_size)
 assert (lo, hi) == (4 * dp.rank, 4 * dp.rank + 4)
+# overlapped gradient exchange: the head (seg/*, adj_conv7) slice is the contiguous tail of the flat buffer and is reduced
+# asynchronously while the rest is still being produced; both slices must end up summed over the ranks
+import numpy as np
+from collections import OrderedDict
+from weaksuppointcloudseg_b200.runtime import VariableStore
+names = ["adj_conv1/weights", "adj_conv1/biases", "adj_conv1/bn/beta", "adj_conv2/weights", "adj_conv7/weights",
+         "adj_conv7/bn/gamma", "seg/conv1/weights", "seg/conv3/biases"]
+params = OrderedDict((n, np.zeros((5, 3) if n.endswith("weights") else (3,), np.float32)) for n in names)
+vs = VariableStore(params, "cpu")
+tail = vs.tail_offset(("adj_conv7/", "seg/"))
+assert tail == vs._toffs["adj_conv7/weights"][0] and 0 < tail < vs.grad.numel()
+assert vs.tail_offset(("adj_conv2/",)) is None            # not a tail: no overlap is attempted
+vs.grad[:] = float(dp.rank + 1)
+work = dp.all_reduce_async(vs.grad[tail:])
+vs.grad[:tail] *= 2.0                                      # "the rest of the backward pass"
+dp.all_reduce(vs.grad[:tail])
+work.wait()
+assert torch.all(vs.grad[tail:] == 3.0) and torch.all(vs.grad[:tail] == 6.0)
 dp.barrier(); dp.shutdown()
 print("rank", dp.rank, "ok")
 '''

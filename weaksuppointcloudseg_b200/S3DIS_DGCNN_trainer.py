@@ -250,7 +250,13 @@ class S3DIS_Trainer():
     def _allreduce_and_step(self, lr):
         gscale = 1.0
         if self.dist is not None:
-            self.dist.all_reduce(self.engine.vs.grad)
+            work = getattr(self, '_tail_work', None)
+            if work is not None:      # the tail slice has been in flight since the head gradients were complete
+                self.dist.all_reduce(self.engine.vs.grad[:self._tail_off])
+                work.wait()
+                self._tail_work = None
+            else:
+                self.dist.all_reduce(self.engine.vs.grad)
             gscale = 1.0 / self.dist.world_size
         self.engine.vs.adam_step(lr, gscale=gscale)
 

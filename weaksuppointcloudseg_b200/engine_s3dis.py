@@ -74,6 +74,7 @@ class S3DISEngine:
         self.MS = torch.empty((P, 128), **f32) if (rt.MAXK_SYNTH and not self.fused) else None   # [pooled max | dout / #ties]
         self.pc7 = rt.PoolConv(self.layers["adj_conv7"], self.dev) if rt.POOLCONV_GRAM else None
         self.prof = None   # optional list of (tag, start_event, end_event) filled around the kNN launches
+        self.on_head_grads_ready = None   # data parallelism: called once the seg/* and adj_conv7 gradients are enqueued
 
     def _tick(self):
         if self.prof is None:
@@ -242,6 +243,8 @@ class S3DISEngine:
             G7 = rt.op_dy_sparse(self.y7, c7, self.dg, self.amax, N)
             rt.wgrad(rt.op_plain(self.cat, 192, 192), G7, P, c7.dW, c7.db, dev)
             rt.rows_gemm(G7, c7.W, 1024, 1, P, 192, 1024, L.Epilogue(out=dcat_a, ldo=192), L.EPI_ACCUM)
+        if self.on_head_grads_ready is not None:
+            self.on_head_grads_ready()
         if self.fused:
             ef, eb = self.ef, self.eb
             rt.edgeblock_backward(ef, eb[2], c5, None, cat_a + 4 * 64, 192, 64, self.idx[2], k, N, P, cat_a + 4 * 128, 192,

@@ -51,6 +51,17 @@ class VariableStore:
         o, shape = offs[name]
         return buf[o:o + int(np.prod(shape))].view(*shape)
 
+    def tail_offset(self, prefixes):
+        """first element of the flat trainable buffer that belongs to a variable whose name starts with one of `prefixes`,
+        provided those variables form the contiguous tail of the buffer (else None)"""
+        offs = {k: o for k, (o, _) in self._toffs.items()}
+        inside = [o for k, o in offs.items() if k.startswith(tuple(prefixes))]
+        if not inside:
+            return None
+        t = min(inside)
+        ok = all((o >= t) == k.startswith(tuple(prefixes)) for k, o in offs.items())
+        return int(t) if ok and t > 0 else None
+
     def p(self, name):
         return self._view(self.theta, self._toffs, name)
 
