@@ -17,6 +17,9 @@ def test_two_rank_nccl_step_matches_oracle_and_ranks_agree():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", "29633", os.path.join(HERE, "mp_step_worker.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-3000:])
+    if out.returncode != 0:
+        print(out.stdout[-1500:])
+        print(out.stderr[-4000:])
+    assert out.returncode == 0, "worker failed (output printed above)"
     assert out.stdout.count(" ok: ") == 2, out.stdout
     print(out.stdout)
