@@ -58,16 +58,20 @@ def test_mapping_onto_the_flat_store():
     state = ['adj_conv1/bn/pop_mean', 'adj_conv1/bn/pop_var']
     shapes = {'adj_conv1/weights': (6, 16), 'adj_conv1/biases': (16,), 'adj_conv1/bn/beta': (16,),
               'adj_conv1/bn/gamma': (16,), 'adj_conv1/bn/pop_mean': (16,), 'adj_conv1/bn/pop_var': (16,)}
-    blob = tfc.to_store_blob(v, trainable, state, shapes)
+    with pytest.raises(KeyError, match="optimiser state"):        # some variables of this checkpoint carry no Adam slots:
+        tfc.to_store_blob(v, trainable, state, shapes)            # a silent restart of Adam / the schedules is refused ...
+    with pytest.warns(UserWarning, match="optimiser state"):      # ... unless the caller asks for the weights only
+        blob = tfc.to_store_blob(v, trainable, state, shapes, allow_missing_optimizer_state=True)
     assert blob['adj_conv1/weights'].shape == (6, 16)             # (1,1,Cin,Cout) kernel -> (Cin,Cout)
     assert np.array_equal(blob['adj_conv1/weights'], v['adj_conv1/weights'][0, 0]) and int(blob['Variable']) == 1234
     n = 6 * 16 + 3 * 16
     assert blob['__adam_m'].shape == (n,) and np.array_equal(blob['__adam_m'][:96], v['adj_conv1/weights/Adam'].reshape(-1))
     assert not blob['__adam_m'][96:].any()                        # variables without slots in the checkpoint start at zero
     with pytest.raises(ValueError):
-        tfc.to_store_blob(v, trainable, state, dict(shapes, **{'adj_conv1/biases': (15,)}))
+        tfc.to_store_blob(v, trainable, state, dict(shapes, **{'adj_conv1/biases': (15,)}), allow_missing_optimizer_state=True)
     with pytest.raises(KeyError):
-        tfc.to_store_blob(v, trainable + ['nope/weights'], state, dict(shapes, **{'nope/weights': (1,)}))
+        tfc.to_store_blob(v, trainable + ['nope/weights'], state, dict(shapes, **{'nope/weights': (1,)}),
+                          allow_missing_optimizer_state=True)
 
 
 def test_restore_checkpoint_reads_a_tf_bundle(tmp_path):

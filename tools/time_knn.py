@@ -36,6 +36,10 @@ def bench(B, N, D, k, flavour, iters=5, coff=None):
 
 if __name__ == "__main__":
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+    if len(sys.argv) > 2 and sys.argv[2] == "ncu":      # two shapes only, for ncu captures (3 launches each: 2 warm-up + 1)
+        bench(B, 4096, 64, 20, 0, iters=1)
+        bench(max(B // 8, 1), 8192, 64, 40, 0, iters=1)
+        sys.exit(0)
     bench(B, 4096, 3, 20, 0)
     bench(B, 4096, 6, 10, 1)
     bench(B, 4096, 3, 20, 0, coff=6)

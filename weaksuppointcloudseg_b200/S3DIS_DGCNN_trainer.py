@@ -525,14 +525,16 @@ class S3DIS_Trainer():
             # the best copy lives next to the checkpoint, under `best_filename` (:592-601)
             np.savez(os.path.join(os.path.dirname(os.path.abspath(save_filepath)), best_filename + '.npz'), **blob)
 
-    def RestoreCheckPoint(self, filepath):
+    def RestoreCheckPoint(self, filepath, weights_only=False):
         """`<filepath>.npz` written by SaveCheckPoint, or -- when `<filepath>.index` / `.data-00000-of-00001` exist -- a
-        checkpoint written by the reference's tf.train.Saver (same variable names; tf_checkpoint.py)."""
+        checkpoint written by the reference's tf.train.Saver (same variable names; tf_checkpoint.py).  A TF checkpoint
+        without global step / Adam slots is refused unless `weights_only` (the schedules would silently restart)."""
         from . import tf_checkpoint
         vs = self.engine.vs
         if not os.path.exists(filepath if filepath.endswith('.npz') else filepath + '.npz') and tf_checkpoint.exists(filepath):
             shapes = {k: tuple(vs.get(k).shape) for k in vs.trainable_names + vs.state_names}
-            blob = tf_checkpoint.to_store_blob(tf_checkpoint.read(filepath), vs.trainable_names, vs.state_names, shapes)
+            blob = tf_checkpoint.to_store_blob(tf_checkpoint.read(filepath), vs.trainable_names, vs.state_names, shapes,
+                                               allow_missing_optimizer_state=weights_only)
         else:
             blob = np.load(filepath if filepath.endswith('.npz') else filepath + '.npz')
         vs.load({k: blob[k] for k in vs.trainable_names + vs.state_names})

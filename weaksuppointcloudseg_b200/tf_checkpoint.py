@@ -179,7 +179,8 @@ def exists(prefix):
     return os.path.exists(prefix + '.index') and os.path.exists(prefix + '.data-00000-of-00001')
 
 
-# ---- writer of the same subset (tests; also lets a wspc checkpoint be handed back to TF tooling) --------------------------
+# ---- writer of the same subset (TEST FIXTURES ONLY: block and tensor checksums are written as zero, which TensorFlow's own
+#      BundleReader rejects -- these files are for this module's reader, not for TF tooling) ----------------------------------
 
 def _field(f, wt, payload):
     tag = _put_varint(f << 3 | wt)
@@ -245,10 +246,22 @@ def write(prefix, arrays, entries_per_block=32):
 
 # ---- mapping onto the flat variable store ------------------------------------------------------------------------------------
 
-def to_store_blob(tf_vars, trainable_names, state_names, shapes):
+def to_store_blob(tf_vars, trainable_names, state_names, shapes, allow_missing_optimizer_state=False):
     """Arrange the variables of a reference checkpoint the way `S3DIS_Trainer.RestoreCheckPoint` consumes its own `.npz`:
-    every trainable / state variable by name (shape-checked), `Variable` (global step, 0 when absent) and the Adam
-    moments as flat buffers in the store's order (`<var>/Adam`, `<var>/Adam_1`; zeros when the checkpoint has none)."""
+    every trainable / state variable by name (shape-checked), `Variable` (global step) and the Adam moments as flat buffers
+    in the store's order (`<var>/Adam`, `<var>/Adam_1`).  A checkpoint without the global step or without Adam slots would
+    silently restart the learning-rate / batch-norm schedules and Adam's bias correction: that is an error unless
+    `allow_missing_optimizer_state` is set (then they start from zero, with a warning)."""
+    missing = [k + slot for k in trainable_names for slot in ('/Adam', '/Adam_1') if k + slot not in tf_vars]
+    if 'Variable' not in tf_vars:
+        missing.append('Variable (global step)')
+    if missing:
+        msg = ("TensorFlow checkpoint lacks optimiser state (%d entries, e.g. %s): resuming would restart the schedules and "
+               "Adam's moments" % (len(missing), missing[0]))
+        if not allow_missing_optimizer_state:
+            raise KeyError(msg + "; pass allow_missing_optimizer_state=True to load the weights only")
+        import warnings
+        warnings.warn(msg)
     blob = {}
     for k in list(trainable_names) + list(state_names):
         if k not in tf_vars:
