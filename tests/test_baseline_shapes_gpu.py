@@ -174,3 +174,34 @@ def test_cfg4_knn_bit_exact(cuda, D, coff, ld):
     idx, dist = ops.knn_fused(torch.from_numpy(feat).to(cuda), k, ops.DIST_TFUTIL, coff=coff, D=D, return_dist=True)
     assert np.array_equal(idx.cpu().numpy(), ridx.astype(np.int32))
     assert np.array_equal(dist.cpu().numpy().view(np.uint32), rdist.astype(np.float32).view(np.uint32))
+
+
+def test_cfg4_engine_step_against_oracle(cuda):
+    """BASELINE cfg-4 (N = 8192, k = 40), one Siamese pair, a full train step of the fused engine against the CPU oracle run with
+    k = 40: first neighbour lists bit-exact, logits / probabilities / the four losses within 1e-3 (feature-space lists of the
+    later blocks taken from the oracle, as in the fixtures)."""
+    from weaksuppointcloudseg_b200 import synthetic as syn
+    from weaksuppointcloudseg_b200.engine_s3dis import S3DISEngine
+    N, k = 8192, 40
+    X, Y, M, _ = syn.s3dis_batch(1, N=N, n_labelled=82, seed=141)
+    B = 2
+    params = od.init_params(od.S3DIS_LAYERS, seed=142)
+    mask = np.floor(0.7 + np.random.default_rng(143).random((B, N, 256))).astype(np.float32)
+    p = od.to_torch(params)
+    opt = od.AdamTF(p, od.trainable_names(p))
+    rec = {}
+    ref = od.train_step_s3dis(p, opt, torch.from_numpy(X), torch.from_numpy(Y), torch.from_numpy(M), step=0,
+                              dropout_mask=torch.from_numpy(mask), rec=rec, k=k)
+    eng = S3DISEngine(params, B, N, device=cuda, k=k)
+    ov = {f"knn{i}": rec[f"knn{i}/idx"].to(torch.int32).to(cuda) for i in (2, 3)}
+    losses = eng.train_step(torch.from_numpy(X).to(cuda), torch.from_numpy(Y).to(cuda), torch.from_numpy(M).to(cuda), lr=1e-3,
+                            bn_decay=od.bn_decay(0, 1, 300000), dropout_mask=torch.from_numpy(mask).to(cuda), knn_override=ov)
+    torch.cuda.synchronize()
+    assert np.array_equal(eng.idx[0].cpu().numpy(), rec["knn1/idx"].numpy().astype(np.int32))
+    zerr = rel(eng.Z.cpu().numpy(), ref["Z"].detach().numpy())
+    perr = rel(eng.Zp.cpu().numpy(), ref["Z_prob"].detach().numpy())
+    got = losses.cpu().numpy()
+    want = [float(ref[n].detach()) for n in ("loss_seg", "loss_siamese", "loss_inexact", "loss_smooth", "loss")]
+    lerr = [abs(g - w) / abs(w) for g, w in zip(got, want)]
+    print(f"cfg-4 shape: logits {zerr:.2e}, probs {perr:.2e}, losses {lerr}")
+    assert zerr <= TOL and perr <= TOL and max(lerr) <= TOL, (zerr, perr, lerr)

@@ -579,17 +579,8 @@ extern "C" int wspc_conv1x1_rows_ws(const wspc_operand_t* A, int a_mode, const f
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // tensor-core (tcgen05) path for eligible shapes; WSPC_GEMM=simt forces the CUDA-core kernels (A/B testing)
   static const bool env_simt = []() { const char* e = getenv("WSPC_GEMM"); return e && strcmp(e, "simt") == 0; }();
-  if (!env_simt && g_gemm_path == 0) {
-    const int rc = rowgemm_tc_dispatch(*A, a_mode, Bm, ldb, b_transposed, M, N, K, *epi, epi_mode, workspace, workspace_bytes, st);
-    if (rc != 0) return rc < 0 ? rc : WSPC_OK;
-  }
-  // narrow outputs (N <= 16, K a multiple of 8): warp-per-row kernel
-  if (!env_simt && g_gemm_path == 0 && epi_mode == EPI_STORE && N <= 16 && K % 8 == 0 && K >= 64 && K <= 2048 &&
-      !epi->rowbias && (a_mode == OP_PLAIN || a_mode == OP_BNRELU) && (size_t)N * (K + 4) * 4 <= 48 * 1024) {
-    if (a_mode == OP_PLAIN) return launch_rows_narrow<OP_PLAIN>(*A, Bm, ldb, b_transposed, M, N, K, *epi, st);
-    return launch_rows_narrow<OP_BNRELU>(*A, Bm, ldb, b_transposed, M, N, K, *epi, st);
-  }
-  // narrow reductions (K <= 16): data gradient of a narrow head fused with the ReLU-mask / BN-sum epilogue
+  // narrow reductions (K <= 16): data gradient of a narrow head fused with the ReLU-mask / BN-sum epilogue.  Checked BEFORE the
+  // tensor-core dispatch, which also accepts the shape but runs its element-wise operand loader for K = 13 (0.87 ms at cfg-3)
   if (!env_simt && g_gemm_path == 0 && epi_mode == EPI_RELUMASK_STATS && a_mode == OP_DY && !A->c1 && K <= 16 && N % 4 == 0 &&
       N <= 1024 && 256 % (N / 4) == 0 && aligned16(epi->out) && (epi->ldo % 4) == 0 && aligned16(epi->yprev) &&
       (epi->ldyp % 4) == 0 && aligned16(epi->scp) && aligned16(epi->shp) && (!epi->dmask || aligned16(epi->dmask))) {
@@ -601,6 +592,16 @@ extern "C" int wspc_conv1x1_rows_ws(const wspc_operand_t* A, int a_mode, const f
     count_launch();
     WSPC_LAUNCH_CHECK("rows_narrowk_relumask_kernel");
     return WSPC_OK;
+  }
+  if (!env_simt && g_gemm_path == 0) {
+    const int rc = rowgemm_tc_dispatch(*A, a_mode, Bm, ldb, b_transposed, M, N, K, *epi, epi_mode, workspace, workspace_bytes, st);
+    if (rc != 0) return rc < 0 ? rc : WSPC_OK;
+  }
+  // narrow outputs (N <= 16, K a multiple of 8): warp-per-row kernel
+  if (!env_simt && g_gemm_path == 0 && epi_mode == EPI_STORE && N <= 16 && K % 8 == 0 && K >= 64 && K <= 2048 &&
+      !epi->rowbias && (a_mode == OP_PLAIN || a_mode == OP_BNRELU) && (size_t)N * (K + 4) * 4 <= 48 * 1024) {
+    if (a_mode == OP_PLAIN) return launch_rows_narrow<OP_PLAIN>(*A, Bm, ldb, b_transposed, M, N, K, *epi, st);
+    return launch_rows_narrow<OP_BNRELU>(*A, Bm, ldb, b_transposed, M, N, K, *epi, st);
   }
   switch (a_mode) {
     case OP_PLAIN: return launch_rows_e<OP_PLAIN>(*A, Bm, ldb, b_transposed, M, N, K, *epi, epi_mode, st);
