@@ -734,12 +734,12 @@ edgeconv2_bwd_kernel(const float* __restrict__ UV, long long ldu, const int32_t*
 // =========================================================== warp-specialised backward (k >= 8) =======================
 // The serial kernels above run build -> MMA -> epilogue one after the other inside a CTA and rely on 2-3 co-resident CTAs for
 // overlap.  Here ONE persistent CTA per SM splits the backward tile by role:
-//   warps 0-7    epilogue   TMEM -> registers -> (arg-max routing, BN backward, operand image | ReLU mask, scatter, row sums);
-//                           thread 0 also issues tcgen05.mma / tcgen05.commit between its phases (a 17th warp would cost the
-//                           register file of 20: allocation is per four warps)
+//   warps 0-7    epilogue   TMEM -> registers -> (arg-max routing, BN backward, operand image | ReLU mask, scatter, row sums)
 //   warps 8-15   builders   the TMA engine gathers the tile's raw rows: one 1-D bulk copy (cp.async.bulk) per neighbour row,
 //                           issued by that row's thread, completing on an mbarrier; a1 = relu(bn1(u_i + v_j + b1)) is then
-//                           formed from shared memory into the bf16 hi / lo operand image
+//                           formed from shared memory into the bf16 hi / lo operand image; one builder thread also issues
+//                           the tcgen05.mma / tcgen05.commit (a 17th warp would cost the register file of 20: allocation
+//                           is per four warps)
 // Buffers: two a1 operand images, two dy2 images, two y2 and two da1 accumulators (tile parity), one raw staging tile; the
 // forward weight image doubles as W2^T (read MN-major).  Roles talk through mbarriers (full / empty per buffer, parity = use
 // count); each group also has a named barrier.  The a1 expression and the MMA sequence of y2 are those of the serial kernels:
@@ -906,6 +906,40 @@ edgeconv2_bwd_ws_kernel(const float* __restrict__ UV, long long ldu, const int32
   const uint32_t kinv = (uint32_t)((1ull << 32) / (uint32_t)k + 1);
   const int n_my = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
+  // tcgen05.mma issue: ONE builder thread (the builders wait for the epilogue most of the time; on an epilogue thread the 28
+  // MMAs + descriptors per tile delayed all sixteen warps by ~5 500 cycles per tile, measured).  Order in the tensor queue:
+  // y2(t), then the gradients of tile t-1.
+  uint32_t accum_w = 0;
+  auto mma1 = [&](int t) {
+    const int s = t % WSB_NA, sg = t & 1;
+    mbar_wait(fullA + s, (uint32_t)(t / WSB_NA) & 1u);
+    tc::fence_after();
+    const uint32_t a_hi = smem_u32(smem + WSB_OFF_A + s * IMG_BYTES);
+    issue_rows_gemm(tmem_base + (uint32_t)(sg * CO), a_hi, a_hi + 8 * AGB, smem_u32(sWhi), smem_u32(sWlo), idesc);
+    tc::commit(barY + sg);
+  };
+  auto mma2 = [&](int t) {
+    const int s = t % WSB_NA, sg = t & 1;
+    mbar_wait(fullG + sg, (uint32_t)(t >> 1) & 1u);
+    tc::fence_after();
+    const uint32_t ah = smem_u32(smem + WSB_OFF_A + s * IMG_BYTES);
+    const uint32_t gh = smem_u32(smem + WSB_OFF_G + sg * BWD_G_REGION), gl = gh + 8 * AGB;
+    // dW2 += a1^T dy2: both images read MN-major (reduction over the 128 rows); M = 128 spans [a1_hi ; a1_lo]
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      const uint32_t gb = pass ? gl : gh;
+#pragma unroll
+      for (int j = 0; j < TILE_M / 16; ++j) {
+        const uint64_t ad = tc::smem_desc(ah + (uint32_t)j * 256, 128, AGB);
+        const uint64_t gd = tc::smem_desc(gb + (uint32_t)j * 256, 128, AGB);
+        tc::mma_bf16(acc_w, ad, gd, idesc_mn, accum_w);
+        accum_w = 1;
+      }
+    }
+    issue_da_gemm(tmem_base + (uint32_t)(2 * CO + sg * CO), gh, gl, smem_u32(sWhi), smem_u32(sWlo), idesc_mix);
+    tc::commit(barD + sg);
+  };
+
   if (warp < 8) {
     const int lq = warp & 3, ch = warp >> 2;
     const int trow = lq * 32 + lane;
@@ -1037,55 +1071,10 @@ edgeconv2_bwd_ws_kernel(const float* __restrict__ UV, long long ldu, const int32
       }
     };
 
-    // thread 0 between its epilogue phases: y2 of the next tile first (keeps the tensor pipe ahead of epi1), then this tile's
-    // gradients.  Accumulator / image reuse is ordered by program order plus the barriers the waits below imply.
-    uint32_t accum_w = 0;
-    auto mma1 = [&](int t) {
-      const int s = t % WSB_NA, sg = t & 1;
-      mbar_wait(fullA + s, (uint32_t)(t / WSB_NA) & 1u);
-      tc::fence_after();
-      const uint32_t a_hi = smem_u32(smem + WSB_OFF_A + s * IMG_BYTES);
-      issue_rows_gemm(tmem_base + (uint32_t)(sg * CO), a_hi, a_hi + 8 * AGB, smem_u32(sWhi), smem_u32(sWlo), idesc);
-      tc::commit(barY + sg);
-    };
-    auto mma2 = [&](int t) {
-      const int s = t % WSB_NA, sg = t & 1;
-      mbar_wait(fullG + sg, (uint32_t)(t >> 1) & 1u);
-      tc::fence_after();
-      const uint32_t ah = smem_u32(smem + WSB_OFF_A + s * IMG_BYTES);
-      const uint32_t gh = smem_u32(smem + WSB_OFF_G + sg * BWD_G_REGION), gl = gh + 8 * AGB;
-      // dW2 += a1^T dy2: both images read MN-major (reduction over the 128 rows); M = 128 spans [a1_hi ; a1_lo]
-#pragma unroll 1
-      for (int pass = 0; pass < 2; ++pass) {
-        const uint32_t gb = pass ? gl : gh;
-#pragma unroll
-        for (int j = 0; j < TILE_M / 16; ++j) {
-          const uint64_t ad = tc::smem_desc(ah + (uint32_t)j * 256, 128, AGB);
-          const uint64_t gd = tc::smem_desc(gb + (uint32_t)j * 256, 128, AGB);
-          tc::mma_bf16(acc_w, ad, gd, idesc_mn, accum_w);
-          accum_w = 1;
-        }
-      }
-      issue_da_gemm(tmem_base + (uint32_t)(2 * CO + sg * CO), gh, gl, smem_u32(sWhi), smem_u32(sWlo), idesc_mix);
-      tc::commit(barD + sg);
-    };
-    // Issue order (tensor queue): y2(0), y2(1), grad(0), | grad(t+1), y2(t+2) per iteration.  With two operand images y2(t+2) can
-    // only be issued once tile t has released its image (end of epi2(t)); issuing it earlier would wait for this very thread.
-    if (n_my > 0) {
-      if (tid == 0) {
-        mma1(0);
-        if (n_my > 1) mma1(1);
-      }
-      epi1(0);
-      if (tid == 0) mma2(0);
-    }
+    if (n_my > 0) epi1(0);
     for (int t = 0; t < n_my; ++t) {
-      if (t + 1 < n_my) {
-        epi1(t + 1);                                  // runs while the tensor pipe works on tile t's gradients
-        if (tid == 0) mma2(t + 1);
-      }
+      if (t + 1 < n_my) epi1(t + 1);                  // runs while the tensor pipe works on tile t's gradients
       epi2(t);
-      if (tid == 0 && t + 2 < n_my) mma1(t + 2);
     }
     // dW2 partial of this CTA: slab 2*cta = a1_hi^T dy2, slab 2*cta + 1 = a1_lo^T dy2 (summed in fp64 by ec_slab_reduce)
     {
@@ -1126,7 +1115,12 @@ edgeconv2_bwd_ws_kernel(const float* __restrict__ UV, long long ldu, const int32
         ws_issue_gather(UV, ldu, g, k, kinv, nb, bt, sV, sU, fullV);
       }
       nb_next = (bt < TILE_M) ? fetch_neighbour(idx, tile + gridDim.x, num_tiles, PT, k, kinv, npts, P, bt) : 0;
+      if (bt == WS_BUILD_THREADS - 1) {
+        mma1(t);
+        if (t > 0) mma2(t - 1);
+      }
     }
+    if (bt == WS_BUILD_THREADS - 1 && n_my > 0) mma2(n_my - 1);
   }
   tc::fence_before();
   __syncthreads();
