@@ -100,11 +100,37 @@ def unnorm_xyz_model(out):
                ux_knn3=tk[2].astype(np.int16))
 
 
+def classification_model(out):
+    """Networks/dgcnn/models/dgcnn.py:20-109: the ModelNet classification DGCNN (get_model in inference mode on seeded variables
+    with non-trivial BN statistics and a non-identity input transform) and get_loss (label smoothing 0.2)."""
+    sys.path.insert(1, os.path.join(REF, "Networks/dgcnn/models"))
+    sys.path.insert(1, os.path.join(REF, "Networks/dgcnn/utils"))
+    sys.path.insert(1, HERE)
+    import dgcnn as network
+    from refgen_common import CLS_LAYERS, xavier_params
+    rng = np.random.default_rng(431)
+    B, N = 3, 160
+    X = rng.uniform(-1, 1, (B, N, 3)).astype(np.float32)
+    lab = rng.integers(0, 40, (B,)).astype(np.int32)
+    params0 = xavier_params(CLS_LAYERS, seed=432, tnet_seed=433)
+    tf.reset()
+    tf.preset_variables(params0)
+    Z, _ = network.get_model(tf.constant(X), tf.constant(False), bn_decay=None)
+    loss = network.get_loss(Z, tf.constant(lab), {})
+    tk = tf.RECORD["top_k"][-5:]
+    out.update(cls_X=X, cls_label=lab, cls_param_seed=np.array([432, 433]), cls_Z=_np(Z), cls_loss=_np(loss))
+    for i, t in enumerate(tk):
+        out["cls_knn%d" % i] = t.astype(np.int16)
+    missing = [k for k in tf.STATE["variables"] if k not in params0]
+    assert not missing, missing
+
+
 if __name__ == "__main__":
     out = {}
     smooth_variants(out)
     loss_module(out)
     unnorm_xyz_model(out)
+    classification_model(out)
     np.savez_compressed(os.path.join(HERE, "ref_util_variants.npz"), **out)
     for k, v in out.items():
         if v.size == 1:

@@ -13,6 +13,12 @@ SHAPENET_LAYERS = [("transform_net1/tconv1", 6, 64, True), ("transform_net1/tcon
                    ("adj_conv4", 64, 64, True), ("adj_conv5", 128, 64, True), ("adj_conv7", 192, 1024, True),
                    ("one_hot_label_expand", 16, 64, True), ("seg/conv1", 1280, 256, True), ("seg/conv2", 256, 256, True),
                    ("seg/conv3", 256, 128, True), ("seg/conv4", 128, 50, False)]
+# Networks/dgcnn/models/dgcnn.py:20-98 (classification net, non-dist batch norm: pop_* = EMA shadows)
+CLS_LAYERS = [("transform_net1/tconv1", 6, 64, True), ("transform_net1/tconv2", 64, 128, True),
+              ("transform_net1/tconv3", 128, 1024, True), ("transform_net1/tfc1", 1024, 512, True),
+              ("transform_net1/tfc2", 512, 256, True), ("dgcnn1", 6, 64, True), ("dgcnn2", 128, 64, True),
+              ("dgcnn3", 128, 64, True), ("dgcnn4", 128, 128, True), ("agg", 320, 1024, True), ("fc1", 1024, 512, True),
+              ("fc2", 512, 256, True), ("fc3", 256, 40, False)]
 MAX_KEEP = 8192          # gradient / weight tensors above this size are stored as a strided subsample
 
 

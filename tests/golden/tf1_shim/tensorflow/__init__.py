@@ -221,7 +221,15 @@ def Variable(initial_value, trainable=True, name=None, dtype=None):
         a = a.astype(_np.float32)
     elif a.dtype.kind in "iu":
         a = a.astype(_np.int32)
-    return _make_variable(name or "Variable_%d" % _VAR_COUNT[0], a, trainable)
+    if name is not None:      # named variables live under the enclosing scopes and honour presets (non-dist batch norm: beta, gamma)
+        full = "/".join(STATE["scope"] + [name])
+        if full in STATE["variables"]:
+            return STATE["variables"][full]
+        preset = STATE.get("preset", {})
+        if full in preset:
+            a = _np.asarray(preset[full], a.dtype).reshape(a.shape)
+        return _make_variable(full, a, trainable)
+    return _make_variable("Variable_%d" % _VAR_COUNT[0], a, trainable)
 
 
 def assign(ref, value):
@@ -263,6 +271,8 @@ def _xavier(shape):
 
 # ---------------------------------------------------------------------------------------- array ops
 def constant(value, dtype=None, shape=None, name=None):
+    if shape is not None and _np.ndim(value) == 0:        # tf.constant(0.0, shape=[C]) fills the shape
+        value = _np.full([_i(d) for d in shape], value, _np.float32 if isinstance(value, float) else None)
     return _t(value, dtype)
 
 
@@ -464,6 +474,24 @@ class _Math:
     equal = staticmethod(lambda a, b, name=None: _t(a) == b)
 
 
+def one_hot(indices, depth, on_value=1.0, off_value=0.0, axis=-1, dtype=float32, name=None):
+    return _torch.nn.functional.one_hot(_t(indices).long(), _i(depth)).to(dtype).as_subclass(Tensor)
+
+
+class _Losses:
+    @staticmethod
+    def softmax_cross_entropy(onehot_labels, logits, weights=1.0, label_smoothing=0, scope=None, **k):
+        """tf.losses.softmax_cross_entropy (TF 1.14): labels*(1-ls) + ls/num_classes, per-example CE, weights = 1 ->
+        reduction SUM_BY_NONZERO_WEIGHTS = mean over the batch"""
+        lab = _t(onehot_labels).to(logits.dtype)
+        if label_smoothing > 0:
+            lab = lab * (1 - label_smoothing) + label_smoothing / lab.shape[-1]
+        return (-(lab * _torch.log_softmax(_t(logits), dim=-1)).sum(-1)).mean().as_subclass(Tensor)
+
+
+losses = _Losses()
+
+
 math = _Math()     # noqa: A001  (shadows the stdlib name inside this module only after its last use above)
 
 
@@ -583,8 +611,25 @@ nn = _NN()
 
 # ----------------------------------------------------------------------------------------- tf.train
 class _EMA:
+    """tf.train.ExponentialMovingAverage as tf_util.batch_norm_template (:462-499) uses it: the shadow values of (batch_mean,
+    batch_var) are the population statistics read in inference mode.  They are kept under `<scope>/pop_mean`, `<scope>/pop_var`
+    (the names of the dist template, so one weight dictionary serves both).  Only the inference read is implemented."""
+
     def __init__(self, decay=None, **k):
-        raise NotImplementedError("tf1_shim: ExponentialMovingAverage (non-dist batch norm) is not on the hot path")
+        self.decay, self._reads = decay, 0
+
+    def apply(self, tensors):
+        raise NotImplementedError("tf1_shim: training-mode ExponentialMovingAverage (zero-debiased shadow update) is not modelled")
+
+    def average(self, tensor):
+        name = ("pop_mean", "pop_var")[self._reads % 2]       # batch_norm_template reads mean, then variance
+        self._reads += 1
+        full = "/".join(STATE["scope"] + [name])
+        if full not in STATE["variables"]:
+            preset = STATE.get("preset", {})
+            val = preset[full] if full in preset else (_np.zeros if name == "pop_mean" else _np.ones)(tensor.shape, _np.float32)
+            _make_variable(full, _np.asarray(val, _np.float32).reshape(tuple(tensor.shape)), False)
+        return STATE["variables"][full]
 
 
 class _Saver:

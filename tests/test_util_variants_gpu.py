@@ -99,3 +99,28 @@ def test_get_model_unnormxyz_matches_reference_code(cuda):
     Z2 = eng2.forward(X, False).cpu().numpy()
     assert np.abs(Z2 - G["ux_Z"]).max() > 10 * TOL * np.abs(G["ux_Z"]).max()
     assert hasattr(DGCNN_S3DIS, "get_model_unnormXYZ")
+
+
+def test_classification_dgcnn_matches_reference_code(cuda):
+    """Networks/dgcnn/models/dgcnn.py get_model / get_loss (the ModelNet classification net the trainers never build) against the
+    reference module run on the TF shim: inference mode, seeded variables with non-trivial BN statistics, non-identity T-net."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import refgen_common as rc
+    CLS_LAYERS = rc.CLS_LAYERS
+    from weaksuppointcloudseg_b200 import dgcnn, tf_util
+    params = rc.xavier_params(CLS_LAYERS, int(G["cls_param_seed"][0]), tnet_seed=int(G["cls_param_seed"][1]))
+    tf_util.VARIABLES.clear()
+    for name, a in params.items():
+        tf_util.VARIABLES[name] = torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    X = cu("cls_X")
+    Z, end_points = dgcnn.get_model(X, False, bn_decay=None)
+    assert tuple(Z.shape) == (X.shape[0], 40) and end_points == {}
+    ref = G["cls_Z"]
+    err = np.abs(Z.cpu().numpy() - ref).max() / np.abs(ref).max()
+    loss = float(dgcnn.get_loss(Z, cu("cls_label"), end_points))
+    print(f"classification DGCNN: logits {err:.2e}, loss {loss:.6f} vs {float(G['cls_loss']):.6f}")
+    # the four feature-space graphs are not teacher-forced here: a last-bit tie may swap one neighbour (App. A-2), hence 5e-3
+    assert err <= 5e-3, err
+    assert abs(loss - float(G["cls_loss"])) <= 5e-3 * abs(float(G["cls_loss"]))
+    tf_util.VARIABLES.clear()
