@@ -233,7 +233,8 @@ int wspc_cloud_colsum(const wspc_operand_t* G, int B, int N, float* S, wspc_stre
  * S3DIS_DGCNN_trainer.py:85-102,120-137 / ShapeNet_DGCNN_trainer.py:85-100,115-133;
  * Util/SmoothConstraint.py:155-165 (the kNN graph comes from wspc_knn_fused with WSPC_DIST_SMOOTH).
  *   Z (B,N,C) logits, Y (B,N,C) one-hot float, Mask (B,N); sm_idx/sm_dist (B,N,knn) or NULL
- *   full=1: loss = seg + siamese + inexact + smooth (ramp-up gate open); full=0: seg only ("Plain")
+ *   full=1: loss = seg + siamese + inexact + smooth (ramp-up gate open); full=0: seg only ("Plain");
+ *   full=2: all four VALUES, gradient of the seg term only (Full graph with the gate closed, S3DIS_DGCNN_trainer.py:100-102)
  *   P (B,N,C) softmax out; dZ (B,N,C) d loss / d Z (required if want_grad or full)
  *   losses[5] = {seg, siamese, inexact, smooth, total}            C <= 64 */
 size_t wspc_head_losses_workspace_bytes(int B, int N, int C);

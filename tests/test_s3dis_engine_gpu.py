@@ -59,7 +59,7 @@ def setup(cuda):
     losses = eng.train_step(Xd, Yd, Md, lr=1e-3, bn_decay=od.bn_decay(0, n_samples, 300000),
                             dropout_mask=torch.from_numpy(mask).to(cuda), knn_override=ov)
     torch.cuda.synchronize()
-    return dict(eng=eng, out=out, rec=rec, p=p, losses=losses.cpu().numpy(), X=X, params0=params)
+    return dict(eng=eng, out=out, rec=rec, p=p, losses=losses.cpu().numpy(), X=X, Y=Y, M=M, params0=params)
 
 
 def test_knn1_and_smooth_graph_bit_exact(setup):
@@ -158,6 +158,25 @@ def test_siamese_zero_for_identical_pairs(setup, cuda):
     l = eng.losses_and_grad(Y, M, full=True, want_grad=True).cpu().numpy()
     assert l[1] == 0.0
     assert l[3] >= 0.0
+
+
+def test_closed_gate_head_pass(setup, cuda):
+    """full=2 (Full graph, ramp-up gate closed, S3DIS_DGCNN_trainer.py:100-102): one head pass returns the four loss values
+    of the Full graph and exactly the Plain-style gradient."""
+    eng = setup["eng"]
+    X = torch.from_numpy(setup["X"]).to(cuda)
+    Y = torch.from_numpy(setup["Y"]).to(cuda)
+    M = torch.from_numpy(setup["M"]).to(cuda)
+    eng.forward(X, False)
+    l_full = eng.losses_and_grad(Y, M, full=True, want_grad=True).clone()
+    dz_full = eng.dZ.clone()
+    eng.losses_and_grad(Y, M, full=False, want_grad=True)
+    dz_plain = eng.dZ.clone()
+    eng.dZ.fill_(7.0)
+    l_closed = eng.losses_and_grad(Y, M, full=2, want_grad=True).clone()
+    assert torch.equal(eng.dZ, dz_plain)
+    assert float((dz_full - dz_plain).abs().max()) > 0
+    assert torch.allclose(l_closed[:4], l_full[:4], rtol=1e-6, atol=0)   # fp64 atomics: order-dependent last bit only
 
 
 def test_cfg4_stress_shape_properties(cuda):

@@ -202,22 +202,18 @@ class S3DIS_Trainer():
         Y = self._to_device('Y', seg_onehot_feed, side=True, after_forward=True)
         M = self._to_device('Mask', Mask_bin_feed, side=True, after_forward=True)
         torch.cuda.current_stream().wait_stream(self._copy_stream())
-        if full and not self.weak_gate:
-            # Full graph, gate closed: the weak terms are evaluated (and printed) but multiplied by 0 (:100-102)
-            eng.losses_and_grad(Y, M, full=True, want_grad=False)
-            weak = self._fetch_losses()
-            eng.losses_and_grad(Y, M, full=False, want_grad=True)
-        else:
-            weak = None
-            eng.losses_and_grad(Y, M, full=full, want_grad=True)
+        gate_closed = full and not self.weak_gate
+        # Full graph, gate closed: the weak terms are evaluated (and printed) but multiplied by 0 (:100-102) -- one head pass
+        # that returns all four values and differentiates the segmentation term only
+        eng.losses_and_grad(Y, M, full=2 if gate_closed else full, want_grad=True)
         zp = self._fetch_prob(side=True) if fetch_prob else None    # D2H of Z_prob overlaps the backward pass
         eng.backward()
         self._allreduce_and_step(lr)
         l = self._fetch_losses()          # synchronises the stream: the step is complete on return
         if fetch_prob:
             self._copy_stream().synchronize()
-        if weak is not None:
-            return float(l[0]), float(weak[1]), float(weak[2]), float(weak[3]), zp
+        if gate_closed:
+            return float(l[0]), float(l[1]), float(l[2]), float(l[3]), zp
         return float(l[4]), float(l[1]), float(l[2]), float(l[3]), zp
 
     def _fetch_losses(self):

@@ -53,19 +53,14 @@ class ShapeNet_Trainer(S3DIS_Trainer):
         lr, decay = self.get_learning_rate(), self.get_bn_decay()
         full = self.style == 'Full'
         eng.forward(X, Lb, True, decay, dropout_masks)
-        if full and not self.weak_gate:
-            eng.losses_and_grad(Y, M, full=True, want_grad=False)
-            weak = self._fetch_losses()
-            eng.losses_and_grad(Y, M, full=False, want_grad=True)
-        else:
-            weak = None
-            eng.losses_and_grad(Y, M, full=full, want_grad=True)
+        gate_closed = full and not self.weak_gate
+        eng.losses_and_grad(Y, M, full=2 if gate_closed else full, want_grad=True)       # gate closed: one pass, see S3DIS trainer
         eng.backward()
         self._allreduce_and_step(lr)
         zp = self._fetch_prob() if fetch_prob else None
         l = self._fetch_losses()
-        if weak is not None:
-            return float(l[0]), float(weak[1]), float(weak[2]), float(weak[3]), zp
+        if gate_closed:
+            return float(l[0]), float(l[1]), float(l[2]), float(l[3]), zp
         return float(l[4]), float(l[1]), float(l[2]), float(l[3]), zp
 
     def eval_batch(self, data_feed, label_onehot_feed, seg_onehot_feed, Mask_bin_feed):

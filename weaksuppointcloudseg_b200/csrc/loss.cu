@@ -284,6 +284,10 @@ extern "C" int wspc_head_losses(const float* Z, const float* Y, const float* Mas
   WSPC_REQUIRE(B >= 1 && N >= 1 && C >= 1 && C <= MAXC, "head_losses: bad shape (C <= %d)", MAXC);
   WSPC_REQUIRE(!full || (B % 2) == 0, "head_losses: Siamese pairs need an even batch (B=%d)", B);
   WSPC_REQUIRE(!want_grad || dZ, "head_losses: dZ is null");
+  WSPC_REQUIRE(full >= 0 && full <= 2, "head_losses: full must be 0 (Plain), 1 (Full) or 2 (Full values, seg-only gradient)");
+  // full == 2: the Full graph with its ramp-up gate closed (S3DIS_DGCNN_trainer.py:100-102): the weak terms are evaluated (the
+  // training loop prints them) but multiplied by 0, so only the segmentation term is differentiated -- in ONE pass
+  const bool grad_full = full == 1;
   const bool smooth = full && sm_idx && sm_dist && knn > 0;
   if (workspace_bytes < wspc_head_losses_workspace_bytes(B, N, C)) {
     set_error("head_losses: workspace too small");
@@ -298,7 +302,7 @@ extern "C" int wspc_head_losses(const float* Z, const float* Y, const float* Mas
   double* acc = reinterpret_cast<double*>(w + small);
   float* dP = reinterpret_cast<float*>(w + small + 256);
   WSPC_CUDA(cudaMemsetAsync(w, 0, small + 256, st));
-  if (smooth && want_grad) WSPC_CUDA(cudaMemsetAsync(dP, 0, (size_t)B * N * C * 4, st));
+  if (smooth && want_grad && grad_full) WSPC_CUDA(cudaMemsetAsync(dP, 0, (size_t)B * N * C * 4, st));
 
   const int nblk = (N + 7) / 8 < 64 ? (N + 7) / 8 : 64;
   head_softmax_kernel<<<dim3(nblk, B), 256, 0, st>>>(Z, Y, Mask, B, N, C, P, colmaxZ, colmaxY, acc);
@@ -313,7 +317,7 @@ extern "C" int wspc_head_losses(const float* Z, const float* Y, const float* Mas
     const long long pts = (long long)B * N;
     const float gscale = 1.f / (float)((double)C * B * N * knn);
     smooth_kernel<<<(unsigned)((pts + 7) / 8), 256, 0, st>>>(P, sm_idx, sm_dist, B, N, C, knn, gamma, gscale,
-                                                            want_grad ? dP : nullptr, acc);
+                                                            (want_grad && grad_full) ? dP : nullptr, acc);
     count_launch();
     WSPC_LAUNCH_CHECK("smooth_kernel");
   }
@@ -322,7 +326,7 @@ extern "C" int wspc_head_losses(const float* Z, const float* Y, const float* Mas
     // the loss values are wanted in Full style
     WSPC_REQUIRE(dZ, "head_losses: Full style needs a dZ buffer (also used as scratch)");
     const long long total = (long long)(B / 2) * N;
-    if (full) {
+    if (grad_full) {
       head_grad_kernel<<<(unsigned)((total + 7) / 8), 256, 0, st>>>(Z, P, Y, Mask, (smooth && want_grad) ? dP : nullptr,
                                                                    colmaxZ, colmaxY, tiecnt, B, N, C, siam_w, 1, dZ, acc);
     } else {
@@ -334,7 +338,7 @@ extern "C" int wspc_head_losses(const float* Z, const float* Y, const float* Mas
     count_launch();
     WSPC_LAUNCH_CHECK("head_grad_kernel");
   }
-  head_finalize_kernel<<<1, 256, 0, st>>>(colmaxZ, colmaxY, B, N, C, smooth ? knn : 0, siam_w, full, acc, losses);
+  head_finalize_kernel<<<1, 256, 0, st>>>(colmaxZ, colmaxY, B, N, C, smooth ? knn : 0, siam_w, full ? 1 : 0, acc, losses);
   count_launch();
   WSPC_LAUNCH_CHECK("head_finalize_kernel");
   return WSPC_OK;

@@ -215,7 +215,7 @@ class ShapeNetEngine:
         ws = L.workspace(L.lib().wspc_head_losses_workspace_bytes(B, N, C), self.dev, "head")
         L.check(L.lib().wspc_head_losses(L.ptr(self.Z), L.ptr(Y), L.ptr(Mask), L.ptr(self.idxS) if full else None,
                                          L.ptr(self.dS) if full else None, B, N, C, SMOOTH_KNN, SMOOTH_GAMMA, SIAMESE_W,
-                                         1 if full else 0, 1 if want_grad else 0, L.ptr(self.Zp), L.ptr(self.dZ),
+                                         int(full), 1 if want_grad else 0, L.ptr(self.Zp), L.ptr(self.dZ),
                                          L.ptr(self.losses), L.ptr(ws), ws.numel(), L.stream()))
         return self.losses
 
