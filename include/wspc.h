@@ -222,6 +222,19 @@ int wspc_maxk_bnrelu_bwd_stats(const float* y, const float* sc, const float* sh,
 /* g[b,c] = max_n relu(bn(y[b,n,c])), amax = first arg-max  == tf_util.max_pool2d([N,1]) (tf_util.py:357-380) */
 int wspc_maxn_bnrelu_fwd(const float* y, const float* sc, const float* sh, int B, int N, int C, float* g,
                          int32_t* amax, wspc_stream_t stream);
+/* conv2d 1x1 -> BN -> ReLU -> max_pool2d([N,1]) (adj_conv7 + the global feature, DGCNN_S3DIS.py:80-85) WITHOUT writing the
+ * (M, N) conv output: one pass of the warp-specialised tcgen05 GEMM accumulates the BN sums into `stats` (2, N; the caller
+ * zeroes them) and, per (cloud, column), a packed key (order-preserving bits of y or -y | ~row) of the row with the largest
+ * (gamma >= 0) or smallest (gamma < 0) pre-BN value -- BN and ReLU are monotone per column, so that row is max_pool2d's first
+ * arg-max.  `keys` is (M / npts, N) and is cleared by the call.  wspc_conv1x1_pool_supported says whether a shape is eligible
+ * (K > 128, K % 32 == 0, npts % 128 == 0, >= 592 row tiles); otherwise run wspc_conv1x1_rows + wspc_maxn_bnrelu_fwd.
+ * workspace: wspc_conv1x1_rows_workspace_bytes(N, K).  wspc_maxn_from_keys then gives g = relu(bn(y*)), amax and y* (B, C). */
+int wspc_conv1x1_pool_supported(long long M, int N, int K, int npts);
+int wspc_conv1x1_pool_fwd(const wspc_operand_t* A, int a_mode, const float* W, long long ldw, long long M, int N, int K,
+                          int npts, const float* bias, const float* gamma, double* stats, unsigned long long* keys,
+                          void* workspace, size_t workspace_bytes, wspc_stream_t stream);
+int wspc_maxn_from_keys(const unsigned long long* keys, const float* gamma, const float* sc, const float* sh, int B, int C,
+                        float* g, int32_t* amax, float* ymax, wspc_stream_t stream);
 /* dg = dgin*[g>0]; stats (2,C) = (sum, sum*y at the arg-max rows): the sparse gradient of max_pool2d */
 int wspc_maxn_bwd_gate(const float* g, const float* dgin, const int32_t* amax, const float* y, int B, int N, int C,
                        float* dg, double* stats, wspc_stream_t stream);

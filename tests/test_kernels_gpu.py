@@ -294,6 +294,127 @@ def test_rows_gemm_chunked_shapes(cuda, gemm_path, K, N, kind):
         assert rel(out, out0 + dy @ Wl.double().T) <= _tol(gemm_path)
 
 
+@pytest.mark.parametrize("K,N,kind", [(192, 1024, "plain_stats_rowbias"), (192, 512, "plain_stats_rowbias"),
+                                      (512, 256, "bnrelu_stats"), (256, 512, "dy_relumask_drop"), (512, 192, "dy_store"),
+                                      (160, 320, "bnrelu_stats"), (256, 256, "dy_plain_store")])
+def test_rows_gemm_warp_specialised(cuda, K, N, kind):
+    """per-point layers at training size (>= 592 row tiles, K > 128 in 32-channel chunks): the warp-specialised kernel
+    (cp.async operand ring, MMA issue off the epilogue warps, two TMEM accumulators).  Ragged last tile, several column
+    tiles, every operand map / epilogue it takes over from the serial kernel."""
+    from weaksuppointcloudseg_b200 import _lib as L, runtime as rt
+    g = torch.Generator(device="cuda").manual_seed(11)
+    Bc, Np = 19, 4001
+    M = Bc * Np                                                      # 76019 rows: 593.9 tiles
+    W = torch.randn((K, N), device=cuda, generator=g) * 0.1
+    out = torch.full((M, N), 3.0, device=cuda)
+    tol = 2e-4                                                       # bf16 x 3 split, as _tol(0)
+    if kind == "plain_stats_rowbias":
+        a = torch.randn((M, K), device=cuda, generator=g)
+        b = torch.randn(N, device=cuda, generator=g)
+        rb = torch.randn((Bc, N), device=cuda, generator=g)
+        stats = torch.zeros((2, N), dtype=torch.float64, device=cuda)
+        A = (L.Operand(p=a.data_ptr(), ld=K, C=K), L.OP_PLAIN)
+        epi = L.Epilogue(out=out.data_ptr(), ldo=N, bias=b.data_ptr(), rowbias=rb.data_ptr(), rb_rows=Np, ldrb=N,
+                         stats=stats.data_ptr())
+        rt.rows_gemm(A, W, N, 0, M, N, K, epi, L.EPI_STORE_STATS)
+        ref = a.double() @ W.double() + b.double() + rb.double().repeat_interleave(Np, 0)
+        assert rel(out, ref) <= tol
+        assert rel(stats[0], out.double().sum(0)) <= 1e-6 and rel(stats[1], (out.double() ** 2).sum(0)) <= 1e-6
+    elif kind == "bnrelu_stats":
+        y = torch.randn((M, K), device=cuda, generator=g)
+        sc = torch.rand(K, device=cuda, generator=g) + 0.5
+        sh = torch.randn(K, device=cuda, generator=g) * 0.2
+        b = torch.randn(N, device=cuda, generator=g)
+        stats = torch.zeros((2, N), dtype=torch.float64, device=cuda)
+        A = (L.Operand(p=y.data_ptr(), ld=K, C=K, sc=sc.data_ptr(), sh=sh.data_ptr()), L.OP_BNRELU)
+        rt.rows_gemm(A, W, N, 0, M, N, K, L.Epilogue(out=out.data_ptr(), ldo=N, bias=b.data_ptr(), stats=stats.data_ptr()),
+                     L.EPI_STORE_STATS)
+        ref = torch.relu(y.double() * sc.double() + sh.double()) @ W.double() + b.double()
+        assert rel(out, ref) <= tol
+        assert rel(stats[0], out.double().sum(0)) <= 1e-6 and rel(stats[1], (out.double() ** 2).sum(0)) <= 1e-6
+    else:
+        G = torch.randn((M, K), device=cuda, generator=g)
+        y = torch.randn((M, K), device=cuda, generator=g)
+        Wl = torch.randn((N, K), device=cuda, generator=g) * 0.1          # layer weight (Cin=N, Cout=K)
+        if kind == "dy_plain_store":
+            A = (L.Operand(p=G.data_ptr(), ld=K, C=K), L.OP_DY)
+            dy = G.double()
+        else:
+            c1, c2, c3 = (torch.randn(K, device=cuda, generator=g) * 0.5 for _ in range(3))
+            A = (L.Operand(p=G.data_ptr(), ld=K, C=K, y=y.data_ptr(), ldy=K, c1=c1.data_ptr(), c2=c2.data_ptr(),
+                           c3=c3.data_ptr()), L.OP_DY)
+            dy = c1.double() * G.double() + c2.double() + c3.double() * y.double()
+        if kind == "dy_relumask_drop":
+            yprev = torch.randn((M, N), device=cuda, generator=g)
+            scp = torch.rand(N, device=cuda, generator=g) + 0.5
+            shp = torch.randn(N, device=cuda, generator=g) * 0.3
+            dm = torch.floor(0.7 + torch.rand((M, N), device=cuda, generator=g))
+            stats = torch.zeros((2, N), dtype=torch.float64, device=cuda)
+            epi = L.Epilogue(out=out.data_ptr(), ldo=N, stats=stats.data_ptr(), yprev=yprev.data_ptr(), ldyp=N,
+                             scp=scp.data_ptr(), shp=shp.data_ptr(), dmask=dm.data_ptr(), dscale=1 / 0.7)
+            rt.rows_gemm(A, Wl, K, 1, M, N, K, epi, L.EPI_RELUMASK_STATS)
+            on = torch.addcmul(shp, yprev, scp) > 0
+            ref = (dy @ Wl.double().T) * on * dm.double() / 0.7
+            bad = (out.double() - ref).abs() > tol * ref.abs().max()
+            near0 = (yprev.double() * scp.double() + shp.double()).abs() < 1e-6
+            assert int((bad & ~near0).sum()) == 0
+            assert rel(stats[0], out.double().sum(0)) <= 1e-6
+            assert rel(stats[1], (out.double() * yprev.double()).sum(0)) <= 1e-6
+        else:
+            rt.rows_gemm(A, Wl, K, 1, M, N, K, L.Epilogue(out=out.data_ptr(), ldo=N), L.EPI_STORE)
+            assert rel(out, dy @ Wl.double().T) <= tol
+
+
+@pytest.mark.parametrize("Bc,Np,K,N", [(20, 3840, 192, 1024), (38, 2048, 256, 320)])
+def test_conv_pool_forward_fused(cuda, Bc, Np, K, N):
+    """adj_conv7 + max_pool2d([N,1]) in one pass (wspc_conv1x1_pool_fwd + wspc_maxn_from_keys): BN sums, pooled activation,
+    arg-max rows and the pre-BN value at the arg-max against the unfused definition, with negative BN scales (the pooled row is
+    then the column MINIMUM) and a tie (duplicated points: the first row wins, as max_pool2d's gradient does)."""
+    import ctypes
+    from weaksuppointcloudseg_b200 import _lib as L
+    g = torch.Generator(device="cuda").manual_seed(5)
+    M = Bc * Np
+    assert L.lib().wspc_conv1x1_pool_supported(M, N, K, Np) == 1
+    assert L.lib().wspc_conv1x1_pool_supported(M, N, K, Np - 64) == 0          # tiles would straddle clouds
+    a = torch.randn((M, K), device=cuda, generator=g)
+    a[5 * Np + 77] = a[5 * Np + 3]                                            # duplicated point inside cloud 5
+    W = torch.randn((K, N), device=cuda, generator=g) * 0.1
+    b = torch.randn(N, device=cuda, generator=g)
+    gamma = torch.randn(N, device=cuda, generator=g)
+    gamma[::7] = -gamma[::7].abs()
+    stats = torch.zeros((2, N), dtype=torch.float64, device=cuda)
+    keys = torch.empty((Bc, N), dtype=torch.int64, device=cuda)
+    nbytes = L.lib().wspc_conv1x1_rows_workspace_bytes(N, K)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=cuda)
+    A = L.Operand(p=a.data_ptr(), ld=K, C=K)
+    L.check(L.lib().wspc_conv1x1_pool_fwd(ctypes.byref(A), L.OP_PLAIN, L.ptr(W), N, M, N, K, Np, L.ptr(b), L.ptr(gamma),
+                                          L.ptr(stats), L.ptr(keys), L.ptr(ws), ws.numel(), L.stream()))
+    y = (a.double() @ W.double() + b.double())
+    assert rel(stats[0], y.sum(0)) <= 2e-5 and rel(stats[1], (y ** 2).sum(0)) <= 2e-5
+    mean, var = y.mean(0), y.var(0, unbiased=False)
+    sc = (gamma.double() / torch.sqrt(var + 1e-3)).float()
+    sh = (-mean * sc.double()).float()
+    gout = torch.empty((Bc, N), device=cuda)
+    amax = torch.empty((Bc, N), dtype=torch.int32, device=cuda)
+    ymax = torch.empty((Bc, N), device=cuda)
+    L.check(L.lib().wspc_maxn_from_keys(L.ptr(keys), L.ptr(gamma), L.ptr(sc), L.ptr(sh), Bc, N, L.ptr(gout), L.ptr(amax),
+                                        L.ptr(ymax), L.stream()))
+    y3 = y.view(Bc, Np, N)
+    act = torch.relu(y3 * sc.double() + sh.double())
+    assert rel(gout, act.max(1).values) <= 2e-4
+    assert int(amax.min()) >= 0 and int(amax.max()) < Np
+    picked = torch.gather(y3, 1, amax.long().unsqueeze(1)).squeeze(1)
+    assert rel(ymax, picked) <= 2e-4                                          # the reported value is the one at the reported row
+    ext = torch.where(gamma >= 0, y3.max(1).values, y3.min(1).values)
+    assert float(((picked - ext).abs() / y.abs().max()).max()) <= 2e-4        # ... and it is the column extreme
+    # tie: wherever the duplicated pair holds the extreme, the earlier row is reported
+    dup = (amax[5] == 77)
+    assert int(dup.sum()) == 0
+    with pytest.raises(Exception):
+        L.check(L.lib().wspc_conv1x1_pool_fwd(ctypes.byref(A), L.OP_PLAIN, L.ptr(W), N, M, N, K, Np - 64, L.ptr(b), L.ptr(gamma),
+                                              L.ptr(stats), L.ptr(keys), L.ptr(ws), ws.numel(), L.stream()))
+
+
 # ---- narrow heads (seg/conv3 of the S3DIS net: 256 -> 13, DGCNN_S3DIS.py:100-101) ------------------------------------
 @pytest.mark.parametrize("K,N,dropout", [(256, 13, True), (128, 16, False), (64, 9, False)])
 def test_narrow_head_forward(cuda, gemm_path, K, N, dropout):

@@ -145,6 +145,10 @@ _EXTRA_DECLS.update({
     "wspc_edge_combine_bwd_maxk": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_longlong, c_int, c_int, c_int, _P, c_longlong, _P]),
     "wspc_maxn_bnrelu_fwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P, _P]),
     "wspc_maxn_bwd_gate": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P]),
+    "wspc_conv1x1_pool_supported": (c_int, [c_longlong, c_int, c_int, c_int]),
+    "wspc_conv1x1_pool_fwd": (c_int, [_OPP, c_int, _P, c_longlong, c_longlong, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_size_t,
+                                      _P]),
+    "wspc_maxn_from_keys": (c_int, [_P, _P, _P, _P, c_int, c_int, _P, _P, _P, _P]),
     "wspc_cloud_colsum": (c_int, [_OPP, c_int, c_int, _P, _P]),
     "wspc_head_losses_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "wspc_head_losses": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_int, _P, _P,

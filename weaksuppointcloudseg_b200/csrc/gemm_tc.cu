@@ -18,6 +18,8 @@
 #include "operand.cuh"
 #include <cuda_bf16.h>
 #include <type_traits>
+#include <cstdlib>
+#include <cstring>
 
 namespace wspc {
 void count_launch(int n = 1);
@@ -788,6 +790,493 @@ bool tc_supported(const Operand& A, int amode, const float* Bm, long long M, int
   return true;
 }
 
+// ------------------------------------------------------------------ warp-specialised row GEMM (chunked K, P-row layers) ---
+// The kernel above runs "synthesise A -> MMA -> epilogue" one after the other inside a CTA.  For the per-point layers
+// (K = 192 ... 512 in 64-channel chunks, 256-column tiles) that leaves the tensor pipe at 12-21 % and HBM at ~1.5 TB/s
+// (profiles/r1_gemm_summary.md).  Here one persistent CTA per SM splits the roles:
+//   * warps 0-7  (producers): every thread streams ITS OWN 2 rows x 8 channels of each 32-channel chunk into a private
+//     shared-memory slot with cp.async (64 KB in flight per SM, no registers held, no cross-thread hand-over), then
+//     applies the operand map (BN+ReLU / BN-backward affine), splits into bf16 hi + lo and writes the UMMA image of a
+//     2-stage ring; thread 255 issues the chunk's 6 tcgen05.mma (hi*hi + lo*hi + hi*lo) and refills the 2-stage ring of
+//     pre-split weight chunks (wprep_kernel image) with one bulk copy per chunk;
+//   * warps 8-15 (epilogue): read the finished 128 x <=256 accumulator (two TMEM accumulators alternate, so the next
+//     tile's MMAs run under this tile's epilogue), stage 64-column passes and store coalesced with the fused epilogue.
+constexpr int WS_THREADS = 544;                 // 8 producer warps + 8 epilogue warps + 1 MMA / weight-copy warp
+constexpr int WS_PROD = 256;
+constexpr int WS_EPI = 256;
+constexpr int WS_KC = 32;                       // channels per ring stage
+constexpr int WS_NA = 2;                        // operand-image ring
+constexpr int WS_NB_1 = 3, WS_NB_2 = 2;          // weight-chunk ring: one-operand maps / OP_DY (two operand streams to land)
+constexpr int WS_AGRP = TILE_M * 16 + 32;       // image group stride: 4 groups x 2 rows per quarter-warp hit 8 distinct 16-B banks
+constexpr int WS_RAW_BYTES_1 = 48 * 1024;       // cp.async landing slots (thread-private): 3 chunks of one operand in flight
+constexpr int WS_RAW_BYTES_2 = 64 * 1024;       // ... or 2 chunks of OP_DY's two operands
+constexpr int WS_STAGE_LD = 36;                 // epilogue staging pitch (floats): float4 rows land on distinct banks
+
+struct WsSmem {
+  int b_group_bytes;
+  uint32_t bstage;
+  size_t off_raw, off_a, off_b, off_stage, off_bar, total;
+};
+__host__ __device__ inline WsSmem ws_smem_plan(int NtMax, bool two_ops) {
+  WsSmem s;
+  const int Npad = (NtMax + 15) / 16 * 16;
+  s.b_group_bytes = Npad * 16 + 16;
+  s.bstage = 2u * (WS_KC / 8) * (uint32_t)s.b_group_bytes;      // [hi | lo] of one chunk, as wprep_kernel writes it
+  size_t o = 0;
+  s.off_raw = o; o += two_ops ? WS_RAW_BYTES_2 : WS_RAW_BYTES_1;
+  s.off_a = o; o += (size_t)WS_NA * 2 * (WS_KC / 8) * WS_AGRP;
+  s.off_b = o; o += ((size_t)(two_ops ? WS_NB_2 : WS_NB_1) * s.bstage + 127) / 128 * 128;
+  s.off_stage = o; o += (size_t)8 * 32 * WS_STAGE_LD * 4;      // one 32 x 32 staging tile per epilogue warp
+  s.off_bar = o; o += 256;
+  s.total = o;
+  return s;
+}
+
+// order-preserving map float -> uint32 (and back) for the packed (value, row) keys of EPI_STATS_POOL
+__host__ __device__ __forceinline__ uint32_t f32_ordered(float f) {
+#ifdef __CUDA_ARCH__
+  const uint32_t u = __float_as_uint(f);
+#else
+  uint32_t u; memcpy(&u, &f, 4);
+#endif
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
+
+template <int AMODE, int EMODE, int MAXPASS>
+__global__ void __launch_bounds__(WS_THREADS, 1)
+rowgemm_ws_kernel(const Operand A, long long M, int N, int K, const Epilogue E, int num_tiles, int NtMax, int ntn,
+                  const unsigned char* __restrict__ wimg, int dbg) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int NOPS = (AMODE == OP_DY) ? 2 : 1;
+  constexpr int WS_NB = (NOPS == 2) ? WS_NB_2 : WS_NB_1;
+  const WsSmem sp = ws_smem_plan(NtMax, NOPS == 2);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sp.off_bar);
+  uint64_t *fullA = bars, *emptyA = bars + 2, *fullB = bars + 4, *emptyB = bars + 8, *accFull = bars + 12, *accEmpty = bars + 14;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nkc = K / WS_KC;
+  // CTA -> (column tile ny, every tstride-th row tile): neighbouring CTAs work on the same rows at the same time (the A rows
+  // of the second column tile come from L2) and a CTA's BN statistics stay with fixed columns
+  const int ny = blockIdx.x % ntn, tile0 = blockIdx.x / ntn, tstride = gridDim.x / ntn;
+  const int n_items = (num_tiles > tile0) ? (num_tiles - tile0 + tstride - 1) / tstride : 0;
+  const int n0 = ny * NtMax;
+  const int Nt = (N - n0 < NtMax) ? (N - n0) : NtMax;
+  const int Ntp = (Nt + 15) / 16 * 16;
+  // every CTA walks the K chunks of a tile in its own rotation: all SMs fetching the SAME 33 KB weight chunk at the same time
+  // concentrates 148 readers on the few L2 slices that hold it (measured: the MMA thread waited on the weight ring 2/3 of the time)
+  const int rot = (int)(blockIdx.x / ntn) % nkc;
+
+  if (warp == 8) tc_alloc(tmem_slot, 512u);
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(fullB + i, 1);
+      mbar_init(emptyB + i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(fullA + i, WS_PROD / 32);          // one arrival per producer warp
+      mbar_init(emptyA + i, 1);
+      mbar_init(accFull + i, 1);
+      mbar_init(accEmpty + i, WS_EPI / 32);
+    }
+    mbar_fence_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (tid < WS_PROD) {
+    // ======================================================================== producers =====
+    constexpr int DEPTH = (NOPS == 2 ? WS_RAW_BYTES_2 : WS_RAW_BYTES_1) / (NOPS * 4 * WS_PROD * 16);   // chunks in flight: 3 / 2
+    const int kg = tid & 3, rr = tid >> 2;                              // channel group of the chunk; rows rr, rr + 64
+    unsigned char* raw = smem + sp.off_raw;
+    auto slot = [&](int d, int piece) { return raw + ((size_t)(d * (NOPS * 4) + piece) * WS_PROD + tid) * 16; };
+    const bool two_ops = (AMODE == OP_DY) && A.c1 != nullptr;
+    const int Q = n_items * nkc;
+    // fetch cursor: chunk index inside the tile (already rotated) and the thread's first row of the tile
+    int f_kc = rot, f_left = nkc;
+    long long f_row = (long long)tile0 * TILE_M + rr;
+    const long long row_step = (long long)tstride * TILE_M;
+    auto issue = [&](int q) {
+      if (q < Q) {
+        const int c0 = f_kc * WS_KC + kg * 8;
+        const int d = q % DEPTH;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const long long row = f_row + 64 * i;
+          if (row < M) {
+            const float* src = A.p + row * A.ld + c0;
+            cp_async16(slot(d, i * 2), src);
+            cp_async16(slot(d, i * 2 + 1), src + 4);
+            if (NOPS == 2 && two_ops) {
+              const float* sy = A.y + row * A.ldy + c0;
+              cp_async16(slot(d, 4 + i * 2), sy);
+              cp_async16(slot(d, 4 + i * 2 + 1), sy + 4);
+            }
+          }
+        }
+        if (++f_kc == nkc) f_kc = 0;
+        if (--f_left == 0) { f_left = nkc; f_row += row_step; }
+      }
+      cp_async_commit();
+    };
+#pragma unroll
+    for (int d = 0; d < DEPTH; ++d) issue(d);
+    const uint32_t a_bytes_half = (WS_KC / 8) * WS_AGRP;
+    unsigned char* const a_img = smem + sp.off_a + (size_t)kg * WS_AGRP;
+    // consume cursor
+    int b_kc = rot, b_left = nkc;
+    long long b_row = (long long)tile0 * TILE_M + rr;
+    // one chunk: raw slot -> operand map -> bf16 hi / lo image of ring stage s
+    auto build = [&](int q, int s, int kcr, long long row_a) {
+      const int cg = kcr * (WS_KC / 8) + kg;
+      float pc0[8], pc1[8], pc2[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { pc0[i] = 0.f; pc1[i] = 0.f; pc2[i] = 0.f; }
+      if (AMODE == OP_BNRELU) { ld8(A.sc + cg * 8, pc0); ld8(A.sh + cg * 8, pc1); }
+      if (AMODE == OP_DY && two_ops) { ld8(A.c1 + cg * 8, pc0); ld8(A.c2 + cg * 8, pc1); ld8(A.c3 + cg * 8, pc2); }
+      RawChunk w[2];
+      const int d = q % DEPTH;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float4 a0 = *reinterpret_cast<const float4*>(slot(d, i * 2));
+        const float4 a1 = *reinterpret_cast<const float4*>(slot(d, i * 2 + 1));
+        w[i].a[0] = a0.x; w[i].a[1] = a0.y; w[i].a[2] = a0.z; w[i].a[3] = a0.w;
+        w[i].a[4] = a1.x; w[i].a[5] = a1.y; w[i].a[6] = a1.z; w[i].a[7] = a1.w;
+        if (NOPS == 2) {
+          const float4 b0 = *reinterpret_cast<const float4*>(slot(d, 4 + i * 2));
+          const float4 b1 = *reinterpret_cast<const float4*>(slot(d, 4 + i * 2 + 1));
+          w[i].b[0] = b0.x; w[i].b[1] = b0.y; w[i].b[2] = b0.z; w[i].b[3] = b0.w;
+          w[i].b[4] = b1.x; w[i].b[5] = b1.y; w[i].b[6] = b1.z; w[i].b[7] = b1.w;
+        }
+      }
+      unsigned char* a_hi = a_img + (size_t)s * 2 * a_bytes_half;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const long long row = row_a + 64 * i;
+        float v[8];
+        finish_chunk<AMODE>(A, row, cg, row < M, 0, 0, pc0, pc1, pc2, w[i], v);
+        uint4 hi, lo;
+        split8(v, hi, lo);
+        *reinterpret_cast<uint4*>(a_hi + (rr + 64 * i) * 16) = hi;
+        *reinterpret_cast<uint4*>(a_hi + a_bytes_half + (rr + 64 * i) * 16) = lo;
+      }
+    };
+    auto advance = [&]() {
+      if (++b_kc == nkc) b_kc = 0;
+      if (--b_left == 0) { b_left = nkc; b_row += row_step; }
+    };
+#pragma unroll 1
+    for (int q = 0; q < ((dbg & 8) ? 0 : Q); ++q) {
+      const int s = q & 1;
+      cp_async_wait<DEPTH - 1>();
+      if (lane == 0) mbar_wait(emptyA + s, ((uint32_t)(q >> 1) & 1u) ^ 1u);   // the MMAs that read this stage two chunks ago retired
+      __syncwarp();
+      build(q, s, b_kc, b_row);
+      advance();
+      // one release-arrival per warp; the generic -> async proxy fence is executed by the MMA thread after its acquire (a
+      // fence.proxy.async here would also wait for this thread's cp.async prefetches)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(fullA + s);
+      issue(q + DEPTH);                                                 // refill the slot just consumed
+    }
+    cp_async_wait<0>();
+  } else if (tid >= WS_PROD + WS_EPI) {
+    // ================================================================ MMA issue + weight ring =====
+    if (lane == 0) {
+      const uint32_t bstage = sp.bstage;
+      unsigned char* sB = smem + sp.off_b;
+      const unsigned char* wsrc = wimg + (size_t)ny * nkc * bstage;     // this CTA's column tile: chunk kc at wsrc + kc*bstage
+      const int Q = n_items * nkc;
+      for (int c = 0; c < WS_NB && c < Q; ++c) {
+        mbar_expect_tx(fullB + c, bstage);
+        bulk_g2s(sB + (size_t)c * bstage, wsrc + (size_t)((c + rot) % nkc) * bstage, bstage, fullB + c);
+      }
+      const uint32_t idesc = umma_idesc(Ntp);
+      const uint32_t a_bytes_half = (WS_KC / 8) * WS_AGRP;
+      int item = 0, kc = 0;
+#pragma unroll 1
+      for (int q = 0; q < Q; ++q) {
+        const int s = q & 1, acc = item & 1, sb = q % WS_NB;
+        if (kc == 0) mbar_wait(accEmpty + acc, ((uint32_t)(item >> 1) & 1u) ^ 1u);   // the epilogue drained this accumulator
+        if (!(dbg & 2)) mbar_wait(fullB + sb, (uint32_t)(q / WS_NB) & 1u);
+        if (!(dbg & 1)) mbar_wait(fullA + s, (uint32_t)(q >> 1) & 1u);
+        fence_proxy_async_smem();
+        tc_fence_after();
+        const uint32_t ah = smem_u32(smem + sp.off_a + (size_t)s * 2 * a_bytes_half), al = ah + a_bytes_half;
+        const uint32_t bh = smem_u32(sB + (size_t)sb * bstage), bl = bh + (WS_KC / 8) * (uint32_t)sp.b_group_bytes;
+        const uint32_t dcol = tmem_base + (uint32_t)acc * 256u;
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t ab = (pass == 1) ? al : ah;
+          const uint32_t bb = (pass == 2) ? bl : bh;
+#pragma unroll
+          for (int kk = 0; kk < WS_KC / 16; ++kk) {
+            const uint64_t ad = umma_desc(ab + (uint32_t)(2 * kk) * WS_AGRP, WS_AGRP, 128);
+            const uint64_t bd = umma_desc(bb + (uint32_t)(2 * kk) * sp.b_group_bytes, sp.b_group_bytes, 128);
+            tc_mma_bf16(dcol, ad, bd, idesc, (kc | pass | kk) ? 1u : 0u);
+          }
+        }
+        tc_commit(emptyA + s);
+        tc_commit(emptyB + sb);
+        if (kc == nkc - 1) tc_commit(accFull + acc);
+        const int c = q + WS_NB - 1;                                    // weight chunk q+NB-1 goes where chunk q-1 was
+        if (c >= WS_NB && c < Q && !(dbg & 2)) {
+          const int cs = c % WS_NB;
+          mbar_wait(emptyB + cs, ((uint32_t)(c / WS_NB) & 1u) ^ 1u);
+          mbar_expect_tx(fullB + cs, bstage);
+          bulk_g2s(sB + (size_t)cs * bstage, wsrc + (size_t)((c + rot) % nkc) * bstage, bstage, fullB + cs);
+        }
+        if (++kc == nkc) { kc = 0; ++item; }
+      }
+    }
+  } else {
+    // ========================================================================= epilogue =====
+    // Every warp drains its own 32-row x 128-column part of the accumulator in 32 x 32 blocks through a warp-private
+    // staging tile (TMEM lane = row -> shared -> 4 rows x 128 B per store instruction): no block-wide barrier anywhere, so
+    // the eight warps drift apart and hide each other's TMEM / store latencies.
+    const int et = tid - WS_PROD, ew = et >> 5;
+    const int lq = ew & 3, chh = ew >> 2;         // TMEM lane quadrant (hardware warp id % 4) / 128-column half of the tile
+    float* stage_w = reinterpret_cast<float*>(smem + sp.off_stage) + ew * (32 * WS_STAGE_LD);
+    const int sr = lane >> 3, cq = lane & 7;      // store phase: sub-row within a group of 4 rows, 4-column group
+    constexpr bool kStats = (EMODE == EPI_STORE_STATS || EMODE == EPI_RELUMASK_STATS || EMODE == EPI_STATS_POOL);
+    constexpr int NBLK = 4;
+    double st0[kStats ? NBLK : 1][4], st1[kStats ? NBLK : 1][4];
+    if (kStats) {
+#pragma unroll
+      for (int p = 0; p < NBLK; ++p)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { st0[p][j] = 0.0; st1[p][j] = 0.0; }
+    }
+    int last_blk = -1;                            // last 32-column block of this warp's half that holds columns
+#pragma unroll
+    for (int nb = 0; nb < NBLK; ++nb)
+      if (chh * 128 + nb * 32 < Nt) last_blk = nb;
+#pragma unroll 1
+    for (int item = 0; item < n_items; ++item) {
+      const long long row0 = (long long)(tile0 + item * tstride) * TILE_M;
+      const int acc = item & 1;
+      if (lane == 0) mbar_wait(accFull + acc, (uint32_t)(item >> 1) & 1u);
+      __syncwarp();
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(lq * 32) << 16);
+      if (last_blk < 0) {                         // this warp's column half is empty: nothing to read, hand the accumulator back
+        if (lane == 0) mbar_arrive(accEmpty + acc);
+        continue;
+      }
+      long long rb_cloud0 = 0;
+      uint32_t rb_rem0 = 0;
+      if ((EMODE == EPI_STORE || EMODE == EPI_STORE_STATS) && E.rowbias) {
+        rb_cloud0 = div_pos(row0, E.rb_rows);
+        rb_rem0 = (uint32_t)(row0 - rb_cloud0 * E.rb_rows);
+      }
+#pragma unroll
+      for (int nb = 0; nb < NBLK; ++nb) {
+        const int c0 = chh * 128 + nb * 32;       // first column of the block inside this N tile
+        if (c0 >= Nt) break;
+        {
+          float v[32];
+          tc_ld32(tacc + (uint32_t)c0, v);
+          float* srow = stage_w + lane * WS_STAGE_LD;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(srow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
+        if (nb == last_blk) {                     // every tcgen05.ld of this warp on the accumulator has completed: hand it back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(accEmpty + acc);
+        }
+        __syncwarp();
+        const int cl = c0 + cq * 4;               // column within this N tile
+        const int cbase = n0 + cl;                // global column
+        if (cl < Nt && !(dbg & 4)) {
+          float bias[4] = {0.f, 0.f, 0.f, 0.f}, scp[4] = {0.f, 0.f, 0.f, 0.f}, shp[4] = {-1.f, -1.f, -1.f, -1.f};
+          if ((EMODE == EPI_STORE || EMODE == EPI_STORE_STATS || EMODE == EPI_STATS_POOL) && E.bias) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bias[j] = E.bias[cbase + j];
+          }
+          if (EMODE == EPI_RELUMASK_STATS) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { scp[j] = E.scp[cbase + j]; shp[j] = E.shp[cbase + j]; }
+          }
+          float f0[4] = {0.f, 0.f, 0.f, 0.f}, f1[4] = {0.f, 0.f, 0.f, 0.f};
+          const int rbase = lq * 32 + sr;         // tile-local row of iteration 0; + 4 per iteration
+          if (EMODE == EPI_STATS_POOL) {
+            // BN (gamma * invstd > 0 or < 0) and ReLU are monotone per column: the pooled maximum over the cloud's points sits at
+            // the row with the largest (gamma >= 0) or smallest (gamma < 0) pre-BN value; first row on ties (max_pool2d's arg-max)
+            float sgn[4], best[4];
+            int brow[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { sgn[j] = (E.scp[cbase + j] < 0.f) ? -1.f : 1.f; best[j] = -INFINITY; }
+            const uint32_t rin0 = (uint32_t)(row0 % E.npts);              // tiles never straddle clouds (npts % 128 == 0)
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int r = rbase + 4 * it;
+              if (row0 + r >= M) break;
+              const float4 s4 = *reinterpret_cast<const float4*>(stage_w + (it * 4 + sr) * WS_STAGE_LD + cq * 4);
+              const float o[4] = {s4.x + bias[0], s4.y + bias[1], s4.z + bias[2], s4.w + bias[3]};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                f0[j] += o[j];
+                f1[j] = fmaf(o[j], o[j], f1[j]);
+                const float ys = o[j] * sgn[j];
+                if (ys > best[j]) { best[j] = ys; brow[j] = r; }
+              }
+            }
+            unsigned long long* keys = reinterpret_cast<unsigned long long*>(E.dx) + (row0 / E.npts) * N + cbase;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              unsigned long long key = (row0 + rbase < M)
+                  ? ((unsigned long long)f32_ordered(best[j]) << 32) | (unsigned long long)(0xFFFFFFFFu - (rin0 + (uint32_t)brow[j]))
+                  : 0ull;
+              unsigned long long other = __shfl_xor_sync(0xffffffffu, key, 8);
+              if (other > key) key = other;
+              other = __shfl_xor_sync(0xffffffffu, key, 16);
+              if (other > key) key = other;
+              if (sr == 0) atomicMax(keys + j, key);
+            }
+          } else {
+            float4 pre[8];
+            if (EMODE == EPI_RELUMASK_STATS) {
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                const long long row = row0 + rbase + 4 * it;
+                pre[it] = (row < M) ? *reinterpret_cast<const float4*>(E.yprev + row * E.ldyp + cbase) : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+            }
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int r = rbase + 4 * it;
+              const long long row = row0 + r;
+              if (row >= M) break;
+              const float4 s4 = *reinterpret_cast<const float4*>(stage_w + (it * 4 + sr) * WS_STAGE_LD + cq * 4);
+              float o[4] = {s4.x, s4.y, s4.z, s4.w};
+              if (EMODE == EPI_STORE || EMODE == EPI_STORE_STATS) {
+                const float* rb = nullptr;
+                if (E.rowbias) {
+                  long long cl0 = rb_cloud0;
+                  const uint32_t x = rb_rem0 + (uint32_t)r;
+                  if (x >= (uint32_t)E.rb_rows) { cl0 += x / (uint32_t)E.rb_rows; }
+                  rb = E.rowbias + cl0 * E.ldrb + cbase;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  o[j] += bias[j];
+                  if (rb) o[j] += rb[j];
+                }
+                if (EMODE == EPI_STORE_STATS) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) { f0[j] += o[j]; f1[j] = fmaf(o[j], o[j], f1[j]); }
+                }
+              } else if (EMODE == EPI_RELUMASK_STATS) {
+                const float4 y4 = pre[it];
+                const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
+                float dm[4] = {1.f, 1.f, 1.f, 1.f};
+                if (E.dmask) {
+                  const float4 m4 = *reinterpret_cast<const float4*>(E.dmask + row * N + cbase);
+                  dm[0] = m4.x * E.dscale; dm[1] = m4.y * E.dscale; dm[2] = m4.z * E.dscale; dm[3] = m4.w * E.dscale;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const bool on = fmaf(yv[j], scp[j], shp[j]) > 0.f;
+                  o[j] = on ? o[j] * dm[j] : 0.f;
+                  f0[j] += o[j];
+                  f1[j] = fmaf(o[j], yv[j], f1[j]);
+                }
+              }
+              *reinterpret_cast<float4*>(E.out + row * E.ldo + cbase) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+          }
+          if (kStats) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { st0[nb][j] += (double)f0[j]; st1[nb][j] += (double)f1[j]; }
+          }
+        }
+        __syncwarp();        // the staging tile may be overwritten by the next block
+      }
+    }
+    if (kStats) {
+#pragma unroll
+      for (int nb = 0; nb < NBLK; ++nb) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          double a = st0[nb][j], b = st1[nb][j];
+          a += __shfl_xor_sync(0xffffffffu, a, 8);    // the four sub-row lanes of a column group
+          b += __shfl_xor_sync(0xffffffffu, b, 8);
+          a += __shfl_xor_sync(0xffffffffu, a, 16);
+          b += __shfl_xor_sync(0xffffffffu, b, 16);
+          const int cl = chh * 128 + nb * 32 + cq * 4 + j;
+          if (sr == 0 && cl < Nt) {
+            atomicAdd(E.stats + n0 + cl, a);
+            atomicAdd(E.stats + N + n0 + cl, b);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tc_dealloc(tmem_base, 512u);
+}
+
+// the serial kernel stays the path for single-chunk layers, edge operands and short inputs; WSPC_ROWGEMM_KERNEL=serial forces it
+bool ws_rowgemm_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("WSPC_ROWGEMM_KERNEL");
+    return !(e && strcmp(e, "serial") == 0);
+  }();
+  return on;
+}
+
+// conv2d -> (BN -> ReLU) -> max over the cloud's points without writing the conv output: eligibility and launch
+bool ws_pool_supported(long long M, int N, int K, int npts) {
+  if (!ws_rowgemm_enabled()) return false;
+  const TcPlan pl = tc_plan(N, K);
+  const long long num_tiles = (M + TILE_M - 1) / TILE_M;
+  return K > 128 && K % WS_KC == 0 && N % 16 == 0 && pl.ntiles_n <= kNumSM / 2 && num_tiles >= 4 * kNumSM && npts >= TILE_M &&
+         npts % TILE_M == 0 && M % npts == 0 && tc_wimg_bytes(N, K) > 0;
+}
+
+__global__ void __launch_bounds__(256)
+pool_keys_finish_kernel(const unsigned long long* __restrict__ keys, const float* __restrict__ gamma, const float* __restrict__ sc,
+                        const float* __restrict__ sh, long long total, int C, float* __restrict__ g, int32_t* __restrict__ amax,
+                        float* __restrict__ ymax) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  const unsigned long long key = keys[i];
+  const uint32_t u = (uint32_t)(key >> 32);
+  const float ys = __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+  const float y = (gamma[c] < 0.f) ? -ys : ys;
+  g[i] = fmaxf(fmaf(y, sc[c], sh[c]), 0.f);
+  amax[i] = (int32_t)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull));
+  ymax[i] = y;
+}
+
+template <int AMODE>
+int launch_ws_pool(const Operand& A, const float* Bm, long long ldb, long long M, int N, int K, const Epilogue& E, void* ws,
+                   cudaStream_t st) {
+  const TcPlan pl = tc_plan(N, K);
+  const int num_tiles = (int)((M + TILE_M - 1) / TILE_M);
+  wprep_kernel<<<dim3(K / WS_KC, pl.ntiles_n), 256, 0, st>>>(Bm, ldb, 0, N, K, WS_KC, pl.NtMax, static_cast<unsigned char*>(ws));
+  count_launch();
+  const WsSmem wp = ws_smem_plan(pl.NtMax, AMODE == OP_DY);
+  const int grid = kNumSM / pl.ntiles_n * pl.ntiles_n;
+  auto kern = rowgemm_ws_kernel<AMODE, EPI_STATS_POOL, 4>;
+  WSPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wp.total));
+  kern<<<grid, WS_THREADS, wp.total, st>>>(A, M, N, K, E, num_tiles, pl.NtMax, pl.ntiles_n, static_cast<const unsigned char*>(ws), 0);
+  count_launch();
+  WSPC_LAUNCH_CHECK("rowgemm_ws_kernel(pool)");
+  return WSPC_OK;
+}
+
 template <int AMODE, int EMODE>
 int launch_tc(const Operand& A, const float* Bm, long long ldb, int bT, long long M, int N, int K, const Epilogue& E,
               void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -795,13 +1284,32 @@ int launch_tc(const Operand& A, const float* Bm, long long ldb, int bT, long lon
   const TcPlan pl = tc_plan(N, K);
   const unsigned char* wimg = nullptr;
   const size_t need = tc_wimg_bytes(N, K);
+  const int num_tiles = (int)((M + TILE_M - 1) / TILE_M);
+  constexpr bool kWsModes = (AMODE == OP_PLAIN || AMODE == OP_BNRELU || AMODE == OP_DY) &&
+                            (EMODE == EPI_STORE || EMODE == EPI_STORE_STATS || EMODE == EPI_RELUMASK_STATS);
+  if constexpr (kWsModes) {
+    if (ws_rowgemm_enabled() && need && ws && ws_bytes >= need && aligned16(ws) && !generic && K % WS_KC == 0 && pl.ntiles_n <= kNumSM / 2 &&
+        num_tiles >= 4 * kNumSM && !(AMODE == OP_BNRELU && A.dmask)) {
+      // pre-split weights in 32-channel chunks (same bytes as the 64-channel image when K % 64 == 0, fewer otherwise)
+      wprep_kernel<<<dim3(K / WS_KC, pl.ntiles_n), 256, 0, st>>>(Bm, ldb, bT, N, K, WS_KC, pl.NtMax, static_cast<unsigned char*>(ws));
+      count_launch();
+      const WsSmem wp = ws_smem_plan(pl.NtMax, AMODE == OP_DY);
+      const int grid = kNumSM / pl.ntiles_n * pl.ntiles_n;
+      auto kern = rowgemm_ws_kernel<AMODE, EMODE, 4>;
+      WSPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wp.total));
+      static const int dbg = getenv("WSPC_WS_DBG") ? atoi(getenv("WSPC_WS_DBG")) : 0;
+      kern<<<grid, WS_THREADS, wp.total, st>>>(A, M, N, K, E, num_tiles, pl.NtMax, pl.ntiles_n, static_cast<const unsigned char*>(ws), dbg);
+      count_launch();
+      WSPC_LAUNCH_CHECK("rowgemm_ws_kernel");
+      return WSPC_OK;
+    }
+  }
   if (need && ws && ws_bytes >= need && aligned16(ws)) {     // chunked K: stage pre-split weights with bulk copies
     const int nkc = (K + pl.KC - 1) / pl.KC;
     wprep_kernel<<<dim3(nkc, pl.ntiles_n), 256, 0, st>>>(Bm, ldb, bT, N, K, pl.KC, pl.NtMax, static_cast<unsigned char*>(ws));
     count_launch();
     wimg = static_cast<const unsigned char*>(ws);
   }
-  const int num_tiles = (int)((M + TILE_M - 1) / TILE_M);
   const int ctas = pl.minb * kNumSM;
   int gx = (ctas + pl.ntiles_n - 1) / pl.ntiles_n;
   if (gx > num_tiles) gx = num_tiles;
@@ -1280,3 +1788,49 @@ int rowgemm_tc_dispatch(const Operand& A, int amode, const float* Bm, long long 
 }
 
 }  // namespace wspc
+
+// ---------------------------------------------------------------------------------------------------------------------
+// adj_conv7 + max_pool2d([N,1]) (DGCNN_S3DIS.py:80-85, DGCNN_ShapeNet.py:80-85) in one pass; see include/wspc.h
+extern "C" int wspc_conv1x1_pool_supported(long long M, int N, int K, int npts) {
+  return wspc::ws_pool_supported(M, N, K, npts) ? 1 : 0;
+}
+
+extern "C" int wspc_conv1x1_pool_fwd(const wspc_operand_t* A, int a_mode, const float* W, long long ldw, long long M, int N, int K,
+                                     int npts, const float* bias, const float* gamma, double* stats, unsigned long long* keys,
+                                     void* workspace, size_t workspace_bytes, wspc_stream_t stream) {
+  using namespace wspc;
+  if (int rc = check_arch()) return rc;
+  WSPC_REQUIRE(A && W && gamma && stats && keys && workspace, "conv1x1_pool_fwd: null argument");
+  WSPC_REQUIRE(a_mode == OP_PLAIN || a_mode == OP_BNRELU, "conv1x1_pool_fwd: operand mode %d (PLAIN or BNRELU)", a_mode);
+  WSPC_REQUIRE(A->p && A->C == K, "conv1x1_pool_fwd: operand channels %d != K %d", A->C, K);
+  WSPC_REQUIRE(ws_pool_supported(M, N, K, npts), "conv1x1_pool_fwd: shape M=%lld N=%d K=%d npts=%d is not eligible "
+               "(wspc_conv1x1_pool_supported)", M, N, K, npts);
+  WSPC_REQUIRE(tc_operand_fast(*A, a_mode, K) && !(a_mode == OP_BNRELU && A->dmask), "conv1x1_pool_fwd: operand must be 16-byte aligned");
+  if (workspace_bytes < tc_wimg_bytes(N, K) || !aligned16(workspace)) {
+    set_error("conv1x1_pool_fwd: workspace too small (wspc_conv1x1_rows_workspace_bytes)");
+    return WSPC_ERR_WORKSPACE;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  WSPC_CUDA(cudaMemsetAsync(keys, 0, (size_t)(M / npts) * N * sizeof(unsigned long long), st));
+  Epilogue E{};
+  E.bias = bias;
+  E.stats = stats;
+  E.scp = gamma;
+  E.dx = reinterpret_cast<float*>(keys);
+  E.npts = npts;
+  if (a_mode == OP_PLAIN) return launch_ws_pool<OP_PLAIN>(*A, W, ldw, M, N, K, E, workspace, st);
+  return launch_ws_pool<OP_BNRELU>(*A, W, ldw, M, N, K, E, workspace, st);
+}
+
+extern "C" int wspc_maxn_from_keys(const unsigned long long* keys, const float* gamma, const float* sc, const float* sh, int B,
+                                   int C, float* g, int32_t* amax, float* ymax, wspc_stream_t stream) {
+  using namespace wspc;
+  if (int rc = check_arch()) return rc;
+  WSPC_REQUIRE(keys && gamma && sc && sh && g && amax && ymax && B >= 1 && C >= 1, "maxn_from_keys: bad argument");
+  const long long total = (long long)B * C;
+  pool_keys_finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(keys, gamma, sc, sh,
+                                                                                                          total, C, g, amax, ymax);
+  count_launch();
+  WSPC_LAUNCH_CHECK("pool_keys_finish_kernel");
+  return WSPC_OK;
+}

@@ -114,7 +114,9 @@ enum EpiMode : int {
   EPI_STORE_STATS = 1,     // + per-column (sum, sum of squares) in double  -> BN batch statistics
   EPI_RELUMASK_STATS = 2,  // out = acc * [prev activation > 0] (* dropout); stats = (sum G, sum G*y_prev)
   EPI_ACCUM = 3,           // out += acc
-  EPI_EDGE_SCATTER = 4     // acc = [dE_c | dE_d] -> atomics into point gradients (tf_util.py:700-705 backward)
+  EPI_EDGE_SCATTER = 4,    // acc = [dE_c | dE_d] -> atomics into point gradients (tf_util.py:700-705 backward)
+  EPI_STATS_POOL = 5       // nothing stored: BN sums + per (cloud, column) extreme row of acc + bias (conv2d -> BN -> ReLU -> max over the
+                           // cloud's points; internal to wspc_conv1x1_pool_fwd: scp = gamma, dx = packed keys, npts = rows per cloud)
 };
 
 using Epilogue = wspc_epilogue_t; // declared in include/wspc.h

@@ -58,7 +58,15 @@ class S3DISEngine:
             self.y = [torch.empty((R, 64), **f32) for _ in range(5)]
             self.Ga, self.Gb = torch.empty((R, 64), **f32), torch.empty((R, 64), **f32)
         self.cat, self.dcat = torch.empty((P, 192), **f32), torch.empty((P, 192), **f32)
-        self.y7 = torch.empty((P, 1024), **f32)
+        # adj_conv7 + max over points in one pass (no (P,1024) tensor) when the Gram-identity backward is on and the shape fits
+        self.pool_fused = rt.POOLCONV_GRAM and rt.pool_fusable(P, 1024, 192, N)
+        if self.pool_fused:
+            self.y7 = None
+            self.pool_keys = torch.empty((B, 1024), dtype=torch.int64, device=self.dev)
+            self.y7max = torch.empty((B, 1024), **f32)                 # pre-BN value at the arg-max row
+            self.amax0 = torch.zeros((B, 1024), **i32)
+        else:
+            self.y7 = torch.empty((P, 1024), **f32)
         self.g, self.dg_in, self.dg = (torch.empty((B, 1024), **f32) for _ in range(3))
         self.amax = torch.empty((B, 1024), **i32)
         self.gW, self.S = torch.empty((B, 512), **f32), torch.empty((B, 512), **f32)
@@ -155,9 +163,13 @@ class S3DISEngine:
         Ly = self.layers
         # adj_conv7 + max over points                                                   (:80-85)
         l7 = Ly["adj_conv7"]
-        rt.conv_forward(l7, rt.op_plain(self.cat, 192, 192), P, self.y7, 1024, is_training, bn_decay)
-        L.check(L.lib().wspc_maxn_bnrelu_fwd(L.ptr(self.y7), L.ptr(l7.sc), L.ptr(l7.sh), B, N, 1024, L.ptr(self.g),
-                                             L.ptr(self.amax), L.stream()))
+        if self.pool_fused:     # the (P, 1024) pre-BN tensor is never written: BN sums + arg-max rows in the GEMM epilogue
+            rt.conv_pool_forward(l7, rt.op_plain(self.cat, 192, 192), P, N, self.pool_keys, self.g, self.amax, self.y7max,
+                                 is_training, bn_decay)
+        else:
+            rt.conv_forward(l7, rt.op_plain(self.cat, 192, 192), P, self.y7, 1024, is_training, bn_decay)
+            L.check(L.lib().wspc_maxn_bnrelu_fwd(L.ptr(self.y7), L.ptr(l7.sc), L.ptr(l7.sh), B, N, 1024, L.ptr(self.g),
+                                                 L.ptr(self.amax), L.stream()))
         # seg/conv1 with the tiled global feature folded into a per-cloud bias          (:87-96)
         s1, s2, s3 = Ly["seg/conv1"], Ly["seg/conv2"], Ly["seg/conv3"]
         epi = L.Epilogue(out=L.dptr(self.gW), ldo=512)
@@ -231,7 +243,8 @@ class S3DISEngine:
         rt.rows_gemm(GS, s1.W, 512, 1, B, 1024, 512, L.Epilogue(out=L.dptr(self.dg_in), ldo=1024), L.EPI_STORE)
         # max over points: ReLU gate + BN-backward sums of the sparse gradient, then adj_conv7
         rt.zero_(c7.bstats)
-        L.check(L.lib().wspc_maxn_bwd_gate(L.ptr(self.g), L.ptr(self.dg_in), L.ptr(self.amax), L.ptr(self.y7), B, N, 1024,
+        y7_rows, y7_n, y7_amax = (self.y7max, 1, self.amax0) if self.pool_fused else (self.y7, N, self.amax)
+        L.check(L.lib().wspc_maxn_bwd_gate(L.ptr(self.g), L.ptr(self.dg_in), L.ptr(y7_amax), L.ptr(y7_rows), B, y7_n, 1024,
                                            L.ptr(self.dg), L.ptr(c7.bstats), L.stream()))
         rt.bn_bwd_coeffs(c7, P)
         if self.pc7 is not None:     # Gram identity (csrc/poolconv.cu): no (P,1024) operand, y7 is not read

@@ -76,7 +76,14 @@ class ShapeNetEngine:
             self.Gb = torch.empty((R, 64), **f32)
         self.Ga = torch.empty((R, 64), **f32)
         self.cat, self.dcat = torch.empty((P, 192), **f32), torch.empty((P, 192), **f32)
-        self.y7 = torch.empty((P, 1024), **f32)
+        self.pool_fused = rt.POOLCONV_GRAM and rt.pool_fusable(P, 1024, 192, N)
+        if self.pool_fused:
+            self.y7 = None
+            self.pool_keys = torch.empty((B, 1024), dtype=torch.int64, device=self.dev)
+            self.y7max = torch.empty((B, 1024), **f32)
+            self.amax0 = torch.zeros((B, 1024), **i32)
+        else:
+            self.y7 = torch.empty((P, 1024), **f32)
         self.g, self.dg_in, self.dg = (torch.empty((B, 1024), **f32) for _ in range(3))
         self.amax = torch.empty((B, 1024), **i32)
         self.ylab, self.Glab = torch.empty((B, 64), **f32), torch.empty((B, 64), **f32)
@@ -170,9 +177,12 @@ class ShapeNetEngine:
         B, N, P = self.B, self.N, self.P
         Ly = self.layers
         l7 = Ly["adj_conv7"]
-        rt.conv_forward(l7, rt.op_plain(self.cat, 192, 192), P, self.y7, 1024, tr, d)                     # :80-83
-        L.check(L.lib().wspc_maxn_bnrelu_fwd(L.ptr(self.y7), L.ptr(l7.sc), L.ptr(l7.sh), B, N, 1024, L.ptr(self.g),
-                                             L.ptr(self.amax), L.stream()))                               # :85
+        if self.pool_fused:     # :80-85 in one pass, the (P, 1024) pre-BN tensor is never written
+            rt.conv_pool_forward(l7, rt.op_plain(self.cat, 192, 192), P, N, self.pool_keys, self.g, self.amax, self.y7max, tr, d)
+        else:
+            rt.conv_forward(l7, rt.op_plain(self.cat, 192, 192), P, self.y7, 1024, tr, d)                 # :80-83
+            L.check(L.lib().wspc_maxn_bnrelu_fwd(L.ptr(self.y7), L.ptr(l7.sc), L.ptr(l7.sh), B, N, 1024, L.ptr(self.g),
+                                                 L.ptr(self.amax), L.stream()))                           # :85
         # ---- category branch + folded global feature                         (:87-101)
         lab = Ly["one_hot_label_expand"]
         rt.conv_forward(lab, rt.op_plain(self.label, 16, 16), B, self.ylab, 64, tr, d)
@@ -262,7 +272,8 @@ class ShapeNetEngine:
         rt.wgrad(rt.op_plain(self.label, 16, 16), rt.op_dy(self.Glab, 64, self.ylab, 64, lab, 64), B, lab.dW, lab.db, dev)
         # max over points + adj_conv7
         rt.zero_(c7.bstats)
-        L.check(L.lib().wspc_maxn_bwd_gate(L.ptr(self.g), L.ptr(self.dg_in), L.ptr(self.amax), L.ptr(self.y7), B, N, 1024,
+        y7_rows, y7_n, y7_amax = (self.y7max, 1, self.amax0) if self.pool_fused else (self.y7, N, self.amax)
+        L.check(L.lib().wspc_maxn_bwd_gate(L.ptr(self.g), L.ptr(self.dg_in), L.ptr(y7_amax), L.ptr(y7_rows), B, y7_n, 1024,
                                            L.ptr(self.dg), L.ptr(c7.bstats), L.stream()))
         rt.bn_bwd_coeffs(c7, P)
         G1 = self._G1

@@ -213,6 +213,30 @@ def conv_forward(layer: Layer, A, M, y_out, ldo, training, decay, rowbias=None, 
         bn_finalize(layer, M, training, decay)
 
 
+# WSPC_POOL=unfused keeps the (P, 1024) adj_conv7 output in HBM and pools it with wspc_maxn_bnrelu_fwd (A/B tests)
+POOL_FUSED = os.environ.get("WSPC_POOL", "fused") != "unfused"
+
+
+def pool_fusable(M, N, K, npts):
+    return POOL_FUSED and bool(L.lib().wspc_conv1x1_pool_supported(M, N, K, npts))
+
+
+def conv_pool_forward(layer: Layer, A, M, npts, keys, g, amax, ymax, training, decay):
+    """conv2d 1x1 -> BN -> ReLU -> max over the npts points of every cloud (DGCNN_S3DIS.py:80-85) without the (M, cout)
+    intermediate: BN sums and per-(cloud, channel) extreme rows in one GEMM pass, then g / arg-max / pre-BN value at the
+    arg-max (what the backward gate needs) from the keys."""
+    a, amode = A
+    K, N = a.C, layer.cout
+    zero_(layer.stats)
+    nbytes = L.lib().wspc_conv1x1_rows_workspace_bytes(N, K)
+    ws = L.workspace(nbytes, torch.cuda.current_device(), "gemm_w")
+    L.check(L.lib().wspc_conv1x1_pool_fwd(ctypes.byref(a), amode, L.ptr(layer.W), N, M, N, K, npts, L.ptr(layer.b),
+                                          L.ptr(layer.gamma), L.ptr(layer.stats), L.ptr(keys), L.ptr(ws), ws.numel(), L.stream()))
+    bn_finalize(layer, M, training, decay)
+    L.check(L.lib().wspc_maxn_from_keys(L.ptr(keys), L.ptr(layer.gamma), L.ptr(layer.sc), L.ptr(layer.sh), M // npts, N,
+                                        L.ptr(g), L.ptr(amax), L.ptr(ymax), L.stream()))
+
+
 def bn_finalize(layer: Layer, rows, training, decay):
     d = 0.9 if decay is None else decay   # tf_util.py:523
     L.check(L.lib().wspc_bn_finalize(L.ptr(layer.stats), layer.cout, float(rows), L.ptr(layer.gamma), L.ptr(layer.beta),
