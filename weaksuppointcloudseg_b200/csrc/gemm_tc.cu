@@ -792,15 +792,21 @@ bool tc_supported(const Operand& A, int amode, const float* Bm, long long M, int
 
 // ------------------------------------------------------------------ warp-specialised row GEMM (chunked K, P-row layers) ---
 // The kernel above runs "synthesise A -> MMA -> epilogue" one after the other inside a CTA.  For the per-point layers
-// (K = 192 ... 512 in 64-channel chunks, 256-column tiles) that leaves the tensor pipe at 12-21 % and HBM at ~1.5 TB/s
-// (profiles/r1_gemm_summary.md).  Here one persistent CTA per SM splits the roles:
+// (K = 192 ... 512, 256-column tiles) that leaves the tensor pipe at 12-21 % (profiles/r1_gemm_summary.md).  Here one
+// persistent CTA per SM splits the roles (17 warps):
 //   * warps 0-7  (producers): every thread streams ITS OWN 2 rows x 8 channels of each 32-channel chunk into a private
-//     shared-memory slot with cp.async (64 KB in flight per SM, no registers held, no cross-thread hand-over), then
+//     shared-memory slot with cp.async (48-64 KB in flight per SM, no registers held, no cross-thread hand-over), then
 //     applies the operand map (BN+ReLU / BN-backward affine), splits into bf16 hi + lo and writes the UMMA image of a
-//     2-stage ring; thread 255 issues the chunk's 6 tcgen05.mma (hi*hi + lo*hi + hi*lo) and refills the 2-stage ring of
-//     pre-split weight chunks (wprep_kernel image) with one bulk copy per chunk;
-//   * warps 8-15 (epilogue): read the finished 128 x <=256 accumulator (two TMEM accumulators alternate, so the next
-//     tile's MMAs run under this tile's epilogue), stage 64-column passes and store coalesced with the fused epilogue.
+//     2-stage ring; one release-arrival per warp;
+//   * warp 16 (one thread): waits for operand image + weight chunk, runs the generic->async proxy fence, issues the chunk's
+//     6 tcgen05.mma (hi*hi + lo*hi + hi*lo) and refills the 2-3 stage ring of pre-split weight chunks (wprep_kernel image)
+//     with one bulk copy per chunk.  Every CTA walks the K chunks in its own rotation so that the 148 SMs do not all pull
+//     the same 33 KB chunk from the same L2 slices at the same time;
+//   * warps 8-15 (epilogue): drain the finished 128 x <=256 accumulator (two TMEM accumulators alternate, so the next tile's
+//     MMAs run under this tile's epilogue) in warp-private 32 x 32 blocks -- no block-wide barrier -- with the fused
+//     epilogue (bias / per-cloud row bias / BN sums / ReLU mask + BN-backward sums / pooled arg-max keys).
+// Measured at cfg-3 (profiles/r2_rowgemm_summary.md): tensor pipe 30 -> 45 %; the limiter left is the producers' instruction
+// stream (~17 instructions per operand value at 2 rows per thread and chunk).
 constexpr int WS_THREADS = 544;                 // 8 producer warps + 8 epilogue warps + 1 MMA / weight-copy warp
 constexpr int WS_PROD = 256;
 constexpr int WS_EPI = 256;
@@ -852,7 +858,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 template <int AMODE, int EMODE, int MAXPASS>
 __global__ void __launch_bounds__(WS_THREADS, 1)
 rowgemm_ws_kernel(const Operand A, long long M, int N, int K, const Epilogue E, int num_tiles, int NtMax, int ntn,
-                  const unsigned char* __restrict__ wimg, int dbg) {
+                  const unsigned char* __restrict__ wimg) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int NOPS = (AMODE == OP_DY) ? 2 : 1;
   constexpr int WS_NB = (NOPS == 2) ? WS_NB_2 : WS_NB_1;
@@ -974,7 +980,7 @@ rowgemm_ws_kernel(const Operand A, long long M, int N, int K, const Epilogue E, 
       if (--b_left == 0) { b_left = nkc; b_row += row_step; }
     };
 #pragma unroll 1
-    for (int q = 0; q < ((dbg & 8) ? 0 : Q); ++q) {
+    for (int q = 0; q < Q; ++q) {
       const int s = q & 1;
       cp_async_wait<DEPTH - 1>();
       if (lane == 0) mbar_wait(emptyA + s, ((uint32_t)(q >> 1) & 1u) ^ 1u);   // the MMAs that read this stage two chunks ago retired
@@ -1006,8 +1012,8 @@ rowgemm_ws_kernel(const Operand A, long long M, int N, int K, const Epilogue E, 
       for (int q = 0; q < Q; ++q) {
         const int s = q & 1, acc = item & 1, sb = q % WS_NB;
         if (kc == 0) mbar_wait(accEmpty + acc, ((uint32_t)(item >> 1) & 1u) ^ 1u);   // the epilogue drained this accumulator
-        if (!(dbg & 2)) mbar_wait(fullB + sb, (uint32_t)(q / WS_NB) & 1u);
-        if (!(dbg & 1)) mbar_wait(fullA + s, (uint32_t)(q >> 1) & 1u);
+        mbar_wait(fullB + sb, (uint32_t)(q / WS_NB) & 1u);
+        mbar_wait(fullA + s, (uint32_t)(q >> 1) & 1u);
         fence_proxy_async_smem();
         tc_fence_after();
         const uint32_t ah = smem_u32(smem + sp.off_a + (size_t)s * 2 * a_bytes_half), al = ah + a_bytes_half;
@@ -1028,7 +1034,7 @@ rowgemm_ws_kernel(const Operand A, long long M, int N, int K, const Epilogue E, 
         tc_commit(emptyB + sb);
         if (kc == nkc - 1) tc_commit(accFull + acc);
         const int c = q + WS_NB - 1;                                    // weight chunk q+NB-1 goes where chunk q-1 was
-        if (c >= WS_NB && c < Q && !(dbg & 2)) {
+        if (c >= WS_NB && c < Q) {
           const int cs = c % WS_NB;
           mbar_wait(emptyB + cs, ((uint32_t)(c / WS_NB) & 1u) ^ 1u);
           mbar_expect_tx(fullB + cs, bstage);
@@ -1096,7 +1102,7 @@ rowgemm_ws_kernel(const Operand A, long long M, int N, int K, const Epilogue E, 
         __syncwarp();
         const int cl = c0 + cq * 4;               // column within this N tile
         const int cbase = n0 + cl;                // global column
-        if (cl < Nt && !(dbg & 4)) {
+        if (cl < Nt) {
           float bias[4] = {0.f, 0.f, 0.f, 0.f}, scp[4] = {0.f, 0.f, 0.f, 0.f}, shp[4] = {-1.f, -1.f, -1.f, -1.f};
           if ((EMODE == EPI_STORE || EMODE == EPI_STORE_STATS || EMODE == EPI_STATS_POOL) && E.bias) {
 #pragma unroll
@@ -1271,7 +1277,7 @@ int launch_ws_pool(const Operand& A, const float* Bm, long long ldb, long long M
   const int grid = kNumSM / pl.ntiles_n * pl.ntiles_n;
   auto kern = rowgemm_ws_kernel<AMODE, EPI_STATS_POOL, 4>;
   WSPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wp.total));
-  kern<<<grid, WS_THREADS, wp.total, st>>>(A, M, N, K, E, num_tiles, pl.NtMax, pl.ntiles_n, static_cast<const unsigned char*>(ws), 0);
+  kern<<<grid, WS_THREADS, wp.total, st>>>(A, M, N, K, E, num_tiles, pl.NtMax, pl.ntiles_n, static_cast<const unsigned char*>(ws));
   count_launch();
   WSPC_LAUNCH_CHECK("rowgemm_ws_kernel(pool)");
   return WSPC_OK;
@@ -1297,8 +1303,7 @@ int launch_tc(const Operand& A, const float* Bm, long long ldb, int bT, long lon
       const int grid = kNumSM / pl.ntiles_n * pl.ntiles_n;
       auto kern = rowgemm_ws_kernel<AMODE, EMODE, 4>;
       WSPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wp.total));
-      static const int dbg = getenv("WSPC_WS_DBG") ? atoi(getenv("WSPC_WS_DBG")) : 0;
-      kern<<<grid, WS_THREADS, wp.total, st>>>(A, M, N, K, E, num_tiles, pl.NtMax, pl.ntiles_n, static_cast<const unsigned char*>(ws), dbg);
+      kern<<<grid, WS_THREADS, wp.total, st>>>(A, M, N, K, E, num_tiles, pl.NtMax, pl.ntiles_n, static_cast<const unsigned char*>(ws));
       count_launch();
       WSPC_LAUNCH_CHECK("rowgemm_ws_kernel");
       return WSPC_OK;
