@@ -162,7 +162,23 @@ knn_tc_prep_kernel(const float* __restrict__ x, int N, int ldx, int coff, int D,
   const int n = tile * QT + r;
   const size_t tile_bytes = (size_t)(ghi + glo) * GROUP_BYTES;
   unsigned char* base = img + ((size_t)b * (Npad / QT) + tile) * tile_bytes;
-  const float* xr = x + ((size_t)b * N + (n < N ? n : 0)) * ldx + coff;
+  // the tile's rows are fetched coalesced (float4, 16 lanes per 64-channel row) into shared memory; thread = point then reads
+  // its own row from there (pitch D+1: conflict-free).  Row-per-thread global loads ran this kernel at 0.5 TB/s.
+  __shared__ float sx[QT * 65];
+  const bool staged = (D % 4 == 0) && (ldx % 4 == 0) && (coff % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0);
+  if (staged) {
+    const int d4 = D >> 2;
+    for (int e = r; e < QT * d4; e += QT) {
+      const int rr = e / d4, c4 = e - rr * d4;
+      const int nn = tile * QT + rr;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (nn < N) v = *reinterpret_cast<const float4*>(x + ((size_t)b * N + nn) * ldx + coff + c4 * 4);
+      float* d = sx + rr * (D + 1) + c4 * 4;
+      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+    __syncthreads();
+  }
+  const float* xr = staged ? sx + r * (D + 1) : x + ((size_t)b * N + (n < N ? n : 0)) * ldx + coff;
   const float* cb = centre + b * 64;       // channel sums
   const float inv_n = 1.f / (float)N;
   float acc = 0.f, accc = 0.f;
