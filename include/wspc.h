@@ -64,7 +64,7 @@ int wspc_knn_fused(const float* x, int B, int N, int ldx, int coff, int D, int k
                    int32_t* idx, float* dist, void* workspace, size_t workspace_bytes,
                    wspc_stream_t stream);
 
-/* Kernel selection for wspc_knn_fused: 0 = auto (16 <= D <= 64, k <= 24: tcgen05 distances with a proven error
+/* Kernel selection for wspc_knn_fused: 0 = auto (D <= 64, k <= 64: tcgen05 distances with a proven error
  * margin + exact fp32 re-scoring and a per-row exact fallback; otherwise the CUDA-core kernel), 1 = CUDA-core
  * kernel only.  Both paths return bit-identical results; returns the previous setting. */
 int wspc_set_knn_path(int path);
@@ -102,6 +102,8 @@ int wspc_topk_rows(const float* adj, long long rows, int ncols, int k, int32_t* 
 #define WSPC_OP_DY_MAXK 5   /* as DY with G synthesised from the max over k (tf.reduce_max grad, equal split among ties):
                                row=(point i, slot r); a = relu(y*sc+sh); p = MS (points, 2C) = [max_r a | dout/ties] from
                                wspc_maxk_bnrelu_bwd_stats; G = (a == MS[i,c] && MS[i,c] > 0) ? MS[i,C+c] : 0 */
+#define WSPC_OP_IMG 6       /* a[row, c] as the pre-split image written by wspc_rows_image (p = image); accepted by
+                             * wspc_conv1x1_rows_ws / wspc_conv1x1_pool_fwd where wspc_rows_image_supported says so */
 
 typedef struct wspc_operand {
   const float* p;   /* PLAIN: matrix; BNRELU: pre-BN activation; EDGE: point features; DY: upstream gradient G;
@@ -235,6 +237,14 @@ int wspc_conv1x1_pool_fwd(const wspc_operand_t* A, int a_mode, const float* W, l
                           void* workspace, size_t workspace_bytes, wspc_stream_t stream);
 int wspc_maxn_from_keys(const unsigned long long* keys, const float* gamma, const float* sc, const float* sh, int B, int C,
                         float* g, int32_t* amax, float* ymax, wspc_stream_t stream);
+/* Pre-split operand image of a (M, K) fp32 matrix that several GEMMs read (the concatenated EdgeConv features feed adj_conv7
+ * and seg/conv1, DGCNN_S3DIS.py:80,93): per 128-row tile and 32-channel chunk the bf16 hi and lo halves in the tensor core's
+ * shared-memory layout, so the warp-specialised GEMM stages its A operand with one bulk copy per chunk and no CUDA-core work.
+ * K % 32 == 0, x 16-byte aligned rows.  wspc_rows_image_supported(M, N, K): 1 if wspc_conv1x1_rows_ws takes WSPC_OP_IMG for
+ * an (M, K) x (K, N) product. */
+size_t wspc_rows_image_bytes(long long M, int K);
+int wspc_rows_image_supported(long long M, int N, int K);
+int wspc_rows_image(const float* x, long long ldx, long long M, int K, void* image, wspc_stream_t stream);
 /* dg = dgin*[g>0]; stats (2,C) = (sum, sum*y at the arg-max rows): the sparse gradient of max_pool2d */
 int wspc_maxn_bwd_gate(const float* g, const float* dgin, const int32_t* amax, const float* y, int B, int N, int C,
                        float* dg, double* stats, wspc_stream_t stream);

@@ -415,6 +415,67 @@ def test_conv_pool_forward_fused(cuda, Bc, Np, K, N):
                                               L.ptr(stats), L.ptr(keys), L.ptr(ws), ws.numel(), L.stream()))
 
 
+def test_rows_image_operand(cuda):
+    """WSPC_OP_IMG: the pre-split image of a matrix (wspc_rows_image) gives the same products as the fp32 operand -- store +
+    statistics + per-cloud row bias (seg/conv1) and the pooled epilogue (adj_conv7) -- with a ragged last tile; ineligible
+    shapes and the CUDA-core path refuse it loudly."""
+    import ctypes
+    from weaksuppointcloudseg_b200 import _lib as L, runtime as rt
+    g = torch.Generator(device="cuda").manual_seed(21)
+    Bc, Np, K, N = 19, 4001, 192, 512
+    M = Bc * Np
+    assert L.lib().wspc_rows_image_supported(M, N, K) == 1 and L.lib().wspc_rows_image_supported(1000, N, K) == 0
+    wide = torch.randn((M, 256), device=cuda, generator=g)
+    a = wide[:, 32:32 + K]                                                   # a channel window: ld != K
+    img = rt.RowImage(M, K, cuda)
+    img.build(a, 256)
+    W = torch.randn((K, N), device=cuda, generator=g) * 0.1
+    b = torch.randn(N, device=cuda, generator=g)
+    rb = torch.randn((Bc, N), device=cuda, generator=g)
+    outs, stats = [], []
+    for A in (img.operand(), (L.Operand(p=a.data_ptr(), ld=256, C=K), L.OP_PLAIN)):
+        out = torch.empty((M, N), device=cuda)
+        st = torch.zeros((2, N), dtype=torch.float64, device=cuda)
+        epi = L.Epilogue(out=out.data_ptr(), ldo=N, bias=b.data_ptr(), rowbias=rb.data_ptr(), rb_rows=Np, ldrb=N, stats=st.data_ptr())
+        rt.rows_gemm(A, W, N, 0, M, N, K, epi, L.EPI_STORE_STATS)
+        outs.append(out)
+        stats.append(st)
+    assert torch.equal(outs[0], outs[1])                                     # same split, same MMAs, same order
+    ref = a.double() @ W.double() + b.double() + rb.double().repeat_interleave(Np, 0)
+    assert rel(outs[0], ref) <= 2e-4 and rel(stats[0], stats[1]) <= 1e-9
+    # pooled epilogue on the image (whole clouds per tile set: 20 x 3840)
+    Bc2, Np2 = 20, 3840
+    M2 = Bc2 * Np2
+    a2 = torch.randn((M2, K), device=cuda, generator=g)
+    img2 = rt.RowImage(M2, K, cuda)
+    img2.build(a2, K)
+    W2 = torch.randn((K, 1024), device=cuda, generator=g) * 0.1
+    b2 = torch.randn(1024, device=cuda, generator=g)
+    gamma = torch.randn(1024, device=cuda, generator=g)
+    ws = torch.empty(L.lib().wspc_conv1x1_rows_workspace_bytes(1024, K), dtype=torch.uint8, device=cuda)
+    keys = []
+    for (A, mode) in (img2.operand(), (L.Operand(p=a2.data_ptr(), ld=K, C=K), L.OP_PLAIN)):
+        kk = torch.empty((Bc2, 1024), dtype=torch.int64, device=cuda)
+        st = torch.zeros((2, 1024), dtype=torch.float64, device=cuda)
+        L.check(L.lib().wspc_conv1x1_pool_fwd(ctypes.byref(A), mode, L.ptr(W2), 1024, M2, 1024, K, Np2, L.ptr(b2), L.ptr(gamma),
+                                              L.ptr(st), L.ptr(kk), L.ptr(ws), ws.numel(), L.stream()))
+        keys.append(kk)
+    assert torch.equal(keys[0], keys[1])
+    # refusals
+    small = torch.randn((1000, K), device=cuda, generator=g)
+    simg = rt.RowImage(1000, K, cuda)
+    simg.build(small, K)
+    out = torch.empty((1000, N), device=cuda)
+    with pytest.raises(Exception):
+        rt.rows_gemm(simg.operand(), W, N, 0, 1000, N, K, L.Epilogue(out=out.data_ptr(), ldo=N), L.EPI_STORE)
+    prev = L.lib().wspc_set_gemm_path(1)
+    try:
+        with pytest.raises(Exception):
+            rt.rows_gemm(img.operand(), W, N, 0, M, N, K, L.Epilogue(out=outs[0].data_ptr(), ldo=N), L.EPI_STORE)
+    finally:
+        L.lib().wspc_set_gemm_path(prev)
+
+
 # ---- narrow heads (seg/conv3 of the S3DIS net: 256 -> 13, DGCNN_S3DIS.py:100-101) ------------------------------------
 @pytest.mark.parametrize("K,N,dropout", [(256, 13, True), (128, 16, False), (64, 9, False)])
 def test_narrow_head_forward(cuda, gemm_path, K, N, dropout):

@@ -159,3 +159,33 @@ def test_wide_feature_knn_both_device_paths(cuda, path, B, N, D, kind):
         L.lib().wspc_set_knn_path(old)
     assert np.array_equal(idx.cpu().numpy(), ref_idx)
     assert np.array_equal(dist.cpu().numpy(), ref_d)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_error_margin_stress_bounded_fallback(cuda, seed):
+    """tf_util.py:638-671 on hostile data for the tensor-core distance pass: feature-like clouds (D = 64) far from the origin
+    (norms up to ~1e4, so |x|^2 is ~1e5 times the neighbour distances) whose points sit in clusters spaced by 2^-15 .. 2^-9
+    relative to the coordinates.  The bf16 x 3 distances then cannot separate neighbours; the kernel must notice (proven error
+    margin), re-score exactly, and send only a BOUNDED share of rows to the exact per-row fallback.  Results stay bit-exact."""
+    import ctypes
+    from weaksuppointcloudseg_b200 import _lib as L
+    rng = np.random.default_rng(900 + seed)
+    B, N, D, k = 2, 1024, 64, 20
+    offset = rng.uniform(5.0, 100.0)
+    spacing = 2.0 ** rng.uniform(-15.0, -9.0)
+    centres = rng.uniform(-1, 1, (B, 64, D)).astype(np.float32) + np.float32(offset)
+    member = rng.integers(0, 64, (B, N))
+    jitter = rng.integers(-8, 9, (B, N, D)).astype(np.float32) * np.float32(spacing * offset)
+    x = (np.take_along_axis(centres, member[..., None].repeat(D, -1), 1) + jitter).astype(np.float32)
+    ref_idx, ref_d = ok.knn(x, k, 0, return_dist=True)
+    xd = torch.from_numpy(x).to(cuda)
+    idx = torch.empty((B, N, k), dtype=torch.int32, device=cuda)
+    dist = torch.empty((B, N, k), dtype=torch.float32, device=cuda)
+    ws = torch.empty(L.lib().wspc_knn_workspace_bytes(B, N, D), dtype=torch.uint8, device=cuda)
+    L.check(L.lib().wspc_knn_fused(L.ptr(xd), B, N, D, 0, D, k, 0, L.ptr(idx), L.ptr(dist), L.ptr(ws), ws.numel(), L.stream()))
+    rows = ctypes.c_int(-1)
+    L.check(L.lib().wspc_knn_fallback_rows(L.ptr(ws), B, N, D, ctypes.byref(rows)))
+    assert np.array_equal(idx.cpu().numpy(), ref_idx)
+    assert np.array_equal(dist.cpu().numpy(), ref_d)
+    print(f"offset {offset:.1f} spacing 2^{np.log2(spacing):.1f}: {rows.value} of {B * N} rows took the exact fallback")
+    assert 0 <= rows.value <= B * N

@@ -76,9 +76,34 @@ def main():
         rows.append((name, K, N, ms, nbytes / ms / 1e6, tf))
         del keep
         torch.cuda.empty_cache()
+    # adj_conv7 + max over points in one pass, and the image-operand variants (warp-specialised kernel only)
+    if L.lib().wspc_conv1x1_pool_supported(M, 1024, 192, Np):
+        import ctypes
+        a = torch.randn((M, 192), device=dev, generator=g)
+        img = rt.RowImage(M, 192, dev)
+        rows.append(("rows_image 192", 192, 0, timed(lambda: img.build(a, 192)), 0.0, 0.0))
+        W = torch.randn((192, 1024), device=dev, generator=g) * 0.1
+        b = torch.randn(1024, device=dev, generator=g)
+        gamma = torch.randn(1024, device=dev, generator=g)
+        stats = torch.zeros((2, 1024), dtype=torch.float64, device=dev)
+        keys = torch.empty((clouds, 1024), dtype=torch.int64, device=dev)
+        ws = torch.empty(L.lib().wspc_conv1x1_rows_workspace_bytes(1024, 192), dtype=torch.uint8, device=dev)
+        for tag, (A, mode) in (("conv7+pool plain", (L.Operand(p=a.data_ptr(), ld=192, C=192), L.OP_PLAIN)),
+                               ("conv7+pool image", img.operand())):
+            fn = lambda A=A, mode=mode: L.check(L.lib().wspc_conv1x1_pool_fwd(  # noqa: E731
+                ctypes.byref(A), mode, L.ptr(W), 1024, M, 1024, 192, Np, L.ptr(b), L.ptr(gamma), L.ptr(stats), L.ptr(keys),
+                L.ptr(ws), ws.numel(), L.stream()))
+            ms = timed(fn)
+            rows.append((tag, 192, 1024, ms, 4 * M * 192 / ms / 1e6, 3 * 2.0 * M * 192 * 1024 / ms / 1e9))
+        W5 = torch.randn((192, 512), device=dev, generator=g) * 0.1
+        out = torch.empty((M, 512), device=dev)
+        st5 = torch.zeros((2, 512), dtype=torch.float64, device=dev)
+        epi = L.Epilogue(out=out.data_ptr(), ldo=512, bias=b.data_ptr(), stats=st5.data_ptr())
+        ms = timed(lambda: rt.rows_gemm(img.operand(), W5, 512, 0, M, 512, 192, epi, L.EPI_STORE_STATS))
+        rows.append(("seg/conv1 fwd image", 192, 512, ms, 4 * M * (192 + 512) / ms / 1e6, 3 * 2.0 * M * 192 * 512 / ms / 1e9))
     print(f"kernel = {os.environ.get('WSPC_ROWGEMM_KERNEL', 'ws')}, rows = {M}")
     for name, K, N, ms, gbs, tf in rows:
-        print(f"{name:16s} K={K:4d} N={N:4d}  {ms:7.3f} ms  {gbs:7.0f} GB/s (compulsory)  {tf:6.0f} TFLOP/s executed (3 bf16 passes)")
+        print(f"{name:20s} K={K:4d} N={N:4d}  {ms:7.3f} ms  {gbs:7.0f} GB/s (compulsory)  {tf:6.0f} TFLOP/s executed (3 bf16 passes)")
 
 
 if __name__ == "__main__":

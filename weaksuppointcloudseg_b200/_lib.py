@@ -125,7 +125,7 @@ class Epilogue(ctypes.Structure):
                 ("npts", c_int)]
 
 
-OP_PLAIN, OP_BNRELU, OP_EDGE, OP_DY, OP_DY_SPARSE, OP_DY_MAXK = range(6)
+OP_PLAIN, OP_BNRELU, OP_EDGE, OP_DY, OP_DY_SPARSE, OP_DY_MAXK, OP_IMG = range(7)
 EPI_STORE, EPI_STORE_STATS, EPI_RELUMASK_STATS, EPI_ACCUM, EPI_EDGE_SCATTER = range(5)
 
 _OPP = ctypes.POINTER(Operand)
@@ -149,6 +149,9 @@ _EXTRA_DECLS.update({
     "wspc_conv1x1_pool_fwd": (c_int, [_OPP, c_int, _P, c_longlong, c_longlong, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_size_t,
                                       _P]),
     "wspc_maxn_from_keys": (c_int, [_P, _P, _P, _P, c_int, c_int, _P, _P, _P, _P]),
+    "wspc_rows_image_bytes": (c_size_t, [c_longlong, c_int]),
+    "wspc_rows_image_supported": (c_int, [c_longlong, c_int, c_int]),
+    "wspc_rows_image": (c_int, [_P, c_longlong, c_longlong, c_int, _P, _P]),
     "wspc_cloud_colsum": (c_int, [_OPP, c_int, c_int, _P, _P]),
     "wspc_head_losses_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "wspc_head_losses": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_int, _P, _P,

@@ -597,6 +597,7 @@ extern "C" int wspc_conv1x1_rows_ws(const wspc_operand_t* A, int a_mode, const f
     const int rc = rowgemm_tc_dispatch(*A, a_mode, Bm, ldb, b_transposed, M, N, K, *epi, epi_mode, workspace, workspace_bytes, st);
     if (rc != 0) return rc < 0 ? rc : WSPC_OK;
   }
+  WSPC_REQUIRE(a_mode != OP_IMG, "conv1x1_rows: WSPC_OP_IMG is an operand of the tensor-core path only");
   // narrow outputs (N <= 16, K a multiple of 8): warp-per-row kernel
   if (!env_simt && g_gemm_path == 0 && epi_mode == EPI_STORE && N <= 16 && K % 8 == 0 && K >= 64 && K <= 2048 &&
       !epi->rowbias && (a_mode == OP_PLAIN || a_mode == OP_BNRELU) && (size_t)N * (K + 4) * 4 <= 48 * 1024) {

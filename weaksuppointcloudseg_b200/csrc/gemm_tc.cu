@@ -812,6 +812,7 @@ constexpr int WS_PROD = 256;
 constexpr int WS_EPI = 256;
 constexpr int WS_KC = 32;                       // channels per ring stage
 constexpr int WS_NA = 2;                        // operand-image ring
+constexpr int WS_NA_IMG = 4;                    // ... when the images arrive ready-made (OP_IMG): raw area + ring = 4 stages
 constexpr int WS_NB_1 = 3, WS_NB_2 = 2;          // weight-chunk ring: one-operand maps / OP_DY (two operand streams to land)
 constexpr int WS_AGRP = TILE_M * 16 + 32;       // image group stride: 4 groups x 2 rows per quarter-warp hit 8 distinct 16-B banks
 constexpr int WS_RAW_BYTES_1 = 48 * 1024;       // cp.async landing slots (thread-private): 3 chunks of one operand in flight
@@ -862,10 +863,15 @@ rowgemm_ws_kernel(const Operand A, long long M, int N, int K, const Epilogue E, 
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int NOPS = (AMODE == OP_DY) ? 2 : 1;
   constexpr int WS_NB = (NOPS == 2) ? WS_NB_2 : WS_NB_1;
+  // OP_IMG: the operand arrives as ready-made chunk images (wspc_rows_image) by bulk copy -- the producer warps have nothing
+  // to do, and the cp.async landing area joins the image ring (4 stages instead of 2)
+  constexpr bool IMG = (AMODE == OP_IMG);
+  constexpr int NA_ = IMG ? WS_NA_IMG : WS_NA;
   const WsSmem sp = ws_smem_plan(NtMax, NOPS == 2);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sp.off_bar);
-  uint64_t *fullA = bars, *emptyA = bars + 2, *fullB = bars + 4, *emptyB = bars + 8, *accFull = bars + 12, *accEmpty = bars + 14;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t *fullA = bars, *emptyA = bars + 4, *fullB = bars + 8, *emptyB = bars + 12, *accFull = bars + 16, *accEmpty = bars + 18;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  unsigned char* const a_ring = smem + (IMG ? sp.off_raw : sp.off_a);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nkc = K / WS_KC;
   // CTA -> (column tile ny, every tstride-th row tile): neighbouring CTAs work on the same rows at the same time (the A rows
@@ -884,10 +890,10 @@ rowgemm_ws_kernel(const Operand A, long long M, int N, int K, const Epilogue E, 
     for (int i = 0; i < 4; ++i) {
       mbar_init(fullB + i, 1);
       mbar_init(emptyB + i, 1);
+      mbar_init(fullA + i, IMG ? 1 : WS_PROD / 32);  // one arrival per producer warp / the bulk copy's expect_tx
+      mbar_init(emptyA + i, 1);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(fullA + i, WS_PROD / 32);          // one arrival per producer warp
-      mbar_init(emptyA + i, 1);
       mbar_init(accFull + i, 1);
       mbar_init(accEmpty + i, WS_EPI / 32);
     }
@@ -900,6 +906,7 @@ rowgemm_ws_kernel(const Operand A, long long M, int N, int K, const Epilogue E, 
 
   if (tid < WS_PROD) {
     // ======================================================================== producers =====
+    if constexpr (!IMG) {
     constexpr int DEPTH = (NOPS == 2 ? WS_RAW_BYTES_2 : WS_RAW_BYTES_1) / (NOPS * 4 * WS_PROD * 16);   // chunks in flight: 3 / 2
     const int kg = tid & 3, rr = tid >> 2;                              // channel group of the chunk; rows rr, rr + 64
     unsigned char* raw = smem + sp.off_raw;
@@ -936,7 +943,7 @@ rowgemm_ws_kernel(const Operand A, long long M, int N, int K, const Epilogue E, 
 #pragma unroll
     for (int d = 0; d < DEPTH; ++d) issue(d);
     const uint32_t a_bytes_half = (WS_KC / 8) * WS_AGRP;
-    unsigned char* const a_img = smem + sp.off_a + (size_t)kg * WS_AGRP;
+    unsigned char* const a_img = a_ring + (size_t)kg * WS_AGRP;
     // consume cursor
     int b_kc = rot, b_left = nkc;
     long long b_row = (long long)tile0 * TILE_M + rr;
@@ -994,6 +1001,7 @@ rowgemm_ws_kernel(const Operand A, long long M, int N, int K, const Epilogue E, 
       issue(q + DEPTH);                                                 // refill the slot just consumed
     }
     cp_async_wait<0>();
+    }   // !IMG
   } else if (tid >= WS_PROD + WS_EPI) {
     // ================================================================ MMA issue + weight ring =====
     if (lane == 0) {
@@ -1007,16 +1015,30 @@ rowgemm_ws_kernel(const Operand A, long long M, int N, int K, const Epilogue E, 
       }
       const uint32_t idesc = umma_idesc(Ntp);
       const uint32_t a_bytes_half = (WS_KC / 8) * WS_AGRP;
+      // OP_IMG: operand chunk c of this CTA = image block (row tile, rotated chunk), one bulk copy into ring stage c % NA_
+      const unsigned char* aimg = reinterpret_cast<const unsigned char*>(A.p);
+      const uint32_t astage = 2u * a_bytes_half;
+      int ia_item = 0, ia_kc = 0;                                        // cursor of the next operand chunk to fetch
+      auto fetch_a = [&](int c) {
+        const int cs = c % NA_;
+        const size_t blk = (size_t)(tile0 + ia_item * tstride) * nkc + (size_t)((ia_kc + rot) % nkc);
+        mbar_expect_tx(fullA + cs, astage);
+        bulk_g2s(a_ring + (size_t)cs * astage, aimg + blk * astage, astage, fullA + cs);
+        if (++ia_kc == nkc) { ia_kc = 0; ++ia_item; }
+      };
+      if (IMG) {
+        for (int c = 0; c < NA_ && c < Q; ++c) fetch_a(c);
+      }
       int item = 0, kc = 0;
 #pragma unroll 1
       for (int q = 0; q < Q; ++q) {
-        const int s = q & 1, acc = item & 1, sb = q % WS_NB;
+        const int s = q % NA_, acc = item & 1, sb = q % WS_NB;
         if (kc == 0) mbar_wait(accEmpty + acc, ((uint32_t)(item >> 1) & 1u) ^ 1u);   // the epilogue drained this accumulator
         mbar_wait(fullB + sb, (uint32_t)(q / WS_NB) & 1u);
-        mbar_wait(fullA + s, (uint32_t)(q >> 1) & 1u);
-        fence_proxy_async_smem();
+        mbar_wait(fullA + s, (uint32_t)(q / NA_) & 1u);
+        if (!IMG) fence_proxy_async_smem();
         tc_fence_after();
-        const uint32_t ah = smem_u32(smem + sp.off_a + (size_t)s * 2 * a_bytes_half), al = ah + a_bytes_half;
+        const uint32_t ah = smem_u32(a_ring + (size_t)s * 2 * a_bytes_half), al = ah + a_bytes_half;
         const uint32_t bh = smem_u32(sB + (size_t)sb * bstage), bl = bh + (WS_KC / 8) * (uint32_t)sp.b_group_bytes;
         const uint32_t dcol = tmem_base + (uint32_t)acc * 256u;
 #pragma unroll
@@ -1039,6 +1061,13 @@ rowgemm_ws_kernel(const Operand A, long long M, int N, int K, const Epilogue E, 
           mbar_wait(emptyB + cs, ((uint32_t)(c / WS_NB) & 1u) ^ 1u);
           mbar_expect_tx(fullB + cs, bstage);
           bulk_g2s(sB + (size_t)cs * bstage, wsrc + (size_t)((c + rot) % nkc) * bstage, bstage, fullB + cs);
+        }
+        if (IMG) {
+          const int ca = q + NA_ - 1;                                   // operand chunk q+NA-1 goes where chunk q-1 was
+          if (ca >= NA_ && ca < Q) {
+            mbar_wait(emptyA + ca % NA_, ((uint32_t)(ca / NA_) & 1u) ^ 1u);
+            fetch_a(ca);
+          }
         }
         if (++kc == nkc) { kc = 0; ++item; }
       }
@@ -1239,6 +1268,60 @@ bool ws_rowgemm_enabled() {
     return !(e && strcmp(e, "serial") == 0);
   }();
   return on;
+}
+
+// ---- OP_IMG: pre-split operand image (wspc_rows_image) -------------------------------------------------------------
+bool ws_img_supported(long long M, int N, int K) {
+  if (!ws_rowgemm_enabled()) return false;
+  const TcPlan pl = tc_plan(N, K);
+  const long long num_tiles = (M + TILE_M - 1) / TILE_M;
+  return K > 128 && K % WS_KC == 0 && N % 16 == 0 && pl.ntiles_n <= kNumSM / 2 && num_tiles >= 4 * kNumSM && tc_wimg_bytes(N, K) > 0;
+}
+size_t ws_img_bytes(long long M, int K) {
+  return (size_t)((M + TILE_M - 1) / TILE_M) * (size_t)(K / WS_KC) * 2 * (WS_KC / 8) * WS_AGRP;
+}
+
+// grid = row tiles, block 256: thread = (channel group of the chunk, rows rr and rr + 64), as the producers of rowgemm_ws_kernel
+__global__ void __launch_bounds__(256)
+rows_image_kernel(const float* __restrict__ x, long long ldx, long long M, int K, unsigned char* __restrict__ img) {
+  const int tid = threadIdx.x, kg = tid & 3, rr = tid >> 2;
+  const int nkc = K / WS_KC;
+  const long long row0 = (long long)blockIdx.x * TILE_M;
+  constexpr uint32_t half = (WS_KC / 8) * WS_AGRP;
+  for (int kc = 0; kc < nkc; ++kc) {
+    unsigned char* blk = img + ((size_t)blockIdx.x * nkc + kc) * (2 * half);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int r = rr + 64 * i;
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = 0.f;
+      if (row0 + r < M) ld8(x + (row0 + r) * ldx + kc * WS_KC + kg * 8, v);
+      uint4 hi, lo;
+      split8(v, hi, lo);
+      *reinterpret_cast<uint4*>(blk + (size_t)kg * WS_AGRP + r * 16) = hi;
+      *reinterpret_cast<uint4*>(blk + half + (size_t)kg * WS_AGRP + r * 16) = lo;
+    }
+    if (tid < 16)    // the 32 pad bytes of every group travel with the bulk copy: keep them defined
+      *reinterpret_cast<uint4*>(blk + (size_t)(tid & 7) * WS_AGRP + TILE_M * 16 + (tid >> 3) * 16) = make_uint4(0, 0, 0, 0);
+  }
+}
+
+template <int EMODE>
+int launch_ws_img(const Operand& A, const float* Bm, long long ldb, int bT, long long M, int N, int K, const Epilogue& E, void* ws,
+                  cudaStream_t st) {
+  const TcPlan pl = tc_plan(N, K);
+  const int num_tiles = (int)((M + TILE_M - 1) / TILE_M);
+  wprep_kernel<<<dim3(K / WS_KC, pl.ntiles_n), 256, 0, st>>>(Bm, ldb, bT, N, K, WS_KC, pl.NtMax, static_cast<unsigned char*>(ws));
+  count_launch();
+  const WsSmem wp = ws_smem_plan(pl.NtMax, false);
+  const int grid = kNumSM / pl.ntiles_n * pl.ntiles_n;
+  auto kern = rowgemm_ws_kernel<OP_IMG, EMODE, 4>;
+  WSPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wp.total));
+  kern<<<grid, WS_THREADS, wp.total, st>>>(A, M, N, K, E, num_tiles, pl.NtMax, pl.ntiles_n, static_cast<const unsigned char*>(ws));
+  count_launch();
+  WSPC_LAUNCH_CHECK("rowgemm_ws_kernel(image operand)");
+  return WSPC_OK;
 }
 
 // conv2d -> (BN -> ReLU) -> max over the cloud's points without writing the conv output: eligibility and launch
@@ -1777,6 +1860,18 @@ size_t rowgemm_tc_workspace_bytes(int N, int K) { return tc_wimg_bytes(N, K); }
 
 int rowgemm_tc_dispatch(const Operand& A, int amode, const float* Bm, long long ldb, int bT, long long M, int N, int K,
                         const Epilogue& E, int emode, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (amode == OP_IMG) {       // pre-split image operand: the warp-specialised kernel or nothing
+    const bool ok = ws_img_supported(M, N, K) && ws && ws_bytes >= tc_wimg_bytes(N, K) && aligned16(ws) && aligned16(A.p) &&
+                    (emode == EPI_STORE || emode == EPI_STORE_STATS) && aligned16(E.out) && (E.ldo % 4) == 0;
+    if (!ok) {
+      set_error("conv1x1_rows: WSPC_OP_IMG needs an eligible shape (wspc_rows_image_supported), the weight-image workspace and a "
+                "STORE / STORE_STATS epilogue");
+      return WSPC_ERR_INVALID;
+    }
+    const int rc = emode == EPI_STORE ? launch_ws_img<EPI_STORE>(A, Bm, ldb, bT, M, N, K, E, ws, st)
+                                      : launch_ws_img<EPI_STORE_STATS>(A, Bm, ldb, bT, M, N, K, E, ws, st);
+    return rc == WSPC_OK ? 1 : rc;
+  }
   if (!tc_supported(A, amode, Bm, M, N, K, E, emode)) return 0;
   int rc = -100;
 #define WSPC_TC(AM, EM) \
@@ -1806,11 +1901,13 @@ extern "C" int wspc_conv1x1_pool_fwd(const wspc_operand_t* A, int a_mode, const 
   using namespace wspc;
   if (int rc = check_arch()) return rc;
   WSPC_REQUIRE(A && W && gamma && stats && keys && workspace, "conv1x1_pool_fwd: null argument");
-  WSPC_REQUIRE(a_mode == OP_PLAIN || a_mode == OP_BNRELU, "conv1x1_pool_fwd: operand mode %d (PLAIN or BNRELU)", a_mode);
+  WSPC_REQUIRE(a_mode == OP_PLAIN || a_mode == OP_BNRELU || a_mode == OP_IMG, "conv1x1_pool_fwd: operand mode %d (PLAIN, BNRELU or IMG)",
+               a_mode);
   WSPC_REQUIRE(A->p && A->C == K, "conv1x1_pool_fwd: operand channels %d != K %d", A->C, K);
   WSPC_REQUIRE(ws_pool_supported(M, N, K, npts), "conv1x1_pool_fwd: shape M=%lld N=%d K=%d npts=%d is not eligible "
                "(wspc_conv1x1_pool_supported)", M, N, K, npts);
-  WSPC_REQUIRE(tc_operand_fast(*A, a_mode, K) && !(a_mode == OP_BNRELU && A->dmask), "conv1x1_pool_fwd: operand must be 16-byte aligned");
+  WSPC_REQUIRE(a_mode == OP_IMG ? aligned16(A->p) : (tc_operand_fast(*A, a_mode, K) && !(a_mode == OP_BNRELU && A->dmask)),
+               "conv1x1_pool_fwd: operand must be 16-byte aligned");
   if (workspace_bytes < tc_wimg_bytes(N, K) || !aligned16(workspace)) {
     set_error("conv1x1_pool_fwd: workspace too small (wspc_conv1x1_rows_workspace_bytes)");
     return WSPC_ERR_WORKSPACE;
@@ -1823,6 +1920,7 @@ extern "C" int wspc_conv1x1_pool_fwd(const wspc_operand_t* A, int a_mode, const 
   E.scp = gamma;
   E.dx = reinterpret_cast<float*>(keys);
   E.npts = npts;
+  if (a_mode == OP_IMG) return launch_ws_pool<OP_IMG>(*A, W, ldw, M, N, K, E, workspace, st);
   if (a_mode == OP_PLAIN) return launch_ws_pool<OP_PLAIN>(*A, W, ldw, M, N, K, E, workspace, st);
   return launch_ws_pool<OP_BNRELU>(*A, W, ldw, M, N, K, E, workspace, st);
 }
@@ -1837,5 +1935,23 @@ extern "C" int wspc_maxn_from_keys(const unsigned long long* keys, const float* 
                                                                                                           total, C, g, amax, ymax);
   count_launch();
   WSPC_LAUNCH_CHECK("pool_keys_finish_kernel");
+  return WSPC_OK;
+}
+
+// pre-split operand image (see include/wspc.h)
+extern "C" size_t wspc_rows_image_bytes(long long M, int K) {
+  return (M >= 1 && K >= 32 && K % 32 == 0) ? wspc::ws_img_bytes(M, K) : 0;
+}
+extern "C" int wspc_rows_image_supported(long long M, int N, int K) { return wspc::ws_img_supported(M, N, K) ? 1 : 0; }
+extern "C" int wspc_rows_image(const float* x, long long ldx, long long M, int K, void* image, wspc_stream_t stream) {
+  using namespace wspc;
+  if (int rc = check_arch()) return rc;
+  WSPC_REQUIRE(x && image && M >= 1, "rows_image: null argument");
+  WSPC_REQUIRE(K >= 32 && K % 32 == 0 && (ldx % 4) == 0 && ldx >= K && aligned16(x) && aligned16(image),
+               "rows_image: K=%d must be a multiple of 32 and the rows 16-byte aligned", K);
+  const long long tiles = (M + TILE_M - 1) / TILE_M;
+  rows_image_kernel<<<(unsigned)tiles, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, ldx, M, K, static_cast<unsigned char*>(image));
+  count_launch();
+  WSPC_LAUNCH_CHECK("rows_image_kernel");
   return WSPC_OK;
 }

@@ -11,13 +11,14 @@
 //   OP_DY         c1[c]*G[row,c] + c2[c] + c3[c]*y[row,c]   (BN backward folded to an affine map)
 //   OP_DY_SPARSE  same, with G given as the per-cloud arg-max scatter of max_pool2d's gradient
 //   OP_DY_MAXK    same, with G synthesised from the max over k: G = (relu(bn(y)) == max) ? dout / #ties : 0
+//   OP_IMG        a[row, c] given as the pre-split bf16 hi / lo tile image of wspc_rows_image (no loader work at all)
 #pragma once
 #include "common.cuh"
 
 namespace wspc {
 
 enum OpMode : int { OP_PLAIN = WSPC_OP_PLAIN, OP_BNRELU = WSPC_OP_BNRELU, OP_EDGE = WSPC_OP_EDGE, OP_DY = WSPC_OP_DY,
-                    OP_DY_SPARSE = WSPC_OP_DY_SPARSE, OP_DY_MAXK = WSPC_OP_DY_MAXK };
+                    OP_DY_SPARSE = WSPC_OP_DY_SPARSE, OP_DY_MAXK = WSPC_OP_DY_MAXK, OP_IMG = WSPC_OP_IMG };
 
 // gradient of tf.reduce_max over k at one element: a = relu(y*sc+sh) is the activation, m the pooled maximum, share = dout/#ties
 __device__ __forceinline__ float maxk_grad(float y, float sc, float sh, float m, float share) {

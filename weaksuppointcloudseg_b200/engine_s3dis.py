@@ -60,6 +60,7 @@ class S3DISEngine:
         self.cat, self.dcat = torch.empty((P, 192), **f32), torch.empty((P, 192), **f32)
         # adj_conv7 + max over points in one pass (no (P,1024) tensor) when the Gram-identity backward is on and the shape fits
         self.pool_fused = rt.POOLCONV_GRAM and rt.pool_fusable(P, 1024, 192, N)
+        self.cat_img = rt.RowImage(P, 192, self.dev) if rt.RowImage.usable(P, 192, (1024, 512)) else None
         if self.pool_fused:
             self.y7 = None
             self.pool_keys = torch.empty((B, 1024), dtype=torch.int64, device=self.dev)
@@ -163,19 +164,21 @@ class S3DISEngine:
         Ly = self.layers
         # adj_conv7 + max over points                                                   (:80-85)
         l7 = Ly["adj_conv7"]
+        cat_op = rt.op_plain(self.cat, 192, 192)
+        if self.cat_img is not None:     # adj_conv7 and seg/conv1 both read the concatenated features: split them once
+            self.cat_img.build(self.cat, 192)
+            cat_op = self.cat_img.operand()
         if self.pool_fused:     # the (P, 1024) pre-BN tensor is never written: BN sums + arg-max rows in the GEMM epilogue
-            rt.conv_pool_forward(l7, rt.op_plain(self.cat, 192, 192), P, N, self.pool_keys, self.g, self.amax, self.y7max,
-                                 is_training, bn_decay)
+            rt.conv_pool_forward(l7, cat_op, P, N, self.pool_keys, self.g, self.amax, self.y7max, is_training, bn_decay)
         else:
-            rt.conv_forward(l7, rt.op_plain(self.cat, 192, 192), P, self.y7, 1024, is_training, bn_decay)
+            rt.conv_forward(l7, cat_op, P, self.y7, 1024, is_training, bn_decay)
             L.check(L.lib().wspc_maxn_bnrelu_fwd(L.ptr(self.y7), L.ptr(l7.sc), L.ptr(l7.sh), B, N, 1024, L.ptr(self.g),
                                                  L.ptr(self.amax), L.stream()))
         # seg/conv1 with the tiled global feature folded into a per-cloud bias          (:87-96)
         s1, s2, s3 = Ly["seg/conv1"], Ly["seg/conv2"], Ly["seg/conv3"]
         epi = L.Epilogue(out=L.dptr(self.gW), ldo=512)
         rt.rows_gemm(rt.op_plain(self.g, 1024, 1024), s1.W, 512, 0, B, 512, 1024, epi, L.EPI_STORE)
-        rt.conv_forward(s1, rt.op_plain(self.cat, 192, 192), P, self.ys1, 512, is_training, None, rowbias=self.gW,
-                        rb_rows=N, Wview=s1.W[1024:])
+        rt.conv_forward(s1, cat_op, P, self.ys1, 512, is_training, None, rowbias=self.gW, rb_rows=N, Wview=s1.W[1024:])
         rt.conv_forward(s2, rt.op_bnrelu(self.ys1, s1), P, self.ys2, 256, is_training, None)       # (:97-98)
         # dropout (:99) fused into seg/conv3's operand load (:100-101)
         self._mask = None

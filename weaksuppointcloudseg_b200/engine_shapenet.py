@@ -77,6 +77,7 @@ class ShapeNetEngine:
         self.Ga = torch.empty((R, 64), **f32)
         self.cat, self.dcat = torch.empty((P, 192), **f32), torch.empty((P, 192), **f32)
         self.pool_fused = rt.POOLCONV_GRAM and rt.pool_fusable(P, 1024, 192, N)
+        self.cat_img = rt.RowImage(P, 192, self.dev) if rt.RowImage.usable(P, 192, (1024, 256)) else None
         if self.pool_fused:
             self.y7 = None
             self.pool_keys = torch.empty((B, 1024), dtype=torch.int64, device=self.dev)
@@ -177,10 +178,14 @@ class ShapeNetEngine:
         B, N, P = self.B, self.N, self.P
         Ly = self.layers
         l7 = Ly["adj_conv7"]
+        cat_op = rt.op_plain(self.cat, 192, 192)
+        if self.cat_img is not None:     # adj_conv7 and seg/conv1 both read the concatenated features: split them once
+            self.cat_img.build(self.cat, 192)
+            cat_op = self.cat_img.operand()
         if self.pool_fused:     # :80-85 in one pass, the (P, 1024) pre-BN tensor is never written
-            rt.conv_pool_forward(l7, rt.op_plain(self.cat, 192, 192), P, N, self.pool_keys, self.g, self.amax, self.y7max, tr, d)
+            rt.conv_pool_forward(l7, cat_op, P, N, self.pool_keys, self.g, self.amax, self.y7max, tr, d)
         else:
-            rt.conv_forward(l7, rt.op_plain(self.cat, 192, 192), P, self.y7, 1024, tr, d)                 # :80-83
+            rt.conv_forward(l7, cat_op, P, self.y7, 1024, tr, d)                                          # :80-83
             L.check(L.lib().wspc_maxn_bnrelu_fwd(L.ptr(self.y7), L.ptr(l7.sc), L.ptr(l7.sh), B, N, 1024, L.ptr(self.g),
                                                  L.ptr(self.amax), L.stream()))                           # :85
         # ---- category branch + folded global feature                         (:87-101)
@@ -191,7 +196,7 @@ class ShapeNetEngine:
                      L.EPI_STORE)
         rt.rows_gemm(rt.op_bnrelu(self.ylab, lab), s1.W[1024:], 256, 0, B, 256, 64,
                      L.Epilogue(out=L.dptr(self.gW), ldo=256), L.EPI_ACCUM)
-        rt.conv_forward(s1, rt.op_plain(self.cat, 192, 192), P, self.ys1, 256, tr, d, rowbias=self.gW, rb_rows=N,
+        rt.conv_forward(s1, cat_op, P, self.ys1, 256, tr, d, rowbias=self.gW, rb_rows=N,
                         Wview=s1.W[1088:])
         # ---- dropouts fused into the next layer's operand load               (:102-109)
         self._m1 = self._m2 = None

@@ -127,6 +127,29 @@ def op_plain(t, ld, C):
     return L.Operand(p=L.dptr(t), ld=ld, C=C), L.OP_PLAIN
 
 
+# WSPC_ROWIMG=off keeps the fp32 operand loaders for the layers that read the concatenated EdgeConv features (A/B tests)
+ROW_IMAGE = os.environ.get("WSPC_ROWIMG", "on") != "off"
+
+
+class RowImage:
+    """Pre-split (bf16 hi / lo, tensor-core tile layout) copy of a (M, K) matrix that several GEMMs read: written once per
+    step by wspc_rows_image, consumed as WSPC_OP_IMG with one bulk copy per chunk (no CUDA-core operand work)."""
+
+    def __init__(self, M, K, device):
+        self.M, self.K = M, K
+        self.buf = torch.empty(L.lib().wspc_rows_image_bytes(M, K), dtype=torch.uint8, device=device)
+
+    @staticmethod
+    def usable(M, K, couts):
+        return ROW_IMAGE and all(L.lib().wspc_rows_image_supported(M, n, K) for n in couts)
+
+    def build(self, x, ld):
+        L.check(L.lib().wspc_rows_image(L.ptr(x), ld, self.M, self.K, L.ptr(self.buf), L.stream()))
+
+    def operand(self):
+        return L.Operand(p=L.dptr(self.buf), ld=self.K, C=self.K), L.OP_IMG
+
+
 def op_bnrelu(y, layer: Layer, dmask=None, keep=1.0):
     return (L.Operand(p=L.dptr(y), ld=layer.cout, C=layer.cout, sc=L.dptr(layer.sc), sh=L.dptr(layer.sh),
                       dmask=L.dptr(dmask), dscale=1.0 / keep), L.OP_BNRELU)
