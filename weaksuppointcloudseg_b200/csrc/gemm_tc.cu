@@ -96,6 +96,22 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// the same split for 4 values (same arithmetic per element as split8)
+__device__ __forceinline__ void split4(const float (&v)[4], uint2& hi, uint2& lo) {
+  uint32_t h[2], l[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const __nv_bfloat162 hp = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    const uint32_t hb = *reinterpret_cast<const uint32_t*>(&hp);
+    const float h0 = __uint_as_float(hb << 16), h1 = __uint_as_float(hb & 0xffff0000u);
+    const __nv_bfloat162 lp = __floats2bfloat162_rn(v[2 * i] - h0, v[2 * i + 1] - h1);
+    h[i] = hb;
+    l[i] = *reinterpret_cast<const uint32_t*>(&lp);
+  }
+  hi = make_uint2(h[0], h[1]);
+  lo = make_uint2(l[0], l[1]);
+}
+
 __device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
   const float4 a = *reinterpret_cast<const float4*>(p);
   const float4 b = *reinterpret_cast<const float4*>(p + 4);
@@ -822,7 +838,7 @@ constexpr int WS_STAGE_LD = 36;                 // epilogue staging pitch (float
 struct WsSmem {
   int b_group_bytes;
   uint32_t bstage;
-  size_t off_raw, off_a, off_b, off_stage, off_bar, total;
+  size_t off_raw, off_a, off_b, off_stage, off_bar, off_pool, total;
 };
 __host__ __device__ inline WsSmem ws_smem_plan(int NtMax, bool two_ops) {
   WsSmem s;
@@ -835,6 +851,7 @@ __host__ __device__ inline WsSmem ws_smem_plan(int NtMax, bool two_ops) {
   s.off_b = o; o += ((size_t)(two_ops ? WS_NB_2 : WS_NB_1) * s.bstage + 127) / 128 * 128;
   s.off_stage = o; o += (size_t)8 * 32 * WS_STAGE_LD * 4;      // one 32 x 32 staging tile per epilogue warp
   s.off_bar = o; o += 256;
+  s.off_pool = o; o += 8 * 128 * 8;                 // EPI_STATS_POOL: running (value, row) keys, 128 columns per epilogue warp
   s.total = o;
   return s;
 }
@@ -876,8 +893,15 @@ rowgemm_ws_kernel(const Operand A, long long M, int N, int K, const Epilogue E, 
   const int nkc = K / WS_KC;
   // CTA -> (column tile ny, every tstride-th row tile): neighbouring CTAs work on the same rows at the same time (the A rows
   // of the second column tile come from L2) and a CTA's BN statistics stay with fixed columns
-  const int ny = blockIdx.x % ntn, tile0 = blockIdx.x / ntn, tstride = gridDim.x / ntn;
-  const int n_items = (num_tiles > tile0) ? (num_tiles - tile0 + tstride - 1) / tstride : 0;
+  // the pooled epilogue walks CONTIGUOUS row tiles (tstride = 1) so that a CTA sees a cloud's tiles one after the other and
+  // keeps the running per-column extreme on chip; the other epilogues take every (grid / ntn)-th tile
+  constexpr bool kContig = (EMODE == EPI_STATS_POOL);
+  const int ngroups = gridDim.x / ntn;
+  const int per_cta = (num_tiles + ngroups - 1) / ngroups;
+  const int ny = blockIdx.x % ntn, tile0 = kContig ? (blockIdx.x / ntn) * per_cta : blockIdx.x / ntn;
+  const int tstride = kContig ? 1 : ngroups;
+  const int n_items = kContig ? (num_tiles > tile0 ? (num_tiles - tile0 < per_cta ? num_tiles - tile0 : per_cta) : 0)
+                              : ((num_tiles > tile0) ? (num_tiles - tile0 + tstride - 1) / tstride : 0);
   const int n0 = ny * NtMax;
   const int Nt = (N - n0 < NtMax) ? (N - n0) : NtMax;
   const int Ntp = (Nt + 15) / 16 * 16;
@@ -908,31 +932,27 @@ rowgemm_ws_kernel(const Operand A, long long M, int N, int K, const Epilogue E, 
     // ======================================================================== producers =====
     if constexpr (!IMG) {
     constexpr int DEPTH = (NOPS == 2 ? WS_RAW_BYTES_2 : WS_RAW_BYTES_1) / (NOPS * 4 * WS_PROD * 16);   // chunks in flight: 3 / 2
-    const int kg = tid & 3, rr = tid >> 2;                              // channel group of the chunk; rows rr, rr + 64
+    // thread = (16-byte piece pc of the chunk's 128-byte rows, rows rl + 4j): every cp.async instruction of a warp covers four
+    // whole 128-byte lines (the group-per-thread mapping touched eight half-used lines: twice the shared-memory write passes)
+    const int pc = lane & 7, rl = (tid >> 5) * 16 + (lane >> 3);
     unsigned char* raw = smem + sp.off_raw;
     auto slot = [&](int d, int piece) { return raw + ((size_t)(d * (NOPS * 4) + piece) * WS_PROD + tid) * 16; };
     const bool two_ops = (AMODE == OP_DY) && A.c1 != nullptr;
     const int Q = n_items * nkc;
     // fetch cursor: chunk index inside the tile (already rotated) and the thread's first row of the tile
     int f_kc = rot, f_left = nkc;
-    long long f_row = (long long)tile0 * TILE_M + rr;
+    long long f_row = (long long)tile0 * TILE_M + rl;
     const long long row_step = (long long)tstride * TILE_M;
     auto issue = [&](int q) {
       if (q < Q) {
-        const int c0 = f_kc * WS_KC + kg * 8;
+        const int c0 = f_kc * WS_KC + pc * 4;
         const int d = q % DEPTH;
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const long long row = f_row + 64 * i;
+        for (int j = 0; j < 4; ++j) {
+          const long long row = f_row + 4 * j;
           if (row < M) {
-            const float* src = A.p + row * A.ld + c0;
-            cp_async16(slot(d, i * 2), src);
-            cp_async16(slot(d, i * 2 + 1), src + 4);
-            if (NOPS == 2 && two_ops) {
-              const float* sy = A.y + row * A.ldy + c0;
-              cp_async16(slot(d, 4 + i * 2), sy);
-              cp_async16(slot(d, 4 + i * 2 + 1), sy + 4);
-            }
+            cp_async16(slot(d, j), A.p + row * A.ld + c0);
+            if (NOPS == 2 && two_ops) cp_async16(slot(d, 4 + j), A.y + row * A.ldy + c0);
           }
         }
         if (++f_kc == nkc) f_kc = 0;
@@ -943,43 +963,47 @@ rowgemm_ws_kernel(const Operand A, long long M, int N, int K, const Epilogue E, 
 #pragma unroll
     for (int d = 0; d < DEPTH; ++d) issue(d);
     const uint32_t a_bytes_half = (WS_KC / 8) * WS_AGRP;
-    unsigned char* const a_img = a_ring + (size_t)kg * WS_AGRP;
+    unsigned char* const a_img = a_ring + (size_t)(pc >> 1) * WS_AGRP + (pc & 1) * 8;
     // consume cursor
     int b_kc = rot, b_left = nkc;
-    long long b_row = (long long)tile0 * TILE_M + rr;
-    // one chunk: raw slot -> operand map -> bf16 hi / lo image of ring stage s
+    long long b_row = (long long)tile0 * TILE_M + rl;
+    // one chunk: raw slots -> operand map -> bf16 hi / lo image of ring stage s
     auto build = [&](int q, int s, int kcr, long long row_a) {
-      const int cg = kcr * (WS_KC / 8) + kg;
-      float pc0[8], pc1[8], pc2[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { pc0[i] = 0.f; pc1[i] = 0.f; pc2[i] = 0.f; }
-      if (AMODE == OP_BNRELU) { ld8(A.sc + cg * 8, pc0); ld8(A.sh + cg * 8, pc1); }
-      if (AMODE == OP_DY && two_ops) { ld8(A.c1 + cg * 8, pc0); ld8(A.c2 + cg * 8, pc1); ld8(A.c3 + cg * 8, pc2); }
-      RawChunk w[2];
+      const int c0 = kcr * WS_KC + pc * 4;
+      float4 k0 = make_float4(0.f, 0.f, 0.f, 0.f), k1 = k0, k2 = k0;
+      if (AMODE == OP_BNRELU) {
+        k0 = *reinterpret_cast<const float4*>(A.sc + c0);
+        k1 = *reinterpret_cast<const float4*>(A.sh + c0);
+      }
+      if (AMODE == OP_DY && two_ops) {
+        k0 = *reinterpret_cast<const float4*>(A.c1 + c0);
+        k1 = *reinterpret_cast<const float4*>(A.c2 + c0);
+        k2 = *reinterpret_cast<const float4*>(A.c3 + c0);
+      }
       const int d = q % DEPTH;
+      float4 a[4], b[4];
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const float4 a0 = *reinterpret_cast<const float4*>(slot(d, i * 2));
-        const float4 a1 = *reinterpret_cast<const float4*>(slot(d, i * 2 + 1));
-        w[i].a[0] = a0.x; w[i].a[1] = a0.y; w[i].a[2] = a0.z; w[i].a[3] = a0.w;
-        w[i].a[4] = a1.x; w[i].a[5] = a1.y; w[i].a[6] = a1.z; w[i].a[7] = a1.w;
-        if (NOPS == 2) {
-          const float4 b0 = *reinterpret_cast<const float4*>(slot(d, 4 + i * 2));
-          const float4 b1 = *reinterpret_cast<const float4*>(slot(d, 4 + i * 2 + 1));
-          w[i].b[0] = b0.x; w[i].b[1] = b0.y; w[i].b[2] = b0.z; w[i].b[3] = b0.w;
-          w[i].b[4] = b1.x; w[i].b[5] = b1.y; w[i].b[6] = b1.z; w[i].b[7] = b1.w;
-        }
+      for (int j = 0; j < 4; ++j) {
+        a[j] = *reinterpret_cast<const float4*>(slot(d, j));
+        if (NOPS == 2) b[j] = *reinterpret_cast<const float4*>(slot(d, 4 + j));
       }
       unsigned char* a_hi = a_img + (size_t)s * 2 * a_bytes_half;
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const long long row = row_a + 64 * i;
-        float v[8];
-        finish_chunk<AMODE>(A, row, cg, row < M, 0, 0, pc0, pc1, pc2, w[i], v);
-        uint4 hi, lo;
-        split8(v, hi, lo);
-        *reinterpret_cast<uint4*>(a_hi + (rr + 64 * i) * 16) = hi;
-        *reinterpret_cast<uint4*>(a_hi + a_bytes_half + (rr + 64 * i) * 16) = lo;
+      for (int j = 0; j < 4; ++j) {
+        float v[4] = {a[j].x, a[j].y, a[j].z, a[j].w};
+        if (AMODE == OP_BNRELU) {
+          v[0] = fmaxf(fmaf(v[0], k0.x, k1.x), 0.f); v[1] = fmaxf(fmaf(v[1], k0.y, k1.y), 0.f);
+          v[2] = fmaxf(fmaf(v[2], k0.z, k1.z), 0.f); v[3] = fmaxf(fmaf(v[3], k0.w, k1.w), 0.f);
+        }
+        if (AMODE == OP_DY && two_ops) {
+          v[0] = fmaf(k0.x, v[0], fmaf(k2.x, b[j].x, k1.x)); v[1] = fmaf(k0.y, v[1], fmaf(k2.y, b[j].y, k1.y));
+          v[2] = fmaf(k0.z, v[2], fmaf(k2.z, b[j].z, k1.z)); v[3] = fmaf(k0.w, v[3], fmaf(k2.w, b[j].w, k1.w));
+        }
+        if (row_a + 4 * j >= M) { v[0] = 0.f; v[1] = 0.f; v[2] = 0.f; v[3] = 0.f; }
+        uint2 hi, lo;
+        split4(v, hi, lo);
+        *reinterpret_cast<uint2*>(a_hi + (rl + 4 * j) * 16) = hi;
+        *reinterpret_cast<uint2*>(a_hi + a_bytes_half + (rl + 4 * j) * 16) = lo;
       }
     };
     auto advance = [&]() {
@@ -1090,6 +1114,25 @@ rowgemm_ws_kernel(const Operand A, long long M, int N, int K, const Epilogue E, 
 #pragma unroll
         for (int j = 0; j < 4; ++j) { st0[p][j] = 0.0; st1[p][j] = 0.0; }
     }
+    // EPI_STATS_POOL: lanes with sr == 0 own 16 columns (4 blocks x 4) of this warp's running keys for the current cloud
+    unsigned long long* pool_run = reinterpret_cast<unsigned long long*>(smem + sp.off_pool) + ew * 128 + cq * 4;
+    long long pool_cloud = -1;
+    auto pool_flush = [&]() {
+      if (EMODE == EPI_STATS_POOL && sr == 0 && pool_cloud >= 0) {
+        unsigned long long* keys = reinterpret_cast<unsigned long long*>(E.dx) + pool_cloud * N + n0 + chh * 128 + cq * 4;
+#pragma unroll
+        for (int nb = 0; nb < NBLK; ++nb)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (chh * 128 + nb * 32 + cq * 4 + j < Nt && pool_run[nb * 32 + j] != 0ull) atomicMax(keys + nb * 32 + j, pool_run[nb * 32 + j]);
+      }
+    };
+    if (EMODE == EPI_STATS_POOL && sr == 0) {
+#pragma unroll
+      for (int nb = 0; nb < NBLK; ++nb)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pool_run[nb * 32 + j] = 0ull;
+    }
     int last_blk = -1;                            // last 32-column block of this warp's half that holds columns
 #pragma unroll
     for (int nb = 0; nb < NBLK; ++nb)
@@ -1105,6 +1148,19 @@ rowgemm_ws_kernel(const Operand A, long long M, int N, int K, const Epilogue E, 
       if (last_blk < 0) {                         // this warp's column half is empty: nothing to read, hand the accumulator back
         if (lane == 0) mbar_arrive(accEmpty + acc);
         continue;
+      }
+      if (EMODE == EPI_STATS_POOL) {              // a new cloud starts: publish the finished one, restart the running keys
+        const long long cloud = row0 / E.npts;
+        if (cloud != pool_cloud) {
+          pool_flush();
+          if (sr == 0) {
+#pragma unroll
+            for (int nb = 0; nb < NBLK; ++nb)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) pool_run[nb * 32 + j] = 0ull;
+          }
+          pool_cloud = cloud;
+        }
       }
       long long rb_cloud0 = 0;
       uint32_t rb_rem0 = 0;
@@ -1165,7 +1221,6 @@ rowgemm_ws_kernel(const Operand A, long long M, int N, int K, const Epilogue E, 
                 if (ys > best[j]) { best[j] = ys; brow[j] = r; }
               }
             }
-            unsigned long long* keys = reinterpret_cast<unsigned long long*>(E.dx) + (row0 / E.npts) * N + cbase;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               unsigned long long key = (row0 + rbase < M)
@@ -1175,7 +1230,7 @@ rowgemm_ws_kernel(const Operand A, long long M, int N, int K, const Epilogue E, 
               if (other > key) key = other;
               other = __shfl_xor_sync(0xffffffffu, key, 16);
               if (other > key) key = other;
-              if (sr == 0) atomicMax(keys + j, key);
+              if (sr == 0 && key > pool_run[nb * 32 + j]) pool_run[nb * 32 + j] = key;
             }
           } else {
             float4 pre[8];
@@ -1237,6 +1292,7 @@ rowgemm_ws_kernel(const Operand A, long long M, int N, int K, const Epilogue E, 
         __syncwarp();        // the staging tile may be overwritten by the next block
       }
     }
+    pool_flush();
     if (kStats) {
 #pragma unroll
       for (int nb = 0; nb < NBLK; ++nb) {
