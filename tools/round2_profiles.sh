@@ -14,6 +14,9 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --lo
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:edgeconv2 -c 4 -o gpurun_out/${T}_edgeconv python tools/prof_edgeconv.py 32 4096 20 1 > gpurun_out/${T}_ncu_ec.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:knn_tc_kernel -s 2 -c 1 -o gpurun_out/${T}_knn_k20 python tools/time_knn.py 16 ncu > gpurun_out/${T}_ncu_knn.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:knn_tc_kernel -s 5 -c 1 -o gpurun_out/${T}_knn_k40 python tools/time_knn.py 16 ncu > gpurun_out/${T}_ncu_knn40.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:rowgemm_ws -s 27 -c 1 -o gpurun_out/${T}_rowgemm_ws python tools/time_rowgemm.py > gpurun_out/${T}_ncu_rowgemm.log 2>&1
+timeout 200 python tools/time_rowgemm.py > gpurun_out/${T}_time_rowgemm_ws.log 2>&1
+WSPC_ROWGEMM_KERNEL=serial timeout 200 python tools/time_rowgemm.py > gpurun_out/${T}_time_rowgemm_serial.log 2>&1
 timeout 300 ncu --set full --clock-control none -k regex:lpb_matvec -s 4 -c 1 -o gpurun_out/${T}_lp python tools/time_lp_blocks.py 8 4096 2.0 > gpurun_out/${T}_ncu_lp.log 2>&1
 timeout 200 python tools/time_lp_blocks.py 64 4096 2.0 > gpurun_out/${T}_time_lp.log 2>&1
 timeout 200 python tools/prof_edgeconv.py 128 4096 20 3 > gpurun_out/${T}_time_edgeconv.log 2>&1
