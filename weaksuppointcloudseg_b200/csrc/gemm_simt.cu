@@ -384,6 +384,75 @@ int launch_wgrad_g(const Operand& A, const Operand& G, int gmode, long long M, c
 }
 
 
+// ---------------------------------------------------------------- narrow inputs (K1 <= 12) ---
+// Weight gradient of a layer with a handful of input channels (the factored first EdgeConv layer: X (P, 9 or 3) against the
+// (P, 128) gradient of [u | v], tf_util.py:160-165 backward): dW(K1, K2) = X^T G.  The general kernels tile K1 to 64 and spend
+// their time on padding; here a thread owns 4 gradient columns and all K1 rows of dW, streams G once with float4 loads
+// (the only HBM traffic that matters: K2 * 4 B per row) and reads the row's inputs from a staged shared-memory tile.
+constexpr int NK1_ROWS = 256;      // rows of X staged per round
+__global__ void __launch_bounds__(256)
+wgrad_narrowk1_kernel(const float* __restrict__ X, long long ldx, int K1, const float* __restrict__ G, long long ldg, int K2,
+                      long long M, long long rps, int K1p, int K2p, float* __restrict__ partial, float* __restrict__ partial_b) {
+  __shared__ __align__(16) float sx[NK1_ROWS * 12];
+  __shared__ __align__(16) float red[256 * 4];
+  const int tid = threadIdx.x;
+  const int nq = K2 >> 2;                   // column quads
+  const int cq = tid % nq, rp = tid / nq, RP = 256 / nq;
+  const long long r0 = (long long)blockIdx.x * rps;
+  const long long r1 = (r0 + rps < M) ? r0 + rps : M;
+  float acc[12][4], accb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 12; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; acc[j][3] = 0.f; }
+  for (long long base = r0; base < r1; base += NK1_ROWS) {
+    for (int e = tid; e < NK1_ROWS * 12; e += 256) {
+      const int rr = e / 12, j = e - rr * 12;
+      const long long row = base + rr;
+      sx[e] = (j < K1 && row < r1) ? X[row * ldx + j] : 0.f;
+    }
+    __syncthreads();
+    const int nrow = (r1 - base < NK1_ROWS) ? (int)(r1 - base) : NK1_ROWS;
+#pragma unroll 4
+    for (int rr = rp; rr < nrow; rr += RP) {
+      const float4 g = __ldcs(reinterpret_cast<const float4*>(G + (base + rr) * ldg + cq * 4));
+      const float4* xr = reinterpret_cast<const float4*>(sx + rr * 12);
+      const float4 x0 = xr[0], x1 = xr[1], x2 = xr[2];
+      const float xv[12] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w, x2.x, x2.y, x2.z, x2.w};
+#pragma unroll
+      for (int j = 0; j < 12; ++j) {
+        acc[j][0] = fmaf(xv[j], g.x, acc[j][0]); acc[j][1] = fmaf(xv[j], g.y, acc[j][1]);
+        acc[j][2] = fmaf(xv[j], g.z, acc[j][2]); acc[j][3] = fmaf(xv[j], g.w, acc[j][3]);
+      }
+      accb[0] += g.x; accb[1] += g.y; accb[2] += g.z; accb[3] += g.w;
+    }
+    __syncthreads();
+  }
+  // the RP row phases of a column quad are summed through shared memory, one dW row (or the bias row) per round
+#pragma unroll 1
+  for (int j = 0; j <= K1; ++j) {
+    float4 v;
+    if (j < K1) {
+      // select row j without dynamic register indexing
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+      for (int q = 0; q < 12; ++q)
+        if (q == j) { a0 = acc[q][0]; a1 = acc[q][1]; a2 = acc[q][2]; a3 = acc[q][3]; }
+      v = make_float4(a0, a1, a2, a3);
+    } else {
+      v = make_float4(accb[0], accb[1], accb[2], accb[3]);
+    }
+    *reinterpret_cast<float4*>(red + tid * 4) = v;
+    __syncthreads();
+    if (tid < K2) {
+      const int q = tid >> 2, i = tid & 3;
+      float t = 0.f;
+      for (int ph = 0; ph < RP; ++ph) t += red[(ph * nq + q) * 4 + i];
+      if (j < K1) partial[((size_t)blockIdx.x * K1p + j) * K2p + tid] = t;
+      else if (partial_b) partial_b[(size_t)blockIdx.x * K2p + tid] = t;
+    }
+    __syncthreads();
+  }
+}
+
 // ---------------------------------------------------------------- narrow outputs (N <= 16) ---
 // seg/conv3 of the S3DIS net (256 -> 13, DGCNN_S3DIS.py:100-101) and similar heads: one warp per row, the lane owns
 // 8 input channels per 256-channel slice (coalesced operand load through load8), the transposed weights sit in
@@ -645,6 +714,15 @@ extern "C" int wspc_conv1x1_wgrad(const wspc_operand_t* A, int a_mode, const wsp
   int rc;
   int S_used = p.S;
   static const bool env_simt = []() { const char* e = getenv("WSPC_GEMM"); return e && strcmp(e, "simt") == 0; }();
+  if (a_mode == OP_PLAIN && A->C <= 12 && g_mode == OP_DY && !G->c1 && (G->C % 4) == 0 && G->C <= 256 && 256 % (G->C / 4) == 0 &&
+      aligned16(G->p) && (G->ld % 4) == 0) {
+    const long long rps = (M + p.S - 1) / p.S;
+    wgrad_narrowk1_kernel<<<p.S, 256, 0, st>>>(A->p, A->ld, A->C, G->p, G->ld, G->C, M, rps, p.K1p, p.K2p, partial,
+                                              db ? partial_b : nullptr);
+    count_launch();
+    WSPC_LAUNCH_CHECK("wgrad_narrowk1_kernel");
+    goto reduce;
+  }
   if (!env_simt && g_gemm_path == 0) {
     rc = wgrad_tc_dispatch(*A, a_mode, *G, g_mode, M, p.S_tc, p.K1p, p.K2p, partial, db ? partial_b : nullptr, st);
     if (rc < 0) return rc;

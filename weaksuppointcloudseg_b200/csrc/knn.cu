@@ -405,11 +405,8 @@ int launch_tile(const KnnPlan& p, int B, int N, int k, int flavour, const float*
   const size_t smem = ((size_t)p.Dp * TM + (size_t)NSTAGE * KC * TN + (MODE == 0 ? TM * DLD : 0)) * sizeof(float) +
                       (NSTAGE + 1) * sizeof(uint64_t);
   auto kern = knn_tile_kernel<KC, KSLOT, MODE>;
-  static thread_local size_t configured = 0;
-  if (smem > configured) {
-    WSPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  // set on every launch: the attribute is per device, and a host thread may drive more than one
+  WSPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(p.Npad / TM, B);
   kern<<<grid, KNN_THREADS, smem, st>>>(xT, sq, N, p.Npad, p.Dp, k, flavour, idx, dist, adj);
   count_launch();

@@ -848,13 +848,10 @@ int knn_tc_run(const float* x, int B, int N, int ldx, int coff, int D, int k, in
   knn_tc_centre_kernel<<<dim3(8, B), 256, 0, st>>>(x, N, ldx, coff, D, w.centre);
   knn_tc_prep_kernel<<<dim3(p.ntile, B), 128, 0, st>>>(x, N, ldx, coff, D, p.ghi, p.glo, p.Npad, w.centre, w.img, w.sq, w.sqc,
                                                       w.smax);
-  static thread_local size_t configured[2] = {0, 0};
   const int big = k > KSORT ? 1 : 0;
   auto kern = big ? knn_tc_kernel<true> : knn_tc_kernel<false>;
-  if (p.smem > configured[big]) {
-    WSPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-    configured[big] = p.smem;
-  }
+  // set on every launch: the attribute is per device, and a host thread may drive more than one
+  WSPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
   kern<<<dim3((N + RB - 1) / RB, B), KTC_THREADS, p.smem, st>>>(w.img, w.sq, w.sqc, w.smax, x, N, p.Npad, ldx, coff, D, p.ghi, p.glo,
                                                                p.nst, k, flavour, idx, dist, w.flag_count, w.flag_rows);
   if (k <= 32)
