@@ -472,47 +472,33 @@ rows_narrow_kernel(const Operand A, const float* __restrict__ Bm, long long ldb,
   const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
   const bool fast = aligned16(A.p) && (A.ld & 3) == 0 && (AMODE == OP_PLAIN || (aligned16(A.sc) && aligned16(A.sh) &&
                     (!A.dmask || (aligned16(A.dmask) && (A.C & 3) == 0))));
-  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp; row < M; row += wstride) {
-    float acc[16];
+  // the operand of channels [c0, c0 + 8) of one row
+  auto load_v = [&](long long row, int c0, float (&v)[8]) {
+    if (fast) {   // 16-byte aligned rows: two float4 loads per tensor instead of eight scalar ones
+      const float4 a0 = __ldcs(reinterpret_cast<const float4*>(A.p + row * A.ld + c0));
+      const float4 a1 = __ldcs(reinterpret_cast<const float4*>(A.p + row * A.ld + c0 + 4));
+      v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+      if (AMODE == OP_BNRELU) {
+        const float4 s0 = *reinterpret_cast<const float4*>(A.sc + c0), s1 = *reinterpret_cast<const float4*>(A.sc + c0 + 4);
+        const float4 h0 = *reinterpret_cast<const float4*>(A.sh + c0), h1 = *reinterpret_cast<const float4*>(A.sh + c0 + 4);
+        const float sc8[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        const float sh8[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
-    for (int n = 0; n < 16; ++n) acc[n] = 0.f;
-    for (int c0 = lane * 8; c0 < K; c0 += 256) {
-      float v[8];
-      if (fast) {   // 16-byte aligned rows: two float4 loads per tensor instead of eight scalar ones
-        const float4 a0 = __ldcs(reinterpret_cast<const float4*>(A.p + row * A.ld + c0));
-        const float4 a1 = __ldcs(reinterpret_cast<const float4*>(A.p + row * A.ld + c0 + 4));
-        v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
-        if (AMODE == OP_BNRELU) {
-          const float4 s0 = *reinterpret_cast<const float4*>(A.sc + c0), s1 = *reinterpret_cast<const float4*>(A.sc + c0 + 4);
-          const float4 h0 = *reinterpret_cast<const float4*>(A.sh + c0), h1 = *reinterpret_cast<const float4*>(A.sh + c0 + 4);
-          const float sc8[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-          const float sh8[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+        for (int i = 0; i < 8; ++i) v[i] = fmaxf(fmaf(v[i], sc8[i], sh8[i]), 0.f);
+        if (A.dmask) {
+          const float4 m0 = __ldcs(reinterpret_cast<const float4*>(A.dmask + row * A.C + c0));
+          const float4 m1 = __ldcs(reinterpret_cast<const float4*>(A.dmask + row * A.C + c0 + 4));
+          const float m8[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = fmaxf(fmaf(v[i], sc8[i], sh8[i]), 0.f);
-          if (A.dmask) {
-            const float4 m0 = __ldcs(reinterpret_cast<const float4*>(A.dmask + row * A.C + c0));
-            const float4 m1 = __ldcs(reinterpret_cast<const float4*>(A.dmask + row * A.C + c0 + 4));
-            const float m8[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] *= m8[i] * A.dscale;
-          }
-        }
-      } else {
-        load8<AMODE>(A, row, c0, v);
-      }
-#pragma unroll
-      for (int n = 0; n < 16; ++n) {
-        if (n < N) {
-          const float4 w0 = *reinterpret_cast<const float4*>(Ws + n * pitch + c0);
-          const float4 w1 = *reinterpret_cast<const float4*>(Ws + n * pitch + c0 + 4);
-          acc[n] = fmaf(v[0], w0.x, acc[n]); acc[n] = fmaf(v[1], w0.y, acc[n]);
-          acc[n] = fmaf(v[2], w0.z, acc[n]); acc[n] = fmaf(v[3], w0.w, acc[n]);
-          acc[n] = fmaf(v[4], w1.x, acc[n]); acc[n] = fmaf(v[5], w1.y, acc[n]);
-          acc[n] = fmaf(v[6], w1.z, acc[n]); acc[n] = fmaf(v[7], w1.w, acc[n]);
+          for (int i = 0; i < 8; ++i) v[i] *= m8[i] * A.dscale;
         }
       }
+    } else {
+      load8<AMODE>(A, row, c0, v);
     }
-    // 16 values x 32 lanes -> lane n holds the total of value n: halve the number of live values at every step
+  };
+  // 16 values x 32 lanes -> lane n holds the total of value n (halve the number of live values at every step), then store
+  auto reduce_store = [&](float (&acc)[16], long long row) {
 #pragma unroll
     for (int n = 0; n < 8; ++n) {     // step 16: lanes with bit 4 clear keep values 0..7, the others 8..15
       const float send = (lane & 16) ? acc[n] : acc[n + 8];
@@ -540,6 +526,41 @@ rows_narrow_kernel(const Operand A, const float* __restrict__ Bm, long long ldb,
     // lane l now holds value n(l) = 8*b4 + 4*b3 + 2*b2 + b1 (bits of l); lanes with bit 0 clear write
     const int n = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
     if ((lane & 1) == 0 && n < N) E.out[row * E.ldo + n] = acc[0] + (E.bias ? E.bias[n] : 0.f);
+  };
+  // two rows per trip: every weight vector read from shared memory feeds both (the kernel is bound by those reads)
+  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp; row < M; row += 2 * wstride) {
+    const long long rowb = row + wstride;
+    const bool hasb = rowb < M;
+    float acc[16], accb[16];
+#pragma unroll
+    for (int n = 0; n < 16; ++n) { acc[n] = 0.f; accb[n] = 0.f; }
+    for (int c0 = lane * 8; c0 < K; c0 += 256) {
+      float v[8], vb[8];
+      load_v(row, c0, v);
+      if (hasb) {
+        load_v(rowb, c0, vb);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) vb[i] = 0.f;
+      }
+#pragma unroll
+      for (int n = 0; n < 16; ++n) {
+        if (n < N) {
+          const float4 w0 = *reinterpret_cast<const float4*>(Ws + n * pitch + c0);
+          const float4 w1 = *reinterpret_cast<const float4*>(Ws + n * pitch + c0 + 4);
+          acc[n] = fmaf(v[0], w0.x, acc[n]); acc[n] = fmaf(v[1], w0.y, acc[n]);
+          acc[n] = fmaf(v[2], w0.z, acc[n]); acc[n] = fmaf(v[3], w0.w, acc[n]);
+          acc[n] = fmaf(v[4], w1.x, acc[n]); acc[n] = fmaf(v[5], w1.y, acc[n]);
+          acc[n] = fmaf(v[6], w1.z, acc[n]); acc[n] = fmaf(v[7], w1.w, acc[n]);
+          accb[n] = fmaf(vb[0], w0.x, accb[n]); accb[n] = fmaf(vb[1], w0.y, accb[n]);
+          accb[n] = fmaf(vb[2], w0.z, accb[n]); accb[n] = fmaf(vb[3], w0.w, accb[n]);
+          accb[n] = fmaf(vb[4], w1.x, accb[n]); accb[n] = fmaf(vb[5], w1.y, accb[n]);
+          accb[n] = fmaf(vb[6], w1.z, accb[n]); accb[n] = fmaf(vb[7], w1.w, accb[n]);
+        }
+      }
+    }
+    reduce_store(acc, row);
+    if (hasb) reduce_store(accb, rowb);
   }
 }
 

@@ -105,6 +105,71 @@ __global__ void head_tiecount_kernel(const float* __restrict__ Z, int B, int N, 
 // Smoothness term on the kNN graph of the input points; one warp per point, lanes = classes.
 // W = exp(-d / gamma) (SmoothConstraint.py:157); loss = mean_{b,n,r} W * mean_c (P_i - P_j)^2 (:161-163).
 // dP_i += g, dP_j -= g with g = 2 W (P_i - P_j) / (C * B*N*knn)   (App. E)
+// Small class counts (C <= 16, knn <= 16; the S3DIS head has 13 classes and 10 neighbours): lane = (neighbour slot, half of the
+// channels), so a point's neighbours are fetched and differenced in parallel instead of one after the other with 13 of 32 lanes
+// busy.  Same quantities and options as smooth_kernel below.
+__global__ void __launch_bounds__(256)
+smooth_small_kernel(const float* __restrict__ P, const int32_t* __restrict__ idx, const float* __restrict__ dist, int B, int N,
+                    int C, int knn, float gamma, float gscale, float* __restrict__ dP, double* __restrict__ acc, float cinv,
+                    const int32_t* __restrict__ idx_match, int weights_direct, int want_global) {
+  __shared__ float sred[8], sred_w[8], sred_s[8];
+  if (cinv < 0.f) cinv = 1.f / (float)C;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long pt = (long long)blockIdx.x * 8 + warp;
+  const long long total = (long long)B * N;
+  float lsum = 0.f, wsum = 0.f, sssum = 0.f;
+  if (pt < total) {
+    const int slot = lane >> 1, half = lane & 1, c0 = half * 8;
+    const long long base = (pt / N) * N;
+    const bool act = slot < knn;
+    long long j = pt;
+    float w = 0.f;
+    if (act) {
+      const int nb = idx[pt * knn + slot];
+      j = base + nb;
+      w = weights_direct ? dist[pt * knn + slot] : expf((-dist[pt * knn + slot]) / gamma);
+      if (idx_match && idx_match[pt * knn + slot] != nb) w = 0.f;   // knn_mask of SmoothConstraint.py:113
+    }
+    float d[8], ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = c0 + i;
+      d[i] = (act && c < C) ? P[pt * C + c] - P[j * C + c] : 0.f;
+      ss = fmaf(d[i], d[i], ss);
+    }
+    ss += __shfl_xor_sync(0xffffffffu, ss, 1);                       // both channel halves of the slot
+    const bool once = act && half == 0;
+    lsum = warp_sum(once ? w * (ss * cinv) : 0.f);
+    wsum = warp_sum(once ? w : 0.f);
+    sssum = warp_sum(once ? ss : 0.f);
+    if (dP) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = c0 + i;
+        const float g = 2.f * w * d[i] * gscale;
+        if (act && j != pt && c < C) atomicAdd(dP + j * C + c, -g);
+        float gi = g;                                                // the point's own share: sum over the slots
+        gi += __shfl_xor_sync(0xffffffffu, gi, 2);
+        gi += __shfl_xor_sync(0xffffffffu, gi, 4);
+        gi += __shfl_xor_sync(0xffffffffu, gi, 8);
+        gi += __shfl_xor_sync(0xffffffffu, gi, 16);
+        if (slot == 0 && c < C) atomicAdd(dP + pt * C + c, gi);
+      }
+    }
+  }
+  if (lane == 0) { sred[warp] = lsum; sred_w[warp] = wsum; sred_s[warp] = sssum; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, aw = 0.f, as = 0.f;
+    for (int w8 = 0; w8 < 8; ++w8) { a += sred[w8]; aw += sred_w[w8]; as += sred_s[w8]; }
+    atomicAdd(&acc[4], (double)a);
+    if (want_global) {
+      atomicAdd(&acc[5], (double)aw);
+      atomicAdd(&acc[6], (double)as);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 smooth_kernel(const float* __restrict__ P, const int32_t* __restrict__ idx, const float* __restrict__ dist, int B, int N,
               int C, int knn, float gamma, float gscale, float* __restrict__ dP, double* __restrict__ acc,
@@ -316,8 +381,12 @@ extern "C" int wspc_head_losses(const float* Z, const float* Y, const float* Mas
   if (smooth) {
     const long long pts = (long long)B * N;
     const float gscale = 1.f / (float)((double)C * B * N * knn);
-    smooth_kernel<<<(unsigned)((pts + 7) / 8), 256, 0, st>>>(P, sm_idx, sm_dist, B, N, C, knn, gamma, gscale,
-                                                            (want_grad && grad_full) ? dP : nullptr, acc);
+    if (C <= 16 && knn <= 16)
+      smooth_small_kernel<<<(unsigned)((pts + 7) / 8), 256, 0, st>>>(P, sm_idx, sm_dist, B, N, C, knn, gamma, gscale,
+                                                                    (want_grad && grad_full) ? dP : nullptr, acc, -1.f, nullptr, 0, 0);
+    else
+      smooth_kernel<<<(unsigned)((pts + 7) / 8), 256, 0, st>>>(P, sm_idx, sm_dist, B, N, C, knn, gamma, gscale,
+                                                              (want_grad && grad_full) ? dP : nullptr, acc);
     count_launch();
     WSPC_LAUNCH_CHECK("smooth_kernel");
   }
@@ -370,8 +439,12 @@ extern "C" int wspc_smooth_loss_ex(const float* Z, const int32_t* idx, const flo
   const long long pts = (long long)B * N;
   const float cinv = (flags & WSPC_SMOOTH_SUM_C) ? 1.f : 1.f / (float)C;
   const float gscale = (float)((double)cinv / ((double)B * N * knn));
-  smooth_kernel<<<(unsigned)((pts + 7) / 8), 256, 0, st>>>(Z, idx, dist, B, N, C, knn, gamma, gscale, dZ, acc, cinv, idx_match,
-                                                           (flags & WSPC_SMOOTH_WEIGHTS) ? 1 : 0, global_form ? 1 : 0);
+  if (C <= 16 && knn <= 16)
+    smooth_small_kernel<<<(unsigned)((pts + 7) / 8), 256, 0, st>>>(Z, idx, dist, B, N, C, knn, gamma, gscale, dZ, acc, cinv, idx_match,
+                                                                  (flags & WSPC_SMOOTH_WEIGHTS) ? 1 : 0, global_form ? 1 : 0);
+  else
+    smooth_kernel<<<(unsigned)((pts + 7) / 8), 256, 0, st>>>(Z, idx, dist, B, N, C, knn, gamma, gscale, dZ, acc, cinv, idx_match,
+                                                             (flags & WSPC_SMOOTH_WEIGHTS) ? 1 : 0, global_form ? 1 : 0);
   smooth_finish_kernel<<<1, 1, 0, st>>>(acc, (double)B * N * knn, global_form ? 1 : 0, loss);
   count_launch(2);
   WSPC_LAUNCH_CHECK("smooth_kernel");
