@@ -158,6 +158,24 @@ def test_wgrad_matches_fp64(cuda, gemm_path, K1, K2, mode):
     assert rel(db, dy.sum(0)) <= 2e-5
 
 
+@pytest.mark.parametrize("K1,K2,ldx", [(9, 128, 9), (3, 128, 3), (12, 256, 16), (9, 64, 9)])
+def test_wgrad_narrow_inputs(cuda, K1, K2, ldx):
+    """weight gradient of the factored first EdgeConv layer (X (P, 9 | 3) against the (P, 128) gradient of [u | v]): the
+    narrow-input kernel, ragged row count, X read with a row pitch, bias gradient."""
+    from weaksuppointcloudseg_b200 import _lib as L, runtime as rt
+    g = torch.Generator(device="cuda").manual_seed(31)
+    M = 70001
+    xw = torch.randn((M, ldx), device=cuda, generator=g)
+    G = torch.randn((M, K2), device=cuda, generator=g)
+    A = (L.Operand(p=xw.data_ptr(), ld=ldx, C=K1), L.OP_PLAIN)
+    Gop = (L.Operand(p=G.data_ptr(), ld=K2, C=K2), L.OP_DY)
+    dW = torch.empty((K1, K2), device=cuda)
+    db = torch.empty(K2, device=cuda)
+    rt.wgrad(A, Gop, M, dW, db, cuda)
+    assert rel(dW, xw[:, :K1].double().T @ G.double()) <= 2e-5
+    assert rel(db, G.double().sum(0)) <= 2e-5
+
+
 def test_maxk_fwd_bwd(cuda):
     from weaksuppointcloudseg_b200 import _lib as L
     g = torch.Generator(device="cuda").manual_seed(4)
