@@ -252,10 +252,18 @@ def input_transform_net(p, edge_feature, is_training, bn_decay, rec=None, prefix
     """transform_nets.input_transform_net (Networks/dgcnn/models/transform_nets.py:10-56), K=3."""
     B = edge_feature.shape[0]
     net = conv2d(edge_feature, p, prefix + "tconv1", is_training, bn_decay=bn_decay, rec=rec)   # :18-21
-    net = conv2d(net, p, prefix + "tconv2", is_training, bn_decay=bn_decay, rec=rec)            # :22-25
-    net = reduce_max_k(net)                                                                      # :27
-    net = conv2d(net, p, prefix + "tconv3", is_training, bn_decay=bn_decay, rec=rec)            # :29-32
-    net = max_pool_points(net)                                                                   # :33-36
+    forced = ROUTE.get("maxk/tnet") if ROUTE is not None else None
+    net = conv2d(net, p, prefix + "tconv2", is_training, bn_decay=bn_decay, rec=rec, act=forced is None)   # :22-25
+    if forced is not None:      # ReLU + max over k as one routed selection, as in _edge_block
+        net = (net * forced.to(net.dtype)).sum(dim=-2)
+    else:
+        net = reduce_max_k(net)                                                                  # :27
+    mn = ROUTE.get("maxn/" + prefix + "tconv3") if ROUTE is not None else None
+    net = conv2d(net, p, prefix + "tconv3", is_training, bn_decay=bn_decay, rec=rec, act=mn is None)       # :29-32
+    if mn is None:
+        net = max_pool_points(net)                                                               # :33-36
+    else:
+        net = torch.gather(net, 1, mn[0].long().unsqueeze(1)).squeeze(1) * mn[1].to(net.dtype)
     net = fully_connected(net, p, prefix + "tfc1", is_training, bn_decay=bn_decay, rec=rec)     # :37-38
     net = fully_connected(net, p, prefix + "tfc2", is_training, bn_decay=bn_decay, rec=rec)     # :39-40
     W, b = p[prefix + "transform_XYZ/weights"], p[prefix + "transform_XYZ/biases"]
@@ -282,8 +290,12 @@ def get_model_shapenet(p, point_cloud, input_label, is_training, bn_decay=None, 
     net_2 = _edge_block(net_1, net_1, p, ["adj_conv3", "adj_conv4"], is_training, bn_decay, k, rec, "knn2", ov)
     net_3 = _edge_block(net_2, net_2, p, ["adj_conv5"], is_training, bn_decay, k, rec, "knn3", ov)
     cat = torch.cat([net_1, net_2, net_3], dim=-1)
-    out7 = conv2d(cat, p, "adj_conv7", is_training, bn_decay=bn_decay, rec=rec)                  # :80-83
-    out_max = max_pool_points(out7)                                                              # :85
+    mn = ROUTE.get("maxn/adj_conv7") if ROUTE is not None else None
+    out7 = conv2d(cat, p, "adj_conv7", is_training, bn_decay=bn_decay, rec=rec, act=mn is None)  # :80-83
+    if mn is None:
+        out_max = max_pool_points(out7)                                                          # :85
+    else:
+        out_max = torch.gather(out7, 1, mn[0].long().unsqueeze(1)).squeeze(1) * mn[1].to(out7.dtype)
     lab = conv2d(input_label.to(out_max.dtype), p, "one_hot_label_expand", is_training, bn_decay=bn_decay,
                  rec=rec)                                                                        # :87-91
     g = torch.cat([out_max, lab], dim=-1)                                                        # :92

@@ -33,11 +33,10 @@ def _weights_from_bits(sel, out):
     return sel / n.clamp_min(1.0)
 
 
-def export_s3dis(eng, routing):
-    """routing: the dict the step filled through runtime.ROUTING"""
+def _export_blocks(eng, routing, route, idx_of_block):
+    """the three fused EdgeConv blocks of the segmentation trunk (both engines); idx_of_block: engine.idx entries of knn1..3"""
     B, N, k, P = eng.B, eng.N, eng.k, eng.P
     Ly = eng.layers
-    route = {}
     cat = eng.cat
     base = (torch.arange(B, device=cat.device) * N).view(B, 1, 1)
     bits32 = torch.arange(32, device=cat.device, dtype=torch.int32)
@@ -50,7 +49,7 @@ def export_s3dis(eng, routing):
         else:
             UV = eng.eb[i].UV
             u, v = UV[:, :64], UV[:, 64:]
-            gi = (eng.idx[i].long() + base).reshape(P, k)
+            gi = (idx_of_block[i].long() + base).reshape(P, k)
             t = l1.b * l1.sc + l1.sh
             pre1 = v[gi] * l1.sc + (u.unsqueeze(1) * l1.sc + t)              # (P,k,64) fp32
             route[f"relu/{s1}"] = (pre1 > 0).view(B, N, k, 64).cpu()
@@ -59,10 +58,53 @@ def export_s3dis(eng, routing):
             sel = ((words.unsqueeze(-1) >> bits32) & 1).reshape(P, k, 64)
         route[f"maxk/knn{i + 1}"] = _weights_from_bits(sel, out).view(B, N, k, 64).cpu()
     route["maxn/adj_conv7"] = (eng.amax.long().cpu(), (eng.g > 0).cpu())
-    s1, s2 = Ly["seg/conv1"], Ly["seg/conv2"]
-    route["relu/seg/conv1"] = ((eng.ys1 * s1.sc + s1.sh) > 0).view(B, N, -1).cpu()
-    route["relu/seg/conv2"] = ((eng.ys2 * s2.sc + s2.sh) > 0).view(B, N, -1).cpu()
     Z = eng.Z.double()
     sel = (Z == Z.max(dim=1, keepdim=True).values).double()
     route["inexact"] = (sel / sel.sum(dim=1, keepdim=True)).cpu()
+
+
+def _relu_mask(y, layer):
+    """the decision of the kernels' fmaf(y, sc, sh) > 0 (torch.addcmul fuses the same way on the device)"""
+    return torch.addcmul(layer.sh, y, layer.sc) > 0
+
+
+def export_shapenet(eng, routing):
+    """ShapeNetEngine after one training step run with runtime.ROUTING = {}: the trunk's blocks as above, plus the T-net (its
+    64 -> 128 EdgeConv block runs the materialised kernels: ReLU masks from the stored pre-BN tensors, the max-over-k split
+    EXACTLY as the backward kernel made it: Gt2 / dtmax), the two max-over-points stages, the FC layers, the label branch and
+    the four seg layers."""
+    B, N, k, P = eng.B, eng.N, eng.k, eng.P
+    Ly = eng.layers
+    T = "transform_net1/"
+    route = {}
+    _export_blocks(eng, routing, route, [eng.idx[1], eng.idx[2], eng.idx[3]])
+    t1, t2 = Ly[T + "tconv1"], Ly[T + "tconv2"]
+    route["relu/" + T + "tconv1"] = _relu_mask(eng.yt1, t1).view(B, N, k, 64).cpu()
+    G = eng.Gt2.view(P, k, 128).double()
+    d = eng.dtmax.view(P, 1, 128).double()
+    w = torch.where(d != 0, G / torch.where(d != 0, d, torch.ones_like(d)), torch.zeros_like(G))
+    pre2 = torch.addcmul(t2.sh, eng.yt2, t2.sc).view(P, k, 128)
+    w_fallback = _maxk_weights(pre2.double(), eng.tmax.double())
+    w = torch.where((d != 0).expand_as(w), w, w_fallback)
+    # a positive pooled value is attained by at least one row (and only then)
+    assert bool(((w.sum(1) > 0.5) == (eng.tmax > 0)).all())
+    route["maxk/tnet"] = w.view(B, N, k, 128).cpu()
+    route["maxn/" + T + "tconv3"] = (eng.tamax.long().cpu(), (eng.tg > 0).cpu())
+    route["relu/" + T + "tfc1"] = _relu_mask(eng.yf1, Ly[T + "tfc1"]).cpu()
+    route["relu/" + T + "tfc2"] = _relu_mask(eng.yf2, Ly[T + "tfc2"]).cpu()
+    route["relu/one_hot_label_expand"] = _relu_mask(eng.ylab, Ly["one_hot_label_expand"]).cpu()
+    for i, y in ((1, eng.ys1), (2, eng.ys2), (3, eng.ys3)):
+        route[f"relu/seg/conv{i}"] = _relu_mask(y, Ly[f"seg/conv{i}"]).view(B, N, -1).cpu()
+    return route
+
+
+def export_s3dis(eng, routing):
+    """routing: the dict the step filled through runtime.ROUTING"""
+    B, N = eng.B, eng.N
+    Ly = eng.layers
+    route = {}
+    _export_blocks(eng, routing, route, [eng.idx[0], eng.idx[1], eng.idx[2]])
+    s1, s2 = Ly["seg/conv1"], Ly["seg/conv2"]
+    route["relu/seg/conv1"] = ((eng.ys1 * s1.sc + s1.sh) > 0).view(B, N, -1).cpu()
+    route["relu/seg/conv2"] = ((eng.ys2 * s2.sc + s2.sh) > 0).view(B, N, -1).cpu()
     return route

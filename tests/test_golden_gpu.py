@@ -87,10 +87,11 @@ def _grad_check(got, f, lim):
             assert np.abs(a).max() < 1e-4 * gmax, k
             continue
         e = np.linalg.norm(a - b) / np.linalg.norm(b)
-        # the T-net's gradients all hang off one (B,3,3) tensor and its FC layers normalise over B=6 clouds only:
-        # fp32 routing noise there is ~2x the rest of the net (the fp32 oracle scatters the same way against its
-        # own fp64 run, tests/test_shapenet_engine_gpu.py)
-        if e > (2 * lim if "transform_net1/" in k else lim):
+        # the T-net's gradients all hang off one (B,3,3) tensor and its FC layers normalise over B=6 clouds only: the routing
+        # noise of an UN-forced comparison there is 2-3x the rest of the net and varies from run to run with the summation
+        # order of the statistics (tools/flake_probe.py, 40 runs: trunk 2.4e-2 .. 4.0e-2, T-net 7.8e-2 .. 1.3e-1).  The tight
+        # statement is the forced-routing test (tests/test_baseline_shapes_gpu.py, tests/test_shapenet_engine_gpu.py).
+        if e > (3 * lim if "transform_net1/" in k else lim):
             bad[k] = e
     assert not bad, bad
 

@@ -43,15 +43,7 @@ def setup(cuda):
                             torch.from_numpy(M).to(cuda), lr=1e-3, bn_decay=od.bn_decay(0, n_samples, 16881 * 20),
                             dropout_masks=[torch.from_numpy(m).to(cuda) for m in masks], knn_override=ov)
     torch.cuda.synchronize()
-    # fp64 run of the same oracle on the same neighbour graphs: the yardstick for how far two correct fp32
-    # implementations may drift apart on the discontinuous (ReLU / arg-max) gradient paths
-    p64 = od.to_torch(params, dtype=torch.float64)
-    f64 = lambda a: torch.from_numpy(a).to(torch.float64)
-    out64 = od.train_step_shapenet(p64, od.AdamTF(p64, od.trainable_names(p64)), f64(X), f64(lab), f64(Y), f64(M), step=0,
-                                   dropout_masks=[f64(m) for m in masks], rec={},
-                                   knn_override={f"knn{i}": rec[f"knn{i}/idx"] for i in (0, 1, 2, 3)},
-                                   smooth_graph_=od.smooth_graph(torch.from_numpy(X)))
-    return dict(eng=eng, out=out, out64=out64, rec=rec, p=p, losses=losses.cpu().numpy(), params0=params, X=X)
+    return dict(eng=eng, out=out, rec=rec, p=p, losses=losses.cpu().numpy(), params0=params, X=X, lab=lab, Y=Y, M=M, masks=masks)
 
 
 def test_tnet_and_knn0(setup):
@@ -70,33 +62,46 @@ def test_logits_and_losses(setup):
         assert abs(v - ref) <= TOL * abs(ref), (n, v, ref)
 
 
-def test_gradients(setup):
-    eng, out = setup["eng"], setup["out"]
+def test_gradients(setup, cuda):
+    """Every trainable tensor against the fp64 oracle that takes the ENGINE's discrete branches (ReLU masks, max-over-k
+    splits, arg-max rows of the two max-over-points stages; tests/routing.py): with the routing pinned the comparison is a
+    statement about arithmetic, and the bound is the parity bar of SURVEY 8(c), 1e-3 max-rel, for EVERY tensor (measured:
+    5e-6 .. 5.8e-4; un-forced the same comparison scatters by 3e-2 .. 1e-1 on the T-net, which is why round 1 carried a 3e-1
+    bound and an escape hatch here)."""
+    import routing
+    from weaksuppointcloudseg_b200 import runtime as rt
+    from weaksuppointcloudseg_b200.engine_shapenet import ShapeNetEngine
+    params, X, lab, Y, M, masks = (setup[n] for n in ("params0", "X", "lab", "Y", "M", "masks"))
+    n_samples, N = X.shape[0] // 2, X.shape[1]
+    B = X.shape[0]
+    eng = ShapeNetEngine(params, B, N, device=cuda)
+    rt.ROUTING = {}
+    try:
+        eng.train_step(*(torch.from_numpy(a).to(cuda) for a in (X, lab, Y, M)), lr=1e-3, bn_decay=od.bn_decay(0, n_samples, 16881 * 20),
+                       dropout_masks=[torch.from_numpy(m).to(cuda) for m in masks], apply=False)
+        torch.cuda.synchronize()
+        route = routing.export_shapenet(eng, rt.ROUTING)
+    finally:
+        rt.ROUTING = None
+    ov = {f"knn{i}": eng.idx[i].cpu().long() for i in range(4)}
+    sg = (eng.idxS.cpu().long(), torch.exp(-eng.dS.cpu().double() / 0.1))
+    p64 = od.to_torch(params, dtype=torch.float64)
+    f64 = lambda a: torch.from_numpy(a).to(torch.float64)   # noqa: E731
+    with od.forced_routing(route):
+        ref = od.train_step_shapenet(p64, od.AdamTF(p64, od.trainable_names(p64)), f64(X), f64(lab), f64(Y), f64(M), step=0,
+                                     dropout_masks=[f64(m) for m in masks], knn_override=ov, smooth_graph_=sg)
+    assert rel(eng.Z.cpu().numpy(), ref["Z"].detach().numpy()) <= TOL
     got = eng.vs.grads()
-    gmax = max(float(g.abs().max()) for g in out["grads"].values() if g is not None)
-    bad = {}
-    for name, g in out["grads"].items():
-        a, b = got[name].astype(np.float64), g.numpy().astype(np.float64)
-        bn_bias = name.endswith('/biases') and not (name.startswith('seg/conv4') or 'transform_XYZ' in name)
-        if bn_bias or np.abs(b).max() < 1e-6 * gmax:     # analytically zero gradients: rounding noise on both sides
-            assert np.abs(a).max() < 1e-4 * gmax, name
+    gmax = max(float(g.abs().max()) for g in ref["grads"].values() if g is not None)
+    worst = {}
+    for name, g in ref["grads"].items():
+        a, b = got[name].astype(np.float64), g.numpy()
+        if np.abs(b).max() < 1e-9 * gmax:     # analytically zero gradients (biases of batch-normalised layers)
+            assert np.abs(a).max() < 1e-5 * gmax, name
             continue
-        e = (rel(a, b), np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
-        c = setup["out64"]["grads"][name].numpy()
-        l2 = lambda u, v: np.linalg.norm(u - v) / max(np.linalg.norm(v), 1e-30)
-        # ReLU masks / arg-max pools are discontinuous: activations that differ in the last bits route single-element
-        # gradients differently, and that noise compounds backwards through the 16 BN'd layers of this net (it is
-        # 1e-4 at seg/conv4 and a few 1e-2 at the T-net, whose gradients are all proportional to the single
-        # (B,3,3) tensor dT = X^T dX' and whose FC layers normalise over only B=6 clouds here).  The fp32 oracle
-        # itself scatters by ~1 % against its own fp64 run on these tensors (tools/diag_shapenet.py).  The bound
-        # below (||a-b||/||b|| <= 6e-2, i.e. cosine >= 0.998) still catches any wiring / scaling / indexing error,
-        # and tests/test_kernels_gpu.py pins every kernel to 1e-5 on identical inputs.
-        lim = (3e-1, 6e-2)     # (max-norm: one arg-max flip of max_pool2d moves a whole gradient row)
-        # A tensor beyond that fixed bound still passes when the engine is as close to the exact (fp64) gradient
-        # as the fp32 oracle itself is, within a factor 3: then the gap is fp32 routing noise, not an error.
-        as_good_as_fp32 = l2(a, c) <= 3.0 * l2(b, c) + 1e-3
-        if (e[0] > lim[0] or e[1] > lim[1]) and not as_good_as_fp32:
-            bad[name] = e + (l2(a, c), l2(b, c))
+        worst[name] = rel(a, b)
+    print("ShapeNet (16 x 256) forced-routing gradient errors:", {k_: f"{v:.1e}" for k_, v in worst.items()})
+    bad = {k_: v for k_, v in worst.items() if v > TOL}
     assert not bad, bad
 
 
