@@ -68,7 +68,8 @@ def main():
     checked = 0
     for name in od.trainable_names(p):
         g = avg[name]
-        if g is None or float(g.abs().max()) < 1e-6 * gmax:
+        zero_by_construction = (name.endswith("/biases") and name != "seg/conv3/biases") or name == "adj_conv7/bn/beta"
+        if g is None or zero_by_construction or float(g.abs().max()) < 1e-6 * gmax:
             continue                                 # analytically-zero gradients: the sign of rounding noise
         sig = np.abs(g.numpy()) > 1e-2 * float(g.abs().max())
         d_ref = p[name].detach().numpy() - params0[name]

@@ -59,7 +59,7 @@ def setup(cuda):
     losses = eng.train_step(Xd, Yd, Md, lr=1e-3, bn_decay=od.bn_decay(0, n_samples, 300000),
                             dropout_mask=torch.from_numpy(mask).to(cuda), knn_override=ov)
     torch.cuda.synchronize()
-    return dict(eng=eng, out=out, rec=rec, p=p, losses=losses.cpu().numpy(), X=X, Y=Y, M=M, params0=params)
+    return dict(eng=eng, out=out, rec=rec, p=p, losses=losses.cpu().numpy(), X=X, Y=Y, M=M, params0=params, mask=mask)
 
 
 def test_knn1_and_smooth_graph_bit_exact(setup):
@@ -94,20 +94,45 @@ def test_logits_probs_losses(setup):
         assert abs(v - ref) <= TOL * abs(ref), (n, v, ref)
 
 
-def test_gradients(setup):
-    eng, out = setup["eng"], setup["out"]
+def test_gradients(setup, cuda):
+    """Every trainable tensor against the fp64 oracle that takes the ENGINE's discrete branches (ReLU masks, max-over-k splits,
+    arg-max rows of the max over points; tests/routing.py): max-rel <= 1e-3, the parity bar of SURVEY 8(c).  (Round 1 compared
+    un-forced at 6e-2 max-rel / 2e-2 in L2: two correct fp32 implementations route near-tied maxima differently.)"""
+    import routing
+    from weaksuppointcloudseg_b200 import runtime as rt
+    from weaksuppointcloudseg_b200.engine_s3dis import S3DISEngine
+    params, X, Y, M, mask = (setup[n] for n in ("params0", "X", "Y", "M", "mask"))
+    B, N = X.shape[0], X.shape[1]
+    eng = S3DISEngine(params, B, N, device=cuda)
+    rt.ROUTING = {}
+    try:
+        eng.train_step(torch.from_numpy(X).to(cuda), torch.from_numpy(Y).to(cuda), torch.from_numpy(M).to(cuda), lr=1e-3,
+                       bn_decay=od.bn_decay(0, B // 2, 300000), dropout_mask=torch.from_numpy(mask).to(cuda), apply=False)
+        torch.cuda.synchronize()
+        route = routing.export_s3dis(eng, rt.ROUTING)
+    finally:
+        rt.ROUTING = None
+    ov = {f"knn{i + 1}": eng.idx[i].cpu().long() for i in range(3)}
+    sg = (eng.idxS.cpu().long(), torch.exp(-eng.dS.cpu().double() / 0.1))
+    p64 = od.to_torch(params, dtype=torch.float64)
+    f64 = lambda a: torch.from_numpy(a).double()   # noqa: E731
+    with od.forced_routing(route):
+        ref = od.train_step_s3dis(p64, od.AdamTF(p64, od.trainable_names(p64)), f64(X), f64(Y), f64(M), step=0,
+                                  dropout_mask=f64(mask), knn_override=ov, smooth_graph_=sg)
+    assert rel(eng.Z.cpu().numpy(), ref["Z"].detach().numpy()) <= 2e-4
     got = eng.vs.grads()
+    gmax = max(float(g.abs().max()) for g in ref["grads"].values())
     worst = {}
-    gmax = max(float(g.abs().max()) for g in out["grads"].values())
-    for name, g in out["grads"].items():
-        a, b = got[name].astype(np.float64), g.numpy().astype(np.float64)
-        if np.abs(b).max() < 1e-6 * gmax:
+    for name, g in ref["grads"].items():
+        a, b = got[name].astype(np.float64), g.numpy()
+        if np.abs(b).max() < 1e-9 * gmax:
             # analytically zero (biases of BN'd convs; adj_conv7's beta, whose per-channel shift of the tiled
-            # global feature is removed again by seg/conv1's BN): both sides are rounding noise
+            # global feature is removed again by seg/conv1's BN)
             assert np.abs(a).max() < 1e-5 * gmax, name
             continue
-        worst[name] = (rel(a, b), np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
-    bad = {k: v for k, v in worst.items() if v[0] > 6e-2 or v[1] > 2e-2}
+        worst[name] = rel(a, b)
+    print("S3DIS (6 x 384) forced-routing gradient errors:", {k_: f"{v:.1e}" for k_, v in worst.items()})
+    bad = {k_: v for k_, v in worst.items() if v > TOL}
     assert not bad, bad
 
 
@@ -127,8 +152,12 @@ def test_adam_and_pop_stats(setup):
         d_got = got[name] - setup["params0"][name]
         assert np.abs(d_got).max() <= 1.001e-3, name
         sig = np.abs(g) > 1e-2 * np.abs(g).max()
-        if np.abs(g).max() < 1e-6 * gmax or not sig.any():
-            continue  # analytically-zero gradients (BN'd conv biases, adj_conv7 beta): sign of noise
+        # analytically-zero gradients (biases of batch-normalised convs; adj_conv7's beta): the update is the sign of rounding
+        # noise.  Named explicitly: the fp32 oracle's own noise on them depends on torch's CPU reduction order (thread count)
+        # and sat right at the 1e-6 threshold below
+        zero_by_construction = (name.endswith("/biases") and name != "seg/conv3/biases") or name == "adj_conv7/bn/beta"
+        if zero_by_construction or np.abs(g).max() < 1e-6 * gmax or not sig.any():
+            continue
         assert np.mean(np.abs(d_got[sig] - d_ref[sig]) <= 2e-5) >= 0.999, name
 
 
