@@ -52,3 +52,35 @@ for it in range(n):
     worst_all.append((ez, worst, worst_t))
 w = np.array(worst_all)
 print("max over runs: Z %.2e grads %.3e tnet %.3e" % tuple(w.max(0)))
+
+# ---- the S3DIS reference-code step (tests/test_golden_gpu.py::test_s3dis_step_against_reference_code, bound 3e-2) ----------
+from weaksuppointcloudseg_b200.engine_s3dis import S3DISEngine  # noqa: E402
+
+f = np.load(os.path.join(tg.G, "ref_s3dis_step.npz"))
+params0 = rc.xavier_params(rc.S3DIS_LAYERS, int(f["param_seed"][0]))
+B, N = f["X"].shape[:2]
+X, M = (torch.from_numpy(f[k]).to(cuda) for k in ("X", "Mask"))
+Y = torch.from_numpy(f["Y"].astype(np.float32)).to(cuda)
+gmax = max(np.abs(f[k]).max() for k in f.files if k.startswith("grad/"))
+ws = []
+for it in range(n):
+    eng = S3DISEngine(params0, B, N, device=cuda)
+    ov = {k: tg._i32(f[k], cuda) for k in ("knn2", "knn3")}
+    sg = tg._smooth_graph(X[:, :, 0:6], tg._i32(f["knn_smooth"], cuda), cuda)
+    eng.train_step(X, Y, M, lr=1e-3, bn_decay=0.5, dropout_mask=tg._keep(f["dropout_keep"], cuda), knn_override=ov, smooth_graph=sg,
+                   apply=False)
+    torch.cuda.synchronize()
+    got = eng.vs.grads()
+    worst, wk = 0.0, ""
+    for k in f.files:
+        if not k.startswith("grad/"):
+            continue
+        a, b = rc.subsample(got[k[len("grad/"):]])[0].astype(np.float64), f[k].astype(np.float64)
+        if np.abs(b).max() < 1e-6 * gmax:
+            continue
+        e = np.linalg.norm(a - b) / np.linalg.norm(b)
+        if e > worst:
+            worst, wk = e, k
+    ws.append(worst)
+print("S3DIS step vs reference-code fixture, L2 error of the worst tensor over %d runs: min %.3e median %.3e max %.3e" % (
+    n, min(ws), float(np.median(ws)), max(ws)))
