@@ -2,10 +2,9 @@
 decision its pass took -- ReLU masks, the rows that attain each max over k, the arg-max rows of the max over points, the
 points that attain the per-cloud logit maxima of the inexact loss -- in the form oracle/dgcnn.py's `forced_routing` consumes.
 
-  first conv of a block   the fused engine never stores an edge tensor: a1 = relu(v_j*sc + (u_i*sc + (b*sc + sh))) is
-                          re-evaluated from the stored UV = [u | v] and the folded BN affine (the expression
-                          csrc/edgeconv.cu evaluates; plain torch rounds the products separately from the fused
-                          multiply-adds, which can only matter for values within an ulp of zero)
+  first conv of a block   the fused engine never stores an edge tensor: a1 = relu(fma(v_j, sc, fma(u_i, sc, fma(b, sc, sh)))) is
+                          re-evaluated from the stored UV = [u | v] and the BN affine with the kernels' own fused
+                          multiply-adds (_fma32), so the masks are the kernels' masks bit for bit
   max over k              EXACT: the backward kernels export which rows they routed the gradient to (bit masks,
                           wspc_edgeconv2_bwd_ex / wspc_edge1_bwd_ex); tied rows share it equally as tf.reduce_max does; no row
                           where the pooled value is 0 (clipped by the ReLU)
@@ -33,6 +32,12 @@ def _weights_from_bits(sel, out):
     return sel / n.clamp_min(1.0)
 
 
+def _fma32(a, b, c):
+    """fmaf(a, b, c) of fp32 tensors as the kernels evaluate it (one rounding): the product of two fp32 values is exact in
+    fp64, and the fp64 sum rounds to fp32 like the fused operation except for double-rounding ties (~1e-9 of the elements)"""
+    return (a.double() * b.double() + c.double()).float()
+
+
 def _export_blocks(eng, routing, route, idx_of_block):
     """the three fused EdgeConv blocks of the segmentation trunk (both engines); idx_of_block: engine.idx entries of knn1..3"""
     B, N, k, P = eng.B, eng.N, eng.k, eng.P
@@ -50,8 +55,8 @@ def _export_blocks(eng, routing, route, idx_of_block):
             UV = eng.eb[i].UV
             u, v = UV[:, :64], UV[:, 64:]
             gi = (idx_of_block[i].long() + base).reshape(P, k)
-            t = l1.b * l1.sc + l1.sh
-            pre1 = v[gi] * l1.sc + (u.unsqueeze(1) * l1.sc + t)              # (P,k,64) fp32
+            t = _fma32(l1.b, l1.sc, l1.sh)
+            pre1 = _fma32(v[gi], l1.sc, _fma32(u, l1.sc, t).unsqueeze(1))    # (P,k,64): csrc/edgeconv.cu's nested fmaf, bit for bit
             route[f"relu/{s1}"] = (pre1 > 0).view(B, N, k, 64).cpu()
             del pre1
             words = routing[s2].view(P, k, 2)                                 # bit c of word h = channel 32 h + c
@@ -64,8 +69,8 @@ def _export_blocks(eng, routing, route, idx_of_block):
 
 
 def _relu_mask(y, layer):
-    """the decision of the kernels' fmaf(y, sc, sh) > 0 (torch.addcmul fuses the same way on the device)"""
-    return torch.addcmul(layer.sh, y, layer.sc) > 0
+    """the decision of the kernels' fmaf(y, sc, sh) > 0"""
+    return _fma32(y, layer.sc, layer.sh) > 0
 
 
 def export_shapenet(eng, routing):
@@ -83,7 +88,7 @@ def export_shapenet(eng, routing):
     G = eng.Gt2.view(P, k, 128).double()
     d = eng.dtmax.view(P, 1, 128).double()
     w = torch.where(d != 0, G / torch.where(d != 0, d, torch.ones_like(d)), torch.zeros_like(G))
-    pre2 = torch.addcmul(t2.sh, eng.yt2, t2.sc).view(P, k, 128)
+    pre2 = _fma32(eng.yt2, t2.sc, t2.sh).view(P, k, 128)
     w_fallback = _maxk_weights(pre2.double(), eng.tmax.double())
     w = torch.where((d != 0).expand_as(w), w, w_fallback)
     # a positive pooled value is attained by at least one row (and only then)
@@ -105,6 +110,6 @@ def export_s3dis(eng, routing):
     route = {}
     _export_blocks(eng, routing, route, [eng.idx[0], eng.idx[1], eng.idx[2]])
     s1, s2 = Ly["seg/conv1"], Ly["seg/conv2"]
-    route["relu/seg/conv1"] = ((eng.ys1 * s1.sc + s1.sh) > 0).view(B, N, -1).cpu()
-    route["relu/seg/conv2"] = ((eng.ys2 * s2.sc + s2.sh) > 0).view(B, N, -1).cpu()
+    route["relu/seg/conv1"] = _relu_mask(eng.ys1, s1).view(B, N, -1).cpu()
+    route["relu/seg/conv2"] = _relu_mask(eng.ys2, s2).view(B, N, -1).cpu()
     return route

@@ -102,7 +102,9 @@ def test_shapenet_cfg2_shape_unforced(cuda):
     # (two max-over-points stages -- T-net and adj_conv7 -- and 3 % changed lists in the last block: median logits shift 1.2e-2)
     assert min(frac[:3]) >= 0.99 and frac[3] >= 0.95, frac
     assert q[0] <= 4e-2 and q[2] <= 1e-1, q
-    assert max(lerr) <= 2e-3, lerr          # the Siamese / inexact terms are maxima / differences over few points
+    # the Siamese / inexact terms are maxima / differences over few points; the ShapeNet engine's T-net block accumulates with
+    # fp32 atomics, so the figure moves from run to run (12 runs: inexact term 1.1e-3 .. 2.0e-3, the others <= 1.2e-3)
+    assert max(lerr) <= 4e-3, lerr
 
 
 def test_s3dis_gradients_with_forced_routing(cuda):
