@@ -422,8 +422,7 @@ knn_tc_kernel(const unsigned char* __restrict__ img, const float* __restrict__ s
     for (int c = 0; c < 64; ++c) acc[c] = -CUDART_INF_F;
     for (int u = 0; u < ntile; ++u) {
       const int a = u & 1;
-      if (lane == 0) mbar_wait(&accf[a], (u >> 1) & 1);   // one poller per warp: 512 spinning threads slow the barrier unit
-      __syncwarp();
+      mbar_wait(&accf[a], (u >> 1) & 1);
       tc_fence_after();
       if (m_ok) {
         float v[32];
@@ -486,8 +485,7 @@ knn_tc_kernel(const unsigned char* __restrict__ img, const float* __restrict__ s
     // ---- pass 2: collect every column whose v reaches the threshold
     for (int u = ntile; u < total; ++u) {
       const int a = u & 1;
-      if (lane == 0) mbar_wait(&accf[a], (u >> 1) & 1);   // one poller per warp: 512 spinning threads slow the barrier unit
-      __syncwarp();
+      mbar_wait(&accf[a], (u >> 1) & 1);
       tc_fence_after();
       if (m_ok) {
         const int col0 = (u - ntile) * QT + h * 64;
