@@ -683,11 +683,10 @@ extern "C" int wspc_conv1x1_rows_ws(const wspc_operand_t* A, int a_mode, const f
     WSPC_LAUNCH_CHECK("rows_narrowk_relumask_kernel");
     return WSPC_OK;
   }
-  // Products over a handful of rows (the T-net's FC layers and the folded global feature: M = clouds) take the fp32 CUDA-core
-  // kernel: the time is nothing, and behind them sits a batch norm over those few rows that amplifies the 2^-16 of the
-  // bf16 x 3 split (measured on the ShapeNet T-net with 4 clouds: 6e-6 -> 1e-4 at tfc2, 7e-5 on the 3x3 transform)
-  const bool tiny_m = M < 1024 && a_mode != OP_IMG;
-  if (!env_simt && g_gemm_path == 0 && !tiny_m) {
+  // (Sending the products over a handful of rows -- the T-net's FC layers, the folded global feature: M = clouds -- to the fp32
+  // CUDA-core kernel was measured: the 3x3 transform's error against fp64 moved from 6.8e-5 to 5.9e-5 only, because the
+  // batch norm over the clouds amplifies the error of the layers in FRONT of them, and it cost 0.2-0.5 ms per step.)
+  if (!env_simt && g_gemm_path == 0) {
     const int rc = rowgemm_tc_dispatch(*A, a_mode, Bm, ldb, b_transposed, M, N, K, *epi, epi_mode, workspace, workspace_bytes, st);
     if (rc != 0) return rc < 0 ? rc : WSPC_OK;
   }
@@ -748,7 +747,7 @@ extern "C" int wspc_conv1x1_wgrad(const wspc_operand_t* A, int a_mode, const wsp
     WSPC_LAUNCH_CHECK("wgrad_narrowk1_kernel");
     goto reduce;
   }
-  if (!env_simt && g_gemm_path == 0 && M >= 1024) {      // (few rows: fp32 kernel, see wspc_conv1x1_rows_ws)
+  if (!env_simt && g_gemm_path == 0) {
     rc = wgrad_tc_dispatch(*A, a_mode, *G, g_mode, M, p.S_tc, p.K1p, p.K2p, partial, db ? partial_b : nullptr, st);
     if (rc < 0) return rc;
     if (rc == 1) { S_used = p.S_tc; goto reduce; }
