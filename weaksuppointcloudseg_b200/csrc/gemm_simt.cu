@@ -590,30 +590,42 @@ rows_narrowk_relumask_kernel(const float* __restrict__ G, long long ldg, const f
   const int rpb = blockDim.x / n4;                // rows per block sweep
   const float4 sc = *reinterpret_cast<const float4*>(E.scp + c), sh = *reinterpret_cast<const float4*>(E.shp + c);
   float f0[4] = {0.f, 0.f, 0.f, 0.f}, f1[4] = {0.f, 0.f, 0.f, 0.f};
-  for (long long row = (long long)blockIdx.x * rpb + threadIdx.x / n4; row < M; row += (long long)gridDim.x * rpb) {
-    const float* g = G + row * ldg;
-    float o[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int k = 0; k < K; ++k) {
-      const float gv = g[k];
-      const float4 w = *reinterpret_cast<const float4*>(Wt + (size_t)k * N + c);
-      o[0] = fmaf(gv, w.x, o[0]); o[1] = fmaf(gv, w.y, o[1]); o[2] = fmaf(gv, w.z, o[2]); o[3] = fmaf(gv, w.w, o[3]);
-    }
-    const float4 y4 = *reinterpret_cast<const float4*>(E.yprev + row * E.ldyp + c);
+  const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+  // ReLU mask / dropout of the producing layer, its BN-backward sums, store
+  auto finish = [&](long long row, float (&o)[4], const float4& y4, const float4& m4) {
     const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
-    const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
-    float dm[4] = {1.f, 1.f, 1.f, 1.f};
-    if (E.dmask) {
-      const float4 m4 = *reinterpret_cast<const float4*>(E.dmask + row * N + c);
-      dm[0] = m4.x * E.dscale; dm[1] = m4.y * E.dscale; dm[2] = m4.z * E.dscale; dm[3] = m4.w * E.dscale;
-    }
+    const float dm[4] = {m4.x * E.dscale, m4.y * E.dscale, m4.z * E.dscale, m4.w * E.dscale};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const bool on = fmaf(yv[j], scv[j], shv[j]) > 0.f;
-      o[j] = on ? o[j] * dm[j] : 0.f;
+      o[j] = on ? (E.dmask ? o[j] * dm[j] : o[j]) : 0.f;
       f0[j] += o[j];
       f1[j] = fmaf(o[j], yv[j], f1[j]);
     }
     *reinterpret_cast<float4*>(E.out + row * E.ldo + c) = make_float4(o[0], o[1], o[2], o[3]);
+  };
+  // two rows per trip: the epilogue operands of both are requested before the products, and every weight vector read from
+  // shared memory feeds both rows
+  const long long rstride = (long long)gridDim.x * rpb;
+  const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f);
+  for (long long row = (long long)blockIdx.x * rpb + threadIdx.x / n4; row < M; row += 2 * rstride) {
+    const long long rowb = row + rstride;
+    const bool hasb = rowb < M;
+    const float4 ya = *reinterpret_cast<const float4*>(E.yprev + row * E.ldyp + c);
+    const float4 ma = E.dmask ? *reinterpret_cast<const float4*>(E.dmask + row * N + c) : one4;
+    const float4 yb = hasb ? *reinterpret_cast<const float4*>(E.yprev + rowb * E.ldyp + c) : one4;
+    const float4 mb = (hasb && E.dmask) ? *reinterpret_cast<const float4*>(E.dmask + rowb * N + c) : one4;
+    const float* ga = G + row * ldg;
+    const float* gb = G + (hasb ? rowb : row) * ldg;
+    float oa[4] = {0.f, 0.f, 0.f, 0.f}, ob[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < K; ++k) {
+      const float va = ga[k], vb = gb[k];
+      const float4 w = *reinterpret_cast<const float4*>(Wt + (size_t)k * N + c);
+      oa[0] = fmaf(va, w.x, oa[0]); oa[1] = fmaf(va, w.y, oa[1]); oa[2] = fmaf(va, w.z, oa[2]); oa[3] = fmaf(va, w.w, oa[3]);
+      ob[0] = fmaf(vb, w.x, ob[0]); ob[1] = fmaf(vb, w.y, ob[1]); ob[2] = fmaf(vb, w.z, ob[2]); ob[3] = fmaf(vb, w.w, ob[3]);
+    }
+    finish(row, oa, ya, ma);
+    if (hasb) finish(rowb, ob, yb, mb);
   }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
